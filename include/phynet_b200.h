@@ -1,0 +1,169 @@
+/*
+ * phynet_b200.h -- C ABI of libphynet_b200.so
+ *
+ * A from-scratch sm_100a (B200) implementation of ONE hot path of PhyNetPy: the
+ * sequence log-likelihood (Felsenstein pruning under GTR-family models) that
+ * MCMC_SEQ evaluates per locus per proposal.  The reference has no FFI for this
+ * path (it is NumPy + Python recursion); each entry point below therefore cites
+ * the reference *Python* interface it replaces (paths are into the reference
+ * checkout, file:line).  INTEGRATION.md shows the ctypes binding a reference
+ * maintainer would add.
+ *
+ * Conventions
+ *   - every function returns int: 0 = PNB_OK, otherwise an error code; the text
+ *     is available from pnb_last_error() (thread-local).  Nothing aborts or
+ *     throws across the boundary.
+ *   - handles are opaque, owned by the library, freed by the matching *_destroy.
+ *   - host arrays are borrowed for the duration of the call only.
+ *   - calls on one context are serialised by the caller (the reference is
+ *     single-threaded under the GIL: src/_mcmc_seq.py:746-761).
+ *   - no torch / Python types: plain pointers and sizes.
+ *   - there is NO CPU fallback: without a CUDA device pnb_ctx_create fails.
+ *
+ * State order A,C,G,T = 0..3 (src/_seq_likelihood.py:104-105); tip codes are
+ * 4-bit masks A=1,C=2,G=4,T=8 (IUPAC table src/_seq_likelihood.py:111-117);
+ * P[i*4+j] = prob(parent state i -> child state j) (src/_seq_likelihood.py:238).
+ */
+#ifndef PHYNET_B200_H
+#define PHYNET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PNB_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define PNB_API __attribute__((visibility("default")))
+#else
+#define PNB_API
+#endif
+
+/* status codes */
+#define PNB_OK             0
+#define PNB_ERR_INVALID    1   /* bad argument (maps to ValueError)            */
+#define PNB_ERR_CUDA       2   /* CUDA runtime / launch failure               */
+#define PNB_ERR_NOMEM      3   /* host or device allocation failure           */
+#define PNB_ERR_STATE      4   /* call sequence error (e.g. pending eval)     */
+#define PNB_ERR_UNSUPPORTED 5  /* shape outside this build's limits           */
+
+/* pnb_eval flags */
+#define PNB_EVAL_FULL       0x1u  /* ignore cached partials: recompute every internal node        */
+#define PNB_EVAL_PENDING    0x2u  /* keep result pending until pnb_commit / pnb_rollback          */
+#define PNB_EVAL_NOSTORE    0x4u  /* score only: read cached partials, write none (candidates)    */
+#define PNB_EVAL_OUT_DEVICE 0x8u  /* logL_out is a DEVICE pointer; call returns without host sync */
+
+typedef struct pnb_ctx   pnb_ctx;
+typedef struct pnb_model pnb_model;
+typedef struct pnb_locus pnb_locus;
+
+/* ---- library ---------------------------------------------------------- */
+PNB_API int         pnb_abi_version(void);
+PNB_API const char *pnb_last_error(void);
+
+/* ---- context: one per process per device ------------------------------ */
+/* device < 0 selects the current CUDA device.                             */
+PNB_API int pnb_ctx_create(int device, pnb_ctx **out);
+PNB_API int pnb_ctx_destroy(pnb_ctx *ctx);
+/* Run all work of this context on an existing CUDA stream (cudaStream_t passed
+ * as void*; NULL restores the context's own stream).  Lets the caller order our
+ * kernels with its NCCL collective on the same stream.                    */
+PNB_API int pnb_ctx_set_stream(pnb_ctx *ctx, void *cuda_stream);
+PNB_API int pnb_ctx_synchronize(pnb_ctx *ctx);
+/* counters of the last pnb_eval: [0]=site-node updates, [1]=ops, [2]=tiles,
+ * [3]=kernel launches, [4]=H2D bytes, [5]=D2H bytes, [6]=jobs served from cache,
+ * [7]=internal nodes recomputed                                           */
+PNB_API int pnb_ctx_last_stats(pnb_ctx *ctx, int64_t stats[8]);
+
+/* ---- substitution model ------------------------------------------------ */
+/* Replaces SubstitutionModel._build_and_decompose's outputs being consumed by
+ * p_matrix (src/_seq_likelihood.py:202-244) and GTR._decompose/expt
+ * (src/GTR.py:518-581).  The eigen-system is computed by the HOST exactly as the
+ * reference does (np.linalg.eigh) and handed over; the device evaluates
+ * P(t) = (U * exp(evals*t)) @ Uinv for every branch.                       */
+PNB_API int pnb_model_create_eigen(pnb_ctx *ctx, const double evals[4], const double U[16],
+                           const double Uinv[16], const double pi[4], pnb_model **out);
+/* Closed form of JC69.p_matrix (src/_seq_likelihood.py:259-268).           */
+PNB_API int pnb_model_create_jc69(pnb_ctx *ctx, pnb_model **out);
+/* A model whose p_matrix is overridden on the host (user subclass): P matrices
+ * are supplied per edge to pnb_eval (P_edge argument).                     */
+PNB_API int pnb_model_create_explicit(pnb_ctx *ctx, const double pi[4], pnb_model **out);
+PNB_API int pnb_model_destroy(pnb_model *m);
+
+/* K-a: batched P(t).  Replaces SubstitutionModel.p_matrix / JC69.p_matrix
+ * (src/_seq_likelihood.py:231-244, :259-268) and GTR.expt (src/GTR.py:559-581)
+ * called once per branch.  t[nb] host -> P_out[nb*16] host, row-major 4x4,
+ * negative t clamped to 0 (src/_seq_likelihood.py:241-242).                */
+PNB_API int pnb_pmatrix_batch(pnb_ctx *ctx, const pnb_model *m, const double *t, int64_t nb,
+                      double *P_out);
+
+/* ---- K-d: site-pattern compression (integer, bit-exact) ---------------- */
+/* Replaces FelsensteinCalculator.__init__ (src/_seq_likelihood.py:344-367).
+ * cols: n x L bytes, row-major (row = taxon in dict order), already upper-cased
+ * (the reference keys on ch.upper(), :349).  Patterns are numbered in
+ * first-occurrence order; weights[k] = number of columns with pattern k.
+ * code_of_byte: 256-entry table byte -> 4-bit tip mask (IUPAC, :111-117;
+ * unknown -> 0xF, :135-137).
+ * Outputs (caller-allocated): P_out (1), codes_out n x ld_codes bytes (first
+ * *P_out entries of each row valid), weights_out[L], first_col_out[L] (first
+ * *P_out valid), pattern_of_col_out[L] (may be NULL).
+ * use_device != 0 runs the CUDA implementation (ctx required), otherwise the
+ * host implementation (ctx may be NULL).  Both give identical integers.    */
+PNB_API int pnb_compress(pnb_ctx *ctx, int use_device, const uint8_t *cols, int32_t n, int64_t L,
+                 const uint8_t code_of_byte[256], int64_t *P_out, uint8_t *codes_out,
+                 int64_t ld_codes, int64_t *weights_out, int64_t *first_col_out,
+                 int32_t *pattern_of_col_out);
+
+/* ---- locus: one alignment block resident in HBM ------------------------ */
+/* Replaces the state FelsensteinCalculator keeps after construction
+ * (_weights, _tip_partials: src/_seq_likelihood.py:358-367).  codes: n_rows x P
+ * 4-bit masks with row stride ld_codes; weights: integer multiplicities.   */
+PNB_API int pnb_locus_create(pnb_ctx *ctx, int32_t n_rows, int64_t P, const uint8_t *codes,
+                     int64_t ld_codes, const int64_t *weights, pnb_locus **out);
+PNB_API int pnb_locus_destroy(pnb_locus *loc);
+/* Forget every cached partial of this locus (next eval recomputes all).    */
+PNB_API int pnb_locus_invalidate(pnb_locus *loc);
+/* Copy a committed node partial back to the host (tests / debugging):
+ * node = index in the tree given to the last committed pnb_eval; out[P*4]. */
+PNB_API int pnb_locus_read_partial(pnb_locus *loc, int32_t node, double *out);
+
+/* ---- evaluation -------------------------------------------------------- */
+/* Replaces FelsensteinCalculator.log_likelihood + _postorder_partials
+ * (src/_seq_likelihood.py:369-426) for M (locus, gene tree) jobs at once, i.e.
+ * the loop body of _SeqLikelihoodEngine.log_likelihood (src/_mcmc_seq.py:746-750)
+ * and the candidate loops of the coupled moves (src/_mcmc_seq.py:1882, :1957).
+ *
+ * Trees are flat arrays, concatenated over jobs (CSR): job j owns nodes
+ * node_off[j] .. node_off[j+1]-1, indexed locally from 0:
+ *   parent[i]  local index of the parent, -1 for the root (exactly one);
+ *   blen[i]    length of the edge above node i; NaN = "None" -> 0
+ *              (src/_seq_likelihood.py:419-420); the root's is ignored;
+ *   tip_row[i] for a leaf (node without children): row of the locus' codes, or
+ *              -1 if the label is absent from the alignment -> all ones
+ *              (src/_seq_likelihood.py:409-412); ignored for internal nodes.
+ * Any out-degree >= 1 is accepted (src/_seq_likelihood.py:415-426).
+ * P_edge: NULL, or (explicit models) total_nodes*16 doubles, P of the edge
+ * above each node, already including site_rate.
+ * logL_out[M]: host doubles (device doubles with PNB_EVAL_OUT_DEVICE).
+ *
+ * Partials cache: every locus keeps the per-node partials of its last
+ * COMMITTED tree in HBM.  An evaluation recomputes only internal nodes whose
+ * (children, branch lengths) differ from a committed node -- for a one-branch
+ * MCMC move that is the path to the root.  Without PNB_EVAL_PENDING the new
+ * tree is committed immediately; with it the caller decides (accept -> commit,
+ * reject -> rollback), mirroring clone_caches/restore_caches
+ * (src/_mcmc_seq.py:766-772).  A locus may appear more than once in a batch
+ * only with PNB_EVAL_NOSTORE.                                              */
+PNB_API int pnb_eval(pnb_ctx *ctx, const pnb_model *m, int64_t M, pnb_locus *const *loci,
+             const int64_t *node_off, const int32_t *parent, const double *blen,
+             const int32_t *tip_row, const double *P_edge, double site_rate,
+             uint32_t flags, double *logL_out);
+PNB_API int pnb_commit(pnb_ctx *ctx, int64_t M, pnb_locus *const *loci);
+PNB_API int pnb_rollback(pnb_ctx *ctx, int64_t M, pnb_locus *const *loci);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHYNET_B200_H */

@@ -1,0 +1,1007 @@
+// pnb_api.cu -- the C ABI of libphynet_b200.so (see include/phynet_b200.h).
+//
+// Host-side runtime of the sequence-likelihood path: device arena, per-locus
+// partials cache (which (children, lengths) node lives in which HBM slot),
+// compilation of a gene tree into the flat op program the pruning kernel walks,
+// staging and launches.  The arithmetic lives in pnb_device.cuh.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdlib>
+#include <new>
+
+#define PNB_DEVICE_KERNELS
+#include "pnb_host.hpp"
+
+int pnb_compress_host(const uint8_t* cols, int32_t n, int64_t L, const uint8_t* code_of_byte,
+                      int64_t* P_out, uint8_t* codes_out, int64_t ld_codes, int64_t* weights_out,
+                      int64_t* first_col_out, int32_t* pattern_of_col_out);
+int pnb_compress_device(pnb_ctx* ctx, const uint8_t* cols, int32_t n, int64_t L,
+                        const uint8_t* code_of_byte, int64_t* P_out, uint8_t* codes_out,
+                        int64_t ld_codes, int64_t* weights_out, int64_t* first_col_out,
+                        int32_t* pattern_of_col_out);
+
+namespace pnb {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---------------------------------------------------------------- arena
+int Arena::alloc(size_t bytes, void** out) {
+    bytes = align_up(std::max<size_t>(bytes, 256), 256);
+    auto it = free_.find(bytes);
+    if (it != free_.end() && !it->second.empty()) {
+        *out = it->second.back();
+        it->second.pop_back();
+        return PNB_OK;
+    }
+    for (auto& c : chunks_) {
+        if (c.cap - c.used >= bytes) {
+            *out = c.base + c.used;
+            c.used += bytes;
+            return PNB_OK;
+        }
+    }
+    size_t chunk = std::max<size_t>(64u << 20, std::min<size_t>(reserved_ / 2, size_t(2) << 30));
+    chunk = align_up(std::max(chunk, bytes), 2u << 20);
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, chunk);
+    if (e != cudaSuccess && chunk > bytes) {  // retry with the exact size
+        (void)cudaGetLastError();
+        chunk = align_up(bytes, 2u << 20);
+        e = cudaMalloc(&p, chunk);
+    }
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        set_error("device arena: cudaMalloc(%zu bytes) failed: %s (reserved so far %zu bytes)", chunk,
+                  cudaGetErrorString(e), reserved_);
+        return PNB_ERR_NOMEM;
+    }
+    reserved_ += chunk;
+    chunks_.push_back({static_cast<char*>(p), chunk, bytes});
+    *out = p;
+    return PNB_OK;
+}
+
+void Arena::release(void* p, size_t bytes) {
+    if (!p) return;
+    bytes = align_up(std::max<size_t>(bytes, 256), 256);
+    free_[bytes].push_back(p);
+}
+
+void Arena::destroy() {
+    for (auto& c : chunks_) cudaFree(c.base);
+    chunks_.clear();
+    free_.clear();
+    reserved_ = 0;
+}
+
+static int ensure_device(Buffer& b, size_t bytes) {
+    if (b.cap >= bytes) return PNB_OK;
+    size_t cap = align_up(std::max(bytes, b.cap * 2), 4096);
+    if (b.p) PNB_CUDA_TRY(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    PNB_CUDA_TRY(cudaMalloc(&b.p, cap));
+    b.cap = cap;
+    return PNB_OK;
+}
+
+static int ensure_pinned(Buffer& b, size_t bytes) {
+    if (b.cap >= bytes) return PNB_OK;
+    size_t cap = align_up(std::max(bytes, b.cap * 2), 4096);
+    if (b.p) PNB_CUDA_TRY(cudaFreeHost(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    PNB_CUDA_TRY(cudaMallocHost(&b.p, cap));
+    b.cap = cap;
+    return PNB_OK;
+}
+
+static inline uint64_t dbits(double x) {
+    uint64_t u;
+    memcpy(&u, &x, 8);
+    return u;
+}
+
+}  // namespace pnb
+
+using namespace pnb;
+
+// =====================================================================
+// library / context
+// =====================================================================
+extern "C" int pnb_abi_version(void) { return PNB_ABI_VERSION; }
+extern "C" const char* pnb_last_error(void) { return g_err; }
+
+extern "C" int pnb_ctx_create(int device, pnb_ctx** out) {
+    PNB_REQUIRE(out != nullptr, PNB_ERR_INVALID, "pnb_ctx_create: out is NULL");
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        (void)cudaGetLastError();
+        set_error("pnb_ctx_create: no CUDA device available (%s); this library has no CPU fallback",
+                  e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return PNB_ERR_CUDA;
+    }
+    if (device < 0) PNB_CUDA_TRY(cudaGetDevice(&device));
+    PNB_REQUIRE(device < n_dev, PNB_ERR_INVALID, "pnb_ctx_create: device %d out of range (%d devices)",
+                device, n_dev);
+    PNB_CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PNB_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    PNB_REQUIRE(prop.major >= 10, PNB_ERR_UNSUPPORTED,
+                "pnb_ctx_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                device, prop.major, prop.minor);
+    pnb_ctx* ctx = new (std::nothrow) pnb_ctx();
+    PNB_REQUIRE(ctx != nullptr, PNB_ERR_NOMEM, "pnb_ctx_create: out of host memory");
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->max_smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
+    cudaError_t se = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    if (se != cudaSuccess) {
+        delete ctx;
+        set_error("pnb_ctx_create: cudaStreamCreate failed: %s", cudaGetErrorString(se));
+        return PNB_ERR_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    se = cudaFuncSetAttribute(pnb_prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              ctx->max_smem_optin - 1024);
+    if (se != cudaSuccess) {
+        cudaStreamDestroy(ctx->own_stream);
+        delete ctx;
+        set_error("pnb_ctx_create: cannot configure the pruning kernel (%s): was the library built for "
+                  "sm_100a?", cudaGetErrorString(se));
+        return PNB_ERR_CUDA;
+    }
+    *out = ctx;
+    return PNB_OK;
+}
+
+extern "C" int pnb_ctx_destroy(pnb_ctx* ctx) {
+    if (!ctx) return PNB_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->h_stage.p) cudaFreeHost(ctx->h_stage.p);
+    if (ctx->h_out.p) cudaFreeHost(ctx->h_out.p);
+    for (Buffer* b : {&ctx->d_stage, &ctx->d_P, &ctx->d_tile_sum, &ctx->d_job_done, &ctx->d_out})
+        if (b->p) cudaFree(b->p);
+    ctx->arena.destroy();
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return PNB_OK;
+}
+
+extern "C" int pnb_ctx_set_stream(pnb_ctx* ctx, void* cuda_stream) {
+    PNB_REQUIRE(ctx != nullptr, PNB_ERR_INVALID, "pnb_ctx_set_stream: ctx is NULL");
+    PNB_CUDA_TRY(cudaSetDevice(ctx->device));
+    PNB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return PNB_OK;
+}
+
+extern "C" int pnb_ctx_synchronize(pnb_ctx* ctx) {
+    PNB_REQUIRE(ctx != nullptr, PNB_ERR_INVALID, "pnb_ctx_synchronize: ctx is NULL");
+    PNB_CUDA_TRY(cudaSetDevice(ctx->device));
+    PNB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return PNB_OK;
+}
+
+extern "C" int pnb_ctx_last_stats(pnb_ctx* ctx, int64_t stats[8]) {
+    PNB_REQUIRE(ctx != nullptr && stats != nullptr, PNB_ERR_INVALID, "pnb_ctx_last_stats: NULL argument");
+    memcpy(stats, ctx->stats, sizeof(ctx->stats));
+    return PNB_OK;
+}
+
+// =====================================================================
+// models
+// =====================================================================
+static int model_new(pnb_ctx* ctx, pnb_model** out) {
+    PNB_REQUIRE(ctx != nullptr && out != nullptr, PNB_ERR_INVALID, "pnb_model_create: NULL argument");
+    pnb_model* m = new (std::nothrow) pnb_model();
+    PNB_REQUIRE(m != nullptr, PNB_ERR_NOMEM, "pnb_model_create: out of host memory");
+    memset(&m->mp, 0, sizeof(m->mp));
+    m->ctx = ctx;
+    m->id = ctx->next_model_id++;
+    *out = m;
+    return PNB_OK;
+}
+
+extern "C" int pnb_model_create_eigen(pnb_ctx* ctx, const double evals[4], const double U[16],
+                                      const double Uinv[16], const double pi[4], pnb_model** out) {
+    PNB_REQUIRE(evals && U && Uinv && pi, PNB_ERR_INVALID, "pnb_model_create_eigen: NULL array");
+    int rc = model_new(ctx, out);
+    if (rc) return rc;
+    pnb_model* m = *out;
+    memcpy(m->mp.evals, evals, 4 * sizeof(double));
+    memcpy(m->mp.U, U, 16 * sizeof(double));
+    memcpy(m->mp.Uinv, Uinv, 16 * sizeof(double));
+    memcpy(m->mp.pi, pi, 4 * sizeof(double));
+    m->mp.kind = 0;
+    return PNB_OK;
+}
+
+extern "C" int pnb_model_create_jc69(pnb_ctx* ctx, pnb_model** out) {
+    int rc = model_new(ctx, out);
+    if (rc) return rc;
+    pnb_model* m = *out;
+    for (int i = 0; i < 4; ++i) m->mp.pi[i] = 0.25;
+    m->mp.kind = 1;
+    return PNB_OK;
+}
+
+extern "C" int pnb_model_create_explicit(pnb_ctx* ctx, const double pi[4], pnb_model** out) {
+    PNB_REQUIRE(pi != nullptr, PNB_ERR_INVALID, "pnb_model_create_explicit: pi is NULL");
+    int rc = model_new(ctx, out);
+    if (rc) return rc;
+    pnb_model* m = *out;
+    memcpy(m->mp.pi, pi, 4 * sizeof(double));
+    m->mp.kind = 2;
+    return PNB_OK;
+}
+
+extern "C" int pnb_model_destroy(pnb_model* m) {
+    delete m;
+    return PNB_OK;
+}
+
+extern "C" int pnb_pmatrix_batch(pnb_ctx* ctx, const pnb_model* m, const double* t, int64_t nb,
+                                 double* P_out) {
+    PNB_REQUIRE(ctx && m, PNB_ERR_INVALID, "pnb_pmatrix_batch: NULL handle");
+    PNB_REQUIRE(m->mp.kind != 2, PNB_ERR_INVALID,
+                "pnb_pmatrix_batch: explicit models have no device P(t); compute it on the host");
+    PNB_REQUIRE(nb >= 0, PNB_ERR_INVALID, "pnb_pmatrix_batch: nb < 0");
+    if (nb == 0) return PNB_OK;
+    PNB_REQUIRE(t && P_out, PNB_ERR_INVALID, "pnb_pmatrix_batch: NULL array");
+    PNB_CUDA_TRY(cudaSetDevice(ctx->device));
+    int rc = ensure_device(ctx->d_stage, static_cast<size_t>(nb) * sizeof(double));
+    if (rc) return rc;
+    rc = ensure_device(ctx->d_P, static_cast<size_t>(nb) * 16 * sizeof(double));
+    if (rc) return rc;
+    PNB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    PNB_CUDA_TRY(cudaMemcpyAsync(ctx->d_stage.p, t, nb * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    const int64_t blocks = (nb + 127) / 128;
+    pnb_pmatrix_kernel<<<static_cast<unsigned>(blocks), 128, 0, ctx->stream>>>(
+        m->mp, static_cast<const double*>(ctx->d_stage.p), nb, static_cast<double*>(ctx->d_P.p));
+    PNB_CUDA_TRY(cudaGetLastError());
+    PNB_CUDA_TRY(cudaMemcpyAsync(P_out, ctx->d_P.p, nb * 16 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    PNB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return PNB_OK;
+}
+
+// =====================================================================
+// compression
+// =====================================================================
+extern "C" int pnb_compress(pnb_ctx* ctx, int use_device, const uint8_t* cols, int32_t n, int64_t L,
+                            const uint8_t code_of_byte[256], int64_t* P_out, uint8_t* codes_out,
+                            int64_t ld_codes, int64_t* weights_out, int64_t* first_col_out,
+                            int32_t* pattern_of_col_out) {
+    PNB_REQUIRE(n >= 1, PNB_ERR_INVALID, "pnb_compress: empty alignment (n=%d)", n);
+    PNB_REQUIRE(L >= 0 && L < (int64_t(1) << 31), PNB_ERR_INVALID, "pnb_compress: L=%lld out of range",
+                static_cast<long long>(L));
+    PNB_REQUIRE(P_out && code_of_byte, PNB_ERR_INVALID, "pnb_compress: NULL argument");
+    if (L == 0) {
+        *P_out = 0;
+        return PNB_OK;
+    }
+    PNB_REQUIRE(cols && codes_out && weights_out && first_col_out, PNB_ERR_INVALID,
+                "pnb_compress: NULL array");
+    PNB_REQUIRE(ld_codes >= 1, PNB_ERR_INVALID, "pnb_compress: ld_codes < 1");
+    if (use_device) {
+        PNB_REQUIRE(ctx != nullptr, PNB_ERR_INVALID, "pnb_compress: the device path needs a context");
+        return pnb_compress_device(ctx, cols, n, L, code_of_byte, P_out, codes_out, ld_codes,
+                                   weights_out, first_col_out, pattern_of_col_out);
+    }
+    return pnb_compress_host(cols, n, L, code_of_byte, P_out, codes_out, ld_codes, weights_out,
+                             first_col_out, pattern_of_col_out);
+}
+
+// =====================================================================
+// locus
+// =====================================================================
+static void locus_free_partials(pnb_locus* loc) {
+    if (loc->d_partials) loc->ctx->arena.release(loc->d_partials, loc->partials_bytes);
+    loc->d_partials = nullptr;
+    loc->partials_bytes = 0;
+    loc->n_slots = 0;
+    loc->free_slots.clear();
+    loc->committed.clear();
+    loc->pending.clear();
+    loc->has_pending = false;
+}
+
+static void locus_reset_cache(pnb_locus* loc) {
+    loc->committed.clear();
+    loc->pending.clear();
+    loc->has_pending = false;
+    loc->free_slots.resize(loc->n_slots);
+    for (int s = 0; s < loc->n_slots; ++s) loc->free_slots[s] = loc->n_slots - 1 - s;
+}
+
+static int locus_ensure_slots(pnb_locus* loc, int n_internal) {
+    const int want = std::max(2 * n_internal, 2);
+    if (loc->n_slots >= want) return PNB_OK;
+    locus_free_partials(loc);
+    const size_t bytes = static_cast<size_t>(want) * loc->P_pad * 4 * sizeof(double);
+    void* p = nullptr;
+    int rc = loc->ctx->arena.alloc(bytes, &p);
+    if (rc) return rc;
+    loc->d_partials = static_cast<double*>(p);
+    loc->partials_bytes = bytes;
+    loc->n_slots = want;
+    locus_reset_cache(loc);
+    return PNB_OK;
+}
+
+extern "C" int pnb_locus_create(pnb_ctx* ctx, int32_t n_rows, int64_t P, const uint8_t* codes,
+                                int64_t ld_codes, const int64_t* weights, pnb_locus** out) {
+    PNB_REQUIRE(ctx && out, PNB_ERR_INVALID, "pnb_locus_create: NULL argument");
+    *out = nullptr;
+    PNB_REQUIRE(n_rows >= 1, PNB_ERR_INVALID, "pnb_locus_create: n_rows=%d", n_rows);
+    PNB_REQUIRE(P >= 0 && P < (int64_t(1) << 30), PNB_ERR_INVALID, "pnb_locus_create: P=%lld out of range",
+                static_cast<long long>(P));
+    PNB_REQUIRE(P == 0 || (codes && weights && ld_codes >= P), PNB_ERR_INVALID,
+                "pnb_locus_create: NULL array or ld_codes < P");
+    PNB_CUDA_TRY(cudaSetDevice(ctx->device));
+    pnb_locus* loc = new (std::nothrow) pnb_locus();
+    PNB_REQUIRE(loc != nullptr, PNB_ERR_NOMEM, "pnb_locus_create: out of host memory");
+    loc->ctx = ctx;
+    loc->n_rows = n_rows;
+    loc->P = P;
+    loc->P_pad = static_cast<int64_t>(align_up(static_cast<size_t>(std::max<int64_t>(P, 1)), TPB));
+    if (P > 0) {
+        loc->codes_bytes = static_cast<size_t>(n_rows) * loc->P_pad;
+        loc->weights_bytes = static_cast<size_t>(loc->P_pad) * sizeof(double);
+        void* p = nullptr;
+        int rc = ctx->arena.alloc(loc->codes_bytes, &p);
+        if (rc) { delete loc; return rc; }
+        loc->d_codes = static_cast<uint8_t*>(p);
+        rc = ctx->arena.alloc(loc->weights_bytes, &p);
+        if (rc) { ctx->arena.release(loc->d_codes, loc->codes_bytes); delete loc; return rc; }
+        loc->d_weights = static_cast<double*>(p);
+        // host-side padded images (pad codes with 0 = "no state", weights with 0)
+        std::vector<uint8_t> hc(loc->codes_bytes, 0);
+        for (int r = 0; r < n_rows; ++r)
+            memcpy(hc.data() + static_cast<size_t>(r) * loc->P_pad, codes + static_cast<size_t>(r) * ld_codes,
+                   static_cast<size_t>(P));
+        std::vector<double> hw(loc->P_pad, 0.0);
+        for (int64_t k = 0; k < P; ++k) hw[k] = static_cast<double>(weights[k]);
+        cudaError_t e = cudaMemcpyAsync(loc->d_codes, hc.data(), loc->codes_bytes, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(loc->d_weights, hw.data(), loc->weights_bytes, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            set_error("pnb_locus_create: upload failed: %s", cudaGetErrorString(e));
+            ctx->arena.release(loc->d_codes, loc->codes_bytes);
+            ctx->arena.release(loc->d_weights, loc->weights_bytes);
+            delete loc;
+            return PNB_ERR_CUDA;
+        }
+    }
+    ctx->n_loci_alive++;
+    *out = loc;
+    return PNB_OK;
+}
+
+extern "C" int pnb_locus_destroy(pnb_locus* loc) {
+    if (!loc) return PNB_OK;
+    pnb_ctx* ctx = loc->ctx;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    locus_free_partials(loc);
+    if (loc->d_codes) ctx->arena.release(loc->d_codes, loc->codes_bytes);
+    if (loc->d_weights) ctx->arena.release(loc->d_weights, loc->weights_bytes);
+    ctx->n_loci_alive--;
+    delete loc;
+    return PNB_OK;
+}
+
+extern "C" int pnb_locus_invalidate(pnb_locus* loc) {
+    PNB_REQUIRE(loc != nullptr, PNB_ERR_INVALID, "pnb_locus_invalidate: NULL locus");
+    locus_reset_cache(loc);
+    return PNB_OK;
+}
+
+extern "C" int pnb_locus_read_partial(pnb_locus* loc, int32_t node, double* out) {
+    PNB_REQUIRE(loc && out, PNB_ERR_INVALID, "pnb_locus_read_partial: NULL argument");
+    const auto& c = loc->committed;
+    PNB_REQUIRE(c.valid, PNB_ERR_STATE, "pnb_locus_read_partial: no committed tree");
+    PNB_REQUIRE(node >= 0 && node < static_cast<int32_t>(c.node_ref.size()), PNB_ERR_INVALID,
+                "pnb_locus_read_partial: node %d out of range", node);
+    pnb_ctx* ctx = loc->ctx;
+    PNB_CUDA_TRY(cudaSetDevice(ctx->device));
+    PNB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    const int64_t ref = c.node_ref[node];
+    if (ref >= loc->n_rows) {
+        const int64_t slot = ref - loc->n_rows;
+        PNB_CUDA_TRY(cudaMemcpy(out, loc->d_partials + slot * loc->P_pad * 4,
+                                static_cast<size_t>(loc->P) * 4 * sizeof(double), cudaMemcpyDeviceToHost));
+    } else if (ref >= 0) {
+        std::vector<uint8_t> row(loc->P);
+        PNB_CUDA_TRY(cudaMemcpy(row.data(), loc->d_codes + ref * loc->P_pad, static_cast<size_t>(loc->P),
+                                cudaMemcpyDeviceToHost));
+        for (int64_t k = 0; k < loc->P; ++k)
+            for (int j = 0; j < 4; ++j) out[k * 4 + j] = (row[k] >> j) & 1 ? 1.0 : 0.0;
+    } else {
+        for (int64_t k = 0; k < loc->P * 4; ++k) out[k] = 1.0;
+    }
+    return PNB_OK;
+}
+
+// =====================================================================
+// tree -> op program
+// =====================================================================
+namespace {
+
+constexpr int64_t REF_ABSENT = -1;   // leaf whose taxon is not in the alignment
+constexpr int64_t REF_COMPUTED = -3; // NOSTORE: recomputed node that has no slot
+
+struct JobOut {
+    int n_ops = 0;
+    int n_tip_ops = 0;
+    int root_kind = K_REG;
+    int root_src = 0;
+    int stk_need = 0;
+    int n_dirty = 0;
+    bool root_clean_cached = false;
+};
+
+// Compile one (locus, tree) job.  Writes ops / effective branch lengths (and
+// explicit P matrices) at the cursor; fills loc->pending in store mode.
+int compile_job(pnb_ctx* ctx, pnb_locus* loc, const pnb_model* m, int32_t n, const int32_t* parent,
+                const double* blen, const int32_t* tip_row, const double* P_edge, double site_rate,
+                uint32_t flags, Op* ops, double* t_out, double* Pexp_out, JobOut* jo) {
+    const bool nostore = flags & PNB_EVAL_NOSTORE;
+    const bool full = flags & PNB_EVAL_FULL;
+    auto& cnt = ctx->s_child_cnt;
+    auto& off = ctx->s_child_off;
+    auto& kids = ctx->s_child;
+    auto& post = ctx->s_post;
+    auto& stk = ctx->s_stack;
+    auto& need = ctx->s_need;
+    auto& dirty = ctx->s_dirty;
+    auto& len = ctx->s_len;
+    auto& key = ctx->s_key;
+
+    cnt.assign(n, 0);
+    int root = -1;
+    for (int i = 0; i < n; ++i) {
+        const int p = parent[i];
+        if (p < 0) {
+            PNB_REQUIRE(root < 0, PNB_ERR_INVALID, "pnb_eval: tree has more than one root (nodes %d and %d)", root, i);
+            root = i;
+        } else {
+            PNB_REQUIRE(p < n && p != i, PNB_ERR_INVALID, "pnb_eval: parent[%d]=%d out of range", i, p);
+            cnt[p]++;
+        }
+    }
+    PNB_REQUIRE(root >= 0, PNB_ERR_INVALID, "pnb_eval: tree has no root");
+    off.resize(n + 1);
+    off[0] = 0;
+    for (int i = 0; i < n; ++i) off[i + 1] = off[i] + cnt[i];
+    kids.resize(n);
+    {
+        std::vector<int32_t>& fill = ctx->s_order;
+        fill.assign(off.begin(), off.end() - 1);
+        for (int i = 0; i < n; ++i)
+            if (parent[i] >= 0) kids[fill[parent[i]]++] = i;
+    }
+    // post-order (iterative)
+    post.clear();
+    post.reserve(n);
+    stk.clear();
+    stk.push_back(root);
+    stk.push_back(0);
+    while (!stk.empty()) {
+        const int idx = stk.back();
+        const int v = stk[stk.size() - 2];
+        if (idx < cnt[v]) {
+            stk.back() = idx + 1;
+            stk.push_back(kids[off[v] + idx]);
+            stk.push_back(0);
+        } else {
+            post.push_back(v);
+            stk.pop_back();
+            stk.pop_back();
+        }
+    }
+    PNB_REQUIRE(static_cast<int>(post.size()) == n, PNB_ERR_INVALID,
+                "pnb_eval: tree is not connected (reached %zu of %d nodes): cycle or forest", post.size(), n);
+
+    int n_internal = 0;
+    for (int i = 0; i < n; ++i) n_internal += cnt[i] > 0;
+
+    auto& C = loc->committed;
+    if (C.valid && C.model_id != m->id) locus_reset_cache(loc);  // partials of another model are useless
+    if (!nostore) {
+        if (full && !(flags & PNB_EVAL_PENDING)) locus_reset_cache(loc);
+        int rc = locus_ensure_slots(loc, n_internal);
+        if (rc) return rc;
+    }
+    const bool can_lookup = C.valid && !full;
+    const int64_t n_rows = loc->n_rows;
+
+    // effective branch lengths (reference :419-420 + clamp of p_matrix :241-242)
+    len.resize(n);
+    for (int i = 0; i < n; ++i) {
+        double t = blen ? blen[i] : 0.0;
+        if (std::isnan(t)) t = 0.0;
+        t *= site_rate;
+        if (!(t >= 0.0)) t = 0.0;
+        len[i] = dbits(t);
+    }
+
+    std::vector<int64_t> ref(n);  // small; per job
+    dirty.assign(n, 0);
+    need.assign(n, 0);
+    auto& P_ = loc->pending;
+    if (!nostore) {
+        P_.clear();
+        P_.kid_begin.assign(loc->n_slots, -1);
+        P_.kid_count.assign(loc->n_slots, 0);
+        P_.parent_of.assign(n_rows + loc->n_slots, -1);
+        P_.node_ref.assign(n, REF_ABSENT);
+        P_.model_id = m->id;
+    }
+    int n_dirty = 0;
+    for (int v : post) {
+        const int k = cnt[v];
+        if (k == 0) {
+            const int r = tip_row ? tip_row[v] : -1;
+            PNB_REQUIRE(r < n_rows, PNB_ERR_INVALID, "pnb_eval: tip_row[%d]=%d but the locus has %lld rows", v, r,
+                        static_cast<long long>(n_rows));
+            ref[v] = r >= 0 ? r : REF_ABSENT;
+            if (!nostore) P_.node_ref[v] = ref[v];
+            continue;
+        }
+        key.clear();
+        bool any_dirty = false;
+        for (int j = 0; j < k; ++j) {
+            const int c = kids[off[v] + j];
+            key.emplace_back(ref[c], len[c]);
+            any_dirty |= dirty[c] != 0;
+        }
+        std::sort(key.begin(), key.end());
+        int hit = -1;
+        if (can_lookup && !any_dirty) {
+            for (int j = 0; j < k && hit < 0; ++j) {
+                if (key[j].first < 0) continue;
+                const int q = C.parent_of[key[j].first];
+                if (q >= 0 && C.kid_count[q] == k) {
+                    const int b = C.kid_begin[q];
+                    bool same = true;
+                    for (int x = 0; x < k && same; ++x)
+                        same = C.kid_ref[b + x] == key[x].first && C.kid_len[b + x] == key[x].second;
+                    if (same) hit = q;
+                }
+                break;  // one probe is enough: every child has exactly one committed parent
+            }
+        }
+        int slot = hit;
+        if (hit < 0) {
+            dirty[v] = 1;
+            n_dirty++;
+            if (!nostore) {
+                PNB_REQUIRE(!loc->free_slots.empty(), PNB_ERR_STATE, "pnb_eval: internal error: out of partial slots");
+                slot = loc->free_slots.back();
+                loc->free_slots.pop_back();
+            }
+        }
+        if (nostore) {
+            ref[v] = hit >= 0 ? n_rows + hit : REF_COMPUTED;
+        } else {
+            ref[v] = n_rows + slot;
+            P_.node_ref[v] = ref[v];
+            P_.kid_begin[slot] = static_cast<int32_t>(P_.kid_ref.size());
+            P_.kid_count[slot] = k;
+            for (auto& kv : key) {
+                P_.kid_ref.push_back(kv.first);
+                P_.kid_len.push_back(kv.second);
+                if (kv.first >= 0) P_.parent_of[kv.first] = slot;
+            }
+        }
+        // stash need: dirty internal kids sorted by need (descending); the last one is forwarded in registers
+        if (dirty[v]) {
+            int kd = 0, mx = 0;
+            // selection by repeated max keeps this allocation-free; out-degree is tiny
+            // (need values are recomputed at emit time)
+            std::vector<int>& tmp = ctx->s_order;
+            tmp.clear();
+            for (int j = 0; j < k; ++j) {
+                const int c = kids[off[v] + j];
+                if (dirty[c]) tmp.push_back(need[c]);
+            }
+            std::sort(tmp.begin(), tmp.end(), std::greater<int>());
+            kd = static_cast<int>(tmp.size());
+            for (int i = 0; i < kd; ++i) mx = std::max(mx, i + tmp[i]);
+            need[v] = kd == 0 ? 0 : std::max(mx, kd - 1);
+        }
+    }
+    if (!nostore) {
+        P_.root_ref = ref[root];
+        P_.valid = true;
+    }
+
+    // ---- emit ops: DFS over dirty internal nodes ------------------------
+    int n_ops = 0, n_tip_ops = 0;
+    if (cnt[root] > 0 && dirty[root]) {
+        struct Frame { int v; int i; int sp; int push_idx; int kd; };
+        std::vector<Frame> fs;
+        std::vector<int> dk;  // per frame segment of dirty kids (sorted by need desc), stored contiguously
+        std::vector<int> dk_base;
+        auto open = [&](int v, int sp, int push_idx) {
+            const int base = static_cast<int>(dk.size());
+            for (int j = 0; j < cnt[v]; ++j) {
+                const int c = kids[off[v] + j];
+                if (dirty[c]) dk.push_back(c);
+            }
+            std::stable_sort(dk.begin() + base, dk.end(), [&](int a, int b) { return need[a] > need[b]; });
+            fs.push_back({v, 0, sp, push_idx, static_cast<int>(dk.size()) - base});
+            dk_base.push_back(base);
+        };
+        open(root, 0, -1);
+        while (!fs.empty()) {
+            Frame& f = fs.back();
+            const int base = dk_base.back();
+            if (f.i < f.kd) {
+                const int d = dk[base + f.i];
+                const int i = f.i++;
+                const int sp = f.sp;
+                const int kd = f.kd;
+                open(d, sp + i, (nostore && i < kd - 1) ? sp + i : -1);
+                continue;
+            }
+            // all dirty kids emitted: node's own ops
+            const int v = f.v;
+            const int first_op = n_ops;
+            auto add = [&](uint32_t kind, int src, int aux, int c) {
+                Op& o = ops[n_ops];
+                o.flags = kind;
+                o.src = src;
+                o.dst = 0;
+                o.aux = aux;
+                double tt;
+                memcpy(&tt, &len[c], 8);
+                t_out[n_ops] = tt;
+                if (Pexp_out) memcpy(Pexp_out + static_cast<size_t>(n_ops) * 16, P_edge + static_cast<size_t>(c) * 16, 128);
+                n_ops++;
+            };
+            if (f.kd > 0) add(K_REG, 0, 0, dk[base + f.kd - 1]);
+            for (int i = 0; i + 1 < f.kd; ++i) {
+                const int d = dk[base + i];
+                if (nostore) add(K_STK, f.sp + i, 0, d);
+                else add(K_MEM, static_cast<int>(ref[d] - n_rows), 0, d);
+            }
+            for (int j = 0; j < cnt[v]; ++j) {
+                const int c = kids[off[v] + j];
+                if (dirty[c]) continue;
+                if (cnt[c] == 0) {
+                    if (ref[c] >= 0) add(K_TIP, static_cast<int>(ref[c]), n_tip_ops++, c);
+                    else add(K_TIP, -1, 0, c);
+                } else {
+                    add(K_MEM, static_cast<int>(ref[c] - n_rows), 0, c);
+                }
+            }
+            ops[first_op].flags |= F_FIRST;
+            Op& last = ops[n_ops - 1];
+            last.flags |= F_LAST;
+            if (!nostore) {
+                last.flags |= F_STORE;
+                last.dst = static_cast<int>(ref[v] - n_rows);
+            }
+            if (f.push_idx >= 0) {
+                PNB_REQUIRE(f.push_idx < 256, PNB_ERR_UNSUPPORTED, "pnb_eval: stash depth %d exceeds 255", f.push_idx);
+                last.flags |= F_PUSH | (static_cast<uint32_t>(f.push_idx) << 8);
+            }
+            dk.resize(base);
+            dk_base.pop_back();
+            fs.pop_back();
+        }
+    }
+    jo->n_ops = n_ops;
+    jo->n_tip_ops = n_tip_ops;
+    jo->n_dirty = n_dirty;
+    jo->stk_need = (nostore && cnt[root] > 0 && dirty[root]) ? need[root] : 0;
+    if (cnt[root] == 0) {
+        jo->root_kind = K_TIP;
+        jo->root_src = static_cast<int>(ref[root]);
+    } else if (dirty[root]) {
+        jo->root_kind = K_REG;
+        jo->root_src = 0;
+    } else {
+        jo->root_kind = K_MEM;
+        jo->root_src = static_cast<int>(ref[root] - n_rows);
+    }
+    jo->root_clean_cached = cnt[root] > 0 && !dirty[root] && C.valid && C.logL_valid && C.root_ref == ref[root];
+    if (!nostore) loc->has_pending = true;  // rollback re-derives the free slots from `committed`
+    return PNB_OK;
+}
+
+void locus_commit(pnb_locus* loc) {
+    if (!loc->has_pending) return;
+    std::swap(loc->committed, loc->pending);
+    loc->pending.clear();
+    loc->has_pending = false;
+    // free every slot the committed tree does not use
+    loc->free_slots.clear();
+    for (int s = loc->n_slots - 1; s >= 0; --s)
+        if (loc->committed.kid_begin[s] < 0) loc->free_slots.push_back(s);
+}
+
+void locus_rollback(pnb_locus* loc) {
+    if (!loc->has_pending) return;
+    loc->pending.clear();
+    loc->has_pending = false;
+    loc->free_slots.clear();
+    if (loc->committed.valid) {
+        for (int s = loc->n_slots - 1; s >= 0; --s)
+            if (loc->committed.kid_begin[s] < 0) loc->free_slots.push_back(s);
+    } else {
+        for (int s = loc->n_slots - 1; s >= 0; --s) loc->free_slots.push_back(s);
+    }
+}
+
+}  // namespace
+
+// =====================================================================
+// evaluation
+// =====================================================================
+extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* const* loci,
+                        const int64_t* node_off, const int32_t* parent, const double* blen,
+                        const int32_t* tip_row, const double* P_edge, double site_rate, uint32_t flags,
+                        double* logL_out) {
+    PNB_REQUIRE(ctx && m, PNB_ERR_INVALID, "pnb_eval: NULL handle");
+    PNB_REQUIRE(m->ctx == ctx, PNB_ERR_INVALID, "pnb_eval: model belongs to another context");
+    PNB_REQUIRE(M >= 0, PNB_ERR_INVALID, "pnb_eval: M < 0");
+    memset(ctx->stats, 0, sizeof(ctx->stats));
+    if (M == 0) return PNB_OK;
+    PNB_REQUIRE(loci && node_off && parent && logL_out, PNB_ERR_INVALID, "pnb_eval: NULL array");
+    const bool nostore = flags & PNB_EVAL_NOSTORE;
+    const bool out_dev = flags & PNB_EVAL_OUT_DEVICE;
+    const bool explicit_P = m->mp.kind == 2;
+    PNB_REQUIRE(!explicit_P || P_edge, PNB_ERR_INVALID, "pnb_eval: explicit model needs P_edge");
+    PNB_REQUIRE(!(nostore && (flags & PNB_EVAL_PENDING)), PNB_ERR_INVALID,
+                "pnb_eval: NOSTORE and PENDING are mutually exclusive");
+    PNB_REQUIRE(std::isfinite(site_rate), PNB_ERR_INVALID, "pnb_eval: site_rate is not finite");
+    PNB_CUDA_TRY(cudaSetDevice(ctx->device));
+
+    // ---- pass 0: validate, size the staging regions ---------------------
+    const uint32_t mark = ++ctx->batch_counter;
+    int64_t total_nodes = 0, total_tiles = 0;
+    for (int64_t j = 0; j < M; ++j) {
+        pnb_locus* loc = loci[j];
+        PNB_REQUIRE(loc != nullptr, PNB_ERR_INVALID, "pnb_eval: loci[%lld] is NULL", static_cast<long long>(j));
+        PNB_REQUIRE(loc->ctx == ctx, PNB_ERR_INVALID, "pnb_eval: loci[%lld] belongs to another context",
+                    static_cast<long long>(j));
+        const int64_t nn = node_off[j + 1] - node_off[j];
+        PNB_REQUIRE(nn >= 1 && nn < (1 << 24), PNB_ERR_INVALID, "pnb_eval: job %lld has %lld nodes",
+                    static_cast<long long>(j), static_cast<long long>(nn));
+        if (!nostore) {
+            PNB_REQUIRE(loc->batch_mark != mark, PNB_ERR_INVALID,
+                        "pnb_eval: locus appears twice in a storing batch (job %lld); use PNB_EVAL_NOSTORE",
+                        static_cast<long long>(j));
+            PNB_REQUIRE(!loc->has_pending, PNB_ERR_STATE,
+                        "pnb_eval: locus of job %lld has a pending evaluation; commit or roll back first",
+                        static_cast<long long>(j));
+            loc->batch_mark = mark;
+        }
+        total_nodes += nn;
+        total_tiles += (loc->P + TILE_PATTERNS - 1) / TILE_PATTERNS;
+    }
+    PNB_REQUIRE(total_nodes < (int64_t(1) << 31) && total_tiles < (int64_t(1) << 31), PNB_ERR_UNSUPPORTED,
+                "pnb_eval: batch too large (%lld nodes, %lld tiles)", static_cast<long long>(total_nodes),
+                static_cast<long long>(total_tiles));
+
+    const size_t off_jobs = 0;
+    const size_t off_tiles = align_up(off_jobs + static_cast<size_t>(M) * sizeof(JobDesc), 256);
+    const size_t off_ops = align_up(off_tiles + static_cast<size_t>(total_tiles) * sizeof(int32_t), 256);
+    const size_t off_t = align_up(off_ops + static_cast<size_t>(total_nodes) * sizeof(Op), 256);
+    const size_t off_pexp = align_up(off_t + static_cast<size_t>(total_nodes) * sizeof(double), 256);
+    const size_t stage_bytes = off_pexp + (explicit_P ? static_cast<size_t>(total_nodes) * 128 : 0);
+    int rc;
+    // the previous call's H2D copy must be complete before the pinned buffer is rewritten
+    PNB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if ((rc = ensure_pinned(ctx->h_stage, stage_bytes))) return rc;
+    if ((rc = ensure_device(ctx->d_stage, stage_bytes))) return rc;
+    if ((rc = ensure_pinned(ctx->h_out, static_cast<size_t>(M) * 2 * sizeof(double)))) return rc;
+    char* hs = static_cast<char*>(ctx->h_stage.p);
+    JobDesc* h_jobs = reinterpret_cast<JobDesc*>(hs + off_jobs);
+    int32_t* h_tile_job = reinterpret_cast<int32_t*>(hs + off_tiles);
+    Op* h_ops = reinterpret_cast<Op*>(hs + off_ops);
+    double* h_t = reinterpret_cast<double*>(hs + off_t);
+    double* h_pexp = explicit_P ? reinterpret_cast<double*>(hs + off_pexp) : nullptr;
+    double* h_out = static_cast<double*>(ctx->h_out.p);
+
+    // ---- pass 1: compile -------------------------------------------------
+    int64_t n_jobs = 0, n_tiles = 0, n_ops = 0, updates = 0, n_cached = 0, n_dirty_nodes = 0;
+    int ops_cap = 1, rows_cap = 1, stk_cap = 0;
+    std::vector<int64_t> job_of_batch(M, -1);
+    for (int64_t j = 0; j < M; ++j) {
+        pnb_locus* loc = loci[j];
+        const int64_t b = node_off[j];
+        const int32_t nn = static_cast<int32_t>(node_off[j + 1] - b);
+        JobOut jo;
+        rc = compile_job(ctx, loc, m, nn, parent + b, blen ? blen + b : nullptr, tip_row ? tip_row + b : nullptr,
+                         P_edge ? P_edge + b * 16 : nullptr, site_rate, flags, h_ops + n_ops, h_t + n_ops,
+                         h_pexp ? h_pexp + n_ops * 16 : nullptr, &jo);
+        if (rc) {
+            // undo the pending state of every locus touched so far
+            if (!nostore)
+                for (int64_t q = 0; q <= j; ++q) locus_rollback(loci[q]);
+            return rc;
+        }
+        n_dirty_nodes += jo.n_dirty;
+        if (loc->P == 0) {
+            h_out[j] = 0.0;  // np.dot over zero patterns
+            if (!nostore) { loc->pending.logL = 0.0; loc->pending.logL_valid = true; }
+            continue;
+        }
+        if (jo.root_clean_cached && !out_dev) {
+            h_out[j] = loc->committed.logL;
+            if (!nostore) { loc->pending.logL = loc->committed.logL; loc->pending.logL_valid = true; }
+            n_cached++;
+            continue;
+        }
+        JobDesc& jd = h_jobs[n_jobs];
+        jd.codes = loc->d_codes;
+        jd.partials = loc->d_partials;
+        jd.weights = loc->d_weights;
+        jd.slot_stride = loc->P_pad * 4;
+        jd.P = static_cast<int32_t>(loc->P);
+        jd.ld_codes = static_cast<int32_t>(loc->P_pad);
+        jd.op_off = static_cast<int32_t>(n_ops);
+        jd.n_ops = jo.n_ops;
+        jd.n_tip_ops = jo.n_tip_ops;
+        jd.root_kind = jo.root_kind;
+        jd.root_src = jo.root_src;
+        jd.tile0 = static_cast<int32_t>(n_tiles);
+        jd.n_tiles = static_cast<int32_t>((loc->P + TILE_PATTERNS - 1) / TILE_PATTERNS);
+        jd.out_index = static_cast<int32_t>(j);
+        jd.pad0 = jd.pad1 = 0;
+        for (int t = 0; t < jd.n_tiles; ++t) h_tile_job[n_tiles + t] = static_cast<int32_t>(n_jobs);
+        job_of_batch[j] = n_jobs;
+        n_tiles += jd.n_tiles;
+        n_ops += jo.n_ops;
+        updates += static_cast<int64_t>(jo.n_dirty) * loc->P;
+        ops_cap = std::max(ops_cap, jo.n_ops);
+        rows_cap = std::max(rows_cap, jo.n_tip_ops);
+        stk_cap = std::max(stk_cap, jo.stk_need);
+        n_jobs++;
+    }
+
+    int64_t h2d = 0, d2h = 0, launches = 0;
+    if (n_jobs > 0) {
+        const size_t dyn_smem = static_cast<size_t>(ops_cap) * (sizeof(Op) + 128) +
+                                static_cast<size_t>(2) * rows_cap * TPB + static_cast<size_t>(stk_cap) * TPB * 32;
+        if (dyn_smem > static_cast<size_t>(ctx->max_smem_optin - 1024)) {
+            if (!nostore)
+                for (int64_t q = 0; q < M; ++q) locus_rollback(loci[q]);
+            set_error("pnb_eval: a tree program needs %zu bytes of shared memory (ops=%d, tip rows=%d, stash=%d); "
+                      "limit is %d", dyn_smem, ops_cap, rows_cap, stk_cap, ctx->max_smem_optin - 1024);
+            return PNB_ERR_UNSUPPORTED;
+        }
+        if ((rc = ensure_device(ctx->d_P, static_cast<size_t>(std::max<int64_t>(n_ops, 1)) * 128))) return rc;
+        if ((rc = ensure_device(ctx->d_tile_sum, static_cast<size_t>(n_tiles) * sizeof(double)))) return rc;
+        if ((rc = ensure_device(ctx->d_out, static_cast<size_t>(M) * sizeof(double)))) return rc;
+        if (ctx->d_job_done.cap < static_cast<size_t>(n_jobs) * sizeof(unsigned)) {
+            if ((rc = ensure_device(ctx->d_job_done, static_cast<size_t>(n_jobs) * sizeof(unsigned)))) return rc;
+            PNB_CUDA_TRY(cudaMemsetAsync(ctx->d_job_done.p, 0, ctx->d_job_done.cap, ctx->stream));
+        }
+        char* ds = static_cast<char*>(ctx->d_stage.p);
+        cudaStream_t st = ctx->stream;
+        if (stage_bytes <= (256u << 10)) {
+            PNB_CUDA_TRY(cudaMemcpyAsync(ds, hs, stage_bytes, cudaMemcpyHostToDevice, st));
+            h2d += stage_bytes;
+        } else {
+            PNB_CUDA_TRY(cudaMemcpyAsync(ds + off_jobs, hs + off_jobs, n_jobs * sizeof(JobDesc), cudaMemcpyHostToDevice, st));
+            PNB_CUDA_TRY(cudaMemcpyAsync(ds + off_tiles, hs + off_tiles, n_tiles * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+            h2d += n_jobs * sizeof(JobDesc) + n_tiles * sizeof(int32_t);
+            if (n_ops > 0) {
+                PNB_CUDA_TRY(cudaMemcpyAsync(ds + off_ops, hs + off_ops, n_ops * sizeof(Op), cudaMemcpyHostToDevice, st));
+                h2d += n_ops * sizeof(Op);
+                if (!explicit_P) {
+                    PNB_CUDA_TRY(cudaMemcpyAsync(ds + off_t, hs + off_t, n_ops * sizeof(double), cudaMemcpyHostToDevice, st));
+                    h2d += n_ops * sizeof(double);
+                }
+            }
+        }
+        if (n_ops > 0) {
+            if (explicit_P) {
+                PNB_CUDA_TRY(cudaMemcpyAsync(ctx->d_P.p, h_pexp, n_ops * 128, cudaMemcpyHostToDevice, st));
+                h2d += n_ops * 128;
+            } else {
+                const int64_t blocks = (n_ops + 127) / 128;
+                pnb_pmatrix_kernel<<<static_cast<unsigned>(blocks), 128, 0, st>>>(
+                    m->mp, reinterpret_cast<const double*>(ds + off_t), n_ops, static_cast<double*>(ctx->d_P.p));
+                PNB_CUDA_TRY(cudaGetLastError());
+                launches++;
+            }
+        }
+        double* d_out = out_dev ? logL_out : static_cast<double*>(ctx->d_out.p);
+        PruneLaunch L;
+        L.jobs = reinterpret_cast<const JobDesc*>(ds + off_jobs);
+        L.tile_job = reinterpret_cast<const int32_t*>(ds + off_tiles);
+        L.ops = reinterpret_cast<const Op*>(ds + off_ops);
+        L.Pm = static_cast<const double*>(ctx->d_P.p);
+        L.tile_sum = static_cast<double*>(ctx->d_tile_sum.p);
+        L.job_done = static_cast<unsigned int*>(ctx->d_job_done.p);
+        L.out = d_out;
+        L.ops_cap = ops_cap;
+        L.rows_cap = rows_cap;
+        L.stk_cap = stk_cap;
+        L.pad = 0;
+        if (out_dev && n_jobs < M) {
+            // jobs without device work (empty loci) still need their slot written
+            PNB_CUDA_TRY(cudaMemsetAsync(logL_out, 0, M * sizeof(double), st));
+        }
+        pnb_prune_kernel<<<static_cast<unsigned>(n_tiles), TPB, dyn_smem, st>>>(L, m->mp);
+        PNB_CUDA_TRY(cudaGetLastError());
+        launches++;
+        if (!out_dev) {
+            double* got = h_out + M;  // second half of the pinned result buffer
+            PNB_CUDA_TRY(cudaMemcpyAsync(got, d_out, M * sizeof(double), cudaMemcpyDeviceToHost, st));
+            d2h += M * sizeof(double);
+            cudaError_t e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) {
+                if (!nostore)
+                    for (int64_t q = 0; q < M; ++q) locus_rollback(loci[q]);
+                set_error("pnb_eval: kernel execution failed: %s", cudaGetErrorString(e));
+                return PNB_ERR_CUDA;
+            }
+            for (int64_t j = 0; j < M; ++j)
+                if (job_of_batch[j] >= 0) h_out[j] = got[j];
+        }
+    } else if (out_dev) {
+        // everything was empty: define the output
+        PNB_CUDA_TRY(cudaMemsetAsync(logL_out, 0, M * sizeof(double), ctx->stream));
+    }
+
+    if (!out_dev) {
+        for (int64_t j = 0; j < M; ++j) {
+            logL_out[j] = h_out[j];
+            if (!nostore && job_of_batch[j] >= 0) {
+                loci[j]->pending.logL = h_out[j];
+                loci[j]->pending.logL_valid = true;
+            }
+        }
+    }
+    if (!nostore && !(flags & PNB_EVAL_PENDING))
+        for (int64_t j = 0; j < M; ++j) locus_commit(loci[j]);
+
+    ctx->stats[0] = updates;
+    ctx->stats[1] = n_ops;
+    ctx->stats[2] = n_tiles;
+    ctx->stats[3] = launches;
+    ctx->stats[4] = h2d;
+    ctx->stats[5] = d2h;
+    ctx->stats[6] = n_cached;
+    ctx->stats[7] = n_dirty_nodes;
+    return PNB_OK;
+}
+
+extern "C" int pnb_commit(pnb_ctx* ctx, int64_t M, pnb_locus* const* loci) {
+    PNB_REQUIRE(ctx && (M == 0 || loci), PNB_ERR_INVALID, "pnb_commit: NULL argument");
+    for (int64_t j = 0; j < M; ++j) {
+        PNB_REQUIRE(loci[j] && loci[j]->ctx == ctx, PNB_ERR_INVALID, "pnb_commit: bad locus %lld", static_cast<long long>(j));
+        locus_commit(loci[j]);
+    }
+    return PNB_OK;
+}
+
+extern "C" int pnb_rollback(pnb_ctx* ctx, int64_t M, pnb_locus* const* loci) {
+    PNB_REQUIRE(ctx && (M == 0 || loci), PNB_ERR_INVALID, "pnb_rollback: NULL argument");
+    for (int64_t j = 0; j < M; ++j) {
+        PNB_REQUIRE(loci[j] && loci[j]->ctx == ctx, PNB_ERR_INVALID, "pnb_rollback: bad locus %lld", static_cast<long long>(j));
+        locus_rollback(loci[j]);
+    }
+    return PNB_OK;
+}
