@@ -1,0 +1,174 @@
+"""Batched / dirty-path likelihood engine: the drop-in for the Felsenstein half of
+the reference's ``_SeqLikelihoodEngine`` (``src/_mcmc_seq.py:647-772``).
+
+Same seam as the reference: ``log_likelihood(gene_trees, species_net, theta)``,
+``invalidate_locus(i)``, ``invalidate_network()``, ``clone_caches()`` /
+``restore_caches(snapshot)`` and the scalar per-locus caches ``_felsen`` /
+``_msnc`` -- so every MCMC_SEQ operator and its undo closure work unmodified.
+What changes is how the ``None`` entries of ``_felsen`` are filled: all dirty loci
+go to the GPU in ONE ``pnb_eval`` call, and inside each locus only the nodes whose
+subtree changed are recomputed (per-node partials stay resident in HBM).
+
+The MSNC coalescent density (the other factor, ``src/_msnc_density.py``) is a
+different algorithm and out of scope here; it plugs in as ``msnc_fn``.
+
+Multi-GPU (one process per GPU): loci are sharded in contiguous ranges; every rank
+evaluates its shard into an M-long device vector (zeros elsewhere) and ONE NCCL
+all-reduce gives every rank all per-locus values, summed on the host in locus
+order, so the total does not depend on the number of GPUs.
+"""
+from __future__ import annotations
+
+import math
+from typing import Any, Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._seq_likelihood import FelsensteinCalculator, _device_kind, _explicit_P_edges, _model_handle
+from .device import DeviceContext, default_context, pack_trees
+from .distributed import ShardPlan
+from .tree import FlatTree, flatten
+
+MsncFn = Callable[[int, Any, Any, float], float]
+
+
+class SeqLikelihoodEngine:
+    """Incremental ``sum_i log P(S_i | g_i) [+ log P(g_i | Psi)]`` over all loci.
+
+    Attributes:
+        n_loci: number of loci (global, across all ranks).
+    """
+
+    def __init__(self, loci: Sequence[Any], species_of: Optional[dict] = None, model: Any = None,
+                 branch_thetas: Optional[dict] = None, *, msnc_fn: Optional[MsncFn] = None,
+                 context: Optional[DeviceContext] = None, shard: Optional[ShardPlan] = None) -> None:
+        """``loci``: per-locus alignments (``dict`` label -> sequence) or ready
+        :class:`FelsensteinCalculator` objects.  With ``shard`` only this rank's loci
+        are made resident (entries outside the shard may be ``None``)."""
+        self.n_loci = len(loci)
+        self._species_of = species_of
+        self._model = model
+        self._branch_thetas = branch_thetas
+        self._msnc_fn = msnc_fn
+        self._ctx = context
+        self._shard = shard or ShardPlan.single(self.n_loci)
+        lo, hi = self._shard.local_range()
+        self._calcs: List[Optional[FelsensteinCalculator]] = [None] * self.n_loci
+        for i in range(lo, hi):
+            a = loci[i]
+            self._calcs[i] = a if isinstance(a, FelsensteinCalculator) else FelsensteinCalculator(a, context=context)
+        self._felsen: List[Optional[float]] = [None] * self.n_loci
+        self._msnc: List[Optional[float]] = [None] * self.n_loci
+        self._pending: List[int] = []   # loci with an uncommitted device evaluation
+        self._full_next = False
+        self.last_stats: dict = {}
+
+    # -- reference seam (src/_mcmc_seq.py:696-703, :766-772) ------------------
+    def invalidate_locus(self, i: int) -> None:
+        self._felsen[i] = None
+        self._msnc[i] = None
+
+    def invalidate_network(self) -> None:
+        self._msnc = [None] * self.n_loci
+
+    def clone_caches(self) -> Tuple[list, list]:
+        return list(self._felsen), list(self._msnc)
+
+    def restore_caches(self, snapshot: Tuple[list, list]) -> None:
+        """Reject path: scalar caches come back from the snapshot and the device
+        discards the partials written by the rejected proposal."""
+        self._felsen, self._msnc = list(snapshot[0]), list(snapshot[1])
+        self._rollback_pending()
+
+    def invalidate_device_cache(self) -> None:
+        """Force the next evaluation to recompute every node of every dirty locus."""
+        self._full_next = True
+
+    # -- device bookkeeping ---------------------------------------------------
+    def _context(self) -> DeviceContext:
+        if self._ctx is None:
+            self._ctx = default_context()
+        return self._ctx
+
+    def _handles(self, idx: Sequence[int]) -> np.ndarray:
+        out = np.empty(len(idx), dtype=np.uint64)
+        for k, i in enumerate(idx):
+            out[k] = self._calcs[i]._locus_handle().value
+        return out
+
+    def _commit_pending(self) -> None:
+        if self._pending:
+            self._context().commit(self._handles(self._pending))
+            self._pending = []
+
+    def _rollback_pending(self) -> None:
+        if self._pending:
+            self._context().rollback(self._handles(self._pending))
+            self._pending = []
+
+    # -- evaluation -----------------------------------------------------------
+    def felsenstein_batch(self, idx: Sequence[int], gene_trees: Sequence[Any], *, flags: int = 0,
+                          site_rate: float = 1.0) -> np.ndarray:
+        """log P(S_i | g_i) for the given local loci in one device call."""
+        ctx = self._context()
+        flats = [flatten(gene_trees[i]) for i in idx]
+        node_off, parent, blen, tip_row = pack_trees(flats, [self._calcs[i]._row_of for i in idx])
+        P_edge = None
+        if _device_kind(self._model) == "explicit":
+            P_edge = _explicit_P_edges(self._model, blen, site_rate)
+        out = ctx.eval(_model_handle(self._model, ctx), self._handles(idx), node_off, parent, blen, tip_row,
+                       site_rate, flags, P_edge)
+        self.last_stats = ctx.last_stats()
+        return out
+
+    def log_likelihood(self, gene_trees: Sequence[Any], species_net: Any = None, theta: float = 0.0) -> float:
+        """Total log-likelihood; ``-inf`` when not finite (reference :723-764)."""
+        # whatever was pending belongs to an accepted proposal: it becomes the committed state
+        self._commit_pending()
+        lo, hi = self._shard.local_range()
+        dirty = [i for i in range(lo, hi) if self._felsen[i] is None]
+        flags = _lib.EVAL_PENDING | (_lib.EVAL_FULL if self._full_next else 0)
+        self._full_next = False
+        if self._shard.world_size == 1:
+            if dirty:
+                vals = self.felsenstein_batch(dirty, gene_trees, flags=flags)
+                for i, v in zip(dirty, vals):
+                    self._felsen[i] = float(v)
+                self._pending = list(dirty)
+        else:
+            # every rank fills its dirty local loci, then one all-reduce of the M-vector
+            vec = np.zeros(self.n_loci, dtype=np.float64)
+            for i in range(self.n_loci):
+                if self._felsen[i] is not None and lo <= i < hi:
+                    vec[i] = self._felsen[i]
+            if dirty:
+                vals = self.felsenstein_batch(dirty, gene_trees, flags=flags)
+                vec[dirty] = vals
+                self._pending = list(dirty)
+            vec = self._shard.allreduce_sum(vec)
+            self._felsen = [float(v) for v in vec]
+        total = 0.0
+        for i in range(self.n_loci):
+            if self._msnc_fn is not None and self._msnc[i] is None:
+                self._msnc[i] = float(self._msnc_fn(i, gene_trees[i], species_net, theta))
+            total += self._felsen[i] + (self._msnc[i] if self._msnc_fn is not None else 0.0)
+        if not math.isfinite(total):
+            return float("-inf")
+        return total
+
+    def score_candidates(self, locus: int, trees: Sequence[Any], *, site_rate: float = 1.0) -> np.ndarray:
+        """Felsenstein logL of many candidate trees for ONE locus in one launch (the
+        loops of the coupled moves, reference ``src/_mcmc_seq.py:1864-1992``): cached
+        partials of the committed tree are reused, nothing is written back."""
+        self._commit_pending()
+        idx = [locus] * len(trees)
+        ctx = self._context()
+        flats = [flatten(t) for t in trees]
+        row = self._calcs[locus]._row_of
+        node_off, parent, blen, tip_row = pack_trees(flats, [row] * len(trees))
+        P_edge = _explicit_P_edges(self._model, blen, site_rate) if _device_kind(self._model) == "explicit" else None
+        out = ctx.eval(_model_handle(self._model, ctx), self._handles(idx), node_off, parent, blen, tip_row,
+                       site_rate, _lib.EVAL_NOSTORE, P_edge)
+        self.last_stats = ctx.last_stats()
+        return out

@@ -1,0 +1,122 @@
+"""Device context and batch evaluation helpers above the C ABI.
+
+One :class:`DeviceContext` per process per GPU.  ``run_parallel_chains`` in the
+reference pickles the sampler into spawned workers (reference
+``src/_mcmc_seq.py:4144-4175``); device handles are therefore never pickled and
+are re-created lazily in whichever process touches them (contexts are keyed by
+PID).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from .tree import FlatTree
+
+_contexts: Dict[Tuple[int, int], "DeviceContext"] = {}
+
+STAT_NAMES = ("updates", "ops", "tiles", "launches", "h2d_bytes", "d2h_bytes", "jobs_cached", "nodes_recomputed")
+
+
+def default_device() -> int:
+    for var in ("PHYNET_B200_DEVICE", "LOCAL_RANK"):
+        v = os.environ.get(var)
+        if v not in (None, ""):
+            return int(v)
+    return 0
+
+
+class DeviceContext:
+    """Owns a ``pnb_ctx`` (stream, staging buffers, device arena) on one GPU."""
+
+    def __init__(self, device: Optional[int] = None):
+        lib = _lib.load()
+        self.device = default_device() if device is None else int(device)
+        h = C.c_void_p()
+        _lib.check(lib.pnb_ctx_create(self.device, C.byref(h)))
+        self._h = h
+        self._pid = os.getpid()
+        self._lib = lib
+
+    @property
+    def handle(self) -> C.c_void_p:
+        if self._h is None:
+            raise RuntimeError("DeviceContext was destroyed")
+        return self._h
+
+    def set_stream(self, cuda_stream: Optional[int]) -> None:
+        """Run this context's kernels on an existing CUDA stream (e.g. torch's current stream)."""
+        _lib.check(self._lib.pnb_ctx_set_stream(self.handle, C.c_void_p(cuda_stream or 0)))
+
+    def synchronize(self) -> None:
+        _lib.check(self._lib.pnb_ctx_synchronize(self.handle))
+
+    def last_stats(self) -> Dict[str, int]:
+        arr = (C.c_int64 * 8)()
+        _lib.check(self._lib.pnb_ctx_last_stats(self.handle, arr))
+        return dict(zip(STAT_NAMES, (int(x) for x in arr)))
+
+    def destroy(self) -> None:
+        if self._h is not None and self._pid == os.getpid():
+            self._lib.pnb_ctx_destroy(self._h)
+        self._h = None
+
+    # -- K-a ------------------------------------------------------------------
+    def pmatrix_batch(self, model_handle: C.c_void_p, t: np.ndarray) -> np.ndarray:
+        t = np.ascontiguousarray(t, dtype=np.float64).ravel()
+        out = np.empty((t.shape[0], 4, 4), dtype=np.float64)
+        _lib.check(self._lib.pnb_pmatrix_batch(self.handle, model_handle, _lib.ptr(t), t.shape[0], _lib.ptr(out)))
+        return out
+
+    # -- K-b / K-c ---------------------------------------------------------------
+    def eval(self, model_handle: C.c_void_p, loci: np.ndarray, node_off: np.ndarray, parent: np.ndarray,
+             blen: np.ndarray, tip_row: np.ndarray, site_rate: float = 1.0, flags: int = 0,
+             P_edge: Optional[np.ndarray] = None, out_device_ptr: Optional[int] = None) -> Optional[np.ndarray]:
+        """One ``pnb_eval`` over M (locus, tree) jobs given as CSR-packed arrays."""
+        M = int(loci.shape[0])
+        assert loci.dtype == np.uint64 and node_off.dtype == np.int64 and parent.dtype == np.int32
+        assert blen.dtype == np.float64 and tip_row.dtype == np.int32
+        if out_device_ptr is not None:
+            flags |= _lib.EVAL_OUT_DEVICE
+            out = None
+            out_ptr = C.c_void_p(out_device_ptr)
+        else:
+            out = np.empty(M, dtype=np.float64)
+            out_ptr = _lib.ptr(out)
+        _lib.check(self._lib.pnb_eval(self.handle, model_handle, M, _lib.ptr(loci), _lib.ptr(node_off),
+                                      _lib.ptr(parent), _lib.ptr(blen), _lib.ptr(tip_row),
+                                      _lib.ptr(P_edge) if P_edge is not None else None,
+                                      float(site_rate), flags, out_ptr))
+        return out
+
+    def commit(self, loci: np.ndarray) -> None:
+        _lib.check(self._lib.pnb_commit(self.handle, int(loci.shape[0]), _lib.ptr(loci)))
+
+    def rollback(self, loci: np.ndarray) -> None:
+        _lib.check(self._lib.pnb_rollback(self.handle, int(loci.shape[0]), _lib.ptr(loci)))
+
+
+def default_context(device: Optional[int] = None) -> DeviceContext:
+    dev = default_device() if device is None else int(device)
+    key = (os.getpid(), dev)
+    ctx = _contexts.get(key)
+    if ctx is None or ctx._h is None:
+        ctx = DeviceContext(dev)
+        _contexts[key] = ctx
+    return ctx
+
+
+def pack_trees(trees: Sequence[FlatTree], row_maps: Sequence[dict]) -> Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
+    """Concatenate flat trees into the CSR arrays ``pnb_eval`` takes."""
+    sizes = np.fromiter((t.n_nodes for t in trees), dtype=np.int64, count=len(trees))
+    node_off = np.zeros(len(trees) + 1, dtype=np.int64)
+    np.cumsum(sizes, out=node_off[1:])
+    parent = np.concatenate([t.parent for t in trees]) if trees else np.zeros(0, np.int32)
+    blen = np.concatenate([t.blen for t in trees]) if trees else np.zeros(0, np.float64)
+    tip_row = np.concatenate([t.tip_rows(m) for t, m in zip(trees, row_maps)]) if trees else np.zeros(0, np.int32)
+    return node_off, np.ascontiguousarray(parent, np.int32), np.ascontiguousarray(blen, np.float64), \
+        np.ascontiguousarray(tip_row, np.int32)

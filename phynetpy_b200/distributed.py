@@ -1,0 +1,97 @@
+"""Loci sharding across GPUs: one process per GPU, ``torch.distributed`` plumbing.
+
+The reference has no multi-device path (its only parallelism is independent
+chains in spawned processes, ``src/_mcmc_seq.py:4076-4274``).  Loci are
+independent terms of a plain sum (``src/_mcmc_seq.py:746-761``), so they shard
+without any data-path exchange; the single collective per evaluation is an
+all-reduce (sum) of the M-long per-locus log-likelihood vector in which every
+rank has filled only its own range (zeros elsewhere).  Adding zeros is exact, so
+the reduced vector is bit-identical for any number of ranks, and the host sums it
+in locus order.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+
+def balanced_ranges(work: Sequence[float], world_size: int) -> List[Tuple[int, int]]:
+    """Contiguous locus ranges with near-equal total work (work_i ~ patterns_i * internal nodes_i)."""
+    w = np.asarray(work, dtype=np.float64)
+    M = w.shape[0]
+    if world_size <= 1:
+        return [(0, M)]
+    cum = np.concatenate([[0.0], np.cumsum(w)])
+    total = cum[-1]
+    cuts = [0]
+    for r in range(1, world_size):
+        target = total * r / world_size
+        k = int(np.searchsorted(cum, target, side="left"))
+        # choose the boundary nearest to the target, keeping ranges monotone
+        if k > 0 and abs(cum[k - 1] - target) <= abs(cum[min(k, M)] - target):
+            k -= 1
+        cuts.append(min(max(k, cuts[-1]), M))
+    cuts.append(M)
+    return [(cuts[r], cuts[r + 1]) for r in range(world_size)]
+
+
+@dataclass
+class ShardPlan:
+    """Which loci this rank owns, and how the per-locus vector is combined."""
+
+    n_loci: int
+    rank: int
+    world_size: int
+    ranges: List[Tuple[int, int]]
+    group: Optional[object] = None  # torch.distributed process group (None = default)
+
+    @classmethod
+    def single(cls, n_loci: int) -> "ShardPlan":
+        return cls(n_loci, 0, 1, [(0, n_loci)])
+
+    @classmethod
+    def from_env(cls, n_loci: int, work: Optional[Sequence[float]] = None, group=None) -> "ShardPlan":
+        """Rank / world size from an initialised ``torch.distributed`` (else single)."""
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                rank, world = dist.get_rank(group), dist.get_world_size(group)
+            else:
+                rank, world = 0, 1
+        except ImportError:
+            rank, world = 0, 1
+        w = np.ones(n_loci) if work is None else work
+        return cls(n_loci, rank, world, balanced_ranges(w, world), group)
+
+    def local_range(self) -> Tuple[int, int]:
+        return self.ranges[self.rank]
+
+    def owner_of(self, locus: int) -> int:
+        for r, (lo, hi) in enumerate(self.ranges):
+            if lo <= locus < hi:
+                return r
+        raise IndexError(locus)
+
+    def allreduce_sum(self, vec: np.ndarray) -> np.ndarray:
+        """Sum an M-long host vector over ranks (gloo on CPU tensors, NCCL via a staging
+        CUDA tensor).  Exact when every entry is non-zero on at most one rank."""
+        if self.world_size == 1:
+            return vec
+        import torch
+        import torch.distributed as dist
+        backend = dist.get_backend(self.group)
+        t = torch.from_numpy(np.ascontiguousarray(vec, dtype=np.float64))
+        if backend == "nccl":
+            t = t.cuda()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t.cpu().numpy()
+
+    def allreduce_sum_device_(self, tensor) -> None:
+        """In-place all-reduce of a CUDA tensor the pruning kernel has just written
+        (same stream as the kernel: no host round trip between the two)."""
+        if self.world_size == 1:
+            return
+        import torch.distributed as dist
+        dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=self.group)

@@ -1,0 +1,380 @@
+"""GPU parity tests: the CUDA path, through the C ABI, against (a) the golden vectors
+frozen from the reference and (b) the CPU oracle on seeded inputs.
+
+Bars: integers (pattern count, order, weights, tip codes) bit-exact; log-likelihood
+within 1e-10 relative (north_star) -- in practice ~1e-14; P(t) within 1e-13 abs.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import felsenstein_oracle as O
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+CASES = load_golden("felsen_cases.json")["cases"]
+PM = load_golden("pmatrix_cases.json")["cases"]
+REL = 1e-10
+
+
+def _pkg():
+    from phynetpy_b200 import infer as P
+    return P
+
+
+def _model(P, spec):
+    if spec["kind"] == "JC69":
+        return P.JC69()
+    if spec["kind"] == "HKY85":
+        return P.HKY85(spec["kappa"], spec["pi"])
+    return P.GTR(spec["pi"], spec["rates"])
+
+
+def _omodel(spec):
+    if spec["kind"] == "JC69":
+        return O.jc69()
+    if spec["kind"] == "HKY85":
+        return O.hky85(spec["kappa"], spec["pi"])
+    return O.gtr(spec["pi"], spec["rates"])
+
+
+def _tree(P, t):
+    return P.GeneTree(t["parent"], t["blen"], t["label"])
+
+
+def _otree(ft):
+    return O.OracleTree(ft.parent.tolist(), [None if math.isnan(b) else float(b) for b in ft.blen], ft.label)
+
+
+def rel_err(a, b):
+    return abs(a - b) / max(1.0, abs(b))
+
+
+# ----------------------------------------------------------------- golden vectors
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_golden_logL_and_patterns(case):
+    P = _pkg()
+    fc = P.FelsensteinCalculator(dict(case["alignment"]))
+    assert fc.n_patterns == case["n_patterns"]
+    assert fc._int_weights.tolist() == case["weights"]
+    got = fc.log_likelihood(_tree(P, case["tree"]), _model(P, case["model"]), site_rate=case["site_rate"])
+    assert rel_err(got, case["logL"]) <= REL, (got, case["logL"])
+    # a second call is served from the device cache and must return the same bits
+    again = fc.log_likelihood(_tree(P, case["tree"]), _model(P, case["model"]), site_rate=case["site_rate"])
+    assert again == got
+    full = fc.log_likelihood(_tree(P, case["tree"]), _model(P, case["model"]), site_rate=case["site_rate"], full=True)
+    assert full == got
+
+
+@pytest.mark.parametrize("case", CASES[:30], ids=[c["name"] for c in CASES[:30]])
+def test_device_compress_bit_exact(case):
+    P = _pkg()
+    from phynetpy_b200 import _seq_likelihood as SL
+    seqs = [s for _, s in case["alignment"]]
+    mat, lut = SL._alignment_matrix(seqs)
+    cd, wd, fd, pd_ = SL.compress_alignment(mat, lut, use_device=True)
+    ch, wh, fh, ph = SL.compress_alignment(mat, lut, use_device=False)
+    assert wd.tolist() == case["weights"]
+    assert np.array_equal(cd, ch) and np.array_equal(wd, wh) and np.array_equal(fd, fh) and np.array_equal(pd_, ph)
+
+
+@pytest.mark.parametrize("case", PM, ids=["%s_%d" % (c.get("cls", c.get("model", {}).get("kind")), i) for i, c in enumerate(PM)])
+def test_pmatrix_golden(case):
+    P = _pkg()
+    if case["family"] == "_seq_likelihood":
+        m = _model(P, case["model"])
+        got = m.p_matrix_batch(case["times"])
+        single = np.stack([m.p_matrix(t) for t in case["times"][:3]])
+        assert np.array_equal(single, got[:3])
+    else:
+        from phynetpy_b200 import GTR as G
+        m = getattr(G, case["cls"])(*case["args"])
+        np.testing.assert_allclose(np.asarray(m.getQ()).ravel(), case["Q"], atol=1e-15)
+        got = m.expt_batch(case["times"])
+        np.testing.assert_allclose(m.expt(case["times"][5]), got[5], atol=0)
+    exp = np.asarray(case["P"]).reshape(-1, 4, 4)
+    # reference tests pin expt/p_matrix to expm at 1e-11 (tests/test_gtr.py:221-232, :498-533)
+    np.testing.assert_allclose(got, exp, rtol=0, atol=1e-13)
+
+
+def test_pmatrix_properties():
+    """Properties the reference tests (tests/test_gtr.py:234-285): stochastic rows, P(0)=I,
+    P(500)->pi, Chapman-Kolmogorov, negative-t clamp, detailed balance."""
+    P = _pkg()
+    m = P.GTR([0.1, 0.2, 0.3, 0.4], [1.0, 2.5, 0.7, 1.3, 3.1, 0.9])
+    ts = np.array([0.0, 1e-4, 0.01, 0.1, 0.3, 0.4, 0.7, 1.0, 50.0, 500.0, -1.0])
+    Pm = m.p_matrix_batch(ts)
+    np.testing.assert_allclose(Pm.sum(axis=2), 1.0, atol=1e-13)
+    np.testing.assert_allclose(Pm[0], np.eye(4), atol=1e-14)
+    np.testing.assert_allclose(Pm[-1], np.eye(4), atol=1e-14)
+    np.testing.assert_allclose(Pm[9], np.tile(m.pi, (4, 1)), atol=1e-8)
+    np.testing.assert_allclose(Pm[4] @ Pm[5], Pm[6], atol=1e-13)
+    flux = m.pi[:, None] * Pm[3]
+    np.testing.assert_allclose(flux, flux.T, atol=1e-14)
+    assert (Pm >= -1e-15).all()
+
+
+# ------------------------------------------------------------- oracle on seeded inputs
+@pytest.mark.parametrize("n,L,seed", [(5, 1000, 1), (16, 500, 4), (24, 1000, 3), (32, 2000, 5), (50, 3000, 2)])
+def test_baseline_shapes_vs_oracle(n, L, seed):
+    """BASELINE.json shapes at sizes the oracle finishes in seconds (cfg1 exactly; cfg2-5 one locus)."""
+    P = _pkg()
+    from phynetpy_b200 import simulate as S
+    rng = np.random.default_rng(seed)
+    par, bl = S.random_trees(1, n, rng)
+    aln = S.simulate_alignments(par, bl, L, S.DEFAULT_PI, S.DEFAULT_RATES, rng)[0]
+    ft = S.flat_trees(par, bl)[0]
+    fc = P.FelsensteinCalculator(S.to_alignment_dict(aln))
+    locus = O.OracleLocus(S.to_alignment_dict(aln))
+    assert fc.n_patterns == locus.n_patterns and fc._int_weights.tolist() == locus.int_weights.tolist()
+    assert np.array_equal(fc._codes, locus.codes())
+    got = fc.log_likelihood(ft, P.GTR(S.DEFAULT_PI, S.DEFAULT_RATES))
+    sink = {}
+    exp = O.log_likelihood(locus, _otree(ft), O.gtr(S.DEFAULT_PI, S.DEFAULT_RATES), sink=sink)
+    assert rel_err(got, exp) <= REL
+    # every internal node's partial, as stored in HBM, against the oracle's
+    nc = ft.n_children()
+    for node in np.nonzero(nc > 0)[0][:8]:
+        np.testing.assert_allclose(fc.node_partial(int(node)), sink[int(node)], rtol=1e-12, atol=0)
+
+
+def test_dirty_path_equals_full_recompute():
+    """K-c: after a one-branch change only the path to the root is recomputed, and the
+    result is bit-identical to a full recomputation and within 1e-10 of the oracle."""
+    P = _pkg()
+    from phynetpy_b200 import simulate as S
+    rng = np.random.default_rng(44)
+    n, L = 16, 500
+    par, bl = S.random_trees(1, n, rng)
+    aln = S.simulate_alignments(par, bl, L, S.DEFAULT_PI, S.DEFAULT_RATES, rng)[0]
+    ft = S.flat_trees(par, bl)[0]
+    model = P.GTR(S.DEFAULT_PI, S.DEFAULT_RATES)
+    fc = P.FelsensteinCalculator(S.to_alignment_dict(aln))
+    ctx = fc._context()
+    base = fc.log_likelihood(ft, model)
+    assert ctx.last_stats()["nodes_recomputed"] == n - 1
+    locus = O.OracleLocus(S.to_alignment_dict(aln))
+    om = O.gtr(S.DEFAULT_PI, S.DEFAULT_RATES)
+    for step in range(12):
+        node = int(rng.integers(0, 2 * n - 2))
+        bl2 = ft.blen.copy()
+        bl2[node] *= float(rng.uniform(0.5, 2.0))
+        ft2 = ft.with_lengths(bl2)
+        got = fc.log_likelihood(ft2, model)
+        st = ctx.last_stats()
+        depth = 0
+        p = ft.parent[node]
+        while p >= 0:
+            depth += 1
+            p = ft.parent[p]
+        assert st["nodes_recomputed"] == depth, (st, depth)
+        assert st["updates"] == depth * fc.n_patterns
+        exp = O.log_likelihood(locus, _otree(ft2), om)
+        assert rel_err(got, exp) <= REL
+        fc2 = P.FelsensteinCalculator(S.to_alignment_dict(aln))
+        assert fc2.log_likelihood(ft2, model) == got  # bit-identical to a cold full evaluation
+        fc2.close()
+        ft = ft2
+    assert base != got
+
+
+def test_nni_topology_change_dirty_path():
+    P = _pkg()
+    from phynetpy_b200 import simulate as S
+    rng = np.random.default_rng(9)
+    n = 12
+    par, bl = S.random_trees(1, n, rng)
+    aln = S.simulate_alignments(par, bl, 400, S.DEFAULT_PI, S.DEFAULT_RATES, rng)[0]
+    ft = S.flat_trees(par, bl)[0]
+    model = P.HKY85(3.0, [0.2, 0.3, 0.3, 0.2])
+    om = O.hky85(3.0, [0.2, 0.3, 0.3, 0.2])
+    fc = P.FelsensteinCalculator(S.to_alignment_dict(aln))
+    locus = O.OracleLocus(S.to_alignment_dict(aln))
+    fc.log_likelihood(ft, model)
+    parent = ft.parent.copy()
+    # NNI around an internal edge (v -> u): swap a child of v with v's sibling
+    internal = [i for i in range(n, 2 * n - 2)]
+    v = internal[0]
+    u = int(parent[v])
+    child = int(np.nonzero(parent == v)[0][0])
+    sib = [int(c) for c in np.nonzero(parent == u)[0] if c != v][0]
+    parent[child], parent[sib] = u, v
+    ft2 = P.FlatTree(parent, ft.blen, ft.label)
+    got = fc.log_likelihood(ft2, model)
+    assert fc._context().last_stats()["nodes_recomputed"] < n - 1
+    exp = O.log_likelihood(locus, _otree(ft2), om)
+    assert rel_err(got, exp) <= REL
+
+
+def test_engine_golden_and_cache_semantics(engine_case):
+    P = _pkg()
+    ec = engine_case
+    model = _model(P, ec["model"])
+    loci = [dict(l["alignment"]) for l in ec["loci"]]
+    trees = [_tree(P, l["tree"]) for l in ec["loci"]]
+    eng = P.SeqLikelihoodEngine(loci, None, model)
+    total = eng.log_likelihood(trees, None, 0.0)
+    assert rel_err(total, ec["total"]) <= REL
+    for got, exp in zip(eng._felsen, ec["per_locus"]):
+        assert rel_err(got, exp) <= REL
+    # reject path: snapshot, perturb one locus, evaluate, restore -> old total, device rolled back
+    snap = eng.clone_caches()
+    i = 3
+    ft = trees[i].flat()
+    bl = ft.blen.copy()
+    leaf = int(np.nonzero(ft.n_children() == 0)[0][0])
+    bl[leaf] *= 3.0
+    new_trees = list(trees)
+    new_trees[i] = ft.with_lengths(bl)
+    eng.invalidate_locus(i)
+    t2 = eng.log_likelihood(new_trees, None, 0.0)
+    assert t2 != total and eng.last_stats["jobs_cached"] == 0
+    assert eng.last_stats["nodes_recomputed"] < (ft.n_nodes - 1)
+    eng.restore_caches(snap)
+    assert eng.log_likelihood(trees, None, 0.0) == total
+    # accept path: evaluate again, keep; then the same tree is a pure cache hit
+    eng.invalidate_locus(i)
+    t3 = eng.log_likelihood(new_trees, None, 0.0)
+    assert t3 == t2
+    eng.invalidate_locus(i)
+    t4 = eng.log_likelihood(new_trees, None, 0.0)
+    assert t4 == t2 and eng.last_stats["jobs_cached"] == 1
+    # candidates: many trees for one locus, nothing stored
+    cands = [new_trees[i], trees[i], new_trees[i]]
+    vals = eng.score_candidates(i, cands)
+    assert vals[0] == vals[2]
+    assert rel_err(vals[1], ec["per_locus"][i]) <= REL
+
+
+def test_candidates_nostore_deep_tree_uses_stash():
+    """NOSTORE evaluation of a balanced tree needs the shared-memory stash; result == stored path."""
+    P = _pkg()
+    from phynetpy_b200 import simulate as S
+    rng = np.random.default_rng(21)
+    n = 32
+    # perfectly balanced topology: pair up nodes level by level
+    parent = np.full(2 * n - 1, -1, dtype=np.int32)
+    level = list(range(n))
+    nxt = n
+    while len(level) > 1:
+        new = []
+        for a, b in zip(level[::2], level[1::2]):
+            parent[a] = parent[b] = nxt
+            new.append(nxt)
+            nxt += 1
+        level = new
+    blen = rng.exponential(0.05, size=2 * n - 1)
+    blen[-1] = np.nan
+    par2, bl2 = parent[None, :], blen[None, :]
+    aln = S.simulate_alignments(par2, bl2, 700, S.DEFAULT_PI, S.DEFAULT_RATES, rng)[0]
+    ft = P.FlatTree(parent, blen, S.tip_labels(n) + [None] * (n - 1))
+    model = P.GTR(S.DEFAULT_PI, S.DEFAULT_RATES)
+    eng = P.SeqLikelihoodEngine([S.to_alignment_dict(aln)], None, model)
+    stored = eng.log_likelihood([ft], None, 0.0)
+    exp = O.log_likelihood(O.OracleLocus(S.to_alignment_dict(aln)), _otree(ft), O.gtr(S.DEFAULT_PI, S.DEFAULT_RATES))
+    assert rel_err(stored, exp) <= REL
+    scaled = ft.with_lengths(ft.blen * 1.7)   # every node dirty -> full NOSTORE walk with stash
+    vals = eng.score_candidates(0, [scaled, ft])
+    fc = P.FelsensteinCalculator(S.to_alignment_dict(aln))
+    assert vals[0] == fc.log_likelihood(scaled, model)
+    assert vals[1] == stored
+
+
+def test_explicit_model_subclass_overriding_p_matrix():
+    P = _pkg()
+    base = O.gtr([0.1, 0.2, 0.3, 0.4], [1.0, 2.5, 0.7, 1.3, 3.1, 0.9])
+
+    class HostModel(P.SubstitutionModel):
+        def p_matrix(self, t):  # user code on the host, as the reference allows
+            return base.p_matrix(t)
+
+    case = CASES[3]
+    fc = P.FelsensteinCalculator(dict(case["alignment"]))
+    got = fc.log_likelihood(_tree(P, case["tree"]), HostModel([0.1, 0.2, 0.3, 0.4], [1.0, 2.5, 0.7, 1.3, 3.1, 0.9]))
+    assert rel_err(got, case["logL"]) <= REL
+
+
+def test_model_change_invalidates_cached_partials():
+    P = _pkg()
+    case = CASES[0]
+    fc = P.FelsensteinCalculator(dict(case["alignment"]))
+    t = _tree(P, case["tree"])
+    a = fc.log_likelihood(t, P.JC69())
+    b = fc.log_likelihood(t, P.HKY85(2.5, [0.3, 0.2, 0.2, 0.3]))
+    assert rel_err(a, CASES[0]["logL"]) <= REL and rel_err(b, CASES[1]["logL"]) <= REL
+
+
+def test_edge_cases_empty_and_single_node():
+    P = _pkg()
+    fc = P.FelsensteinCalculator({"A": "", "B": ""})
+    assert fc.n_patterns == 0
+    assert fc.log_likelihood(P.GeneTree.from_newick("(A:0.1,B:0.1);"), P.JC69()) == 0.0
+    # a tree that is a single leaf: likelihood is pi[state] per site (reference :408-413 + :394-397)
+    fc1 = P.FelsensteinCalculator({"A": "ACGTTN"})
+    m = P.GTR([0.1, 0.2, 0.3, 0.4], [1] * 6)
+    single = P.GeneTree([-1], [None], ["A"])
+    exp = math.log(0.1) + math.log(0.2) + math.log(0.3) + 2 * math.log(0.4) + math.log(1.0)
+    assert fc1.log_likelihood(single, m) == pytest.approx(exp, rel=1e-13)
+    with pytest.raises(ValueError):
+        fc1.log_likelihood(P.FlatTree([1, 0], [0.1, 0.1], ["A", None]), m)  # cycle / no root
+
+
+def test_ragged_batch_many_loci_vs_oracle():
+    """Ragged loci (different taxa counts, pattern counts around the 128/512 tile edges) in one batch."""
+    P = _pkg()
+    from phynetpy_b200 import simulate as S
+    rng = np.random.default_rng(77)
+    model = P.GTR(S.DEFAULT_PI, S.DEFAULT_RATES)
+    om = O.gtr(S.DEFAULT_PI, S.DEFAULT_RATES)
+    loci, trees, exp = [], [], []
+    for n, L in [(4, 127), (6, 128), (9, 129), (12, 511), (5, 512), (7, 513), (20, 1300), (3, 1), (11, 2500)]:
+        par, bl = S.random_trees(1, n, rng, height=0.6)
+        aln = S.simulate_alignments(par, bl, L, S.DEFAULT_PI, S.DEFAULT_RATES, rng)[0]
+        ft = S.flat_trees(par, bl)[0]
+        d = S.to_alignment_dict(aln)
+        loci.append(d)
+        trees.append(ft)
+        exp.append(O.log_likelihood(O.OracleLocus(d), _otree(ft), om))
+    eng = P.SeqLikelihoodEngine(loci, None, model)
+    total = eng.log_likelihood(trees, None, 0.0)
+    for got, e in zip(eng._felsen, exp):
+        assert rel_err(got, e) <= REL
+    assert rel_err(total, sum(exp)) <= REL
+
+
+def test_large_locus_full_size_properties():
+    """cfg2-like size on one GPU (50 taxa, >=2e5 patterns): size-independent properties --
+    (1) total == sum over disjoint pattern blocks evaluated as separate loci (linearity),
+    (2) dirty-path == full, (3) oracle agreement on a 20k-pattern prefix block."""
+    P = _pkg()
+    from phynetpy_b200 import simulate as S
+    rng = np.random.default_rng(2)
+    n, L = 50, 250_000
+    par, bl = S.random_trees(1, n, rng)
+    aln = S.simulate_alignments(par, bl, L, S.DEFAULT_PI, S.DEFAULT_RATES, rng)[0]
+    ft = S.flat_trees(par, bl)[0]
+    model = P.GTR(S.DEFAULT_PI, S.DEFAULT_RATES)
+    taxa = S.tip_labels(n)
+    fc = P.FelsensteinCalculator.from_matrix(taxa, aln, device_compress=True)
+    assert fc.n_patterns > 200_000 and int(fc._int_weights.sum()) == L
+    whole = fc.log_likelihood(ft, model)
+    parts = []
+    for lo in range(0, fc.n_patterns, 50_000):
+        sub = P.FelsensteinCalculator.from_codes(taxa, fc._codes[:, lo:lo + 50_000], fc._int_weights[lo:lo + 50_000])
+        parts.append(sub.log_likelihood(ft, model))
+        if lo == 0:
+            exp0 = O.log_likelihood_codes(fc._codes[:, :20_000], fc._int_weights[:20_000],
+                                          ft.tip_rows({t: i for i, t in enumerate(taxa)}), _otree(ft),
+                                          O.gtr(S.DEFAULT_PI, S.DEFAULT_RATES))
+            sub0 = P.FelsensteinCalculator.from_codes(taxa, fc._codes[:, :20_000], fc._int_weights[:20_000])
+            assert rel_err(sub0.log_likelihood(ft, model), exp0) <= REL
+        sub.close()
+    assert rel_err(sum(parts), whole) <= 1e-12
+    bl2 = ft.blen.copy()
+    bl2[7] *= 1.5
+    ft2 = ft.with_lengths(bl2)
+    dirty = fc.log_likelihood(ft2, model)
+    assert fc._context().last_stats()["nodes_recomputed"] < n - 1
+    assert dirty == fc.log_likelihood(ft2, model, full=True)
