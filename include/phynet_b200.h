@@ -76,6 +76,12 @@ PNB_API int pnb_ctx_synchronize(pnb_ctx *ctx);
  * [3]=kernel launches, [4]=H2D bytes, [5]=D2H bytes, [6]=jobs served from cache,
  * [7]=internal nodes recomputed                                           */
 PNB_API int pnb_ctx_last_stats(pnb_ctx *ctx, int64_t stats[8]);
+/* Measurement hooks (bench.py): with profiling on, every pnb_eval brackets its two
+ * kernels with CUDA events on the context's stream.  pnb_ctx_last_timings waits for
+ * the last evaluation and returns milliseconds: [0]=host tree compilation,
+ * [1]=K-a kernel, [2]=pruning kernel, [3]=whole call on the host (launch + wait). */
+PNB_API int pnb_ctx_set_profiling(pnb_ctx *ctx, int enable);
+PNB_API int pnb_ctx_last_timings(pnb_ctx *ctx, double ms[4]);
 
 /* ---- substitution model ------------------------------------------------ */
 /* Replaces SubstitutionModel._build_and_decompose's outputs being consumed by

@@ -311,6 +311,30 @@ def log_likelihood_codes(codes: np.ndarray, weights: np.ndarray, tip_row: Sequen
     return float(np.dot(np.log(site_like), np.asarray(weights, dtype=np.float64)))
 
 
+class OracleCodesLocus:
+    """Tip tables prebuilt from (n_rows, P) codes, as the reference's constructor leaves them
+    (:361-367), so that timing an evaluation excludes construction."""
+
+    def __init__(self, codes: np.ndarray, weights: np.ndarray):
+        bits = np.array([[(c >> j) & 1 for j in range(4)] for c in range(16)], dtype=np.float64)
+        self.n_patterns = int(codes.shape[1])
+        self.rows = [np.ascontiguousarray(bits[codes[r]]) for r in range(codes.shape[0])]
+        self.weights = np.asarray(weights, dtype=np.float64)
+
+    def log_likelihood(self, tip_row: Sequence[int], tree: OracleTree, model: OracleModel, site_rate: float = 1.0) -> float:
+        tips = {}
+        label = list(tree.label)
+        for i in range(len(tree.parent)):
+            if not tree.children[i]:
+                label[i] = "__tip%d" % i
+                if tip_row[i] >= 0:
+                    tips[label[i]] = self.rows[tip_row[i]]
+        t2 = OracleTree(tree.parent, tree.blen, label)
+        partials = postorder_partials(tips, self.n_patterns, t2, t2.root, model, site_rate)
+        site_like = np.maximum(partials @ model.pi, 1e-300)
+        return float(np.dot(np.log(site_like), self.weights))
+
+
 # --- engine loop: src/_mcmc_seq.py:746-764 (Felsenstein factor only) -------
 def engine_log_likelihood(loci: Sequence[OracleLocus], trees: Sequence[OracleTree], model: OracleModel) -> Tuple[float, List[float]]:
     per_locus = [log_likelihood(l, t, model) for l, t in zip(loci, trees)]

@@ -32,6 +32,7 @@ EVAL_OUT_DEVICE = 0x8
 ABI_SYMBOLS = (
     "pnb_abi_version", "pnb_last_error",
     "pnb_ctx_create", "pnb_ctx_destroy", "pnb_ctx_set_stream", "pnb_ctx_synchronize", "pnb_ctx_last_stats",
+    "pnb_ctx_set_profiling", "pnb_ctx_last_timings",
     "pnb_model_create_eigen", "pnb_model_create_jc69", "pnb_model_create_explicit", "pnb_model_destroy",
     "pnb_pmatrix_batch", "pnb_compress",
     "pnb_locus_create", "pnb_locus_destroy", "pnb_locus_invalidate", "pnb_locus_read_partial",
@@ -77,6 +78,8 @@ def load() -> C.CDLL:
             "pnb_ctx_set_stream": [_vp, _vp],
             "pnb_ctx_synchronize": [_vp],
             "pnb_ctx_last_stats": [_vp, C.POINTER(_i64)],
+            "pnb_ctx_set_profiling": [_vp, C.c_int],
+            "pnb_ctx_last_timings": [_vp, _dbl_p],
             "pnb_model_create_eigen": [_vp, _vp, _vp, _vp, _vp, C.POINTER(_vp)],
             "pnb_model_create_jc69": [_vp, C.POINTER(_vp)],
             "pnb_model_create_explicit": [_vp, _vp, C.POINTER(_vp)],

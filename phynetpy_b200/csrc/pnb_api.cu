@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
+#include <chrono>
 #include <cstdlib>
 #include <new>
 
@@ -173,6 +174,7 @@ extern "C" int pnb_ctx_destroy(pnb_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->h_stage.p) cudaFreeHost(ctx->h_stage.p);
     if (ctx->h_out.p) cudaFreeHost(ctx->h_out.p);
+    for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     for (Buffer* b : {&ctx->d_stage, &ctx->d_P, &ctx->d_tile_sum, &ctx->d_job_done, &ctx->d_out})
         if (b->p) cudaFree(b->p);
     ctx->arena.destroy();
@@ -193,6 +195,37 @@ extern "C" int pnb_ctx_synchronize(pnb_ctx* ctx) {
     PNB_REQUIRE(ctx != nullptr, PNB_ERR_INVALID, "pnb_ctx_synchronize: ctx is NULL");
     PNB_CUDA_TRY(cudaSetDevice(ctx->device));
     PNB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return PNB_OK;
+}
+
+extern "C" int pnb_ctx_set_profiling(pnb_ctx* ctx, int enable) {
+    PNB_REQUIRE(ctx != nullptr, PNB_ERR_INVALID, "pnb_ctx_set_profiling: ctx is NULL");
+    PNB_CUDA_TRY(cudaSetDevice(ctx->device));
+    if (enable && !ctx->ev[0])
+        for (auto& e : ctx->ev) PNB_CUDA_TRY(cudaEventCreate(&e));
+    ctx->profiling = enable != 0;
+    ctx->ev_ka = ctx->ev_prune = false;
+    return PNB_OK;
+}
+
+extern "C" int pnb_ctx_last_timings(pnb_ctx* ctx, double ms[4]) {
+    PNB_REQUIRE(ctx != nullptr && ms != nullptr, PNB_ERR_INVALID, "pnb_ctx_last_timings: NULL argument");
+    ms[0] = ctx->t_compile_ms;
+    ms[1] = ms[2] = 0.0;
+    ms[3] = ctx->t_call_ms;
+    if (!ctx->profiling) return PNB_OK;
+    PNB_CUDA_TRY(cudaSetDevice(ctx->device));
+    float f = 0.f;
+    if (ctx->ev_ka) {
+        PNB_CUDA_TRY(cudaEventSynchronize(ctx->ev[1]));
+        PNB_CUDA_TRY(cudaEventElapsedTime(&f, ctx->ev[0], ctx->ev[1]));
+        ms[1] = f;
+    }
+    if (ctx->ev_prune) {
+        PNB_CUDA_TRY(cudaEventSynchronize(ctx->ev[3]));
+        PNB_CUDA_TRY(cudaEventElapsedTime(&f, ctx->ev[2], ctx->ev[3]));
+        ms[2] = f;
+    }
     return PNB_OK;
 }
 
@@ -763,6 +796,8 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
     PNB_REQUIRE(m->ctx == ctx, PNB_ERR_INVALID, "pnb_eval: model belongs to another context");
     PNB_REQUIRE(M >= 0, PNB_ERR_INVALID, "pnb_eval: M < 0");
     memset(ctx->stats, 0, sizeof(ctx->stats));
+    const auto t_call0 = std::chrono::steady_clock::now();
+    ctx->ev_ka = ctx->ev_prune = false;
     if (M == 0) return PNB_OK;
     PNB_REQUIRE(loci && node_off && parent && logL_out, PNB_ERR_INVALID, "pnb_eval: NULL array");
     const bool nostore = flags & PNB_EVAL_NOSTORE;
@@ -822,6 +857,7 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
     double* h_out = static_cast<double*>(ctx->h_out.p);
 
     // ---- pass 1: compile -------------------------------------------------
+    const auto t_comp0 = std::chrono::steady_clock::now();
     int64_t n_jobs = 0, n_tiles = 0, n_ops = 0, updates = 0, n_cached = 0, n_dirty_nodes = 0;
     int ops_cap = 1, rows_cap = 1, stk_cap = 0;
     std::vector<int64_t> job_of_batch(M, -1);
@@ -878,6 +914,7 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
         n_jobs++;
     }
 
+    ctx->t_compile_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_comp0).count();
     int64_t h2d = 0, d2h = 0, launches = 0;
     if (n_jobs > 0) {
         const size_t dyn_smem = static_cast<size_t>(ops_cap) * (sizeof(Op) + 128) +
@@ -920,9 +957,11 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
                 h2d += n_ops * 128;
             } else {
                 const int64_t blocks = (n_ops + 127) / 128;
+                if (ctx->profiling) PNB_CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
                 pnb_pmatrix_kernel<<<static_cast<unsigned>(blocks), 128, 0, st>>>(
                     m->mp, reinterpret_cast<const double*>(ds + off_t), n_ops, static_cast<double*>(ctx->d_P.p));
                 PNB_CUDA_TRY(cudaGetLastError());
+                if (ctx->profiling) { PNB_CUDA_TRY(cudaEventRecord(ctx->ev[1], st)); ctx->ev_ka = true; }
                 launches++;
             }
         }
@@ -943,8 +982,10 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
             // jobs without device work (empty loci) still need their slot written
             PNB_CUDA_TRY(cudaMemsetAsync(logL_out, 0, M * sizeof(double), st));
         }
+        if (ctx->profiling) PNB_CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
         pnb_prune_kernel<<<static_cast<unsigned>(n_tiles), TPB, dyn_smem, st>>>(L, m->mp);
         PNB_CUDA_TRY(cudaGetLastError());
+        if (ctx->profiling) { PNB_CUDA_TRY(cudaEventRecord(ctx->ev[3], st)); ctx->ev_prune = true; }
         launches++;
         if (!out_dev) {
             double* got = h_out + M;  // second half of the pinned result buffer
@@ -977,6 +1018,7 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
     if (!nostore && !(flags & PNB_EVAL_PENDING))
         for (int64_t j = 0; j < M; ++j) locus_commit(loci[j]);
 
+    ctx->t_call_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call0).count();
     ctx->stats[0] = updates;
     ctx->stats[1] = n_ops;
     ctx->stats[2] = n_tiles;

@@ -79,6 +79,10 @@ struct pnb_ctx {
     pnb::Buffer d_tile_sum, d_job_done, d_out, h_out;
     size_t job_done_zeroed = 0;    // counters [0, job_done_zeroed) are known to be zero
     int64_t stats[8] = {0};
+    bool profiling = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // K-a begin/end, prune begin/end
+    bool ev_ka = false, ev_prune = false;
+    double t_compile_ms = 0.0, t_call_ms = 0.0;
     int64_t n_loci_alive = 0;
     // compile scratch (reused across calls)
     std::vector<int32_t> s_child_cnt, s_child_off, s_child, s_post, s_stack, s_ref, s_need, s_order;

@@ -60,6 +60,15 @@ class DeviceContext:
         _lib.check(self._lib.pnb_ctx_last_stats(self.handle, arr))
         return dict(zip(STAT_NAMES, (int(x) for x in arr)))
 
+    def set_profiling(self, enable: bool) -> None:
+        _lib.check(self._lib.pnb_ctx_set_profiling(self.handle, 1 if enable else 0))
+
+    def last_timings(self) -> Dict[str, float]:
+        """ms of the last evaluation: host compile, K-a kernel, pruning kernel, whole host call."""
+        arr = (C.c_double * 4)()
+        _lib.check(self._lib.pnb_ctx_last_timings(self.handle, arr))
+        return {"compile_ms": arr[0], "pmatrix_ms": arr[1], "prune_ms": arr[2], "call_ms": arr[3]}
+
     def destroy(self) -> None:
         if self._h is not None and self._pid == os.getpid():
             self._lib.pnb_ctx_destroy(self._h)
