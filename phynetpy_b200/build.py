@@ -43,7 +43,8 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    defs = os.environ.get("PNB_NVCC_DEFS", "").split()  # tuning knobs, e.g. "-DPNB_PPT=1 -DPNB_MIN_BLOCKS=8"
+    cmd = [_nvcc()] + NVCC_FLAGS + defs + (["-Xptxas", "-v"] if verbose else []) + \
         [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB + ".tmp"]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:

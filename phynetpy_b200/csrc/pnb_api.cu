@@ -390,7 +390,7 @@ extern "C" int pnb_locus_create(pnb_ctx* ctx, int32_t n_rows, int64_t P, const u
     loc->ctx = ctx;
     loc->n_rows = n_rows;
     loc->P = P;
-    loc->P_pad = static_cast<int64_t>(align_up(static_cast<size_t>(std::max<int64_t>(P, 1)), TPB));
+    loc->P_pad = static_cast<int64_t>(align_up(static_cast<size_t>(std::max<int64_t>(P, 1)), TILE_PATTERNS));
     if (P > 0) {
         loc->codes_bytes = static_cast<size_t>(n_rows) * loc->P_pad;
         loc->weights_bytes = static_cast<size_t>(loc->P_pad) * sizeof(double);
@@ -401,11 +401,17 @@ extern "C" int pnb_locus_create(pnb_ctx* ctx, int32_t n_rows, int64_t P, const u
         rc = ctx->arena.alloc(loc->weights_bytes, &p);
         if (rc) { ctx->arena.release(loc->d_codes, loc->codes_bytes); delete loc; return rc; }
         loc->d_weights = static_cast<double*>(p);
-        // host-side padded images (pad codes with 0 = "no state", weights with 0)
-        std::vector<uint8_t> hc(loc->codes_bytes, 0);
-        for (int r = 0; r < n_rows; ++r)
-            memcpy(hc.data() + static_cast<size_t>(r) * loc->P_pad, codes + static_cast<size_t>(r) * ld_codes,
-                   static_cast<size_t>(P));
+        // host-side padded images.  Device tip code: a single state j is stored as j (the kernel
+        // reads column j of P directly); anything else as 0x80 | mask.  Padding = 0x80 (no state).
+        std::vector<uint8_t> hc(loc->codes_bytes, 0x80);
+        for (int r = 0; r < n_rows; ++r) {
+            const uint8_t* src = codes + static_cast<size_t>(r) * ld_codes;
+            uint8_t* dst = hc.data() + static_cast<size_t>(r) * loc->P_pad;
+            for (int64_t k = 0; k < P; ++k) {
+                const uint8_t m = src[k] & 0xF;
+                dst[k] = (m == 1) ? 0 : (m == 2) ? 1 : (m == 4) ? 2 : (m == 8) ? 3 : static_cast<uint8_t>(0x80 | m);
+            }
+        }
         std::vector<double> hw(loc->P_pad, 0.0);
         for (int64_t k = 0; k < P; ++k) hw[k] = static_cast<double>(weights[k]);
         cudaError_t e = cudaMemcpyAsync(loc->d_codes, hc.data(), loc->codes_bytes, cudaMemcpyHostToDevice, ctx->stream);
@@ -462,8 +468,10 @@ extern "C" int pnb_locus_read_partial(pnb_locus* loc, int32_t node, double* out)
         std::vector<uint8_t> row(loc->P);
         PNB_CUDA_TRY(cudaMemcpy(row.data(), loc->d_codes + ref * loc->P_pad, static_cast<size_t>(loc->P),
                                 cudaMemcpyDeviceToHost));
-        for (int64_t k = 0; k < loc->P; ++k)
-            for (int j = 0; j < 4; ++j) out[k * 4 + j] = (row[k] >> j) & 1 ? 1.0 : 0.0;
+        for (int64_t k = 0; k < loc->P; ++k) {
+            const unsigned m = (row[k] & 0x80) ? (row[k] & 0xFu) : (1u << row[k]);
+            for (int j = 0; j < 4; ++j) out[k * 4 + j] = (m >> j) & 1 ? 1.0 : 0.0;
+        }
     } else {
         for (int64_t k = 0; k < loc->P * 4; ++k) out[k] = 1.0;
     }
@@ -918,7 +926,8 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
     int64_t h2d = 0, d2h = 0, launches = 0;
     if (n_jobs > 0) {
         const size_t dyn_smem = static_cast<size_t>(ops_cap) * (sizeof(Op) + 128) +
-                                static_cast<size_t>(2) * rows_cap * TPB + static_cast<size_t>(stk_cap) * TPB * 32;
+                                static_cast<size_t>(rows_cap) * TILE_PATTERNS +
+                                static_cast<size_t>(stk_cap) * TILE_PATTERNS * 32;
         if (dyn_smem > static_cast<size_t>(ctx->max_smem_optin - 1024)) {
             if (!nostore)
                 for (int64_t q = 0; q < M; ++q) locus_rollback(loci[q]);

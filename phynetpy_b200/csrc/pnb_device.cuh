@@ -17,10 +17,20 @@
 
 namespace pnb {
 
-constexpr int TPB = 128;            // threads per block: one thread = one site pattern of a chunk
-constexpr int TILE_PATTERNS = 512;  // patterns per tile; FIXED so the summation order of a locus
-                                    // never depends on batch composition or GPU count
-constexpr int CHUNKS_PER_TILE = TILE_PATTERNS / TPB;
+#ifndef PNB_TPB
+#define PNB_TPB 128
+#endif
+#ifndef PNB_PPT
+#define PNB_PPT 2
+#endif
+#ifndef PNB_MIN_BLOCKS
+#define PNB_MIN_BLOCKS 5
+#endif
+constexpr int TPB = PNB_TPB;        // threads per block
+constexpr int PPT = PNB_PPT;        // site patterns per thread (independent dependency chains)
+constexpr int TILE_PATTERNS = TPB * PPT;  // patterns per tile; FIXED so the summation order of a locus
+                                          // never depends on batch composition or GPU count
+constexpr int PRUNE_MIN_BLOCKS = PNB_MIN_BLOCKS;  // occupancy target of the pruning kernel (register budget)
 
 // child-contribution source kinds
 enum : uint32_t { K_TIP = 0, K_MEM = 1, K_REG = 2, K_STK = 3 };
@@ -43,12 +53,12 @@ struct __align__(16) Op {
 };
 
 struct __align__(16) JobDesc {
-    const uint8_t* codes;   // [n_rows][ld_codes] 4-bit tip masks
+    const uint8_t* codes;   // [n_rows][ld_codes] device tip codes: state j (0..3), or 0x80 | 4-bit mask
     double* partials;       // [n_slots][P_pad][4] per-node partials of this locus
     const double* weights;  // [P_pad] pattern multiplicities (integer valued)
     int64_t slot_stride;    // doubles per slot (= P_pad * 4)
     int32_t P;              // site patterns
-    int32_t ld_codes;       // row stride of codes (= P_pad, multiple of TPB)
+    int32_t ld_codes;       // row stride of codes (= P_pad, multiple of TILE_PATTERNS)
     int32_t op_off;         // first op / P matrix of this job in the batch arrays
     int32_t n_ops;
     int32_t n_tip_ops;      // TIP ops with src >= 0 (rows staged per chunk)
@@ -179,15 +189,19 @@ pnb_pmatrix_kernel(const __grid_constant__ ModelParams mp, const double* __restr
 }
 
 // ------------------------------------------------------------------------
-// K-b / K-c: pruning.  grid = tiles, block = TPB threads.
+// K-b / K-c: pruning.  grid = tiles, block = TPB threads, PPT patterns per thread.
+//
+// A thread owns PPT patterns of the tile (tid, tid + TPB, ...) and walks the
+// job's op program once for all of them: the program, its P matrices and the
+// loop control are shared, and the PPT independent dependency chains give the
+// FP64 pipe and the LSU something to overlap.
 //
 // Dynamic shared memory layout (bytes):
-//   [0, ops_cap*16)                      Op program of the job
-//   [.., + ops_cap*128)                  P matrices, one per op (row-major 4x4 f64)
-//   [.., + 2*rows_cap*TPB)               double-buffered tip-code rows of the chunk
-//   [.., + stk_cap*TPB*32)               (NOSTORE only) partial stash stack
+//   [0, ops_cap*16)                 Op program of the job
+//   [.., + ops_cap*128)             P matrices, one per op (row-major 4x4 f64)
+//   [.., + rows_cap*TILE)           tip-code rows of the tile (one byte per pattern)
+//   [.., + stk_cap*TILE*32)         (NOSTORE only) partial stash stack
 // ------------------------------------------------------------------------
-
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -209,165 +223,225 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
     return s;
 }
 
-__global__ void __launch_bounds__(TPB, 8)
+struct Vec4 { double x0, x1, x2, x3; };
+
+// v = P . l   (child_partials @ P.T, reference :425), P row-major in shared memory (broadcast reads)
+__device__ __forceinline__ void matvec(const double* __restrict__ Pk, const Vec4 (&l)[PPT], Vec4 (&v)[PPT]) {
+    const double2* P2 = reinterpret_cast<const double2*>(Pk);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double2 pa = P2[i * 2 + 0];
+        const double2 pb = P2[i * 2 + 1];
+#pragma unroll
+        for (int u = 0; u < PPT; ++u) {
+            const double r = fma(pb.y, l[u].x3, fma(pb.x, l[u].x2, fma(pa.y, l[u].x1, pa.x * l[u].x0)));
+            if (i == 0) v[u].x0 = r;
+            else if (i == 1) v[u].x1 = r;
+            else if (i == 2) v[u].x2 = r;
+            else v[u].x3 = r;
+        }
+    }
+}
+
+// contribution of a tip child: column(s) of P selected by the device tip code
+//   code < 4        : the single state j = code           -> column j of P
+//   code & 0x80     : ambiguity / gap, low 4 bits = mask   -> sum of the allowed columns, in state order
+__device__ __forceinline__ void tip_contrib(const double* __restrict__ Pk, const uint32_t (&code)[PPT],
+                                            Vec4 (&v)[PPT]) {
+    bool amb = false;
+#pragma unroll
+    for (int u = 0; u < PPT; ++u) amb |= (code[u] & 0x80u) != 0;
+    if (!__any_sync(0xffffffffu, amb)) {
+#pragma unroll
+        for (int u = 0; u < PPT; ++u) {
+            const double* col = Pk + code[u];
+            v[u].x0 = col[0]; v[u].x1 = col[4]; v[u].x2 = col[8]; v[u].x3 = col[12];
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < PPT; ++u) {
+            const uint32_t m = (code[u] & 0x80u) ? (code[u] & 0xFu) : (1u << code[u]);
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (m & (1u << j)) { s0 += Pk[0 + j]; s1 += Pk[4 + j]; s2 += Pk[8 + j]; s3 += Pk[12 + j]; }
+            }
+            v[u].x0 = s0; v[u].x1 = s1; v[u].x2 = s2; v[u].x3 = s3;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TPB, PRUNE_MIN_BLOCKS)
 pnb_prune_kernel(const __grid_constant__ PruneLaunch L, const __grid_constant__ ModelParams mp) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t bar_prog;
-    __shared__ __align__(8) uint64_t bar_codes[2];
+    __shared__ __align__(8) uint64_t bar_stage;
     __shared__ double red[TPB / 32];
     __shared__ int s_is_last;
 
     const int tid = threadIdx.x;
     const int tile = blockIdx.x;
     const int job = L.tile_job[tile];
-    const JobDesc jd = L.jobs[job];
+    const JobDesc& jd = L.jobs[job];
+    const int n_ops = jd.n_ops;
+    const int op_off = jd.op_off;
+    const int n_tip_ops = jd.n_tip_ops;
+    const int tile0 = jd.tile0;
+    const int P = jd.P;
+    const int ld_codes = jd.ld_codes;
+    const uint8_t* g_codes = jd.codes;
 
     Op* s_ops = reinterpret_cast<Op*>(smem_raw);
     double* s_P = reinterpret_cast<double*>(smem_raw + static_cast<size_t>(L.ops_cap) * sizeof(Op));
     unsigned char* s_codes = reinterpret_cast<unsigned char*>(s_P + static_cast<size_t>(L.ops_cap) * 16);
-    double2* s_stk = reinterpret_cast<double2*>(s_codes + static_cast<size_t>(2) * L.rows_cap * TPB);
+    double2* s_stk = reinterpret_cast<double2*>(s_codes + static_cast<size_t>(L.rows_cap) * TILE_PATTERNS);
 
-    const int p0 = (tile - jd.tile0) * TILE_PATTERNS;
-    const int remaining = jd.P - p0;
-    const int n_chunks = (min(remaining, TILE_PATTERNS) + TPB - 1) / TPB;
-    const int n_ops = jd.n_ops;
-    const Op* g_ops = L.ops + jd.op_off;
+    const int p0 = (tile - tile0) * TILE_PATTERNS;
+    const Op* g_ops = L.ops + op_off;
 
     if (tid == 0) {
-        mbar_init(&bar_prog, 1);
-        mbar_init(&bar_codes[0], 1);
-        mbar_init(&bar_codes[1], 1);
+        mbar_init(&bar_stage, 1);
         mbar_fence_init();
     }
     __syncthreads();
 
-    // warp 0 is the TMA producer: program + P matrices once, code rows per chunk
-    auto issue_codes = [&](int chunk) {
-        // called by all lanes of warp 0
-        const int buf = chunk & 1;
-        if (tid == 0) mbar_arrive_expect_tx(&bar_codes[buf], static_cast<uint32_t>(jd.n_tip_ops) * TPB);
-        __syncwarp();
-        const int64_t pc = p0 + chunk * TPB;
-        for (int k = tid; k < n_ops; k += 32) {
-            const Op op = g_ops[k];
-            if ((op.flags & F_KIND_MASK) == K_TIP && op.src >= 0) {
-                tma_bulk_g2s(s_codes + (static_cast<size_t>(buf) * L.rows_cap + op.aux) * TPB,
-                             jd.codes + static_cast<int64_t>(op.src) * jd.ld_codes + pc, TPB,
-                             &bar_codes[buf]);
-            }
-        }
-    };
+    // warp 0 is the TMA producer: program, P matrices and the tile's code rows, one mbarrier
     if (tid < 32) {
         if (tid == 0) {
-            mbar_arrive_expect_tx(&bar_prog, static_cast<uint32_t>(n_ops) * (sizeof(Op) + 128u));
+            mbar_arrive_expect_tx(&bar_stage, static_cast<uint32_t>(n_ops) * (sizeof(Op) + 128u) +
+                                                  static_cast<uint32_t>(n_tip_ops) * TILE_PATTERNS);
             if (n_ops > 0) {
-                tma_bulk_g2s(s_ops, g_ops, static_cast<uint32_t>(n_ops) * sizeof(Op), &bar_prog);
-                tma_bulk_g2s(s_P, L.Pm + static_cast<int64_t>(jd.op_off) * 16,
-                             static_cast<uint32_t>(n_ops) * 128u, &bar_prog);
+                tma_bulk_g2s(s_ops, g_ops, static_cast<uint32_t>(n_ops) * sizeof(Op), &bar_stage);
+                tma_bulk_g2s(s_P, L.Pm + static_cast<int64_t>(op_off) * 16, static_cast<uint32_t>(n_ops) * 128u,
+                             &bar_stage);
             }
         }
-        issue_codes(0);
+        __syncwarp();
+        for (int k = tid; k < n_ops; k += 32) {
+            const Op op = g_ops[k];
+            if ((op.flags & F_KIND_MASK) == K_TIP && op.src >= 0)
+                tma_bulk_g2s(s_codes + static_cast<size_t>(op.aux) * TILE_PATTERNS,
+                             g_codes + static_cast<int64_t>(op.src) * ld_codes + p0, TILE_PATTERNS, &bar_stage);
+        }
     }
 
-    double lsum = 0.0;
-    mbar_wait(&bar_prog, 0);
-
-    for (int c = 0; c < n_chunks; ++c) {
-        if (tid < 32 && c + 1 < n_chunks) issue_codes(c + 1);
-        const int buf = c & 1;
-        mbar_wait(&bar_codes[buf], (c >> 1) & 1);
-
-        const int pat = p0 + c * TPB + tid;
-        const bool active = pat < jd.P;
-        const unsigned char* my_codes = s_codes + static_cast<size_t>(buf) * L.rows_cap * TPB + tid;
-        double* my_part = jd.partials + static_cast<int64_t>(pat) * 4;
-
-        double c0 = 1.0, c1 = 1.0, c2 = 1.0, c3 = 1.0;  // cur: last completed node partial
-        double a0 = 1.0, a1 = 1.0, a2 = 1.0, a3 = 1.0;  // acc: node under construction
-
-        if (active) {
-            for (int k = 0; k < n_ops; ++k) {
-                const Op op = s_ops[k];
-                const double* Pk = s_P + k * 16;
-                const uint32_t kind = op.flags & F_KIND_MASK;
-                double v0, v1, v2, v3;
-                if (kind == K_TIP) {
-                    const uint32_t code = (op.src >= 0) ? my_codes[op.aux * TPB] : 0xFu;
-                    if (__popc(code) == 1) {
-                        const int j = __ffs(code) - 1;
-                        v0 = Pk[0 + j]; v1 = Pk[4 + j]; v2 = Pk[8 + j]; v3 = Pk[12 + j];
-                    } else {
-                        // ambiguity / gap: sum of the allowed columns, in state order
-                        v0 = v1 = v2 = v3 = 0.0;
+    // per-thread pattern bookkeeping while the copies are in flight
+    const int64_t slot_stride = jd.slot_stride;
+    double* part0 = jd.partials + static_cast<int64_t>(p0 + tid) * 4;
+    bool active[PPT];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            if (code & (1u << j)) {
-                                v0 += Pk[0 + j]; v1 += Pk[4 + j]; v2 += Pk[8 + j]; v3 += Pk[12 + j];
-                            }
-                        }
+    for (int u = 0; u < PPT; ++u) active[u] = (p0 + tid + u * TPB) < P;
+    const unsigned char* my_codes = s_codes + tid;
+
+    Vec4 cur[PPT];  // last completed node partial (register forwarding)
+    Vec4 acc[PPT];  // node under construction
+#pragma unroll
+    for (int u = 0; u < PPT; ++u) { cur[u] = {1.0, 1.0, 1.0, 1.0}; acc[u] = {1.0, 1.0, 1.0, 1.0}; }
+
+    mbar_wait(&bar_stage, 0);
+
+    // Warp-uniform guard (tip_contrib votes across the full warp): a warp runs the program if any of
+    // its lanes owns a pattern; lanes past the end compute on zero codes and never touch HBM.
+    if (__any_sync(0xffffffffu, active[0])) {
+        for (int k = 0; k < n_ops; ++k) {
+            const Op op = s_ops[k];
+            const double* Pk = s_P + k * 16;
+            const uint32_t kind = op.flags & F_KIND_MASK;
+            Vec4 v[PPT];
+            if (kind == K_TIP) {
+                uint32_t code[PPT];
+#pragma unroll
+                for (int u = 0; u < PPT; ++u) {
+                    code[u] = 0u;
+                    if (active[u]) code[u] = (op.src >= 0) ? my_codes[op.aux * TILE_PATTERNS + u * TPB] : 0x8Fu;
+                }
+                tip_contrib(Pk, code, v);
+            } else if (kind == K_REG) {
+                matvec(Pk, cur, v);
+            } else {
+                Vec4 l[PPT];
+                if (kind == K_MEM) {
+                    const double* src = part0 + static_cast<int64_t>(op.src) * slot_stride;
+#pragma unroll
+                    for (int u = 0; u < PPT; ++u) {
+                        if (active[u]) ldg256(src + u * TPB * 4, l[u].x0, l[u].x1, l[u].x2, l[u].x3);
+                        else l[u] = {1.0, 1.0, 1.0, 1.0};
                     }
                 } else {
-                    double l0, l1, l2, l3;
-                    if (kind == K_REG) {
-                        l0 = c0; l1 = c1; l2 = c2; l3 = c3;
-                    } else if (kind == K_MEM) {
-                        ldg256(my_part + static_cast<int64_t>(op.src) * jd.slot_stride, l0, l1, l2, l3);
-                    } else {
-                        const double2 x = s_stk[(op.src * 2 + 0) * TPB + tid];
-                        const double2 y = s_stk[(op.src * 2 + 1) * TPB + tid];
-                        l0 = x.x; l1 = x.y; l2 = y.x; l3 = y.y;
+#pragma unroll
+                    for (int u = 0; u < PPT; ++u) {
+                        const double2 x = s_stk[(op.src * 2 + 0) * TILE_PATTERNS + u * TPB + tid];
+                        const double2 y = s_stk[(op.src * 2 + 1) * TILE_PATTERNS + u * TPB + tid];
+                        l[u] = {x.x, x.y, y.x, y.y};
                     }
-                    // child_partials @ P.T  (reference :425): v_i = sum_j P[i][j] * L_j
-                    v0 = fma(Pk[3], l3, fma(Pk[2], l2, fma(Pk[1], l1, Pk[0] * l0)));
-                    v1 = fma(Pk[7], l3, fma(Pk[6], l2, fma(Pk[5], l1, Pk[4] * l0)));
-                    v2 = fma(Pk[11], l3, fma(Pk[10], l2, fma(Pk[9], l1, Pk[8] * l0)));
-                    v3 = fma(Pk[15], l3, fma(Pk[14], l2, fma(Pk[13], l1, Pk[12] * l0)));
                 }
-                if (op.flags & F_FIRST) {
-                    a0 = v0; a1 = v1; a2 = v2; a3 = v3;
-                } else {
-                    a0 *= v0; a1 *= v1; a2 *= v2; a3 *= v3;
+                matvec(Pk, l, v);
+            }
+            if (op.flags & F_FIRST) {
+#pragma unroll
+                for (int u = 0; u < PPT; ++u) acc[u] = v[u];
+            } else {
+#pragma unroll
+                for (int u = 0; u < PPT; ++u) {
+                    acc[u].x0 *= v[u].x0; acc[u].x1 *= v[u].x1; acc[u].x2 *= v[u].x2; acc[u].x3 *= v[u].x3;
                 }
-                if (op.flags & F_LAST) {
-                    c0 = a0; c1 = a1; c2 = a2; c3 = a3;
-                    if (op.flags & F_STORE)
-                        stg256(my_part + static_cast<int64_t>(op.dst) * jd.slot_stride, c0, c1, c2, c3);
-                    if (op.flags & F_PUSH) {
-                        const int si = (op.flags >> 8) & 0xff;
-                        s_stk[(si * 2 + 0) * TPB + tid] = make_double2(c0, c1);
-                        s_stk[(si * 2 + 1) * TPB + tid] = make_double2(c2, c3);
+            }
+            if (op.flags & F_LAST) {
+#pragma unroll
+                for (int u = 0; u < PPT; ++u) cur[u] = acc[u];
+                if (op.flags & F_STORE) {
+                    double* dst = part0 + static_cast<int64_t>(op.dst) * slot_stride;
+#pragma unroll
+                    for (int u = 0; u < PPT; ++u)
+                        if (active[u]) stg256(dst + u * TPB * 4, cur[u].x0, cur[u].x1, cur[u].x2, cur[u].x3);
+                }
+                if (op.flags & F_PUSH) {
+                    const int si = (op.flags >> 8) & 0xff;
+#pragma unroll
+                    for (int u = 0; u < PPT; ++u) {
+                        s_stk[(si * 2 + 0) * TILE_PATTERNS + u * TPB + tid] = make_double2(cur[u].x0, cur[u].x1);
+                        s_stk[(si * 2 + 1) * TILE_PATTERNS + u * TPB + tid] = make_double2(cur[u].x2, cur[u].x3);
                     }
                 }
             }
-            // root: site likelihood, clamp, log, weight  (reference :394-397)
-            if (jd.root_kind == K_MEM) {
-                ldg256(my_part + static_cast<int64_t>(jd.root_src) * jd.slot_stride, c0, c1, c2, c3);
-            } else if (jd.root_kind == K_TIP) {
-                const uint32_t code = (jd.root_src >= 0)
-                    ? jd.codes[static_cast<int64_t>(jd.root_src) * jd.ld_codes + pat] : 0xFu;
-                c0 = (code & 1u) ? 1.0 : 0.0; c1 = (code & 2u) ? 1.0 : 0.0;
-                c2 = (code & 4u) ? 1.0 : 0.0; c3 = (code & 8u) ? 1.0 : 0.0;
-            }
-            double site = fma(c3, mp.pi[3], fma(c2, mp.pi[2], fma(c1, mp.pi[1], c0 * mp.pi[0])));
-            site = (site < 1e-300) ? 1e-300 : site;  // np.maximum(site_like, 1e-300): NaN propagates
-            lsum = fma(log(site), jd.weights[pat], lsum);
         }
-        __syncthreads();  // everyone is done with code buffer `buf` before it is refilled
+    }
+
+    // root: site likelihood, clamp, log, weight  (reference :394-397)
+    double lsum = 0.0;
+    const int root_kind = jd.root_kind;
+    const int root_src = jd.root_src;
+    const double* weights = jd.weights;
+#pragma unroll
+    for (int u = 0; u < PPT; ++u) {
+        if (!active[u]) continue;
+        const int pat = p0 + tid + u * TPB;
+        Vec4 r = cur[u];
+        if (root_kind == K_MEM) {
+            ldg256(part0 + static_cast<int64_t>(root_src) * slot_stride + u * TPB * 4, r.x0, r.x1, r.x2, r.x3);
+        } else if (root_kind == K_TIP) {
+            const uint32_t c = (root_src >= 0) ? g_codes[static_cast<int64_t>(root_src) * ld_codes + pat] : 0x8Fu;
+            const uint32_t m = (c & 0x80u) ? (c & 0xFu) : (1u << c);
+            r = {(m & 1u) ? 1.0 : 0.0, (m & 2u) ? 1.0 : 0.0, (m & 4u) ? 1.0 : 0.0, (m & 8u) ? 1.0 : 0.0};
+        }
+        double site = fma(r.x3, mp.pi[3], fma(r.x2, mp.pi[2], fma(r.x1, mp.pi[1], r.x0 * mp.pi[0])));
+        site = (site < 1e-300) ? 1e-300 : site;  // np.maximum(site_like, 1e-300): NaN propagates
+        lsum = fma(log(site), weights[pat], lsum);
     }
 
     // fused per-locus reduction: tile sum -> last-arriving tile sums tiles in index order
     const double tsum = block_sum(lsum, red);
+    const int n_tiles = jd.n_tiles;
     if (tid == 0) {
         __stcg(&L.tile_sum[tile], tsum);
         __threadfence();
         const unsigned int prev = atomicAdd(&L.job_done[job], 1u);
-        s_is_last = (prev == static_cast<unsigned int>(jd.n_tiles) - 1u);
+        s_is_last = (prev == static_cast<unsigned int>(n_tiles) - 1u);
     }
     __syncthreads();
     if (s_is_last) {
         __threadfence();
         double s = 0.0;
-        for (int t = tid; t < jd.n_tiles; t += TPB) s += __ldcg(&L.tile_sum[jd.tile0 + t]);
+        for (int t = tid; t < n_tiles; t += TPB) s += __ldcg(&L.tile_sum[tile0 + t]);
         const double total = block_sum(s, red);
         if (tid == 0) {
             L.out[jd.out_index] = total;
