@@ -181,7 +181,7 @@ def oracle_time_loci(trees, alns, procs):
     if procs == 1:
         res = [_oracle_worker(parts[0])]
     else:
-        with mp.get_context("fork").Pool(procs) as pool:
+        with mp.get_context("spawn").Pool(procs) as pool:
             res = pool.map(_oracle_worker, parts)
     wall = max(r[0] for r in res)  # evaluation only; construction is excluded as in BASELINE.md
     ups = sum(r[1] for r in res)
@@ -303,20 +303,48 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    prune_ms, pm_ms, comp_ms = [], [], []
     ev0 = torch.cuda.Event(enable_timing=True)
     ev1 = torch.cuda.Event(enable_timing=True)
+    ctx.set_profiling(False)
     barrier()
     ev0.record(stream)
     for _ in range(args.steps):
         step_device()
-        # event queries only; they do not add work to the stream
-        tm = ctx.last_timings()
-        prune_ms.append(tm["prune_ms"]); pm_ms.append(tm["pmatrix_ms"]); comp_ms.append(tm["compile_ms"])
     ev1.record(stream)
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
     logL_device = out_vec.cpu().numpy().copy()
+
+    # ---- per-kernel durations: same steps again with CUDA events around each kernel launch ----
+    ctx.set_profiling(True)
+    prune_ms, pm_ms, comp_ms = [], [], []
+    for _ in range(args.steps):
+        step_device()
+        tm = ctx.last_timings()  # waits for this step's events
+        prune_ms.append(tm["prune_ms"]); pm_ms.append(tm["pmatrix_ms"]); comp_ms.append(tm["compile_ms"])
+    barrier()
+
+    # ---- score-only mode (PNB_EVAL_NOSTORE): same evaluation, partials never leave the SM ----
+    score_ms = None
+    if wl == "cfg2" or world == 1:
+        for c in calcs:
+            c.invalidate()
+        sflags = _lib.EVAL_NOSTORE
+        def step_score():
+            with torch.cuda.stream(stream):
+                ctx.eval(mh, handles, node_off, parent, blen, tip_row, 1.0, sflags, None, out_device_ptr=out_local_ptr)
+        for _ in range(3):
+            step_score()
+        barrier()
+        sk = []
+        for _ in range(args.steps):
+            step_score()
+            sk.append(ctx.last_timings()["prune_ms"])
+        barrier()
+        score_ms = float(np.mean(sk))
+        score_updates = ctx.last_stats()["updates"]
+        score_logL = out_vec.cpu().numpy().copy()
+    ctx.set_profiling(False)
 
     # ---- timed: end to end through the C ABI with host buffers ---------------------------
     for _ in range(2):
@@ -401,6 +429,11 @@ def main():
                 "host_compile_ms": float(np.mean(comp_ms)),
                 "note": "achieved uses the 96 B/update streaming model; the kernel keeps a node's freshly computed "
                         "child in registers, so its real DRAM traffic (`traffic`) is lower than algorithmic",
+            },
+            "score_only": None if score_ms is None else {
+                "what": "PNB_EVAL_NOSTORE: every node recomputed, no partial written to HBM (candidate scoring)",
+                "kernel_ms": score_ms, "updates_per_s_kernel": score_updates / (score_ms * 1e-3),
+                "logL_equal_to_store_mode": bool(np.array_equal(score_logL, logL_device)),
             },
             "clocks": clocks,
             "logL": total_logL,

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
+#include <atomic>
 #include <chrono>
 #include <cstdlib>
 #include <new>
@@ -164,6 +165,11 @@ extern "C" int pnb_ctx_create(int device, pnb_ctx** out) {
                   "sm_100a?", cudaGetErrorString(se));
         return PNB_ERR_CUDA;
     }
+    int workers = static_cast<int>(std::thread::hardware_concurrency());
+    if (const char* e = getenv("PNB_HOST_THREADS")) workers = atoi(e);
+    workers = std::max(1, std::min(workers, 32));
+    ctx->scratch.resize(workers);
+    if (workers > 1) ctx->pool = new (std::nothrow) WorkerPool(workers);
     *out = ctx;
     return PNB_OK;
 }
@@ -172,7 +178,9 @@ extern "C" int pnb_ctx_destroy(pnb_ctx* ctx) {
     if (!ctx) return PNB_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    if (ctx->h_stage.p) cudaFreeHost(ctx->h_stage.p);
+    delete ctx->pool;
+    for (auto& b : ctx->h_stage2) if (b.p) cudaFreeHost(b.p);
+    for (auto& e : ctx->stage_ev) if (e) cudaEventDestroy(e);
     if (ctx->h_out.p) cudaFreeHost(ctx->h_out.p);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     for (Buffer* b : {&ctx->d_stage, &ctx->d_P, &ctx->d_tile_sum, &ctx->d_job_done, &ctx->d_out})
@@ -486,59 +494,59 @@ namespace {
 constexpr int64_t REF_ABSENT = -1;   // leaf whose taxon is not in the alignment
 constexpr int64_t REF_COMPUTED = -3; // NOSTORE: recomputed node that has no slot
 
-struct JobOut {
-    int n_ops = 0;
-    int n_tip_ops = 0;
-    int root_kind = K_REG;
-    int root_src = 0;
-    int stk_need = 0;
-    int n_dirty = 0;
-    bool root_clean_cached = false;
-};
 
-// Compile one (locus, tree) job.  Writes ops / effective branch lengths (and
-// explicit P matrices) at the cursor; fills loc->pending in store mode.
-int compile_job(pnb_ctx* ctx, pnb_locus* loc, const pnb_model* m, int32_t n, const int32_t* parent,
+#define CJ_REQUIRE(cond, code, ...)                           \
+    do {                                                      \
+        if (!(cond)) {                                        \
+            snprintf(S.err, sizeof(S.err), __VA_ARGS__);      \
+            return (code);                                    \
+        }                                                     \
+    } while (0)
+
+// Compile one (locus, tree) job into ops / effective branch lengths (and explicit P matrices)
+// written at the job's fixed offset; fills loc->pending in store mode.  Thread-safe for
+// distinct loci (store mode) and for shared loci in NOSTORE mode (committed cache is read-only).
+int compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int32_t n, const int32_t* parent,
                 const double* blen, const int32_t* tip_row, const double* P_edge, double site_rate,
                 uint32_t flags, Op* ops, double* t_out, double* Pexp_out, JobOut* jo) {
     const bool nostore = flags & PNB_EVAL_NOSTORE;
     const bool full = flags & PNB_EVAL_FULL;
-    auto& cnt = ctx->s_child_cnt;
-    auto& off = ctx->s_child_off;
-    auto& kids = ctx->s_child;
-    auto& post = ctx->s_post;
-    auto& stk = ctx->s_stack;
-    auto& need = ctx->s_need;
-    auto& dirty = ctx->s_dirty;
-    auto& len = ctx->s_len;
-    auto& key = ctx->s_key;
+    auto& cnt = S.child_cnt;
+    auto& off = S.child_off;
+    auto& kids = S.child;
+    auto& post = S.post;
+    auto& stk = S.stack;
+    auto& need = S.need;
+    auto& dirty = S.dirty;
+    auto& len = S.len;
+    auto& key = S.key;
+    auto& ref = S.ref;
 
     cnt.assign(n, 0);
     int root = -1;
     for (int i = 0; i < n; ++i) {
         const int p = parent[i];
         if (p < 0) {
-            PNB_REQUIRE(root < 0, PNB_ERR_INVALID, "pnb_eval: tree has more than one root (nodes %d and %d)", root, i);
+            CJ_REQUIRE(root < 0, PNB_ERR_INVALID, "pnb_eval: tree has more than one root (nodes %d and %d)", root, i);
             root = i;
         } else {
-            PNB_REQUIRE(p < n && p != i, PNB_ERR_INVALID, "pnb_eval: parent[%d]=%d out of range", i, p);
+            CJ_REQUIRE(p < n && p != i, PNB_ERR_INVALID, "pnb_eval: parent[%d]=%d out of range", i, p);
             cnt[p]++;
         }
     }
-    PNB_REQUIRE(root >= 0, PNB_ERR_INVALID, "pnb_eval: tree has no root");
+    CJ_REQUIRE(root >= 0, PNB_ERR_INVALID, "pnb_eval: tree has no root");
     off.resize(n + 1);
     off[0] = 0;
     for (int i = 0; i < n; ++i) off[i + 1] = off[i] + cnt[i];
     kids.resize(n);
     {
-        std::vector<int32_t>& fill = ctx->s_order;
+        auto& fill = S.order;
         fill.assign(off.begin(), off.end() - 1);
         for (int i = 0; i < n; ++i)
             if (parent[i] >= 0) kids[fill[parent[i]]++] = i;
     }
     // post-order (iterative)
     post.clear();
-    post.reserve(n);
     stk.clear();
     stk.push_back(root);
     stk.push_back(0);
@@ -555,20 +563,20 @@ int compile_job(pnb_ctx* ctx, pnb_locus* loc, const pnb_model* m, int32_t n, con
             stk.pop_back();
         }
     }
-    PNB_REQUIRE(static_cast<int>(post.size()) == n, PNB_ERR_INVALID,
-                "pnb_eval: tree is not connected (reached %zu of %d nodes): cycle or forest", post.size(), n);
+    CJ_REQUIRE(static_cast<int>(post.size()) == n, PNB_ERR_INVALID,
+               "pnb_eval: tree is not connected (reached %zu of %d nodes): cycle or forest", post.size(), n);
 
     int n_internal = 0;
     for (int i = 0; i < n; ++i) n_internal += cnt[i] > 0;
 
     auto& C = loc->committed;
-    if (C.valid && C.model_id != m->id) locus_reset_cache(loc);  // partials of another model are useless
     if (!nostore) {
+        if (C.valid && C.model_id != m->id) locus_reset_cache(loc);  // partials of another model are useless
         if (full && !(flags & PNB_EVAL_PENDING)) locus_reset_cache(loc);
-        int rc = locus_ensure_slots(loc, n_internal);
-        if (rc) return rc;
+        S.rc_alloc = PNB_OK;
+        if (loc->n_slots < std::max(2 * n_internal, 2)) return PNB_ERR_STATE + 100;  // caller grows the slots serially
     }
-    const bool can_lookup = C.valid && !full;
+    const bool can_lookup = C.valid && !full && C.model_id == m->id;
     const int64_t n_rows = loc->n_rows;
 
     // effective branch lengths (reference :419-420 + clamp of p_matrix :241-242)
@@ -581,7 +589,7 @@ int compile_job(pnb_ctx* ctx, pnb_locus* loc, const pnb_model* m, int32_t n, con
         len[i] = dbits(t);
     }
 
-    std::vector<int64_t> ref(n);  // small; per job
+    ref.resize(n);
     dirty.assign(n, 0);
     need.assign(n, 0);
     auto& P_ = loc->pending;
@@ -598,8 +606,8 @@ int compile_job(pnb_ctx* ctx, pnb_locus* loc, const pnb_model* m, int32_t n, con
         const int k = cnt[v];
         if (k == 0) {
             const int r = tip_row ? tip_row[v] : -1;
-            PNB_REQUIRE(r < n_rows, PNB_ERR_INVALID, "pnb_eval: tip_row[%d]=%d but the locus has %lld rows", v, r,
-                        static_cast<long long>(n_rows));
+            CJ_REQUIRE(r < n_rows, PNB_ERR_INVALID, "pnb_eval: tip_row[%d]=%d but the locus has %lld rows", v, r,
+                       static_cast<long long>(n_rows));
             ref[v] = r >= 0 ? r : REF_ABSENT;
             if (!nostore) P_.node_ref[v] = ref[v];
             continue;
@@ -611,10 +619,14 @@ int compile_job(pnb_ctx* ctx, pnb_locus* loc, const pnb_model* m, int32_t n, con
             key.emplace_back(ref[c], len[c]);
             any_dirty |= dirty[c] != 0;
         }
-        std::sort(key.begin(), key.end());
+        if (k == 2) {
+            if (key[1] < key[0]) std::swap(key[0], key[1]);
+        } else {
+            std::sort(key.begin(), key.end());
+        }
         int hit = -1;
         if (can_lookup && !any_dirty) {
-            for (int j = 0; j < k && hit < 0; ++j) {
+            for (int j = 0; j < k; ++j) {
                 if (key[j].first < 0) continue;
                 const int q = C.parent_of[key[j].first];
                 if (q >= 0 && C.kid_count[q] == k) {
@@ -632,7 +644,7 @@ int compile_job(pnb_ctx* ctx, pnb_locus* loc, const pnb_model* m, int32_t n, con
             dirty[v] = 1;
             n_dirty++;
             if (!nostore) {
-                PNB_REQUIRE(!loc->free_slots.empty(), PNB_ERR_STATE, "pnb_eval: internal error: out of partial slots");
+                CJ_REQUIRE(!loc->free_slots.empty(), PNB_ERR_STATE, "pnb_eval: internal error: out of partial slots");
                 slot = loc->free_slots.back();
                 loc->free_slots.pop_back();
             }
@@ -650,19 +662,18 @@ int compile_job(pnb_ctx* ctx, pnb_locus* loc, const pnb_model* m, int32_t n, con
                 if (kv.first >= 0) P_.parent_of[kv.first] = slot;
             }
         }
-        // stash need: dirty internal kids sorted by need (descending); the last one is forwarded in registers
+        // stash need: recomputed internal kids are visited in order of decreasing need; the last one is
+        // forwarded in registers, every earlier one is stashed while its later siblings are computed
         if (dirty[v]) {
-            int kd = 0, mx = 0;
-            // selection by repeated max keeps this allocation-free; out-degree is tiny
-            // (need values are recomputed at emit time)
-            std::vector<int>& tmp = ctx->s_order;
+            auto& tmp = S.order;
             tmp.clear();
             for (int j = 0; j < k; ++j) {
                 const int c = kids[off[v] + j];
                 if (dirty[c]) tmp.push_back(need[c]);
             }
-            std::sort(tmp.begin(), tmp.end(), std::greater<int>());
-            kd = static_cast<int>(tmp.size());
+            const int kd = static_cast<int>(tmp.size());
+            if (kd > 1) std::sort(tmp.begin(), tmp.end(), std::greater<int>());
+            int mx = 0;
             for (int i = 0; i < kd; ++i) mx = std::max(mx, i + tmp[i]);
             need[v] = kd == 0 ? 0 : std::max(mx, kd - 1);
         }
@@ -672,36 +683,41 @@ int compile_job(pnb_ctx* ctx, pnb_locus* loc, const pnb_model* m, int32_t n, con
         P_.valid = true;
     }
 
-    // ---- emit ops: DFS over dirty internal nodes ------------------------
+    // ---- emit ops: DFS over recomputed internal nodes --------------------
     int n_ops = 0, n_tip_ops = 0;
     if (cnt[root] > 0 && dirty[root]) {
-        struct Frame { int v; int i; int sp; int push_idx; int kd; };
-        std::vector<Frame> fs;
-        std::vector<int> dk;  // per frame segment of dirty kids (sorted by need desc), stored contiguously
-        std::vector<int> dk_base;
+        auto& fs = S.frames;
+        auto& dk = S.dk;
+        auto& dk_base = S.dk_base;
+        fs.clear();
+        dk.clear();
+        dk_base.clear();
         auto open = [&](int v, int sp, int push_idx) {
             const int base = static_cast<int>(dk.size());
             for (int j = 0; j < cnt[v]; ++j) {
                 const int c = kids[off[v] + j];
                 if (dirty[c]) dk.push_back(c);
             }
-            std::stable_sort(dk.begin() + base, dk.end(), [&](int a, int b) { return need[a] > need[b]; });
+            if (dk.size() - base > 1)
+                std::stable_sort(dk.begin() + base, dk.end(), [&](int a, int b) { return need[a] > need[b]; });
             fs.push_back({v, 0, sp, push_idx, static_cast<int>(dk.size()) - base});
             dk_base.push_back(base);
         };
         open(root, 0, -1);
         while (!fs.empty()) {
-            Frame& f = fs.back();
             const int base = dk_base.back();
-            if (f.i < f.kd) {
-                const int d = dk[base + f.i];
-                const int i = f.i++;
-                const int sp = f.sp;
-                const int kd = f.kd;
-                open(d, sp + i, (nostore && i < kd - 1) ? sp + i : -1);
-                continue;
+            {
+                CompileScratch::Frame& f = fs.back();
+                if (f.i < f.kd) {
+                    const int d = dk[base + f.i];
+                    const int i = f.i++;
+                    const int sp = f.sp;
+                    const int kd = f.kd;
+                    open(d, sp + i, (nostore && i < kd - 1) ? sp + i : -1);
+                    continue;
+                }
             }
-            // all dirty kids emitted: node's own ops
+            const CompileScratch::Frame f = fs.back();
             const int v = f.v;
             const int first_op = n_ops;
             auto add = [&](uint32_t kind, int src, int aux, int c) {
@@ -740,7 +756,7 @@ int compile_job(pnb_ctx* ctx, pnb_locus* loc, const pnb_model* m, int32_t n, con
                 last.dst = static_cast<int>(ref[v] - n_rows);
             }
             if (f.push_idx >= 0) {
-                PNB_REQUIRE(f.push_idx < 256, PNB_ERR_UNSUPPORTED, "pnb_eval: stash depth %d exceeds 255", f.push_idx);
+                CJ_REQUIRE(f.push_idx < 256, PNB_ERR_UNSUPPORTED, "pnb_eval: stash depth %d exceeds 255", f.push_idx);
                 last.flags |= F_PUSH | (static_cast<uint32_t>(f.push_idx) << 8);
             }
             dk.resize(base);
@@ -817,9 +833,9 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
     PNB_REQUIRE(std::isfinite(site_rate), PNB_ERR_INVALID, "pnb_eval: site_rate is not finite");
     PNB_CUDA_TRY(cudaSetDevice(ctx->device));
 
-    // ---- pass 0: validate, size the staging regions ---------------------
+    // ---- pass 0: validate, size the staging regions, make sure partial slots exist ---------
     const uint32_t mark = ++ctx->batch_counter;
-    int64_t total_nodes = 0, total_tiles = 0;
+    int64_t total_tiles = 0;
     for (int64_t j = 0; j < M; ++j) {
         pnb_locus* loc = loci[j];
         PNB_REQUIRE(loc != nullptr, PNB_ERR_INVALID, "pnb_eval: loci[%lld] is NULL", static_cast<long long>(j));
@@ -836,27 +852,49 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
                         "pnb_eval: locus of job %lld has a pending evaluation; commit or roll back first",
                         static_cast<long long>(j));
             loc->batch_mark = mark;
+            // a tree with nn nodes has at most nn - 1 internal nodes (fewer in practice); slots grow rarely
+            if (loc->n_slots < std::max<int64_t>(2 * (nn - 1), 2)) {
+                int n_int = 0;
+                std::vector<uint8_t> has_kid(nn, 0);
+                const int32_t* par = parent + node_off[j];
+                for (int64_t i = 0; i < nn; ++i)
+                    if (par[i] >= 0 && par[i] < nn) has_kid[par[i]] = 1;
+                for (int64_t i = 0; i < nn; ++i) n_int += has_kid[i];
+                int rc0 = locus_ensure_slots(loc, n_int);
+                if (rc0) return rc0;
+            }
         }
-        total_nodes += nn;
         total_tiles += (loc->P + TILE_PATTERNS - 1) / TILE_PATTERNS;
     }
+    const int64_t total_nodes = node_off[M] - node_off[0];
     PNB_REQUIRE(total_nodes < (int64_t(1) << 31) && total_tiles < (int64_t(1) << 31), PNB_ERR_UNSUPPORTED,
                 "pnb_eval: batch too large (%lld nodes, %lld tiles)", static_cast<long long>(total_nodes),
                 static_cast<long long>(total_tiles));
+    // job j owns op slots [node_off[j] - node_off[0] - j, ...): a tree with nn nodes has at most nn - 1 edges
+    const int64_t ops_bound = total_nodes - M + 1;
 
     const size_t off_jobs = 0;
     const size_t off_tiles = align_up(off_jobs + static_cast<size_t>(M) * sizeof(JobDesc), 256);
     const size_t off_ops = align_up(off_tiles + static_cast<size_t>(total_tiles) * sizeof(int32_t), 256);
-    const size_t off_t = align_up(off_ops + static_cast<size_t>(total_nodes) * sizeof(Op), 256);
-    const size_t off_pexp = align_up(off_t + static_cast<size_t>(total_nodes) * sizeof(double), 256);
-    const size_t stage_bytes = off_pexp + (explicit_P ? static_cast<size_t>(total_nodes) * 128 : 0);
+    const size_t off_t = align_up(off_ops + static_cast<size_t>(ops_bound) * sizeof(Op), 256);
+    const size_t off_pexp = align_up(off_t + static_cast<size_t>(ops_bound) * sizeof(double), 256);
+    const size_t stage_bytes = off_pexp + (explicit_P ? static_cast<size_t>(ops_bound) * 128 : 0);
     int rc;
-    // the previous call's H2D copy must be complete before the pinned buffer is rewritten
-    PNB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    if ((rc = ensure_pinned(ctx->h_stage, stage_bytes))) return rc;
-    if ((rc = ensure_device(ctx->d_stage, stage_bytes))) return rc;
+    // two pinned staging buffers alternate: the one used two calls ago must have finished its H2D copy
+    const int sb = ctx->stage_idx;
+    ctx->stage_idx ^= 1;
+    if (ctx->stage_ev_valid[sb]) PNB_CUDA_TRY(cudaEventSynchronize(ctx->stage_ev[sb]));
+    if (ctx->h_stage2[sb].cap < stage_bytes) {
+        // growing frees the old pinned buffer: no copy may still read it
+        PNB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if ((rc = ensure_pinned(ctx->h_stage2[sb], stage_bytes))) return rc;
+    }
+    if (ctx->d_stage.cap < stage_bytes) {
+        PNB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if ((rc = ensure_device(ctx->d_stage, stage_bytes))) return rc;
+    }
     if ((rc = ensure_pinned(ctx->h_out, static_cast<size_t>(M) * 2 * sizeof(double)))) return rc;
-    char* hs = static_cast<char*>(ctx->h_stage.p);
+    char* hs = static_cast<char*>(ctx->h_stage2[sb].p);
     JobDesc* h_jobs = reinterpret_cast<JobDesc*>(hs + off_jobs);
     int32_t* h_tile_job = reinterpret_cast<int32_t*>(hs + off_tiles);
     Op* h_ops = reinterpret_cast<Op*>(hs + off_ops);
@@ -864,25 +902,58 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
     double* h_pexp = explicit_P ? reinterpret_cast<double*>(hs + off_pexp) : nullptr;
     double* h_out = static_cast<double*>(ctx->h_out.p);
 
-    // ---- pass 1: compile -------------------------------------------------
+    // ---- pass 1: compile (parallel over jobs for large batches) ---------------------------
     const auto t_comp0 = std::chrono::steady_clock::now();
-    int64_t n_jobs = 0, n_tiles = 0, n_ops = 0, updates = 0, n_cached = 0, n_dirty_nodes = 0;
+    ctx->job_out.resize(M);
+    JobOut* jout = ctx->job_out.data();
+    auto compile_range = [&](CompileScratch& S, int64_t j0, int64_t j1) {
+        for (int64_t j = j0; j < j1; ++j) {
+            pnb_locus* loc = loci[j];
+            const int64_t b = node_off[j];
+            const int32_t nn = static_cast<int32_t>(node_off[j + 1] - b);
+            const int64_t o = b - node_off[0] - j;
+            JobOut jo;
+            jo.rc = compile_job(S, loc, m, nn, parent + b, blen ? blen + b : nullptr, tip_row ? tip_row + b : nullptr,
+                                P_edge ? P_edge + b * 16 : nullptr, site_rate, flags, h_ops + o, h_t + o,
+                                h_pexp ? h_pexp + o * 16 : nullptr, &jo);
+            if (jo.rc != PNB_OK && S.first_err_job < 0) S.first_err_job = j;
+            jout[j] = jo;
+        }
+    };
+    const int n_workers = ctx->pool ? ctx->pool->size() : 0;
+    for (auto& S : ctx->scratch) S.first_err_job = -1;
+    if (M >= 256 && n_workers > 1) {
+        const int64_t grain = std::max<int64_t>(32, M / (n_workers * 8));
+        std::atomic<int64_t> next{0};
+        ctx->pool->run([&](int w) {
+            CompileScratch& S = ctx->scratch[w];
+            for (;;) {
+                const int64_t j0 = next.fetch_add(grain);
+                if (j0 >= M) break;
+                compile_range(S, j0, std::min(M, j0 + grain));
+            }
+        });
+    } else {
+        compile_range(ctx->scratch[0], 0, M);
+    }
+    for (auto& S : ctx->scratch) {
+        if (S.first_err_job >= 0) {
+            const int code = jout[S.first_err_job].rc;
+            set_error("%s (job %lld)", S.err, static_cast<long long>(S.first_err_job));
+            if (!nostore)
+                for (int64_t q = 0; q < M; ++q) locus_rollback(loci[q]);
+            return code >= 100 ? PNB_ERR_STATE : code;
+        }
+    }
+
+    // ---- pass 2: job descriptors, tile map (serial, cheap) ---------------------------------
+    int64_t n_jobs = 0, n_tiles = 0, n_ops_used = 0, updates = 0, n_cached = 0, n_dirty_nodes = 0, ops_hi = 0;
     int ops_cap = 1, rows_cap = 1, stk_cap = 0;
-    std::vector<int64_t> job_of_batch(M, -1);
+    auto& job_of_batch = ctx->job_of_batch;
+    job_of_batch.assign(M, -1);
     for (int64_t j = 0; j < M; ++j) {
         pnb_locus* loc = loci[j];
-        const int64_t b = node_off[j];
-        const int32_t nn = static_cast<int32_t>(node_off[j + 1] - b);
-        JobOut jo;
-        rc = compile_job(ctx, loc, m, nn, parent + b, blen ? blen + b : nullptr, tip_row ? tip_row + b : nullptr,
-                         P_edge ? P_edge + b * 16 : nullptr, site_rate, flags, h_ops + n_ops, h_t + n_ops,
-                         h_pexp ? h_pexp + n_ops * 16 : nullptr, &jo);
-        if (rc) {
-            // undo the pending state of every locus touched so far
-            if (!nostore)
-                for (int64_t q = 0; q <= j; ++q) locus_rollback(loci[q]);
-            return rc;
-        }
+        const JobOut& jo = jout[j];
         n_dirty_nodes += jo.n_dirty;
         if (loc->P == 0) {
             h_out[j] = 0.0;  // np.dot over zero patterns
@@ -895,6 +966,7 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
             n_cached++;
             continue;
         }
+        const int64_t o = node_off[j] - node_off[0] - j;
         JobDesc& jd = h_jobs[n_jobs];
         jd.codes = loc->d_codes;
         jd.partials = loc->d_partials;
@@ -902,7 +974,7 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
         jd.slot_stride = loc->P_pad * 4;
         jd.P = static_cast<int32_t>(loc->P);
         jd.ld_codes = static_cast<int32_t>(loc->P_pad);
-        jd.op_off = static_cast<int32_t>(n_ops);
+        jd.op_off = static_cast<int32_t>(o);
         jd.n_ops = jo.n_ops;
         jd.n_tip_ops = jo.n_tip_ops;
         jd.root_kind = jo.root_kind;
@@ -914,28 +986,32 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
         for (int t = 0; t < jd.n_tiles; ++t) h_tile_job[n_tiles + t] = static_cast<int32_t>(n_jobs);
         job_of_batch[j] = n_jobs;
         n_tiles += jd.n_tiles;
-        n_ops += jo.n_ops;
+        n_ops_used += jo.n_ops;
+        if (jo.n_ops > 0) ops_hi = std::max(ops_hi, o + jo.n_ops);
         updates += static_cast<int64_t>(jo.n_dirty) * loc->P;
         ops_cap = std::max(ops_cap, jo.n_ops);
         rows_cap = std::max(rows_cap, jo.n_tip_ops);
         stk_cap = std::max(stk_cap, jo.stk_need);
         n_jobs++;
     }
-
     ctx->t_compile_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_comp0).count();
+
     int64_t h2d = 0, d2h = 0, launches = 0;
+    auto fail_rollback = [&]() {
+        if (!nostore)
+            for (int64_t q = 0; q < M; ++q) locus_rollback(loci[q]);
+    };
     if (n_jobs > 0) {
         const size_t dyn_smem = static_cast<size_t>(ops_cap) * (sizeof(Op) + 128) +
                                 static_cast<size_t>(rows_cap) * TILE_PATTERNS +
                                 static_cast<size_t>(stk_cap) * TILE_PATTERNS * 32;
         if (dyn_smem > static_cast<size_t>(ctx->max_smem_optin - 1024)) {
-            if (!nostore)
-                for (int64_t q = 0; q < M; ++q) locus_rollback(loci[q]);
+            fail_rollback();
             set_error("pnb_eval: a tree program needs %zu bytes of shared memory (ops=%d, tip rows=%d, stash=%d); "
                       "limit is %d", dyn_smem, ops_cap, rows_cap, stk_cap, ctx->max_smem_optin - 1024);
             return PNB_ERR_UNSUPPORTED;
         }
-        if ((rc = ensure_device(ctx->d_P, static_cast<size_t>(std::max<int64_t>(n_ops, 1)) * 128))) return rc;
+        if ((rc = ensure_device(ctx->d_P, static_cast<size_t>(std::max<int64_t>(ops_hi, 1)) * 128))) return rc;
         if ((rc = ensure_device(ctx->d_tile_sum, static_cast<size_t>(n_tiles) * sizeof(double)))) return rc;
         if ((rc = ensure_device(ctx->d_out, static_cast<size_t>(M) * sizeof(double)))) return rc;
         if (ctx->d_job_done.cap < static_cast<size_t>(n_jobs) * sizeof(unsigned)) {
@@ -951,28 +1027,30 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
             PNB_CUDA_TRY(cudaMemcpyAsync(ds + off_jobs, hs + off_jobs, n_jobs * sizeof(JobDesc), cudaMemcpyHostToDevice, st));
             PNB_CUDA_TRY(cudaMemcpyAsync(ds + off_tiles, hs + off_tiles, n_tiles * sizeof(int32_t), cudaMemcpyHostToDevice, st));
             h2d += n_jobs * sizeof(JobDesc) + n_tiles * sizeof(int32_t);
-            if (n_ops > 0) {
-                PNB_CUDA_TRY(cudaMemcpyAsync(ds + off_ops, hs + off_ops, n_ops * sizeof(Op), cudaMemcpyHostToDevice, st));
-                h2d += n_ops * sizeof(Op);
+            if (ops_hi > 0) {
+                PNB_CUDA_TRY(cudaMemcpyAsync(ds + off_ops, hs + off_ops, ops_hi * sizeof(Op), cudaMemcpyHostToDevice, st));
+                h2d += ops_hi * sizeof(Op);
                 if (!explicit_P) {
-                    PNB_CUDA_TRY(cudaMemcpyAsync(ds + off_t, hs + off_t, n_ops * sizeof(double), cudaMemcpyHostToDevice, st));
-                    h2d += n_ops * sizeof(double);
+                    PNB_CUDA_TRY(cudaMemcpyAsync(ds + off_t, hs + off_t, ops_hi * sizeof(double), cudaMemcpyHostToDevice, st));
+                    h2d += ops_hi * sizeof(double);
                 }
             }
         }
-        if (n_ops > 0) {
-            if (explicit_P) {
-                PNB_CUDA_TRY(cudaMemcpyAsync(ctx->d_P.p, h_pexp, n_ops * 128, cudaMemcpyHostToDevice, st));
-                h2d += n_ops * 128;
-            } else {
-                const int64_t blocks = (n_ops + 127) / 128;
-                if (ctx->profiling) PNB_CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
-                pnb_pmatrix_kernel<<<static_cast<unsigned>(blocks), 128, 0, st>>>(
-                    m->mp, reinterpret_cast<const double*>(ds + off_t), n_ops, static_cast<double*>(ctx->d_P.p));
-                PNB_CUDA_TRY(cudaGetLastError());
-                if (ctx->profiling) { PNB_CUDA_TRY(cudaEventRecord(ctx->ev[1], st)); ctx->ev_ka = true; }
-                launches++;
-            }
+        if (ops_hi > 0 && explicit_P) {
+            PNB_CUDA_TRY(cudaMemcpyAsync(ctx->d_P.p, h_pexp, ops_hi * 128, cudaMemcpyHostToDevice, st));
+            h2d += ops_hi * 128;
+        }
+        if (!ctx->stage_ev[sb]) PNB_CUDA_TRY(cudaEventCreateWithFlags(&ctx->stage_ev[sb], cudaEventDisableTiming));
+        PNB_CUDA_TRY(cudaEventRecord(ctx->stage_ev[sb], st));
+        ctx->stage_ev_valid[sb] = true;
+        if (ops_hi > 0 && !explicit_P) {
+            const int64_t blocks = (ops_hi + 127) / 128;
+            if (ctx->profiling) PNB_CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
+            pnb_pmatrix_kernel<<<static_cast<unsigned>(blocks), 128, 0, st>>>(
+                m->mp, reinterpret_cast<const double*>(ds + off_t), ops_hi, static_cast<double*>(ctx->d_P.p));
+            PNB_CUDA_TRY(cudaGetLastError());
+            if (ctx->profiling) { PNB_CUDA_TRY(cudaEventRecord(ctx->ev[1], st)); ctx->ev_ka = true; }
+            launches++;
         }
         double* d_out = out_dev ? logL_out : static_cast<double*>(ctx->d_out.p);
         PruneLaunch L;
@@ -1002,8 +1080,7 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
             d2h += M * sizeof(double);
             cudaError_t e = cudaStreamSynchronize(st);
             if (e != cudaSuccess) {
-                if (!nostore)
-                    for (int64_t q = 0; q < M; ++q) locus_rollback(loci[q]);
+                fail_rollback();
                 set_error("pnb_eval: kernel execution failed: %s", cudaGetErrorString(e));
                 return PNB_ERR_CUDA;
             }
@@ -1029,7 +1106,7 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
 
     ctx->t_call_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call0).count();
     ctx->stats[0] = updates;
-    ctx->stats[1] = n_ops;
+    ctx->stats[1] = n_ops_used;
     ctx->stats[2] = n_tiles;
     ctx->stats[3] = launches;
     ctx->stats[4] = h2d;

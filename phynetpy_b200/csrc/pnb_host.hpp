@@ -4,8 +4,13 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <map>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -57,6 +62,92 @@ struct Buffer {
     size_t cap = 0;
 };
 
+// Result of compiling one (locus, tree) job into an op program.
+struct JobOut {
+    int rc = 0;
+    int n_ops = 0;
+    int n_tip_ops = 0;
+    int root_kind = 0;
+    int root_src = 0;
+    int stk_need = 0;
+    int n_dirty = 0;
+    bool root_clean_cached = false;
+};
+
+// Per-thread scratch of the tree compiler (no allocation in steady state).
+struct CompileScratch {
+    struct Frame { int v; int i; int sp; int push_idx; int kd; };
+    std::vector<int32_t> child_cnt, child_off, child, post, stack, need, order, dk, dk_base;
+    std::vector<uint8_t> dirty;
+    std::vector<uint64_t> len;
+    std::vector<int64_t> ref;
+    std::vector<std::pair<int64_t, uint64_t>> key;
+    std::vector<Frame> frames;
+    int64_t first_err_job = -1;
+    int rc_alloc = 0;
+    char err[512] = "";
+};
+
+// Minimal persistent worker pool: run(f) executes f(worker_index) on every worker (the caller
+// is worker 0) and returns when all are done.  Used to compile large batches of trees.
+class WorkerPool {
+  public:
+    explicit WorkerPool(int n) : n_(n < 1 ? 1 : n) {
+        for (int w = 1; w < n_; ++w) threads_.emplace_back([this, w] { loop(w); });
+    }
+    ~WorkerPool() {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            stop_ = true;
+            ++gen_;
+        }
+        cv_.notify_all();
+        for (auto& t : threads_) t.join();
+    }
+    int size() const { return n_; }
+    void run(const std::function<void(int)>& f) {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            fn_ = &f;
+            pending_ = n_ - 1;
+            ++gen_;
+        }
+        cv_.notify_all();
+        f(0);
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+
+  private:
+    void loop(int w) {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(int)>* f;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+                f = fn_;
+            }
+            (*f)(w);
+            {
+                std::lock_guard<std::mutex> g(m_);
+                if (--pending_ == 0) done_.notify_one();
+            }
+        }
+    }
+    int n_;
+    std::vector<std::thread> threads_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    const std::function<void(int)>* fn_ = nullptr;
+    uint64_t gen_ = 0;
+    int pending_ = 0;
+    bool stop_ = false;
+};
+
 }  // namespace pnb
 
 struct pnb_model {
@@ -74,7 +165,11 @@ struct pnb_ctx {
     uint64_t next_model_id = 1;
     uint32_t batch_counter = 0;
     pnb::Arena arena;
-    pnb::Buffer h_stage, d_stage;  // pinned host / device staging of the batch program
+    pnb::Buffer d_stage;           // device staging of the batch program (stream-ordered reuse)
+    pnb::Buffer h_stage2[2];       // pinned host staging, double-buffered so the host can run ahead
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};  // "H2D copy out of h_stage2[i] has completed"
+    bool stage_ev_valid[2] = {false, false};
+    int stage_idx = 0;
     pnb::Buffer d_P;               // [ops][16] P matrices (K-a output)
     pnb::Buffer d_tile_sum, d_job_done, d_out, h_out;
     size_t job_done_zeroed = 0;    // counters [0, job_done_zeroed) are known to be zero
@@ -84,11 +179,12 @@ struct pnb_ctx {
     bool ev_ka = false, ev_prune = false;
     double t_compile_ms = 0.0, t_call_ms = 0.0;
     int64_t n_loci_alive = 0;
-    // compile scratch (reused across calls)
-    std::vector<int32_t> s_child_cnt, s_child_off, s_child, s_post, s_stack, s_ref, s_need, s_order;
-    std::vector<uint8_t> s_dirty;
-    std::vector<uint64_t> s_len;
-    std::vector<std::pair<int64_t, uint64_t>> s_key;
+    // tree compiler: per-worker scratch, worker pool (lazily sized), per-call job results
+    std::vector<pnb::CompileScratch> scratch;
+    pnb::WorkerPool* pool = nullptr;
+    typedef pnb::JobOut JobOutRaw;
+    std::vector<pnb::JobOut> job_out;
+    std::vector<int64_t> job_of_batch;
 };
 
 struct pnb_locus {
