@@ -162,22 +162,23 @@ def oracle_time_single(codes, weights, ft, n_patterns, repeats):
 
 def _oracle_worker(args):
     from oracle import felsenstein_oracle as O
-    alns, trees = args
+    alns, trees, reps = args
     om = O.gtr(PI, RATES)
     loci = [O.OracleLocus({"t%d" % i: a[i].tobytes().decode() for i in range(a.shape[0])}) for a in alns]
     otrees = [O.OracleTree(t.parent.tolist(), [None if math.isnan(b) else float(b) for b in t.blen], t.label) for t in trees]
     t0 = time.perf_counter()
-    vals = [O.log_likelihood(l, t, om) for l, t in zip(loci, otrees)]
-    dt = time.perf_counter() - t0
+    for _ in range(reps):
+        vals = [O.log_likelihood(l, t, om) for l, t in zip(loci, otrees)]
+    dt = (time.perf_counter() - t0) / reps
     ups = sum(l.n_patterns * (len(t.parent) - sum(1 for c in t.children if not c)) for l, t in zip(loci, otrees))
     return dt, ups, vals
 
 
-def oracle_time_loci(trees, alns, procs):
+def oracle_time_loci(trees, alns, procs, reps=10):
     """Reference loop over loci (src/_mcmc_seq.py:746-750), loci split over host processes."""
     import multiprocessing as mp
     procs = max(1, min(procs, len(trees)))
-    parts = [(alns[i::procs], trees[i::procs]) for i in range(procs)]
+    parts = [(alns[i::procs], trees[i::procs], reps) for i in range(procs)]
     if procs == 1:
         res = [_oracle_worker(parts[0])]
     else:
@@ -254,7 +255,7 @@ def main():
         trees, alns = make_locus_data(M, spec["n"], spec["L"], {"cfg3": 3, "cfg4": 4, "cfg5": 5}[wl], lo, hi)
         taxa = ["t%d" % i for i in range(spec["n"])]
         calcs = [P.FelsensteinCalculator.from_matrix(taxa, a, device_compress=False) for a in alns]
-        cpu_sample = (trees[:64], alns[:64])
+        cpu_sample = (trees[:256], alns[:256])
         del alns
     for c in calcs:
         c._locus_handle()
@@ -264,8 +265,9 @@ def main():
     patterns_local = int(sum(c.n_patterns for c in calcs))
     setup["setup_s"] = round(time.perf_counter() - t_setup0, 2)
 
-    out_vec = torch.zeros(M, dtype=torch.float64, device="cuda")
-    out_local_ptr = out_vec.data_ptr() + 8 * lo
+    out_vec = torch.zeros(M, dtype=torch.float64, device="cuda")      # all-reduced per-locus logL
+    local_vec = torch.zeros(M, dtype=torch.float64, device="cuda") if world > 1 else out_vec
+    out_local_ptr = local_vec.data_ptr() + 8 * lo                      # the kernel writes this rank's slice
     flags = _lib.EVAL_FULL
 
     def step_device():
@@ -273,6 +275,7 @@ def main():
         with torch.cuda.stream(stream):
             ctx.eval(mh, handles, node_off, parent, blen, tip_row, 1.0, flags, None, out_device_ptr=out_local_ptr)
             if world > 1:
+                out_vec.copy_(local_vec)   # zeros outside this rank's range: the sum is exact
                 dist.all_reduce(out_vec)
 
     def step_e2e():
@@ -345,6 +348,11 @@ def main():
         score_updates = ctx.last_stats()["updates"]
         score_logL = out_vec.cpu().numpy().copy()
     ctx.set_profiling(False)
+
+    # ---- cfg4: MCMC chain steps with dirty-path recompute (one locus per proposal) -------------
+    chain = None
+    if wl == "cfg4" and world == 1:
+        chain = chain_steps(P, ctx, calcs, trees, model, n_steps=max(200, 20 * args.steps))
 
     # ---- timed: end to end through the C ABI with host buffers ---------------------------
     for _ in range(2):
@@ -435,6 +443,7 @@ def main():
                 "kernel_ms": score_ms, "updates_per_s_kernel": score_updates / (score_ms * 1e-3),
                 "logL_equal_to_store_mode": bool(np.array_equal(score_logL, logL_device)),
             },
+            "chain": chain,
             "clocks": clocks,
             "logL": total_logL,
             "logL_e2e": e2e_total,
@@ -448,6 +457,71 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def chain_steps(P, ctx, calcs, trees, model, n_steps, seed=4):
+    """BASELINE cfg4: a stream of single-locus proposals through the engine seam the sampler uses
+    (invalidate_locus -> log_likelihood -> accept | restore_caches).  Each proposal moves one
+    internal node's height (its two child branches and its parent branch change, as
+    op_gene_node_height does, reference src/_mcmc_seq.py:1020-1039), so the device recomputes
+    that node and its ancestors only.  Ends with a full recomputation of every locus, which must
+    reproduce the incrementally maintained total bit for bit."""
+    rng = np.random.default_rng(seed)
+    eng = P.SeqLikelihoodEngine(calcs, None, model, context=ctx)
+    cur = list(trees)
+    total = eng.log_likelihood(cur, None, 0.0)
+    eng._commit_pending()
+    M = len(cur)
+    nodes = cur[0].n_nodes
+    n_tips = (nodes + 1) // 2
+    upd, recomputed, accepted = 0, 0, 0
+    lat, c_ms = [], []
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        i = int(rng.integers(0, M))
+        ft = cur[i]
+        v = int(rng.integers(n_tips, nodes - 1))           # internal, non-root
+        kids = np.nonzero(ft.parent == v)[0]
+        room_dn = float(ft.blen[kids].min())
+        room_up = float(ft.blen[v])
+        delta = float(rng.uniform(-0.5 * room_dn, 0.5 * room_up))
+        bl = ft.blen.copy()
+        bl[kids] += delta
+        bl[v] -= delta
+        prop = list(cur)
+        prop[i] = ft.with_lengths(bl)
+        snap = eng.clone_caches()
+        eng.invalidate_locus(i)
+        s0 = time.perf_counter()
+        new_total = eng.log_likelihood(prop, None, 0.0)
+        lat.append(time.perf_counter() - s0)
+        c_ms.append(ctx.last_timings()["call_ms"])
+        upd += eng.last_stats["updates"]
+        recomputed += eng.last_stats["nodes_recomputed"]
+        if math.log(rng.random()) < (new_total - total):    # Metropolis on the likelihood alone
+            cur, total = prop, new_total
+            accepted += 1
+        else:
+            eng.restore_caches(snap)
+    wall = time.perf_counter() - t0
+    eng._commit_pending()
+    incremental = list(eng._felsen)
+    # full recomputation of the final state
+    for i in range(M):
+        eng.invalidate_locus(i)
+    eng.invalidate_device_cache()
+    full = eng.log_likelihood(cur, None, 0.0)
+    eng._commit_pending()
+    return {
+        "what": "single-locus node-height proposals through SeqLikelihoodEngine (dirty-path recompute, "
+                "commit on accept / rollback on reject), Python host loop included",
+        "steps": n_steps, "steps_per_s": n_steps / wall, "accept_rate": accepted / n_steps,
+        "mean_nodes_recomputed": recomputed / n_steps, "mean_updates_per_step": upd / n_steps,
+        "median_eval_latency_us": float(np.median(lat) * 1e6),
+        "median_c_abi_call_us": float(np.median(c_ms) * 1e3),
+        "full_recompute_total": full,
+        "per_locus_incremental_equals_full_recompute_bitwise": bool(incremental == list(eng._felsen)),
+    }
 
 
 def cpu_baseline(wl, spec, sample):
@@ -472,7 +546,7 @@ def cpu_baseline(wl, spec, sample):
     dt, ups = oracle_time_loci(trees, alns, procs)
     return {"value": ups / dt, "unit": "updates/s", "cores": procs, "kind": "port",
             "sample": "oracle (NumPy restatement of the reference loop src/_mcmc_seq.py:746-750) on the first %d loci, "
-                      "loci split over %d processes, evaluation only (construction excluded)" % (len(trees), procs),
+                      "loci split over %d processes, mean of 10 evaluations each (construction excluded)" % (len(trees), procs),
             "seconds_sample": dt}
 
 

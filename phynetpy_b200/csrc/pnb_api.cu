@@ -834,37 +834,74 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
     PNB_CUDA_TRY(cudaSetDevice(ctx->device));
 
     // ---- pass 0: validate, size the staging regions, make sure partial slots exist ---------
+    // (parallel over jobs for large batches: at 10^4 loci even this bookkeeping is milliseconds)
     const uint32_t mark = ++ctx->batch_counter;
+    const int n_workers = ctx->pool ? ctx->pool->size() : 0;
+    auto parallel_for = [&](int64_t n, int64_t min_parallel, const std::function<void(int, int64_t, int64_t)>& fn) {
+        if (n >= min_parallel && n_workers > 1) {
+            const int64_t grain = std::max<int64_t>(64, n / (n_workers * 4));
+            std::atomic<int64_t> next{0};
+            ctx->pool->run([&](int w) {
+                for (;;) {
+                    const int64_t a0 = next.fetch_add(grain);
+                    if (a0 >= n) break;
+                    fn(w, a0, std::min(n, a0 + grain));
+                }
+            });
+        } else {
+            fn(0, 0, n);
+        }
+    };
+    for (auto& S : ctx->scratch) { S.first_err_job = -1; S.tiles = 0; S.grow.clear(); }
+    parallel_for(M, 2048, [&](int w, int64_t j0, int64_t j1) {
+        CompileScratch& S = ctx->scratch[w];
+        auto fail = [&](int64_t j, int code, const char* msg) {
+            if (S.first_err_job < 0) { S.first_err_job = j; S.rc_alloc = code; snprintf(S.err, sizeof(S.err), "%s", msg); }
+        };
+        for (int64_t j = j0; j < j1; ++j) {
+            pnb_locus* loc = loci[j];
+            if (loc == nullptr) { fail(j, PNB_ERR_INVALID, "pnb_eval: NULL locus"); continue; }
+            if (loc->ctx != ctx) { fail(j, PNB_ERR_INVALID, "pnb_eval: locus belongs to another context"); continue; }
+            const int64_t nn = node_off[j + 1] - node_off[j];
+            if (nn < 1 || nn >= (1 << 24)) { fail(j, PNB_ERR_INVALID, "pnb_eval: job has an invalid node count"); continue; }
+            if (!nostore) {
+                if (loc->batch_mark.exchange(mark) == mark) {
+                    fail(j, PNB_ERR_INVALID, "pnb_eval: locus appears twice in a storing batch; use PNB_EVAL_NOSTORE");
+                    continue;
+                }
+                if (loc->has_pending) {
+                    fail(j, PNB_ERR_STATE, "pnb_eval: locus has a pending evaluation; commit or roll back first");
+                    continue;
+                }
+                // a tree with nn nodes has at most nn - 1 internal nodes; growing slots is rare and serial
+                if (loc->n_slots < std::max<int64_t>(2 * (nn - 1), 2)) S.grow.push_back(j);
+            }
+            S.tiles += (loc->P + TILE_PATTERNS - 1) / TILE_PATTERNS;
+        }
+    });
     int64_t total_tiles = 0;
-    for (int64_t j = 0; j < M; ++j) {
-        pnb_locus* loc = loci[j];
-        PNB_REQUIRE(loc != nullptr, PNB_ERR_INVALID, "pnb_eval: loci[%lld] is NULL", static_cast<long long>(j));
-        PNB_REQUIRE(loc->ctx == ctx, PNB_ERR_INVALID, "pnb_eval: loci[%lld] belongs to another context",
-                    static_cast<long long>(j));
-        const int64_t nn = node_off[j + 1] - node_off[j];
-        PNB_REQUIRE(nn >= 1 && nn < (1 << 24), PNB_ERR_INVALID, "pnb_eval: job %lld has %lld nodes",
-                    static_cast<long long>(j), static_cast<long long>(nn));
-        if (!nostore) {
-            PNB_REQUIRE(loc->batch_mark != mark, PNB_ERR_INVALID,
-                        "pnb_eval: locus appears twice in a storing batch (job %lld); use PNB_EVAL_NOSTORE",
-                        static_cast<long long>(j));
-            PNB_REQUIRE(!loc->has_pending, PNB_ERR_STATE,
-                        "pnb_eval: locus of job %lld has a pending evaluation; commit or roll back first",
-                        static_cast<long long>(j));
-            loc->batch_mark = mark;
-            // a tree with nn nodes has at most nn - 1 internal nodes (fewer in practice); slots grow rarely
-            if (loc->n_slots < std::max<int64_t>(2 * (nn - 1), 2)) {
-                int n_int = 0;
-                std::vector<uint8_t> has_kid(nn, 0);
-                const int32_t* par = parent + node_off[j];
-                for (int64_t i = 0; i < nn; ++i)
-                    if (par[i] >= 0 && par[i] < nn) has_kid[par[i]] = 1;
-                for (int64_t i = 0; i < nn; ++i) n_int += has_kid[i];
+    for (auto& S : ctx->scratch) {
+        if (S.first_err_job >= 0) {
+            set_error("%s (job %lld)", S.err, static_cast<long long>(S.first_err_job));
+            return S.rc_alloc;
+        }
+        total_tiles += S.tiles;
+    }
+    for (auto& S : ctx->scratch) {
+        for (int64_t j : S.grow) {
+            pnb_locus* loc = loci[j];
+            const int64_t nn = node_off[j + 1] - node_off[j];
+            const int32_t* par = parent + node_off[j];
+            std::vector<uint8_t> has_kid(nn, 0);
+            for (int64_t i = 0; i < nn; ++i)
+                if (par[i] >= 0 && par[i] < nn) has_kid[par[i]] = 1;
+            int n_int = 0;
+            for (int64_t i = 0; i < nn; ++i) n_int += has_kid[i];
+            if (loc->n_slots < std::max(2 * n_int, 2)) {
                 int rc0 = locus_ensure_slots(loc, n_int);
                 if (rc0) return rc0;
             }
         }
-        total_tiles += (loc->P + TILE_PATTERNS - 1) / TILE_PATTERNS;
     }
     const int64_t total_nodes = node_off[M] - node_off[0];
     PNB_REQUIRE(total_nodes < (int64_t(1) << 31) && total_tiles < (int64_t(1) << 31), PNB_ERR_UNSUPPORTED,
@@ -902,8 +939,8 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
     double* h_pexp = explicit_P ? reinterpret_cast<double*>(hs + off_pexp) : nullptr;
     double* h_out = static_cast<double*>(ctx->h_out.p);
 
-    // ---- pass 1: compile (parallel over jobs for large batches) ---------------------------
-    const auto t_comp0 = std::chrono::steady_clock::now();
+    // ---- passes 1-3, chunk by chunk: compile the chunk's trees (in parallel when large), fill
+    // its job descriptors, copy and launch it -- the GPU runs chunk c while the host compiles c+1.
     ctx->job_out.resize(M);
     JobOut* jout = ctx->job_out.data();
     auto compile_range = [&](CompileScratch& S, int64_t j0, int64_t j1) {
@@ -920,139 +957,157 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
             jout[j] = jo;
         }
     };
-    const int n_workers = ctx->pool ? ctx->pool->size() : 0;
-    for (auto& S : ctx->scratch) S.first_err_job = -1;
-    if (M >= 256 && n_workers > 1) {
-        const int64_t grain = std::max<int64_t>(32, M / (n_workers * 8));
-        std::atomic<int64_t> next{0};
-        ctx->pool->run([&](int w) {
-            CompileScratch& S = ctx->scratch[w];
-            for (;;) {
-                const int64_t j0 = next.fetch_add(grain);
-                if (j0 >= M) break;
-                compile_range(S, j0, std::min(M, j0 + grain));
-            }
-        });
-    } else {
-        compile_range(ctx->scratch[0], 0, M);
-    }
-    for (auto& S : ctx->scratch) {
-        if (S.first_err_job >= 0) {
-            const int code = jout[S.first_err_job].rc;
-            set_error("%s (job %lld)", S.err, static_cast<long long>(S.first_err_job));
-            if (!nostore)
-                for (int64_t q = 0; q < M; ++q) locus_rollback(loci[q]);
-            return code >= 100 ? PNB_ERR_STATE : code;
-        }
-    }
-
-    // ---- pass 2: job descriptors, tile map (serial, cheap) ---------------------------------
-    int64_t n_jobs = 0, n_tiles = 0, n_ops_used = 0, updates = 0, n_cached = 0, n_dirty_nodes = 0, ops_hi = 0;
-    int ops_cap = 1, rows_cap = 1, stk_cap = 0;
-    auto& job_of_batch = ctx->job_of_batch;
-    job_of_batch.assign(M, -1);
-    for (int64_t j = 0; j < M; ++j) {
-        pnb_locus* loc = loci[j];
-        const JobOut& jo = jout[j];
-        n_dirty_nodes += jo.n_dirty;
-        if (loc->P == 0) {
-            h_out[j] = 0.0;  // np.dot over zero patterns
-            if (!nostore) { loc->pending.logL = 0.0; loc->pending.logL_valid = true; }
-            continue;
-        }
-        if (jo.root_clean_cached && !out_dev) {
-            h_out[j] = loc->committed.logL;
-            if (!nostore) { loc->pending.logL = loc->committed.logL; loc->pending.logL_valid = true; }
-            n_cached++;
-            continue;
-        }
-        const int64_t o = node_off[j] - node_off[0] - j;
-        JobDesc& jd = h_jobs[n_jobs];
-        jd.codes = loc->d_codes;
-        jd.partials = loc->d_partials;
-        jd.weights = loc->d_weights;
-        jd.slot_stride = loc->P_pad * 4;
-        jd.P = static_cast<int32_t>(loc->P);
-        jd.ld_codes = static_cast<int32_t>(loc->P_pad);
-        jd.op_off = static_cast<int32_t>(o);
-        jd.n_ops = jo.n_ops;
-        jd.n_tip_ops = jo.n_tip_ops;
-        jd.root_kind = jo.root_kind;
-        jd.root_src = jo.root_src;
-        jd.tile0 = static_cast<int32_t>(n_tiles);
-        jd.n_tiles = static_cast<int32_t>((loc->P + TILE_PATTERNS - 1) / TILE_PATTERNS);
-        jd.out_index = static_cast<int32_t>(j);
-        jd.pad0 = jd.pad1 = 0;
-        for (int t = 0; t < jd.n_tiles; ++t) h_tile_job[n_tiles + t] = static_cast<int32_t>(n_jobs);
-        job_of_batch[j] = n_jobs;
-        n_tiles += jd.n_tiles;
-        n_ops_used += jo.n_ops;
-        if (jo.n_ops > 0) ops_hi = std::max(ops_hi, o + jo.n_ops);
-        updates += static_cast<int64_t>(jo.n_dirty) * loc->P;
-        ops_cap = std::max(ops_cap, jo.n_ops);
-        rows_cap = std::max(rows_cap, jo.n_tip_ops);
-        stk_cap = std::max(stk_cap, jo.stk_need);
-        n_jobs++;
-    }
-    ctx->t_compile_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_comp0).count();
-
-    int64_t h2d = 0, d2h = 0, launches = 0;
     auto fail_rollback = [&]() {
         if (!nostore)
             for (int64_t q = 0; q < M; ++q) locus_rollback(loci[q]);
     };
-    if (n_jobs > 0) {
+    const int64_t n_chunks = (total_nodes >= 32768) ? std::min<int64_t>(8, std::max<int64_t>(1, M / 256)) : 1;
+    if ((rc = ensure_device(ctx->d_P, static_cast<size_t>(std::max<int64_t>(ops_bound, 1)) * 128))) return rc;
+    if ((rc = ensure_device(ctx->d_tile_sum, static_cast<size_t>(std::max<int64_t>(total_tiles, 1)) * sizeof(double)))) return rc;
+    if ((rc = ensure_device(ctx->d_out, static_cast<size_t>(M) * sizeof(double)))) return rc;
+    if (ctx->d_job_done.cap < static_cast<size_t>(M) * sizeof(unsigned)) {
+        PNB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if ((rc = ensure_device(ctx->d_job_done, static_cast<size_t>(M) * sizeof(unsigned)))) return rc;
+        PNB_CUDA_TRY(cudaMemsetAsync(ctx->d_job_done.p, 0, ctx->d_job_done.cap, ctx->stream));
+    }
+    char* ds = static_cast<char*>(ctx->d_stage.p);
+    cudaStream_t st = ctx->stream;
+    double* d_out = out_dev ? logL_out : static_cast<double*>(ctx->d_out.p);
+
+    int64_t n_jobs = 0, n_tiles = 0, n_ops_used = 0, updates = 0, n_cached = 0, n_dirty_nodes = 0;
+    int64_t h2d = 0, d2h = 0, launches = 0;
+    double compile_ms = 0.0;
+    auto& job_of_batch = ctx->job_of_batch;
+    job_of_batch.assign(M, -1);
+    bool memset_done = false;
+    for (int64_t c = 0; c < n_chunks; ++c) {
+        const int64_t j0 = M * c / n_chunks, j1 = M * (c + 1) / n_chunks;
+        const auto t_comp0 = std::chrono::steady_clock::now();
+        for (auto& S : ctx->scratch) S.first_err_job = -1;
+        if ((node_off[j1] - node_off[j0]) >= 4096 && n_workers > 1) {
+            const int64_t grain = std::max<int64_t>(16, (j1 - j0) / (n_workers * 4));
+            std::atomic<int64_t> next{j0};
+            ctx->pool->run([&](int w) {
+                CompileScratch& S = ctx->scratch[w];
+                for (;;) {
+                    const int64_t a0 = next.fetch_add(grain);
+                    if (a0 >= j1) break;
+                    compile_range(S, a0, std::min(j1, a0 + grain));
+                }
+            });
+        } else {
+            compile_range(ctx->scratch[0], j0, j1);
+        }
+        for (auto& S : ctx->scratch) {
+            if (S.first_err_job >= 0) {
+                const int code = jout[S.first_err_job].rc;
+                set_error("%s (job %lld)", S.err, static_cast<long long>(S.first_err_job));
+                // loci compiled so far (all chunks up to this one) hold pending state: undo it
+                cudaStreamSynchronize(st);
+                fail_rollback();
+                return code >= 100 ? PNB_ERR_STATE : code;
+            }
+        }
+        // job descriptors + tile map of this chunk (serial, cheap); numbering is global
+        const int64_t jobs_first = n_jobs, tiles_first = n_tiles;
+        int64_t ops_lo = -1, ops_hi = 0;
+        int ops_cap = 1, rows_cap = 1, stk_cap = 0;
+        for (int64_t j = j0; j < j1; ++j) {
+            pnb_locus* loc = loci[j];
+            const JobOut& jo = jout[j];
+            n_dirty_nodes += jo.n_dirty;
+            if (loc->P == 0) {
+                h_out[j] = 0.0;  // np.dot over zero patterns
+                if (!nostore) { loc->pending.logL = 0.0; loc->pending.logL_valid = true; }
+                continue;
+            }
+            if (jo.root_clean_cached && !out_dev) {
+                h_out[j] = loc->committed.logL;
+                if (!nostore) { loc->pending.logL = loc->committed.logL; loc->pending.logL_valid = true; }
+                n_cached++;
+                continue;
+            }
+            const int64_t o = node_off[j] - node_off[0] - j;
+            JobDesc& jd = h_jobs[n_jobs];
+            jd.codes = loc->d_codes;
+            jd.partials = loc->d_partials;
+            jd.weights = loc->d_weights;
+            jd.slot_stride = loc->P_pad * 4;
+            jd.P = static_cast<int32_t>(loc->P);
+            jd.ld_codes = static_cast<int32_t>(loc->P_pad);
+            jd.op_off = static_cast<int32_t>(o);
+            jd.n_ops = jo.n_ops;
+            jd.n_tip_ops = jo.n_tip_ops;
+            jd.root_kind = jo.root_kind;
+            jd.root_src = jo.root_src;
+            jd.tile0 = static_cast<int32_t>(n_tiles);
+            jd.n_tiles = static_cast<int32_t>((loc->P + TILE_PATTERNS - 1) / TILE_PATTERNS);
+            jd.out_index = static_cast<int32_t>(j);
+            jd.pad0 = jd.pad1 = 0;
+            for (int t = 0; t < jd.n_tiles; ++t) h_tile_job[n_tiles + t] = static_cast<int32_t>(n_jobs);
+            job_of_batch[j] = n_jobs;
+            n_tiles += jd.n_tiles;
+            n_ops_used += jo.n_ops;
+            if (jo.n_ops > 0) {
+                if (ops_lo < 0) ops_lo = o;
+                ops_hi = std::max(ops_hi, o + jo.n_ops);
+            }
+            updates += static_cast<int64_t>(jo.n_dirty) * loc->P;
+            ops_cap = std::max(ops_cap, jo.n_ops);
+            rows_cap = std::max(rows_cap, jo.n_tip_ops);
+            stk_cap = std::max(stk_cap, jo.stk_need);
+            n_jobs++;
+        }
+        compile_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_comp0).count();
+        const int64_t cj = n_jobs - jobs_first, ct = n_tiles - tiles_first;
+        if (cj == 0) continue;
         const size_t dyn_smem = static_cast<size_t>(ops_cap) * (sizeof(Op) + 128) +
                                 static_cast<size_t>(rows_cap) * TILE_PATTERNS +
                                 static_cast<size_t>(stk_cap) * TILE_PATTERNS * 32;
         if (dyn_smem > static_cast<size_t>(ctx->max_smem_optin - 1024)) {
+            cudaStreamSynchronize(st);
             fail_rollback();
             set_error("pnb_eval: a tree program needs %zu bytes of shared memory (ops=%d, tip rows=%d, stash=%d); "
                       "limit is %d", dyn_smem, ops_cap, rows_cap, stk_cap, ctx->max_smem_optin - 1024);
             return PNB_ERR_UNSUPPORTED;
         }
-        if ((rc = ensure_device(ctx->d_P, static_cast<size_t>(std::max<int64_t>(ops_hi, 1)) * 128))) return rc;
-        if ((rc = ensure_device(ctx->d_tile_sum, static_cast<size_t>(n_tiles) * sizeof(double)))) return rc;
-        if ((rc = ensure_device(ctx->d_out, static_cast<size_t>(M) * sizeof(double)))) return rc;
-        if (ctx->d_job_done.cap < static_cast<size_t>(n_jobs) * sizeof(unsigned)) {
-            if ((rc = ensure_device(ctx->d_job_done, static_cast<size_t>(n_jobs) * sizeof(unsigned)))) return rc;
-            PNB_CUDA_TRY(cudaMemsetAsync(ctx->d_job_done.p, 0, ctx->d_job_done.cap, ctx->stream));
-        }
-        char* ds = static_cast<char*>(ctx->d_stage.p);
-        cudaStream_t st = ctx->stream;
-        if (stage_bytes <= (256u << 10)) {
+        const int64_t n_op_range = ops_lo < 0 ? 0 : ops_hi - ops_lo;
+        if (n_chunks == 1 && stage_bytes <= (256u << 10)) {
             PNB_CUDA_TRY(cudaMemcpyAsync(ds, hs, stage_bytes, cudaMemcpyHostToDevice, st));
             h2d += stage_bytes;
         } else {
-            PNB_CUDA_TRY(cudaMemcpyAsync(ds + off_jobs, hs + off_jobs, n_jobs * sizeof(JobDesc), cudaMemcpyHostToDevice, st));
-            PNB_CUDA_TRY(cudaMemcpyAsync(ds + off_tiles, hs + off_tiles, n_tiles * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-            h2d += n_jobs * sizeof(JobDesc) + n_tiles * sizeof(int32_t);
-            if (ops_hi > 0) {
-                PNB_CUDA_TRY(cudaMemcpyAsync(ds + off_ops, hs + off_ops, ops_hi * sizeof(Op), cudaMemcpyHostToDevice, st));
-                h2d += ops_hi * sizeof(Op);
+            PNB_CUDA_TRY(cudaMemcpyAsync(ds + off_jobs + jobs_first * sizeof(JobDesc), hs + off_jobs + jobs_first * sizeof(JobDesc),
+                                         cj * sizeof(JobDesc), cudaMemcpyHostToDevice, st));
+            PNB_CUDA_TRY(cudaMemcpyAsync(ds + off_tiles + tiles_first * sizeof(int32_t), hs + off_tiles + tiles_first * sizeof(int32_t),
+                                         ct * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+            h2d += cj * sizeof(JobDesc) + ct * sizeof(int32_t);
+            if (n_op_range > 0) {
+                PNB_CUDA_TRY(cudaMemcpyAsync(ds + off_ops + ops_lo * sizeof(Op), hs + off_ops + ops_lo * sizeof(Op),
+                                             n_op_range * sizeof(Op), cudaMemcpyHostToDevice, st));
+                h2d += n_op_range * sizeof(Op);
                 if (!explicit_P) {
-                    PNB_CUDA_TRY(cudaMemcpyAsync(ds + off_t, hs + off_t, ops_hi * sizeof(double), cudaMemcpyHostToDevice, st));
-                    h2d += ops_hi * sizeof(double);
+                    PNB_CUDA_TRY(cudaMemcpyAsync(ds + off_t + ops_lo * sizeof(double), hs + off_t + ops_lo * sizeof(double),
+                                                 n_op_range * sizeof(double), cudaMemcpyHostToDevice, st));
+                    h2d += n_op_range * sizeof(double);
                 }
             }
         }
-        if (ops_hi > 0 && explicit_P) {
-            PNB_CUDA_TRY(cudaMemcpyAsync(ctx->d_P.p, h_pexp, ops_hi * 128, cudaMemcpyHostToDevice, st));
-            h2d += ops_hi * 128;
+        if (n_op_range > 0 && explicit_P) {
+            PNB_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(ctx->d_P.p) + ops_lo * 128, h_pexp + ops_lo * 16, n_op_range * 128,
+                                         cudaMemcpyHostToDevice, st));
+            h2d += n_op_range * 128;
         }
-        if (!ctx->stage_ev[sb]) PNB_CUDA_TRY(cudaEventCreateWithFlags(&ctx->stage_ev[sb], cudaEventDisableTiming));
-        PNB_CUDA_TRY(cudaEventRecord(ctx->stage_ev[sb], st));
-        ctx->stage_ev_valid[sb] = true;
-        if (ops_hi > 0 && !explicit_P) {
-            const int64_t blocks = (ops_hi + 127) / 128;
-            if (ctx->profiling) PNB_CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
+        const bool prof = ctx->profiling && n_chunks == 1;
+        if (n_op_range > 0 && !explicit_P) {
+            const int64_t blocks = (n_op_range + 127) / 128;
+            if (prof) PNB_CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
             pnb_pmatrix_kernel<<<static_cast<unsigned>(blocks), 128, 0, st>>>(
-                m->mp, reinterpret_cast<const double*>(ds + off_t), ops_hi, static_cast<double*>(ctx->d_P.p));
+                m->mp, reinterpret_cast<const double*>(ds + off_t) + ops_lo, n_op_range,
+                static_cast<double*>(ctx->d_P.p) + ops_lo * 16);
             PNB_CUDA_TRY(cudaGetLastError());
-            if (ctx->profiling) { PNB_CUDA_TRY(cudaEventRecord(ctx->ev[1], st)); ctx->ev_ka = true; }
+            if (prof) { PNB_CUDA_TRY(cudaEventRecord(ctx->ev[1], st)); ctx->ev_ka = true; }
             launches++;
         }
-        double* d_out = out_dev ? logL_out : static_cast<double*>(ctx->d_out.p);
         PruneLaunch L;
         L.jobs = reinterpret_cast<const JobDesc*>(ds + off_jobs);
         L.tile_job = reinterpret_cast<const int32_t*>(ds + off_tiles);
@@ -1064,16 +1119,25 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
         L.ops_cap = ops_cap;
         L.rows_cap = rows_cap;
         L.stk_cap = stk_cap;
-        L.pad = 0;
-        if (out_dev && n_jobs < M) {
-            // jobs without device work (empty loci) still need their slot written
+        L.tile_base = static_cast<int32_t>(tiles_first);
+        if (out_dev && !memset_done) {
+            // jobs without device work (empty loci) still need their slot defined
             PNB_CUDA_TRY(cudaMemsetAsync(logL_out, 0, M * sizeof(double), st));
+            memset_done = true;
         }
-        if (ctx->profiling) PNB_CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
-        pnb_prune_kernel<<<static_cast<unsigned>(n_tiles), TPB, dyn_smem, st>>>(L, m->mp);
+        if (ctx->profiling && c == 0) PNB_CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
+        pnb_prune_kernel<<<static_cast<unsigned>(ct), TPB, dyn_smem, st>>>(L, m->mp);
         PNB_CUDA_TRY(cudaGetLastError());
-        if (ctx->profiling) { PNB_CUDA_TRY(cudaEventRecord(ctx->ev[3], st)); ctx->ev_prune = true; }
+        if (ctx->profiling && c == n_chunks - 1) { PNB_CUDA_TRY(cudaEventRecord(ctx->ev[3], st)); ctx->ev_prune = true; }
         launches++;
+    }
+    ctx->t_compile_ms = compile_ms;
+    if (h2d > 0) {  // the pinned buffer may be rewritten once every copy out of it has completed
+        if (!ctx->stage_ev[sb]) PNB_CUDA_TRY(cudaEventCreateWithFlags(&ctx->stage_ev[sb], cudaEventDisableTiming));
+        PNB_CUDA_TRY(cudaEventRecord(ctx->stage_ev[sb], st));
+        ctx->stage_ev_valid[sb] = true;
+    }
+    if (n_jobs > 0) {
         if (!out_dev) {
             double* got = h_out + M;  // second half of the pinned result buffer
             PNB_CUDA_TRY(cudaMemcpyAsync(got, d_out, M * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1088,21 +1152,23 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
                 if (job_of_batch[j] >= 0) h_out[j] = got[j];
         }
     } else if (out_dev) {
-        // everything was empty: define the output
+        // everything was empty or cached: define the output
         PNB_CUDA_TRY(cudaMemsetAsync(logL_out, 0, M * sizeof(double), ctx->stream));
     }
 
-    if (!out_dev) {
-        for (int64_t j = 0; j < M; ++j) {
-            logL_out[j] = h_out[j];
-            if (!nostore && job_of_batch[j] >= 0) {
-                loci[j]->pending.logL = h_out[j];
-                loci[j]->pending.logL_valid = true;
+    const bool auto_commit = !nostore && !(flags & PNB_EVAL_PENDING);
+    parallel_for(M, 2048, [&](int, int64_t j0, int64_t j1) {
+        for (int64_t j = j0; j < j1; ++j) {
+            if (!out_dev) {
+                logL_out[j] = h_out[j];
+                if (!nostore && job_of_batch[j] >= 0) {
+                    loci[j]->pending.logL = h_out[j];
+                    loci[j]->pending.logL_valid = true;
+                }
             }
+            if (auto_commit) locus_commit(loci[j]);
         }
-    }
-    if (!nostore && !(flags & PNB_EVAL_PENDING))
-        for (int64_t j = 0; j < M; ++j) locus_commit(loci[j]);
+    });
 
     ctx->t_call_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call0).count();
     ctx->stats[0] = updates;

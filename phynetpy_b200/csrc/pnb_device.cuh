@@ -90,7 +90,7 @@ struct PruneLaunch {
     int32_t ops_cap;           // smem capacity in ops
     int32_t rows_cap;          // smem capacity in staged code rows
     int32_t stk_cap;           // smem stash entries
-    int32_t pad;
+    int32_t tile_base;         // first tile of this launch (a batch may be launched in chunks)
 };
 
 #ifdef PNB_DEVICE_KERNELS  // kernel bodies: compiled into exactly one translation unit (pnb_api.cu)
@@ -279,7 +279,7 @@ pnb_prune_kernel(const __grid_constant__ PruneLaunch L, const __grid_constant__ 
     __shared__ int s_is_last;
 
     const int tid = threadIdx.x;
-    const int tile = blockIdx.x;
+    const int tile = blockIdx.x + L.tile_base;
     const int job = L.tile_job[tile];
     const JobDesc& jd = L.jobs[job];
     const int n_ops = jd.n_ops;

@@ -85,6 +85,8 @@ struct CompileScratch {
     std::vector<Frame> frames;
     int64_t first_err_job = -1;
     int rc_alloc = 0;
+    int64_t tiles = 0;            // pass-0 partial sums
+    std::vector<int64_t> grow;    // jobs whose locus needs more partial slots
     char err[512] = "";
 };
 
@@ -219,5 +221,5 @@ struct pnb_locus {
     TreeCache committed, pending;
     bool has_pending = false;
     std::vector<int32_t> free_slots;
-    uint32_t batch_mark = 0;  // duplicate detection inside one pnb_eval batch
+    std::atomic<uint32_t> batch_mark{0};  // duplicate detection inside one pnb_eval batch
 };

@@ -378,3 +378,46 @@ def test_large_locus_full_size_properties():
     dirty = fc.log_likelihood(ft2, model)
     assert fc._context().last_stats()["nodes_recomputed"] < n - 1
     assert dirty == fc.log_likelihood(ft2, model, full=True)
+
+
+def test_big_batch_chunked_parallel_compile_vs_oracle():
+    """A batch large enough for the chunked launch path + multi-threaded tree compilation
+    (>= 32768 nodes): per-locus results equal single-job evaluations bit for bit and the oracle
+    to 1e-10; then a one-branch change in EVERY locus (dirty path in every job) and a rollback."""
+    P = _pkg()
+    from phynetpy_b200 import simulate as S
+    rng = np.random.default_rng(123)
+    M, n, L = 640, 30, 90
+    par, bl = S.random_trees(M, n, rng, height=0.4)
+    aln = S.simulate_alignments(par, bl, L, S.DEFAULT_PI, S.DEFAULT_RATES, rng)
+    trees = S.flat_trees(par, bl)
+    taxa = S.tip_labels(n)
+    calcs = [P.FelsensteinCalculator.from_matrix(taxa, aln[i], device_compress=False) for i in range(M)]
+    model = P.GTR(S.DEFAULT_PI, S.DEFAULT_RATES)
+    eng = P.SeqLikelihoodEngine(calcs, None, model)
+    total = eng.log_likelihood(trees, None, 0.0)
+    assert eng.last_stats["launches"] >= 4  # chunked: several (K-a, prune) pairs
+    om = O.gtr(S.DEFAULT_PI, S.DEFAULT_RATES)
+    for i in list(range(0, M, 97)) + [M - 1]:
+        exp = O.log_likelihood(O.OracleLocus(S.to_alignment_dict(aln[i])), _otree(trees[i]), om)
+        assert rel_err(eng._felsen[i], exp) <= REL
+        solo = P.FelsensteinCalculator.from_matrix(taxa, aln[i], device_compress=False)
+        assert solo.log_likelihood(trees[i], model) == eng._felsen[i]
+        solo.close()
+    assert rel_err(total, sum(eng._felsen)) <= 1e-13
+    # dirty path in every locus at once
+    snap = eng.clone_caches()
+    new_trees = []
+    for i, t in enumerate(trees):
+        b = t.blen.copy()
+        b[i % n] *= 1.5
+        new_trees.append(t.with_lengths(b))
+        eng.invalidate_locus(i)
+    t2 = eng.log_likelihood(new_trees, None, 0.0)
+    assert eng.last_stats["nodes_recomputed"] < M * (n - 1) // 2
+    for i in (0, 333, M - 1):
+        exp = O.log_likelihood(O.OracleLocus(S.to_alignment_dict(aln[i])), _otree(new_trees[i]), om)
+        assert rel_err(eng._felsen[i], exp) <= REL
+    eng.restore_caches(snap)
+    assert eng.log_likelihood(trees, None, 0.0) == total
+    assert t2 != total
