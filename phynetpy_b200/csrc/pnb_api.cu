@@ -470,6 +470,9 @@ extern "C" int pnb_locus_read_partial(pnb_locus* loc, int32_t node, double* out)
     const int64_t ref = c.node_ref[node];
     if (ref >= loc->n_rows) {
         const int64_t slot = ref - loc->n_rows;
+        PNB_REQUIRE(c.stored[slot], PNB_ERR_STATE,
+                    "pnb_locus_read_partial: node %d is a tip-only node; those are recomputed from the tip codes, "
+                    "not kept in HBM", node);
         PNB_CUDA_TRY(cudaMemcpy(out, loc->d_partials + slot * loc->P_pad * 4,
                                 static_cast<size_t>(loc->P) * 4 * sizeof(double), cudaMemcpyDeviceToHost));
     } else if (ref >= 0) {
@@ -592,12 +595,25 @@ int compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int32_t n
     ref.resize(n);
     dirty.assign(n, 0);
     need.assign(n, 0);
+    // Tip-only internal nodes ("cherries") are VIRTUAL: their partial is a product of P columns selected
+    // by 1-byte tip codes, cheaper to recompute than to move 32 B/pattern through HBM.  They keep a slot
+    // id (identity in the cache keys) but are never written unless they must be held while a sibling is
+    // being computed, and never read back: whoever needs them recomputes them.
+    auto& virt = S.virt;
+    virt.assign(n, 0);
+    for (int v = 0; v < n; ++v) {
+        if (cnt[v] == 0) continue;
+        bool all_tips = true;
+        for (int j = 0; j < cnt[v] && all_tips; ++j) all_tips = cnt[kids[off[v] + j]] == 0;
+        virt[v] = all_tips;
+    }
     auto& P_ = loc->pending;
     if (!nostore) {
         P_.clear();
         P_.kid_begin.assign(loc->n_slots, -1);
         P_.kid_count.assign(loc->n_slots, 0);
         P_.parent_of.assign(n_rows + loc->n_slots, -1);
+        P_.stored.assign(loc->n_slots, 0);
         P_.node_ref.assign(n, REF_ABSENT);
         P_.model_id = m->id;
     }
@@ -654,6 +670,7 @@ int compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int32_t n
         } else {
             ref[v] = n_rows + slot;
             P_.node_ref[v] = ref[v];
+            P_.stored[slot] = hit >= 0 ? C.stored[hit] : 0;  // set to 1 when this evaluation writes it
             P_.kid_begin[slot] = static_cast<int32_t>(P_.kid_ref.size());
             P_.kid_count[slot] = k;
             for (auto& kv : key) {
@@ -669,7 +686,7 @@ int compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int32_t n
             tmp.clear();
             for (int j = 0; j < k; ++j) {
                 const int c = kids[off[v] + j];
-                if (dirty[c]) tmp.push_back(need[c]);
+                if (cnt[c] > 0 && (dirty[c] || virt[c])) tmp.push_back(need[c]);
             }
             const int kd = static_cast<int>(tmp.size());
             if (kd > 1) std::sort(tmp.begin(), tmp.end(), std::greater<int>());
@@ -683,23 +700,33 @@ int compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int32_t n
         P_.valid = true;
     }
 
-    // ---- emit ops: DFS over recomputed internal nodes --------------------
+    // ---- emit ops: DFS over the nodes that are computed in this evaluation ----
+    // R(X) = children of X computed now = recomputed stored nodes (largest stash need first) followed by
+    // virtual (tip-only) children, clean or not.  The LAST member of R(X) is forwarded in registers; the
+    // earlier ones are held in their HBM slot (store mode: written now, re-read from L2) or in the
+    // shared-memory stash (NOSTORE).
     int n_ops = 0, n_tip_ops = 0;
-    if (cnt[root] > 0 && dirty[root]) {
+    const bool compute_root = cnt[root] > 0 && (dirty[root] || virt[root]);
+    if (compute_root) {
         auto& fs = S.frames;
         auto& dk = S.dk;
         auto& dk_base = S.dk_base;
         fs.clear();
         dk.clear();
         dk_base.clear();
+        // frame.push_idx: >= 0 stash index (NOSTORE); -1 nothing; -2 must be written to its slot
         auto open = [&](int v, int sp, int push_idx) {
             const int base = static_cast<int>(dk.size());
             for (int j = 0; j < cnt[v]; ++j) {
                 const int c = kids[off[v] + j];
-                if (dirty[c]) dk.push_back(c);
+                if (cnt[c] > 0 && dirty[c] && !virt[c]) dk.push_back(c);
             }
             if (dk.size() - base > 1)
                 std::stable_sort(dk.begin() + base, dk.end(), [&](int a, int b) { return need[a] > need[b]; });
+            for (int j = 0; j < cnt[v]; ++j) {
+                const int c = kids[off[v] + j];
+                if (cnt[c] > 0 && virt[c]) dk.push_back(c);
+            }
             fs.push_back({v, 0, sp, push_idx, static_cast<int>(dk.size()) - base});
             dk_base.push_back(base);
         };
@@ -712,8 +739,10 @@ int compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int32_t n
                     const int d = dk[base + f.i];
                     const int i = f.i++;
                     const int sp = f.sp;
-                    const int kd = f.kd;
-                    open(d, sp + i, (nostore && i < kd - 1) ? sp + i : -1);
+                    const bool is_last = i == f.kd - 1;
+                    int disp = -1;
+                    if (!is_last) disp = nostore ? sp + i : -2;
+                    open(d, sp + i, disp);
                     continue;
                 }
             }
@@ -740,20 +769,21 @@ int compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int32_t n
             }
             for (int j = 0; j < cnt[v]; ++j) {
                 const int c = kids[off[v] + j];
-                if (dirty[c]) continue;
                 if (cnt[c] == 0) {
                     if (ref[c] >= 0) add(K_TIP, static_cast<int>(ref[c]), n_tip_ops++, c);
                     else add(K_TIP, -1, 0, c);
-                } else {
-                    add(K_MEM, static_cast<int>(ref[c] - n_rows), 0, c);
+                } else if (!dirty[c] && !virt[c]) {
+                    add(K_MEM, static_cast<int>(ref[c] - n_rows), 0, c);  // unchanged stored subtree
                 }
             }
             ops[first_op].flags |= F_FIRST;
             Op& last = ops[n_ops - 1];
             last.flags |= F_LAST;
-            if (!nostore) {
+            const bool write_slot = !nostore && ((!virt[v] && dirty[v]) || f.push_idx == -2);
+            if (write_slot) {
                 last.flags |= F_STORE;
                 last.dst = static_cast<int>(ref[v] - n_rows);
+                loc->pending.stored[last.dst] = 1;
             }
             if (f.push_idx >= 0) {
                 CJ_REQUIRE(f.push_idx < 256, PNB_ERR_UNSUPPORTED, "pnb_eval: stash depth %d exceeds 255", f.push_idx);
@@ -767,11 +797,11 @@ int compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int32_t n
     jo->n_ops = n_ops;
     jo->n_tip_ops = n_tip_ops;
     jo->n_dirty = n_dirty;
-    jo->stk_need = (nostore && cnt[root] > 0 && dirty[root]) ? need[root] : 0;
+    jo->stk_need = (nostore && compute_root) ? need[root] : 0;
     if (cnt[root] == 0) {
         jo->root_kind = K_TIP;
         jo->root_src = static_cast<int>(ref[root]);
-    } else if (dirty[root]) {
+    } else if (compute_root) {
         jo->root_kind = K_REG;
         jo->root_src = 0;
     } else {

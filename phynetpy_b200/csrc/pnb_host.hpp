@@ -78,7 +78,7 @@ struct JobOut {
 struct CompileScratch {
     struct Frame { int v; int i; int sp; int push_idx; int kd; };
     std::vector<int32_t> child_cnt, child_off, child, post, stack, need, order, dk, dk_base;
-    std::vector<uint8_t> dirty;
+    std::vector<uint8_t> dirty, virt;
     std::vector<uint64_t> len;
     std::vector<int64_t> ref;
     std::vector<std::pair<int64_t, uint64_t>> key;
@@ -209,13 +209,14 @@ struct pnb_locus {
         std::vector<uint64_t> kid_len;    // bit pattern of the effective branch length
         std::vector<int32_t> parent_of;   // per ref (n_rows + n_slots): slot of the node having it as child
         std::vector<int64_t> node_ref;    // per node of the tree as given by the caller
+        std::vector<uint8_t> stored;      // per slot: the partial is materialised in HBM
         int64_t root_ref = -2;
         bool logL_valid = false;
         double logL = 0.0;
         void clear() {
             valid = false; logL_valid = false; root_ref = -2;
             kid_begin.clear(); kid_count.clear(); kid_ref.clear(); kid_len.clear();
-            parent_of.clear(); node_ref.clear();
+            parent_of.clear(); node_ref.clear(); stored.clear();
         }
     };
     TreeCache committed, pending;

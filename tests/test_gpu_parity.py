@@ -135,9 +135,20 @@ def test_baseline_shapes_vs_oracle(n, L, seed):
     exp = O.log_likelihood(locus, _otree(ft), O.gtr(S.DEFAULT_PI, S.DEFAULT_RATES), sink=sink)
     assert rel_err(got, exp) <= REL
     # every internal node's partial, as stored in HBM, against the oracle's
+    # tip-only nodes ("cherries") are recomputed from the 1-byte codes instead of being kept in HBM
     nc = ft.n_children()
-    for node in np.nonzero(nc > 0)[0][:8]:
-        np.testing.assert_allclose(fc.node_partial(int(node)), sink[int(node)], rtol=1e-12, atol=0)
+    checked = 0
+    for node in np.nonzero(nc > 0)[0]:
+        kids = np.nonzero(ft.parent == node)[0]
+        try:
+            got_partial = fc.node_partial(int(node))
+        except P.PhyNetB200Error as e:
+            # only tip-only nodes may be absent (one that had to be held for a sibling IS materialised)
+            assert "tip-only" in str(e) and (nc[kids] == 0).all()
+            continue
+        np.testing.assert_allclose(got_partial, sink[int(node)], rtol=1e-12, atol=0)
+        checked += 1
+    assert checked >= (n - 1) // 3 or n <= 5
 
 
 def test_dirty_path_equals_full_recompute():
