@@ -379,6 +379,12 @@ static int locus_ensure_slots(pnb_locus* loc, int n_internal) {
     loc->d_partials = static_cast<double*>(p);
     loc->partials_bytes = bytes;
     loc->n_slots = want;
+    // lanes past the last pattern read and write the padding of a slot: make it defined
+    if (cudaMemsetAsync(p, 0, bytes, loc->ctx->stream) != cudaSuccess) {
+        (void)cudaGetLastError();
+        set_error("pnb_eval: cudaMemset of a partials buffer failed");
+        return PNB_ERR_CUDA;
+    }
     locus_reset_cache(loc);
     return PNB_OK;
 }
@@ -410,8 +416,9 @@ extern "C" int pnb_locus_create(pnb_ctx* ctx, int32_t n_rows, int64_t P, const u
         if (rc) { ctx->arena.release(loc->d_codes, loc->codes_bytes); delete loc; return rc; }
         loc->d_weights = static_cast<double*>(p);
         // host-side padded images.  Device tip code: a single state j is stored as j (the kernel
-        // reads column j of P directly); anything else as 0x80 | mask.  Padding = 0x80 (no state).
-        std::vector<uint8_t> hc(loc->codes_bytes, 0x80);
+        // reads column j of P directly); anything else as 0x80 | mask.  Padding = 0 (lanes past the last
+        // pattern follow the fast path on it; their results are never stored in a sum).
+        std::vector<uint8_t> hc(loc->codes_bytes, 0);
         for (int r = 0; r < n_rows; ++r) {
             const uint8_t* src = codes + static_cast<size_t>(r) * ld_codes;
             uint8_t* dst = hc.data() + static_cast<size_t>(r) * loc->P_pad;

@@ -225,20 +225,53 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 
 struct Vec4 { double x0, x1, x2, x3; };
 
-// v = P . l   (child_partials @ P.T, reference :425), P row-major in shared memory (broadcast reads)
-__device__ __forceinline__ void matvec(const double* __restrict__ Pk, const Vec4 (&l)[PPT], Vec4 (&v)[PPT]) {
-    const double2* P2 = reinterpret_cast<const double2*>(Pk);
+// Shared-memory accesses through explicit 32-bit shared addresses (ld.shared / st.shared): the
+// program walk is a chain of small dependent loads, and generic-pointer arithmetic was a third of
+// the instruction stream in the first version of this kernel (profiles/prune_r1_v2_cfg2_ncu.json).
+template <int OFF>
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(a), "n"(OFF));
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ void lds_v2f64(uint32_t a, double& x, double& y) {
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2+%3];" : "=d"(x), "=d"(y) : "r"(a), "n"(OFF));
+}
+__device__ __forceinline__ void sts_v2f64(uint32_t a, double x, double y) {
+    asm volatile("st.shared.v2.f64 [%0], {%1,%2};" :: "r"(a), "d"(x), "d"(y) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void lds_op(uint32_t a, uint32_t& f, int32_t& src, int32_t& dst, int32_t& aux) {
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(f), "=r"(src), "=r"(dst), "=r"(aux) : "r"(a));
+}
+
+// v = P . l   (child_partials @ P.T, reference :425); P row-major at shared address pk (broadcast reads).
+// OUT may alias nothing in `l`; ACCUM = multiply the result into `out` instead of overwriting it.
+template <bool ACCUM>
+__device__ __forceinline__ void matvec(uint32_t pk, const Vec4 (&l)[PPT], Vec4 (&out)[PPT]) {
+    double r[PPT][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const double2 pa = P2[i * 2 + 0];
-        const double2 pb = P2[i * 2 + 1];
+        double p0, p1, p2, p3;
+        if (i == 0) { lds_v2f64<0>(pk, p0, p1); lds_v2f64<16>(pk, p2, p3); }
+        else if (i == 1) { lds_v2f64<32>(pk, p0, p1); lds_v2f64<48>(pk, p2, p3); }
+        else if (i == 2) { lds_v2f64<64>(pk, p0, p1); lds_v2f64<80>(pk, p2, p3); }
+        else { lds_v2f64<96>(pk, p0, p1); lds_v2f64<112>(pk, p2, p3); }
 #pragma unroll
-        for (int u = 0; u < PPT; ++u) {
-            const double r = fma(pb.y, l[u].x3, fma(pb.x, l[u].x2, fma(pa.y, l[u].x1, pa.x * l[u].x0)));
-            if (i == 0) v[u].x0 = r;
-            else if (i == 1) v[u].x1 = r;
-            else if (i == 2) v[u].x2 = r;
-            else v[u].x3 = r;
+        for (int u = 0; u < PPT; ++u)
+            r[u][i] = fma(p3, l[u].x3, fma(p2, l[u].x2, fma(p1, l[u].x1, p0 * l[u].x0)));
+    }
+#pragma unroll
+    for (int u = 0; u < PPT; ++u) {
+        if (ACCUM) {
+            out[u].x0 *= r[u][0]; out[u].x1 *= r[u][1]; out[u].x2 *= r[u][2]; out[u].x3 *= r[u][3];
+        } else {
+            out[u].x0 = r[u][0]; out[u].x1 = r[u][1]; out[u].x2 = r[u][2]; out[u].x3 = r[u][3];
         }
     }
 }
@@ -246,16 +279,18 @@ __device__ __forceinline__ void matvec(const double* __restrict__ Pk, const Vec4
 // contribution of a tip child: column(s) of P selected by the device tip code
 //   code < 4        : the single state j = code           -> column j of P
 //   code & 0x80     : ambiguity / gap, low 4 bits = mask   -> sum of the allowed columns, in state order
-__device__ __forceinline__ void tip_contrib(const double* __restrict__ Pk, const uint32_t (&code)[PPT],
-                                            Vec4 (&v)[PPT]) {
+template <bool ACCUM>
+__device__ __forceinline__ void tip_contrib(uint32_t pk, const uint32_t (&code)[PPT], Vec4 (&out)[PPT]) {
     bool amb = false;
 #pragma unroll
     for (int u = 0; u < PPT; ++u) amb |= (code[u] & 0x80u) != 0;
     if (!__any_sync(0xffffffffu, amb)) {
 #pragma unroll
         for (int u = 0; u < PPT; ++u) {
-            const double* col = Pk + code[u];
-            v[u].x0 = col[0]; v[u].x1 = col[4]; v[u].x2 = col[8]; v[u].x3 = col[12];
+            const uint32_t col = pk + code[u] * 8u;
+            const double v0 = lds_f64<0>(col), v1 = lds_f64<32>(col), v2 = lds_f64<64>(col), v3 = lds_f64<96>(col);
+            if (ACCUM) { out[u].x0 *= v0; out[u].x1 *= v1; out[u].x2 *= v2; out[u].x3 *= v3; }
+            else { out[u].x0 = v0; out[u].x1 = v1; out[u].x2 = v2; out[u].x3 = v3; }
         }
     } else {
 #pragma unroll
@@ -264,9 +299,13 @@ __device__ __forceinline__ void tip_contrib(const double* __restrict__ Pk, const
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                if (m & (1u << j)) { s0 += Pk[0 + j]; s1 += Pk[4 + j]; s2 += Pk[8 + j]; s3 += Pk[12 + j]; }
+                if (m & (1u << j)) {
+                    const uint32_t col = pk + j * 8;
+                    s0 += lds_f64<0>(col); s1 += lds_f64<32>(col); s2 += lds_f64<64>(col); s3 += lds_f64<96>(col);
+                }
             }
-            v[u].x0 = s0; v[u].x1 = s1; v[u].x2 = s2; v[u].x3 = s3;
+            if (ACCUM) { out[u].x0 *= s0; out[u].x1 *= s1; out[u].x2 *= s2; out[u].x3 *= s3; }
+            else { out[u].x0 = s0; out[u].x1 = s1; out[u].x2 = s2; out[u].x3 = s3; }
         }
     }
 }
@@ -293,7 +332,7 @@ pnb_prune_kernel(const __grid_constant__ PruneLaunch L, const __grid_constant__ 
     Op* s_ops = reinterpret_cast<Op*>(smem_raw);
     double* s_P = reinterpret_cast<double*>(smem_raw + static_cast<size_t>(L.ops_cap) * sizeof(Op));
     unsigned char* s_codes = reinterpret_cast<unsigned char*>(s_P + static_cast<size_t>(L.ops_cap) * 16);
-    double2* s_stk = reinterpret_cast<double2*>(s_codes + static_cast<size_t>(L.rows_cap) * TILE_PATTERNS);
+    unsigned char* s_stk = s_codes + static_cast<size_t>(L.rows_cap) * TILE_PATTERNS;
 
     const int p0 = (tile - tile0) * TILE_PATTERNS;
     const Op* g_ops = L.ops + op_off;
@@ -324,82 +363,74 @@ pnb_prune_kernel(const __grid_constant__ PruneLaunch L, const __grid_constant__ 
         }
     }
 
-    // per-thread pattern bookkeeping while the copies are in flight
+    // per-thread bookkeeping while the copies are in flight.  Every array is padded to a multiple of
+    // the tile (codes with state 0, partial slots zero-filled), so lanes past the last pattern run the
+    // same instruction stream on padding and only the final weighted sum looks at `active`.
     const int64_t slot_stride = jd.slot_stride;
     double* part0 = jd.partials + static_cast<int64_t>(p0 + tid) * 4;
-    bool active[PPT];
-#pragma unroll
-    for (int u = 0; u < PPT; ++u) active[u] = (p0 + tid + u * TPB) < P;
-    const unsigned char* my_codes = s_codes + tid;
+    const bool warp_active = __any_sync(0xffffffffu, (p0 + tid) < P);
+    uint32_t op_addr = smem_u32(s_ops);
+    uint32_t pk = smem_u32(s_P);
+    const uint32_t codes_addr = smem_u32(s_codes) + tid;
+    const uint32_t stk_addr = smem_u32(s_stk) + tid * 16;
 
-    Vec4 cur[PPT];  // last completed node partial (register forwarding)
-    Vec4 acc[PPT];  // node under construction
+    Vec4 acc[PPT];  // node under construction; once complete it is also the register-forwarded child
 #pragma unroll
-    for (int u = 0; u < PPT; ++u) { cur[u] = {1.0, 1.0, 1.0, 1.0}; acc[u] = {1.0, 1.0, 1.0, 1.0}; }
+    for (int u = 0; u < PPT; ++u) acc[u] = {1.0, 1.0, 1.0, 1.0};
 
     mbar_wait(&bar_stage, 0);
 
-    // Warp-uniform guard (tip_contrib votes across the full warp): a warp runs the program if any of
-    // its lanes owns a pattern; lanes past the end compute on zero codes and never touch HBM.
-    if (__any_sync(0xffffffffu, active[0])) {
-        for (int k = 0; k < n_ops; ++k) {
-            const Op op = s_ops[k];
-            const double* Pk = s_P + k * 16;
-            const uint32_t kind = op.flags & F_KIND_MASK;
-            Vec4 v[PPT];
+    if (warp_active) {
+        for (int k = 0; k < n_ops; ++k, op_addr += 16, pk += 128) {
+            uint32_t flags;
+            int32_t src, dst, aux;
+            lds_op(op_addr, flags, src, dst, aux);
+            const uint32_t kind = flags & F_KIND_MASK;
+            const bool first = (flags & F_FIRST) != 0;
             if (kind == K_TIP) {
                 uint32_t code[PPT];
 #pragma unroll
-                for (int u = 0; u < PPT; ++u) {
-                    code[u] = 0u;
-                    if (active[u]) code[u] = (op.src >= 0) ? my_codes[op.aux * TILE_PATTERNS + u * TPB] : 0x8Fu;
-                }
-                tip_contrib(Pk, code, v);
+                for (int u = 0; u < PPT; ++u)
+                    code[u] = (src >= 0) ? lds_u8(codes_addr + aux * TILE_PATTERNS + u * TPB) : 0x8Fu;
+                if (first) tip_contrib<false>(pk, code, acc);
+                else tip_contrib<true>(pk, code, acc);
             } else if (kind == K_REG) {
-                matvec(Pk, cur, v);
-            } else {
-                Vec4 l[PPT];
-                if (kind == K_MEM) {
-                    const double* src = part0 + static_cast<int64_t>(op.src) * slot_stride;
-#pragma unroll
-                    for (int u = 0; u < PPT; ++u) {
-                        if (active[u]) ldg256(src + u * TPB * 4, l[u].x0, l[u].x1, l[u].x2, l[u].x3);
-                        else l[u] = {1.0, 1.0, 1.0, 1.0};
-                    }
-                } else {
-#pragma unroll
-                    for (int u = 0; u < PPT; ++u) {
-                        const double2 x = s_stk[(op.src * 2 + 0) * TILE_PATTERNS + u * TPB + tid];
-                        const double2 y = s_stk[(op.src * 2 + 1) * TILE_PATTERNS + u * TPB + tid];
-                        l[u] = {x.x, x.y, y.x, y.y};
-                    }
-                }
-                matvec(Pk, l, v);
-            }
-            if (op.flags & F_FIRST) {
+                // the child is the node completed just before: its partial is still in `acc`
+                // (the host always emits the forwarded child as the FIRST op of its parent)
+                Vec4 v[PPT];
+                matvec<false>(pk, acc, v);
 #pragma unroll
                 for (int u = 0; u < PPT; ++u) acc[u] = v[u];
             } else {
+                Vec4 l[PPT];
+                if (kind == K_MEM) {
+                    const double* g = part0 + static_cast<int64_t>(src) * slot_stride;
 #pragma unroll
-                for (int u = 0; u < PPT; ++u) {
-                    acc[u].x0 *= v[u].x0; acc[u].x1 *= v[u].x1; acc[u].x2 *= v[u].x2; acc[u].x3 *= v[u].x3;
-                }
-            }
-            if (op.flags & F_LAST) {
-#pragma unroll
-                for (int u = 0; u < PPT; ++u) cur[u] = acc[u];
-                if (op.flags & F_STORE) {
-                    double* dst = part0 + static_cast<int64_t>(op.dst) * slot_stride;
-#pragma unroll
-                    for (int u = 0; u < PPT; ++u)
-                        if (active[u]) stg256(dst + u * TPB * 4, cur[u].x0, cur[u].x1, cur[u].x2, cur[u].x3);
-                }
-                if (op.flags & F_PUSH) {
-                    const int si = (op.flags >> 8) & 0xff;
+                    for (int u = 0; u < PPT; ++u) ldg256(g + u * TPB * 4, l[u].x0, l[u].x1, l[u].x2, l[u].x3);
+                } else {
+                    const uint32_t a = stk_addr + static_cast<uint32_t>(src) * (TILE_PATTERNS * 32);
 #pragma unroll
                     for (int u = 0; u < PPT; ++u) {
-                        s_stk[(si * 2 + 0) * TILE_PATTERNS + u * TPB + tid] = make_double2(cur[u].x0, cur[u].x1);
-                        s_stk[(si * 2 + 1) * TILE_PATTERNS + u * TPB + tid] = make_double2(cur[u].x2, cur[u].x3);
+                        lds_v2f64<0>(a + u * TPB * 16, l[u].x0, l[u].x1);
+                        lds_v2f64<TILE_PATTERNS * 16>(a + u * TPB * 16, l[u].x2, l[u].x3);
+                    }
+                }
+                if (first) matvec<false>(pk, l, acc);
+                else matvec<true>(pk, l, acc);
+            }
+            if (flags & F_LAST) {
+                if (flags & F_STORE) {
+                    double* g = part0 + static_cast<int64_t>(dst) * slot_stride;
+#pragma unroll
+                    for (int u = 0; u < PPT; ++u)
+                        stg256(g + u * TPB * 4, acc[u].x0, acc[u].x1, acc[u].x2, acc[u].x3);
+                }
+                if (flags & F_PUSH) {
+                    const uint32_t a = stk_addr + ((flags >> 8) & 0xffu) * (TILE_PATTERNS * 32);
+#pragma unroll
+                    for (int u = 0; u < PPT; ++u) {
+                        sts_v2f64(a + u * TPB * 16, acc[u].x0, acc[u].x1);
+                        sts_v2f64(a + u * TPB * 16 + TILE_PATTERNS * 16, acc[u].x2, acc[u].x3);
                     }
                 }
             }
@@ -413,9 +444,9 @@ pnb_prune_kernel(const __grid_constant__ PruneLaunch L, const __grid_constant__ 
     const double* weights = jd.weights;
 #pragma unroll
     for (int u = 0; u < PPT; ++u) {
-        if (!active[u]) continue;
         const int pat = p0 + tid + u * TPB;
-        Vec4 r = cur[u];
+        if (pat >= P) continue;
+        Vec4 r = acc[u];
         if (root_kind == K_MEM) {
             ldg256(part0 + static_cast<int64_t>(root_src) * slot_stride + u * TPB * 4, r.x0, r.x1, r.x2, r.x3);
         } else if (root_kind == K_TIP) {
