@@ -270,17 +270,27 @@ def main():
     out_local_ptr = local_vec.data_ptr() + 8 * lo                      # the kernel writes this rank's slice
     flags = _lib.EVAL_FULL
 
+    # every step scores the same topologies with NEW branch lengths (a height-rescaling proposal):
+    # nothing of a previous step's result can be reused, and the host recompiles lengths each time
+    blens = [np.ascontiguousarray(blen * (1.0 + 0.002 * k)) for k in range(max(args.steps, 1))]
+    step_no = [0]
+
+    def next_blen():
+        b = blens[step_no[0] % len(blens)]
+        step_no[0] += 1
+        return b
+
     def step_device():
         """inputs resident in HBM; logL stays on the device; all-reduce when sharded"""
         with torch.cuda.stream(stream):
-            ctx.eval(mh, handles, node_off, parent, blen, tip_row, 1.0, flags, None, out_device_ptr=out_local_ptr)
+            ctx.eval(mh, handles, node_off, parent, next_blen(), tip_row, 1.0, flags, None, out_device_ptr=out_local_ptr)
             if world > 1:
                 out_vec.copy_(local_vec)   # zeros outside this rank's range: the sum is exact
                 dist.all_reduce(out_vec)
 
     def step_e2e():
         """the call a user makes: host trees in, host log-likelihoods out"""
-        vals = ctx.eval(mh, handles, node_off, parent, blen, tip_row, 1.0, flags, None)
+        vals = ctx.eval(mh, handles, node_off, parent, next_blen(), tip_row, 1.0, flags, None)
         if world > 1:
             v = torch.zeros(M, dtype=torch.float64)
             v[lo:hi] = torch.from_numpy(vals)
@@ -310,6 +320,7 @@ def main():
     ev1 = torch.cuda.Event(enable_timing=True)
     ctx.set_profiling(False)
     barrier()
+    step_no[0] = 0
     ev0.record(stream)
     for _ in range(args.steps):
         step_device()
@@ -335,11 +346,12 @@ def main():
         sflags = _lib.EVAL_NOSTORE
         def step_score():
             with torch.cuda.stream(stream):
-                ctx.eval(mh, handles, node_off, parent, blen, tip_row, 1.0, sflags, None, out_device_ptr=out_local_ptr)
+                ctx.eval(mh, handles, node_off, parent, next_blen(), tip_row, 1.0, sflags, None, out_device_ptr=out_local_ptr)
         for _ in range(3):
             step_score()
         barrier()
         sk = []
+        step_no[0] = 0
         for _ in range(args.steps):
             step_score()
             sk.append(ctx.last_timings()["prune_ms"])
@@ -358,6 +370,7 @@ def main():
     for _ in range(2):
         step_e2e()
     barrier()
+    step_no[0] = 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
         vals_e2e = step_e2e()
@@ -410,7 +423,8 @@ def main():
                 "loci": M, "taxa": spec["n"], "site_patterns_total": int(u[1]),
                 "updates_per_step": int(updates_total),
                 "model": "GTR pi=(.1,.2,.3,.4) rates=(1,2.5,.7,1.3,3.1,.9)",
-                "step": "full logL evaluation: P(t) of every branch + every internal node recomputed + root reduction"
+                "step": "full logL evaluation of a fresh proposal (same topologies, new branch lengths every step): "
+                        "P(t) of every branch + every internal node recomputed + root reduction"
                         + (" + NCCL all-reduce of the per-locus vector" if world > 1 else ""),
                 "parallelism": "loci sharded over %d GPU(s), one process per GPU" % world,
                 "l2": "working set per step (%.2f GB of partials written) exceeds the 126 MB L2; no flush needed"

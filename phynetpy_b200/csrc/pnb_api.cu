@@ -165,7 +165,12 @@ extern "C" int pnb_ctx_create(int device, pnb_ctx** out) {
                   "sm_100a?", cudaGetErrorString(se));
         return PNB_ERR_CUDA;
     }
+    // host workers for tree compilation: share the box's cores between the ranks of one node
     int workers = static_cast<int>(std::thread::hardware_concurrency());
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) {
+        const int lw = atoi(e);
+        if (lw > 1) workers = std::max(1, workers / lw);
+    }
     if (const char* e = getenv("PNB_HOST_THREADS")) workers = atoi(e);
     workers = std::max(1, std::min(workers, 32));
     ctx->scratch.resize(workers);
@@ -532,6 +537,53 @@ int compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int32_t n
     auto& key = S.key;
     auto& ref = S.ref;
 
+    auto& C = loc->committed;
+    if (!nostore) {
+        if (C.valid && C.model_id != m->id) locus_reset_cache(loc);  // partials of another model are useless
+        if (full && !(flags & PNB_EVAL_PENDING)) locus_reset_cache(loc);
+    }
+    const bool can_lookup = C.valid && !full && C.model_id == m->id;
+    // every node will be recomputed and (store mode) slots come off the free list in canonical order
+    const bool all_dirty_canonical = nostore ? !can_lookup : !C.valid;
+    auto eff_len = [&](int i) -> double {
+        double t = blen ? blen[i] : 0.0;  // reference :419-420 (None -> 0) + clamp of p_matrix :241-242
+        if (std::isnan(t)) t = 0.0;
+        t *= site_rate;
+        if (!(t >= 0.0)) t = 0.0;
+        return t;
+    };
+
+    // ---- fast path: same topology as the last all-dirty compilation of this locus --------------
+    pnb_locus::Template& T = loc->tmpl[nostore ? 1 : 0];
+    if (T.valid && all_dirty_canonical && T.n == n && (nostore || T.n_slots == loc->n_slots) &&
+        T.has_tip_row == (tip_row != nullptr) &&
+        memcmp(T.parent.data(), parent, static_cast<size_t>(n) * sizeof(int32_t)) == 0 &&
+        (!tip_row || memcmp(T.tip_row.data(), tip_row, static_cast<size_t>(n) * sizeof(int32_t)) == 0)) {
+        const int n_ops_t = T.jo.n_ops;
+        if (n_ops_t > 0) memcpy(ops, T.ops.data(), static_cast<size_t>(n_ops_t) * sizeof(Op));
+        for (int k = 0; k < n_ops_t; ++k) {
+            const int c = T.op_child[k];
+            t_out[k] = eff_len(c);
+            if (Pexp_out) memcpy(Pexp_out + static_cast<size_t>(k) * 16, P_edge + static_cast<size_t>(c) * 16, 128);
+        }
+        if (!nostore) {
+            auto& P_ = loc->pending;
+            P_ = T.cache;
+            const size_t ne = T.kid_child.size();
+            P_.kid_len.resize(ne);
+            for (size_t e = 0; e < ne; ++e) P_.kid_len[e] = dbits(eff_len(T.kid_child[e]));
+            P_.model_id = m->id;
+            P_.valid = true;
+            P_.logL_valid = false;
+            loc->free_slots.resize(static_cast<size_t>(loc->n_slots - T.slots_used));
+            loc->has_pending = true;
+        }
+        *jo = T.jo;
+        jo->rc = PNB_OK;
+        jo->root_clean_cached = false;
+        return PNB_OK;
+    }
+
     cnt.assign(n, 0);
     int root = -1;
     for (int i = 0; i < n; ++i) {
@@ -579,25 +631,14 @@ int compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int32_t n
     int n_internal = 0;
     for (int i = 0; i < n; ++i) n_internal += cnt[i] > 0;
 
-    auto& C = loc->committed;
     if (!nostore) {
-        if (C.valid && C.model_id != m->id) locus_reset_cache(loc);  // partials of another model are useless
-        if (full && !(flags & PNB_EVAL_PENDING)) locus_reset_cache(loc);
         S.rc_alloc = PNB_OK;
         if (loc->n_slots < std::max(2 * n_internal, 2)) return PNB_ERR_STATE + 100;  // caller grows the slots serially
     }
-    const bool can_lookup = C.valid && !full && C.model_id == m->id;
     const int64_t n_rows = loc->n_rows;
 
-    // effective branch lengths (reference :419-420 + clamp of p_matrix :241-242)
     len.resize(n);
-    for (int i = 0; i < n; ++i) {
-        double t = blen ? blen[i] : 0.0;
-        if (std::isnan(t)) t = 0.0;
-        t *= site_rate;
-        if (!(t >= 0.0)) t = 0.0;
-        len[i] = dbits(t);
-    }
+    for (int i = 0; i < n; ++i) len[i] = dbits(eff_len(i));
 
     ref.resize(n);
     dirty.assign(n, 0);
@@ -625,6 +666,9 @@ int compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int32_t n
         P_.model_id = m->id;
     }
     int n_dirty = 0;
+    bool templ_ok = true;
+    S.kid_child.clear();
+    S.op_child.clear();
     for (int v : post) {
         const int k = cnt[v];
         if (k == 0) {
@@ -639,24 +683,28 @@ int compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int32_t n
         bool any_dirty = false;
         for (int j = 0; j < k; ++j) {
             const int c = kids[off[v] + j];
-            key.emplace_back(ref[c], len[c]);
+            key.push_back({ref[c], len[c], c});
             any_dirty |= dirty[c] != 0;
         }
+        auto key_less = [](const CompileScratch::Key& a, const CompileScratch::Key& b) {
+            return a.ref != b.ref ? a.ref < b.ref : a.len < b.len;
+        };
         if (k == 2) {
-            if (key[1] < key[0]) std::swap(key[0], key[1]);
-        } else {
-            std::sort(key.begin(), key.end());
+            if (key_less(key[1], key[0])) std::swap(key[0], key[1]);
+        } else if (k > 2) {
+            std::sort(key.begin(), key.end(), key_less);
         }
+        for (int j = 0; j + 1 < k; ++j) templ_ok &= key[j].ref != key[j + 1].ref;  // order must not depend on lengths
         int hit = -1;
         if (can_lookup && !any_dirty) {
             for (int j = 0; j < k; ++j) {
-                if (key[j].first < 0) continue;
-                const int q = C.parent_of[key[j].first];
+                if (key[j].ref < 0) continue;
+                const int q = C.parent_of[key[j].ref];
                 if (q >= 0 && C.kid_count[q] == k) {
                     const int b = C.kid_begin[q];
                     bool same = true;
                     for (int x = 0; x < k && same; ++x)
-                        same = C.kid_ref[b + x] == key[x].first && C.kid_len[b + x] == key[x].second;
+                        same = C.kid_ref[b + x] == key[x].ref && C.kid_len[b + x] == key[x].len;
                     if (same) hit = q;
                 }
                 break;  // one probe is enough: every child has exactly one committed parent
@@ -681,9 +729,10 @@ int compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int32_t n
             P_.kid_begin[slot] = static_cast<int32_t>(P_.kid_ref.size());
             P_.kid_count[slot] = k;
             for (auto& kv : key) {
-                P_.kid_ref.push_back(kv.first);
-                P_.kid_len.push_back(kv.second);
-                if (kv.first >= 0) P_.parent_of[kv.first] = slot;
+                P_.kid_ref.push_back(kv.ref);
+                P_.kid_len.push_back(kv.len);
+                S.kid_child.push_back(kv.child);
+                if (kv.ref >= 0) P_.parent_of[kv.ref] = slot;
             }
         }
         // stash need: recomputed internal kids are visited in order of decreasing need; the last one is
@@ -766,6 +815,7 @@ int compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int32_t n
                 memcpy(&tt, &len[c], 8);
                 t_out[n_ops] = tt;
                 if (Pexp_out) memcpy(Pexp_out + static_cast<size_t>(n_ops) * 16, P_edge + static_cast<size_t>(c) * 16, 128);
+                S.op_child.push_back(c);
                 n_ops++;
             };
             if (f.kd > 0) add(K_REG, 0, 0, dk[base + f.kd - 1]);
@@ -817,6 +867,25 @@ int compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int32_t n
     }
     jo->root_clean_cached = cnt[root] > 0 && !dirty[root] && C.valid && C.logL_valid && C.root_ref == ref[root];
     if (!nostore) loc->has_pending = true;  // rollback re-derives the free slots from `committed`
+    // remember this program: the next all-dirty evaluation of the same topology only refreshes lengths
+    if (all_dirty_canonical && templ_ok && n_dirty == n_internal) {
+        T.valid = true;
+        T.n = n;
+        T.n_slots = loc->n_slots;
+        T.slots_used = nostore ? 0 : n_dirty;
+        T.has_tip_row = tip_row != nullptr;
+        T.parent.assign(parent, parent + n);
+        if (tip_row) T.tip_row.assign(tip_row, tip_row + n); else T.tip_row.clear();
+        T.ops.assign(ops, ops + n_ops);
+        T.op_child = S.op_child;
+        T.jo = *jo;
+        if (!nostore) {
+            T.cache = loc->pending;
+            T.kid_child = S.kid_child;
+        }
+    } else if (all_dirty_canonical) {
+        T.valid = false;
+    }
     return PNB_OK;
 }
 

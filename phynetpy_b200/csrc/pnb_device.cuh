@@ -24,7 +24,7 @@ namespace pnb {
 #define PNB_PPT 2
 #endif
 #ifndef PNB_MIN_BLOCKS
-#define PNB_MIN_BLOCKS 5
+#define PNB_MIN_BLOCKS 6
 #endif
 constexpr int TPB = PNB_TPB;        // threads per block
 constexpr int PPT = PNB_PPT;        // site patterns per thread (independent dependency chains)

@@ -81,7 +81,9 @@ struct CompileScratch {
     std::vector<uint8_t> dirty, virt;
     std::vector<uint64_t> len;
     std::vector<int64_t> ref;
-    std::vector<std::pair<int64_t, uint64_t>> key;
+    struct Key { int64_t ref; uint64_t len; int32_t child; };
+    std::vector<Key> key;
+    std::vector<int32_t> op_child, kid_child;
     std::vector<Frame> frames;
     int64_t first_err_job = -1;
     int rc_alloc = 0;
@@ -221,6 +223,21 @@ struct pnb_locus {
     };
     TreeCache committed, pending;
     bool has_pending = false;
+
+    // Compiled-program template of the last tree that was evaluated with EVERY node recomputed
+    // ([0] storing, [1] NOSTORE).  The op program depends on the topology only, so when the same
+    // topology comes back with all nodes to recompute (full evaluations, height rescalings, the
+    // 5 scale candidates of a coupled move) only the branch lengths are refreshed.
+    struct Template {
+        bool valid = false;
+        int32_t n = 0, n_slots = 0, slots_used = 0;
+        bool has_tip_row = false;
+        std::vector<int32_t> parent, tip_row, op_child, kid_child;
+        std::vector<pnb::Op> ops;
+        pnb::JobOut jo;
+        TreeCache cache;  // pending-cache image (store mode), kid_len refreshed per evaluation
+    };
+    Template tmpl[2];
     std::vector<int32_t> free_slots;
     std::atomic<uint32_t> batch_mark{0};  // duplicate detection inside one pnb_eval batch
 };

@@ -432,3 +432,52 @@ def test_big_batch_chunked_parallel_compile_vs_oracle():
     eng.restore_caches(snap)
     assert eng.log_likelihood(trees, None, 0.0) == total
     assert t2 != total
+
+
+def test_program_template_same_topology_new_lengths():
+    """All-dirty evaluations of an unchanged topology reuse the compiled op program and only refresh
+    branch lengths (host fast path).  Results must equal a cold evaluation bit for bit, the cache
+    left behind must support a correct dirty-path step, and NOSTORE scoring must agree."""
+    P = _pkg()
+    from phynetpy_b200 import simulate as S
+    rng = np.random.default_rng(314)
+    n = 14
+    par, bl = S.random_trees(1, n, rng, height=0.5)
+    aln = S.simulate_alignments(par, bl, 333, S.DEFAULT_PI, S.DEFAULT_RATES, rng)[0]
+    d = S.to_alignment_dict(aln)
+    ft = S.flat_trees(par, bl)[0]
+    model = P.GTR(S.DEFAULT_PI, S.DEFAULT_RATES)
+    om = O.gtr(S.DEFAULT_PI, S.DEFAULT_RATES)
+    locus = O.OracleLocus(d)
+    fc = P.FelsensteinCalculator(d)
+    ctx = fc._context()
+    for k, scale in enumerate([1.0, 0.25, 0.5, 2.0, 4.0, 1.0]):   # the coupled moves' height scales
+        t = ft.with_lengths(ft.blen * scale)
+        got = fc.log_likelihood(t, model, full=True)
+        assert ctx.last_stats()["nodes_recomputed"] == n - 1
+        cold = P.FelsensteinCalculator(d)
+        assert cold.log_likelihood(t, model) == got
+        cold.close()
+        assert rel_err(got, O.log_likelihood(locus, _otree(t), om)) <= REL
+    # the cache image restored from the template describes the LAST tree: a one-branch change is a short path
+    b2 = ft.blen.copy()
+    b2[3] *= 1.3
+    t2 = ft.with_lengths(b2)
+    got = fc.log_likelihood(t2, model)
+    assert 0 < ctx.last_stats()["nodes_recomputed"] < n - 1
+    assert rel_err(got, O.log_likelihood(locus, _otree(t2), om)) <= REL
+    # NOSTORE template: candidates that rescale every height
+    eng = P.SeqLikelihoodEngine([d], None, model)
+    eng.log_likelihood([ft], None, 0.0)
+    cands = [ft.with_lengths(ft.blen * s) for s in (0.25, 0.5, 2.0, 4.0, 0.25)]
+    vals = eng.score_candidates(0, cands)
+    for t, v in zip(cands, vals):
+        assert rel_err(v, O.log_likelihood(locus, _otree(t), om)) <= REL
+    assert vals[0] == vals[4]
+    # a polytomy with two absent taxa below one node (equal child refs): still correct
+    gt = P.GeneTree.from_newick("((t0:0.1,zz1:0.2,zz2:0.05):0.1,(t1:0.1,t2:0.3):0.2,t3:0.2);")
+    for scale in (1.0, 2.0, 0.5):
+        t = gt.flat()
+        t = t.with_lengths(t.blen * scale)
+        got = fc.log_likelihood(t, model, full=True)
+        assert rel_err(got, O.log_likelihood(locus, _otree(t), om)) <= REL
