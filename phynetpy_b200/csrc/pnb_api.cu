@@ -166,13 +166,17 @@ extern "C" int pnb_ctx_create(int device, pnb_ctx** out) {
         return PNB_ERR_CUDA;
     }
     // host workers for tree compilation: share the box's cores between the ranks of one node
-    int workers = static_cast<int>(std::thread::hardware_concurrency());
+    // Half of the cores at most (the CUDA driver, NCCL and the caller's own threads need the rest:
+    // a descheduled worker stalls a whole batch), divided between the ranks of the node.
+    int workers = static_cast<int>(std::thread::hardware_concurrency()) / 2;
     if (const char* e = getenv("LOCAL_WORLD_SIZE")) {
         const int lw = atoi(e);
-        if (lw > 1) workers = std::max(1, workers / lw);
+        if (lw > 1) workers /= lw;
     }
+    workers = std::min(workers, 8);
     if (const char* e = getenv("PNB_HOST_THREADS")) workers = atoi(e);
     workers = std::max(1, std::min(workers, 32));
+    if (const char* e = getenv("PNB_CHUNK_MIN_JOBS")) ctx->chunk_min_jobs = std::max(2, atoi(e));
     ctx->scratch.resize(workers);
     if (workers > 1) ctx->pool = new (std::nothrow) WorkerPool(workers);
     *out = ctx;
@@ -959,7 +963,7 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
         }
     };
     for (auto& S : ctx->scratch) { S.first_err_job = -1; S.tiles = 0; S.grow.clear(); }
-    parallel_for(M, 2048, [&](int w, int64_t j0, int64_t j1) {
+    parallel_for(M, 4096, [&](int w, int64_t j0, int64_t j1) {
         CompileScratch& S = ctx->scratch[w];
         auto fail = [&](int64_t j, int code, const char* msg) {
             if (S.first_err_job < 0) { S.first_err_job = j; S.rc_alloc = code; snprintf(S.err, sizeof(S.err), "%s", msg); }
@@ -1045,6 +1049,7 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
     double* h_pexp = explicit_P ? reinterpret_cast<double*>(hs + off_pexp) : nullptr;
     double* h_out = static_cast<double*>(ctx->h_out.p);
 
+    const bool auto_commit = !nostore && !(flags & PNB_EVAL_PENDING);
     // ---- passes 1-3, chunk by chunk: compile the chunk's trees (in parallel when large), fill
     // its job descriptors, copy and launch it -- the GPU runs chunk c while the host compiles c+1.
     ctx->job_out.resize(M);
@@ -1060,14 +1065,23 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
                                 P_edge ? P_edge + b * 16 : nullptr, site_rate, flags, h_ops + o, h_t + o,
                                 h_pexp ? h_pexp + o * 16 : nullptr, &jo);
             if (jo.rc != PNB_OK && S.first_err_job < 0) S.first_err_job = j;
+            if (jo.rc == PNB_OK && auto_commit) {
+                // host bookkeeping only (which slot holds which node); independent of the GPU finishing
+                if (jo.root_clean_cached) jo.cached_logL = loc->committed.logL;
+                locus_commit(loc);
+            }
             jout[j] = jo;
         }
     };
     auto fail_rollback = [&]() {
-        if (!nostore)
-            for (int64_t q = 0; q < M; ++q) locus_rollback(loci[q]);
+        if (nostore) return;
+        // auto-commit batches have already published their new trees: drop those caches entirely
+        for (int64_t q = 0; q < M; ++q) {
+            if (auto_commit) locus_reset_cache(loci[q]);
+            else locus_rollback(loci[q]);
+        }
     };
-    const int64_t n_chunks = (total_nodes >= 32768) ? std::min<int64_t>(8, std::max<int64_t>(1, M / 256)) : 1;
+    const int64_t n_chunks = (M >= ctx->chunk_min_jobs) ? std::max<int64_t>(1, std::min<int64_t>(8, 2 * M / ctx->chunk_min_jobs)) : 1;
     if ((rc = ensure_device(ctx->d_P, static_cast<size_t>(std::max<int64_t>(ops_bound, 1)) * 128))) return rc;
     if ((rc = ensure_device(ctx->d_tile_sum, static_cast<size_t>(std::max<int64_t>(total_tiles, 1)) * sizeof(double)))) return rc;
     if ((rc = ensure_device(ctx->d_out, static_cast<size_t>(M) * sizeof(double)))) return rc;
@@ -1122,14 +1136,16 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
             pnb_locus* loc = loci[j];
             const JobOut& jo = jout[j];
             n_dirty_nodes += jo.n_dirty;
+            pnb_locus::TreeCache* tc = nostore ? nullptr : (auto_commit ? &loc->committed : &loc->pending);
             if (loc->P == 0) {
                 h_out[j] = 0.0;  // np.dot over zero patterns
-                if (!nostore) { loc->pending.logL = 0.0; loc->pending.logL_valid = true; }
+                if (tc) { tc->logL = 0.0; tc->logL_valid = true; }
                 continue;
             }
             if (jo.root_clean_cached && !out_dev) {
-                h_out[j] = loc->committed.logL;
-                if (!nostore) { loc->pending.logL = loc->committed.logL; loc->pending.logL_valid = true; }
+                const double v = auto_commit ? jo.cached_logL : loc->committed.logL;
+                h_out[j] = v;
+                if (tc) { tc->logL = v; tc->logL_valid = true; }
                 n_cached++;
                 continue;
             }
@@ -1262,19 +1278,16 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
         PNB_CUDA_TRY(cudaMemsetAsync(logL_out, 0, M * sizeof(double), ctx->stream));
     }
 
-    const bool auto_commit = !nostore && !(flags & PNB_EVAL_PENDING);
-    parallel_for(M, 2048, [&](int, int64_t j0, int64_t j1) {
-        for (int64_t j = j0; j < j1; ++j) {
-            if (!out_dev) {
-                logL_out[j] = h_out[j];
-                if (!nostore && job_of_batch[j] >= 0) {
-                    loci[j]->pending.logL = h_out[j];
-                    loci[j]->pending.logL_valid = true;
-                }
+    if (!out_dev) {
+        for (int64_t j = 0; j < M; ++j) {
+            logL_out[j] = h_out[j];
+            if (!nostore && job_of_batch[j] >= 0) {
+                pnb_locus::TreeCache& tc = auto_commit ? loci[j]->committed : loci[j]->pending;
+                tc.logL = h_out[j];
+                tc.logL_valid = true;
             }
-            if (auto_commit) locus_commit(loci[j]);
         }
-    });
+    }
 
     ctx->t_call_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call0).count();
     ctx->stats[0] = updates;

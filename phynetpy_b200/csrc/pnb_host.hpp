@@ -72,6 +72,7 @@ struct JobOut {
     int stk_need = 0;
     int n_dirty = 0;
     bool root_clean_cached = false;
+    double cached_logL = 0.0;   // committed logL captured before an in-worker commit
 };
 
 // Per-thread scratch of the tree compiler (no allocation in steady state).
@@ -93,63 +94,74 @@ struct CompileScratch {
 };
 
 // Minimal persistent worker pool: run(f) executes f(worker_index) on every worker (the caller
-// is worker 0) and returns when all are done.  Used to compile large batches of trees.
+// is worker 0) and returns when all are done.  Used to compile large batches of trees.  Workers
+// spin briefly after a task before sleeping: evaluations arrive back to back in an MCMC loop and a
+// futex wake-up (tens of microseconds) would cost more than compiling a few hundred trees.
 class WorkerPool {
   public:
     explicit WorkerPool(int n) : n_(n < 1 ? 1 : n) {
         for (int w = 1; w < n_; ++w) threads_.emplace_back([this, w] { loop(w); });
     }
     ~WorkerPool() {
+        stop_.store(true, std::memory_order_release);
+        gen_.fetch_add(1, std::memory_order_release);
         {
             std::lock_guard<std::mutex> g(m_);
-            stop_ = true;
-            ++gen_;
+            cv_.notify_all();
         }
-        cv_.notify_all();
         for (auto& t : threads_) t.join();
     }
     int size() const { return n_; }
     void run(const std::function<void(int)>& f) {
+        fn_ = &f;
+        pending_.store(n_ - 1, std::memory_order_relaxed);
+        gen_.fetch_add(1, std::memory_order_release);
         {
             std::lock_guard<std::mutex> g(m_);
-            fn_ = &f;
-            pending_ = n_ - 1;
-            ++gen_;
+            if (sleepers_ > 0) cv_.notify_all();
         }
-        cv_.notify_all();
         f(0);
-        std::unique_lock<std::mutex> lk(m_);
-        done_.wait(lk, [this] { return pending_ == 0; });
+        int spins = 0;
+        while (pending_.load(std::memory_order_acquire) != 0) {
+            if (++spins > 4096) std::this_thread::yield();
+        }
         fn_ = nullptr;
     }
 
   private:
+    static constexpr int kSpin = 20000;  // ~50 us of polling before a worker goes to sleep
     void loop(int w) {
         uint64_t seen = 0;
         for (;;) {
-            const std::function<void(int)>* f;
-            {
-                std::unique_lock<std::mutex> lk(m_);
-                cv_.wait(lk, [&] { return gen_ != seen; });
-                seen = gen_;
-                if (stop_) return;
-                f = fn_;
+            int spins = 0;
+            while (gen_.load(std::memory_order_acquire) == seen) {
+                if (++spins < kSpin) {
+#if defined(__x86_64__)
+                    __builtin_ia32_pause();
+#endif
+                } else {
+                    std::unique_lock<std::mutex> lk(m_);
+                    ++sleepers_;
+                    cv_.wait(lk, [&] { return gen_.load(std::memory_order_acquire) != seen; });
+                    --sleepers_;
+                }
             }
-            (*f)(w);
-            {
-                std::lock_guard<std::mutex> g(m_);
-                if (--pending_ == 0) done_.notify_one();
-            }
+            seen = gen_.load(std::memory_order_acquire);
+            if (stop_.load(std::memory_order_acquire)) return;
+            const std::function<void(int)>* f = fn_;
+            if (f) (*f)(w);
+            pending_.fetch_sub(1, std::memory_order_release);
         }
     }
     int n_;
     std::vector<std::thread> threads_;
     std::mutex m_;
-    std::condition_variable cv_, done_;
-    const std::function<void(int)>* fn_ = nullptr;
-    uint64_t gen_ = 0;
-    int pending_ = 0;
-    bool stop_ = false;
+    std::condition_variable cv_;
+    const std::function<void(int)>* volatile fn_ = nullptr;
+    std::atomic<uint64_t> gen_{0};
+    std::atomic<int> pending_{0};
+    std::atomic<bool> stop_{false};
+    int sleepers_ = 0;  // guarded by m_
 };
 
 }  // namespace pnb
@@ -168,6 +180,7 @@ struct pnb_ctx {
     int max_smem_optin = 0;
     uint64_t next_model_id = 1;
     uint32_t batch_counter = 0;
+    int chunk_min_jobs = 2048;     // batches of at least this many jobs are launched in chunks
     pnb::Arena arena;
     pnb::Buffer d_stage;           // device staging of the batch program (stream-ordered reuse)
     pnb::Buffer h_stage2[2];       // pinned host staging, double-buffered so the host can run ahead

@@ -12,6 +12,10 @@ import sys
 
 import pytest
 
+# read once when the device context is created: make the GPU tests exercise the chunked launch path
+# with batches of a few hundred loci instead of thousands
+os.environ.setdefault("PNB_CHUNK_MIN_JOBS", "256")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
