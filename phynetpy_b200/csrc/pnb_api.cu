@@ -166,14 +166,14 @@ extern "C" int pnb_ctx_create(int device, pnb_ctx** out) {
         return PNB_ERR_CUDA;
     }
     // host workers for tree compilation: share the box's cores between the ranks of one node
-    // Half of the cores at most (the CUDA driver, NCCL and the caller's own threads need the rest:
-    // a descheduled worker stalls a whole batch), divided between the ranks of the node.
-    int workers = static_cast<int>(std::thread::hardware_concurrency()) / 2;
+    // Host workers for tree compilation: the node's cores divided between its ranks, minus one per rank
+    // for the CUDA driver / NCCL / the caller's own threads (a descheduled worker stalls a whole batch).
+    int workers = static_cast<int>(std::thread::hardware_concurrency());
     if (const char* e = getenv("LOCAL_WORLD_SIZE")) {
         const int lw = atoi(e);
         if (lw > 1) workers /= lw;
     }
-    workers = std::min(workers, 8);
+    workers = std::min(workers - 1, 8);  // leave a core per rank to the driver / NCCL / caller threads
     if (const char* e = getenv("PNB_HOST_THREADS")) workers = atoi(e);
     workers = std::max(1, std::min(workers, 32));
     if (const char* e = getenv("PNB_CHUNK_MIN_JOBS")) ctx->chunk_min_jobs = std::max(2, atoi(e));
@@ -359,6 +359,7 @@ extern "C" int pnb_compress(pnb_ctx* ctx, int use_device, const uint8_t* cols, i
 // locus
 // =====================================================================
 static void locus_free_partials(pnb_locus* loc) {
+    loc->committed_from_tmpl = loc->pending_from_tmpl = false;
     if (loc->d_partials) loc->ctx->arena.release(loc->d_partials, loc->partials_bytes);
     loc->d_partials = nullptr;
     loc->partials_bytes = 0;
@@ -373,6 +374,7 @@ static void locus_reset_cache(pnb_locus* loc) {
     loc->committed.clear();
     loc->pending.clear();
     loc->has_pending = false;
+    loc->committed_from_tmpl = loc->pending_from_tmpl = false;
     loc->free_slots.resize(loc->n_slots);
     for (int s = 0; s < loc->n_slots; ++s) loc->free_slots[s] = loc->n_slots - 1 - s;
 }
@@ -542,13 +544,6 @@ int compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int32_t n
     auto& ref = S.ref;
 
     auto& C = loc->committed;
-    if (!nostore) {
-        if (C.valid && C.model_id != m->id) locus_reset_cache(loc);  // partials of another model are useless
-        if (full && !(flags & PNB_EVAL_PENDING)) locus_reset_cache(loc);
-    }
-    const bool can_lookup = C.valid && !full && C.model_id == m->id;
-    // every node will be recomputed and (store mode) slots come off the free list in canonical order
-    const bool all_dirty_canonical = nostore ? !can_lookup : !C.valid;
     auto eff_len = [&](int i) -> double {
         double t = blen ? blen[i] : 0.0;  // reference :419-420 (None -> 0) + clamp of p_matrix :241-242
         if (std::isnan(t)) t = 0.0;
@@ -556,13 +551,12 @@ int compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int32_t n
         if (!(t >= 0.0)) t = 0.0;
         return t;
     };
-
-    // ---- fast path: same topology as the last all-dirty compilation of this locus --------------
-    pnb_locus::Template& T = loc->tmpl[nostore ? 1 : 0];
-    if (T.valid && all_dirty_canonical && T.n == n && (nostore || T.n_slots == loc->n_slots) &&
-        T.has_tip_row == (tip_row != nullptr) &&
-        memcmp(T.parent.data(), parent, static_cast<size_t>(n) * sizeof(int32_t)) == 0 &&
-        (!tip_row || memcmp(T.tip_row.data(), tip_row, static_cast<size_t>(n) * sizeof(int32_t)) == 0)) {
+    auto same_topology = [&](const pnb_locus::Template& T) {
+        return T.valid && T.n == n && T.has_tip_row == (tip_row != nullptr) &&
+               memcmp(T.parent.data(), parent, static_cast<size_t>(n) * sizeof(int32_t)) == 0 &&
+               (!tip_row || memcmp(T.tip_row.data(), tip_row, static_cast<size_t>(n) * sizeof(int32_t)) == 0);
+    };
+    auto refresh_program = [&](const pnb_locus::Template& T) {
         const int n_ops_t = T.jo.n_ops;
         if (n_ops_t > 0) memcpy(ops, T.ops.data(), static_cast<size_t>(n_ops_t) * sizeof(Op));
         for (int k = 0; k < n_ops_t; ++k) {
@@ -570,6 +564,34 @@ int compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int32_t n
             t_out[k] = eff_len(c);
             if (Pexp_out) memcpy(Pexp_out + static_cast<size_t>(k) * 16, P_edge + static_cast<size_t>(c) * 16, 128);
         }
+    };
+    // ---- fastest path: a full, immediately committed re-evaluation of the topology the committed
+    // cache already describes (same slots): refresh branch lengths in place, no pending image.
+    if (!nostore && full && !(flags & PNB_EVAL_PENDING) && loc->committed_from_tmpl && C.valid &&
+        loc->tmpl[0].n_slots == loc->n_slots && same_topology(loc->tmpl[0])) {
+        const pnb_locus::Template& T0 = loc->tmpl[0];
+        refresh_program(T0);
+        const size_t ne = T0.kid_child.size();
+        for (size_t e = 0; e < ne; ++e) C.kid_len[e] = dbits(eff_len(T0.kid_child[e]));
+        C.model_id = m->id;
+        C.logL_valid = false;
+        *jo = T0.jo;
+        jo->rc = PNB_OK;
+        jo->root_clean_cached = false;
+        jo->in_place = true;
+        return PNB_OK;
+    }
+    if (!nostore) {
+        if (C.valid && C.model_id != m->id) locus_reset_cache(loc);  // partials of another model are useless
+        if (full && !(flags & PNB_EVAL_PENDING)) locus_reset_cache(loc);
+    }
+    const bool can_lookup = C.valid && !full && C.model_id == m->id;
+    // every node will be recomputed and (store mode) slots come off the free list in canonical order
+    const bool all_dirty_canonical = nostore ? !can_lookup : !C.valid;
+    // ---- fast path: same topology as the last all-dirty compilation of this locus --------------
+    pnb_locus::Template& T = loc->tmpl[nostore ? 1 : 0];
+    if (all_dirty_canonical && (nostore || T.n_slots == loc->n_slots) && same_topology(T)) {
+        refresh_program(T);
         if (!nostore) {
             auto& P_ = loc->pending;
             P_ = T.cache;
@@ -581,6 +603,7 @@ int compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int32_t n
             P_.logL_valid = false;
             loc->free_slots.resize(static_cast<size_t>(loc->n_slots - T.slots_used));
             loc->has_pending = true;
+            loc->pending_from_tmpl = true;
         }
         *jo = T.jo;
         jo->rc = PNB_OK;
@@ -870,7 +893,10 @@ int compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int32_t n
         jo->root_src = static_cast<int>(ref[root] - n_rows);
     }
     jo->root_clean_cached = cnt[root] > 0 && !dirty[root] && C.valid && C.logL_valid && C.root_ref == ref[root];
-    if (!nostore) loc->has_pending = true;  // rollback re-derives the free slots from `committed`
+    if (!nostore) {
+        loc->has_pending = true;  // rollback re-derives the free slots from `committed`
+        loc->pending_from_tmpl = false;
+    }
     // remember this program: the next all-dirty evaluation of the same topology only refreshes lengths
     if (all_dirty_canonical && templ_ok && n_dirty == n_internal) {
         T.valid = true;
@@ -886,6 +912,7 @@ int compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int32_t n
         if (!nostore) {
             T.cache = loc->pending;
             T.kid_child = S.kid_child;
+            loc->pending_from_tmpl = true;
         }
     } else if (all_dirty_canonical) {
         T.valid = false;
@@ -898,6 +925,8 @@ void locus_commit(pnb_locus* loc) {
     std::swap(loc->committed, loc->pending);
     loc->pending.clear();
     loc->has_pending = false;
+    loc->committed_from_tmpl = loc->pending_from_tmpl;
+    loc->pending_from_tmpl = false;
     // free every slot the committed tree does not use
     loc->free_slots.clear();
     for (int s = loc->n_slots - 1; s >= 0; --s)
@@ -963,7 +992,7 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
         }
     };
     for (auto& S : ctx->scratch) { S.first_err_job = -1; S.tiles = 0; S.grow.clear(); }
-    parallel_for(M, 4096, [&](int w, int64_t j0, int64_t j1) {
+    parallel_for(M, 512, [&](int w, int64_t j0, int64_t j1) {
         CompileScratch& S = ctx->scratch[w];
         auto fail = [&](int64_t j, int code, const char* msg) {
             if (S.first_err_job < 0) { S.first_err_job = j; S.rc_alloc = code; snprintf(S.err, sizeof(S.err), "%s", msg); }
@@ -1065,7 +1094,7 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
                                 P_edge ? P_edge + b * 16 : nullptr, site_rate, flags, h_ops + o, h_t + o,
                                 h_pexp ? h_pexp + o * 16 : nullptr, &jo);
             if (jo.rc != PNB_OK && S.first_err_job < 0) S.first_err_job = j;
-            if (jo.rc == PNB_OK && auto_commit) {
+            if (jo.rc == PNB_OK && auto_commit && !jo.in_place) {
                 // host bookkeeping only (which slot holds which node); independent of the GPU finishing
                 if (jo.root_clean_cached) jo.cached_logL = loc->committed.logL;
                 locus_commit(loc);

@@ -73,6 +73,7 @@ struct JobOut {
     int n_dirty = 0;
     bool root_clean_cached = false;
     double cached_logL = 0.0;   // committed logL captured before an in-worker commit
+    bool in_place = false;      // the committed cache was refreshed in place: nothing to commit
 };
 
 // Per-thread scratch of the tree compiler (no allocation in steady state).
@@ -236,6 +237,7 @@ struct pnb_locus {
     };
     TreeCache committed, pending;
     bool has_pending = false;
+    bool committed_from_tmpl = false, pending_from_tmpl = false;  // cache image == tmpl[0].cache (slots included)
 
     // Compiled-program template of the last tree that was evaluated with EVERY node recomputed
     // ([0] storing, [1] NOSTORE).  The op program depends on the topology only, so when the same
