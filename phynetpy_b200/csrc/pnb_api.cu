@@ -878,6 +878,19 @@ int compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int32_t n
             fs.pop_back();
         }
     }
+    // long programs are streamed through shared memory in segments of SEG_MAX_OPS ops: the staging row
+    // of a tip op is then its index among the tip ops of ITS segment
+    int rows_cap_job = n_tip_ops;
+    if (n_ops > SEG_MAX_OPS) {
+        rows_cap_job = 0;
+        for (int s0 = 0; s0 < n_ops; s0 += SEG_MAX_OPS) {
+            int c = 0;
+            for (int k = s0; k < std::min(n_ops, s0 + SEG_MAX_OPS); ++k)
+                if ((ops[k].flags & F_KIND_MASK) == K_TIP && ops[k].src >= 0) ops[k].aux = c++;
+            rows_cap_job = std::max(rows_cap_job, c);
+        }
+    }
+    jo->rows_cap = rows_cap_job;
     jo->n_ops = n_ops;
     jo->n_tip_ops = n_tip_ops;
     jo->n_dirty = n_dirty;
@@ -1204,8 +1217,8 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
                 ops_hi = std::max(ops_hi, o + jo.n_ops);
             }
             updates += static_cast<int64_t>(jo.n_dirty) * loc->P;
-            ops_cap = std::max(ops_cap, jo.n_ops);
-            rows_cap = std::max(rows_cap, jo.n_tip_ops);
+            ops_cap = std::max(ops_cap, std::min(jo.n_ops, SEG_MAX_OPS));
+            rows_cap = std::max(rows_cap, jo.rows_cap);
             stk_cap = std::max(stk_cap, jo.stk_need);
             n_jobs++;
         }

@@ -28,6 +28,7 @@ namespace pnb {
 #endif
 constexpr int TPB = PNB_TPB;        // threads per block
 constexpr int PPT = PNB_PPT;        // site patterns per thread (independent dependency chains)
+constexpr int SEG_MAX_OPS = 192;     // a tree program longer than this is streamed through shared memory in segments
 constexpr int TILE_PATTERNS = TPB * PPT;  // patterns per tile; FIXED so the summation order of a locus
                                           // never depends on batch composition or GPU count
 constexpr int PRUNE_MIN_BLOCKS = PNB_MIN_BLOCKS;  // occupancy target of the pruning kernel (register budget)
@@ -323,7 +324,6 @@ pnb_prune_kernel(const __grid_constant__ PruneLaunch L, const __grid_constant__ 
     const JobDesc& jd = L.jobs[job];
     const int n_ops = jd.n_ops;
     const int op_off = jd.op_off;
-    const int n_tip_ops = jd.n_tip_ops;
     const int tile0 = jd.tile0;
     const int P = jd.P;
     const int ld_codes = jd.ld_codes;
@@ -343,34 +343,14 @@ pnb_prune_kernel(const __grid_constant__ PruneLaunch L, const __grid_constant__ 
     }
     __syncthreads();
 
-    // warp 0 is the TMA producer: program, P matrices and the tile's code rows, one mbarrier
-    if (tid < 32) {
-        if (tid == 0) {
-            mbar_arrive_expect_tx(&bar_stage, static_cast<uint32_t>(n_ops) * (sizeof(Op) + 128u) +
-                                                  static_cast<uint32_t>(n_tip_ops) * TILE_PATTERNS);
-            if (n_ops > 0) {
-                tma_bulk_g2s(s_ops, g_ops, static_cast<uint32_t>(n_ops) * sizeof(Op), &bar_stage);
-                tma_bulk_g2s(s_P, L.Pm + static_cast<int64_t>(op_off) * 16, static_cast<uint32_t>(n_ops) * 128u,
-                             &bar_stage);
-            }
-        }
-        __syncwarp();
-        for (int k = tid; k < n_ops; k += 32) {
-            const Op op = g_ops[k];
-            if ((op.flags & F_KIND_MASK) == K_TIP && op.src >= 0)
-                tma_bulk_g2s(s_codes + static_cast<size_t>(op.aux) * TILE_PATTERNS,
-                             g_codes + static_cast<int64_t>(op.src) * ld_codes + p0, TILE_PATTERNS, &bar_stage);
-        }
-    }
-
-    // per-thread bookkeeping while the copies are in flight.  Every array is padded to a multiple of
-    // the tile (codes with state 0, partial slots zero-filled), so lanes past the last pattern run the
-    // same instruction stream on padding and only the final weighted sum looks at `active`.
+    // per-thread bookkeeping.  Every array is padded to a multiple of the tile (codes with state 0,
+    // partial slots zero-filled), so lanes past the last pattern run the same instruction stream on
+    // padding and only the final weighted sum looks at the pattern index.
     const int64_t slot_stride = jd.slot_stride;
     double* part0 = jd.partials + static_cast<int64_t>(p0 + tid) * 4;
     const bool warp_active = __any_sync(0xffffffffu, (p0 + tid) < P);
-    uint32_t op_addr = smem_u32(s_ops);
-    uint32_t pk = smem_u32(s_P);
+    const uint32_t ops_base = smem_u32(s_ops);
+    const uint32_t p_base = smem_u32(s_P);
     const uint32_t codes_addr = smem_u32(s_codes) + tid;
     const uint32_t stk_addr = smem_u32(s_stk) + tid * 16;
 
@@ -378,10 +358,41 @@ pnb_prune_kernel(const __grid_constant__ PruneLaunch L, const __grid_constant__ 
 #pragma unroll
     for (int u = 0; u < PPT; ++u) acc[u] = {1.0, 1.0, 1.0, 1.0};
 
-    mbar_wait(&bar_stage, 0);
+    // The program is walked in segments of at most SEG_MAX_OPS ops (one segment for trees of up to
+    // ~97 taxa): warp 0 is the TMA producer of a segment -- its ops, its P matrices and the code rows
+    // of its tip ops, all completing on one mbarrier whose phase flips per segment.
+    const int seg_cap = (n_ops > SEG_MAX_OPS) ? SEG_MAX_OPS : n_ops;
+    uint32_t phase = 0;
+    for (int seg = 0; seg < n_ops; seg += seg_cap, phase ^= 1u) {
+        const int nseg = min(seg_cap, n_ops - seg);
+        if (seg > 0) __syncthreads();  // every warp is done with the previous segment's shared memory
+        if (tid < 32) {
+            if (tid == 0) {
+                tma_bulk_g2s(s_ops, g_ops + seg, static_cast<uint32_t>(nseg) * sizeof(Op), &bar_stage);
+                tma_bulk_g2s(s_P, L.Pm + (static_cast<int64_t>(op_off) + seg) * 16, static_cast<uint32_t>(nseg) * 128u,
+                             &bar_stage);
+            }
+            int my_rows = 0;
+            for (int k = tid; k < nseg; k += 32) {
+                const Op op = g_ops[seg + k];
+                if ((op.flags & F_KIND_MASK) == K_TIP && op.src >= 0) {
+                    tma_bulk_g2s(s_codes + static_cast<size_t>(op.aux) * TILE_PATTERNS,
+                                 g_codes + static_cast<int64_t>(op.src) * ld_codes + p0, TILE_PATTERNS, &bar_stage);
+                    ++my_rows;
+                }
+            }
+            const int rows = __reduce_add_sync(0xffffffffu, my_rows);
+            // the pending arrival keeps the phase open until the byte count has been announced
+            if (tid == 0)
+                mbar_arrive_expect_tx(&bar_stage, static_cast<uint32_t>(nseg) * (sizeof(Op) + 128u) +
+                                                      static_cast<uint32_t>(rows) * TILE_PATTERNS);
+        }
+        mbar_wait(&bar_stage, phase);
+        if (!warp_active) continue;
 
-    if (warp_active) {
-        for (int k = 0; k < n_ops; ++k, op_addr += 16, pk += 128) {
+        uint32_t op_addr = ops_base;
+        uint32_t pk = p_base;
+        for (int k = 0; k < nseg; ++k, op_addr += 16, pk += 128) {
             uint32_t flags;
             int32_t src, dst, aux;
             lds_op(op_addr, flags, src, dst, aux);

@@ -67,6 +67,7 @@ struct JobOut {
     int rc = 0;
     int n_ops = 0;
     int n_tip_ops = 0;
+    int rows_cap = 0;           // staged code rows per program segment (max over segments)
     int root_kind = 0;
     int root_src = 0;
     int stk_need = 0;

@@ -481,3 +481,36 @@ def test_program_template_same_topology_new_lengths():
         t = t.with_lengths(t.blen * scale)
         got = fc.log_likelihood(t, model, full=True)
         assert rel_err(got, O.log_likelihood(locus, _otree(t), om)) <= REL
+
+
+def test_large_tree_program_streamed_in_segments():
+    """Trees whose op program exceeds one shared-memory segment (SEG_MAX_OPS = 192 ops, ~97 taxa):
+    320 taxa -> 638 ops -> 4 segments.  Store mode, dirty path and NOSTORE (deep stash) vs the oracle."""
+    P = _pkg()
+    from phynetpy_b200 import simulate as S
+    rng = np.random.default_rng(2718)
+    n, L = 320, 150
+    par, bl = S.random_trees(1, n, rng, height=0.25)
+    aln = S.simulate_alignments(par, bl, L, S.DEFAULT_PI, S.DEFAULT_RATES, rng)[0]
+    ft = S.flat_trees(par, bl)[0]
+    taxa = S.tip_labels(n)
+    model = P.GTR(S.DEFAULT_PI, S.DEFAULT_RATES)
+    om = O.gtr(S.DEFAULT_PI, S.DEFAULT_RATES)
+    fc = P.FelsensteinCalculator.from_matrix(taxa, aln, device_compress=False)
+    locus = O.OracleLocus(S.to_alignment_dict(aln))
+    assert fc.n_patterns == locus.n_patterns
+    exp = O.log_likelihood(locus, _otree(ft), om)
+    assert exp > -600.0 * L  # not the clamp regime: a real comparison
+    got = fc.log_likelihood(ft, model)
+    assert rel_err(got, exp) <= REL
+    assert fc._context().last_stats()["ops"] == 2 * (n - 1)
+    b2 = ft.blen.copy()
+    b2[11] *= 2.0
+    t2 = ft.with_lengths(b2)
+    got2 = fc.log_likelihood(t2, model)
+    assert fc._context().last_stats()["nodes_recomputed"] < n - 1
+    assert rel_err(got2, O.log_likelihood(locus, _otree(t2), om)) <= REL
+    eng = P.SeqLikelihoodEngine([fc], None, model)
+    vals = eng.score_candidates(0, [ft.with_lengths(ft.blen * 1.1), t2])
+    assert rel_err(vals[0], O.log_likelihood(locus, _otree(ft.with_lengths(ft.blen * 1.1)), om)) <= REL
+    assert vals[1] == got2
