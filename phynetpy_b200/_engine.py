@@ -157,6 +157,34 @@ class SeqLikelihoodEngine:
             return float("-inf")
         return total
 
+    def score_candidate_sets(self, sets: Sequence[Tuple[int, Sequence[Any]]], *, site_rate: float = 1.0) -> List[np.ndarray]:
+        """Candidate trees for MANY loci in ONE launch: ``sets = [(locus, [tree, ...]), ...]``.
+
+        This is the whole inner double loop of ``_coupled_gene_tree_reproposal`` (reference
+        ``src/_mcmc_seq.py:2028`` over loci x ``_enumerate_scored_candidates`` ``:1935-1957`` over
+        ``({g} U NNI(g)) x (0.25, 0.5, 1, 2, 4)``), i.e. up to 2*5*(1+2(n-2)) prunings per locus, as a
+        single ``PNB_EVAL_NOSTORE`` batch.  Returns one array of log-likelihoods per set."""
+        self._commit_pending()
+        ctx = self._context()
+        idx: List[int] = []
+        flats: List[FlatTree] = []
+        for locus, trees in sets:
+            for t in trees:
+                idx.append(locus)
+                flats.append(flatten(t))
+        if not idx:
+            return [np.zeros(0) for _ in sets]
+        node_off, parent, blen, tip_row = pack_trees(flats, [self._calcs[i]._row_of for i in idx])
+        P_edge = _explicit_P_edges(self._model, blen, site_rate) if _device_kind(self._model) == "explicit" else None
+        out = ctx.eval(_model_handle(self._model, ctx), self._handles(idx), node_off, parent, blen, tip_row,
+                       site_rate, _lib.EVAL_NOSTORE, P_edge)
+        self.last_stats = ctx.last_stats()
+        res, k = [], 0
+        for _, trees in sets:
+            res.append(out[k:k + len(trees)])
+            k += len(trees)
+        return res
+
     def score_candidates(self, locus: int, trees: Sequence[Any], *, site_rate: float = 1.0) -> np.ndarray:
         """Felsenstein logL of many candidate trees for ONE locus in one launch (the
         loops of the coupled moves, reference ``src/_mcmc_seq.py:1864-1992``): cached

@@ -257,6 +257,13 @@ def test_engine_golden_and_cache_semantics(engine_case):
     vals = eng.score_candidates(i, cands)
     assert vals[0] == vals[2]
     assert rel_err(vals[1], ec["per_locus"][i]) <= REL
+    # candidate sets for several loci in one launch (the coupled moves' double loop)
+    sets = [(j, [trees[j], trees[j].flat().with_lengths(trees[j].flat().blen * 2.0)]) for j in (0, 5, 11)]
+    res = eng.score_candidate_sets(sets)
+    assert [len(r) for r in res] == [2, 2, 2]
+    for (j, _), r in zip(sets, res):
+        assert rel_err(r[0], ec["per_locus"][j]) <= REL and r[1] != r[0]
+    assert eng.last_stats["launches"] == 2 and eng.log_likelihood(new_trees, None, 0.0) == t2
 
 
 def test_candidates_nostore_deep_tree_uses_stash():
