@@ -463,6 +463,8 @@ extern "C" int pnb_locus_destroy(pnb_locus* loc) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     locus_free_partials(loc);
+    for (auto& T : loc->tmpl)
+        if (T.d_ops) ctx->arena.release(T.d_ops, static_cast<size_t>(T.d_ops_cap) * sizeof(Op));
     if (loc->d_codes) ctx->arena.release(loc->d_codes, loc->codes_bytes);
     if (loc->d_weights) ctx->arena.release(loc->d_weights, loc->weights_bytes);
     ctx->n_loci_alive--;
@@ -558,7 +560,8 @@ int compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int32_t n
     };
     auto refresh_program = [&](const pnb_locus::Template& T) {
         const int n_ops_t = T.jo.n_ops;
-        if (n_ops_t > 0) memcpy(ops, T.ops.data(), static_cast<size_t>(n_ops_t) * sizeof(Op));
+        // with a valid device-resident copy of the program only the branch lengths travel
+        if (n_ops_t > 0 && !T.d_ops_valid) memcpy(ops, T.ops.data(), static_cast<size_t>(n_ops_t) * sizeof(Op));
         for (int k = 0; k < n_ops_t; ++k) {
             const int c = T.op_child[k];
             t_out[k] = eff_len(c);
@@ -579,6 +582,8 @@ int compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int32_t n
         jo->rc = PNB_OK;
         jo->root_clean_cached = false;
         jo->in_place = true;
+        jo->tmpl_hit = 0;
+        jo->tmpl_new = -1;
         return PNB_OK;
     }
     if (!nostore) {
@@ -590,7 +595,18 @@ int compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int32_t n
     const bool all_dirty_canonical = nostore ? !can_lookup : !C.valid;
     // ---- fast path: same topology as the last all-dirty compilation of this locus --------------
     pnb_locus::Template& T = loc->tmpl[nostore ? 1 : 0];
-    if (all_dirty_canonical && (nostore || T.n_slots == loc->n_slots) && same_topology(T)) {
+    bool read_locked = false;
+    if (all_dirty_canonical) {
+        int v = loc->tmpl_lock.load(std::memory_order_acquire);
+        while (v >= 0 && !loc->tmpl_lock.compare_exchange_weak(v, v + 1, std::memory_order_acquire)) {}
+        read_locked = v >= 0;
+    }
+    struct ReadUnlock {
+        std::atomic<int>* l;
+        ~ReadUnlock() { if (l) l->fetch_sub(1, std::memory_order_release); }
+        void release() { if (l) { l->fetch_sub(1, std::memory_order_release); l = nullptr; } }
+    } read_guard{read_locked ? &loc->tmpl_lock : nullptr};
+    if (read_locked && (nostore || T.n_slots == loc->n_slots) && same_topology(T)) {
         refresh_program(T);
         if (!nostore) {
             auto& P_ = loc->pending;
@@ -608,8 +624,12 @@ int compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int32_t n
         *jo = T.jo;
         jo->rc = PNB_OK;
         jo->root_clean_cached = false;
+        jo->in_place = false;
+        jo->tmpl_hit = nostore ? 1 : 0;
+        jo->tmpl_new = -1;
         return PNB_OK;
     }
+    read_guard.release();
 
     cnt.assign(n, 0);
     int root = -1;
@@ -911,7 +931,13 @@ int compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int32_t n
         loc->pending_from_tmpl = false;
     }
     // remember this program: the next all-dirty evaluation of the same topology only refreshes lengths
-    if (all_dirty_canonical && templ_ok && n_dirty == n_internal) {
+    jo->tmpl_hit = -1;
+    jo->tmpl_new = -1;
+    jo->in_place = false;
+    int expect0 = 0;
+    const bool write_locked = all_dirty_canonical &&
+                              loc->tmpl_lock.compare_exchange_strong(expect0, -1, std::memory_order_acquire);
+    if (write_locked && templ_ok && n_dirty == n_internal) {
         T.valid = true;
         T.n = n;
         T.n_slots = loc->n_slots;
@@ -921,15 +947,22 @@ int compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int32_t n
         if (tip_row) T.tip_row.assign(tip_row, tip_row + n); else T.tip_row.clear();
         T.ops.assign(ops, ops + n_ops);
         T.op_child = S.op_child;
+        T.d_ops_valid = false;  // refreshed (stream-ordered) by pnb_eval after this batch's copy
+        jo->tmpl_hit = -1;
+        jo->in_place = false;
+        jo->tmpl_new = nostore ? 1 : 0;
         T.jo = *jo;
+        T.jo.tmpl_new = -1;
         if (!nostore) {
             T.cache = loc->pending;
             T.kid_child = S.kid_child;
             loc->pending_from_tmpl = true;
         }
-    } else if (all_dirty_canonical) {
+    } else if (write_locked) {
         T.valid = false;
+        T.d_ops_valid = false;
     }
+    if (write_locked) loc->tmpl_lock.store(0, std::memory_order_release);
     return PNB_OK;
 }
 
@@ -1172,7 +1205,10 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
         }
         // job descriptors + tile map of this chunk (serial, cheap); numbering is global
         const int64_t jobs_first = n_jobs, tiles_first = n_tiles;
-        int64_t ops_lo = -1, ops_hi = 0;
+        int64_t ops_lo = -1, ops_hi = 0;    // range of P matrices / branch lengths used by this chunk
+        int64_t prog_lo = -1, prog_hi = 0;  // range of op programs that travel with this chunk
+        std::vector<int64_t>& save_list = ctx->save_list;
+        save_list.clear();
         int ops_cap = 1, rows_cap = 1, stk_cap = 0;
         for (int64_t j = j0; j < j1; ++j) {
             pnb_locus* loc = loci[j];
@@ -1207,7 +1243,14 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
             jd.tile0 = static_cast<int32_t>(n_tiles);
             jd.n_tiles = static_cast<int32_t>((loc->P + TILE_PATTERNS - 1) / TILE_PATTERNS);
             jd.out_index = static_cast<int32_t>(j);
-            jd.pad0 = jd.pad1 = 0;
+            const pnb_locus::Template* Th = jo.tmpl_hit >= 0 ? &loc->tmpl[jo.tmpl_hit] : nullptr;
+            const bool resident = Th && Th->d_ops_valid && jo.n_ops > 0;
+            jd.ops = resident ? Th->d_ops : reinterpret_cast<const Op*>(ds + off_ops) + o;
+            if (!resident && jo.n_ops > 0) {
+                if (prog_lo < 0) prog_lo = o;
+                prog_hi = std::max(prog_hi, o + jo.n_ops);
+            }
+            if (jo.tmpl_new >= 0 && jo.n_ops > 0) save_list.push_back(j);
             for (int t = 0; t < jd.n_tiles; ++t) h_tile_job[n_tiles + t] = static_cast<int32_t>(n_jobs);
             job_of_batch[j] = n_jobs;
             n_tiles += jd.n_tiles;
@@ -1245,10 +1288,12 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
             PNB_CUDA_TRY(cudaMemcpyAsync(ds + off_tiles + tiles_first * sizeof(int32_t), hs + off_tiles + tiles_first * sizeof(int32_t),
                                          ct * sizeof(int32_t), cudaMemcpyHostToDevice, st));
             h2d += cj * sizeof(JobDesc) + ct * sizeof(int32_t);
+            if (prog_lo >= 0) {
+                PNB_CUDA_TRY(cudaMemcpyAsync(ds + off_ops + prog_lo * sizeof(Op), hs + off_ops + prog_lo * sizeof(Op),
+                                             (prog_hi - prog_lo) * sizeof(Op), cudaMemcpyHostToDevice, st));
+                h2d += (prog_hi - prog_lo) * sizeof(Op);
+            }
             if (n_op_range > 0) {
-                PNB_CUDA_TRY(cudaMemcpyAsync(ds + off_ops + ops_lo * sizeof(Op), hs + off_ops + ops_lo * sizeof(Op),
-                                             n_op_range * sizeof(Op), cudaMemcpyHostToDevice, st));
-                h2d += n_op_range * sizeof(Op);
                 if (!explicit_P) {
                     PNB_CUDA_TRY(cudaMemcpyAsync(ds + off_t + ops_lo * sizeof(double), hs + off_t + ops_lo * sizeof(double),
                                                  n_op_range * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -1260,6 +1305,30 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
             PNB_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(ctx->d_P.p) + ops_lo * 128, h_pexp + ops_lo * 16, n_op_range * 128,
                                          cudaMemcpyHostToDevice, st));
             h2d += n_op_range * 128;
+        }
+        // programs compiled from scratch in this chunk get a device-resident copy next to their locus, so
+        // that later evaluations of the same topology send branch lengths only (D2D, stream-ordered)
+        for (int64_t j : save_list) {
+            pnb_locus* loc = loci[j];
+            pnb_locus::Template& Tn = loc->tmpl[jout[j].tmpl_new];
+            const int nops = jout[j].n_ops;
+            const int64_t o_chk = node_off[j] - node_off[0] - j;
+            // several jobs of one locus may have rebuilt the template in this batch: only a job whose
+            // program IS the template's final program may publish the device copy
+            if (!Tn.valid || Tn.jo.n_ops != nops ||
+                memcmp(Tn.ops.data(), h_ops + o_chk, static_cast<size_t>(nops) * sizeof(Op)) != 0) continue;
+            if (Tn.d_ops_cap < nops) {
+                if (Tn.d_ops) ctx->arena.release(Tn.d_ops, static_cast<size_t>(Tn.d_ops_cap) * sizeof(Op));
+                void* pp = nullptr;
+                const int cap = std::max(nops, 64);
+                if (ctx->arena.alloc(static_cast<size_t>(cap) * sizeof(Op), &pp) != PNB_OK) { Tn.d_ops = nullptr; Tn.d_ops_cap = 0; continue; }
+                Tn.d_ops = static_cast<Op*>(pp);
+                Tn.d_ops_cap = cap;
+            }
+            const int64_t o = node_off[j] - node_off[0] - j;
+            PNB_CUDA_TRY(cudaMemcpyAsync(Tn.d_ops, ds + off_ops + o * sizeof(Op), static_cast<size_t>(nops) * sizeof(Op),
+                                         cudaMemcpyDeviceToDevice, st));
+            Tn.d_ops_valid = true;
         }
         const bool prof = ctx->profiling && n_chunks == 1;
         if (n_op_range > 0 && !explicit_P) {
@@ -1275,7 +1344,6 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
         PruneLaunch L;
         L.jobs = reinterpret_cast<const JobDesc*>(ds + off_jobs);
         L.tile_job = reinterpret_cast<const int32_t*>(ds + off_tiles);
-        L.ops = reinterpret_cast<const Op*>(ds + off_ops);
         L.Pm = static_cast<const double*>(ctx->d_P.p);
         L.tile_sum = static_cast<double*>(ctx->d_tile_sum.p);
         L.job_done = static_cast<unsigned int*>(ctx->d_job_done.p);

@@ -68,7 +68,7 @@ struct __align__(16) JobDesc {
     int32_t tile0;          // first tile of this job
     int32_t n_tiles;
     int32_t out_index;      // where the job's logL goes in the output vector
-    int32_t pad0, pad1;
+    const Op* ops;          // the job's op program: in the batch staging area, or the locus' resident copy
 };
 
 struct ModelParams {
@@ -83,7 +83,6 @@ struct ModelParams {
 struct PruneLaunch {
     const JobDesc* jobs;
     const int32_t* tile_job;   // tile -> job
-    const Op* ops;             // batch program
     const double* Pm;          // batch P matrices [total_ops][16]
     double* tile_sum;          // [n_tiles]
     unsigned int* job_done;    // [n_jobs] arrival counters (self-resetting)
@@ -335,7 +334,7 @@ pnb_prune_kernel(const __grid_constant__ PruneLaunch L, const __grid_constant__ 
     unsigned char* s_stk = s_codes + static_cast<size_t>(L.rows_cap) * TILE_PATTERNS;
 
     const int p0 = (tile - tile0) * TILE_PATTERNS;
-    const Op* g_ops = L.ops + op_off;
+    const Op* g_ops = jd.ops;
 
     if (tid == 0) {
         mbar_init(&bar_stage, 1);

@@ -75,6 +75,8 @@ struct JobOut {
     bool root_clean_cached = false;
     double cached_logL = 0.0;   // committed logL captured before an in-worker commit
     bool in_place = false;      // the committed cache was refreshed in place: nothing to commit
+    int8_t tmpl_hit = -1;       // >= 0: program taken from tmpl[tmpl_hit]; its resident device copy can be used
+    int8_t tmpl_new = -1;       // >= 0: tmpl[tmpl_new] was (re)built by this job and needs its device copy
 };
 
 // Per-thread scratch of the tree compiler (no allocation in steady state).
@@ -204,6 +206,7 @@ struct pnb_ctx {
     typedef pnb::JobOut JobOutRaw;
     std::vector<pnb::JobOut> job_out;
     std::vector<int64_t> job_of_batch;
+    std::vector<int64_t> save_list;
 };
 
 struct pnb_locus {
@@ -252,8 +255,15 @@ struct pnb_locus {
         std::vector<pnb::Op> ops;
         pnb::JobOut jo;
         TreeCache cache;  // pending-cache image (store mode), kid_len refreshed per evaluation
+        pnb::Op* d_ops = nullptr;   // device-resident copy of `ops` (arena): template hits send no program
+        int32_t d_ops_cap = 0;      // capacity of d_ops in ops
+        bool d_ops_valid = false;   // d_ops holds (or a stream-ordered copy will hold) exactly `ops`
     };
     Template tmpl[2];
+    // readers/writer spin state for tmpl[] (a NOSTORE batch may hold the same locus many times and is
+    // compiled by several workers): >= 0 number of readers, -1 one writer.  Never waited on: a worker
+    // that cannot get the lock simply takes the general path / skips the template update.
+    std::atomic<int> tmpl_lock{0};
     std::vector<int32_t> free_slots;
     std::atomic<uint32_t> batch_mark{0};  // duplicate detection inside one pnb_eval batch
 };

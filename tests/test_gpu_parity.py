@@ -521,3 +521,35 @@ def test_large_tree_program_streamed_in_segments():
     vals = eng.score_candidates(0, [ft.with_lengths(ft.blen * 1.1), t2])
     assert rel_err(vals[0], O.log_likelihood(locus, _otree(ft.with_lengths(ft.blen * 1.1)), om)) <= REL
     assert vals[1] == got2
+
+
+def test_many_candidates_one_locus_parallel_compile_with_templates():
+    """The coupled moves' batch: one locus, hundreds of candidate trees ({g} U NNI(g)) x height scales,
+    compiled by several host workers that share the locus' program template.  Every value must equal
+    the single-tree evaluation bit for bit and the oracle to 1e-10."""
+    P = _pkg()
+    from phynetpy_b200 import simulate as S
+    rng = np.random.default_rng(99)
+    n = 16
+    par, bl = S.random_trees(3, n, rng, height=0.4)
+    aln = S.simulate_alignments(par[:1], bl[:1], 290, S.DEFAULT_PI, S.DEFAULT_RATES, rng)[0]
+    d = S.to_alignment_dict(aln)
+    topo = S.flat_trees(par, bl)            # three different topologies over the same taxa
+    model = P.GTR(S.DEFAULT_PI, S.DEFAULT_RATES)
+    om = O.gtr(S.DEFAULT_PI, S.DEFAULT_RATES)
+    locus = O.OracleLocus(d)
+    eng = P.SeqLikelihoodEngine([d], None, model)
+    eng.log_likelihood([topo[0]], None, 0.0)
+    scales = (0.25, 0.5, 1.0, 2.0, 4.0)
+    cands = []
+    for k in range(300):                    # 300 x 31 nodes = 9300 nodes -> multi-threaded compile
+        t = topo[int(rng.integers(0, 3))]
+        cands.append(t.with_lengths(t.blen * scales[k % 5] * (1.0 + 0.001 * (k // 5))))
+    vals = eng.score_candidates(0, cands)
+    assert eng.last_stats["launches"] in (2, 4)   # one (K-a, prune) pair per chunk
+    fc = P.FelsensteinCalculator(d)
+    for k in list(range(0, 300, 23)) + [299]:
+        assert vals[k] == fc.log_likelihood(cands[k], model, full=True)
+        assert rel_err(vals[k], O.log_likelihood(locus, _otree(cands[k]), om)) <= REL
+    again = eng.score_candidates(0, cands)
+    assert np.array_equal(vals, again)
