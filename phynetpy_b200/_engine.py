@@ -61,6 +61,8 @@ class SeqLikelihoodEngine:
         self._felsen: List[Optional[float]] = [None] * self.n_loci
         self._msnc: List[Optional[float]] = [None] * self.n_loci
         self._pending: List[int] = []   # loci with an uncommitted device evaluation
+        self._dirty: set = set(range(lo, hi))  # local loci whose _felsen entry is None
+        self._snap_dirty: dict = {}            # id(snapshot list) -> dirty set at clone time
         self._full_next = False
         self.last_stats: dict = {}
 
@@ -68,17 +70,30 @@ class SeqLikelihoodEngine:
     def invalidate_locus(self, i: int) -> None:
         self._felsen[i] = None
         self._msnc[i] = None
+        lo, hi = self._shard.local_range()
+        if lo <= i < hi:
+            self._dirty.add(i)
 
     def invalidate_network(self) -> None:
         self._msnc = [None] * self.n_loci
 
     def clone_caches(self) -> Tuple[list, list]:
-        return list(self._felsen), list(self._msnc)
+        snap = (list(self._felsen), list(self._msnc))
+        if len(self._snap_dirty) > 8:
+            self._snap_dirty.clear()
+        self._snap_dirty[id(snap[0])] = (snap[0], frozenset(self._dirty))
+        return snap
 
     def restore_caches(self, snapshot: Tuple[list, list]) -> None:
         """Reject path: scalar caches come back from the snapshot and the device
         discards the partials written by the rejected proposal."""
         self._felsen, self._msnc = list(snapshot[0]), list(snapshot[1])
+        known = self._snap_dirty.get(id(snapshot[0]))
+        if known is not None and known[0] is snapshot[0]:
+            self._dirty = set(known[1])
+        else:  # a snapshot we did not hand out: recount
+            lo, hi = self._shard.local_range()
+            self._dirty = {i for i in range(lo, hi) if self._felsen[i] is None}
         self._rollback_pending()
 
     def invalidate_device_cache(self) -> None:
@@ -122,12 +137,16 @@ class SeqLikelihoodEngine:
         self.last_stats = ctx.last_stats()
         return out
 
-    def log_likelihood(self, gene_trees: Sequence[Any], species_net: Any = None, theta: float = 0.0) -> float:
+    def log_likelihood(self, gene_trees: Sequence[Any], species_net: Any = None, theta: float = 0.0,
+                       *, rescan: bool = False) -> float:
         """Total log-likelihood; ``-inf`` when not finite (reference :723-764)."""
         # whatever was pending belongs to an accepted proposal: it becomes the committed state
         self._commit_pending()
         lo, hi = self._shard.local_range()
-        dirty = [i for i in range(lo, hi) if self._felsen[i] is None]
+        if rescan:  # entries were set to None behind our back (a caller sharing the list): recount
+            self._dirty = {i for i in range(lo, hi) if self._felsen[i] is None}
+        dirty = sorted(i for i in self._dirty if self._felsen[i] is None)
+        self._dirty.clear()
         flags = _lib.EVAL_PENDING | (_lib.EVAL_FULL if self._full_next else 0)
         self._full_next = False
         if self._shard.world_size == 1:
@@ -148,11 +167,21 @@ class SeqLikelihoodEngine:
                 self._pending = list(dirty)
             vec = self._shard.allreduce_sum(vec)
             self._felsen = [float(v) for v in vec]
-        total = 0.0
-        for i in range(self.n_loci):
-            if self._msnc_fn is not None and self._msnc[i] is None:
-                self._msnc[i] = float(self._msnc_fn(i, gene_trees[i], species_net, theta))
-            total += self._felsen[i] + (self._msnc[i] if self._msnc_fn is not None else 0.0)
+        try:
+            if self._msnc_fn is None:
+                total = sum(self._felsen)  # C loop, locus order
+            else:
+                total = 0.0
+                for i in range(self.n_loci):  # reference loop, src/_mcmc_seq.py:745-761
+                    if self._msnc[i] is None:
+                        self._msnc[i] = float(self._msnc_fn(i, gene_trees[i], species_net, theta))
+                    total += self._felsen[i] + self._msnc[i]
+        except TypeError:
+            # an entry is still None: it was invalidated without invalidate_locus() (a caller that shares
+            # the list); recount the dirty set once and evaluate again
+            if rescan:
+                raise
+            return self.log_likelihood(gene_trees, species_net, theta, rescan=True)
         if not math.isfinite(total):
             return float("-inf")
         return total

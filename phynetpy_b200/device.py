@@ -121,6 +121,9 @@ def default_context(device: Optional[int] = None) -> DeviceContext:
 
 def pack_trees(trees: Sequence[FlatTree], row_maps: Sequence[dict]) -> Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
     """Concatenate flat trees into the CSR arrays ``pnb_eval`` takes."""
+    if len(trees) == 1:  # the single-locus MCMC step: no concatenation
+        t = trees[0]
+        return (np.array([0, t.n_nodes], dtype=np.int64), t.parent, t.blen, t.tip_rows(row_maps[0]))
     sizes = np.fromiter((t.n_nodes for t in trees), dtype=np.int64, count=len(trees))
     node_off = np.zeros(len(trees) + 1, dtype=np.int64)
     np.cumsum(sizes, out=node_off[1:])

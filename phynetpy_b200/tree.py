@@ -25,7 +25,7 @@ class FlatTree:
     """Rooted tree as arrays: ``parent[i]`` (-1 = root), ``blen[i]`` = length of the
     edge above node ``i`` (NaN = the reference's ``None`` -> 0), ``label[i]``."""
 
-    __slots__ = ("parent", "blen", "label", "_n_children")
+    __slots__ = ("parent", "blen", "label", "_n_children", "_tip_rows")
 
     def __init__(self, parent: Sequence[int], blen: Sequence[Optional[float]], label: Sequence[Optional[str]]):
         self.parent = np.ascontiguousarray(parent, dtype=np.int32)
@@ -37,6 +37,7 @@ class FlatTree:
         if self.blen.shape[0] != n or len(self.label) != n:
             raise ValueError("FlatTree: parent, blen and label must have the same length")
         self._n_children = None
+        self._tip_rows = None  # (id(row_of_label), array): shared by every with_lengths() copy
 
     @property
     def n_nodes(self) -> int:
@@ -54,16 +55,21 @@ class FlatTree:
         t.blen = np.ascontiguousarray(blen, dtype=np.float64)
         t.label = self.label
         t._n_children = self._n_children
+        t._tip_rows = self._tip_rows
         return t
 
     def tip_rows(self, row_of_label: dict) -> np.ndarray:
         """Row of the locus' code matrix per node: leaf with a known label -> row;
         leaf absent from the alignment -> -1 (all-ones partial, reference :409-412);
         internal nodes -> -2 (ignored by the library)."""
+        cached = self._tip_rows
+        if cached is not None and cached[0] is row_of_label:
+            return cached[1]
         nc = self.n_children()
         out = np.full(self.n_nodes, -2, dtype=np.int32)
         for i in np.nonzero(nc == 0)[0]:
             out[i] = row_of_label.get(self.label[i], -1)
+        self._tip_rows = (row_of_label, out)  # topology and labels are immutable: safe to reuse
         return out
 
 

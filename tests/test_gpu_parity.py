@@ -553,3 +553,18 @@ def test_many_candidates_one_locus_parallel_compile_with_templates():
         assert rel_err(vals[k], O.log_likelihood(locus, _otree(cands[k]), om)) <= REL
     again = eng.score_candidates(0, cands)
     assert np.array_equal(vals, again)
+
+
+def test_engine_entries_invalidated_behind_its_back():
+    """INTEGRATION.md shares the scalar cache list with the reference engine: an entry set to None
+    without invalidate_locus() must still be recomputed."""
+    P = _pkg()
+    ec = load_golden("engine_case.json")
+    model = _model(P, ec["model"])
+    eng = P.SeqLikelihoodEngine([dict(l["alignment"]) for l in ec["loci"]], None, model)
+    trees = [_tree(P, l["tree"]) for l in ec["loci"]]
+    total = eng.log_likelihood(trees, None, 0.0)
+    eng._felsen[4] = None
+    eng._felsen[7] = None
+    assert eng.log_likelihood(trees, None, 0.0) == total
+    assert all(v is not None for v in eng._felsen)
