@@ -156,8 +156,11 @@ extern "C" int pnb_ctx_create(int device, pnb_ctx** out) {
         return PNB_ERR_CUDA;
     }
     ctx->stream = ctx->own_stream;
-    se = cudaFuncSetAttribute(pnb_prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    se = cudaFuncSetAttribute(pnb_prune_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               ctx->max_smem_optin - 1024);
+    if (se == cudaSuccess)
+        se = cudaFuncSetAttribute(pnb_prune_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  ctx->max_smem_optin - 1024);
     if (se != cudaSuccess) {
         cudaStreamDestroy(ctx->own_stream);
         delete ctx;
@@ -177,6 +180,7 @@ extern "C" int pnb_ctx_create(int device, pnb_ctx** out) {
     if (const char* e = getenv("PNB_HOST_THREADS")) workers = atoi(e);
     workers = std::max(1, std::min(workers, 32));
     if (const char* e = getenv("PNB_CHUNK_MIN_JOBS")) ctx->chunk_min_jobs = std::max(2, atoi(e));
+    if (const char* e = getenv("PNB_NO_FUSED")) ctx->allow_fused = atoi(e) == 0;
     ctx->scratch.resize(workers);
     if (workers > 1) ctx->pool = new (std::nothrow) WorkerPool(workers);
     *out = ctx;
@@ -1168,6 +1172,18 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
     char* ds = static_cast<char*>(ctx->d_stage.p);
     cudaStream_t st = ctx->stream;
     double* d_out = out_dev ? logL_out : static_cast<double*>(ctx->d_out.p);
+    // Latency path for small batches (the single-locus MCMC step): ONE kernel reads the job
+    // descriptors / program / branch lengths straight from the pinned staging memory (UVA), computes
+    // P(t) itself and writes logL into mapped host memory: no H2D copy, no K-a launch, no D2H copy.
+    bool fused = false;
+    if (ctx->allow_fused && !explicit_P && n_chunks == 1 && total_tiles <= 64 && stage_bytes <= (64u << 10)) {
+        void *da = nullptr, *db = nullptr;
+        fused = cudaHostGetDevicePointer(&da, hs, 0) == cudaSuccess && da == static_cast<void*>(hs) &&
+                cudaHostGetDevicePointer(&db, h_out, 0) == cudaSuccess && db == static_cast<void*>(h_out);
+        if (!fused) (void)cudaGetLastError();
+    }
+    const char* prog_base = fused ? hs : ds;  // where non-resident op programs are read from
+    bool stage_read_by_kernel = false;
 
     int64_t n_jobs = 0, n_tiles = 0, n_ops_used = 0, updates = 0, n_cached = 0, n_dirty_nodes = 0;
     int64_t h2d = 0, d2h = 0, launches = 0;
@@ -1245,7 +1261,7 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
             jd.out_index = static_cast<int32_t>(j);
             const pnb_locus::Template* Th = jo.tmpl_hit >= 0 ? &loc->tmpl[jo.tmpl_hit] : nullptr;
             const bool resident = Th && Th->d_ops_valid && jo.n_ops > 0;
-            jd.ops = resident ? Th->d_ops : reinterpret_cast<const Op*>(ds + off_ops) + o;
+            jd.ops = resident ? Th->d_ops : reinterpret_cast<const Op*>(prog_base + off_ops) + o;
             if (!resident && jo.n_ops > 0) {
                 if (prog_lo < 0) prog_lo = o;
                 prog_hi = std::max(prog_hi, o + jo.n_ops);
@@ -1279,7 +1295,9 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
             return PNB_ERR_UNSUPPORTED;
         }
         const int64_t n_op_range = ops_lo < 0 ? 0 : ops_hi - ops_lo;
-        if (n_chunks == 1 && stage_bytes <= (256u << 10)) {
+        if (fused) {
+            // nothing to copy: the kernel reads the staging buffer in place
+        } else if (n_chunks == 1 && stage_bytes <= (256u << 10)) {
             PNB_CUDA_TRY(cudaMemcpyAsync(ds, hs, stage_bytes, cudaMemcpyHostToDevice, st));
             h2d += stage_bytes;
         } else {
@@ -1326,12 +1344,13 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
                 Tn.d_ops_cap = cap;
             }
             const int64_t o = node_off[j] - node_off[0] - j;
-            PNB_CUDA_TRY(cudaMemcpyAsync(Tn.d_ops, ds + off_ops + o * sizeof(Op), static_cast<size_t>(nops) * sizeof(Op),
-                                         cudaMemcpyDeviceToDevice, st));
+            PNB_CUDA_TRY(cudaMemcpyAsync(Tn.d_ops, prog_base + off_ops + o * sizeof(Op), static_cast<size_t>(nops) * sizeof(Op),
+                                         fused ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
+            if (fused) h2d += static_cast<size_t>(nops) * sizeof(Op);
             Tn.d_ops_valid = true;
         }
         const bool prof = ctx->profiling && n_chunks == 1;
-        if (n_op_range > 0 && !explicit_P) {
+        if (n_op_range > 0 && !explicit_P && !fused) {
             const int64_t blocks = (n_op_range + 127) / 128;
             if (prof) PNB_CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
             pnb_pmatrix_kernel<<<static_cast<unsigned>(blocks), 128, 0, st>>>(
@@ -1342,12 +1361,14 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
             launches++;
         }
         PruneLaunch L;
-        L.jobs = reinterpret_cast<const JobDesc*>(ds + off_jobs);
-        L.tile_job = reinterpret_cast<const int32_t*>(ds + off_tiles);
+        L.jobs = reinterpret_cast<const JobDesc*>(prog_base + off_jobs);
+        L.tile_job = reinterpret_cast<const int32_t*>(prog_base + off_tiles);
         L.Pm = static_cast<const double*>(ctx->d_P.p);
+        L.t = reinterpret_cast<const double*>(prog_base + off_t);
+        if (fused && !out_dev) L.out = h_out + M;  // mapped pinned memory: the result needs no D2H copy
         L.tile_sum = static_cast<double*>(ctx->d_tile_sum.p);
         L.job_done = static_cast<unsigned int*>(ctx->d_job_done.p);
-        L.out = d_out;
+        if (!(fused && !out_dev)) L.out = d_out;
         L.ops_cap = ops_cap;
         L.rows_cap = rows_cap;
         L.stk_cap = stk_cap;
@@ -1358,13 +1379,18 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
             memset_done = true;
         }
         if (ctx->profiling && c == 0) PNB_CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
-        pnb_prune_kernel<<<static_cast<unsigned>(ct), TPB, dyn_smem, st>>>(L, m->mp);
+        if (fused) {
+            pnb_prune_kernel_t<true><<<static_cast<unsigned>(ct), TPB, dyn_smem, st>>>(L, m->mp);
+            stage_read_by_kernel = true;
+        } else {
+            pnb_prune_kernel_t<false><<<static_cast<unsigned>(ct), TPB, dyn_smem, st>>>(L, m->mp);
+        }
         PNB_CUDA_TRY(cudaGetLastError());
         if (ctx->profiling && c == n_chunks - 1) { PNB_CUDA_TRY(cudaEventRecord(ctx->ev[3], st)); ctx->ev_prune = true; }
         launches++;
     }
     ctx->t_compile_ms = compile_ms;
-    if (h2d > 0) {  // the pinned buffer may be rewritten once every copy out of it has completed
+    if (h2d > 0 || stage_read_by_kernel) {  // the pinned buffer may be rewritten once every reader of it is done
         if (!ctx->stage_ev[sb]) PNB_CUDA_TRY(cudaEventCreateWithFlags(&ctx->stage_ev[sb], cudaEventDisableTiming));
         PNB_CUDA_TRY(cudaEventRecord(ctx->stage_ev[sb], st));
         ctx->stage_ev_valid[sb] = true;
@@ -1372,8 +1398,10 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
     if (n_jobs > 0) {
         if (!out_dev) {
             double* got = h_out + M;  // second half of the pinned result buffer
-            PNB_CUDA_TRY(cudaMemcpyAsync(got, d_out, M * sizeof(double), cudaMemcpyDeviceToHost, st));
-            d2h += M * sizeof(double);
+            if (!fused) {
+                PNB_CUDA_TRY(cudaMemcpyAsync(got, d_out, M * sizeof(double), cudaMemcpyDeviceToHost, st));
+                d2h += M * sizeof(double);
+            }
             cudaError_t e = cudaStreamSynchronize(st);
             if (e != cudaSuccess) {
                 fail_rollback();

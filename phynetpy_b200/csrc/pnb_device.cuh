@@ -84,6 +84,7 @@ struct PruneLaunch {
     const JobDesc* jobs;
     const int32_t* tile_job;   // tile -> job
     const double* Pm;          // batch P matrices [total_ops][16]
+    const double* t;           // FUSED launches: effective branch length per op (P(t) is computed in-kernel)
     double* tile_sum;          // [n_tiles]
     unsigned int* job_done;    // [n_jobs] arrival counters (self-resetting)
     double* out;               // per-job logL
@@ -310,12 +311,17 @@ __device__ __forceinline__ void tip_contrib(uint32_t pk, const uint32_t (&code)[
     }
 }
 
+// FUSED = latency path for small batches (a single-locus MCMC step): the kernel reads the job
+// descriptors, the program and the branch lengths straight from the caller's pinned staging memory,
+// computes P(t) of its ops itself (no K-a launch, no H2D copy) and writes logL to mapped host memory.
+template <bool FUSED>
 __global__ void __launch_bounds__(TPB, PRUNE_MIN_BLOCKS)
-pnb_prune_kernel(const __grid_constant__ PruneLaunch L, const __grid_constant__ ModelParams mp) {
+pnb_prune_kernel_t(const __grid_constant__ PruneLaunch L, const __grid_constant__ ModelParams mp) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar_stage;
     __shared__ double red[TPB / 32];
     __shared__ int s_is_last;
+    __shared__ int s_rows;
 
     const int tid = threadIdx.x;
     const int tile = blockIdx.x + L.tile_base;
@@ -364,6 +370,27 @@ pnb_prune_kernel(const __grid_constant__ PruneLaunch L, const __grid_constant__ 
     uint32_t phase = 0;
     for (int seg = 0; seg < n_ops; seg += seg_cap, phase ^= 1u) {
         const int nseg = min(seg_cap, n_ops - seg);
+        if (FUSED) {
+            if (tid == 0) s_rows = 0;
+            __syncthreads();  // also: every warp is done with the previous segment's shared memory
+            int my_rows = 0;
+            for (int k = tid; k < nseg; k += TPB) {
+                const Op op = g_ops[seg + k];
+                s_ops[k] = op;
+                double Pm[16];
+                pmatrix_of_t(mp, L.t[op_off + seg + k], Pm);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) s_P[k * 16 + i] = Pm[i];
+                if ((op.flags & F_KIND_MASK) == K_TIP && op.src >= 0) {
+                    tma_bulk_g2s(s_codes + static_cast<size_t>(op.aux) * TILE_PATTERNS,
+                                 g_codes + static_cast<int64_t>(op.src) * ld_codes + p0, TILE_PATTERNS, &bar_stage);
+                    ++my_rows;
+                }
+            }
+            if (my_rows) atomicAdd(&s_rows, my_rows);
+            __syncthreads();
+            if (tid == 0) mbar_arrive_expect_tx(&bar_stage, static_cast<uint32_t>(s_rows) * TILE_PATTERNS);
+        } else {
         if (seg > 0) __syncthreads();  // every warp is done with the previous segment's shared memory
         if (tid < 32) {
             if (tid == 0) {
@@ -385,6 +412,7 @@ pnb_prune_kernel(const __grid_constant__ PruneLaunch L, const __grid_constant__ 
             if (tid == 0)
                 mbar_arrive_expect_tx(&bar_stage, static_cast<uint32_t>(nseg) * (sizeof(Op) + 128u) +
                                                       static_cast<uint32_t>(rows) * TILE_PATTERNS);
+        }
         }
         mbar_wait(&bar_stage, phase);
         if (!warp_active) continue;

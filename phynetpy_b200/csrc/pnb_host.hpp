@@ -185,6 +185,7 @@ struct pnb_ctx {
     uint64_t next_model_id = 1;
     uint32_t batch_counter = 0;
     int chunk_min_jobs = 2048;     // batches of at least this many jobs are launched in chunks
+    bool allow_fused = true;       // small batches: single-kernel latency path (PNB_NO_FUSED=1 disables)
     pnb::Arena arena;
     pnb::Buffer d_stage;           // device staging of the batch program (stream-ordered reuse)
     pnb::Buffer h_stage2[2];       // pinned host staging, double-buffered so the host can run ahead

