@@ -568,3 +568,45 @@ def test_engine_entries_invalidated_behind_its_back():
     eng._felsen[7] = None
     assert eng.log_likelihood(trees, None, 0.0) == total
     assert all(v is not None for v in eng._felsen)
+
+
+def test_out_device_on_caller_stream_matches_host_output():
+    """PNB_EVAL_OUT_DEVICE + pnb_ctx_set_stream: the kernel writes per-locus logL straight into a
+    caller-owned device vector (the NCCL buffer of the multi-GPU path) on the caller's stream."""
+    import torch
+    P = _pkg()
+    from phynetpy_b200 import _lib
+    from phynetpy_b200._seq_likelihood import _model_handle
+    from phynetpy_b200.device import pack_trees
+    ec = load_golden("engine_case.json")
+    model = _model(P, ec["model"])
+    calcs = [P.FelsensteinCalculator(dict(l["alignment"])) for l in ec["loci"]]
+    trees = [_tree(P, l["tree"]).flat() for l in ec["loci"]]
+    ctx = calcs[0]._context()
+    for c in calcs:
+        c._locus_handle()
+    handles = np.array([c._locus.value for c in calcs], dtype=np.uint64)
+    node_off, parent, blen, tip_row = pack_trees(trees, [c._row_of for c in calcs])
+    mh = _model_handle(model, ctx)
+    host = ctx.eval(mh, handles, node_off, parent, blen, tip_row, 1.0, _lib.EVAL_FULL)
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+    try:
+        ctx.set_profiling(True)
+        out = torch.full((len(calcs) + 2,), -1.0, dtype=torch.float64, device="cuda")
+        with torch.cuda.stream(stream):
+            ctx.eval(mh, handles, node_off, parent, blen, tip_row, 1.0, _lib.EVAL_FULL, None,
+                     out_device_ptr=out.data_ptr() + 8)
+            doubled = out * 2.0  # ordered after the kernel on the same stream
+        stream.synchronize()
+        tm = ctx.last_timings()
+        assert tm["prune_ms"] > 0.0 and tm["call_ms"] > 0.0
+        got = out.cpu().numpy()
+        assert got[0] == -1.0 and got[-1] == -1.0
+        assert np.array_equal(got[1:-1], host)
+        assert np.array_equal(doubled.cpu().numpy()[1:-1], 2.0 * host)
+        for a, b in zip(host, ec["per_locus"]):
+            assert rel_err(a, b) <= REL
+    finally:
+        ctx.set_profiling(False)
+        ctx.set_stream(None)
