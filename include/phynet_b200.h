@@ -54,6 +54,11 @@ extern "C" {
 #define PNB_EVAL_PENDING    0x2u  /* keep result pending until pnb_commit / pnb_rollback          */
 #define PNB_EVAL_NOSTORE    0x4u  /* score only: read cached partials, write none (candidates)    */
 #define PNB_EVAL_OUT_DEVICE 0x8u  /* logL_out is a DEVICE pointer; call returns without host sync */
+#define PNB_EVAL_RESCALE    0x10u /* beyond the reference: renormalise every node by an exact power of
+                                   * two and carry the exponent, so huge trees do not underflow (the
+                                   * reference, and the default here, floor such sites at 1e-300,
+                                   * src/_seq_likelihood.py:396).  Cached partials of one mode are not
+                                   * reused by the other.                                            */
 
 typedef struct pnb_ctx   pnb_ctx;
 typedef struct pnb_model pnb_model;

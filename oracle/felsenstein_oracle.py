@@ -335,6 +335,43 @@ class OracleCodesLocus:
         return float(np.dot(np.log(site_like), self.weights))
 
 
+def log_likelihood_rescaled(locus: OracleLocus, tree: OracleTree, model: OracleModel, site_rate: float = 1.0) -> float:
+    """NOT in the reference: the same pruning with per-node renormalisation (each node divided by its
+    largest state, the logs accumulated), i.e. what the likelihood is where the reference underflows.
+    Independent check for the library's optional PNB_EVAL_RESCALE mode."""
+    n_pat = locus.n_patterns
+    logscale = np.zeros(n_pat)
+
+    def rec(node: int) -> np.ndarray:
+        nonlocal logscale
+        kids = tree.children[node]
+        if not kids:
+            tip = locus.tip_partials.get(tree.label[node])
+            return np.ones((n_pat, 4)) if tip is None else tip
+        res = np.ones((n_pat, 4))
+        for c in kids:
+            t = tree.blen[c]
+            t = 0.0 if t is None else float(t) * site_rate
+            res = res * (rec(c) @ model.p_matrix(t).T)
+        m = res.max(axis=1)
+        ok = m > 0
+        res[ok] /= m[ok, None]
+        logscale = logscale + np.where(ok, np.log(np.where(ok, m, 1.0)), 0.0)
+        return res
+
+    import sys
+    old = sys.getrecursionlimit()
+    sys.setrecursionlimit(max(old, 10 * len(tree.parent) + 100))
+    try:
+        root = rec(tree.root)
+    finally:
+        sys.setrecursionlimit(old)
+    site = root @ model.pi
+    with np.errstate(divide="ignore"):
+        ls = np.where(site > 0, np.log(np.where(site > 0, site, 1.0)) + logscale, math.log(1e-300))
+    return float(np.dot(ls, locus.weights))
+
+
 # --- engine loop: src/_mcmc_seq.py:746-764 (Felsenstein factor only) -------
 def engine_log_likelihood(loci: Sequence[OracleLocus], trees: Sequence[OracleTree], model: OracleModel) -> Tuple[float, List[float]]:
     per_locus = [log_likelihood(l, t, model) for l, t in zip(loci, trees)]

@@ -42,7 +42,8 @@ class SeqLikelihoodEngine:
 
     def __init__(self, loci: Sequence[Any], species_of: Optional[dict] = None, model: Any = None,
                  branch_thetas: Optional[dict] = None, *, msnc_fn: Optional[MsncFn] = None,
-                 context: Optional[DeviceContext] = None, shard: Optional[ShardPlan] = None) -> None:
+                 context: Optional[DeviceContext] = None, shard: Optional[ShardPlan] = None,
+                 rescale: bool = False) -> None:
         """``loci``: per-locus alignments (``dict`` label -> sequence) or ready
         :class:`FelsensteinCalculator` objects.  With ``shard`` only this rank's loci
         are made resident (entries outside the shard may be ``None``)."""
@@ -64,6 +65,7 @@ class SeqLikelihoodEngine:
         self._dirty: set = set(range(lo, hi))  # local loci whose _felsen entry is None
         self._snap_dirty: dict = {}            # id(snapshot list) -> dirty set at clone time
         self._full_next = False
+        self._mode = _lib.EVAL_RESCALE if rescale else 0  # numerical mode (beyond the reference when set)
         self.last_stats: dict = {}
 
     # -- reference seam (src/_mcmc_seq.py:696-703, :766-772) ------------------
@@ -147,7 +149,7 @@ class SeqLikelihoodEngine:
             self._dirty = {i for i in range(lo, hi) if self._felsen[i] is None}
         dirty = sorted(i for i in self._dirty if self._felsen[i] is None)
         self._dirty.clear()
-        flags = _lib.EVAL_PENDING | (_lib.EVAL_FULL if self._full_next else 0)
+        flags = _lib.EVAL_PENDING | self._mode | (_lib.EVAL_FULL if self._full_next else 0)
         self._full_next = False
         if self._shard.world_size == 1:
             if dirty:
@@ -206,7 +208,7 @@ class SeqLikelihoodEngine:
         node_off, parent, blen, tip_row = pack_trees(flats, [self._calcs[i]._row_of for i in idx])
         P_edge = _explicit_P_edges(self._model, blen, site_rate) if _device_kind(self._model) == "explicit" else None
         out = ctx.eval(_model_handle(self._model, ctx), self._handles(idx), node_off, parent, blen, tip_row,
-                       site_rate, _lib.EVAL_NOSTORE, P_edge)
+                       site_rate, _lib.EVAL_NOSTORE | self._mode, P_edge)
         self.last_stats = ctx.last_stats()
         res, k = [], 0
         for _, trees in sets:
@@ -226,6 +228,6 @@ class SeqLikelihoodEngine:
         node_off, parent, blen, tip_row = pack_trees(flats, [row] * len(trees))
         P_edge = _explicit_P_edges(self._model, blen, site_rate) if _device_kind(self._model) == "explicit" else None
         out = ctx.eval(_model_handle(self._model, ctx), self._handles(idx), node_off, parent, blen, tip_row,
-                       site_rate, _lib.EVAL_NOSTORE, P_edge)
+                       site_rate, _lib.EVAL_NOSTORE | self._mode, P_edge)
         self.last_stats = ctx.last_stats()
         return out

@@ -27,6 +27,7 @@ EVAL_FULL = 0x1
 EVAL_PENDING = 0x2
 EVAL_NOSTORE = 0x4
 EVAL_OUT_DEVICE = 0x8
+EVAL_RESCALE = 0x10
 
 # every symbol include/phynet_b200.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = (

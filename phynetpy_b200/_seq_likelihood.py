@@ -421,18 +421,23 @@ class FelsensteinCalculator:
 
     # -- evaluation ---------------------------------------------------------------
     def log_likelihood(self, gene_tree: Any, model: Any, *, site_rate: float = 1.0,
-                       full: bool = False) -> float:
+                       full: bool = False, rescale: bool = False) -> float:
         """Felsenstein log-likelihood of the alignment on ``gene_tree`` (reference :369-397).
 
         ``gene_tree`` is borrowed and not mutated; any object with the reference's
         ``Network`` read API, a :class:`~phynetpy_b200.tree.GeneTree` or a
         :class:`~phynetpy_b200.tree.FlatTree`.  ``full=True`` ignores cached partials.
+
+        ``rescale=True`` is an option beyond the reference: every node is renormalised by an
+        exact power of two and carries its exponent, so trees of thousands of taxa do not
+        underflow.  The default reproduces the reference exactly, including its floor of
+        ``1e-300`` per site (:396) when a site likelihood underflows.
         """
         ft = flatten(gene_tree)
         ctx = self._context()
         self._locus_handle()
         node_off, parent, blen, tip_row = pack_trees([ft], [self._row_of])
-        flags = _lib.EVAL_FULL if full else 0
+        flags = (_lib.EVAL_FULL if full else 0) | (_lib.EVAL_RESCALE if rescale else 0)
         mh = _model_handle(model, ctx)
         P_edge = _explicit_P_edges(model, blen, float(site_rate)) if _device_kind(model) == "explicit" else None
         out = ctx.eval(mh, self._handle_arr, node_off, parent, blen, tip_row, float(site_rate), flags, P_edge)

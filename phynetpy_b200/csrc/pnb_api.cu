@@ -156,10 +156,16 @@ extern "C" int pnb_ctx_create(int device, pnb_ctx** out) {
         return PNB_ERR_CUDA;
     }
     ctx->stream = ctx->own_stream;
-    se = cudaFuncSetAttribute(pnb_prune_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    se = cudaFuncSetAttribute(pnb_prune_kernel_t<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               ctx->max_smem_optin - 1024);
     if (se == cudaSuccess)
-        se = cudaFuncSetAttribute(pnb_prune_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        se = cudaFuncSetAttribute(pnb_prune_kernel_t<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  ctx->max_smem_optin - 1024);
+    if (se == cudaSuccess)
+        se = cudaFuncSetAttribute(pnb_prune_kernel_t<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  ctx->max_smem_optin - 1024);
+    if (se == cudaSuccess)
+        se = cudaFuncSetAttribute(pnb_prune_kernel_t<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   ctx->max_smem_optin - 1024);
     if (se != cudaSuccess) {
         cudaStreamDestroy(ctx->own_stream);
@@ -364,6 +370,9 @@ extern "C" int pnb_compress(pnb_ctx* ctx, int use_device, const uint8_t* cols, i
 // =====================================================================
 static void locus_free_partials(pnb_locus* loc) {
     loc->committed_from_tmpl = loc->pending_from_tmpl = false;
+    if (loc->d_scale) loc->ctx->arena.release(loc->d_scale, loc->scale_bytes);
+    loc->d_scale = nullptr;
+    loc->scale_bytes = 0;
     if (loc->d_partials) loc->ctx->arena.release(loc->d_partials, loc->partials_bytes);
     loc->d_partials = nullptr;
     loc->partials_bytes = 0;
@@ -574,8 +583,9 @@ int compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int32_t n
     };
     // ---- fastest path: a full, immediately committed re-evaluation of the topology the committed
     // cache already describes (same slots): refresh branch lengths in place, no pending image.
+    const bool rescale = (flags & PNB_EVAL_RESCALE) != 0;
     if (!nostore && full && !(flags & PNB_EVAL_PENDING) && loc->committed_from_tmpl && C.valid &&
-        loc->tmpl[0].n_slots == loc->n_slots && same_topology(loc->tmpl[0])) {
+        C.rescale == rescale && loc->tmpl[0].n_slots == loc->n_slots && same_topology(loc->tmpl[0])) {
         const pnb_locus::Template& T0 = loc->tmpl[0];
         refresh_program(T0);
         const size_t ne = T0.kid_child.size();
@@ -591,10 +601,11 @@ int compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int32_t n
         return PNB_OK;
     }
     if (!nostore) {
-        if (C.valid && C.model_id != m->id) locus_reset_cache(loc);  // partials of another model are useless
+        // partials of another model, or stored in the other numerical mode, are useless
+        if (C.valid && (C.model_id != m->id || C.rescale != rescale)) locus_reset_cache(loc);
         if (full && !(flags & PNB_EVAL_PENDING)) locus_reset_cache(loc);
     }
-    const bool can_lookup = C.valid && !full && C.model_id == m->id;
+    const bool can_lookup = C.valid && !full && C.model_id == m->id && C.rescale == rescale;
     // every node will be recomputed and (store mode) slots come off the free list in canonical order
     const bool all_dirty_canonical = nostore ? !can_lookup : !C.valid;
     // ---- fast path: same topology as the last all-dirty compilation of this locus --------------
@@ -619,6 +630,7 @@ int compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int32_t n
             P_.kid_len.resize(ne);
             for (size_t e = 0; e < ne; ++e) P_.kid_len[e] = dbits(eff_len(T.kid_child[e]));
             P_.model_id = m->id;
+            P_.rescale = rescale;
             P_.valid = true;
             P_.logL_valid = false;
             loc->free_slots.resize(static_cast<size_t>(loc->n_slots - T.slots_used));
@@ -715,6 +727,7 @@ int compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int32_t n
         P_.stored.assign(loc->n_slots, 0);
         P_.node_ref.assign(n, REF_ABSENT);
         P_.model_id = m->id;
+        P_.rescale = rescale;
     }
     int n_dirty = 0;
     bool templ_ok = true;
@@ -1041,6 +1054,7 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
             fn(0, 0, n);
         }
     };
+    const bool rescale_flag = (flags & PNB_EVAL_RESCALE) != 0;
     for (auto& S : ctx->scratch) { S.first_err_job = -1; S.tiles = 0; S.grow.clear(); }
     parallel_for(M, 512, [&](int w, int64_t j0, int64_t j1) {
         CompileScratch& S = ctx->scratch[w];
@@ -1063,7 +1077,9 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
                     continue;
                 }
                 // a tree with nn nodes has at most nn - 1 internal nodes; growing slots is rare and serial
-                if (loc->n_slots < std::max<int64_t>(2 * (nn - 1), 2)) S.grow.push_back(j);
+                if (loc->n_slots < std::max<int64_t>(2 * (nn - 1), 2) || (rescale_flag && !loc->d_scale)) S.grow.push_back(j);
+            } else if (rescale_flag && !loc->d_scale && loc->n_slots > 0) {
+                S.grow.push_back(j);  // NOSTORE reading committed partials in RESCALE mode needs the exponent array
             }
             S.tiles += (loc->P + TILE_PATTERNS - 1) / TILE_PATTERNS;
         }
@@ -1076,6 +1092,7 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
         }
         total_tiles += S.tiles;
     }
+    const bool rescale = (flags & PNB_EVAL_RESCALE) != 0;
     for (auto& S : ctx->scratch) {
         for (int64_t j : S.grow) {
             pnb_locus* loc = loci[j];
@@ -1086,9 +1103,18 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
                 if (par[i] >= 0 && par[i] < nn) has_kid[par[i]] = 1;
             int n_int = 0;
             for (int64_t i = 0; i < nn; ++i) n_int += has_kid[i];
-            if (loc->n_slots < std::max(2 * n_int, 2)) {
+            if (!nostore && loc->n_slots < std::max(2 * n_int, 2)) {
                 int rc0 = locus_ensure_slots(loc, n_int);
                 if (rc0) return rc0;
+            }
+            if (rescale && !loc->d_scale && loc->n_slots > 0) {
+                const size_t bytes = static_cast<size_t>(loc->n_slots) * loc->P_pad * sizeof(int32_t);
+                void* pp = nullptr;
+                int rc0 = ctx->arena.alloc(bytes, &pp);
+                if (rc0) return rc0;
+                loc->d_scale = static_cast<int32_t*>(pp);
+                loc->scale_bytes = bytes;
+                PNB_CUDA_TRY(cudaMemsetAsync(pp, 0, bytes, ctx->stream));
             }
         }
     }
@@ -1259,6 +1285,8 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
             jd.tile0 = static_cast<int32_t>(n_tiles);
             jd.n_tiles = static_cast<int32_t>((loc->P + TILE_PATTERNS - 1) / TILE_PATTERNS);
             jd.out_index = static_cast<int32_t>(j);
+            jd.scale = loc->d_scale;
+            jd.pad0 = 0;
             const pnb_locus::Template* Th = jo.tmpl_hit >= 0 ? &loc->tmpl[jo.tmpl_hit] : nullptr;
             const bool resident = Th && Th->d_ops_valid && jo.n_ops > 0;
             jd.ops = resident ? Th->d_ops : reinterpret_cast<const Op*>(prog_base + off_ops) + o;
@@ -1286,7 +1314,7 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
         if (cj == 0) continue;
         const size_t dyn_smem = static_cast<size_t>(ops_cap) * (sizeof(Op) + 128) +
                                 static_cast<size_t>(rows_cap) * TILE_PATTERNS +
-                                static_cast<size_t>(stk_cap) * TILE_PATTERNS * 32;
+                                static_cast<size_t>(stk_cap) * TILE_PATTERNS * (rescale ? 36 : 32);
         if (dyn_smem > static_cast<size_t>(ctx->max_smem_optin - 1024)) {
             cudaStreamSynchronize(st);
             fail_rollback();
@@ -1379,11 +1407,14 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
             memset_done = true;
         }
         if (ctx->profiling && c == 0) PNB_CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
+        const unsigned grid = static_cast<unsigned>(ct);
         if (fused) {
-            pnb_prune_kernel_t<true><<<static_cast<unsigned>(ct), TPB, dyn_smem, st>>>(L, m->mp);
+            if (rescale) pnb_prune_kernel_t<true, true><<<grid, TPB, dyn_smem, st>>>(L, m->mp);
+            else pnb_prune_kernel_t<true, false><<<grid, TPB, dyn_smem, st>>>(L, m->mp);
             stage_read_by_kernel = true;
         } else {
-            pnb_prune_kernel_t<false><<<static_cast<unsigned>(ct), TPB, dyn_smem, st>>>(L, m->mp);
+            if (rescale) pnb_prune_kernel_t<false, true><<<grid, TPB, dyn_smem, st>>>(L, m->mp);
+            else pnb_prune_kernel_t<false, false><<<grid, TPB, dyn_smem, st>>>(L, m->mp);
         }
         PNB_CUDA_TRY(cudaGetLastError());
         if (ctx->profiling && c == n_chunks - 1) { PNB_CUDA_TRY(cudaEventRecord(ctx->ev[3], st)); ctx->ev_prune = true; }

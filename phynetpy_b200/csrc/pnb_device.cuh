@@ -69,6 +69,8 @@ struct __align__(16) JobDesc {
     int32_t n_tiles;
     int32_t out_index;      // where the job's logL goes in the output vector
     const Op* ops;          // the job's op program: in the batch staging area, or the locus' resident copy
+    int32_t* scale;         // RESCALE launches: [n_slots][P_pad] binary exponent carried by each stored partial
+    int64_t pad0;
 };
 
 struct ModelParams {
@@ -255,6 +257,24 @@ __device__ __forceinline__ void lds_op(uint32_t a, uint32_t& f, int32_t& src, in
 // OUT may alias nothing in `l`; ACCUM = multiply the result into `out` instead of overwriting it.
 template <bool ACCUM>
 __device__ __forceinline__ void matvec(uint32_t pk, const Vec4 (&l)[PPT], Vec4 (&out)[PPT]) {
+#ifdef PNB_MATVEC_P_IN_REGS
+    // the whole 4x4 P in registers, then one pattern at a time: `out` may alias `l`
+    double p[16];
+    lds_v2f64<0>(pk, p[0], p[1]);    lds_v2f64<16>(pk, p[2], p[3]);
+    lds_v2f64<32>(pk, p[4], p[5]);   lds_v2f64<48>(pk, p[6], p[7]);
+    lds_v2f64<64>(pk, p[8], p[9]);   lds_v2f64<80>(pk, p[10], p[11]);
+    lds_v2f64<96>(pk, p[12], p[13]); lds_v2f64<112>(pk, p[14], p[15]);
+#pragma unroll
+    for (int u = 0; u < PPT; ++u) {
+        const double a0 = l[u].x0, a1 = l[u].x1, a2 = l[u].x2, a3 = l[u].x3;
+        const double r0 = fma(p[3], a3, fma(p[2], a2, fma(p[1], a1, p[0] * a0)));
+        const double r1 = fma(p[7], a3, fma(p[6], a2, fma(p[5], a1, p[4] * a0)));
+        const double r2 = fma(p[11], a3, fma(p[10], a2, fma(p[9], a1, p[8] * a0)));
+        const double r3 = fma(p[15], a3, fma(p[14], a2, fma(p[13], a1, p[12] * a0)));
+        if (ACCUM) { out[u].x0 *= r0; out[u].x1 *= r1; out[u].x2 *= r2; out[u].x3 *= r3; }
+        else { out[u].x0 = r0; out[u].x1 = r1; out[u].x2 = r2; out[u].x3 = r3; }
+    }
+#else
     double r[PPT][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -275,6 +295,7 @@ __device__ __forceinline__ void matvec(uint32_t pk, const Vec4 (&l)[PPT], Vec4 (
             out[u].x0 = r[u][0]; out[u].x1 = r[u][1]; out[u].x2 = r[u][2]; out[u].x3 = r[u][3];
         }
     }
+#endif
 }
 
 // contribution of a tip child: column(s) of P selected by the device tip code
@@ -314,7 +335,10 @@ __device__ __forceinline__ void tip_contrib(uint32_t pk, const uint32_t (&code)[
 // FUSED = latency path for small batches (a single-locus MCMC step): the kernel reads the job
 // descriptors, the program and the branch lengths straight from the caller's pinned staging memory,
 // computes P(t) of its ops itself (no K-a launch, no H2D copy) and writes logL to mapped host memory.
-template <bool FUSED>
+// RESCALE = optional numerical mode beyond the reference: every completed node is renormalised by an
+// exact power of two and carries the binary exponent of its subtree, so trees of thousands of taxa do
+// not underflow (the reference, and the default mode here, floor such sites at 1e-300).
+template <bool FUSED, bool RESCALE>
 __global__ void __launch_bounds__(TPB, PRUNE_MIN_BLOCKS)
 pnb_prune_kernel_t(const __grid_constant__ PruneLaunch L, const __grid_constant__ ModelParams mp) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -360,8 +384,13 @@ pnb_prune_kernel_t(const __grid_constant__ PruneLaunch L, const __grid_constant_
     const uint32_t stk_addr = smem_u32(s_stk) + tid * 16;
 
     Vec4 acc[PPT];  // node under construction; once complete it is also the register-forwarded child
+    int acc_e[PPT]; // RESCALE: binary exponent carried by `acc` (true partial = acc * 2^acc_e)
 #pragma unroll
-    for (int u = 0; u < PPT; ++u) acc[u] = {1.0, 1.0, 1.0, 1.0};
+    for (int u = 0; u < PPT; ++u) { acc[u] = {1.0, 1.0, 1.0, 1.0}; acc_e[u] = 0; }
+    int32_t* scale0 = RESCALE ? jd.scale + (p0 + tid) : nullptr;
+    const int64_t scale_stride = slot_stride / 4;  // ints per slot (= P_pad)
+    // stash exponents live behind the stash partials: [stk_cap][TILE_PATTERNS] int32
+    const uint32_t stk_e_addr = smem_u32(s_stk) + static_cast<uint32_t>(L.stk_cap) * (TILE_PATTERNS * 32) + tid * 4;
 
     // The program is walked in segments of at most SEG_MAX_OPS ops (one segment for trees of up to
     // ~97 taxa): warp 0 is the TMA producer of a segment -- its ops, its P matrices and the code rows
@@ -432,19 +461,33 @@ pnb_prune_kernel_t(const __grid_constant__ PruneLaunch L, const __grid_constant_
                     code[u] = (src >= 0) ? lds_u8(codes_addr + aux * TILE_PATTERNS + u * TPB) : 0x8Fu;
                 if (first) tip_contrib<false>(pk, code, acc);
                 else tip_contrib<true>(pk, code, acc);
+                if (RESCALE && first) {
+#pragma unroll
+                    for (int u = 0; u < PPT; ++u) acc_e[u] = 0;
+                }
             } else if (kind == K_REG) {
                 // the child is the node completed just before: its partial is still in `acc`
                 // (the host always emits the forwarded child as the FIRST op of its parent)
+#ifdef PNB_MATVEC_P_IN_REGS
+                matvec<false>(pk, acc, acc);
+#else
                 Vec4 v[PPT];
                 matvec<false>(pk, acc, v);
 #pragma unroll
                 for (int u = 0; u < PPT; ++u) acc[u] = v[u];
+#endif
             } else {
                 Vec4 l[PPT];
+                int le[PPT];
                 if (kind == K_MEM) {
                     const double* g = part0 + static_cast<int64_t>(src) * slot_stride;
 #pragma unroll
                     for (int u = 0; u < PPT; ++u) ldg256(g + u * TPB * 4, l[u].x0, l[u].x1, l[u].x2, l[u].x3);
+                    if (RESCALE) {
+                        const int32_t* ge = scale0 + static_cast<int64_t>(src) * scale_stride;
+#pragma unroll
+                        for (int u = 0; u < PPT; ++u) le[u] = ge[u * TPB];
+                    }
                 } else {
                     const uint32_t a = stk_addr + static_cast<uint32_t>(src) * (TILE_PATTERNS * 32);
 #pragma unroll
@@ -452,16 +495,43 @@ pnb_prune_kernel_t(const __grid_constant__ PruneLaunch L, const __grid_constant_
                         lds_v2f64<0>(a + u * TPB * 16, l[u].x0, l[u].x1);
                         lds_v2f64<TILE_PATTERNS * 16>(a + u * TPB * 16, l[u].x2, l[u].x3);
                     }
+                    if (RESCALE) {
+                        const uint32_t ae = stk_e_addr + static_cast<uint32_t>(src) * (TILE_PATTERNS * 4);
+#pragma unroll
+                        for (int u = 0; u < PPT; ++u)
+                            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(le[u]) : "r"(ae + u * TPB * 4));
+                    }
                 }
                 if (first) matvec<false>(pk, l, acc);
                 else matvec<true>(pk, l, acc);
+                if (RESCALE) {
+#pragma unroll
+                    for (int u = 0; u < PPT; ++u) acc_e[u] = first ? le[u] : acc_e[u] + le[u];
+                }
             }
             if (flags & F_LAST) {
+                if (RESCALE) {
+#pragma unroll
+                    for (int u = 0; u < PPT; ++u) {
+                        const double mx = fmax(fmax(acc[u].x0, acc[u].x1), fmax(acc[u].x2, acc[u].x3));
+                        if (mx > 0.0) {  // exact renormalisation by 2^-e, e = binary exponent of the largest state
+                            const int e = ((__double2hiint(mx) >> 20) & 0x7ff) - 1023;
+                            const double f = __hiloint2double((1023 - e) << 20, 0);
+                            acc[u].x0 *= f; acc[u].x1 *= f; acc[u].x2 *= f; acc[u].x3 *= f;
+                            acc_e[u] += e;
+                        }
+                    }
+                }
                 if (flags & F_STORE) {
                     double* g = part0 + static_cast<int64_t>(dst) * slot_stride;
 #pragma unroll
                     for (int u = 0; u < PPT; ++u)
                         stg256(g + u * TPB * 4, acc[u].x0, acc[u].x1, acc[u].x2, acc[u].x3);
+                    if (RESCALE) {
+                        int32_t* ge = scale0 + static_cast<int64_t>(dst) * scale_stride;
+#pragma unroll
+                        for (int u = 0; u < PPT; ++u) ge[u * TPB] = acc_e[u];
+                    }
                 }
                 if (flags & F_PUSH) {
                     const uint32_t a = stk_addr + ((flags >> 8) & 0xffu) * (TILE_PATTERNS * 32);
@@ -469,6 +539,12 @@ pnb_prune_kernel_t(const __grid_constant__ PruneLaunch L, const __grid_constant_
                     for (int u = 0; u < PPT; ++u) {
                         sts_v2f64(a + u * TPB * 16, acc[u].x0, acc[u].x1);
                         sts_v2f64(a + u * TPB * 16 + TILE_PATTERNS * 16, acc[u].x2, acc[u].x3);
+                    }
+                    if (RESCALE) {
+                        const uint32_t ae = stk_e_addr + ((flags >> 8) & 0xffu) * (TILE_PATTERNS * 4);
+#pragma unroll
+                        for (int u = 0; u < PPT; ++u)
+                            asm volatile("st.shared.s32 [%0], %1;" :: "r"(ae + u * TPB * 4), "r"(acc_e[u]) : "memory");
                     }
                 }
             }
@@ -485,16 +561,26 @@ pnb_prune_kernel_t(const __grid_constant__ PruneLaunch L, const __grid_constant_
         const int pat = p0 + tid + u * TPB;
         if (pat >= P) continue;
         Vec4 r = acc[u];
+        int re = RESCALE ? acc_e[u] : 0;
         if (root_kind == K_MEM) {
             ldg256(part0 + static_cast<int64_t>(root_src) * slot_stride + u * TPB * 4, r.x0, r.x1, r.x2, r.x3);
+            if (RESCALE) re = scale0[static_cast<int64_t>(root_src) * scale_stride + u * TPB];
         } else if (root_kind == K_TIP) {
+            re = 0;
             const uint32_t c = (root_src >= 0) ? g_codes[static_cast<int64_t>(root_src) * ld_codes + pat] : 0x8Fu;
             const uint32_t m = (c & 0x80u) ? (c & 0xFu) : (1u << c);
             r = {(m & 1u) ? 1.0 : 0.0, (m & 2u) ? 1.0 : 0.0, (m & 4u) ? 1.0 : 0.0, (m & 8u) ? 1.0 : 0.0};
         }
         double site = fma(r.x3, mp.pi[3], fma(r.x2, mp.pi[2], fma(r.x1, mp.pi[1], r.x0 * mp.pi[0])));
-        site = (site < 1e-300) ? 1e-300 : site;  // np.maximum(site_like, 1e-300): NaN propagates
-        lsum = fma(log(site), weights[pat], lsum);
+        if (RESCALE) {
+            // log(site * 2^re); a site that is exactly impossible keeps the reference's floor
+            const double ls = (site > 0.0) ? fma(static_cast<double>(re), 0.6931471805599453094, log(site))
+                                           : ((site == 0.0) ? -690.77552789821370 : site);
+            lsum = fma(ls, weights[pat], lsum);
+        } else {
+            site = (site < 1e-300) ? 1e-300 : site;  // np.maximum(site_like, 1e-300): NaN propagates
+            lsum = fma(log(site), weights[pat], lsum);
+        }
     }
 
     // fused per-locus reduction: tile sum -> last-arriving tile sums tiles in index order

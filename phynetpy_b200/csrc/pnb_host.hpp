@@ -217,12 +217,15 @@ struct pnb_locus {
     uint8_t* d_codes = nullptr;
     double* d_weights = nullptr;
     double* d_partials = nullptr;
+    int32_t* d_scale = nullptr;   // [n_slots][P_pad] exponents of the stored partials (RESCALE mode), lazily allocated
+    size_t scale_bytes = 0;
     int32_t n_slots = 0;
     size_t codes_bytes = 0, weights_bytes = 0, partials_bytes = 0;
 
     // One cached tree description: which partial slot holds which (children, lengths) node.
     struct TreeCache {
         bool valid = false;
+        bool rescale = false;             // the stored partials carry exponents (PNB_EVAL_RESCALE)
         uint64_t model_id = 0;
         std::vector<int32_t> kid_begin;   // per slot: range in kid_ref/kid_len, -1 = slot unused
         std::vector<int32_t> kid_count;

@@ -610,3 +610,44 @@ def test_out_device_on_caller_stream_matches_host_output():
     finally:
         ctx.set_profiling(False)
         ctx.set_stream(None)
+
+
+def test_rescale_mode_beyond_the_reference():
+    """PNB_EVAL_RESCALE: (1) on trees where nothing underflows it agrees with the default mode (and
+    hence the reference) to ~1e-13; (2) on a 1,200-taxon tree the default mode reproduces the
+    reference's floor (every site at log(1e-300)), while the rescaled mode gives the true likelihood,
+    checked against an independently rescaled NumPy pruning; (3) dirty path and NOSTORE work in it."""
+    P = _pkg()
+    from phynetpy_b200 import simulate as S
+    model = P.GTR(S.DEFAULT_PI, S.DEFAULT_RATES)
+    om = O.gtr(S.DEFAULT_PI, S.DEFAULT_RATES)
+    for case in CASES[:12]:
+        fc = P.FelsensteinCalculator(dict(case["alignment"]))
+        a = fc.log_likelihood(_tree(P, case["tree"]), _model(P, case["model"]), site_rate=case["site_rate"])
+        b = fc.log_likelihood(_tree(P, case["tree"]), _model(P, case["model"]), site_rate=case["site_rate"], rescale=True)
+        assert rel_err(b, a) <= 1e-12 and rel_err(b, case["logL"]) <= REL
+    rng = np.random.default_rng(5150)
+    n, L = 1200, 60
+    par, bl = S.random_trees(1, n, rng, height=1.5)
+    aln = S.simulate_alignments(par, bl, L, S.DEFAULT_PI, S.DEFAULT_RATES, rng)[0]
+    ft = S.flat_trees(par, bl)[0]
+    taxa = S.tip_labels(n)
+    fc = P.FelsensteinCalculator.from_matrix(taxa, aln, device_compress=False)
+    locus = O.OracleLocus(S.to_alignment_dict(aln))
+    ref_like = O.log_likelihood(locus, _otree(ft), om)          # what the reference returns: the floor
+    assert ref_like == pytest.approx(L * math.log(1e-300), rel=1e-12)
+    assert rel_err(fc.log_likelihood(ft, model), ref_like) <= REL
+    true_ll = O.log_likelihood_rescaled(locus, _otree(ft), om)
+    assert true_ll < ref_like                                     # far below the floor
+    got = fc.log_likelihood(ft, model, rescale=True)
+    assert rel_err(got, true_ll) <= REL
+    b2 = ft.blen.copy()
+    b2[17] *= 3.0
+    t2 = ft.with_lengths(b2)
+    got2 = fc.log_likelihood(t2, model, rescale=True)
+    assert fc._context().last_stats()["nodes_recomputed"] < 200
+    assert rel_err(got2, O.log_likelihood_rescaled(locus, _otree(t2), om)) <= REL
+    eng = P.SeqLikelihoodEngine([fc], None, model, rescale=True)
+    assert eng.log_likelihood([t2], None, 0.0) == got2
+    vals = eng.score_candidates(0, [ft, t2])
+    assert vals[1] == got2 and rel_err(vals[0], true_ll) <= REL
