@@ -199,6 +199,7 @@ def main():
     ap.add_argument("--workload", default="auto", choices=["auto"] + sorted(WORKLOADS))
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (smoke runs only; reported)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-allreduce", action="store_true", help="diagnostic only: time the sharded step without the collective")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -284,7 +285,7 @@ def main():
         """inputs resident in HBM; logL stays on the device; all-reduce when sharded"""
         with torch.cuda.stream(stream):
             ctx.eval(mh, handles, node_off, parent, next_blen(), tip_row, 1.0, flags, None, out_device_ptr=out_local_ptr)
-            if world > 1:
+            if world > 1 and not args.skip_allreduce:
                 out_vec.copy_(local_vec)   # zeros outside this rank's range: the sum is exact
                 dist.all_reduce(out_vec)
 
@@ -331,11 +332,12 @@ def main():
 
     # ---- per-kernel durations: same steps again with CUDA events around each kernel launch ----
     ctx.set_profiling(True)
-    prune_ms, pm_ms, comp_ms = [], [], []
+    prune_ms, pm_ms, comp_ms, call_ms = [], [], [], []
     for _ in range(args.steps):
         step_device()
         tm = ctx.last_timings()  # waits for this step's events
         prune_ms.append(tm["prune_ms"]); pm_ms.append(tm["pmatrix_ms"]); comp_ms.append(tm["compile_ms"])
+        call_ms.append(tm["call_ms"])
     barrier()
 
     # ---- score-only mode (PNB_EVAL_NOSTORE): same evaluation, partials never leave the SM ----
@@ -429,7 +431,7 @@ def main():
                 "parallelism": "loci sharded over %d GPU(s), one process per GPU" % world,
                 "l2": "working set per step (%.2f GB of partials written) exceeds the 126 MB L2; no flush needed"
                       % (updates_local * 32 / 1e9),
-                "scale": args.scale,
+                "scale": args.scale, "diagnostic_skip_allreduce": bool(args.skip_allreduce),
                 **setup,
             },
             "e2e": {
@@ -448,7 +450,7 @@ def main():
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_update": ALGO_BYTES_PER_UPDATE,
                 "kernel_ms": k_ms, "pmatrix_kernel_ms": float(np.mean(pm_ms)),
-                "host_compile_ms": float(np.mean(comp_ms)),
+                "host_compile_ms": float(np.mean(comp_ms)), "host_call_ms": float(np.mean(call_ms)),
                 "note": "achieved uses the 96 B/update streaming model; the kernel keeps a node's freshly computed "
                         "child in registers, so its real DRAM traffic (`traffic`) is lower than algorithmic",
             },

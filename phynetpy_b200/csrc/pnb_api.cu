@@ -156,6 +156,16 @@ extern "C" int pnb_ctx_create(int device, pnb_ctx** out) {
         return PNB_ERR_CUDA;
     }
     ctx->stream = ctx->own_stream;
+    se = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 8 && se == cudaSuccess; ++i)
+        se = cudaEventCreateWithFlags(&ctx->chunk_ready[i], cudaEventDisableTiming);
+    if (se == cudaSuccess) se = cudaEventCreateWithFlags(&ctx->prev_done, cudaEventDisableTiming);
+    if (se != cudaSuccess) {
+        set_error("pnb_ctx_create: stream/event creation failed: %s", cudaGetErrorString(se));
+        cudaStreamDestroy(ctx->own_stream);
+        delete ctx;
+        return PNB_ERR_CUDA;
+    }
     se = cudaFuncSetAttribute(pnb_prune_kernel_t<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               ctx->max_smem_optin - 1024);
     if (se == cudaSuccess)
@@ -198,6 +208,9 @@ extern "C" int pnb_ctx_destroy(pnb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     delete ctx->pool;
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    for (auto& e : ctx->chunk_ready) if (e) cudaEventDestroy(e);
+    if (ctx->prev_done) cudaEventDestroy(ctx->prev_done);
     for (auto& b : ctx->h_stage2) if (b.p) cudaFreeHost(b.p);
     for (auto& e : ctx->stage_ev) if (e) cudaEventDestroy(e);
     if (ctx->h_out.p) cudaFreeHost(ctx->h_out.p);
@@ -221,6 +234,7 @@ extern "C" int pnb_ctx_set_stream(pnb_ctx* ctx, void* cuda_stream) {
 extern "C" int pnb_ctx_synchronize(pnb_ctx* ctx) {
     PNB_REQUIRE(ctx != nullptr, PNB_ERR_INVALID, "pnb_ctx_synchronize: ctx is NULL");
     PNB_CUDA_TRY(cudaSetDevice(ctx->device));
+    PNB_CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
     PNB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return PNB_OK;
 }
@@ -1186,7 +1200,8 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
             else locus_rollback(loci[q]);
         }
     };
-    const int64_t n_chunks = (M >= ctx->chunk_min_jobs) ? std::max<int64_t>(1, std::min<int64_t>(8, 2 * M / ctx->chunk_min_jobs)) : 1;
+    // ~1,000 jobs per chunk: below that the extra launches / events cost more than the overlap gains
+    const int64_t n_chunks = std::max<int64_t>(1, std::min<int64_t>(8, M / ctx->chunk_min_jobs));
     if ((rc = ensure_device(ctx->d_P, static_cast<size_t>(std::max<int64_t>(ops_bound, 1)) * 128))) return rc;
     if ((rc = ensure_device(ctx->d_tile_sum, static_cast<size_t>(std::max<int64_t>(total_tiles, 1)) * sizeof(double)))) return rc;
     if ((rc = ensure_device(ctx->d_out, static_cast<size_t>(M) * sizeof(double)))) return rc;
@@ -1210,6 +1225,15 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
     }
     const char* prog_base = fused ? hs : ds;  // where non-resident op programs are read from
     bool stage_read_by_kernel = false;
+    // Chunked batches upload (and run K-a for) chunk c+1 on the copy stream while the main stream prunes
+    // chunk c.  The copy stream may only start once the previous evaluation's kernels, which read the
+    // single-buffered device staging area and P array, are done.
+    const bool two_streams = n_chunks > 1;
+    cudaStream_t up = two_streams ? ctx->copy_stream : st;
+    if (two_streams) {
+        PNB_CUDA_TRY(cudaEventRecord(ctx->prev_done, st));  // everything queued on the main stream so far
+        PNB_CUDA_TRY(cudaStreamWaitEvent(up, ctx->prev_done, 0));
+    }
 
     int64_t n_jobs = 0, n_tiles = 0, n_ops_used = 0, updates = 0, n_cached = 0, n_dirty_nodes = 0;
     int64_t h2d = 0, d2h = 0, launches = 0;
@@ -1326,30 +1350,30 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
         if (fused) {
             // nothing to copy: the kernel reads the staging buffer in place
         } else if (n_chunks == 1 && stage_bytes <= (256u << 10)) {
-            PNB_CUDA_TRY(cudaMemcpyAsync(ds, hs, stage_bytes, cudaMemcpyHostToDevice, st));
+            PNB_CUDA_TRY(cudaMemcpyAsync(ds, hs, stage_bytes, cudaMemcpyHostToDevice, up));
             h2d += stage_bytes;
         } else {
             PNB_CUDA_TRY(cudaMemcpyAsync(ds + off_jobs + jobs_first * sizeof(JobDesc), hs + off_jobs + jobs_first * sizeof(JobDesc),
-                                         cj * sizeof(JobDesc), cudaMemcpyHostToDevice, st));
+                                         cj * sizeof(JobDesc), cudaMemcpyHostToDevice, up));
             PNB_CUDA_TRY(cudaMemcpyAsync(ds + off_tiles + tiles_first * sizeof(int32_t), hs + off_tiles + tiles_first * sizeof(int32_t),
-                                         ct * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+                                         ct * sizeof(int32_t), cudaMemcpyHostToDevice, up));
             h2d += cj * sizeof(JobDesc) + ct * sizeof(int32_t);
             if (prog_lo >= 0) {
                 PNB_CUDA_TRY(cudaMemcpyAsync(ds + off_ops + prog_lo * sizeof(Op), hs + off_ops + prog_lo * sizeof(Op),
-                                             (prog_hi - prog_lo) * sizeof(Op), cudaMemcpyHostToDevice, st));
+                                             (prog_hi - prog_lo) * sizeof(Op), cudaMemcpyHostToDevice, up));
                 h2d += (prog_hi - prog_lo) * sizeof(Op);
             }
             if (n_op_range > 0) {
                 if (!explicit_P) {
                     PNB_CUDA_TRY(cudaMemcpyAsync(ds + off_t + ops_lo * sizeof(double), hs + off_t + ops_lo * sizeof(double),
-                                                 n_op_range * sizeof(double), cudaMemcpyHostToDevice, st));
+                                                 n_op_range * sizeof(double), cudaMemcpyHostToDevice, up));
                     h2d += n_op_range * sizeof(double);
                 }
             }
         }
         if (n_op_range > 0 && explicit_P) {
             PNB_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(ctx->d_P.p) + ops_lo * 128, h_pexp + ops_lo * 16, n_op_range * 128,
-                                         cudaMemcpyHostToDevice, st));
+                                         cudaMemcpyHostToDevice, up));
             h2d += n_op_range * 128;
         }
         // programs compiled from scratch in this chunk get a device-resident copy next to their locus, so
@@ -1373,20 +1397,24 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
             }
             const int64_t o = node_off[j] - node_off[0] - j;
             PNB_CUDA_TRY(cudaMemcpyAsync(Tn.d_ops, prog_base + off_ops + o * sizeof(Op), static_cast<size_t>(nops) * sizeof(Op),
-                                         fused ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
+                                         fused ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, up));
             if (fused) h2d += static_cast<size_t>(nops) * sizeof(Op);
             Tn.d_ops_valid = true;
         }
         const bool prof = ctx->profiling && n_chunks == 1;
         if (n_op_range > 0 && !explicit_P && !fused) {
             const int64_t blocks = (n_op_range + 127) / 128;
-            if (prof) PNB_CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
-            pnb_pmatrix_kernel<<<static_cast<unsigned>(blocks), 128, 0, st>>>(
+            if (prof) PNB_CUDA_TRY(cudaEventRecord(ctx->ev[0], up));
+            pnb_pmatrix_kernel<<<static_cast<unsigned>(blocks), 128, 0, up>>>(
                 m->mp, reinterpret_cast<const double*>(ds + off_t) + ops_lo, n_op_range,
                 static_cast<double*>(ctx->d_P.p) + ops_lo * 16);
             PNB_CUDA_TRY(cudaGetLastError());
-            if (prof) { PNB_CUDA_TRY(cudaEventRecord(ctx->ev[1], st)); ctx->ev_ka = true; }
+            if (prof) { PNB_CUDA_TRY(cudaEventRecord(ctx->ev[1], up)); ctx->ev_ka = true; }
             launches++;
+        }
+        if (two_streams) {
+            PNB_CUDA_TRY(cudaEventRecord(ctx->chunk_ready[c], up));
+            PNB_CUDA_TRY(cudaStreamWaitEvent(st, ctx->chunk_ready[c], 0));
         }
         PruneLaunch L;
         L.jobs = reinterpret_cast<const JobDesc*>(prog_base + off_jobs);
@@ -1423,7 +1451,7 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
     ctx->t_compile_ms = compile_ms;
     if (h2d > 0 || stage_read_by_kernel) {  // the pinned buffer may be rewritten once every reader of it is done
         if (!ctx->stage_ev[sb]) PNB_CUDA_TRY(cudaEventCreateWithFlags(&ctx->stage_ev[sb], cudaEventDisableTiming));
-        PNB_CUDA_TRY(cudaEventRecord(ctx->stage_ev[sb], st));
+        PNB_CUDA_TRY(cudaEventRecord(ctx->stage_ev[sb], stage_read_by_kernel ? st : up));
         ctx->stage_ev_valid[sb] = true;
     }
     if (n_jobs > 0) {

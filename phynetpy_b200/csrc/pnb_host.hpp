@@ -180,11 +180,15 @@ struct pnb_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // uploads + K-a of chunk c+1 run here while `stream` prunes chunk c
+    cudaEvent_t chunk_ready[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t prev_done = nullptr;      // last pruning launch of the previous evaluation (it reads d_stage / d_P)
+    bool prev_done_valid = false;
     int sm_count = 0;
     int max_smem_optin = 0;
     uint64_t next_model_id = 1;
     uint32_t batch_counter = 0;
-    int chunk_min_jobs = 2048;     // batches of at least this many jobs are launched in chunks
+    int chunk_min_jobs = 1024;     // batches of at least this many jobs are launched in chunks
     bool allow_fused = true;       // small batches: single-kernel latency path (PNB_NO_FUSED=1 disables)
     pnb::Arena arena;
     pnb::Buffer d_stage;           // device staging of the batch program (stream-ordered reuse)

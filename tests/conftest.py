@@ -14,7 +14,7 @@ import pytest
 
 # read once when the device context is created: make the GPU tests exercise the chunked launch path
 # with batches of a few hundred loci instead of thousands
-os.environ.setdefault("PNB_CHUNK_MIN_JOBS", "256")
+os.environ.setdefault("PNB_CHUNK_MIN_JOBS", "128")
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:

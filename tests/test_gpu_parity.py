@@ -546,7 +546,7 @@ def test_many_candidates_one_locus_parallel_compile_with_templates():
         t = topo[int(rng.integers(0, 3))]
         cands.append(t.with_lengths(t.blen * scales[k % 5] * (1.0 + 0.001 * (k // 5))))
     vals = eng.score_candidates(0, cands)
-    assert eng.last_stats["launches"] in (2, 4)   # one (K-a, prune) pair per chunk
+    assert eng.last_stats["launches"] >= 2 and eng.last_stats["launches"] % 2 == 0  # (K-a, prune) per chunk
     fc = P.FelsensteinCalculator(d)
     for k in list(range(0, 300, 23)) + [299]:
         assert vals[k] == fc.log_likelihood(cands[k], model, full=True)
