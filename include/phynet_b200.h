@@ -174,6 +174,22 @@ PNB_API int pnb_eval(pnb_ctx *ctx, const pnb_model *m, int64_t M, pnb_locus *con
 PNB_API int pnb_commit(pnb_ctx *ctx, int64_t M, pnb_locus *const *loci);
 PNB_API int pnb_rollback(pnb_ctx *ctx, int64_t M, pnb_locus *const *loci);
 
+/* ---- host-only planning (tests of the host runtime; no device involved) -- */
+/* A planning context owns no GPU: loci created on it hold no device memory and
+ * pnb_eval on it fails.  pnb_plan runs exactly the host half of pnb_eval -- cache
+ * resolution against the committed tree, op-program compilation, slot assignment,
+ * commit / pending bookkeeping (same flags) -- and returns the programs instead of
+ * launching them, so the CPU test-suite can interpret them against the oracle.
+ * job_info[j*8..]: n_ops, n_tip_ops, root_kind (0 TIP / 1 MEM / 2 REG), root_src,
+ * stash need, nodes recomputed, staged code rows per segment, 1 if served from cache.
+ * ops_out: int32[4] per op (flags, src, dst, aux), job j at offset
+ * (node_off[j] - node_off[0] - j); t_out: effective branch length per op.     */
+PNB_API int pnb_ctx_create_host(pnb_ctx **out);
+PNB_API int pnb_plan(pnb_ctx *ctx, const pnb_model *m, int64_t M, pnb_locus *const *loci,
+                     const int64_t *node_off, const int32_t *parent, const double *blen,
+                     const int32_t *tip_row, double site_rate, uint32_t flags,
+                     int32_t *job_info, int32_t *ops_out, double *t_out);
+
 #ifdef __cplusplus
 }
 #endif

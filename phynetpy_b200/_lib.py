@@ -38,6 +38,7 @@ ABI_SYMBOLS = (
     "pnb_pmatrix_batch", "pnb_compress",
     "pnb_locus_create", "pnb_locus_destroy", "pnb_locus_invalidate", "pnb_locus_read_partial",
     "pnb_eval", "pnb_commit", "pnb_rollback",
+    "pnb_ctx_create_host", "pnb_plan",
 )
 
 
@@ -94,6 +95,8 @@ def load() -> C.CDLL:
             "pnb_eval": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, C.c_uint32, _vp],
             "pnb_commit": [_vp, _i64, _vp],
             "pnb_rollback": [_vp, _i64, _vp],
+            "pnb_ctx_create_host": [C.POINTER(_vp)],
+            "pnb_plan": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, C.c_double, C.c_uint32, _vp, _vp, _vp],
         }
         for name, argtypes in sigs.items():
             fn = getattr(lib, name)

@@ -203,8 +203,22 @@ extern "C" int pnb_ctx_create(int device, pnb_ctx** out) {
     return PNB_OK;
 }
 
+extern "C" int pnb_ctx_create_host(pnb_ctx** out) {
+    PNB_REQUIRE(out != nullptr, PNB_ERR_INVALID, "pnb_ctx_create_host: out is NULL");
+    pnb_ctx* ctx = new (std::nothrow) pnb_ctx();
+    PNB_REQUIRE(ctx != nullptr, PNB_ERR_NOMEM, "pnb_ctx_create_host: out of host memory");
+    ctx->device = -1;  // planning only: no stream, no arena, no kernels
+    ctx->scratch.resize(1);
+    *out = ctx;
+    return PNB_OK;
+}
+
 extern "C" int pnb_ctx_destroy(pnb_ctx* ctx) {
     if (!ctx) return PNB_OK;
+    if (ctx->device < 0) {
+        delete ctx;
+        return PNB_OK;
+    }
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     delete ctx->pool;
@@ -224,7 +238,7 @@ extern "C" int pnb_ctx_destroy(pnb_ctx* ctx) {
 }
 
 extern "C" int pnb_ctx_set_stream(pnb_ctx* ctx, void* cuda_stream) {
-    PNB_REQUIRE(ctx != nullptr, PNB_ERR_INVALID, "pnb_ctx_set_stream: ctx is NULL");
+    PNB_REQUIRE(ctx != nullptr && ctx->device >= 0, PNB_ERR_INVALID, "pnb_ctx_set_stream: NULL or host-only context");
     PNB_CUDA_TRY(cudaSetDevice(ctx->device));
     PNB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
@@ -232,7 +246,7 @@ extern "C" int pnb_ctx_set_stream(pnb_ctx* ctx, void* cuda_stream) {
 }
 
 extern "C" int pnb_ctx_synchronize(pnb_ctx* ctx) {
-    PNB_REQUIRE(ctx != nullptr, PNB_ERR_INVALID, "pnb_ctx_synchronize: ctx is NULL");
+    PNB_REQUIRE(ctx != nullptr && ctx->device >= 0, PNB_ERR_INVALID, "pnb_ctx_synchronize: NULL or host-only context");
     PNB_CUDA_TRY(cudaSetDevice(ctx->device));
     PNB_CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
     PNB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -240,7 +254,7 @@ extern "C" int pnb_ctx_synchronize(pnb_ctx* ctx) {
 }
 
 extern "C" int pnb_ctx_set_profiling(pnb_ctx* ctx, int enable) {
-    PNB_REQUIRE(ctx != nullptr, PNB_ERR_INVALID, "pnb_ctx_set_profiling: ctx is NULL");
+    PNB_REQUIRE(ctx != nullptr && ctx->device >= 0, PNB_ERR_INVALID, "pnb_ctx_set_profiling: NULL or host-only context");
     PNB_CUDA_TRY(cudaSetDevice(ctx->device));
     if (enable && !ctx->ev[0])
         for (auto& e : ctx->ev) PNB_CUDA_TRY(cudaEventCreate(&e));
@@ -331,6 +345,7 @@ extern "C" int pnb_model_destroy(pnb_model* m) {
 extern "C" int pnb_pmatrix_batch(pnb_ctx* ctx, const pnb_model* m, const double* t, int64_t nb,
                                  double* P_out) {
     PNB_REQUIRE(ctx && m, PNB_ERR_INVALID, "pnb_pmatrix_batch: NULL handle");
+    PNB_REQUIRE(ctx->device >= 0, PNB_ERR_STATE, "pnb_pmatrix_batch: host-only planning context has no device");
     PNB_REQUIRE(m->mp.kind != 2, PNB_ERR_INVALID,
                 "pnb_pmatrix_batch: explicit models have no device P(t); compute it on the host");
     PNB_REQUIRE(nb >= 0, PNB_ERR_INVALID, "pnb_pmatrix_batch: nb < 0");
@@ -410,6 +425,11 @@ static int locus_ensure_slots(pnb_locus* loc, int n_internal) {
     const int want = std::max(2 * n_internal, 2);
     if (loc->n_slots >= want) return PNB_OK;
     locus_free_partials(loc);
+    if (loc->ctx->device < 0) {  // planning context: slot ids only
+        loc->n_slots = want;
+        locus_reset_cache(loc);
+        return PNB_OK;
+    }
     const size_t bytes = static_cast<size_t>(want) * loc->P_pad * 4 * sizeof(double);
     void* p = nullptr;
     int rc = loc->ctx->arena.alloc(bytes, &p);
@@ -436,14 +456,14 @@ extern "C" int pnb_locus_create(pnb_ctx* ctx, int32_t n_rows, int64_t P, const u
                 static_cast<long long>(P));
     PNB_REQUIRE(P == 0 || (codes && weights && ld_codes >= P), PNB_ERR_INVALID,
                 "pnb_locus_create: NULL array or ld_codes < P");
-    PNB_CUDA_TRY(cudaSetDevice(ctx->device));
+    if (ctx->device >= 0) PNB_CUDA_TRY(cudaSetDevice(ctx->device));
     pnb_locus* loc = new (std::nothrow) pnb_locus();
     PNB_REQUIRE(loc != nullptr, PNB_ERR_NOMEM, "pnb_locus_create: out of host memory");
     loc->ctx = ctx;
     loc->n_rows = n_rows;
     loc->P = P;
     loc->P_pad = static_cast<int64_t>(align_up(static_cast<size_t>(std::max<int64_t>(P, 1)), TILE_PATTERNS));
-    if (P > 0) {
+    if (P > 0 && ctx->device >= 0) {
         loc->codes_bytes = static_cast<size_t>(n_rows) * loc->P_pad;
         loc->weights_bytes = static_cast<size_t>(loc->P_pad) * sizeof(double);
         void* p = nullptr;
@@ -487,6 +507,11 @@ extern "C" int pnb_locus_create(pnb_ctx* ctx, int32_t n_rows, int64_t P, const u
 extern "C" int pnb_locus_destroy(pnb_locus* loc) {
     if (!loc) return PNB_OK;
     pnb_ctx* ctx = loc->ctx;
+    if (ctx->device < 0) {
+        ctx->n_loci_alive--;
+        delete loc;
+        return PNB_OK;
+    }
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     locus_free_partials(loc);
@@ -1033,6 +1058,7 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
                         const int32_t* tip_row, const double* P_edge, double site_rate, uint32_t flags,
                         double* logL_out) {
     PNB_REQUIRE(ctx && m, PNB_ERR_INVALID, "pnb_eval: NULL handle");
+    PNB_REQUIRE(ctx->device >= 0, PNB_ERR_STATE, "pnb_eval: host-only planning context has no device (use pnb_plan)");
     PNB_REQUIRE(m->ctx == ctx, PNB_ERR_INVALID, "pnb_eval: model belongs to another context");
     PNB_REQUIRE(M >= 0, PNB_ERR_INVALID, "pnb_eval: M < 0");
     memset(ctx->stats, 0, sizeof(ctx->stats));
@@ -1495,6 +1521,68 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
     ctx->stats[5] = d2h;
     ctx->stats[6] = n_cached;
     ctx->stats[7] = n_dirty_nodes;
+    return PNB_OK;
+}
+
+extern "C" int pnb_plan(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* const* loci,
+                        const int64_t* node_off, const int32_t* parent, const double* blen,
+                        const int32_t* tip_row, double site_rate, uint32_t flags, int32_t* job_info,
+                        int32_t* ops_out, double* t_out) {
+    PNB_REQUIRE(ctx && m && m->ctx == ctx, PNB_ERR_INVALID, "pnb_plan: NULL handle or foreign model");
+    PNB_REQUIRE(ctx->device < 0, PNB_ERR_STATE, "pnb_plan: needs a host-only context (pnb_ctx_create_host)");
+    PNB_REQUIRE(M >= 0 && (M == 0 || (loci && node_off && parent && job_info && ops_out && t_out)), PNB_ERR_INVALID,
+                "pnb_plan: NULL array");
+    PNB_REQUIRE(!(flags & PNB_EVAL_OUT_DEVICE), PNB_ERR_INVALID, "pnb_plan: OUT_DEVICE makes no sense without a device");
+    const bool nostore = flags & PNB_EVAL_NOSTORE;
+    PNB_REQUIRE(!(nostore && (flags & PNB_EVAL_PENDING)), PNB_ERR_INVALID, "pnb_plan: NOSTORE and PENDING are mutually exclusive");
+    const bool auto_commit = !nostore && !(flags & PNB_EVAL_PENDING);
+    const uint32_t mark = ++ctx->batch_counter;
+    CompileScratch& S = ctx->scratch[0];
+    static_assert(sizeof(Op) == 4 * sizeof(int32_t), "Op layout");
+    for (int64_t j = 0; j < M; ++j) {
+        pnb_locus* loc = loci[j];
+        PNB_REQUIRE(loc && loc->ctx == ctx, PNB_ERR_INVALID, "pnb_plan: bad locus (job %lld)", static_cast<long long>(j));
+        const int64_t b = node_off[j];
+        const int64_t nn = node_off[j + 1] - b;
+        PNB_REQUIRE(nn >= 1 && nn < (1 << 24), PNB_ERR_INVALID, "pnb_plan: job %lld has an invalid node count", static_cast<long long>(j));
+        if (!nostore) {
+            PNB_REQUIRE(loc->batch_mark.exchange(mark) != mark, PNB_ERR_INVALID,
+                        "pnb_eval: locus appears twice in a storing batch; use PNB_EVAL_NOSTORE (job %lld)", static_cast<long long>(j));
+            PNB_REQUIRE(!loc->has_pending, PNB_ERR_STATE,
+                        "pnb_eval: locus has a pending evaluation; commit or roll back first (job %lld)", static_cast<long long>(j));
+            int n_int = 0;
+            std::vector<uint8_t> has_kid(nn, 0);
+            for (int64_t i = 0; i < nn; ++i) {
+                const int32_t pa = parent[b + i];
+                if (pa >= 0 && pa < nn) has_kid[pa] = 1;
+            }
+            for (int64_t i = 0; i < nn; ++i) n_int += has_kid[i];
+            int rc0 = locus_ensure_slots(loc, n_int);
+            if (rc0) return rc0;
+        }
+        const int64_t o = b - node_off[0] - j;
+        JobOut jo;
+        S.err[0] = 0;
+        jo.rc = compile_job(S, loc, m, static_cast<int32_t>(nn), parent + b, blen ? blen + b : nullptr,
+                            tip_row ? tip_row + b : nullptr, nullptr, site_rate, flags,
+                            reinterpret_cast<Op*>(ops_out) + o, t_out + o, nullptr, &jo);
+        if (jo.rc != PNB_OK) {
+            set_error("%s (job %lld)", S.err, static_cast<long long>(j));
+            for (int64_t q = 0; q <= j; ++q) {
+                if (nostore) break;
+                if (auto_commit) locus_reset_cache(loci[q]); else locus_rollback(loci[q]);
+            }
+            return jo.rc >= 100 ? PNB_ERR_STATE : jo.rc;
+        }
+        // a template hit with a valid resident copy does not rewrite the program: hand it out anyway
+        if (jo.tmpl_hit >= 0 && loc->tmpl[jo.tmpl_hit].d_ops_valid && jo.n_ops > 0)
+            memcpy(reinterpret_cast<Op*>(ops_out) + o, loc->tmpl[jo.tmpl_hit].ops.data(), static_cast<size_t>(jo.n_ops) * sizeof(Op));
+        const bool cached = jo.root_clean_cached;
+        if (auto_commit && !jo.in_place) locus_commit(loc);
+        int32_t* info = job_info + j * 8;
+        info[0] = jo.n_ops; info[1] = jo.n_tip_ops; info[2] = jo.root_kind; info[3] = jo.root_src;
+        info[4] = jo.stk_need; info[5] = jo.n_dirty; info[6] = jo.rows_cap; info[7] = cached ? 1 : 0;
+    }
     return PNB_OK;
 }
 

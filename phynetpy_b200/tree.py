@@ -46,7 +46,8 @@ class FlatTree:
     def n_children(self) -> np.ndarray:
         if self._n_children is None:
             p = self.parent
-            self._n_children = np.bincount(p[p >= 0], minlength=p.shape[0]).astype(np.int32)
+            ok = (p >= 0) & (p < p.shape[0])  # out-of-range parents are reported by the library, not here
+            self._n_children = np.bincount(p[ok], minlength=p.shape[0]).astype(np.int32)
         return self._n_children
 
     def with_lengths(self, blen: np.ndarray) -> "FlatTree":
