@@ -363,24 +363,25 @@ def test_ragged_batch_many_loci_vs_oracle():
 
 
 def test_large_locus_full_size_properties():
-    """cfg2-like size on one GPU (50 taxa, >=2e5 patterns): size-independent properties --
+    """BASELINE cfg2 at full size on one GPU (50 taxa, 1e6 unique patterns): size-independent properties --
     (1) total == sum over disjoint pattern blocks evaluated as separate loci (linearity),
     (2) dirty-path == full, (3) oracle agreement on a 20k-pattern prefix block."""
     P = _pkg()
     from phynetpy_b200 import simulate as S
     rng = np.random.default_rng(2)
-    n, L = 50, 250_000
+    n, L = 50, 1_060_000
     par, bl = S.random_trees(1, n, rng)
-    aln = S.simulate_alignments(par, bl, L, S.DEFAULT_PI, S.DEFAULT_RATES, rng)[0]
+    aln = np.concatenate([S.simulate_alignments(par, bl, min(132_500, L - c0), S.DEFAULT_PI, S.DEFAULT_RATES, rng)[0]
+                          for c0 in range(0, L, 132_500)], axis=1)
     ft = S.flat_trees(par, bl)[0]
     model = P.GTR(S.DEFAULT_PI, S.DEFAULT_RATES)
     taxa = S.tip_labels(n)
     fc = P.FelsensteinCalculator.from_matrix(taxa, aln, device_compress=True)
-    assert fc.n_patterns > 200_000 and int(fc._int_weights.sum()) == L
+    assert fc.n_patterns >= 1_000_000 and int(fc._int_weights.sum()) == L
     whole = fc.log_likelihood(ft, model)
     parts = []
-    for lo in range(0, fc.n_patterns, 50_000):
-        sub = P.FelsensteinCalculator.from_codes(taxa, fc._codes[:, lo:lo + 50_000], fc._int_weights[lo:lo + 50_000])
+    for lo in range(0, fc.n_patterns, 200_000):
+        sub = P.FelsensteinCalculator.from_codes(taxa, fc._codes[:, lo:lo + 200_000], fc._int_weights[lo:lo + 200_000])
         parts.append(sub.log_likelihood(ft, model))
         if lo == 0:
             exp0 = O.log_likelihood_codes(fc._codes[:, :20_000], fc._int_weights[:20_000],
@@ -651,3 +652,35 @@ def test_rescale_mode_beyond_the_reference():
     assert eng.log_likelihood([t2], None, 0.0) == got2
     vals = eng.score_candidates(0, [ft, t2])
     assert vals[1] == got2 and rel_err(vals[0], true_ll) <= REL
+
+
+def test_cfg5_shape_batch_split_invariance():
+    """BASELINE cfg5 shape (32 taxa x 2,000 sites per locus) at 192 loci: the per-locus values do not
+    depend on how the loci are batched (one call, two calls, locus by locus) -- the property that makes
+    the multi-GPU sum independent of the number of ranks -- and a sample agrees with the oracle."""
+    P = _pkg()
+    from phynetpy_b200 import simulate as S
+    rng = np.random.default_rng(55)
+    M, n, L = 192, 32, 2000
+    par, bl = S.random_trees(M, n, rng)
+    aln = S.simulate_alignments(par, bl, L, S.DEFAULT_PI, S.DEFAULT_RATES, rng)
+    trees = S.flat_trees(par, bl)
+    taxa = S.tip_labels(n)
+    model = P.GTR(S.DEFAULT_PI, S.DEFAULT_RATES)
+    calcs = [P.FelsensteinCalculator.from_matrix(taxa, aln[i], device_compress=False) for i in range(M)]
+    one = P.SeqLikelihoodEngine(calcs, None, model)
+    total = one.log_likelihood(trees, None, 0.0)
+    whole = list(one._felsen)
+    a = P.SeqLikelihoodEngine(calcs[:100], None, model)
+    b = P.SeqLikelihoodEngine(calcs[100:], None, model)
+    a.invalidate_device_cache(); b.invalidate_device_cache()
+    ta = a.log_likelihood(trees[:100], None, 0.0)
+    tb = b.log_likelihood(trees[100:], None, 0.0)
+    assert a._felsen + b._felsen == whole
+    assert rel_err(ta + tb, total) <= 1e-14
+    for i in (0, 77, 191):
+        assert calcs[i].log_likelihood(trees[i], model, full=True) == whole[i]
+    om = O.gtr(S.DEFAULT_PI, S.DEFAULT_RATES)
+    for i in (3, 150):
+        exp = O.log_likelihood(O.OracleLocus(S.to_alignment_dict(aln[i])), _otree(trees[i]), om)
+        assert rel_err(whole[i], exp) <= REL
