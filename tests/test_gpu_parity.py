@@ -671,11 +671,13 @@ def test_cfg5_shape_batch_split_invariance():
     one = P.SeqLikelihoodEngine(calcs, None, model)
     total = one.log_likelihood(trees, None, 0.0)
     whole = list(one._felsen)
+    one._commit_pending()   # the engines below share the loci: nothing may stay pending
     a = P.SeqLikelihoodEngine(calcs[:100], None, model)
     b = P.SeqLikelihoodEngine(calcs[100:], None, model)
     a.invalidate_device_cache(); b.invalidate_device_cache()
     ta = a.log_likelihood(trees[:100], None, 0.0)
     tb = b.log_likelihood(trees[100:], None, 0.0)
+    a._commit_pending(); b._commit_pending()
     assert a._felsen + b._felsen == whole
     assert rel_err(ta + tb, total) <= 1e-14
     for i in (0, 77, 191):
