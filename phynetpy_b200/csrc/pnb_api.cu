@@ -197,6 +197,7 @@ extern "C" int pnb_ctx_create(int device, pnb_ctx** out) {
     workers = std::max(1, std::min(workers, 32));
     if (const char* e = getenv("PNB_CHUNK_MIN_JOBS")) ctx->chunk_min_jobs = std::max(2, atoi(e));
     if (const char* e = getenv("PNB_NO_FUSED")) ctx->allow_fused = atoi(e) == 0;
+    if (const char* e = getenv("PNB_STORE_STASH")) ctx->store_stash_levels = std::max(0, std::min(atoi(e), 8));
     ctx->scratch.resize(workers);
     if (workers > 1) ctx->pool = new (std::nothrow) WorkerPool(workers);
     *out = ctx;
@@ -209,6 +210,7 @@ extern "C" int pnb_ctx_create_host(pnb_ctx** out) {
     PNB_REQUIRE(ctx != nullptr, PNB_ERR_NOMEM, "pnb_ctx_create_host: out of host memory");
     ctx->device = -1;  // planning only: no stream, no arena, no kernels
     ctx->scratch.resize(1);
+    if (const char* e = getenv("PNB_STORE_STASH")) ctx->store_stash_levels = std::max(0, std::min(atoi(e), 8));
     *out = ctx;
     return PNB_OK;
 }
@@ -866,6 +868,7 @@ int compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int32_t n
     // shared-memory stash (NOSTORE).
     int n_ops = 0, n_tip_ops = 0;
     const bool compute_root = cnt[root] > 0 && (dirty[root] || virt[root]);
+    const int stash_levels = nostore ? (1 << 30) : loc->ctx->store_stash_levels;
     if (compute_root) {
         auto& fs = S.frames;
         auto& dk = S.dk;
@@ -900,7 +903,7 @@ int compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int32_t n
                     const int sp = f.sp;
                     const bool is_last = i == f.kd - 1;
                     int disp = -1;
-                    if (!is_last) disp = nostore ? sp + i : -2;
+                    if (!is_last) disp = (nostore || sp + i < stash_levels) ? sp + i : -2;
                     open(d, sp + i, disp);
                     continue;
                 }
@@ -924,7 +927,7 @@ int compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int32_t n
             if (f.kd > 0) add(K_REG, 0, 0, dk[base + f.kd - 1]);
             for (int i = 0; i + 1 < f.kd; ++i) {
                 const int d = dk[base + i];
-                if (nostore) add(K_STK, f.sp + i, 0, d);
+                if (nostore || f.sp + i < stash_levels) add(K_STK, f.sp + i, 0, d);
                 else add(K_MEM, static_cast<int>(ref[d] - n_rows), 0, d);
             }
             for (int j = 0; j < cnt[v]; ++j) {
@@ -970,7 +973,7 @@ int compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int32_t n
     jo->n_ops = n_ops;
     jo->n_tip_ops = n_tip_ops;
     jo->n_dirty = n_dirty;
-    jo->stk_need = (nostore && compute_root) ? need[root] : 0;
+    jo->stk_need = compute_root ? std::min(need[root], stash_levels) : 0;
     if (cnt[root] == 0) {
         jo->root_kind = K_TIP;
         jo->root_src = static_cast<int>(ref[root]);

@@ -189,6 +189,8 @@ struct pnb_ctx {
     uint64_t next_model_id = 1;
     uint32_t batch_counter = 0;
     int chunk_min_jobs = 1024;     // batches of at least this many jobs are launched in chunks
+    int store_stash_levels = 0;    // storing evaluations: siblings waiting at stash index < this use shared memory
+                                   // instead of an L2 round trip through their slot (PNB_STORE_STASH)
     bool allow_fused = true;       // small batches: single-kernel latency path (PNB_NO_FUSED=1 disables)
     pnb::Arena arena;
     pnb::Buffer d_stage;           // device staging of the batch program (stream-ordered reuse)
