@@ -96,7 +96,7 @@ struct PruneLaunch {
     int32_t tile_base;         // first tile of this launch (a batch may be launched in chunks)
 };
 
-#ifdef PNB_DEVICE_KERNELS  // kernel bodies: compiled into exactly one translation unit (pnb_api.cu)
+#ifdef PNB_DEVICE_KERNELS  // kernel bodies: compiled into exactly one translation unit (pnb_eval.cu)
 
 // ------------------------------------------------------------------------
 // PTX helpers: 256-bit global access, mbarrier, TMA bulk copy (UBLKCP)

@@ -61,6 +61,15 @@ struct Buffer {
     void* p = nullptr;
     size_t cap = 0;
 };
+int ensure_device(Buffer& b, size_t bytes);
+int ensure_pinned(Buffer& b, size_t bytes);
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline uint64_t dbits(double x) {
+    uint64_t u;
+    memcpy(&u, &x, 8);
+    return u;
+}
 
 // Result of compiling one (locus, tree) job into an op program.
 struct JobOut {
@@ -277,3 +286,18 @@ struct pnb_locus {
     std::vector<int32_t> free_slots;
     std::atomic<uint32_t> batch_mark{0};  // duplicate detection inside one pnb_eval batch
 };
+
+namespace pnb {
+// pnb_runtime.cu
+void locus_free_partials(pnb_locus* loc);
+void locus_reset_cache(pnb_locus* loc);
+int locus_ensure_slots(pnb_locus* loc, int n_internal);
+// pnb_compile.cu
+int compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int32_t n, const int32_t* parent,
+                const double* blen, const int32_t* tip_row, const double* P_edge, double site_rate,
+                uint32_t flags, Op* ops, double* t_out, double* Pexp_out, JobOut* jo);
+void locus_commit(pnb_locus* loc);
+void locus_rollback(pnb_locus* loc);
+// pnb_eval.cu: opt the pruning kernels into large dynamic shared memory; returns a cudaError_t
+int configure_kernels(pnb_ctx* ctx);
+}  // namespace pnb
