@@ -379,6 +379,17 @@ def main():
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     st_e2e = ctx.last_stats()
+    # the same call one level up: the reference-shaped Python facade with a Network-like tree OBJECT
+    # (root()/get_children()/get_edge().get_length()), marshalled per call as the reference's callers do
+    facade_ms = None
+    if wl == "cfg2":
+        gt = P.GeneTree.from_flat(trees[0])
+        calcs[0].log_likelihood(gt, model, full=True)
+        t0 = time.perf_counter()
+        nrep = min(args.steps, 10)
+        for _ in range(nrep):
+            facade_val = calcs[0].log_likelihood(gt, model, full=True)
+        facade_ms = (time.perf_counter() - t0) * 1e3 / nrep
     barrier()
     clocks = sampler.stop() if rank == 0 else None
 
@@ -439,6 +450,10 @@ def main():
                 "h2d_bytes_per_step": int(st_e2e["h2d_bytes"]), "d2h_bytes_per_step": int(st_e2e["d2h_bytes"]),
                 "what": "pnb_eval through the C ABI: host tree arrays in (compiled to the op program on the host, "
                         "copied H2D), kernels, per-locus logL copied D2H; alignment resident since construction",
+                "python_facade_ms_per_step": facade_ms,
+                "python_facade_what": None if facade_ms is None else
+                    "FelsensteinCalculator.log_likelihood(tree object, model, full=True): per-call marshalling of a "
+                    "Network-like object included",
             },
             "gpu_launches": int(launches_per_step * args.steps),
             "kernels_per_step": {"pnb_pmatrix_kernel": 1, "pnb_prune_kernel": 1},
