@@ -367,6 +367,7 @@ def main():
     chain = None
     if wl == "cfg4" and world == 1:
         chain = chain_steps(P, ctx, calcs, trees, model, n_steps=max(200, 20 * args.steps))
+        chain["coupled_move_candidates"] = candidate_batch(P, ctx, calcs, trees, model, n_loci=min(200, len(calcs)))
 
     # ---- timed: end to end through the C ABI with host buffers ---------------------------
     for _ in range(2):
@@ -552,6 +553,36 @@ def chain_steps(P, ctx, calcs, trees, model, n_steps, seed=4):
         "median_c_abi_call_us": float(np.median(c_ms) * 1e3),
         "full_recompute_total": full,
         "per_locus_incremental_equals_full_recompute_bitwise": bool(incremental == list(eng._felsen)),
+    }
+
+
+def candidate_batch(P, ctx, calcs, trees, model, n_loci):
+    """The coupled moves' inner double loop (reference src/_mcmc_seq.py:2028 x :1935-1957): for every locus
+    the candidate set (tree + height-preserving NNI neighbours) x (0.25, 0.5, 1, 2, 4), every member scored
+    by a full pruning -- here all loci x all candidates in ONE PNB_EVAL_NOSTORE call."""
+    from phynetpy_b200.candidates import candidate_set
+    eng = P.SeqLikelihoodEngine(calcs[:n_loci], None, model, context=ctx)
+    base = eng.log_likelihood(trees[:n_loci], None, 0.0)
+    eng._commit_pending()
+    t0 = time.perf_counter()
+    sets = [(i, candidate_set(trees[i])) for i in range(n_loci)]
+    t_enum = time.perf_counter() - t0
+    n_trees = sum(len(c) for _, c in sets)
+    eng.score_candidate_sets(sets)                     # warm-up (templates, buffers)
+    t0 = time.perf_counter()
+    res = eng.score_candidate_sets(sets)
+    wall = time.perf_counter() - t0
+    st = dict(eng.last_stats)
+    tm = ctx.last_timings()
+    # the identity candidate of every locus must reproduce the committed tree's value
+    ident_ok = all(any(v == eng._felsen[i] for v in vals) for (i, _), vals in zip(sets, res))
+    return {
+        "what": "all candidates of %d loci scored in one device call (NOSTORE), Python packing included" % n_loci,
+        "candidate_trees": n_trees, "trees_per_locus": n_trees / n_loci,
+        "seconds": wall, "trees_per_s": n_trees / wall, "updates_per_s": st["updates"] / wall,
+        "c_abi_call_ms": tm["call_ms"], "host_compile_ms": tm["compile_ms"],
+        "enumeration_seconds_python": t_enum,
+        "identity_candidate_reproduces_committed_value": bool(ident_ok), "base_total": base,
     }
 
 

@@ -1,0 +1,145 @@
+"""Candidate gene trees of the coupled moves, on flat arrays.
+
+The reference's coupled add / delete / relocate-reticulation moves re-draw every locus' gene
+tree from a finite set: the tree, its height-preserving NNI neighbours, each at the height scales
+(0.25, 0.5, 1, 2, 4) (``_candidate_set`` ``src/_mcmc_seq.py:1836-1861``,
+``_gene_tree_nni_neighbors`` ``:1724-1788``, ``_scaled_gene_tree`` ``:1819-1833``,
+``_gt_signature`` ``:1699-1713``, ``_HEIGHT_SCALE_GRID`` ``:1816``) and score every member with a
+full Felsenstein pruning (``:1935-1957``) -- up to ``5*(1+2(n-2))`` prunings per locus, forward and
+reverse.  That loop is the dominant source of Felsenstein calls in a chain.
+
+Here the set is enumerated on :class:`~phynetpy_b200.tree.FlatTree` arrays (no graph cloning) so
+that ``SeqLikelihoodEngine.score_candidate_sets`` can score all loci x all candidates in one
+device call.  Same semantics as the reference:
+
+* node height = max over children of (child height + branch length), leaves at 0, a missing
+  length counts as 0 (``src/GraphUtils.py:786-819``);
+* an NNI around internal node ``v`` (parent ``p``, single sibling ``s``) swaps ``s`` with a child
+  ``c`` of ``v`` and is allowed only if ``h[v] > h[s]``; node heights are preserved and every
+  branch length is re-derived as ``max(h[parent] - h[child], 0)`` (``_sync_lengths`` ``:418-434``);
+* scaling multiplies every node height by an exact power of two;
+* candidates are de-duplicated by (descendant-leaf-set, round(height, 12)) of the internal nodes.
+"""
+from __future__ import annotations
+
+from typing import FrozenSet, List, Sequence, Tuple
+
+import numpy as np
+
+from .tree import FlatTree
+
+HEIGHT_SCALE_GRID: Tuple[float, ...] = (0.25, 0.5, 1.0, 2.0, 4.0)
+
+
+def _children(parent: np.ndarray) -> List[List[int]]:
+    kids: List[List[int]] = [[] for _ in range(parent.shape[0])]
+    for i, p in enumerate(parent):
+        if p >= 0:
+            kids[int(p)].append(i)
+    return kids
+
+
+def _postorder(parent: np.ndarray, kids: List[List[int]]) -> List[int]:
+    root = int(np.nonzero(parent < 0)[0][0])
+    order, stack = [], [(root, 0)]
+    while stack:
+        v, k = stack.pop()
+        if k < len(kids[v]):
+            stack.append((v, k + 1))
+            stack.append((kids[v][k], 0))
+        else:
+            order.append(v)
+    return order
+
+
+def node_heights(ft: FlatTree) -> np.ndarray:
+    """Height of every node above the present (reference ``_node_heights``)."""
+    kids = _children(ft.parent)
+    h = np.zeros(ft.n_nodes, dtype=np.float64)
+    blen = np.nan_to_num(ft.blen, nan=0.0)
+    for v in _postorder(ft.parent, kids):
+        best = 0.0
+        for c in kids[v]:
+            best = max(best, h[c] + float(blen[c]))
+        h[v] = best
+    return h
+
+
+def _lengths_from_heights(parent: np.ndarray, h: np.ndarray) -> np.ndarray:
+    out = np.full(parent.shape[0], np.nan, dtype=np.float64)
+    nz = parent >= 0
+    out[nz] = np.maximum(h[parent[nz]] - h[nz], 0.0)   # _sync_lengths clamps at 0
+    return out
+
+
+def _leaf_sets(ft: FlatTree, kids: List[List[int]]) -> List[FrozenSet]:
+    sets: List[FrozenSet] = [frozenset()] * ft.n_nodes
+    for v in _postorder(ft.parent, kids):
+        if not kids[v]:
+            sets[v] = frozenset([ft.label[v]])
+        else:
+            s = frozenset()
+            for c in kids[v]:
+                s = s | sets[c]
+            sets[v] = s
+    return sets
+
+
+def signature(ft: FlatTree, heights: np.ndarray = None) -> FrozenSet:
+    """Topology + time signature (reference ``_gt_signature``)."""
+    kids = _children(ft.parent)
+    h = node_heights(ft) if heights is None else heights
+    ls = _leaf_sets(ft, kids)
+    return frozenset((ls[v], round(float(h[v]), 12)) for v in range(ft.n_nodes) if kids[v])
+
+
+def nni_neighbors(ft: FlatTree) -> List[Tuple[FlatTree, np.ndarray]]:
+    """Height-preserving single-NNI rearrangements (reference ``_gene_tree_nni_neighbors``)."""
+    kids = _children(ft.parent)
+    h = node_heights(ft)
+    out, seen = [], set()
+    for v in range(ft.n_nodes):
+        if len(kids[v]) < 2 or ft.parent[v] < 0:
+            continue
+        p = int(ft.parent[v])
+        sibs = [c for c in kids[p] if c != v]
+        if len(sibs) != 1:
+            continue
+        s = sibs[0]
+        if h[v] <= h[s]:
+            continue
+        for c in kids[v]:
+            parent = ft.parent.copy()
+            parent[s], parent[c] = v, p                    # s goes under v, c goes under p
+            cand = FlatTree(parent, _lengths_from_heights(parent, h), ft.label)
+            cand._tip_rows = ft._tip_rows   # an NNI re-hangs subtrees: leaves stay leaves, rows are unchanged
+            sig = signature(cand, h)
+            if sig in seen:
+                continue
+            seen.add(sig)
+            out.append((cand, h))
+    return out
+
+
+def candidate_set(ft: FlatTree, scales: Sequence[float] = HEIGHT_SCALE_GRID) -> List[FlatTree]:
+    """The re-proposal support of one locus: (tree + NNI neighbours) x height scales, de-duplicated
+    (reference ``_candidate_set``).  The identity -- ``ft`` at scale 1 -- is always present."""
+    h0 = node_heights(ft)
+    bases = [(FlatTree(ft.parent, _lengths_from_heights(ft.parent, h0), ft.label), h0)]
+    bases.extend(nni_neighbors(ft))
+    out, seen = [], set()
+    for k, (base, h) in enumerate(bases):
+        for s in scales:
+            hs = h * s if s != 1.0 else h
+            # the reference leaves the tree itself untouched at scale 1 (:1828-1832)
+            lengths = ft.blen if (k == 0 and s == 1.0) else _lengths_from_heights(base.parent, hs)
+            cand = FlatTree.__new__(FlatTree)
+            cand.parent, cand.blen, cand.label = base.parent, np.ascontiguousarray(lengths, dtype=np.float64), base.label
+            cand._n_children = base._n_children
+            cand._tip_rows = base._tip_rows if base._tip_rows is not None else ft._tip_rows
+            sig = signature(cand, hs)
+            if sig in seen:
+                continue
+            seen.add(sig)
+            out.append(cand)
+    return out
