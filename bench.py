@@ -574,6 +574,10 @@ def candidate_batch(P, ctx, calcs, trees, model, n_loci):
     wall = time.perf_counter() - t0
     st = dict(eng.last_stats)
     tm = ctx.last_timings()
+    ctx.set_profiling(True)
+    eng.score_candidate_sets(sets)
+    tm_prof = ctx.last_timings()
+    ctx.set_profiling(False)
     # the identity candidate of every locus must reproduce the committed tree's value
     ident_ok = all(any(v == eng._felsen[i] for v in vals) for (i, _), vals in zip(sets, res))
     return {
@@ -581,6 +585,7 @@ def candidate_batch(P, ctx, calcs, trees, model, n_loci):
         "candidate_trees": n_trees, "trees_per_locus": n_trees / n_loci,
         "seconds": wall, "trees_per_s": n_trees / wall, "updates_per_s": st["updates"] / wall,
         "c_abi_call_ms": tm["call_ms"], "host_compile_ms": tm["compile_ms"],
+        "kernel_span_ms": tm_prof["prune_ms"], "tiles": st["tiles"], "launches": st["launches"],
         "enumeration_seconds_python": t_enum,
         "identity_candidate_reproduces_committed_value": bool(ident_ok), "base_total": base,
     }
