@@ -560,14 +560,14 @@ def candidate_batch(P, ctx, calcs, trees, model, n_loci):
     """The coupled moves' inner double loop (reference src/_mcmc_seq.py:2028 x :1935-1957): for every locus
     the candidate set (tree + height-preserving NNI neighbours) x (0.25, 0.5, 1, 2, 4), every member scored
     by a full pruning -- here all loci x all candidates in ONE PNB_EVAL_NOSTORE call."""
-    from phynetpy_b200.candidates import candidate_set
+    from phynetpy_b200.candidates import candidate_arrays
     eng = P.SeqLikelihoodEngine(calcs[:n_loci], None, model, context=ctx)
     base = eng.log_likelihood(trees[:n_loci], None, 0.0)
     eng._commit_pending()
     t0 = time.perf_counter()
-    sets = [(i, candidate_set(trees[i])) for i in range(n_loci)]
+    sets = [(i, (trees[i],) + candidate_arrays(trees[i])) for i in range(n_loci)]
     t_enum = time.perf_counter() - t0
-    n_trees = sum(len(c) for _, c in sets)
+    n_trees = sum(c[1].shape[0] for _, c in sets)
     eng.score_candidate_sets(sets)                     # warm-up (templates, buffers)
     t0 = time.perf_counter()
     res = eng.score_candidate_sets(sets)

@@ -197,6 +197,8 @@ class SeqLikelihoodEngine:
         single ``PNB_EVAL_NOSTORE`` batch.  Returns one array of log-likelihoods per set."""
         self._commit_pending()
         ctx = self._context()
+        if sets and all(isinstance(t, tuple) and len(t) == 3 and isinstance(t[1], np.ndarray) for _, t in sets):
+            return self._score_candidate_arrays(sets, site_rate)
         idx: List[int] = []
         flats: List[FlatTree] = []
         for locus, trees in sets:
@@ -214,6 +216,36 @@ class SeqLikelihoodEngine:
         for _, trees in sets:
             res.append(out[k:k + len(trees)])
             k += len(trees)
+        return res
+
+    def _score_candidate_arrays(self, sets, site_rate: float) -> List[np.ndarray]:
+        """``sets = [(locus, (base_tree, parent[K, n], blen[K, n])), ...]`` as produced by
+        ``candidates.candidate_arrays``: packed with a handful of NumPy calls per locus instead of K tree
+        objects (the host side of a 20,000-tree batch is otherwise slower than the GPU)."""
+        ctx = self._context()
+        handles, parents, blens, tips, counts = [], [], [], [], []
+        for locus, (base, par, bl) in sets:
+            K, n = par.shape
+            calc = self._calcs[locus]
+            handles.append(np.full(K, calc._locus_handle().value, dtype=np.uint64))
+            parents.append(par.reshape(-1))
+            blens.append(bl.reshape(-1))
+            tips.append(np.tile(flatten(base).tip_rows(calc._row_of), K))   # leaves stay leaves under NNI
+            counts.append(np.full(K, n, dtype=np.int64))
+        sizes = np.concatenate(counts)
+        node_off = np.zeros(sizes.shape[0] + 1, dtype=np.int64)
+        np.cumsum(sizes, out=node_off[1:])
+        parent = np.ascontiguousarray(np.concatenate(parents), dtype=np.int32)
+        blen = np.ascontiguousarray(np.concatenate(blens), dtype=np.float64)
+        tip_row = np.ascontiguousarray(np.concatenate(tips), dtype=np.int32)
+        P_edge = _explicit_P_edges(self._model, blen, site_rate) if _device_kind(self._model) == "explicit" else None
+        out = ctx.eval(_model_handle(self._model, ctx), np.concatenate(handles), node_off, parent, blen, tip_row,
+                       site_rate, _lib.EVAL_NOSTORE | self._mode, P_edge)
+        self.last_stats = ctx.last_stats()
+        res, k = [], 0
+        for _, (_, par, _) in sets:
+            res.append(out[k:k + par.shape[0]])
+            k += par.shape[0]
         return res
 
     def score_candidates(self, locus: int, trees: Sequence[Any], *, site_rate: float = 1.0) -> np.ndarray:

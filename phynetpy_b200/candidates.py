@@ -121,6 +121,36 @@ def nni_neighbors(ft: FlatTree) -> List[Tuple[FlatTree, np.ndarray]]:
     return out
 
 
+def candidate_arrays(ft: FlatTree, scales: Sequence[float] = HEIGHT_SCALE_GRID) -> Tuple[np.ndarray, np.ndarray]:
+    """The candidate set as stacked arrays ``(parent[K, n], blen[K, n])`` -- the form
+    ``SeqLikelihoodEngine.score_candidate_sets`` packs without creating K tree objects.
+
+    Same members and order as :func:`candidate_set`.  De-duplication: bases are distinct by
+    signature (checked in :func:`nni_neighbors`); two scales of one base coincide only if their
+    rounded internal heights coincide, which is what is compared here (same leaf sets by construction).
+    """
+    h0 = node_heights(ft)
+    bases = [(ft, h0)] + nni_neighbors(ft)
+    base_sigs = set()
+    parents, lengths = [], []
+    internal = ft.n_children() > 0
+    for k, (base, h) in enumerate(bases):
+        bsig = signature(base, h)
+        if k > 0 and bsig in base_sigs:
+            continue
+        base_sigs.add(bsig)
+        seen_h = set()
+        for s in scales:
+            hs = h * s if s != 1.0 else h
+            key = tuple(np.round(hs[internal], 12).tolist())
+            if key in seen_h:
+                continue
+            seen_h.add(key)
+            parents.append(base.parent)
+            lengths.append(ft.blen if (k == 0 and s == 1.0) else _lengths_from_heights(base.parent, hs))
+    return np.ascontiguousarray(np.stack(parents), dtype=np.int32), np.ascontiguousarray(np.stack(lengths), dtype=np.float64)
+
+
 def candidate_set(ft: FlatTree, scales: Sequence[float] = HEIGHT_SCALE_GRID) -> List[FlatTree]:
     """The re-proposal support of one locus: (tree + NNI neighbours) x height scales, de-duplicated
     (reference ``_candidate_set``).  The identity -- ``ft`` at scale 1 -- is always present."""

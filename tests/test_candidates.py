@@ -3,7 +3,8 @@ the reference's ``_candidate_set``) and their scores in one device call (GPU, 1e
 import numpy as np
 import pytest
 
-from phynetpy_b200.candidates import HEIGHT_SCALE_GRID, candidate_set, nni_neighbors, node_heights, signature
+from phynetpy_b200.candidates import (HEIGHT_SCALE_GRID, candidate_arrays, candidate_set, nni_neighbors,
+                                      node_heights, signature)
 from phynetpy_b200.tree import FlatTree
 from conftest import load_golden
 
@@ -36,6 +37,11 @@ def test_candidate_set_equals_reference(case):
     for nb, hh in nni_neighbors(ft):
         assert np.array_equal(hh, h)
         np.testing.assert_allclose(node_heights(nb), h, rtol=0, atol=1e-15)
+    # the stacked-array form holds the same trees in the same order
+    par, bl = candidate_arrays(ft)
+    assert par.shape == (len(cands), ft.n_nodes)
+    for k, c in enumerate(cands):
+        assert np.array_equal(par[k], c.parent) and np.array_equal(bl[k], c.blen, equal_nan=True)
     # the scale grid is closed under reciprocals: scaling a candidate back reproduces its heights exactly
     assert all(1.0 / s in HEIGHT_SCALE_GRID for s in HEIGHT_SCALE_GRID)
 
@@ -58,3 +64,6 @@ def test_candidate_scores_match_reference(case):
     # all loci x all candidates in ONE call (here: the same locus three times)
     res = eng.score_candidate_sets([(0, cands), (0, cands[:3]), (0, cands)])
     assert np.array_equal(res[0], vals) and np.array_equal(res[2], vals) and np.array_equal(res[1], vals[:3])
+    par, bl = candidate_arrays(ft)
+    (vals2,) = eng.score_candidate_sets([(0, (ft, par, bl))])
+    assert np.array_equal(vals2, vals)
