@@ -568,7 +568,8 @@ def candidate_batch(P, ctx, calcs, trees, model, n_loci):
     sets = [(i, (trees[i],) + candidate_arrays(trees[i])) for i in range(n_loci)]
     t_enum = time.perf_counter() - t0
     n_trees = sum(c[1].shape[0] for _, c in sets)
-    eng.score_candidate_sets(sets)                     # warm-up (templates, buffers)
+    for _ in range(2):                                 # warm-up: templates, both pinned staging buffers
+        eng.score_candidate_sets(sets)
     t0 = time.perf_counter()
     res = eng.score_candidate_sets(sets)
     wall = time.perf_counter() - t0

@@ -350,6 +350,7 @@ pnb_prune_kernel_t(const __grid_constant__ PruneLaunch L, const __grid_constant_
     const int tid = threadIdx.x;
     const int tile = blockIdx.x + L.tile_base;
     const int job = L.tile_job[tile];
+    if (job < 0) return;  // tile of a job that needed no device work (served from the cache)
     const JobDesc& jd = L.jobs[job];
     const int n_ops = jd.n_ops;
     const int op_off = jd.op_off;

@@ -98,6 +98,8 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
     };
     const bool rescale_flag = (flags & PNB_EVAL_RESCALE) != 0;
     for (auto& S : ctx->scratch) { S.first_err_job = -1; S.tiles = 0; S.grow.clear(); }
+    auto& tile_first = ctx->tile_first;
+    tile_first.assign(M + 1, 0);
     parallel_for(M, 512, [&](int w, int64_t j0, int64_t j1) {
         CompileScratch& S = ctx->scratch[w];
         auto fail = [&](int64_t j, int code, const char* msg) {
@@ -123,7 +125,9 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
             } else if (rescale_flag && !loc->d_scale && loc->n_slots > 0) {
                 S.grow.push_back(j);  // NOSTORE reading committed partials in RESCALE mode needs the exponent array
             }
-            S.tiles += (loc->P + TILE_PATTERNS - 1) / TILE_PATTERNS;
+            const int64_t jt = (loc->P + TILE_PATTERNS - 1) / TILE_PATTERNS;
+            S.tiles += jt;
+            tile_first[j + 1] = jt;
         }
     });
     int64_t total_tiles = 0;
@@ -160,6 +164,7 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
             }
         }
     }
+    for (int64_t j = 0; j < M; ++j) tile_first[j + 1] += tile_first[j];  // prefix: job j owns tiles [tile_first[j], tile_first[j+1])
     const int64_t total_nodes = node_off[M] - node_off[0];
     PNB_REQUIRE(total_nodes < (int64_t(1) << 31) && total_tiles < (int64_t(1) << 31), PNB_ERR_UNSUPPORTED,
                 "pnb_eval: batch too large (%lld nodes, %lld tiles)", static_cast<long long>(total_nodes),
@@ -201,6 +206,69 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
     // its job descriptors, copy and launch it -- the GPU runs chunk c while the host compiles c+1.
     ctx->job_out.resize(M);
     JobOut* jout = ctx->job_out.data();
+    auto& job_of_batch = ctx->job_of_batch;
+    job_of_batch.assign(M, -1);
+    const char* desc_prog_base = nullptr;  // set once the launch mode is known (before any compile)
+    // descriptor + tile map of one job; runs in the compile worker right after the job's compilation.
+    // Jobs are numbered by their batch index and tiles by the prefix sum of pass 0, so nothing here
+    // depends on other jobs; a job that needs no device work leaves its tiles marked -1.
+    auto fill_desc = [&](CompileScratch::ChunkAcc& A, int64_t j, const JobOut& jo) {
+        pnb_locus* loc = loci[j];
+        A.n_dirty += jo.n_dirty;
+        pnb_locus::TreeCache* tc = nostore ? nullptr : (auto_commit ? &loc->committed : &loc->pending);
+        const int64_t t0 = tile_first[j], t1 = tile_first[j + 1];
+        if (loc->P == 0) {
+            h_out[j] = 0.0;  // np.dot over zero patterns
+            if (tc) { tc->logL = 0.0; tc->logL_valid = true; }
+            return;
+        }
+        if (jo.root_clean_cached && !out_dev) {
+            const double v = auto_commit ? jo.cached_logL : loc->committed.logL;
+            h_out[j] = v;
+            if (tc) { tc->logL = v; tc->logL_valid = true; }
+            A.n_cached++;
+            for (int64_t t = t0; t < t1; ++t) h_tile_job[t] = -1;
+            return;
+        }
+        const int64_t o = node_off[j] - node_off[0] - j;
+        JobDesc& jd = h_jobs[j];
+        jd.codes = loc->d_codes;
+        jd.partials = loc->d_partials;
+        jd.weights = loc->d_weights;
+        jd.slot_stride = loc->P_pad * 4;
+        jd.P = static_cast<int32_t>(loc->P);
+        jd.ld_codes = static_cast<int32_t>(loc->P_pad);
+        jd.op_off = static_cast<int32_t>(o);
+        jd.n_ops = jo.n_ops;
+        jd.n_tip_ops = jo.n_tip_ops;
+        jd.root_kind = jo.root_kind;
+        jd.root_src = jo.root_src;
+        jd.tile0 = static_cast<int32_t>(t0);
+        jd.n_tiles = static_cast<int32_t>(t1 - t0);
+        jd.out_index = static_cast<int32_t>(j);
+        jd.scale = loc->d_scale;
+        jd.pad0 = 0;
+        const pnb_locus::Template* Th = jo.tmpl_hit >= 0 ? &loc->tmpl[jo.tmpl_hit] : nullptr;
+        const bool resident = Th && Th->d_ops_valid && jo.n_ops > 0;
+        jd.ops = resident ? Th->d_ops : reinterpret_cast<const Op*>(desc_prog_base + off_ops) + o;
+        if (!resident && jo.n_ops > 0) {
+            if (A.prog_lo < 0 || o < A.prog_lo) A.prog_lo = o;
+            A.prog_hi = std::max(A.prog_hi, o + jo.n_ops);
+        }
+        if (jo.tmpl_new >= 0 && jo.n_ops > 0) A.save.push_back(j);
+        for (int64_t t = t0; t < t1; ++t) h_tile_job[t] = static_cast<int32_t>(j);
+        job_of_batch[j] = j;
+        A.n_jobs++;
+        A.n_ops_used += jo.n_ops;
+        if (jo.n_ops > 0) {
+            if (A.ops_lo < 0 || o < A.ops_lo) A.ops_lo = o;
+            A.ops_hi = std::max(A.ops_hi, o + jo.n_ops);
+        }
+        A.updates += static_cast<int64_t>(jo.n_dirty) * loc->P;
+        A.ops_cap = std::max(A.ops_cap, std::min(jo.n_ops, SEG_MAX_OPS));
+        A.rows_cap = std::max(A.rows_cap, jo.rows_cap);
+        A.stk_cap = std::max(A.stk_cap, jo.stk_need);
+    };
     auto compile_range = [&](CompileScratch& S, int64_t j0, int64_t j1) {
         for (int64_t j = j0; j < j1; ++j) {
             pnb_locus* loc = loci[j];
@@ -218,6 +286,7 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
                 locus_commit(loc);
             }
             jout[j] = jo;
+            if (jo.rc == PNB_OK) fill_desc(S.acc, j, jo);
         }
     };
     auto fail_rollback = [&]() {
@@ -252,6 +321,7 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
         if (!fused) (void)cudaGetLastError();
     }
     const char* prog_base = fused ? hs : ds;  // where non-resident op programs are read from
+    desc_prog_base = prog_base;
     bool stage_read_by_kernel = false;
     // Chunked batches upload (and run K-a for) chunk c+1 on the copy stream while the main stream prunes
     // chunk c.  The copy stream may only start once the previous evaluation's kernels, which read the
@@ -266,13 +336,11 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
     int64_t n_jobs = 0, n_tiles = 0, n_ops_used = 0, updates = 0, n_cached = 0, n_dirty_nodes = 0;
     int64_t h2d = 0, d2h = 0, launches = 0;
     double compile_ms = 0.0;
-    auto& job_of_batch = ctx->job_of_batch;
-    job_of_batch.assign(M, -1);
     bool memset_done = false;
     for (int64_t c = 0; c < n_chunks; ++c) {
         const int64_t j0 = M * c / n_chunks, j1 = M * (c + 1) / n_chunks;
         const auto t_comp0 = std::chrono::steady_clock::now();
-        for (auto& S : ctx->scratch) S.first_err_job = -1;
+        for (auto& S : ctx->scratch) { S.first_err_job = -1; S.acc.reset(); }
         if ((node_off[j1] - node_off[j0]) >= 4096 && n_workers > 1) {
             const int64_t grain = std::max<int64_t>(16, (j1 - j0) / (n_workers * 4));
             std::atomic<int64_t> next{j0};
@@ -297,73 +365,35 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
                 return code >= 100 ? PNB_ERR_STATE : code;
             }
         }
-        // job descriptors + tile map of this chunk (serial, cheap); numbering is global
-        const int64_t jobs_first = n_jobs, tiles_first = n_tiles;
+        // reduce the workers' descriptor-pass accumulators
+        const int64_t jobs_first = j0, tiles_first = tile_first[j0];
         int64_t ops_lo = -1, ops_hi = 0;    // range of P matrices / branch lengths used by this chunk
         int64_t prog_lo = -1, prog_hi = 0;  // range of op programs that travel with this chunk
         std::vector<int64_t>& save_list = ctx->save_list;
         save_list.clear();
         int ops_cap = 1, rows_cap = 1, stk_cap = 0;
-        for (int64_t j = j0; j < j1; ++j) {
-            pnb_locus* loc = loci[j];
-            const JobOut& jo = jout[j];
-            n_dirty_nodes += jo.n_dirty;
-            pnb_locus::TreeCache* tc = nostore ? nullptr : (auto_commit ? &loc->committed : &loc->pending);
-            if (loc->P == 0) {
-                h_out[j] = 0.0;  // np.dot over zero patterns
-                if (tc) { tc->logL = 0.0; tc->logL_valid = true; }
-                continue;
-            }
-            if (jo.root_clean_cached && !out_dev) {
-                const double v = auto_commit ? jo.cached_logL : loc->committed.logL;
-                h_out[j] = v;
-                if (tc) { tc->logL = v; tc->logL_valid = true; }
-                n_cached++;
-                continue;
-            }
-            const int64_t o = node_off[j] - node_off[0] - j;
-            JobDesc& jd = h_jobs[n_jobs];
-            jd.codes = loc->d_codes;
-            jd.partials = loc->d_partials;
-            jd.weights = loc->d_weights;
-            jd.slot_stride = loc->P_pad * 4;
-            jd.P = static_cast<int32_t>(loc->P);
-            jd.ld_codes = static_cast<int32_t>(loc->P_pad);
-            jd.op_off = static_cast<int32_t>(o);
-            jd.n_ops = jo.n_ops;
-            jd.n_tip_ops = jo.n_tip_ops;
-            jd.root_kind = jo.root_kind;
-            jd.root_src = jo.root_src;
-            jd.tile0 = static_cast<int32_t>(n_tiles);
-            jd.n_tiles = static_cast<int32_t>((loc->P + TILE_PATTERNS - 1) / TILE_PATTERNS);
-            jd.out_index = static_cast<int32_t>(j);
-            jd.scale = loc->d_scale;
-            jd.pad0 = 0;
-            const pnb_locus::Template* Th = jo.tmpl_hit >= 0 ? &loc->tmpl[jo.tmpl_hit] : nullptr;
-            const bool resident = Th && Th->d_ops_valid && jo.n_ops > 0;
-            jd.ops = resident ? Th->d_ops : reinterpret_cast<const Op*>(prog_base + off_ops) + o;
-            if (!resident && jo.n_ops > 0) {
-                if (prog_lo < 0) prog_lo = o;
-                prog_hi = std::max(prog_hi, o + jo.n_ops);
-            }
-            if (jo.tmpl_new >= 0 && jo.n_ops > 0) save_list.push_back(j);
-            for (int t = 0; t < jd.n_tiles; ++t) h_tile_job[n_tiles + t] = static_cast<int32_t>(n_jobs);
-            job_of_batch[j] = n_jobs;
-            n_tiles += jd.n_tiles;
-            n_ops_used += jo.n_ops;
-            if (jo.n_ops > 0) {
-                if (ops_lo < 0) ops_lo = o;
-                ops_hi = std::max(ops_hi, o + jo.n_ops);
-            }
-            updates += static_cast<int64_t>(jo.n_dirty) * loc->P;
-            ops_cap = std::max(ops_cap, std::min(jo.n_ops, SEG_MAX_OPS));
-            rows_cap = std::max(rows_cap, jo.rows_cap);
-            stk_cap = std::max(stk_cap, jo.stk_need);
-            n_jobs++;
+        int64_t chunk_jobs = 0;
+        for (auto& S : ctx->scratch) {
+            const auto& A = S.acc;
+            chunk_jobs += A.n_jobs;
+            n_ops_used += A.n_ops_used;
+            updates += A.updates;
+            n_cached += A.n_cached;
+            n_dirty_nodes += A.n_dirty;
+            if (A.ops_lo >= 0 && (ops_lo < 0 || A.ops_lo < ops_lo)) ops_lo = A.ops_lo;
+            ops_hi = std::max(ops_hi, A.ops_hi);
+            if (A.prog_lo >= 0 && (prog_lo < 0 || A.prog_lo < prog_lo)) prog_lo = A.prog_lo;
+            prog_hi = std::max(prog_hi, A.prog_hi);
+            ops_cap = std::max(ops_cap, A.ops_cap);
+            rows_cap = std::max(rows_cap, A.rows_cap);
+            stk_cap = std::max(stk_cap, A.stk_cap);
+            save_list.insert(save_list.end(), A.save.begin(), A.save.end());
         }
+        n_jobs += chunk_jobs;
+        n_tiles += tile_first[j1] - tile_first[j0];
         compile_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_comp0).count();
-        const int64_t cj = n_jobs - jobs_first, ct = n_tiles - tiles_first;
-        if (cj == 0) continue;
+        const int64_t cj = j1 - j0, ct = tile_first[j1] - tile_first[j0];  // descriptors / tiles of the chunk (with holes)
+        if (chunk_jobs == 0) continue;
         const size_t dyn_smem = static_cast<size_t>(ops_cap) * (sizeof(Op) + 128) +
                                 static_cast<size_t>(rows_cap) * TILE_PATTERNS +
                                 static_cast<size_t>(stk_cap) * TILE_PATTERNS * (rescale ? 36 : 32);

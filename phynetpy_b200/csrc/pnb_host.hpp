@@ -99,6 +99,14 @@ struct CompileScratch {
     std::vector<Key> key;
     std::vector<int32_t> op_child, kid_child;
     std::vector<Frame> frames;
+    // per-worker accumulators of one chunk's descriptor pass (reduced by the caller)
+    struct ChunkAcc {
+        int64_t n_jobs = 0, n_ops_used = 0, updates = 0, n_cached = 0, n_dirty = 0;
+        int64_t ops_lo = -1, ops_hi = 0, prog_lo = -1, prog_hi = 0;
+        int ops_cap = 1, rows_cap = 1, stk_cap = 0;
+        std::vector<int64_t> save;
+        void reset() { *this = ChunkAcc(); }
+    } acc;
     int64_t first_err_job = -1;
     int rc_alloc = 0;
     int64_t tiles = 0;            // pass-0 partial sums
@@ -223,6 +231,7 @@ struct pnb_ctx {
     std::vector<pnb::JobOut> job_out;
     std::vector<int64_t> job_of_batch;
     std::vector<int64_t> save_list;
+    std::vector<int64_t> tile_first;   // per job of the batch: its first tile (prefix sum, M + 1 entries)
 };
 
 struct pnb_locus {
