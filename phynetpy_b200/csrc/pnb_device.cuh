@@ -6,9 +6,9 @@
 //        (reference: SubstitutionModel.p_matrix  src/_seq_likelihood.py:231-244,
 //                    JC69.p_matrix               src/_seq_likelihood.py:259-268,
 //                    GTR.expt                    src/GTR.py:559-581)
-//   K-b/K-c pnb_prune_kernel  post-order partial updates + fused root/log/weight
-//        reduction; the same kernel runs a full evaluation (all internal nodes)
-//        and a dirty-path evaluation (only nodes whose subtree changed)
+//   K-b/K-c pnb_prune_kernel_t<FUSED, RESCALE>  post-order partial updates + fused
+//        root/log/weight reduction; the same kernel runs a full evaluation (all
+//        internal nodes) and a dirty-path evaluation (only nodes whose subtree changed)
 //        (reference: FelsensteinCalculator._postorder_partials :399-426 and
 //                    log_likelihood :391-397)
 #pragma once
@@ -38,13 +38,14 @@ enum : uint32_t { K_TIP = 0, K_MEM = 1, K_REG = 2, K_STK = 3 };
 // op flag bits
 constexpr uint32_t F_KIND_MASK = 0x3u;
 constexpr uint32_t F_FIRST = 0x4u;   // first child of its node: acc  = v
-constexpr uint32_t F_LAST  = 0x8u;   // last child of its node:  cur  = acc (node complete)
+constexpr uint32_t F_LAST  = 0x8u;   // last child of its node: `acc` is now the complete node partial
 constexpr uint32_t F_STORE = 0x10u;  // on F_LAST: write the node partial to HBM slot `dst`
 constexpr uint32_t F_PUSH  = 0x20u;  // on F_LAST: stash the node partial in smem stack[(flags>>8)&0xff]
 
 // One op = one (parent <- child) edge: v = P(edge) . L(child); acc (*)= v.
 // Op k of a job uses P matrix k of that job (one-to-one), so the program and
-// its P matrices are two contiguous arrays staged by two TMA bulk copies.
+// its P matrices are two contiguous arrays staged by two TMA bulk copies.  A K_REG op consumes the node
+// completed just before it and is always the FIRST op of its parent (the host compiler guarantees it).
 struct __align__(16) Op {
     uint32_t flags;
     int32_t src;   // TIP: row in the locus code matrix (-1: taxon absent -> all ones)
@@ -62,8 +63,8 @@ struct __align__(16) JobDesc {
     int32_t ld_codes;       // row stride of codes (= P_pad, multiple of TILE_PATTERNS)
     int32_t op_off;         // first op / P matrix of this job in the batch arrays
     int32_t n_ops;
-    int32_t n_tip_ops;      // TIP ops with src >= 0 (rows staged per chunk)
-    int32_t root_kind;      // K_REG: root partial is `cur` after the last op; K_MEM / K_TIP: root_src
+    int32_t n_tip_ops;      // TIP ops with src >= 0 (informational: the producer warp counts per segment)
+    int32_t root_kind;      // K_REG: root partial is `acc` after the last op; K_MEM / K_TIP: root_src
     int32_t root_src;
     int32_t tile0;          // first tile of this job
     int32_t n_tiles;
@@ -84,11 +85,11 @@ struct ModelParams {
 
 struct PruneLaunch {
     const JobDesc* jobs;
-    const int32_t* tile_job;   // tile -> job
+    const int32_t* tile_job;   // tile -> job (batch index), -1 for tiles of jobs served from the cache
     const double* Pm;          // batch P matrices [total_ops][16]
     const double* t;           // FUSED launches: effective branch length per op (P(t) is computed in-kernel)
     double* tile_sum;          // [n_tiles]
-    unsigned int* job_done;    // [n_jobs] arrival counters (self-resetting)
+    unsigned int* job_done;    // [batch jobs] arrival counters (self-resetting)
     double* out;               // per-job logL
     int32_t ops_cap;           // smem capacity in ops
     int32_t rows_cap;          // smem capacity in staged code rows
