@@ -64,7 +64,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -193,7 +193,7 @@ def oracle_time_loci(trees, alns, procs, reps=10):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="auto", choices=["auto"] + sorted(WORKLOADS))
@@ -273,7 +273,7 @@ def main():
 
     # every step scores the same topologies with NEW branch lengths (a height-rescaling proposal):
     # nothing of a previous step's result can be reused, and the host recompiles lengths each time
-    blens = [np.ascontiguousarray(blen * (1.0 + 0.002 * k)) for k in range(max(args.steps, 1))]
+    blens = [np.ascontiguousarray(blen * (1.0 + 0.002 * k)) for k in range(max(min(args.steps, 8), 1))]
     step_no = [0]
 
     def next_blen():
@@ -366,7 +366,7 @@ def main():
     # ---- cfg4: MCMC chain steps with dirty-path recompute (one locus per proposal) -------------
     chain = None
     if wl == "cfg4" and world == 1:
-        chain = chain_steps(P, ctx, calcs, trees, model, n_steps=max(200, 20 * args.steps))
+        chain = chain_steps(P, ctx, calcs, trees, model, n_steps=min(max(200, 20 * args.steps), 2000))
         chain["coupled_move_candidates"] = candidate_batch(P, ctx, calcs, trees, model, n_loci=min(200, len(calcs)))
 
     # ---- timed: end to end through the C ABI with host buffers ---------------------------
