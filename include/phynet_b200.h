@@ -174,6 +174,40 @@ PNB_API int pnb_eval(pnb_ctx *ctx, const pnb_model *m, int64_t M, pnb_locus *con
 PNB_API int pnb_commit(pnb_ctx *ctx, int64_t M, pnb_locus *const *loci);
 PNB_API int pnb_rollback(pnb_ctx *ctx, int64_t M, pnb_locus *const *loci);
 
+/* ---- K-m: timed MSNC density log P(g | Psi) ---------------------- */
+/* The other factor of the MCMC_SEQ likelihood, sum_i [log P(S_i|g_i) + log P(g_i|Psi)]
+ * (src/_mcmc_seq.py:745-761).  A species network handle replaces _NetworkIndex +
+ * build_network_msnc_index (src/_msnc_density.py:838-935, :392-417): nodes 0..n_nodes-1, edges
+ * parent -> child in the reference's E() order (the in-edge order of a reticulation decides which
+ * gamma goes with which parent, :311-322), edge_gamma NaN where the reference has None (filled in as
+ * there: both absent -> 0.5 / 0.5, one absent -> complement), node_height = height above the present
+ * (_node_height, src/GraphUtils.py:786-819), node_species[v] = species id (0..n_species-1) of leaf
+ * v, -1 for internal nodes.  A node with two parents is a reticulation.  Any context will do;
+ * on a host-only context the network is only compiled (pnb_msnc_net_info).                     */
+typedef struct pnb_msnc_net pnb_msnc_net;
+PNB_API int pnb_msnc_net_create(pnb_ctx *ctx, int32_t n_nodes, int32_t n_edges, const int32_t *edge_src,
+                                const int32_t *edge_dst, const double *edge_gamma,
+                                const double *node_height, const int32_t *node_species,
+                                int32_t n_species, pnb_msnc_net **out);
+PNB_API int pnb_msnc_net_destroy(pnb_msnc_net *net);
+/* info: [0] open-edge slots per frontier entry, [1] steps (= nodes), [2] reticulations, [3] species */
+PNB_API int pnb_msnc_net_info(const pnb_msnc_net *net, int32_t info[4]);
+/* Frontier entries a single gene tree may need before pnb_msnc_eval gives up with
+ * PNB_ERR_UNSUPPORTED (default 65536; the scratch is sized from the network and the batch, this is
+ * only the ceiling).                                                                          */
+PNB_API int pnb_msnc_net_set_max_frontier(pnb_msnc_net *net, int64_t entries);
+/* Batched msnc_log_density_prebuilt (src/_msnc_density.py:465-491) for n_trees gene trees against one
+ * network: the per-locus loop of _SeqLikelihoodEngine.log_likelihood (src/_mcmc_seq.py:750-760) and
+ * the per-candidate loop of the coupled moves (:1935-1957) in one call.  Trees are CSR-packed like
+ * pnb_eval's (tree_off, parent, blen; NaN length = None = 0); node_species[i] = species id of the
+ * species a LEAF's allele maps to (species_of, :262-266), -1 if unmapped; ignored for internal nodes.
+ * Coalescence times are node heights (max over children of child height + length).  Gene trees of
+ * up to 128 nodes.  logp_out[j] = log P(g_j | Psi), -inf when g_j does not embed (:488-490),
+ * 0 for an empty tree (:222-223).                                                             */
+PNB_API int pnb_msnc_eval(pnb_ctx *ctx, const pnb_msnc_net *net, int64_t n_trees, const int64_t *tree_off,
+                          const int32_t *parent, const double *blen, const int32_t *node_species,
+                          double theta, double *logp_out);
+
 /* ---- host-only planning (tests of the host runtime; no device involved) -- */
 /* A planning context owns no GPU: loci created on it hold no device memory and
  * pnb_eval on it fails.  pnb_plan runs exactly the host half of pnb_eval -- cache

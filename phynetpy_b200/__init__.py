@@ -12,6 +12,7 @@ from ._seq_likelihood import (
 )
 from ._seq_likelihood import GTR as SeqGTR  # `phynetpy_b200.GTR` is the public-model MODULE (as in the reference)
 from ._engine import SeqLikelihoodEngine
+from ._msnc_density import SpeciesNetwork, gene_tree_msnc_log_density, msnc_log_density_batch
 from .device import DeviceContext, default_context
 from .distributed import ShardPlan, balanced_ranges
 from .tree import FlatTree, GeneTree, flatten
@@ -21,5 +22,6 @@ __version__ = "0.1.0"
 __all__ = [
     "PhyNetB200Error", "DNA_STATES", "FelsensteinCalculator", "SeqGTR", "HKY85", "JC69", "SubstitutionModel",
     "tip_partials_for_char", "SeqLikelihoodEngine", "DeviceContext", "default_context", "ShardPlan",
-    "balanced_ranges", "FlatTree", "GeneTree", "flatten",
+    "balanced_ranges", "FlatTree", "GeneTree", "flatten", "SpeciesNetwork", "gene_tree_msnc_log_density",
+    "msnc_log_density_batch",
 ]

@@ -9,8 +9,10 @@ What changes is how the ``None`` entries of ``_felsen`` are filled: all dirty lo
 go to the GPU in ONE ``pnb_eval`` call, and inside each locus only the nodes whose
 subtree changed are recomputed (per-node partials stay resident in HBM).
 
-The MSNC coalescent density (the other factor, ``src/_msnc_density.py``) is a
-different algorithm and out of scope here; it plugs in as ``msnc_fn``.
+The MSNC coalescent density (the other factor, ``src/_msnc_density.py``) is filled
+the same way when a species network is passed: every locus whose ``_msnc`` entry is
+``None`` goes to kernel K-m in ONE ``pnb_msnc_eval`` call (``_msnc_density.py`` here).
+A host callable can still be plugged in as ``msnc_fn`` instead.
 
 Multi-GPU (one process per GPU): loci are sharded in contiguous ranges; every rank
 evaluates its shard into an M-long device vector (zeros elsewhere) and ONE NCCL
@@ -25,6 +27,7 @@ from typing import Any, Callable, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _lib
+from ._msnc_density import SpeciesNetwork, as_species_network, msnc_eval_packed, _check_theta
 from ._seq_likelihood import FelsensteinCalculator, _device_kind, _explicit_P_edges, _model_handle
 from .device import DeviceContext, default_context, pack_trees
 from .distributed import ShardPlan
@@ -67,6 +70,13 @@ class SeqLikelihoodEngine:
         self._full_next = False
         self._mode = _lib.EVAL_RESCALE if rescale else 0  # numerical mode (beyond the reference when set)
         self.last_stats: dict = {}
+        # MSNC side: the network view is rebuilt when a different network OBJECT arrives (the reference
+        # keys on identity too, src/_mcmc_seq.py:705-713); per-locus species ids are keyed by the label list
+        if branch_thetas and msnc_fn is None:
+            raise NotImplementedError("per-branch thetas are not implemented on the device MSNC path; pass msnc_fn")
+        self._net_obj: Any = None
+        self._net: Optional[SpeciesNetwork] = None
+        self._sp_ids: List[Optional[Tuple[Any, np.ndarray]]] = [None] * self.n_loci
 
     # -- reference seam (src/_mcmc_seq.py:696-703, :766-772) ------------------
     def invalidate_locus(self, i: int) -> None:
@@ -170,8 +180,13 @@ class SeqLikelihoodEngine:
             vec = self._shard.allreduce_sum(vec)
             self._felsen = [float(v) for v in vec]
         try:
-            if self._msnc_fn is None:
+            if self._msnc_fn is None and species_net is None:
                 total = sum(self._felsen)  # C loop, locus order
+            elif self._msnc_fn is None:
+                self._fill_msnc(gene_trees, species_net, theta)
+                total = 0.0
+                for f, m in zip(self._felsen, self._msnc):  # reference order, src/_mcmc_seq.py:745-761
+                    total += f + m
             else:
                 total = 0.0
                 for i in range(self.n_loci):  # reference loop, src/_mcmc_seq.py:745-761
@@ -187,6 +202,82 @@ class SeqLikelihoodEngine:
         if not math.isfinite(total):
             return float("-inf")
         return total
+
+    # -- MSNC density on the device ----------------------------------------------------------------
+    def _network(self, species_net: Any) -> SpeciesNetwork:
+        if species_net is not self._net_obj or self._net is None:
+            self._net = as_species_network(species_net)
+            self._net_obj = species_net
+            self._sp_ids = [None] * self.n_loci
+        return self._net
+
+    def _species_ids(self, i: int, ft: FlatTree, net: SpeciesNetwork) -> np.ndarray:
+        hit = self._sp_ids[i]
+        if hit is not None and hit[0] is ft.label:
+            return hit[1]
+        species_of = self._species_of
+        if species_of is None:   # one allele per species, named after it
+            species_of = {lab: lab for lab in ft.label if lab is not None}
+        ids = net.species_ids_of(ft, species_of)
+        self._sp_ids[i] = (ft.label, ids)
+        return ids
+
+    def _fill_msnc(self, gene_trees: Sequence[Any], species_net: Any, theta: float) -> None:
+        """Every ``None`` entry of ``_msnc`` in one ``pnb_msnc_eval`` (all ranks evaluate all loci: the
+        work is tiny next to the pruning and it saves a second collective)."""
+        need = [i for i in range(self.n_loci) if self._msnc[i] is None]
+        if not need:
+            return
+        theta = _check_theta(theta)
+        net = self._network(species_net)
+        flats = [flatten(gene_trees[i]) for i in need]
+        sizes = np.fromiter((t.n_nodes for t in flats), dtype=np.int64, count=len(flats))
+        off = np.zeros(len(flats) + 1, dtype=np.int64)
+        np.cumsum(sizes, out=off[1:])
+        parent = np.ascontiguousarray(np.concatenate([t.parent for t in flats]), dtype=np.int32)
+        blen = np.ascontiguousarray(np.concatenate([t.blen for t in flats]), dtype=np.float64)
+        ids = np.ascontiguousarray(np.concatenate([self._species_ids(i, t, net) for i, t in zip(need, flats)]), dtype=np.int32)
+        vals = msnc_eval_packed(net, off, parent, blen, ids, theta, self._context())
+        for i, v in zip(need, vals):
+            self._msnc[i] = float(v)
+
+    def msnc_candidate_sets(self, sets: Sequence[Tuple[int, Any]], species_net: Any, theta: float) -> List[np.ndarray]:
+        """log P(g | Psi) of the candidate trees of MANY loci in one device call -- the MSNC half of
+        ``_enumerate_scored_candidates`` (reference ``src/_mcmc_seq.py:1935-1957``).  ``sets`` as for
+        :meth:`score_candidate_sets`: ``[(locus, [tree, ...])]`` or ``[(locus, (base, parent[K, n], blen[K, n]))]``."""
+        theta = _check_theta(theta)
+        net = self._network(species_net)
+        parents, blens, idss, counts, per_set = [], [], [], [], []
+        for locus, trees in sets:
+            if isinstance(trees, tuple) and len(trees) == 3 and isinstance(trees[1], np.ndarray):
+                base, par, bl = trees
+                K, n = par.shape
+                parents.append(par.reshape(-1))
+                blens.append(bl.reshape(-1))
+                idss.append(np.tile(self._species_ids(locus, flatten(base), net), K))   # leaves stay leaves under NNI
+                counts.append(np.full(K, n, dtype=np.int64))
+                per_set.append(K)
+            else:
+                for t in trees:
+                    ft = flatten(t)
+                    parents.append(ft.parent)
+                    blens.append(ft.blen)
+                    idss.append(self._species_ids(locus, ft, net))
+                    counts.append(np.array([ft.n_nodes], dtype=np.int64))
+                per_set.append(len(trees))
+        if not counts:
+            return [np.zeros(0) for _ in sets]
+        sizes = np.concatenate(counts)
+        off = np.zeros(sizes.shape[0] + 1, dtype=np.int64)
+        np.cumsum(sizes, out=off[1:])
+        out = msnc_eval_packed(net, off, np.ascontiguousarray(np.concatenate(parents), dtype=np.int32),
+                               np.ascontiguousarray(np.concatenate(blens), dtype=np.float64),
+                               np.ascontiguousarray(np.concatenate(idss), dtype=np.int32), theta, self._context())
+        res, k = [], 0
+        for K in per_set:
+            res.append(out[k:k + K])
+            k += K
+        return res
 
     def score_candidate_sets(self, sets: Sequence[Tuple[int, Sequence[Any]]], *, site_rate: float = 1.0) -> List[np.ndarray]:
         """Candidate trees for MANY loci in ONE launch: ``sets = [(locus, [tree, ...]), ...]``.

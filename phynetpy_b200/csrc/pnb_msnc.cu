@@ -1,0 +1,334 @@
+// pnb_msnc.cu -- K-m: batched timed MSNC density log P(g_j | Psi) on the GPU.
+//
+// Replaces msnc_log_density_prebuilt (src/_msnc_density.py:465-491) called once per locus by
+// _SeqLikelihoodEngine.log_likelihood (src/_mcmc_seq.py:750-760) and once per candidate by the
+// coupled moves (src/_mcmc_seq.py:1935-1957).  The network is compiled once (pnb_msnc_net_create);
+// an evaluation prepares every gene tree on the host workers (heights, sorted coalescence events,
+// species lineage sets -- integer / comparison work, O(n log n) per tree), uploads one packed
+// buffer and runs ONE kernel, one thread per gene tree (pnb_msnc_core.hpp has the DP).
+#include "pnb_host.hpp"
+#include "pnb_msnc_core.hpp"
+
+#include <atomic>
+#include <functional>
+
+using namespace pnb;
+using namespace pnb::msnc;
+
+struct pnb_msnc_net {
+    pnb_ctx* ctx = nullptr;
+    NetProgram prog;
+    Step* d_steps = nullptr;
+    int32_t* d_down = nullptr;
+    int64_t max_frontier = 1 << 16;   // entries per job the scratch may be sized for
+};
+
+namespace {
+
+struct MsncLaunch {
+    const Step* steps;
+    const int32_t* down_slot;
+    int32_t n_steps, W, cap, n_species;
+    int64_t n_jobs;
+    const int64_t* ev_off;      // [n_jobs + 1] event offsets
+    const double* ev_t;
+    const uint32_t* ev_n;
+    const uint64_t* species_mask;   // [n_jobs][n_species][NW]
+    const int32_t* root_bit;        // [n_jobs]; -1 = empty gene tree
+    uint64_t* fr_mask;              // [n_jobs][(2 cap + 1) W NW]
+    double* fr_lp;                  // [n_jobs][2 cap]
+    double inv_theta, log_two_over_theta;
+    double* out;
+    int32_t* status;
+};
+
+template <int NW>
+__global__ void __launch_bounds__(128) pnb_msnc_kernel(MsncLaunch L) {
+    const int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (j >= L.n_jobs) return;
+    const int root_bit = L.root_bit[j];
+    if (root_bit < 0) {   // empty gene tree: density 1 (src/_msnc_density.py:222-223)
+        L.out[j] = 0.0;
+        L.status[j] = JOB_OK;
+        return;
+    }
+    const int64_t e0 = L.ev_off[j];
+    const size_t entry = static_cast<size_t>(L.W) * NW;
+    int status;
+    const double v = msnc_dp<NW>(L.steps, L.n_steps, L.down_slot, L.W, L.cap, L.ev_t + e0, L.ev_n + e0,
+                                 static_cast<int>(L.ev_off[j + 1] - e0),
+                                 L.species_mask + static_cast<size_t>(j) * L.n_species * NW, root_bit, L.inv_theta,
+                                 L.log_two_over_theta, L.fr_mask + static_cast<size_t>(j) * (2 * static_cast<size_t>(L.cap) + 1) * entry,
+                                 L.fr_lp + static_cast<size_t>(j) * 2 * L.cap, &status);
+    L.out[j] = v;
+    L.status[j] = status;
+}
+
+}  // namespace
+
+extern "C" int pnb_msnc_net_create(pnb_ctx* ctx, int32_t n_nodes, int32_t n_edges, const int32_t* edge_src,
+                                   const int32_t* edge_dst, const double* edge_gamma, const double* node_height,
+                                   const int32_t* node_species, int32_t n_species, pnb_msnc_net** out) {
+    PNB_REQUIRE(ctx && out, PNB_ERR_INVALID, "pnb_msnc_net_create: NULL handle");
+    PNB_REQUIRE(n_nodes > 0 && n_edges >= 0 && n_species >= 0, PNB_ERR_INVALID, "pnb_msnc_net_create: bad sizes");
+    PNB_REQUIRE(node_height && node_species && (n_edges == 0 || (edge_src && edge_dst && edge_gamma)), PNB_ERR_INVALID,
+                "pnb_msnc_net_create: NULL array");
+    pnb_msnc_net* net = new (std::nothrow) pnb_msnc_net();
+    PNB_REQUIRE(net, PNB_ERR_NOMEM, "pnb_msnc_net_create: out of host memory");
+    net->ctx = ctx;
+    const std::string err = compile_network(n_nodes, n_edges, edge_src, edge_dst, edge_gamma, node_height, node_species,
+                                            n_species, net->prog);
+    if (!err.empty()) {
+        delete net;
+        set_error("pnb_msnc_net_create: %s", err.c_str());
+        return PNB_ERR_INVALID;
+    }
+    if (ctx->device >= 0) {
+        if (cudaSetDevice(ctx->device) != cudaSuccess) {
+            delete net;
+            set_error("pnb_msnc_net_create: cudaSetDevice failed");
+            return PNB_ERR_CUDA;
+        }
+        void* p = nullptr;
+        const size_t sb = net->prog.steps.size() * sizeof(Step);
+        const size_t db = std::max<size_t>(net->prog.down_slot.size(), 1) * sizeof(int32_t);
+        int rc = ctx->arena.alloc(sb, &p);
+        if (rc) { delete net; return rc; }
+        net->d_steps = static_cast<Step*>(p);
+        rc = ctx->arena.alloc(db, &p);
+        if (rc) { ctx->arena.release(net->d_steps, sb); delete net; return rc; }
+        net->d_down = static_cast<int32_t*>(p);
+        cudaError_t ce = cudaMemcpyAsync(net->d_steps, net->prog.steps.data(), sb, cudaMemcpyHostToDevice, ctx->stream);
+        if (ce == cudaSuccess && !net->prog.down_slot.empty())
+            ce = cudaMemcpyAsync(net->d_down, net->prog.down_slot.data(), net->prog.down_slot.size() * sizeof(int32_t),
+                                 cudaMemcpyHostToDevice, ctx->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);   // the vectors are pageable
+        if (ce != cudaSuccess) {
+            ctx->arena.release(net->d_steps, sb);
+            ctx->arena.release(net->d_down, db);
+            delete net;
+            set_error("pnb_msnc_net_create: upload failed: %s", cudaGetErrorString(ce));
+            return PNB_ERR_CUDA;
+        }
+    }
+    *out = net;
+    return PNB_OK;
+}
+
+extern "C" int pnb_msnc_net_destroy(pnb_msnc_net* net) {
+    if (!net) return PNB_OK;
+    if (net->d_steps) {
+        cudaSetDevice(net->ctx->device);
+        cudaStreamSynchronize(net->ctx->stream);
+        net->ctx->arena.release(net->d_steps, net->prog.steps.size() * sizeof(Step));
+        net->ctx->arena.release(net->d_down, std::max<size_t>(net->prog.down_slot.size(), 1) * sizeof(int32_t));
+    }
+    delete net;
+    return PNB_OK;
+}
+
+extern "C" int pnb_msnc_net_info(const pnb_msnc_net* net, int32_t info[4]) {
+    PNB_REQUIRE(net && info, PNB_ERR_INVALID, "pnb_msnc_net_info: NULL argument");
+    info[0] = net->prog.W;
+    info[1] = static_cast<int32_t>(net->prog.steps.size());
+    info[2] = static_cast<int32_t>(net->prog.retic_step.size());
+    info[3] = net->prog.n_species;
+    return PNB_OK;
+}
+
+extern "C" int pnb_msnc_net_set_max_frontier(pnb_msnc_net* net, int64_t entries) {
+    PNB_REQUIRE(net && entries >= 1, PNB_ERR_INVALID, "pnb_msnc_net_set_max_frontier: bad argument");
+    net->max_frontier = entries;
+    return PNB_OK;
+}
+
+extern "C" int pnb_msnc_eval(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_trees, const int64_t* tree_off,
+                             const int32_t* parent, const double* blen, const int32_t* node_species, double theta,
+                             double* logp_out) {
+    PNB_REQUIRE(ctx && net, PNB_ERR_INVALID, "pnb_msnc_eval: NULL handle");
+    PNB_REQUIRE(ctx->device >= 0, PNB_ERR_STATE, "pnb_msnc_eval: host-only planning context has no device");
+    PNB_REQUIRE(net->ctx == ctx, PNB_ERR_INVALID, "pnb_msnc_eval: network belongs to another context");
+    PNB_REQUIRE(n_trees >= 0, PNB_ERR_INVALID, "pnb_msnc_eval: n_trees < 0");
+    PNB_REQUIRE(theta > 0.0 && std::isfinite(theta), PNB_ERR_INVALID, "pnb_msnc_eval: theta must be positive and finite");
+    if (n_trees == 0) return PNB_OK;
+    PNB_REQUIRE(tree_off && parent && blen && node_species && logp_out, PNB_ERR_INVALID, "pnb_msnc_eval: NULL array");
+    PNB_CUDA_TRY(cudaSetDevice(ctx->device));
+    const NetProgram& prog = net->prog;
+    const int n_species = std::max(prog.n_species, 1);
+
+    // ---- sizes ---------------------------------------------------------------------------
+    int max_n = 0;
+    for (int64_t j = 0; j < n_trees; ++j) {
+        const int64_t n = tree_off[j + 1] - tree_off[j];
+        PNB_REQUIRE(n >= 0, PNB_ERR_INVALID, "pnb_msnc_eval: tree_off is not non-decreasing at tree %lld", static_cast<long long>(j));
+        PNB_REQUIRE(n <= 64 * MAX_NW, PNB_ERR_UNSUPPORTED, "pnb_msnc_eval: gene tree %lld has %lld nodes; this build handles %d",
+                    static_cast<long long>(j), static_cast<long long>(n), 64 * MAX_NW);
+        max_n = std::max(max_n, static_cast<int>(n));
+    }
+    const int NW = max_n <= 64 ? 1 : 2;
+    const int64_t total_nodes = tree_off[n_trees] - tree_off[0];
+    // events: a tree of n nodes has at most (n - 1) / 2 binary nodes; job j's events start at
+    // (tree_off[j] - tree_off[0]) / 2 rounded down -- a bound, offsets are exact per job below
+    const size_t ev_cap = static_cast<size_t>(total_nodes / 2 + n_trees);
+
+    const size_t off_evoff = 0;
+    const size_t off_root = align_up(off_evoff + static_cast<size_t>(n_trees + 1) * sizeof(int64_t), 256);
+    const size_t off_evt = align_up(off_root + static_cast<size_t>(n_trees) * sizeof(int32_t), 256);
+    const size_t off_evn = align_up(off_evt + ev_cap * sizeof(double), 256);
+    const size_t off_sp = align_up(off_evn + ev_cap * sizeof(uint32_t), 256);
+    const size_t stage_bytes = off_sp + static_cast<size_t>(n_trees) * n_species * NW * sizeof(uint64_t);
+
+    // the felsenstein path's staging buffers are reused: wait for whatever still reads them
+    PNB_CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
+    PNB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    int rc;
+    if ((rc = ensure_pinned(ctx->h_stage2[0], stage_bytes))) return rc;
+    if ((rc = ensure_device(ctx->d_stage, stage_bytes))) return rc;
+    char* hs = static_cast<char*>(ctx->h_stage2[0].p);
+    int64_t* ev_off = reinterpret_cast<int64_t*>(hs + off_evoff);
+    int32_t* root_bit = reinterpret_cast<int32_t*>(hs + off_root);
+    double* ev_t = reinterpret_cast<double*>(hs + off_evt);
+    uint32_t* ev_n = reinterpret_cast<uint32_t*>(hs + off_evn);
+    uint64_t* sp_mask = reinterpret_cast<uint64_t*>(hs + off_sp);
+
+    // ---- host preparation, parallel over trees ---------------------------------------------
+    // job j writes its events at slot base (tree_off[j] - tree_off[0]) / 2 + j (disjoint, an upper
+    // bound on everything before it); ev_off records [begin, end) so no compaction pass is needed.
+    const int n_workers = ctx->pool ? ctx->pool->size() : 1;
+    std::vector<TreeScratch> scratch(n_workers);
+    std::vector<std::string> errs(n_workers);
+    std::vector<int64_t> err_job(n_workers, -1);
+    std::vector<int32_t> alleles_max(static_cast<size_t>(n_workers) * n_species, 0);
+    std::vector<int64_t> ev_end(n_trees);
+    auto body = [&](int w, int64_t a, int64_t b) {
+        TreeScratch& sc = scratch[w];
+        for (int64_t j = a; j < b; ++j) {
+            const int64_t o = tree_off[j];
+            const int n = static_cast<int>(tree_off[j + 1] - o);
+            const int64_t base = (o - tree_off[0]) / 2 + j;
+            ev_off[j] = base;
+            uint64_t* mj = sp_mask + static_cast<size_t>(j) * n_species * NW;
+            if (n == 0) {
+                root_bit[j] = -1;
+                ev_end[j] = base;
+                for (size_t i = 0; i < static_cast<size_t>(n_species) * NW; ++i) mj[i] = 0;
+                continue;
+            }
+            int n_ev = 0, rb = 0;
+            const std::string e = prepare_tree(n, parent + o, blen + o, node_species + o, prog.n_species, NW, sc, ev_t + base,
+                                               ev_n + base, &n_ev, mj, &rb);
+            if (!e.empty()) {
+                if (err_job[w] < 0) { err_job[w] = j; errs[w] = e; }
+                root_bit[j] = -1;
+                ev_end[j] = base;
+                continue;
+            }
+            root_bit[j] = rb;
+            ev_end[j] = base + n_ev;
+            int32_t* am = alleles_max.data() + static_cast<size_t>(w) * n_species;
+            for (int s = 0; s < prog.n_species; ++s) {
+                int c = 0;
+                for (int i = 0; i < NW; ++i) c += __builtin_popcountll(mj[static_cast<size_t>(s) * NW + i]);
+                if (c > am[s]) am[s] = c;
+            }
+        }
+    };
+    if (n_trees >= 256 && n_workers > 1) {
+        const int64_t grain = std::max<int64_t>(64, n_trees / (n_workers * 4));
+        std::atomic<int64_t> next{0};
+        ctx->pool->run([&](int w) {
+            for (;;) {
+                const int64_t a0 = next.fetch_add(grain);
+                if (a0 >= n_trees) break;
+                body(w, a0, std::min(n_trees, a0 + grain));
+            }
+        });
+    } else {
+        body(0, 0, n_trees);
+    }
+    for (int w = 0; w < n_workers; ++w)
+        PNB_REQUIRE(err_job[w] < 0, PNB_ERR_INVALID, "pnb_msnc_eval: gene tree %lld: %s", static_cast<long long>(err_job[w]),
+                    errs[w].c_str());
+    // The kernel reads job j's events in [ev_off[j], ev_off[j+1]); with the gaps above that range would
+    // include the unused tail of job j's slot range, so events are compacted here (a single memmove pass).
+    {
+        int64_t w_pos = 0;
+        for (int64_t j = 0; j < n_trees; ++j) {
+            const int64_t b = ev_off[j], n_ev = ev_end[j] - b;
+            if (b != w_pos && n_ev > 0) {
+                memmove(ev_t + w_pos, ev_t + b, static_cast<size_t>(n_ev) * sizeof(double));
+                memmove(ev_n + w_pos, ev_n + b, static_cast<size_t>(n_ev) * sizeof(uint32_t));
+            }
+            ev_off[j] = w_pos;
+            w_pos += n_ev;
+        }
+        ev_off[n_trees] = w_pos;
+    }
+    for (int w = 1; w < n_workers; ++w)
+        for (int s = 0; s < n_species; ++s)
+            alleles_max[s] = std::max(alleles_max[s], alleles_max[static_cast<size_t>(w) * n_species + s]);
+
+    // ---- frontier capacity and scratch ---------------------------------------------------------
+    const double bound = frontier_bound(prog, alleles_max.data());
+    const int cap = static_cast<int>(std::min<double>(bound, static_cast<double>(net->max_frontier))) + 1;
+    const size_t entry = static_cast<size_t>(prog.W) * NW;
+    const size_t job_mask_words = (2 * static_cast<size_t>(cap) + 1) * entry;
+    const size_t per_job = job_mask_words * sizeof(uint64_t) + 2 * static_cast<size_t>(cap) * sizeof(double);
+    // jobs per launch: bounded scratch (the frontiers of a batch may not fit at once)
+    const size_t scratch_budget = size_t{2} << 30;
+    const int64_t jobs_per_launch = std::max<int64_t>(1, std::min<int64_t>(n_trees, static_cast<int64_t>(scratch_budget / per_job)));
+    const size_t off_lp = align_up(static_cast<size_t>(jobs_per_launch) * job_mask_words * sizeof(uint64_t), 256);
+    if ((rc = ensure_device(ctx->d_P, off_lp + static_cast<size_t>(jobs_per_launch) * 2 * cap * sizeof(double)))) return rc;
+    const size_t off_status = align_up(static_cast<size_t>(n_trees) * sizeof(double), 256);
+    if ((rc = ensure_device(ctx->d_out, off_status + static_cast<size_t>(n_trees) * sizeof(int32_t)))) return rc;
+    if ((rc = ensure_pinned(ctx->h_out, off_status + static_cast<size_t>(n_trees) * sizeof(int32_t)))) return rc;
+
+    cudaStream_t st = ctx->stream;
+    PNB_CUDA_TRY(cudaMemcpyAsync(ctx->d_stage.p, hs, stage_bytes, cudaMemcpyHostToDevice, st));
+    char* ds = static_cast<char*>(ctx->d_stage.p);
+    MsncLaunch L;
+    L.steps = net->d_steps;
+    L.down_slot = net->d_down;
+    L.n_steps = static_cast<int32_t>(prog.steps.size());
+    L.W = prog.W;
+    L.cap = cap;
+    L.n_species = n_species;
+    L.inv_theta = 1.0 / theta;
+    L.log_two_over_theta = log(2.0 * L.inv_theta);
+    L.fr_mask = static_cast<uint64_t*>(ctx->d_P.p);
+    L.fr_lp = reinterpret_cast<double*>(static_cast<char*>(ctx->d_P.p) + off_lp);
+    int64_t launches = 0;
+    for (int64_t j0 = 0; j0 < n_trees; j0 += jobs_per_launch) {
+        const int64_t nj = std::min(jobs_per_launch, n_trees - j0);
+        L.n_jobs = nj;
+        L.ev_off = reinterpret_cast<const int64_t*>(ds + off_evoff) + j0;
+        L.ev_t = reinterpret_cast<const double*>(ds + off_evt);
+        L.ev_n = reinterpret_cast<const uint32_t*>(ds + off_evn);
+        L.species_mask = reinterpret_cast<const uint64_t*>(ds + off_sp) + static_cast<size_t>(j0) * n_species * NW;
+        L.root_bit = reinterpret_cast<const int32_t*>(ds + off_root) + j0;
+        L.out = static_cast<double*>(ctx->d_out.p) + j0;
+        L.status = reinterpret_cast<int32_t*>(static_cast<char*>(ctx->d_out.p) + off_status) + j0;
+        const unsigned blocks = static_cast<unsigned>((nj + 127) / 128);
+        if (NW == 1) pnb_msnc_kernel<1><<<blocks, 128, 0, st>>>(L);
+        else pnb_msnc_kernel<2><<<blocks, 128, 0, st>>>(L);
+        PNB_CUDA_TRY(cudaGetLastError());
+        ++launches;
+    }
+    PNB_CUDA_TRY(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, off_status + static_cast<size_t>(n_trees) * sizeof(int32_t),
+                                 cudaMemcpyDeviceToHost, st));
+    PNB_CUDA_TRY(cudaStreamSynchronize(st));
+    const double* ho = static_cast<const double*>(ctx->h_out.p);
+    const int32_t* hstat = reinterpret_cast<const int32_t*>(static_cast<const char*>(ctx->h_out.p) + off_status);
+    for (int64_t j = 0; j < n_trees; ++j) {
+        PNB_REQUIRE(hstat[j] == JOB_OK, PNB_ERR_UNSUPPORTED,
+                    "pnb_msnc_eval: gene tree %lld needs more than %d frontier entries (raise pnb_msnc_net_set_max_frontier)",
+                    static_cast<long long>(j), cap - 1);
+        logp_out[j] = ho[j];
+    }
+    memset(ctx->stats, 0, sizeof(ctx->stats));
+    ctx->stats[3] = launches;
+    ctx->stats[4] = static_cast<int64_t>(stage_bytes);
+    ctx->stats[5] = static_cast<int64_t>(off_status + static_cast<size_t>(n_trees) * sizeof(int32_t));
+    ctx->stats[1] = ev_off[n_trees];
+    return PNB_OK;
+}
