@@ -368,6 +368,7 @@ def main():
     if wl == "cfg4" and world == 1:
         chain = chain_steps(P, ctx, calcs, trees, model, n_steps=min(max(200, 20 * args.steps), 2000))
         chain["coupled_move_candidates"] = candidate_batch(P, ctx, calcs, trees, model, n_loci=min(200, len(calcs)))
+        chain["msnc_density"] = msnc_leg(P, ctx, n_loci=len(calcs), n_species=spec["n"], cpu=not args.no_cpu_baseline)
 
     # ---- timed: end to end through the C ABI with host buffers ---------------------------
     for _ in range(2):
@@ -590,6 +591,73 @@ def candidate_batch(P, ctx, calcs, trees, model, n_loci):
         "enumeration_seconds_python": t_enum,
         "identity_candidate_reproduces_committed_value": bool(ident_ok), "base_total": base,
     }
+
+
+def msnc_leg(P, ctx, n_loci, n_species, cpu=True, seed=44):
+    """The other factor of the MCMC_SEQ likelihood, log P(g_i | Psi) (kernel K-m):
+    all loci of a full evaluation in one pnb_msnc_eval call, and the candidate sets of the coupled moves in
+    one call, on a species tree and on a network with two reticulations.  Host arrays in, host values out."""
+    from phynetpy_b200 import simulate as S
+    from phynetpy_b200._msnc_density import msnc_eval_packed
+    from phynetpy_b200.candidates import candidate_arrays
+    from oracle import msnc_oracle as MO   # checker and CPU baseline only
+    rng = np.random.default_rng(seed)
+    theta = 0.02
+    out = {}
+    for name, n_retic in (("species_tree", 0), ("network_2_reticulations", 2)):
+        net = S.random_species_network(n_species, n_retic, rng, height=0.005 * (n_species - 1))
+        trees, species_of = S.simulate_gene_trees_msnc(net, 1, theta, rng, n_loci)
+
+        def pack(sets):
+            par = np.ascontiguousarray(np.concatenate([p.reshape(-1) for p, _, _ in sets]), dtype=np.int32)
+            bl = np.ascontiguousarray(np.concatenate([b.reshape(-1) for _, b, _ in sets]), dtype=np.float64)
+            ids = np.ascontiguousarray(np.concatenate([np.tile(i, p.shape[0]) for p, _, i in sets]), dtype=np.int32)
+            sizes = np.concatenate([np.full(p.shape[0], p.shape[1], dtype=np.int64) for p, _, _ in sets])
+            off = np.zeros(sizes.shape[0] + 1, dtype=np.int64)
+            np.cumsum(sizes, out=off[1:])
+            return off, par, bl, ids
+
+        ids_of = [net.species_ids_of(t, species_of) for t in trees]
+        full = pack([(t.parent[None, :], t.blen[None, :], i) for t, i in zip(trees, ids_of)])
+        n_cand_loci = min(200, n_loci)
+        cand = pack([candidate_arrays(trees[k]) + (ids_of[k],) for k in range(n_cand_loci)])
+        res = {"reticulations": n_retic, "program": net.info(ctx)}
+        for tag, arrs in (("all_loci", full), ("candidate_sets", cand)):
+            n_trees = arrs[0].shape[0] - 1
+            for _ in range(3):
+                vals = msnc_eval_packed(net, *arrs, theta, ctx)
+            reps = 20
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                vals = msnc_eval_packed(net, *arrs, theta, ctx)
+            wall = (time.perf_counter() - t0) / reps
+            ctx.set_profiling(True)
+            msnc_eval_packed(net, *arrs, theta, ctx)
+            tm = ctx.last_timings()
+            ctx.set_profiling(False)
+            res[tag] = {"gene_trees": int(n_trees), "ms_per_call": wall * 1e3, "trees_per_s": n_trees / wall,
+                        "kernel_ms": tm["prune_ms"], "host_prepare_ms": tm["compile_ms"],
+                        "finite": int(np.isfinite(vals).sum())}
+            if tag == "all_loci":
+                netd = {"n_nodes": net.n_nodes, "edge_src": net.edge_src.tolist(), "edge_dst": net.edge_dst.tolist(),
+                        "edge_gamma": [None if g != g else g for g in net.edge_gamma.tolist()],
+                        "height": net.height.tolist(), "leaf_label": net.leaf_label,
+                        "is_retic": (np.bincount(net.edge_dst, minlength=net.n_nodes) >= 2).tolist()}
+                k = min(100, n_loci)
+                t0 = time.perf_counter()
+                want = [MO.msnc_log_density(netd, t.parent.tolist(), t.blen.tolist(), t.label, species_of, theta)
+                        for t in trees[:k]] if cpu else []
+                dt = time.perf_counter() - t0
+                if cpu:
+                    err = max(abs(g - w) / max(1.0, abs(w)) for g, w in zip(vals[:k], want))
+                    res["parity_max_rel_err_vs_oracle"] = err
+                    res["cpu_baseline"] = {"value": k / dt, "unit": "gene trees/s", "cores": 1, "kind": "port",
+                                           "sample": "oracle/msnc_oracle.py (Python restatement of the reference DP) on %d of the "
+                                                     "gene trees" % k}
+        out[name] = res
+    out["what"] = ("pnb_msnc_eval through the C ABI: packed host tree arrays in -> host preparation (heights, sorted "
+                   "coalescence events, lineage sets) -> one kernel, one thread per gene tree -> values out")
+    return out
 
 
 def cpu_baseline(wl, spec, sample):

@@ -10,6 +10,7 @@
 #include "pnb_msnc_core.hpp"
 
 #include <atomic>
+#include <chrono>
 #include <functional>
 
 using namespace pnb;
@@ -153,6 +154,8 @@ extern "C" int pnb_msnc_eval(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_tr
     if (n_trees == 0) return PNB_OK;
     PNB_REQUIRE(tree_off && parent && blen && node_species && logp_out, PNB_ERR_INVALID, "pnb_msnc_eval: NULL array");
     PNB_CUDA_TRY(cudaSetDevice(ctx->device));
+    const auto t_call0 = std::chrono::steady_clock::now();
+    ctx->ev_ka = ctx->ev_prune = false;
     const NetProgram& prog = net->prog;
     const int n_species = std::max(prog.n_species, 1);
 
@@ -283,8 +286,10 @@ extern "C" int pnb_msnc_eval(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_tr
     if ((rc = ensure_device(ctx->d_out, off_status + static_cast<size_t>(n_trees) * sizeof(int32_t)))) return rc;
     if ((rc = ensure_pinned(ctx->h_out, off_status + static_cast<size_t>(n_trees) * sizeof(int32_t)))) return rc;
 
+    ctx->t_compile_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call0).count();
     cudaStream_t st = ctx->stream;
     PNB_CUDA_TRY(cudaMemcpyAsync(ctx->d_stage.p, hs, stage_bytes, cudaMemcpyHostToDevice, st));
+    if (ctx->profiling) PNB_CUDA_TRY(cudaEventRecord(ctx->ev[2], st));   // reported as the "prune" slot of last_timings
     char* ds = static_cast<char*>(ctx->d_stage.p);
     MsncLaunch L;
     L.steps = net->d_steps;
@@ -314,6 +319,7 @@ extern "C" int pnb_msnc_eval(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_tr
         PNB_CUDA_TRY(cudaGetLastError());
         ++launches;
     }
+    if (ctx->profiling) { PNB_CUDA_TRY(cudaEventRecord(ctx->ev[3], st)); ctx->ev_prune = true; }
     PNB_CUDA_TRY(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, off_status + static_cast<size_t>(n_trees) * sizeof(int32_t),
                                  cudaMemcpyDeviceToHost, st));
     PNB_CUDA_TRY(cudaStreamSynchronize(st));
@@ -330,5 +336,8 @@ extern "C" int pnb_msnc_eval(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_tr
     ctx->stats[4] = static_cast<int64_t>(stage_bytes);
     ctx->stats[5] = static_cast<int64_t>(off_status + static_cast<size_t>(n_trees) * sizeof(int32_t));
     ctx->stats[1] = ev_off[n_trees];
+    ctx->stats[0] = n_trees;
+    ctx->stats[2] = cap - 1;
+    ctx->t_call_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call0).count();
     return PNB_OK;
 }

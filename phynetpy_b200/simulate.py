@@ -109,3 +109,129 @@ def to_alignment_dict(mat: np.ndarray) -> dict:
 
 DEFAULT_PI = (0.1, 0.2, 0.3, 0.4)
 DEFAULT_RATES = (1.0, 2.5, 0.7, 1.3, 3.1, 0.9)
+
+
+# ---------------------------------------------------------------------------------------------
+# Species networks and gene trees under the multispecies network coalescent (inputs of K-m)
+# ---------------------------------------------------------------------------------------------
+def random_species_network(n_species: int, n_retic: int, rng: np.random.Generator, height: float = 0.05):
+    """A random ultrametric species network: a coalescent-shaped tree over ``s0..s{n-1}`` plus
+    ``n_retic`` reticulations, each a hybrid node placed on a recipient edge with a second parent edge
+    coming from a node placed on a donor edge at or above the same height.  Returns a
+    :class:`~phynetpy_b200._msnc_density.SpeciesNetwork`."""
+    from ._msnc_density import SpeciesNetwork
+    label: List[Optional[str]] = ["s%d" % i for i in range(n_species)]
+    h: List[float] = [0.0] * n_species
+    edges: List[List] = []     # [src, dst, gamma | None]
+    live = list(range(n_species))
+    t = 0.0
+    while len(live) > 1:
+        t += float(rng.exponential(height / n_species))
+        i, j = sorted(rng.choice(len(live), size=2, replace=False).tolist(), reverse=True)
+        a, b = live.pop(i), live.pop(j)
+        label.append(None)
+        h.append(t)
+        v = len(h) - 1
+        edges += [[v, a, None], [v, b, None]]
+        live.append(v)
+
+    def split(e: int, m: int, gamma_into_m):
+        p, c, g = edges[e]
+        edges[e] = [p, m, gamma_into_m]
+        edges.append([m, c, g])   # a gamma on p -> c stays on the half that still points into c
+
+    for _ in range(n_retic):
+        for _try in range(1000):
+            r, d = int(rng.integers(len(edges))), int(rng.integers(len(edges)))
+            if r == d:
+                continue
+            (pr, cr, _g), (pd, cd, _g2) = edges[r], edges[d]
+            lo_r, hi_r = h[cr], h[pr]
+            if hi_r - lo_r < 1e-9:
+                continue
+            th = float(rng.uniform(lo_r + 0.1 * (hi_r - lo_r), hi_r - 0.1 * (hi_r - lo_r)))
+            lo_d, hi_d = max(h[cd], th), h[pd]
+            if hi_d - lo_d < 1e-9:
+                continue
+            tx = float(rng.uniform(lo_d + 0.05 * (hi_d - lo_d), hi_d - 0.05 * (hi_d - lo_d)))
+            g = float(rng.uniform(0.1, 0.9))
+            label.extend([None, None])
+            h.extend([th, tx])
+            hyb, don = len(h) - 2, len(h) - 1
+            split(r, hyb, 1.0 - g)
+            split(d, don, None)
+            edges.append([don, hyb, g])
+            break
+        else:
+            raise RuntimeError("could not place a reticulation")
+    return SpeciesNetwork([e[0] for e in edges], [e[1] for e in edges], [e[2] for e in edges], h, label)
+
+
+def simulate_gene_trees_msnc(net, alleles_per_species: int, theta: float, rng: np.random.Generator, M: int):
+    """M gene trees drawn from the multispecies network coalescent on ``net`` (the process the timed
+    MSNC density scores): lineages enter at the leaves, coalesce pairwise at rate u(u-1)/theta inside a
+    branch, choose a parent edge with probability gamma at a reticulation, and finish above the root.
+
+    Returns ``(trees, species_of)``: :class:`FlatTree` objects with leaves first and the root last
+    (``parent[i] > i``, so :func:`simulate_alignments` accepts their stacked arrays) and the
+    allele -> species map.  Allele labels are ``t0, t1, ...`` in species order."""
+    n_nodes = net.n_nodes
+    down = [[] for _ in range(n_nodes)]
+    up = [[] for _ in range(n_nodes)]
+    for e, (s, d) in enumerate(zip(net.edge_src.tolist(), net.edge_dst.tolist())):
+        down[s].append(e)
+        up[d].append(e)
+    gam = net.edge_gamma.tolist()
+    order = sorted(range(n_nodes), key=lambda v: (net.height[v], len(down[v]) > 0))
+    n_leaves = len(net.species) * alleles_per_species
+    labels = ["t%d" % i for i in range(n_leaves)] + [None] * (n_leaves - 1)
+    species_of = {"t%d" % (s * alleles_per_species + k): net.species[s]
+                  for s in range(len(net.species)) for k in range(alleles_per_species)}
+    trees = []
+    for _ in range(M):
+        parent = [-1] * (2 * n_leaves - 1)
+        node_h = [0.0] * (2 * n_leaves - 1)
+        nxt = n_leaves
+        at_edge = {}     # edge -> lineages (gene-tree node ids) waiting at its bottom
+
+        def coalesce(lin, lo, hi):
+            nonlocal nxt
+            t = lo
+            lin = list(lin)
+            while len(lin) > 1:
+                u = len(lin)
+                t += float(rng.exponential(theta / (u * (u - 1))))
+                if hi is not None and t >= hi:
+                    break
+                i, j = sorted(rng.choice(u, size=2, replace=False).tolist(), reverse=True)
+                a, b = lin.pop(i), lin.pop(j)
+                parent[a] = parent[b] = nxt
+                node_h[nxt] = t
+                lin.append(nxt)
+                nxt += 1
+            return lin
+
+        for v in order:
+            if not down[v]:
+                s = int(net.node_species[v])
+                arriving = list(range(s * alleles_per_species, (s + 1) * alleles_per_species))
+            else:
+                arriving = []
+                for e in down[v]:
+                    arriving += coalesce(at_edge.pop(e, []), float(net.height[net.edge_dst[e]]), float(net.height[v]))
+            if not up[v]:
+                coalesce(arriving, float(net.height[v]), None)
+            elif len(up[v]) == 2:
+                e1, e2 = up[v]
+                g1, g2 = gam[e1], gam[e2]
+                if g1 != g1 and g2 != g2:
+                    g1 = 0.5
+                elif g1 != g1:
+                    g1 = 1.0 - g2
+                for x in arriving:
+                    at_edge.setdefault(e1 if rng.random() < g1 else e2, []).append(x)
+            else:
+                at_edge.setdefault(up[v][0], []).extend(arriving)
+        blen = [float("nan") if parent[i] < 0 else node_h[parent[i]] - node_h[i] for i in range(2 * n_leaves - 1)]
+        trees.append(FlatTree(parent, blen, labels))
+    return trees, species_of
