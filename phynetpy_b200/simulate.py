@@ -1,5 +1,6 @@
-"""Synthetic inputs for tests and benchmarks: random ultrametric gene trees and
-GTR-simulated alignments of the shapes BASELINE.json names.
+"""Synthetic inputs for tests and benchmarks: random ultrametric gene trees,
+GTR-simulated alignments of the shapes BASELINE.json names, random species networks and gene
+trees drawn from the multispecies network coalescent on them.
 
 Host NumPy only (input generation, not part of the timed path).  Own generator:
 the reference's simulators (``src/_sim_seq.py``) are out of scope and are not
