@@ -639,10 +639,7 @@ def msnc_leg(P, ctx, n_loci, n_species, cpu=True, seed=44):
                         "kernel_ms": tm["prune_ms"], "host_prepare_ms": tm["compile_ms"],
                         "finite": int(np.isfinite(vals).sum())}
             if tag == "all_loci":
-                netd = {"n_nodes": net.n_nodes, "edge_src": net.edge_src.tolist(), "edge_dst": net.edge_dst.tolist(),
-                        "edge_gamma": [None if g != g else g for g in net.edge_gamma.tolist()],
-                        "height": net.height.tolist(), "leaf_label": net.leaf_label,
-                        "is_retic": (np.bincount(net.edge_dst, minlength=net.n_nodes) >= 2).tolist()}
+                netd = net.to_dict()
                 k = min(100, n_loci)
                 t0 = time.perf_counter()
                 want = [MO.msnc_log_density(netd, t.parent.tolist(), t.blen.tolist(), t.label, species_of, theta)

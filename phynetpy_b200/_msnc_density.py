@@ -72,6 +72,13 @@ class SpeciesNetwork:
         """From the layout of ``tests/golden/msnc_cases.json`` (``network`` entries)."""
         return cls(d["edge_src"], d["edge_dst"], d["edge_gamma"], d["height"], d["leaf_label"])
 
+    def to_dict(self) -> dict:
+        """The layout :meth:`from_dict` reads (plain lists; ``None`` for an absent gamma)."""
+        return {"n_nodes": self.n_nodes, "edge_src": self.edge_src.tolist(), "edge_dst": self.edge_dst.tolist(),
+                "edge_gamma": [None if g != g else g for g in self.edge_gamma.tolist()],
+                "height": self.height.tolist(), "leaf_label": list(self.leaf_label),
+                "is_retic": (np.bincount(self.edge_dst, minlength=self.n_nodes) >= 2).tolist()}
+
     @classmethod
     def from_network(cls, net: Any) -> "SpeciesNetwork":
         """From an object with the reference's read API: ``V()``, ``E()``, ``edge.src`` / ``.dest`` /

@@ -11,6 +11,7 @@
 
 #include <atomic>
 #include <chrono>
+#include <cstdlib>
 #include <functional>
 
 using namespace pnb;
@@ -41,6 +42,7 @@ struct MsncLaunch {
     double inv_theta, log_two_over_theta;
     double* out;
     int32_t* status;
+    int32_t frontier_in_smem;       // 1: the frontier of every thread lives in shared memory, interleaved
 };
 
 template <int NW>
@@ -55,12 +57,28 @@ __global__ void __launch_bounds__(128) pnb_msnc_kernel(MsncLaunch L) {
     }
     const int64_t e0 = L.ev_off[j];
     const size_t entry = static_cast<size_t>(L.W) * NW;
+    const size_t mask_words = (2 * static_cast<size_t>(L.cap) + 1) * entry;
+    // Frontier storage.  A thread re-reads what it has just written (copy entry, merge slots, compare
+    // for duplicates): in global memory every such read is an L2 round trip, in shared memory ~30 cycles.
+    // Shared layout: word k of thread t at [k * blockDim.x + t] -- consecutive threads, consecutive banks.
+    extern __shared__ uint64_t pnb_msnc_smem[];
+    uint64_t* fr_mask;
+    double* fr_lp;
+    size_t stride;
+    if (L.frontier_in_smem) {
+        fr_mask = pnb_msnc_smem + threadIdx.x;
+        fr_lp = reinterpret_cast<double*>(pnb_msnc_smem + mask_words * blockDim.x) + threadIdx.x;
+        stride = blockDim.x;
+    } else {
+        fr_mask = L.fr_mask + static_cast<size_t>(j) * mask_words;
+        fr_lp = L.fr_lp + static_cast<size_t>(j) * 2 * L.cap;
+        stride = 1;
+    }
     int status;
     const double v = msnc_dp<NW>(L.steps, L.n_steps, L.down_slot, L.W, L.cap, L.ev_t + e0, L.ev_n + e0,
                                  static_cast<int>(L.ev_off[j + 1] - e0),
                                  L.species_mask + static_cast<size_t>(j) * L.n_species * NW, root_bit, L.inv_theta,
-                                 L.log_two_over_theta, L.fr_mask + static_cast<size_t>(j) * (2 * static_cast<size_t>(L.cap) + 1) * entry,
-                                 L.fr_lp + static_cast<size_t>(j) * 2 * L.cap, &status);
+                                 L.log_two_over_theta, fr_mask, fr_lp, stride, &status);
     L.out[j] = v;
     L.status[j] = status;
 }
@@ -277,11 +295,26 @@ extern "C" int pnb_msnc_eval(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_tr
     const size_t entry = static_cast<size_t>(prog.W) * NW;
     const size_t job_mask_words = (2 * static_cast<size_t>(cap) + 1) * entry;
     const size_t per_job = job_mask_words * sizeof(uint64_t) + 2 * static_cast<size_t>(cap) * sizeof(double);
+    // Block size: small batches use small blocks so that they spread over the SMs; the frontier goes to
+    // shared memory when a block's worth of it fits (it does for every tree-shaped network and for
+    // networks whose reticulations sit above few gene lineages), else to a global scratch buffer.
+    int threads = n_trees >= int64_t(ctx->sm_count) * 256 ? 128 : (n_trees >= int64_t(ctx->sm_count) * 128 ? 64 : 32);
+    const size_t smem_limit = static_cast<size_t>(std::max(ctx->max_smem_optin - 2048, 0));
+    const char* no_smem = getenv("PNB_MSNC_NO_SMEM");   // test knob: force the global-scratch path
+    const bool in_smem = per_job * 32 <= smem_limit && !(no_smem && no_smem[0] == '1');
+    if (in_smem)
+        while (per_job * threads > smem_limit) threads /= 2;
+    const size_t dyn_smem = in_smem ? per_job * threads : 0;
     // jobs per launch: bounded scratch (the frontiers of a batch may not fit at once)
     const size_t scratch_budget = size_t{2} << 30;
-    const int64_t jobs_per_launch = std::max<int64_t>(1, std::min<int64_t>(n_trees, static_cast<int64_t>(scratch_budget / per_job)));
+    const int64_t jobs_per_launch =
+        in_smem ? n_trees : std::max<int64_t>(1, std::min<int64_t>(n_trees, static_cast<int64_t>(scratch_budget / per_job)));
     const size_t off_lp = align_up(static_cast<size_t>(jobs_per_launch) * job_mask_words * sizeof(uint64_t), 256);
-    if ((rc = ensure_device(ctx->d_P, off_lp + static_cast<size_t>(jobs_per_launch) * 2 * cap * sizeof(double)))) return rc;
+    if (!in_smem && (rc = ensure_device(ctx->d_P, off_lp + static_cast<size_t>(jobs_per_launch) * 2 * cap * sizeof(double)))) return rc;
+    if (in_smem) {
+        PNB_CUDA_TRY(cudaFuncSetAttribute(pnb_msnc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_limit)));
+        PNB_CUDA_TRY(cudaFuncSetAttribute(pnb_msnc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_limit)));
+    }
     const size_t off_status = align_up(static_cast<size_t>(n_trees) * sizeof(double), 256);
     if ((rc = ensure_device(ctx->d_out, off_status + static_cast<size_t>(n_trees) * sizeof(int32_t)))) return rc;
     if ((rc = ensure_pinned(ctx->h_out, off_status + static_cast<size_t>(n_trees) * sizeof(int32_t)))) return rc;
@@ -300,8 +333,9 @@ extern "C" int pnb_msnc_eval(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_tr
     L.n_species = n_species;
     L.inv_theta = 1.0 / theta;
     L.log_two_over_theta = log(2.0 * L.inv_theta);
-    L.fr_mask = static_cast<uint64_t*>(ctx->d_P.p);
-    L.fr_lp = reinterpret_cast<double*>(static_cast<char*>(ctx->d_P.p) + off_lp);
+    L.frontier_in_smem = in_smem ? 1 : 0;
+    L.fr_mask = in_smem ? nullptr : static_cast<uint64_t*>(ctx->d_P.p);
+    L.fr_lp = in_smem ? nullptr : reinterpret_cast<double*>(static_cast<char*>(ctx->d_P.p) + off_lp);
     int64_t launches = 0;
     for (int64_t j0 = 0; j0 < n_trees; j0 += jobs_per_launch) {
         const int64_t nj = std::min(jobs_per_launch, n_trees - j0);
@@ -313,9 +347,9 @@ extern "C" int pnb_msnc_eval(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_tr
         L.root_bit = reinterpret_cast<const int32_t*>(ds + off_root) + j0;
         L.out = static_cast<double*>(ctx->d_out.p) + j0;
         L.status = reinterpret_cast<int32_t*>(static_cast<char*>(ctx->d_out.p) + off_status) + j0;
-        const unsigned blocks = static_cast<unsigned>((nj + 127) / 128);
-        if (NW == 1) pnb_msnc_kernel<1><<<blocks, 128, 0, st>>>(L);
-        else pnb_msnc_kernel<2><<<blocks, 128, 0, st>>>(L);
+        const unsigned blocks = static_cast<unsigned>((nj + threads - 1) / threads);
+        if (NW == 1) pnb_msnc_kernel<1><<<blocks, threads, dyn_smem, st>>>(L);
+        else pnb_msnc_kernel<2><<<blocks, threads, dyn_smem, st>>>(L);
         PNB_CUDA_TRY(cudaGetLastError());
         ++launches;
     }
@@ -338,6 +372,8 @@ extern "C" int pnb_msnc_eval(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_tr
     ctx->stats[1] = ev_off[n_trees];
     ctx->stats[0] = n_trees;
     ctx->stats[2] = cap - 1;
+    ctx->stats[6] = in_smem ? static_cast<int64_t>(dyn_smem) : 0;   // bytes of shared memory per block holding frontiers
+    ctx->stats[7] = threads;
     ctx->t_call_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call0).count();
     return PNB_OK;
 }

@@ -141,22 +141,24 @@ PNB_HD double log_add(double a, double b) {   // _frontier_acc, src/_msnc_densit
 constexpr int JOB_OK = 0, JOB_OVERFLOW = 1;
 
 // The DP of one gene tree.  Frontier storage, private to the job: fr_mask holds 2*cap + 1 entries of
-// W*NW words (two ping-pong frontiers and one work entry), fr_lp 2*cap doubles.
+// W*NW words (two ping-pong frontiers and one work entry), fr_lp 2*cap doubles; element k of either
+// array lives at [k * stride], so the same code runs on a contiguous global block (stride 1) and on
+// shared memory interleaved over the threads of a block (stride = blockDim.x: conflict-free).
 // Returns log P(g | Psi), -inf if the gene tree does not embed.
 template <int NW>
 PNB_HD double msnc_dp(const Step* steps, int n_steps, const int32_t* down_slot, int W, int cap,
                       const double* ev_t, const uint32_t* ev_n, int n_ev,
                       const uint64_t* species_mask /* [n_species][NW] */, int root_bit,
                       double inv_theta, double log_two_over_theta,
-                      uint64_t* fr_mask, double* fr_lp, int* status) {
+                      uint64_t* fr_mask, double* fr_lp, size_t stride, int* status) {
     const size_t entry = static_cast<size_t>(W) * NW;
-    uint64_t* cur_m = fr_mask;
-    uint64_t* new_m = fr_mask + static_cast<size_t>(cap) * entry;
-    uint64_t* base = fr_mask + 2 * static_cast<size_t>(cap) * entry;
-    double* cur_lp = fr_lp;
-    double* new_lp = fr_lp + cap;
-    for (size_t i = 0; i < entry; ++i) cur_m[i] = 0;
-    cur_lp[0] = 0.0;
+    size_t cur_m = 0, new_m = static_cast<size_t>(cap) * entry;      // word offsets of the two frontiers
+    const size_t base = 2 * static_cast<size_t>(cap) * entry;        // ... and of the work entry
+    size_t cur_lp = 0, new_lp = static_cast<size_t>(cap);
+#define PNB_M(off) fr_mask[(off) * stride]
+#define PNB_LP(off) fr_lp[(off) * stride]
+    for (size_t i = 0; i < entry; ++i) PNB_M(cur_m + i) = 0;
+    PNB_LP(cur_lp) = 0.0;
     int n_cur = 1;
     int root_slot = 0;
     *status = JOB_OK;
@@ -164,32 +166,32 @@ PNB_HD double msnc_dp(const Step* steps, int n_steps, const int32_t* down_slot, 
     for (int s = 0; s < n_steps; ++s) {
         const Step st = steps[s];
         int n_new = 0;
-        // Adds the entry (base with up slot a = ma [, up slot b = mb]) with log-weight lp to the new
+        // Adds the entry (work entry with up slot a = ma [, up slot b = mb]) with log-weight lp to the new
         // frontier; an equal entry already there absorbs it (first-insertion order, as a dict would).
         auto emit = [&](int a, const Mask<NW>& ma, int b, const Mask<NW>& mb, double lp) -> bool {
             if (n_new >= cap) return false;
-            uint64_t* mine = new_m + static_cast<size_t>(n_new) * entry;
-            for (size_t i = 0; i < entry; ++i) mine[i] = base[i];
-            for (int i = 0; i < NW; ++i) mine[static_cast<size_t>(a) * NW + i] = ma.w[i];
+            const size_t mine = new_m + static_cast<size_t>(n_new) * entry;
+            for (size_t i = 0; i < entry; ++i) PNB_M(mine + i) = PNB_M(base + i);
+            for (int i = 0; i < NW; ++i) PNB_M(mine + static_cast<size_t>(a) * NW + i) = ma.w[i];
             if (b >= 0)
-                for (int i = 0; i < NW; ++i) mine[static_cast<size_t>(b) * NW + i] = mb.w[i];
+                for (int i = 0; i < NW; ++i) PNB_M(mine + static_cast<size_t>(b) * NW + i) = mb.w[i];
             for (int j = 0; j < n_new; ++j) {
-                const uint64_t* other = new_m + static_cast<size_t>(j) * entry;
+                const size_t other = new_m + static_cast<size_t>(j) * entry;
                 bool same = true;
-                for (size_t i = 0; i < entry; ++i) same = same && (other[i] == mine[i]);
+                for (size_t i = 0; i < entry; ++i) same = same && (PNB_M(other + i) == PNB_M(mine + i));
                 if (same) {
-                    new_lp[j] = log_add(new_lp[j], lp);
+                    PNB_LP(new_lp + j) = log_add(PNB_LP(new_lp + j), lp);
                     return true;
                 }
             }
-            new_lp[n_new] = lp;
+            PNB_LP(new_lp + n_new) = lp;
             ++n_new;
             return true;
         };
         for (int k = 0; k < n_cur; ++k) {
-            const uint64_t* src = cur_m + static_cast<size_t>(k) * entry;
-            for (size_t i = 0; i < entry; ++i) base[i] = src[i];
-            const double lp = cur_lp[k];
+            const size_t src = cur_m + static_cast<size_t>(k) * entry;
+            for (size_t i = 0; i < entry; ++i) PNB_M(base + i) = PNB_M(src + i);
+            const double lp = PNB_LP(cur_lp + k);
             Mask<NW> at_v;
             at_v.clear();
             if (st.kind & KIND_LEAF) {
@@ -197,10 +199,10 @@ PNB_HD double msnc_dp(const Step* steps, int n_steps, const int32_t* down_slot, 
                     for (int i = 0; i < NW; ++i) at_v.w[i] = species_mask[static_cast<size_t>(st.species) * NW + i];
             } else {
                 for (int d = 0; d < st.n_down; ++d) {
-                    uint64_t* slot = base + static_cast<size_t>(down_slot[st.down_off + d]) * NW;
+                    const size_t slot = base + static_cast<size_t>(down_slot[st.down_off + d]) * NW;
                     for (int i = 0; i < NW; ++i) {
-                        at_v.w[i] |= slot[i];
-                        slot[i] = 0;   // the edge is closed
+                        at_v.w[i] |= PNB_M(slot + i);
+                        PNB_M(slot + i) = 0;   // the edge is closed
                     }
                 }
             }
@@ -234,10 +236,10 @@ PNB_HD double msnc_dp(const Step* steps, int n_steps, const int32_t* down_slot, 
                 return nan("");
             }
         }
-        uint64_t* tm = cur_m;
+        const size_t tm = cur_m;
         cur_m = new_m;
         new_m = tm;
-        double* tl = cur_lp;
+        const size_t tl = cur_lp;
         cur_lp = new_lp;
         new_lp = tl;
         n_cur = n_new;
@@ -245,18 +247,20 @@ PNB_HD double msnc_dp(const Step* steps, int n_steps, const int32_t* down_slot, 
 
     // the one entry whose root slot holds exactly the gene-tree root (src/_msnc_density.py:374-389)
     for (int k = 0; k < n_cur; ++k) {
-        const uint64_t* e = cur_m + static_cast<size_t>(k) * entry + static_cast<size_t>(root_slot) * NW;
+        const size_t e = cur_m + static_cast<size_t>(k) * entry + static_cast<size_t>(root_slot) * NW;
         bool hit = true;
         for (int i = 0; i < NW; ++i) {
             const uint64_t want = ((root_bit >> 6) == i) ? (uint64_t{1} << (root_bit & 63)) : 0;
-            hit = hit && (e[i] == want);
+            hit = hit && (PNB_M(e + i) == want);
         }
         if (hit) {
-            const double score = cur_lp[k];
+            const double score = PNB_LP(cur_lp + k);
             return (score <= LOG_FLOOR + 1.0) ? -INFINITY : score;   // msnc_log_density_prebuilt :488-490
         }
     }
     return -INFINITY;
+#undef PNB_M
+#undef PNB_LP
 }
 
 // ------------------------------------------------------------------------------------------

@@ -12,6 +12,7 @@ extern "C" int msnc_host_eval(int n_nodes, int n_edges, const int32_t* edge_src,
                               const double* edge_gamma, const double* height, const int32_t* node_species,
                               int n_species, int64_t n_trees, const int64_t* tree_off, const int32_t* parent,
                               const double* blen, const int32_t* gene_species, double theta, int cap, int force_nw,
+                              int stride_in,
                               double* out, int32_t* info /* W, n_steps, max status, NW used */, char* err, int err_cap) {
     NetProgram prog;
     std::string e = compile_network(n_nodes, n_edges, edge_src, edge_dst, edge_gamma, height, node_species, n_species, prog);
@@ -31,8 +32,10 @@ extern "C" int msnc_host_eval(int n_nodes, int n_edges, const int32_t* edge_src,
     std::vector<double> ev_t(std::max(max_n, 1));
     std::vector<uint32_t> ev_n(std::max(max_n, 1));
     std::vector<uint64_t> sp_mask(static_cast<size_t>(std::max(n_species, 1)) * NW);
-    std::vector<uint64_t> fr_mask((2 * static_cast<size_t>(cap) + 1) * prog.W * NW);
-    std::vector<double> fr_lp(2 * static_cast<size_t>(cap));
+    // stride > 1 emulates the interleaved shared-memory layout of the kernel (element k at [k * stride])
+    const size_t stride = stride_in > 0 ? static_cast<size_t>(stride_in) : 1;
+    std::vector<uint64_t> fr_mask((2 * static_cast<size_t>(cap) + 1) * prog.W * NW * stride);
+    std::vector<double> fr_lp(2 * static_cast<size_t>(cap) * stride);
     for (int64_t j = 0; j < n_trees; ++j) {
         const int n = static_cast<int>(tree_off[j + 1] - tree_off[j]);
         if (n == 0) {
@@ -50,11 +53,11 @@ extern "C" int msnc_host_eval(int n_nodes, int n_edges, const int32_t* edge_src,
         if (NW == 1)
             out[j] = msnc_dp<1>(prog.steps.data(), static_cast<int>(prog.steps.size()), prog.down_slot.data(), prog.W, cap,
                                 ev_t.data(), ev_n.data(), n_ev, sp_mask.data(), root_bit, inv_theta, l2t, fr_mask.data(),
-                                fr_lp.data(), &status);
+                                fr_lp.data(), stride, &status);
         else
             out[j] = msnc_dp<2>(prog.steps.data(), static_cast<int>(prog.steps.size()), prog.down_slot.data(), prog.W, cap,
                                 ev_t.data(), ev_n.data(), n_ev, sp_mask.data(), root_bit, inv_theta, l2t, fr_mask.data(),
-                                fr_lp.data(), &status);
+                                fr_lp.data(), stride, &status);
         info[2] = std::max(info[2], status);
     }
     return 0;

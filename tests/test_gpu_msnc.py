@@ -43,6 +43,27 @@ def test_golden_density(case):
         assert _close(float(g), e), (g, e)
 
 
+def test_both_frontier_placements_agree(monkeypatch):
+    """The frontier lives in shared memory when a block's worth fits, else in a global scratch buffer
+    (PNB_MSNC_NO_SMEM=1 forces the latter): same DP source, identical results."""
+    P = _pkg()
+    ctx = P.default_context()
+    for name in ("rand_n8_r3_a1", "rand_n16_r0_a1", "rand_n5_r2_a2", "rand_n20_r1_a2"):
+        case = next(c for c in CASES if c["name"] == name)
+        net = P.SpeciesNetwork.from_dict(case["network"])
+        trees = _trees(P, case)
+        monkeypatch.delenv("PNB_MSNC_NO_SMEM", raising=False)
+        a = P.msnc_log_density_batch(trees, net, case["species_of"], case["theta"])
+        smem_bytes = ctx.last_stats()["jobs_cached"]          # stats slot 6: bytes of shared memory per block
+        monkeypatch.setenv("PNB_MSNC_NO_SMEM", "1")
+        b = P.msnc_log_density_batch(trees, net, case["species_of"], case["theta"])
+        assert ctx.last_stats()["jobs_cached"] == 0
+        assert np.array_equal(a, b)
+        if name == "rand_n16_r0_a1":
+            assert smem_bytes > 0                              # a species tree always fits
+    monkeypatch.delenv("PNB_MSNC_NO_SMEM", raising=False)
+
+
 def test_single_tree_entry_point_and_newick_network():
     P = _pkg()
     by = {c["name"]: c for c in CASES}

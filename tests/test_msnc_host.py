@@ -91,22 +91,24 @@ def _pack(case, net=None):
             np.concatenate(sp).astype(np.int32))
 
 
-def _run_harness(lib, net, off, par, bl, sp, theta, cap=4096, force_nw=0):
+def _run_harness(lib, net, off, par, bl, sp, theta, cap=4096, force_nw=0, stride=1):
     n = len(off) - 1
     out = np.zeros(n)
     info = np.zeros(4, np.int32)
     err = C.create_string_buffer(256)
     rc = lib.msnc_host_eval(net.n_nodes, int(net.edge_src.shape[0]), _p(net.edge_src), _p(net.edge_dst), _p(net.edge_gamma),
                             _p(net.height), _p(net.node_species), len(net.species), C.c_int64(n), _p(off), _p(par), _p(bl),
-                            _p(sp), C.c_double(theta), cap, force_nw, _p(out), _p(info), err, 256)
+                            _p(sp), C.c_double(theta), cap, force_nw, stride, _p(out), _p(info), err, 256)
     return rc, out, info, err.value.decode()
 
 
-@pytest.mark.parametrize("force_nw", [0, 2])
+@pytest.mark.parametrize("force_nw,stride", [(0, 1), (2, 1), (0, 32)])
 @pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
-def test_kernel_source_on_host_matches_reference(harness, case, force_nw):
+def test_kernel_source_on_host_matches_reference(harness, case, force_nw, stride):
+    # stride 32 = the interleaved layout the kernel uses when the frontier fits in shared memory
     net, off, par, bl, sp = _pack(case)
-    rc, out, info, err = _run_harness(harness, net, off, par, bl, sp, case["theta"], force_nw=force_nw)
+    rc, out, info, err = _run_harness(harness, net, off, par, bl, sp, case["theta"], force_nw=force_nw, stride=stride,
+                                      cap=256 if stride > 1 else 4096)
     assert rc == 0, err
     assert info[2] == 0   # no frontier overflow
     for got, e in zip(out, case["expected"]):
@@ -222,10 +224,7 @@ def test_extended_newick_reader_rebuilds_the_reference_network(case):
     assert sorted(mine.species) == sorted(ref.species)
     # same density for the same gene trees (node / edge numbering is free)
     for t, e in list(zip(case["trees"], case["expected"]))[:5]:
-        d = {"n_nodes": mine.n_nodes, "edge_src": mine.edge_src.tolist(), "edge_dst": mine.edge_dst.tolist(),
-             "edge_gamma": [None if g != g else g for g in mine.edge_gamma.tolist()],
-             "height": mine.height.tolist(), "is_retic": (np.bincount(mine.edge_dst, minlength=mine.n_nodes) >= 2).tolist(),
-             "leaf_label": mine.leaf_label}
+        d = mine.to_dict()
         got = MO.msnc_log_density(d, t["parent"], t["blen"], t["label"], case["species_of"], case["theta"])
         assert _close(got, _expected(e))
 
