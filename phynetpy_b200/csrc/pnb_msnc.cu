@@ -236,9 +236,9 @@ extern "C" int pnb_msnc_eval(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_tr
                 continue;
             }
             int n_ev = 0, rb = 0;
-            const std::string e = prepare_tree(n, parent + o, blen + o, node_species + o, prog.n_species, NW, sc, ev_t + base,
-                                               ev_n + base, &n_ev, mj, &rb);
-            if (!e.empty()) {
+            const char* e = prepare_tree(n, parent + o, blen + o, node_species + o, prog.n_species, NW, sc, ev_t + base,
+                                         ev_n + base, &n_ev, mj, &rb);
+            if (e) {
                 if (err_job[w] < 0) { err_job[w] = j; errs[w] = e; }
                 root_bit[j] = -1;
                 ev_end[j] = base;

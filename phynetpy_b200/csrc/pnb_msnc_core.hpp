@@ -425,21 +425,27 @@ inline std::string compile_network(int n_nodes, int n_edges, const int32_t* edge
 
 // One gene tree -> sorted coalescence events, species lineage sets, root bit.
 // (_gene_coalescence_events src/_msnc_density.py:142-169; _node_height src/GraphUtils.py:786-819;
-// species_to_bits :262-266.)  Returns "" or an error text.
-struct TreeScratch {
-    std::vector<int32_t> n_kids, remaining, kid0, kid1, queue, order;
-    std::vector<double> h;
+// species_to_bits :262-266.)  Returns nullptr or an error text.  No heap use: at 2*10^4 candidate
+// trees per call this runs ~10^5 times per millisecond budget.
+struct TreeScratch {   // kept for callers that hold one per worker; the work arrays live on the stack
+    int unused = 0;
 };
 
-inline std::string prepare_tree(int n, const int32_t* parent, const double* blen, const int32_t* node_species,
-                                int n_species, int NW, TreeScratch& sc, double* ev_t, uint32_t* ev_n, int* n_ev_out,
+inline const char* prepare_tree(int n, const int32_t* parent, const double* blen, const int32_t* node_species,
+                                int n_species, int NW, TreeScratch&, double* ev_t, uint32_t* ev_n, int* n_ev_out,
                                 uint64_t* species_mask /* [n_species][NW], zeroed here */, int* root_bit_out) {
-    if (n > 64 * NW) return "gene tree has more nodes than the lineage-set width";
-    sc.n_kids.assign(n, 0);
-    sc.kid0.assign(n, -1);
-    sc.kid1.assign(n, -1);
-    sc.h.assign(n, 0.0);
+    constexpr int MAXN = 64 * MAX_NW;
+    if (n > 64 * NW || n > MAXN) return "gene tree has more nodes than the lineage-set width";
+    // written branch-free where the data decides (which child comes first, which child is taller): on random
+    // trees those branches mispredict every other node and were 3/4 of this function's time
+    uint8_t n_kids[MAXN], kid[MAXN][2], remaining[MAXN], queue[MAXN], order[MAXN];
+    double h[MAXN];
     int root = -1;
+    bool children_first = true;    // parent[i] > i for every non-root node: one forward pass gives the heights
+    for (int i = 0; i < n; ++i) {
+        n_kids[i] = 0;
+        h[i] = 0.0;
+    }
     for (int i = 0; i < n; ++i) {
         const int p = parent[i];
         if (p < 0) {
@@ -447,48 +453,65 @@ inline std::string prepare_tree(int n, const int32_t* parent, const double* blen
             continue;
         }
         if (p >= n || p == i) return "gene-tree parent index out of range";
-        if (sc.n_kids[p] == 0) sc.kid0[p] = i;
-        else if (sc.n_kids[p] == 1) sc.kid1[p] = i;
-        ++sc.n_kids[p];
+        children_first = children_first & (p > i);
+        const unsigned c = n_kids[p];
+        kid[p][c < 1u ? c : 1u] = static_cast<uint8_t>(i);    // a third child overwrites [1]; such a node emits no event
+        n_kids[p] = static_cast<uint8_t>(c + (c < 255u));
     }
     if (root < 0) return "gene tree has no root";
     for (size_t i = 0; i < static_cast<size_t>(n_species) * NW; ++i) species_mask[i] = 0;
-    // heights: children before parents (Kahn)
-    sc.remaining = sc.n_kids;
-    sc.queue.clear();
     for (int i = 0; i < n; ++i)
-        if (sc.n_kids[i] == 0) {
-            sc.queue.push_back(i);
+        if (n_kids[i] == 0) {
             const int sp = node_species[i];
             if (sp >= n_species) return "gene-tree leaf species id out of range";
             if (sp >= 0) species_mask[static_cast<size_t>(sp) * NW + (i >> 6)] |= uint64_t{1} << (i & 63);
         }
-    size_t head = 0;
-    while (head < sc.queue.size()) {
-        const int v = sc.queue[head++];
-        const int p = parent[v];
-        if (p < 0) continue;
-        double len = blen[v];
-        if (!(len == len)) len = 0.0;            // None counts as 0
-        const double cand = sc.h[v] + len;
-        if (cand > sc.h[p]) sc.h[p] = cand;
-        if (--sc.remaining[p] == 0) sc.queue.push_back(p);
+    if (children_first) {
+        for (int v = 0; v < n; ++v) {
+            const int p = parent[v];
+            if (p < 0) continue;
+            const double len = blen[v];
+            const double cand = h[v] + ((len == len) ? len : 0.0);   // None counts as 0
+            h[p] = (cand > h[p]) ? cand : h[p];
+        }
+    } else {   // children before parents by Kahn's algorithm
+        int tail = 0;
+        for (int i = 0; i < n; ++i) {
+            remaining[i] = n_kids[i];
+            if (n_kids[i] == 0) queue[tail++] = static_cast<uint8_t>(i);
+        }
+        int head = 0;
+        while (head < tail) {
+            const int v = queue[head++];
+            const int p = parent[v];
+            if (p < 0) continue;
+            const double len = blen[v];
+            const double cand = h[v] + ((len == len) ? len : 0.0);
+            h[p] = (cand > h[p]) ? cand : h[p];
+            if (--remaining[p] == 0) queue[tail++] = static_cast<uint8_t>(p);
+        }
+        if (tail != n) return "gene tree has a cycle";
     }
-    if (static_cast<int>(sc.queue.size()) != n) return "gene tree has a cycle";
-    // events: binary nodes in node order, stable sort by time
-    sc.order.clear();
-    for (int i = 0; i < n; ++i)
-        if (sc.n_kids[i] == 2) sc.order.push_back(i);
-    std::stable_sort(sc.order.begin(), sc.order.end(), [&](int a, int b) { return sc.h[a] < sc.h[b]; });
+    // events: binary nodes in node order, stably sorted by time (insertion keeps equal times in node order)
     int k = 0;
-    for (int v : sc.order) {
-        ev_t[k] = sc.h[v];
-        ev_n[k] = static_cast<uint32_t>(v) | (static_cast<uint32_t>(sc.kid0[v]) << 8) | (static_cast<uint32_t>(sc.kid1[v]) << 16);
+    for (int v = 0; v < n; ++v) {
+        if (n_kids[v] != 2) continue;
+        int pos = k;
+        while (pos > 0 && h[order[pos - 1]] > h[v]) {
+            order[pos] = order[pos - 1];
+            --pos;
+        }
+        order[pos] = static_cast<uint8_t>(v);
         ++k;
+    }
+    for (int e = 0; e < k; ++e) {
+        const int v = order[e];
+        ev_t[e] = h[v];
+        ev_n[e] = static_cast<uint32_t>(v) | (static_cast<uint32_t>(kid[v][0]) << 8) | (static_cast<uint32_t>(kid[v][1]) << 16);
     }
     *n_ev_out = k;
     *root_bit_out = root;
-    return "";
+    return nullptr;
 }
 
 // Upper bound on the frontier size of any job whose species s carries at most alleles[s] gene leaves:

@@ -43,10 +43,10 @@ extern "C" int msnc_host_eval(int n_nodes, int n_edges, const int32_t* edge_src,
             continue;
         }
         int n_ev = 0, root_bit = 0;
-        e = prepare_tree(n, parent + tree_off[j], blen + tree_off[j], gene_species + tree_off[j], n_species, NW, sc,
-                         ev_t.data(), ev_n.data(), &n_ev, sp_mask.data(), &root_bit);
-        if (!e.empty()) {
-            snprintf(err, err_cap, "tree %lld: %s", static_cast<long long>(j), e.c_str());
+        const char* te = prepare_tree(n, parent + tree_off[j], blen + tree_off[j], gene_species + tree_off[j], n_species, NW, sc,
+                                      ev_t.data(), ev_n.data(), &n_ev, sp_mask.data(), &root_bit);
+        if (te) {
+            snprintf(err, err_cap, "tree %lld: %s", static_cast<long long>(j), te);
             return 1;
         }
         int status = 0;
