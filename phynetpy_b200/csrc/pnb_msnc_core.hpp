@@ -104,20 +104,21 @@ struct Mask {
 };
 
 // One lineage set through one species branch (reference _apply_branch_timed, single entry).
-// ev_n packs parent | child0 << 8 | child1 << 16 (gene-tree node indices).
+// ev_n packs parent | child0 << 8 | child1 << 16 (gene-tree node indices).  [j_lo, j_hi) is the range of
+// events with tau_low <= t < tau_high -- the events the reference's loop does not skip (`t < tau_low:
+// continue`) before it stops (`t >= tau_high: break`); it depends on the step only, so the caller finds it
+// once per step instead of re-scanning the event list for every frontier entry and every subset.
 template <int NW>
 PNB_HD void branch_timed(Mask<NW>& cfg, double& lp_out, double tau_low, double tau_high, bool has_high,
                          double inv_theta, double log_two_over_theta, const double* ev_t,
-                         const uint32_t* ev_n, int n_ev) {
+                         const uint32_t* ev_n, int j_lo, int j_hi) {
     double cur = tau_low, lp = 0.0;
     int u = cfg.count();
-    for (int j = 0; j < n_ev; ++j) {
-        const double t = ev_t[j];
-        if (t < tau_low) continue;
-        if (has_high && t >= tau_high) break;
+    for (int j = j_lo; j < j_hi; ++j) {
         const uint32_t e = ev_n[j];
         const int c0 = (e >> 8) & 0xff, c1 = (e >> 16) & 0xff;
         if (cfg.test(c0) && cfg.test(c1)) {
+            const double t = ev_t[j];
             double b = mul_rn(mul_rn(mul_rn(-(t - cur), static_cast<double>(u)), static_cast<double>(u - 1)), inv_theta);
             b = add_rn(b, log_two_over_theta);
             cur = t;
@@ -131,6 +132,17 @@ PNB_HD void branch_timed(Mask<NW>& cfg, double& lp_out, double tau_low, double t
     if (has_high && u > 1)
         lp = add_rn(lp, mul_rn(mul_rn(mul_rn(-(tau_high - cur), static_cast<double>(u)), static_cast<double>(u - 1)), inv_theta));
     lp_out = lp;
+}
+
+// Events are sorted by time: first index with t >= tau (n_ev if none).
+PNB_HD int first_event_at_or_after(const double* ev_t, int n_ev, double tau) {
+    int lo = 0, hi = n_ev;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (ev_t[mid] < tau) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
 }
 
 PNB_HD double log_add(double a, double b) {   // _frontier_acc, src/_msnc_density.py:1408-1419
@@ -166,6 +178,11 @@ PNB_HD double msnc_dp(const Step* steps, int n_steps, const int32_t* down_slot, 
     for (int s = 0; s < n_steps; ++s) {
         const Step st = steps[s];
         int n_new = 0;
+        // the events inside this node's parent branch(es): a property of the step, shared by all entries
+        const int j_lo = first_event_at_or_after(ev_t, n_ev, st.tau_low);
+        const bool is_root = (st.kind & KIND_ROOT) != 0;
+        const int j_hi0 = is_root ? n_ev : first_event_at_or_after(ev_t, n_ev, st.tau_high[0]);
+        const int j_hi1 = (st.kind & KIND_RETIC) ? first_event_at_or_after(ev_t, n_ev, st.tau_high[1]) : j_lo;
         // Adds the entry (work entry with up slot a = ma [, up slot b = mb]) with log-weight lp to the new
         // frontier; an equal entry already there absorbs it (first-insertion order, as a dict would).
         auto emit = [&](int a, const Mask<NW>& ma, int b, const Mask<NW>& mb, double lp) -> bool {
@@ -217,8 +234,8 @@ PNB_HD double msnc_dp(const Step* steps, int n_steps, const int32_t* down_slot, 
                     Mask<NW> top1 = sub, top2;
                     for (int i = 0; i < NW; ++i) top2.w[i] = at_v.w[i] ^ sub.w[i];
                     double lp1, lp2;
-                    branch_timed<NW>(top1, lp1, st.tau_low, st.tau_high[0], true, inv_theta, log_two_over_theta, ev_t, ev_n, n_ev);
-                    branch_timed<NW>(top2, lp2, st.tau_low, st.tau_high[1], true, inv_theta, log_two_over_theta, ev_t, ev_n, n_ev);
+                    branch_timed<NW>(top1, lp1, st.tau_low, st.tau_high[0], true, inv_theta, log_two_over_theta, ev_t, ev_n, j_lo, j_hi0);
+                    branch_timed<NW>(top2, lp2, st.tau_low, st.tau_high[1], true, inv_theta, log_two_over_theta, ev_t, ev_n, j_lo, j_hi1);
                     // lp + factor + lp1 + lp2, left to right (src/_msnc_density.py:353)
                     ok = emit(st.up_slot[0], top1, st.up_slot[1], top2, add_rn(add_rn(add_rn(lp, factor), lp1), lp2));
                     if (!ok || sub.zero()) break;
@@ -226,8 +243,7 @@ PNB_HD double msnc_dp(const Step* steps, int n_steps, const int32_t* down_slot, 
                 }
             } else {
                 double blp;
-                const bool is_root = (st.kind & KIND_ROOT) != 0;
-                branch_timed<NW>(at_v, blp, st.tau_low, st.tau_high[0], !is_root, inv_theta, log_two_over_theta, ev_t, ev_n, n_ev);
+                branch_timed<NW>(at_v, blp, st.tau_low, st.tau_high[0], !is_root, inv_theta, log_two_over_theta, ev_t, ev_n, j_lo, j_hi0);
                 if (is_root) root_slot = st.up_slot[0];
                 ok = emit(st.up_slot[0], at_v, -1, at_v, add_rn(lp, blp));
             }
