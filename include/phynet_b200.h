@@ -192,6 +192,10 @@ PNB_API int pnb_msnc_net_create(pnb_ctx *ctx, int32_t n_nodes, int32_t n_edges, 
 PNB_API int pnb_msnc_net_destroy(pnb_msnc_net *net);
 /* info: [0] open-edge slots per frontier entry, [1] steps (= nodes), [2] reticulations, [3] species */
 PNB_API int pnb_msnc_net_info(const pnb_msnc_net *net, int32_t info[4]);
+/* Fixed per-population thetas (the reference's branch_thetas, resolve_branch_theta src/_units.py:90-125, with
+ * the label keys already turned into edge ids by the caller): edge_theta[e] replaces the call's theta on the
+ * branch of edge e, root_theta on the branch above the root; NaN = no override.  edge_theta NULL clears all. */
+PNB_API int pnb_msnc_net_set_branch_thetas(pnb_msnc_net *net, const double *edge_theta, double root_theta);
 /* Frontier entries a single gene tree may need before pnb_msnc_eval gives up with
  * PNB_ERR_UNSUPPORTED (default 65536; the scratch is sized from the network and the batch, this is
  * only the ceiling).                                                                          */

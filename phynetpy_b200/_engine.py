@@ -72,8 +72,6 @@ class SeqLikelihoodEngine:
         self.last_stats: dict = {}
         # MSNC side: the network view is rebuilt when a different network OBJECT arrives (the reference
         # keys on identity too, src/_mcmc_seq.py:705-713); per-locus species ids are keyed by the label list
-        if branch_thetas and msnc_fn is None:
-            raise NotImplementedError("per-branch thetas are not implemented on the device MSNC path; pass msnc_fn")
         self._net_obj: Any = None
         self._net: Optional[SpeciesNetwork] = None
         self._sp_ids: List[Optional[Tuple[Any, np.ndarray]]] = [None] * self.n_loci
@@ -237,7 +235,7 @@ class SeqLikelihoodEngine:
         parent = np.ascontiguousarray(np.concatenate([t.parent for t in flats]), dtype=np.int32)
         blen = np.ascontiguousarray(np.concatenate([t.blen for t in flats]), dtype=np.float64)
         ids = np.ascontiguousarray(np.concatenate([self._species_ids(i, t, net) for i, t in zip(need, flats)]), dtype=np.int32)
-        vals = msnc_eval_packed(net, off, parent, blen, ids, theta, self._context())
+        vals = msnc_eval_packed(net, off, parent, blen, ids, theta, self._context(), self._branch_thetas)
         for i, v in zip(need, vals):
             self._msnc[i] = float(v)
 
@@ -272,7 +270,8 @@ class SeqLikelihoodEngine:
         np.cumsum(sizes, out=off[1:])
         out = msnc_eval_packed(net, off, np.ascontiguousarray(np.concatenate(parents), dtype=np.int32),
                                np.ascontiguousarray(np.concatenate(blens), dtype=np.float64),
-                               np.ascontiguousarray(np.concatenate(idss), dtype=np.int32), theta, self._context())
+                               np.ascontiguousarray(np.concatenate(idss), dtype=np.int32), theta, self._context(),
+                               self._branch_thetas)
         res, k = [], 0
         for K in per_set:
             res.append(out[k:k + K])

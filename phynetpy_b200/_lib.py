@@ -39,7 +39,8 @@ ABI_SYMBOLS = (
     "pnb_locus_create", "pnb_locus_destroy", "pnb_locus_invalidate", "pnb_locus_read_partial",
     "pnb_eval", "pnb_commit", "pnb_rollback",
     "pnb_ctx_create_host", "pnb_plan",
-    "pnb_msnc_net_create", "pnb_msnc_net_destroy", "pnb_msnc_net_info", "pnb_msnc_net_set_max_frontier", "pnb_msnc_eval",
+    "pnb_msnc_net_create", "pnb_msnc_net_destroy", "pnb_msnc_net_info", "pnb_msnc_net_set_max_frontier", "pnb_msnc_net_set_branch_thetas",
+    "pnb_msnc_eval",
 )
 
 
@@ -102,6 +103,7 @@ def load() -> C.CDLL:
             "pnb_msnc_net_destroy": [_vp],
             "pnb_msnc_net_info": [_vp, C.POINTER(_i32)],
             "pnb_msnc_net_set_max_frontier": [_vp, _i64],
+            "pnb_msnc_net_set_branch_thetas": [_vp, _vp, C.c_double],
             "pnb_msnc_eval": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, C.c_double, _vp],
         }
         for name, argtypes in sigs.items():

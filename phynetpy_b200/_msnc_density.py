@@ -12,7 +12,7 @@ Mirrors the public surface of the reference's ``src/_msnc_density.py`` for the t
   ``[&gamma=...]`` annotations.
 
 The arithmetic runs in kernel K-m behind ``pnb_msnc_eval`` (``include/phynet_b200.h``); there is no
-CPU fallback.  Per-branch thetas (``branch_thetas``) are not implemented and raise.
+CPU fallback.  Fixed per-branch thetas (``branch_thetas``, label-keyed as in ``src/_units.py``) are supported.
 """
 from __future__ import annotations
 
@@ -40,13 +40,16 @@ class SpeciesNetwork:
     """
 
     def __init__(self, edge_src: Sequence[int], edge_dst: Sequence[int], edge_gamma: Sequence[Optional[float]],
-                 height: Sequence[float], leaf_label: Sequence[Optional[str]]):
+                 height: Sequence[float], leaf_label: Sequence[Optional[str]],
+                 node_label: Optional[Sequence[Optional[str]]] = None):
         self.edge_src = np.ascontiguousarray(edge_src, dtype=np.int32)
         self.edge_dst = np.ascontiguousarray(edge_dst, dtype=np.int32)
         self.edge_gamma = np.ascontiguousarray(
             [math.nan if g is None else float(g) for g in edge_gamma], dtype=np.float64)
         self.height = np.ascontiguousarray(height, dtype=np.float64)
         self.leaf_label = list(leaf_label)
+        # labels of ALL nodes: only needed to resolve label-keyed per-branch thetas
+        self.node_label = list(node_label) if node_label is not None else list(leaf_label)
         n = self.height.shape[0]
         if len(self.leaf_label) != n:
             raise ValueError("SpeciesNetwork: height and leaf_label must have one entry per node")
@@ -70,13 +73,13 @@ class SpeciesNetwork:
     @classmethod
     def from_dict(cls, d: dict) -> "SpeciesNetwork":
         """From the layout of ``tests/golden/msnc_cases.json`` (``network`` entries)."""
-        return cls(d["edge_src"], d["edge_dst"], d["edge_gamma"], d["height"], d["leaf_label"])
+        return cls(d["edge_src"], d["edge_dst"], d["edge_gamma"], d["height"], d["leaf_label"], d.get("node_label"))
 
     def to_dict(self) -> dict:
         """The layout :meth:`from_dict` reads (plain lists; ``None`` for an absent gamma)."""
         return {"n_nodes": self.n_nodes, "edge_src": self.edge_src.tolist(), "edge_dst": self.edge_dst.tolist(),
                 "edge_gamma": [None if g != g else g for g in self.edge_gamma.tolist()],
-                "height": self.height.tolist(), "leaf_label": list(self.leaf_label),
+                "height": self.height.tolist(), "leaf_label": list(self.leaf_label), "node_label": list(self.node_label),
                 "is_retic": (np.bincount(self.edge_dst, minlength=self.n_nodes) >= 2).tolist()}
 
     @classmethod
@@ -114,7 +117,7 @@ class SpeciesNetwork:
         for v in range(n):
             height(v)
         labels = [nodes[v].label if not kids[v] else None for v in range(n)]
-        return cls(src, dst, gam, h, labels)
+        return cls(src, dst, gam, h, labels, [getattr(nd, "label", None) for nd in nodes])
 
     @classmethod
     def from_newick(cls, newick: str) -> "SpeciesNetwork":
@@ -204,7 +207,7 @@ class SpeciesNetwork:
         else:
             raise ValueError("extended Newick: the network has a cycle")
         leaf_label = [labels[v] if not kids[v] else None for v in range(n)]
-        return cls([e[0] for e in edges], [e[1] for e in edges], [e[3] for e in edges], h, leaf_label)
+        return cls([e[0] for e in edges], [e[1] for e in edges], [e[3] for e in edges], h, leaf_label, labels)
 
     # -- device handle -------------------------------------------------------------------------
     @property
@@ -214,13 +217,40 @@ class SpeciesNetwork:
     def n_reticulations(self) -> int:
         return int((np.bincount(self.edge_dst, minlength=self.n_nodes) >= 2).sum())
 
-    def handle(self, ctx: DeviceContext) -> C.c_void_p:
+    def handle(self, ctx: DeviceContext, branch_thetas: Optional[dict] = None) -> C.c_void_p:
         key = (os.getpid(), id(ctx))
         h = self._handles.get(key)
         if h is None or h.ctx is not ctx or ctx._h is None:
             h = _NetHandle(self, ctx)
             self._handles[key] = h
+        h.set_branch_thetas(self, branch_thetas)
         return h.h
+
+    def branch_theta_arrays(self, branch_thetas: Optional[dict]) -> Tuple[Optional[np.ndarray], float]:
+        """Label-keyed overrides -> (theta per edge, theta above the root), NaN = the default theta.
+        Precedence as ``resolve_branch_theta`` (``src/_units.py:90-125``): ``(parent_label, child_label)``
+        before ``child_label``; above the root ``("__root__", label)``, ``"__root__"``, then the label."""
+        if not branch_thetas:
+            return None, math.nan
+        validate_branch_thetas(branch_thetas)
+        lab = self.node_label
+        edge_theta = np.full(self.edge_src.shape[0], math.nan, dtype=np.float64)
+        for e, (s, d) in enumerate(zip(self.edge_src.tolist(), self.edge_dst.tolist())):
+            for key in ((lab[s], lab[d]), lab[d]):
+                if key in branch_thetas:
+                    edge_theta[e] = float(branch_thetas[key])
+                    break
+        root_theta = math.nan
+        has_parent = np.zeros(self.n_nodes, dtype=bool)
+        has_parent[self.edge_dst] = True
+        roots = np.nonzero(~has_parent)[0]
+        if roots.shape[0]:
+            r = lab[int(roots[0])]
+            for key in (("__root__", r), "__root__", r):
+                if key in branch_thetas:
+                    root_theta = float(branch_thetas[key])
+                    break
+        return edge_theta, root_theta
 
     def info(self, ctx: Optional[DeviceContext] = None) -> Dict[str, int]:
         """Shape of the compiled step program (open-edge slots, steps, reticulations, species)."""
@@ -258,6 +288,16 @@ class _NetHandle:
             _lib.ptr(net.edge_gamma), _lib.ptr(net.height), _lib.ptr(net.node_species), len(net.species), C.byref(h)))
         self.h = h
         self._pid = os.getpid()
+        self._thetas: Any = None      # the branch_thetas mapping currently installed on the handle (by content)
+
+    def set_branch_thetas(self, net: "SpeciesNetwork", branch_thetas: Optional[dict]) -> None:
+        want = tuple(sorted(branch_thetas.items(), key=repr)) if branch_thetas else None
+        if want == self._thetas:
+            return
+        edge_theta, root_theta = net.branch_theta_arrays(branch_thetas)
+        _lib.check(self._lib.pnb_msnc_net_set_branch_thetas(
+            self.h, _lib.ptr(edge_theta) if edge_theta is not None else None, C.c_double(root_theta)))
+        self._thetas = want
 
     def __del__(self):
         try:
@@ -278,23 +318,38 @@ def as_species_network(species_net: Any) -> SpeciesNetwork:
     return SpeciesNetwork.from_network(species_net)
 
 
+def validate_branch_thetas(branch_thetas: Optional[dict]) -> None:
+    """``validate_branch_thetas`` of the reference (``src/_units.py:71-87``)."""
+    for key, value in (branch_thetas or {}).items():
+        if not (isinstance(key, str) or (isinstance(key, tuple) and len(key) == 2 and all(isinstance(x, str) for x in key))):
+            raise ValueError("branch theta keys must be child labels or (parent_label, child_label) pairs; got %r." % (key,))
+        try:
+            v = float(value)
+        except (TypeError, ValueError) as exc:
+            raise ValueError("branch theta for %r must be numeric; got %r." % (key, value)) from exc
+        if not math.isfinite(v) or v <= 0.0:
+            raise ValueError("branch theta for %r must be finite and positive; got %s." % (key, v))
+
+
 def msnc_eval_packed(net: SpeciesNetwork, tree_off: np.ndarray, parent: np.ndarray, blen: np.ndarray,
-                     node_species: np.ndarray, theta: float, context: Optional[DeviceContext] = None) -> np.ndarray:
+                     node_species: np.ndarray, theta: float, context: Optional[DeviceContext] = None,
+                     branch_thetas: Optional[dict] = None) -> np.ndarray:
     """``pnb_msnc_eval`` on CSR-packed gene trees (the form candidate batches are built in)."""
     ctx = context or default_context()
     n = int(tree_off.shape[0]) - 1
     assert tree_off.dtype == np.int64 and parent.dtype == np.int32 and blen.dtype == np.float64
     assert node_species.dtype == np.int32
     out = np.empty(n, dtype=np.float64)
-    _lib.check(_lib.load().pnb_msnc_eval(ctx.handle, net.handle(ctx), n, _lib.ptr(tree_off), _lib.ptr(parent),
+    _lib.check(_lib.load().pnb_msnc_eval(ctx.handle, net.handle(ctx, branch_thetas), n, _lib.ptr(tree_off), _lib.ptr(parent),
                                          _lib.ptr(blen), _lib.ptr(node_species), float(theta), _lib.ptr(out)))
     return out
 
 
 def msnc_log_density_batch(gene_trees: Sequence[Any], species_net: Any, species_of: Dict[str, str], theta: float,
-                           *, context: Optional[DeviceContext] = None) -> np.ndarray:
+                           *, branch_thetas: Optional[dict] = None, context: Optional[DeviceContext] = None) -> np.ndarray:
     """log P(g_j | Psi) for every gene tree in one device call; ``-inf`` where g_j does not embed."""
     _check_theta(theta)
+    validate_branch_thetas(branch_thetas)
     net = as_species_network(species_net)
     flats = [flatten(g) for g in gene_trees]
     if not flats:
@@ -305,15 +360,14 @@ def msnc_log_density_batch(gene_trees: Sequence[Any], species_net: Any, species_
     parent = np.ascontiguousarray(np.concatenate([t.parent for t in flats]), dtype=np.int32)
     blen = np.ascontiguousarray(np.concatenate([t.blen for t in flats]), dtype=np.float64)
     nsp = np.ascontiguousarray(np.concatenate([net.species_ids_of(t, species_of) for t in flats]), dtype=np.int32)
-    return msnc_eval_packed(net, off, parent, blen, nsp, theta, context)
+    return msnc_eval_packed(net, off, parent, blen, nsp, theta, context, branch_thetas)
 
 
 def gene_tree_msnc_log_density(gene_tree: Any, species_net: Any, species_of: Dict[str, str], *, theta: float = 0.02,
                                branch_thetas: Optional[dict] = None, context: Optional[DeviceContext] = None) -> float:
     """Log timed MSNC density log P(g | Psi) (reference ``gene_tree_msnc_log_density``, ``:496-526``)."""
-    if branch_thetas:
-        raise NotImplementedError("per-branch thetas are not implemented on the device path")
-    return float(msnc_log_density_batch([gene_tree], species_net, species_of, theta, context=context)[0])
+    return float(msnc_log_density_batch([gene_tree], species_net, species_of, theta, branch_thetas=branch_thetas,
+                                        context=context)[0])
 
 
 def _check_theta(theta: Any) -> float:

@@ -23,6 +23,9 @@ struct pnb_msnc_net {
     Step* d_steps = nullptr;
     int32_t* d_down = nullptr;
     int64_t max_frontier = 1 << 16;   // entries per job the scratch may be sized for
+    int32_t n_edges = 0;
+    std::vector<double> edge_theta;   // per-branch theta overrides (NaN = the call's theta); empty = none
+    double root_theta = NAN;
 };
 
 namespace {
@@ -39,7 +42,7 @@ struct MsncLaunch {
     const int32_t* root_bit;        // [n_jobs]; -1 = empty gene tree
     uint64_t* fr_mask;              // [n_jobs][(2 cap + 1) W NW]
     double* fr_lp;                  // [n_jobs][2 cap]
-    double inv_theta, log_two_over_theta;
+    const double* step_theta;       // [n_steps][4]: 1/theta, log(2/theta) of the branch(es) above each step's node
     double* out;
     int32_t* status;
     int32_t frontier_in_smem;       // 1: the frontier of every thread lives in shared memory, interleaved
@@ -77,8 +80,8 @@ __global__ void __launch_bounds__(128) pnb_msnc_kernel(MsncLaunch L) {
     int status;
     const double v = msnc_dp<NW>(L.steps, L.n_steps, L.down_slot, L.W, L.cap, L.ev_t + e0, L.ev_n + e0,
                                  static_cast<int>(L.ev_off[j + 1] - e0),
-                                 L.species_mask + static_cast<size_t>(j) * L.n_species * NW, root_bit, L.inv_theta,
-                                 L.log_two_over_theta, fr_mask, fr_lp, stride, &status);
+                                 L.species_mask + static_cast<size_t>(j) * L.n_species * NW, root_bit, L.step_theta,
+                                 fr_mask, fr_lp, stride, &status);
     L.out[j] = v;
     L.status[j] = status;
 }
@@ -95,6 +98,7 @@ extern "C" int pnb_msnc_net_create(pnb_ctx* ctx, int32_t n_nodes, int32_t n_edge
     pnb_msnc_net* net = new (std::nothrow) pnb_msnc_net();
     PNB_REQUIRE(net, PNB_ERR_NOMEM, "pnb_msnc_net_create: out of host memory");
     net->ctx = ctx;
+    net->n_edges = n_edges;
     const std::string err = compile_network(n_nodes, n_edges, edge_src, edge_dst, edge_gamma, node_height, node_species,
                                             n_species, net->prog);
     if (!err.empty()) {
@@ -155,6 +159,22 @@ extern "C" int pnb_msnc_net_info(const pnb_msnc_net* net, int32_t info[4]) {
     return PNB_OK;
 }
 
+extern "C" int pnb_msnc_net_set_branch_thetas(pnb_msnc_net* net, const double* edge_theta, double root_theta) {
+    PNB_REQUIRE(net, PNB_ERR_INVALID, "pnb_msnc_net_set_branch_thetas: NULL network");
+    if (edge_theta) {
+        for (int32_t e = 0; e < net->n_edges; ++e)
+            PNB_REQUIRE(!(edge_theta[e] == edge_theta[e]) || (edge_theta[e] > 0.0 && std::isfinite(edge_theta[e])), PNB_ERR_INVALID,
+                        "pnb_msnc_net_set_branch_thetas: theta of edge %d must be finite and positive", e);
+        net->edge_theta.assign(edge_theta, edge_theta + net->n_edges);
+    } else {
+        net->edge_theta.clear();
+    }
+    PNB_REQUIRE(!(root_theta == root_theta) || (root_theta > 0.0 && std::isfinite(root_theta)), PNB_ERR_INVALID,
+                "pnb_msnc_net_set_branch_thetas: root theta must be finite and positive");
+    net->root_theta = root_theta;
+    return PNB_OK;
+}
+
 extern "C" int pnb_msnc_net_set_max_frontier(pnb_msnc_net* net, int64_t entries) {
     PNB_REQUIRE(net && entries >= 1, PNB_ERR_INVALID, "pnb_msnc_net_set_max_frontier: bad argument");
     net->max_frontier = entries;
@@ -197,7 +217,8 @@ extern "C" int pnb_msnc_eval(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_tr
     const size_t off_evt = align_up(off_root + static_cast<size_t>(n_trees) * sizeof(int32_t), 256);
     const size_t off_evn = align_up(off_evt + ev_cap * sizeof(double), 256);
     const size_t off_sp = align_up(off_evn + ev_cap * sizeof(uint32_t), 256);
-    const size_t stage_bytes = off_sp + static_cast<size_t>(n_trees) * n_species * NW * sizeof(uint64_t);
+    const size_t off_theta = align_up(off_sp + static_cast<size_t>(n_trees) * n_species * NW * sizeof(uint64_t), 256);
+    const size_t stage_bytes = off_theta + prog.steps.size() * 4 * sizeof(double);
 
     // the felsenstein path's staging buffers are reused: wait for whatever still reads them
     PNB_CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
@@ -211,6 +232,8 @@ extern "C" int pnb_msnc_eval(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_tr
     double* ev_t = reinterpret_cast<double*>(hs + off_evt);
     uint32_t* ev_n = reinterpret_cast<uint32_t*>(hs + off_evn);
     uint64_t* sp_mask = reinterpret_cast<uint64_t*>(hs + off_sp);
+    fill_step_theta(prog, theta, net->edge_theta.empty() ? nullptr : net->edge_theta.data(), net->root_theta,
+                    reinterpret_cast<double*>(hs + off_theta));
 
     // ---- host preparation, parallel over trees ---------------------------------------------
     // job j writes its events at slot base (tree_off[j] - tree_off[0]) / 2 + j (disjoint, an upper
@@ -331,8 +354,7 @@ extern "C" int pnb_msnc_eval(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_tr
     L.W = prog.W;
     L.cap = cap;
     L.n_species = n_species;
-    L.inv_theta = 1.0 / theta;
-    L.log_two_over_theta = log(2.0 * L.inv_theta);
+    L.step_theta = reinterpret_cast<const double*>(ds + off_theta);
     L.frontier_in_smem = in_smem ? 1 : 0;
     L.fr_mask = in_smem ? nullptr : static_cast<uint64_t*>(ctx->d_P.p);
     L.fr_lp = in_smem ? nullptr : reinterpret_cast<double*>(static_cast<char*>(ctx->d_P.p) + off_lp);

@@ -161,7 +161,7 @@ template <int NW>
 PNB_HD double msnc_dp(const Step* steps, int n_steps, const int32_t* down_slot, int W, int cap,
                       const double* ev_t, const uint32_t* ev_n, int n_ev,
                       const uint64_t* species_mask /* [n_species][NW] */, int root_bit,
-                      double inv_theta, double log_two_over_theta,
+                      const double* step_theta /* [n_steps][4]: 1/theta and log(2/theta) of the up branch(es) */,
                       uint64_t* fr_mask, double* fr_lp, size_t stride, int* status) {
     const size_t entry = static_cast<size_t>(W) * NW;
     size_t cur_m = 0, new_m = static_cast<size_t>(cap) * entry;      // word offsets of the two frontiers
@@ -183,6 +183,8 @@ PNB_HD double msnc_dp(const Step* steps, int n_steps, const int32_t* down_slot, 
         const bool is_root = (st.kind & KIND_ROOT) != 0;
         const int j_hi0 = is_root ? n_ev : first_event_at_or_after(ev_t, n_ev, st.tau_high[0]);
         const int j_hi1 = (st.kind & KIND_RETIC) ? first_event_at_or_after(ev_t, n_ev, st.tau_high[1]) : j_lo;
+        const double inv_theta0 = step_theta[4 * s], l2t0 = step_theta[4 * s + 1];
+        const double inv_theta1 = step_theta[4 * s + 2], l2t1 = step_theta[4 * s + 3];
         // Adds the entry (work entry with up slot a = ma [, up slot b = mb]) with log-weight lp to the new
         // frontier; an equal entry already there absorbs it (first-insertion order, as a dict would).
         auto emit = [&](int a, const Mask<NW>& ma, int b, const Mask<NW>& mb, double lp) -> bool {
@@ -234,8 +236,8 @@ PNB_HD double msnc_dp(const Step* steps, int n_steps, const int32_t* down_slot, 
                     Mask<NW> top1 = sub, top2;
                     for (int i = 0; i < NW; ++i) top2.w[i] = at_v.w[i] ^ sub.w[i];
                     double lp1, lp2;
-                    branch_timed<NW>(top1, lp1, st.tau_low, st.tau_high[0], true, inv_theta, log_two_over_theta, ev_t, ev_n, j_lo, j_hi0);
-                    branch_timed<NW>(top2, lp2, st.tau_low, st.tau_high[1], true, inv_theta, log_two_over_theta, ev_t, ev_n, j_lo, j_hi1);
+                    branch_timed<NW>(top1, lp1, st.tau_low, st.tau_high[0], true, inv_theta0, l2t0, ev_t, ev_n, j_lo, j_hi0);
+                    branch_timed<NW>(top2, lp2, st.tau_low, st.tau_high[1], true, inv_theta1, l2t1, ev_t, ev_n, j_lo, j_hi1);
                     // lp + factor + lp1 + lp2, left to right (src/_msnc_density.py:353)
                     ok = emit(st.up_slot[0], top1, st.up_slot[1], top2, add_rn(add_rn(add_rn(lp, factor), lp1), lp2));
                     if (!ok || sub.zero()) break;
@@ -243,7 +245,7 @@ PNB_HD double msnc_dp(const Step* steps, int n_steps, const int32_t* down_slot, 
                 }
             } else {
                 double blp;
-                branch_timed<NW>(at_v, blp, st.tau_low, st.tau_high[0], !is_root, inv_theta, log_two_over_theta, ev_t, ev_n, j_lo, j_hi0);
+                branch_timed<NW>(at_v, blp, st.tau_low, st.tau_high[0], !is_root, inv_theta0, l2t0, ev_t, ev_n, j_lo, j_hi0);
                 if (is_root) root_slot = st.up_slot[0];
                 ok = emit(st.up_slot[0], at_v, -1, at_v, add_rn(lp, blp));
             }
@@ -287,6 +289,7 @@ struct NetProgram {
     std::vector<int32_t> down_slot;
     int W = 1;                      // slots per frontier entry
     int n_species = 0;
+    std::vector<int32_t> step_edge;           // [n_steps][2] up edge ids of each step (-1: none / root branch)
     std::vector<int32_t> retic_step;          // steps that are reticulations
     std::vector<std::vector<int32_t>> species_below;   // per reticulation step: species ids below it
 };
@@ -433,6 +436,8 @@ inline std::string compile_network(int n_nodes, int n_edges, const int32_t* edge
             st.up_slot[0] = slot_of_edge[e] = take();
         }
         for (int e : down[v]) free_slots.push_back(slot_of_edge[e]);
+        out.step_edge.push_back(up[v].empty() ? -1 : up[v][0]);
+        out.step_edge.push_back(up[v].size() == 2 ? up[v][1] : -1);
         out.steps.push_back(st);
     }
     out.W = std::max(1, n_slots);
@@ -528,6 +533,27 @@ inline const char* prepare_tree(int n, const int32_t* parent, const double* blen
     *n_ev_out = k;
     *root_bit_out = root;
     return nullptr;
+}
+
+// Per call: 1/theta and log(2/theta) of the branch(es) above every step's node.  edge_theta[e] / root_theta
+// override the default where they are not NaN (resolve_branch_theta, src/_units.py:90-125; the caller has
+// turned label keys into edge ids).  The logarithm is taken here, by the host's libm, as the reference does.
+inline void fill_step_theta(const NetProgram& prog, double theta, const double* edge_theta, double root_theta,
+                            double* out /* [n_steps][4] */) {
+    const size_t n = prog.steps.size();
+    for (size_t s = 0; s < n; ++s)
+        for (int k = 0; k < 2; ++k) {
+            const int e = prog.step_edge[2 * s + k];
+            double th = theta;
+            if (e >= 0) {
+                if (edge_theta && edge_theta[e] == edge_theta[e]) th = edge_theta[e];
+            } else if (k == 0 && (prog.steps[s].kind & KIND_ROOT)) {
+                if (root_theta == root_theta) th = root_theta;
+            }
+            const double inv = 1.0 / th;
+            out[4 * s + 2 * k] = inv;
+            out[4 * s + 2 * k + 1] = log(2.0 * inv);
+        }
 }
 
 // Upper bound on the frontier size of any job whose species s carries at most alleles[s] gene leaves:

@@ -123,6 +123,7 @@ def export_network(net):
         "is_retic": [bool(b) for b in idx.is_retic],
         "height": [float(h) for h in heights],
         "leaf_label": [idx.leaf_label.get(i) for i in range(idx.n_nodes)],
+        "node_label": [n.label for n in idx._node_objs],
     }
 
 
@@ -161,26 +162,29 @@ def timed_newick(flat, factor=1.0):
     return rec(root) + ";"
 
 
-def density(gt, net, species_of, theta):
-    v = gene_tree_msnc_log_density(gt, net, species_of, theta=theta)
+def density(gt, net, species_of, theta, branch_thetas=None):
+    v = gene_tree_msnc_log_density(gt, net, species_of, theta=theta, branch_thetas=branch_thetas)
     return None if (isinstance(v, float) and math.isinf(v)) else float(v)
 
 
-def make_case(name, nw, alleles, theta, rng, n_trees, scales=(0.5, 0.9, 1.3)):
+def make_case(name, nw, alleles, theta, rng, n_trees, scales=(0.5, 0.9, 1.3), branch_thetas=None):
     net = Network.from_newick(nw, branch_length_unit=UNIT)
     species_of = {a: sp for sp, al in alleles.items() for a in al}
     trees, expect = [], []
     for k in range(n_trees):
-        gt = simulate_gene_tree(net, alleles, theta, rng)
+        gt = simulate_gene_tree(net, alleles, theta, rng, branch_thetas=branch_thetas)
         flat = export_gene_tree(gt)
         trees.append(flat)
-        expect.append(density(gt, net, species_of, theta))
+        expect.append(density(gt, net, species_of, theta, branch_thetas))
         for sc in (scales if k % 3 == 0 else ()):
             gtn = Network.from_newick(timed_newick(flat, sc), branch_length_unit=UNIT)
             trees.append(export_gene_tree(gtn))
-            expect.append(density(gtn, net, species_of, theta))
-    return {"name": name, "newick": nw, "network": export_network(net), "species_of": species_of,
+            expect.append(density(gtn, net, species_of, theta, branch_thetas))
+    case = {"name": name, "newick": nw, "network": export_network(net), "species_of": species_of,
             "theta": theta, "trees": trees, "expected": expect}
+    if branch_thetas:   # JSON has no tuple keys: [[key, value], ...] with key a label or [parent, child]
+        case["branch_thetas"] = [[list(k) if isinstance(k, tuple) else k, v] for k, v in branch_thetas.items()]
+    return case
 
 
 def main():
@@ -216,6 +220,19 @@ def main():
         alleles = {"s%d" % i: (["s%d" % i] if per_sp == 1 else ["s%d_%d" % (i, k) for k in range(per_sp)])
                    for i in range(n_leaves)}
         cases.append(make_case("rand_n%d_r%d_a%d" % (n_leaves, n_retic, per_sp), nw, alleles, theta, rng, n_trees))
+    # fixed per-population thetas (resolve_branch_theta src/_units.py:90-125): edge keys, child keys, both root forms;
+    # with them the reference takes its pure-Python DP (src/_msnc_density.py:229-233)
+    cases.append(make_case("branch_thetas_ref_net", sp_g.replace("):0.01,(#H1", ")x:0.01,(#H1").replace("):0.005);", ")y:0.005)r;"),
+                           one, 0.02, rng, 6, branch_thetas={("x", "A"): 0.01, "A": 0.5, "#H1": 0.03, ("y", "#H1"): 0.05,
+                                                             "C": 0.04, ("__root__", "r"): 0.08}))
+    nodes, edges = random_network(7, 2, rng)
+    bt = {"i7": 0.05, ("i8", "i7"): 0.011, "s3": 0.004, "#H0": 0.07, "x1": 0.015, "__root__": 0.033, "s0": 0.02}
+    cases.append(make_case("branch_thetas_rand_n7_r2", enewick(nodes, edges), {"s%d" % i: ["s%d" % i] for i in range(7)},
+                           0.02, rng, 8, branch_thetas=bt))
+    nodes, edges = random_network(9, 0, rng)
+    root_label = nodes[-1][0]
+    cases.append(make_case("branch_thetas_rand_n9_tree", enewick(nodes, edges), {"s%d" % i: ["s%d_a" % i, "s%d_b" % i] for i in range(9)},
+                           0.03, rng, 6, branch_thetas={root_label: 0.2, "s1": 0.01, "s2": 0.02, "i9": 0.06, "i12": 0.002}))
     out = os.path.join(HERE, "msnc_cases.json")
     with open(out, "w") as f:
         json.dump({"source": "PhyNetPy v0.6.0 gene_tree_msnc_log_density; null = -inf", "cases": cases}, f)

@@ -12,7 +12,7 @@ extern "C" int msnc_host_eval(int n_nodes, int n_edges, const int32_t* edge_src,
                               const double* edge_gamma, const double* height, const int32_t* node_species,
                               int n_species, int64_t n_trees, const int64_t* tree_off, const int32_t* parent,
                               const double* blen, const int32_t* gene_species, double theta, int cap, int force_nw,
-                              int stride_in,
+                              int stride_in, const double* edge_theta, double root_theta,
                               double* out, int32_t* info /* W, n_steps, max status, NW used */, char* err, int err_cap) {
     NetProgram prog;
     std::string e = compile_network(n_nodes, n_edges, edge_src, edge_dst, edge_gamma, height, node_species, n_species, prog);
@@ -27,7 +27,8 @@ extern "C" int msnc_host_eval(int n_nodes, int n_edges, const int32_t* edge_src,
     info[1] = static_cast<int32_t>(prog.steps.size());
     info[2] = 0;
     info[3] = NW;
-    const double inv_theta = 1.0 / theta, l2t = log(2.0 * inv_theta);
+    std::vector<double> step_theta(4 * prog.steps.size());
+    fill_step_theta(prog, theta, edge_theta, root_theta, step_theta.data());
     TreeScratch sc;
     std::vector<double> ev_t(std::max(max_n, 1));
     std::vector<uint32_t> ev_n(std::max(max_n, 1));
@@ -52,11 +53,11 @@ extern "C" int msnc_host_eval(int n_nodes, int n_edges, const int32_t* edge_src,
         int status = 0;
         if (NW == 1)
             out[j] = msnc_dp<1>(prog.steps.data(), static_cast<int>(prog.steps.size()), prog.down_slot.data(), prog.W, cap,
-                                ev_t.data(), ev_n.data(), n_ev, sp_mask.data(), root_bit, inv_theta, l2t, fr_mask.data(),
+                                ev_t.data(), ev_n.data(), n_ev, sp_mask.data(), root_bit, step_theta.data(), fr_mask.data(),
                                 fr_lp.data(), stride, &status);
         else
             out[j] = msnc_dp<2>(prog.steps.data(), static_cast<int>(prog.steps.size()), prog.down_slot.data(), prog.W, cap,
-                                ev_t.data(), ev_n.data(), n_ev, sp_mask.data(), root_bit, inv_theta, l2t, fr_mask.data(),
+                                ev_t.data(), ev_n.data(), n_ev, sp_mask.data(), root_bit, step_theta.data(), fr_mask.data(),
                                 fr_lp.data(), stride, &status);
         info[2] = std::max(info[2], status);
     }

@@ -29,6 +29,11 @@ def _close(got, want, rel=REL):
     return abs(got - want) <= rel * max(1.0, abs(want))
 
 
+def _thetas(case):
+    bt = case.get("branch_thetas")
+    return None if not bt else {(tuple(k) if isinstance(k, list) else k): v for k, v in bt}
+
+
 def _trees(P, case):
     return [P.FlatTree(t["parent"], t["blen"], t["label"]) for t in case["trees"]]
 
@@ -37,7 +42,7 @@ def _trees(P, case):
 def test_golden_density(case):
     P = _pkg()
     net = P.SpeciesNetwork.from_dict(case["network"])
-    got = P.msnc_log_density_batch(_trees(P, case), net, case["species_of"], case["theta"])
+    got = P.msnc_log_density_batch(_trees(P, case), net, case["species_of"], case["theta"], branch_thetas=_thetas(case))
     assert got.shape == (len(case["trees"]),)
     for g, e in zip(got, case["expected"]):
         assert _close(float(g), e), (g, e)
@@ -76,8 +81,18 @@ def test_single_tree_entry_point_and_newick_network():
     assert d_g == pytest.approx(d_1 + math.log(0.3), abs=1e-9)      # tests/test_mcmc_seq.py:229-240
     with pytest.raises(ValueError, match="finite and positive"):
         P.gene_tree_msnc_log_density(gt, case["newick"], so, theta=0.0)
-    with pytest.raises(NotImplementedError):
-        P.gene_tree_msnc_log_density(gt, case["newick"], so, theta=0.02, branch_thetas={"A": 0.1})
+    # fixed per-population thetas: installed on the network handle, removed again by the next plain call
+    bt_case = by["branch_thetas_ref_net"]
+    net = P.SpeciesNetwork.from_newick(bt_case["newick"])
+    t0 = bt_case["trees"][0]
+    g0 = P.FlatTree(t0["parent"], t0["blen"], t0["label"])
+    with_bt = P.gene_tree_msnc_log_density(g0, net, so, theta=0.02, branch_thetas=_thetas(bt_case))
+    assert _close(with_bt, bt_case["expected"][0])
+    plain = P.gene_tree_msnc_log_density(g0, net, so, theta=0.02)
+    assert _close(plain, MO.msnc_log_density(bt_case["network"], t0["parent"], t0["blen"], t0["label"], so, 0.02))
+    assert abs(plain - with_bt) > 1e-6
+    with pytest.raises(ValueError, match="finite and positive"):
+        P.gene_tree_msnc_log_density(g0, net, so, theta=0.02, branch_thetas={"A": -1.0})
 
 
 def test_one_call_for_many_trees_equals_one_call_per_tree():
@@ -116,12 +131,13 @@ def test_random_inputs_against_the_oracle():
             continue
         net = P.SpeciesNetwork.from_dict(case["network"])
         theta = case["theta"] * float(rng.uniform(0.5, 3.0))
+        bt = _thetas(case)
         flats, want = [], []
         for t in case["trees"][:5]:
             bl = [None if b is None else b * float(rng.uniform(0.9, 1.5)) for b in t["blen"]]
             flats.append(P.FlatTree(t["parent"], bl, t["label"]))
-            want.append(MO.msnc_log_density(case["network"], t["parent"], bl, t["label"], case["species_of"], theta))
-        got = P.msnc_log_density_batch(flats, net, case["species_of"], theta)
+            want.append(MO.msnc_log_density(case["network"], t["parent"], bl, t["label"], case["species_of"], theta, bt))
+        got = P.msnc_log_density_batch(flats, net, case["species_of"], theta, branch_thetas=bt)
         for g, w in zip(got, want):
             assert _close(float(g), w), (case["name"], g, w)
             n_checked += 1

@@ -30,6 +30,12 @@ def _expected(e):
     return -math.inf if e is None else e
 
 
+def _thetas(case):
+    """branch_thetas of a golden case: JSON [[key, value], ...] -> {label | (parent, child): value}."""
+    bt = case.get("branch_thetas")
+    return None if not bt else {(tuple(k) if isinstance(k, list) else k): v for k, v in bt}
+
+
 def _close(got, want):
     if want == -math.inf:
         return got == -math.inf
@@ -40,7 +46,8 @@ def _close(got, want):
 @pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
 def test_oracle_matches_reference(case):
     for t, e in zip(case["trees"], case["expected"]):
-        got = MO.msnc_log_density(case["network"], t["parent"], t["blen"], t["label"], case["species_of"], case["theta"])
+        got = MO.msnc_log_density(case["network"], t["parent"], t["blen"], t["label"], case["species_of"], case["theta"],
+                                  _thetas(case))
         assert _close(got, _expected(e)), (got, e)
 
 
@@ -53,6 +60,13 @@ def test_golden_covers_the_interesting_regimes():
     assert any(sum(c["network"]["is_retic"]) >= 3 for c in CASES)
     assert any(max(len(t["parent"]) for t in c["trees"]) > 64 for c in CASES)      # two-word lineage sets
     assert any(len(set(c["species_of"].values())) < len(c["species_of"]) for c in CASES)  # several alleles per species
+    with_thetas = [c for c in CASES if c.get("branch_thetas")]
+    assert len(with_thetas) >= 3
+    for c in with_thetas:   # the overrides matter: without them the density differs
+        t = next(t for t, e in zip(c["trees"], c["expected"]) if e is not None)
+        e = next(e for e in c["expected"] if e is not None)
+        plain = MO.msnc_log_density(c["network"], t["parent"], t["blen"], t["label"], c["species_of"], c["theta"])
+        assert abs(plain - e) > 1e-6
 
 
 def test_reference_gamma_mixture_identity():
@@ -91,14 +105,16 @@ def _pack(case, net=None):
             np.concatenate(sp).astype(np.int32))
 
 
-def _run_harness(lib, net, off, par, bl, sp, theta, cap=4096, force_nw=0, stride=1):
+def _run_harness(lib, net, off, par, bl, sp, theta, cap=4096, force_nw=0, stride=1, branch_thetas=None):
     n = len(off) - 1
+    edge_theta, root_theta = net.branch_theta_arrays(branch_thetas)
     out = np.zeros(n)
     info = np.zeros(4, np.int32)
     err = C.create_string_buffer(256)
     rc = lib.msnc_host_eval(net.n_nodes, int(net.edge_src.shape[0]), _p(net.edge_src), _p(net.edge_dst), _p(net.edge_gamma),
                             _p(net.height), _p(net.node_species), len(net.species), C.c_int64(n), _p(off), _p(par), _p(bl),
-                            _p(sp), C.c_double(theta), cap, force_nw, stride, _p(out), _p(info), err, 256)
+                            _p(sp), C.c_double(theta), cap, force_nw, stride, _p(edge_theta) if edge_theta is not None else None,
+                            C.c_double(root_theta), _p(out), _p(info), err, 256)
     return rc, out, info, err.value.decode()
 
 
@@ -108,7 +124,7 @@ def test_kernel_source_on_host_matches_reference(harness, case, force_nw, stride
     # stride 32 = the interleaved layout the kernel uses when the frontier fits in shared memory
     net, off, par, bl, sp = _pack(case)
     rc, out, info, err = _run_harness(harness, net, off, par, bl, sp, case["theta"], force_nw=force_nw, stride=stride,
-                                      cap=256 if stride > 1 else 4096)
+                                      cap=256 if stride > 1 else 4096, branch_thetas=_thetas(case))
     assert rc == 0, err
     assert info[2] == 0   # no frontier overflow
     for got, e in zip(out, case["expected"]):
@@ -121,7 +137,7 @@ def test_tree_shaped_networks_are_bit_identical(harness):
         if any(case["network"]["is_retic"]):
             continue
         net, off, par, bl, sp = _pack(case)
-        rc, out, info, err = _run_harness(harness, net, off, par, bl, sp, case["theta"])
+        rc, out, info, err = _run_harness(harness, net, off, par, bl, sp, case["theta"], branch_thetas=_thetas(case))
         assert rc == 0, err
         # the visiting order differs from the reference's (depth-first, to keep entries narrow), which
         # permutes the per-branch terms of the sum: equal to a few ulps, not always to the bit
@@ -173,6 +189,7 @@ def test_harness_agrees_with_oracle_on_fresh_random_inputs(harness):
     for case in CASES:
         if case["name"].startswith("ref_gamma_mixture"):
             continue
+        bt = _thetas(case)
         netd = json.loads(json.dumps(case["network"]))
         species_of = dict(case["species_of"])
         drop = sorted(species_of)[0]
@@ -182,10 +199,10 @@ def test_harness_agrees_with_oracle_on_fresh_random_inputs(harness):
             bl = [None if b is None else b * float(rng.uniform(0.8, 1.6)) for b in t["blen"]]
             sub["trees"].append({"parent": t["parent"], "blen": bl, "label": t["label"]})
         net, off, par, bl, sp = _pack(sub)
-        rc, out, info, err = _run_harness(harness, net, off, par, bl, sp, sub["theta"])
+        rc, out, info, err = _run_harness(harness, net, off, par, bl, sp, sub["theta"], branch_thetas=bt)
         assert rc == 0, err
         for t, got in zip(sub["trees"], out):
-            want = MO.msnc_log_density(netd, t["parent"], t["blen"], t["label"], species_of, sub["theta"])
+            want = MO.msnc_log_density(netd, t["parent"], t["blen"], t["label"], species_of, sub["theta"], bt)
             assert _close(got, want), (case["name"], got, want)
 
 
@@ -225,7 +242,7 @@ def test_extended_newick_reader_rebuilds_the_reference_network(case):
     # same density for the same gene trees (node / edge numbering is free)
     for t, e in list(zip(case["trees"], case["expected"]))[:5]:
         d = mine.to_dict()
-        got = MO.msnc_log_density(d, t["parent"], t["blen"], t["label"], case["species_of"], case["theta"])
+        got = MO.msnc_log_density(d, t["parent"], t["blen"], t["label"], case["species_of"], case["theta"], _thetas(case))
         assert _close(got, _expected(e))
 
 
@@ -264,6 +281,28 @@ def test_from_network_duck_typing():
     ft = FlatTree([2, 2, 4, 4, -1], [0.012, 0.012, 0.013, 0.025, None], ["A", "B", None, "C", None])
     assert sn.species_ids_of(ft, {"A": "A", "B": "B", "C": "C"}).tolist() == [0, 1, -1, 2, -1]
     assert sn.species_ids_of(ft, {"A": "A", "C": "nowhere"}).tolist() == [0, -1, -1, -1, -1]
+
+
+def test_branch_theta_resolution_follows_the_reference():
+    # resolve_branch_theta, src/_units.py:90-125: edge key before child key; root: ("__root__", label), "__root__", label
+    sn = SpeciesNetwork.from_newick("((A:1,B:1)ab:1,C:2)r;")
+    lab = sn.node_label
+    e_of = {(lab[s], lab[d]): e for e, (s, d) in enumerate(zip(sn.edge_src.tolist(), sn.edge_dst.tolist()))}
+    et, rt = sn.branch_theta_arrays({("ab", "A"): 0.1, "A": 0.5, "B": 0.2, "r": 0.9})
+    assert et[e_of[("ab", "A")]] == 0.1 and et[e_of[("ab", "B")]] == 0.2
+    assert np.isnan(et[e_of[("r", "C")]]) and np.isnan(et[e_of[("r", "ab")]])
+    assert rt == 0.9
+    assert sn.branch_theta_arrays({"__root__": 0.3, "r": 0.9})[1] == 0.3
+    assert sn.branch_theta_arrays({("__root__", "r"): 0.4, "__root__": 0.3})[1] == 0.4
+    none = sn.branch_theta_arrays(None)
+    assert none[0] is None and np.isnan(none[1]) and sn.branch_theta_arrays({})[0] is None
+    from phynetpy_b200._msnc_density import validate_branch_thetas
+    with pytest.raises(ValueError, match="child labels or"):
+        validate_branch_thetas({1: 0.1})
+    with pytest.raises(ValueError, match="finite and positive"):
+        validate_branch_thetas({"A": 0.0})
+    with pytest.raises(ValueError, match="numeric"):
+        validate_branch_thetas({"A": "x"})
 
 
 def test_theta_validation_follows_the_reference():
