@@ -369,6 +369,8 @@ def main():
         chain = chain_steps(P, ctx, calcs, trees, model, n_steps=min(max(200, 20 * args.steps), 2000))
         chain["coupled_move_candidates"] = candidate_batch(P, ctx, calcs, trees, model, n_loci=min(200, len(calcs)))
         chain["msnc_density"] = msnc_leg(P, ctx, n_loci=len(calcs), n_species=spec["n"], cpu=not args.no_cpu_baseline)
+        chain["joint_likelihood_chain"] = joint_chain(P, ctx, model, n_loci=len(calcs), n_species=spec["n"], L=spec["L"],
+                                                      n_steps=1000)
 
     # ---- timed: end to end through the C ABI with host buffers ---------------------------
     for _ in range(2):
@@ -554,6 +556,82 @@ def chain_steps(P, ctx, calcs, trees, model, n_steps, seed=4):
         "median_c_abi_call_us": float(np.median(c_ms) * 1e3),
         "full_recompute_total": full,
         "per_locus_incremental_equals_full_recompute_bitwise": bool(incremental == list(eng._felsen)),
+    }
+
+
+def joint_chain(P, ctx, model, n_loci, n_species, L, n_steps, seed=45):
+    """MCMC_SEQ's whole likelihood, sum_i [log P(S_i|g_i) + log P(g_i|Psi)] (reference src/_mcmc_seq.py:745-761),
+    through the engine seam with BOTH factors on the device: single-locus node-height proposals (dirty-path
+    pruning + one MSNC density) and, every 10th step, a theta proposal (invalidate_network: the MSNC density of
+    every locus in one call).  Data: a 1-reticulation species network, gene trees from the network coalescent on
+    it, GTR alignments on those trees.  Ends with a full recomputation that must reproduce both cached factors."""
+    from phynetpy_b200 import simulate as S
+    rng = np.random.default_rng(seed)
+    theta = 0.02
+    net = S.random_species_network(n_species, 1, rng, height=0.005 * (n_species - 1))
+    trees, species_of = S.simulate_gene_trees_msnc(net, 1, theta, rng, n_loci)
+    par = np.stack([t.parent for t in trees])
+    bl = np.stack([t.blen for t in trees])
+    aln = S.simulate_alignments(par, bl, L, S.DEFAULT_PI, S.DEFAULT_RATES, rng)
+    loci = [S.to_alignment_dict(aln[i]) for i in range(n_loci)]
+    eng = P.SeqLikelihoodEngine(loci, species_of, model, context=ctx)
+    cur = list(trees)
+    total = eng.log_likelihood(cur, net, theta)
+    eng._commit_pending()
+    nodes = cur[0].n_nodes
+    n_tips = (nodes + 1) // 2
+    lat_locus, lat_theta, accepted, impossible = [], [], 0, 0
+    t0 = time.perf_counter()
+    for step in range(n_steps):
+        snap = eng.clone_caches()
+        if step % 10 == 9:
+            new_theta = theta * math.exp(float(rng.uniform(-0.2, 0.2)))
+            eng.invalidate_network()
+            prop = cur
+            s0 = time.perf_counter()
+            new_total = eng.log_likelihood(prop, net, new_theta)
+            lat_theta.append(time.perf_counter() - s0)
+        else:
+            new_theta = theta
+            i = int(rng.integers(0, n_loci))
+            ft = cur[i]
+            v = int(rng.integers(n_tips, nodes - 1))
+            kids = np.nonzero(ft.parent == v)[0]
+            delta = float(rng.uniform(-0.5 * float(ft.blen[kids].min()), 0.5 * float(ft.blen[v])))
+            b2 = ft.blen.copy()
+            b2[kids] += delta
+            b2[v] -= delta
+            prop = list(cur)
+            prop[i] = ft.with_lengths(b2)
+            eng.invalidate_locus(i)
+            s0 = time.perf_counter()
+            new_total = eng.log_likelihood(prop, net, theta)
+            lat_locus.append(time.perf_counter() - s0)
+        impossible += new_total == -math.inf
+        if math.log(rng.random()) < (new_total - total):
+            cur, total, theta = prop, new_total, new_theta
+            accepted += 1
+        else:
+            eng.restore_caches(snap)
+    wall = time.perf_counter() - t0
+    eng._commit_pending()
+    inc_f, inc_m = list(eng._felsen), list(eng._msnc)
+    for i in range(n_loci):
+        eng.invalidate_locus(i)
+    eng.invalidate_device_cache()
+    full = eng.log_likelihood(cur, net, theta)
+    eng._commit_pending()
+    return {
+        "what": "both factors of the MCMC_SEQ likelihood on the device through SeqLikelihoodEngine.log_likelihood("
+                "gene_trees, species_net, theta); Python host loop included",
+        "loci": n_loci, "species": n_species, "reticulations": 1, "sites": L,
+        "steps": n_steps, "logL_evaluations_per_s": n_steps / wall, "accept_rate": accepted / n_steps,
+        "proposals_without_embedding": int(impossible),
+        "median_latency_us_locus_move": float(np.median(lat_locus) * 1e6),
+        "median_latency_us_theta_move_all_loci_msnc": float(np.median(lat_theta) * 1e6),
+        "final_total": full,
+        "incremental_equals_full_recompute_bitwise": bool(inc_f == list(eng._felsen) and inc_m == list(eng._msnc)
+                                                          and full == total),
     }
 
 
