@@ -66,7 +66,9 @@ class SeqLikelihoodEngine:
         self._msnc: List[Optional[float]] = [None] * self.n_loci
         self._pending: List[int] = []   # loci with an uncommitted device evaluation
         self._dirty: set = set(range(lo, hi))  # local loci whose _felsen entry is None
-        self._snap_dirty: dict = {}            # id(snapshot list) -> dirty set at clone time
+        self._snap_dirty: dict = {}            # id(snapshot list) -> dirty sets at clone time
+        self._msnc_dirty: set = set()          # loci whose _msnc entry is None (when not all of them are)
+        self._msnc_all = True                  # every _msnc entry is None
         self._full_next = False
         self._mode = _lib.EVAL_RESCALE if rescale else 0  # numerical mode (beyond the reference when set)
         self.last_stats: dict = {}
@@ -75,6 +77,7 @@ class SeqLikelihoodEngine:
         self._net_obj: Any = None
         self._net: Optional[SpeciesNetwork] = None
         self._sp_ids: List[Optional[Tuple[Any, np.ndarray]]] = [None] * self.n_loci
+        self._store: Optional[dict] = None     # packed gene trees of all loci (see _packed_all)
 
     # -- reference seam (src/_mcmc_seq.py:696-703, :766-772) ------------------
     def invalidate_locus(self, i: int) -> None:
@@ -83,15 +86,18 @@ class SeqLikelihoodEngine:
         lo, hi = self._shard.local_range()
         if lo <= i < hi:
             self._dirty.add(i)
+        self._msnc_dirty.add(i)
 
     def invalidate_network(self) -> None:
         self._msnc = [None] * self.n_loci
+        self._msnc_all = True
+        self._msnc_dirty.clear()
 
     def clone_caches(self) -> Tuple[list, list]:
         snap = (list(self._felsen), list(self._msnc))
         if len(self._snap_dirty) > 8:
             self._snap_dirty.clear()
-        self._snap_dirty[id(snap[0])] = (snap[0], frozenset(self._dirty))
+        self._snap_dirty[id(snap[0])] = (snap[0], frozenset(self._dirty), frozenset(self._msnc_dirty), self._msnc_all)
         return snap
 
     def restore_caches(self, snapshot: Tuple[list, list]) -> None:
@@ -101,9 +107,11 @@ class SeqLikelihoodEngine:
         known = self._snap_dirty.get(id(snapshot[0]))
         if known is not None and known[0] is snapshot[0]:
             self._dirty = set(known[1])
+            self._msnc_dirty, self._msnc_all = set(known[2]), known[3]
         else:  # a snapshot we did not hand out: recount
             lo, hi = self._shard.local_range()
             self._dirty = {i for i in range(lo, hi) if self._felsen[i] is None}
+            self._recount_msnc()
         self._rollback_pending()
 
     def invalidate_device_cache(self) -> None:
@@ -155,6 +163,7 @@ class SeqLikelihoodEngine:
         lo, hi = self._shard.local_range()
         if rescan:  # entries were set to None behind our back (a caller sharing the list): recount
             self._dirty = {i for i in range(lo, hi) if self._felsen[i] is None}
+            self._recount_msnc()
         dirty = sorted(i for i in self._dirty if self._felsen[i] is None)
         self._dirty.clear()
         flags = _lib.EVAL_PENDING | self._mode | (_lib.EVAL_FULL if self._full_next else 0)
@@ -182,9 +191,9 @@ class SeqLikelihoodEngine:
                 total = sum(self._felsen)  # C loop, locus order
             elif self._msnc_fn is None:
                 self._fill_msnc(gene_trees, species_net, theta)
-                total = 0.0
-                for f, m in zip(self._felsen, self._msnc):  # reference order, src/_mcmc_seq.py:745-761
-                    total += f + m
+                # two C-level sums instead of the reference's Python loop over loci (src/_mcmc_seq.py:745-761):
+                # at 10^3 loci that loop costs more than the device work of a single-locus move
+                total = sum(self._felsen) + sum(self._msnc)
             else:
                 total = 0.0
                 for i in range(self.n_loci):  # reference loop, src/_mcmc_seq.py:745-761
@@ -207,6 +216,7 @@ class SeqLikelihoodEngine:
             self._net = as_species_network(species_net)
             self._net_obj = species_net
             self._sp_ids = [None] * self.n_loci
+            self._store = None
         return self._net
 
     def _species_ids(self, i: int, ft: FlatTree, net: SpeciesNetwork) -> np.ndarray:
@@ -220,24 +230,84 @@ class SeqLikelihoodEngine:
         self._sp_ids[i] = (ft.label, ids)
         return ids
 
+    def _recount_msnc(self) -> None:
+        none = [i for i, v in enumerate(self._msnc) if v is None]
+        self._msnc_all = len(none) == self.n_loci
+        self._msnc_dirty = set() if self._msnc_all else set(none)
+
     def _fill_msnc(self, gene_trees: Sequence[Any], species_net: Any, theta: float) -> None:
         """Every ``None`` entry of ``_msnc`` in one ``pnb_msnc_eval`` (all ranks evaluate all loci: the
-        work is tiny next to the pruning and it saves a second collective)."""
-        need = [i for i in range(self.n_loci) if self._msnc[i] is None]
-        if not need:
+        work is tiny next to the pruning and it saves a second collective).  Which entries are ``None`` is
+        tracked, not searched; after ``invalidate_network`` the trees of ALL loci go to the device from a
+        packed store that is updated in place for the loci whose tree object changed."""
+        if not self._msnc_all and not self._msnc_dirty:
             return
         theta = _check_theta(theta)
         net = self._network(species_net)
-        flats = [flatten(gene_trees[i]) for i in need]
+        if self._msnc_all:
+            need: Sequence[int] = range(self.n_loci)
+            off, parent, blen, ids = self._packed_all(gene_trees, net)
+        else:
+            need = sorted(i for i in self._msnc_dirty if self._msnc[i] is None)
+            if not need:
+                self._msnc_dirty.clear()
+                return
+            flats = [flatten(gene_trees[i]) for i in need]
+            if len(flats) == 1:
+                t = flats[0]
+                off = np.array([0, t.n_nodes], dtype=np.int64)
+                parent, blen, ids = t.parent, t.blen, self._species_ids(need[0], t, net)
+            else:
+                sizes = np.fromiter((t.n_nodes for t in flats), dtype=np.int64, count=len(flats))
+                off = np.zeros(len(flats) + 1, dtype=np.int64)
+                np.cumsum(sizes, out=off[1:])
+                parent = np.ascontiguousarray(np.concatenate([t.parent for t in flats]), dtype=np.int32)
+                blen = np.ascontiguousarray(np.concatenate([t.blen for t in flats]), dtype=np.float64)
+                ids = np.ascontiguousarray(np.concatenate([self._species_ids(i, t, net) for i, t in zip(need, flats)]),
+                                           dtype=np.int32)
+        vals = msnc_eval_packed(net, off, parent, blen, ids, theta, self._context(), self._branch_thetas)
+        if self._msnc_all:
+            self._msnc[:] = vals.tolist()   # in place: a caller may share this list
+        else:
+            for i, v in zip(need, vals.tolist()):
+                self._msnc[i] = v
+        self._msnc_all = False
+        self._msnc_dirty.clear()
+
+    def _packed_all(self, gene_trees: Sequence[Any], net: SpeciesNetwork):
+        """CSR arrays of the current gene trees of all loci, kept between calls: only the rows of loci whose
+        tree OBJECT changed are rewritten (the reference's identity convention, src/_mcmc_seq.py:682-694)."""
+        st = self._store
+        if st is not None and st["net"] is net and len(st["objs"]) == self.n_loci:
+            objs, off = st["objs"], st["off"]
+            ok = True
+            for i, g in enumerate(gene_trees):
+                if g is objs[i]:
+                    continue
+                t = flatten(g)
+                a, b = int(off[i]), int(off[i + 1])
+                if t.n_nodes != b - a:
+                    ok = False
+                    break
+                st["parent"][a:b] = t.parent
+                st["blen"][a:b] = t.blen
+                st["ids"][a:b] = self._species_ids(i, t, net)
+                objs[i] = g
+            if ok:
+                return off, st["parent"], st["blen"], st["ids"]
+        flats = [flatten(g) for g in gene_trees]
         sizes = np.fromiter((t.n_nodes for t in flats), dtype=np.int64, count=len(flats))
         off = np.zeros(len(flats) + 1, dtype=np.int64)
         np.cumsum(sizes, out=off[1:])
-        parent = np.ascontiguousarray(np.concatenate([t.parent for t in flats]), dtype=np.int32)
-        blen = np.ascontiguousarray(np.concatenate([t.blen for t in flats]), dtype=np.float64)
-        ids = np.ascontiguousarray(np.concatenate([self._species_ids(i, t, net) for i, t in zip(need, flats)]), dtype=np.int32)
-        vals = msnc_eval_packed(net, off, parent, blen, ids, theta, self._context(), self._branch_thetas)
-        for i, v in zip(need, vals):
-            self._msnc[i] = float(v)
+        self._store = {
+            "net": net, "objs": list(gene_trees), "off": off,
+            "parent": np.ascontiguousarray(np.concatenate([t.parent for t in flats]), dtype=np.int32),
+            "blen": np.ascontiguousarray(np.concatenate([t.blen for t in flats]), dtype=np.float64),
+            "ids": np.ascontiguousarray(np.concatenate([self._species_ids(i, t, net) for i, t in enumerate(flats)]),
+                                        dtype=np.int32),
+        }
+        st = self._store
+        return off, st["parent"], st["blen"], st["ids"]
 
     def msnc_candidate_sets(self, sets: Sequence[Tuple[int, Any]], species_net: Any, theta: float) -> List[np.ndarray]:
         """log P(g | Psi) of the candidate trees of MANY loci in one device call -- the MSNC half of

@@ -193,6 +193,20 @@ def test_engine_adds_the_coalescent_factor():
     assert t2 == pytest.approx(felsen_only + sum(w2), rel=1e-12)
     eng.restore_caches(snap)
     assert eng.log_likelihood(trees, net, case["theta"]) == total
+    # a tree change followed by a network change: the packed store rewrites that locus' rows in place
+    t3 = case["trees"][good[3]]
+    stretched = P.FlatTree(t3["parent"], [None if b is None else b * 1.25 for b in t3["blen"]], t3["label"])
+    new = list(trees)
+    new[3] = stretched
+    eng.invalidate_locus(3)
+    eng.invalidate_network()
+    eng.log_likelihood(new, net, case["theta"])
+    w3 = MO.msnc_log_density(case["network"], t3["parent"], stretched.blen.tolist(), t3["label"], case["species_of"], case["theta"])
+    assert _close(eng._msnc[3], w3)
+    for k in (0, 1, 2, 4, 5):
+        assert _close(eng._msnc[k], want_msnc[k])
+    eng.invalidate_locus(3)
+    assert eng.log_likelihood(trees, net, case["theta"]) == total
     # a gene tree that no longer embeds makes the state impossible
     bad_i = next(i for i, e in enumerate(case["expected"]) if e is None)
     bt = case["trees"][bad_i]
