@@ -700,11 +700,12 @@ def msnc_leg(P, ctx, n_loci, n_species, cpu=True, seed=44):
         n_cand_loci = min(200, n_loci)
         cand = pack([candidate_arrays(trees[k]) + (ids_of[k],) for k in range(n_cand_loci)])
         res = {"reticulations": n_retic, "program": net.info(ctx)}
-        for tag, arrs in (("all_loci", full), ("candidate_sets", cand)):
+        one = pack([(trees[0].parent[None, :], trees[0].blen[None, :], ids_of[0])])
+        for tag, arrs in (("one_locus", one), ("all_loci", full), ("candidate_sets", cand)):
             n_trees = arrs[0].shape[0] - 1
             for _ in range(3):
                 vals = msnc_eval_packed(net, *arrs, theta, ctx)
-            reps = 20
+            reps = 200 if tag == "one_locus" else 20
             t0 = time.perf_counter()
             for _ in range(reps):
                 vals = msnc_eval_packed(net, *arrs, theta, ctx)

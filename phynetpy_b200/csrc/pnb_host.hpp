@@ -209,6 +209,7 @@ struct pnb_ctx {
     int store_stash_levels = 0;    // storing evaluations: siblings waiting at stash index < this use shared memory
                                    // instead of an L2 round trip through their slot (PNB_STORE_STASH)
     bool allow_fused = true;       // small batches: single-kernel latency path (PNB_NO_FUSED=1 disables)
+    bool msnc_configured = false;  // K-m kernels have their dynamic shared-memory limit raised
     pnb::Arena arena;
     pnb::Buffer d_stage;           // device staging of the batch program (stream-ordered reuse)
     pnb::Buffer h_stage2[2];       // pinned host staging, double-buffered so the host can run ahead

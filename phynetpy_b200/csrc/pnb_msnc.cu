@@ -46,10 +46,27 @@ struct MsncLaunch {
     double* out;
     int32_t* status;
     int32_t frontier_in_smem;       // 1: the frontier of every thread lives in shared memory, interleaved
+    int32_t n_down;                 // entries of down_slot
+    int32_t program_words;          // 8-byte words of shared memory holding the staged program (frontiers follow)
 };
 
 template <int NW>
 __global__ void __launch_bounds__(128) pnb_msnc_kernel(MsncLaunch L) {
+    // Dynamic shared memory: [step program | step thetas | down slots] [frontiers, if they fit].
+    // Every thread walks the same program; staging it once per block turns ~3 dependent global loads per
+    // step (L2 / DRAM latency each when the batch is a single gene tree) into shared-memory broadcasts.
+    extern __shared__ uint64_t pnb_msnc_smem[];
+    Step* s_steps = reinterpret_cast<Step*>(pnb_msnc_smem);
+    double* s_theta = reinterpret_cast<double*>(s_steps + L.n_steps);
+    int32_t* s_down = reinterpret_cast<int32_t*>(s_theta + 4 * static_cast<size_t>(L.n_steps));
+    {
+        const uint64_t* src = reinterpret_cast<const uint64_t*>(L.steps);
+        const int words = L.n_steps * static_cast<int>(sizeof(Step) / 8);
+        for (int i = threadIdx.x; i < words; i += blockDim.x) pnb_msnc_smem[i] = src[i];
+        for (int i = threadIdx.x; i < 4 * L.n_steps; i += blockDim.x) s_theta[i] = L.step_theta[i];
+        for (int i = threadIdx.x; i < L.n_down; i += blockDim.x) s_down[i] = L.down_slot[i];
+    }
+    __syncthreads();
     const int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (j >= L.n_jobs) return;
     const int root_bit = L.root_bit[j];
@@ -64,13 +81,13 @@ __global__ void __launch_bounds__(128) pnb_msnc_kernel(MsncLaunch L) {
     // Frontier storage.  A thread re-reads what it has just written (copy entry, merge slots, compare
     // for duplicates): in global memory every such read is an L2 round trip, in shared memory ~30 cycles.
     // Shared layout: word k of thread t at [k * blockDim.x + t] -- consecutive threads, consecutive banks.
-    extern __shared__ uint64_t pnb_msnc_smem[];
     uint64_t* fr_mask;
     double* fr_lp;
     size_t stride;
     if (L.frontier_in_smem) {
-        fr_mask = pnb_msnc_smem + threadIdx.x;
-        fr_lp = reinterpret_cast<double*>(pnb_msnc_smem + mask_words * blockDim.x) + threadIdx.x;
+        uint64_t* fr = pnb_msnc_smem + L.program_words;
+        fr_mask = fr + threadIdx.x;
+        fr_lp = reinterpret_cast<double*>(fr + mask_words * blockDim.x) + threadIdx.x;
         stride = blockDim.x;
     } else {
         fr_mask = L.fr_mask + static_cast<size_t>(j) * mask_words;
@@ -78,9 +95,9 @@ __global__ void __launch_bounds__(128) pnb_msnc_kernel(MsncLaunch L) {
         stride = 1;
     }
     int status;
-    const double v = msnc_dp<NW>(L.steps, L.n_steps, L.down_slot, L.W, L.cap, L.ev_t + e0, L.ev_n + e0,
+    const double v = msnc_dp<NW>(s_steps, L.n_steps, s_down, L.W, L.cap, L.ev_t + e0, L.ev_n + e0,
                                  static_cast<int>(L.ev_off[j + 1] - e0),
-                                 L.species_mask + static_cast<size_t>(j) * L.n_species * NW, root_bit, L.step_theta,
+                                 L.species_mask + static_cast<size_t>(j) * L.n_species * NW, root_bit, s_theta,
                                  fr_mask, fr_lp, stride, &status);
     L.out[j] = v;
     L.status[j] = status;
@@ -322,21 +339,28 @@ extern "C" int pnb_msnc_eval(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_tr
     // shared memory when a block's worth of it fits (it does for every tree-shaped network and for
     // networks whose reticulations sit above few gene lineages), else to a global scratch buffer.
     int threads = n_trees >= int64_t(ctx->sm_count) * 256 ? 128 : (n_trees >= int64_t(ctx->sm_count) * 128 ? 64 : 32);
-    const size_t smem_limit = static_cast<size_t>(std::max(ctx->max_smem_optin - 2048, 0));
+    // the step program is staged in shared memory by every block (steps, thetas, down slots)
+    const size_t program_bytes = align_up(prog.steps.size() * (sizeof(Step) + 4 * sizeof(double)) +
+                                          prog.down_slot.size() * sizeof(int32_t), 16);
+    PNB_REQUIRE(program_bytes + 4096 < static_cast<size_t>(ctx->max_smem_optin), PNB_ERR_UNSUPPORTED,
+                "pnb_msnc_eval: the species network has too many nodes (%zu) for the staged step program", prog.steps.size());
+    const size_t smem_limit = static_cast<size_t>(std::max(ctx->max_smem_optin - 2048, 0)) - program_bytes;
     const char* no_smem = getenv("PNB_MSNC_NO_SMEM");   // test knob: force the global-scratch path
     const bool in_smem = per_job * 32 <= smem_limit && !(no_smem && no_smem[0] == '1');
     if (in_smem)
         while (per_job * threads > smem_limit) threads /= 2;
-    const size_t dyn_smem = in_smem ? per_job * threads : 0;
+    const size_t dyn_smem = program_bytes + (in_smem ? per_job * threads : 0);
     // jobs per launch: bounded scratch (the frontiers of a batch may not fit at once)
     const size_t scratch_budget = size_t{2} << 30;
     const int64_t jobs_per_launch =
         in_smem ? n_trees : std::max<int64_t>(1, std::min<int64_t>(n_trees, static_cast<int64_t>(scratch_budget / per_job)));
     const size_t off_lp = align_up(static_cast<size_t>(jobs_per_launch) * job_mask_words * sizeof(uint64_t), 256);
     if (!in_smem && (rc = ensure_device(ctx->d_P, off_lp + static_cast<size_t>(jobs_per_launch) * 2 * cap * sizeof(double)))) return rc;
-    if (in_smem) {
-        PNB_CUDA_TRY(cudaFuncSetAttribute(pnb_msnc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_limit)));
-        PNB_CUDA_TRY(cudaFuncSetAttribute(pnb_msnc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_limit)));
+    if (!ctx->msnc_configured) {   // once per context: opt in to large dynamic shared memory
+        const int lim = std::max(ctx->max_smem_optin - 2048, 0);
+        PNB_CUDA_TRY(cudaFuncSetAttribute(pnb_msnc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        PNB_CUDA_TRY(cudaFuncSetAttribute(pnb_msnc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        ctx->msnc_configured = true;
     }
     const size_t off_status = align_up(static_cast<size_t>(n_trees) * sizeof(double), 256);
     if ((rc = ensure_device(ctx->d_out, off_status + static_cast<size_t>(n_trees) * sizeof(int32_t)))) return rc;
@@ -356,6 +380,8 @@ extern "C" int pnb_msnc_eval(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_tr
     L.n_species = n_species;
     L.step_theta = reinterpret_cast<const double*>(ds + off_theta);
     L.frontier_in_smem = in_smem ? 1 : 0;
+    L.n_down = static_cast<int32_t>(prog.down_slot.size());
+    L.program_words = static_cast<int32_t>(program_bytes / 8);
     L.fr_mask = in_smem ? nullptr : static_cast<uint64_t*>(ctx->d_P.p);
     L.fr_lp = in_smem ? nullptr : reinterpret_cast<double*>(static_cast<char*>(ctx->d_P.p) + off_lp);
     int64_t launches = 0;
@@ -394,7 +420,7 @@ extern "C" int pnb_msnc_eval(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_tr
     ctx->stats[1] = ev_off[n_trees];
     ctx->stats[0] = n_trees;
     ctx->stats[2] = cap - 1;
-    ctx->stats[6] = in_smem ? static_cast<int64_t>(dyn_smem) : 0;   // bytes of shared memory per block holding frontiers
+    ctx->stats[6] = in_smem ? static_cast<int64_t>(dyn_smem - program_bytes) : 0;   // bytes of shared memory per block holding frontiers
     ctx->stats[7] = threads;
     ctx->t_call_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call0).count();
     return PNB_OK;

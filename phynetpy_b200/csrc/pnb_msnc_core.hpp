@@ -57,6 +57,8 @@ struct Step {
     double log_g[2];       // log inheritance probabilities of the two parent edges (reticulation)
 };
 
+static_assert(sizeof(Step) == 72 && sizeof(Step) % 8 == 0, "Step is copied to shared memory in 8-byte words");
+
 // Exactly-rounded product / sum: the device must not contract a*b+c into an FMA, so that a
 // tree-shaped network gives the reference's bits.
 #if defined(__CUDA_ARCH__)
