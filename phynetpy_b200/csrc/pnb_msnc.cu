@@ -48,6 +48,7 @@ struct MsncLaunch {
     int32_t frontier_in_smem;       // 1: the frontier of every thread lives in shared memory, interleaved
     int32_t n_down;                 // entries of down_slot
     int32_t program_words;          // 8-byte words of shared memory holding the staged program (frontiers follow)
+    int32_t tree_shaped;            // 1: no reticulation -> msnc_dp_tree
 };
 
 template <int NW>
@@ -93,6 +94,12 @@ __global__ void __launch_bounds__(128) pnb_msnc_kernel(MsncLaunch L) {
         fr_mask = L.fr_mask + static_cast<size_t>(j) * mask_words;
         fr_lp = L.fr_lp + static_cast<size_t>(j) * 2 * L.cap;
         stride = 1;
+    }
+    if (L.tree_shaped) {   // no reticulation: single-entry frontier, updated in place
+        L.out[j] = msnc_dp_tree<NW>(s_steps, L.n_steps, s_down, L.ev_t + e0, L.ev_n + e0, static_cast<int>(L.ev_off[j + 1] - e0),
+                                    L.species_mask + static_cast<size_t>(j) * L.n_species * NW, root_bit, s_theta, fr_mask, stride);
+        L.status[j] = JOB_OK;
+        return;
     }
     int status;
     const double v = msnc_dp<NW>(s_steps, L.n_steps, s_down, L.W, L.cap, L.ev_t + e0, L.ev_n + e0,
@@ -380,6 +387,7 @@ extern "C" int pnb_msnc_eval(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_tr
     L.n_species = n_species;
     L.step_theta = reinterpret_cast<const double*>(ds + off_theta);
     L.frontier_in_smem = in_smem ? 1 : 0;
+    L.tree_shaped = prog.retic_step.empty() ? 1 : 0;
     L.n_down = static_cast<int32_t>(prog.down_slot.size());
     L.program_words = static_cast<int32_t>(program_bytes / 8);
     L.fr_mask = in_smem ? nullptr : static_cast<uint64_t*>(ctx->d_P.p);

@@ -116,6 +116,10 @@ PNB_HD void branch_timed(Mask<NW>& cfg, double& lp_out, double tau_low, double t
                          const uint32_t* ev_n, int j_lo, int j_hi) {
     double cur = tau_low, lp = 0.0;
     int u = cfg.count();
+    if (u <= 1) {   // nothing can coalesce and the survival term needs two lineages: the factor is exactly 1
+        lp_out = 0.0;
+        return;
+    }
     for (int j = j_lo; j < j_hi; ++j) {
         const uint32_t e = ev_n[j];
         const int c0 = (e >> 8) & 0xff, c1 = (e >> 16) & 0xff;
@@ -153,6 +157,55 @@ PNB_HD double log_add(double a, double b) {   // _frontier_acc, src/_msnc_densit
 
 // status of one job
 constexpr int JOB_OK = 0, JOB_OVERFLOW = 1;
+
+// Tree-shaped network (no reticulation: the MSC case): the frontier is always ONE entry, so there is
+// nothing to copy, ping-pong or merge -- one vector of W lineage sets updated in place (slot k at
+// slots[k * NW * stride + i * stride]) and one running log-density, added in step order exactly as the
+// general DP would (lp + branch factor per step).  A closed slot is never read again before it is
+// reopened, so it is not cleared.
+template <int NW>
+PNB_HD double msnc_dp_tree(const Step* steps, int n_steps, const int32_t* down_slot,
+                           const double* ev_t, const uint32_t* ev_n, int n_ev,
+                           const uint64_t* species_mask, int root_bit, const double* step_theta,
+                           uint64_t* slots, size_t stride) {
+    double lp = 0.0;
+    Mask<NW> at_v;
+    at_v.clear();
+    for (int s = 0; s < n_steps; ++s) {
+        const Step st = steps[s];
+        at_v.clear();
+        if (st.kind & KIND_LEAF) {
+            if (st.species >= 0)
+                for (int i = 0; i < NW; ++i) at_v.w[i] = species_mask[static_cast<size_t>(st.species) * NW + i];
+        } else {
+            for (int d = 0; d < st.n_down; ++d) {
+                const size_t slot = static_cast<size_t>(down_slot[st.down_off + d]) * NW;
+                for (int i = 0; i < NW; ++i) at_v.w[i] |= slots[(slot + i) * stride];
+            }
+        }
+        const bool is_root = (st.kind & KIND_ROOT) != 0;
+        if (at_v.count() > 1) {
+            const int j_lo = first_event_at_or_after(ev_t, n_ev, st.tau_low);
+            const int j_hi = is_root ? n_ev : first_event_at_or_after(ev_t, n_ev, st.tau_high[0]);
+            double blp;
+            branch_timed<NW>(at_v, blp, st.tau_low, st.tau_high[0], !is_root, step_theta[4 * s], step_theta[4 * s + 1],
+                             ev_t, ev_n, j_lo, j_hi);
+            lp = add_rn(lp, blp);
+        }
+        if (!is_root) {
+            const size_t slot = static_cast<size_t>(st.up_slot[0]) * NW;
+            for (int i = 0; i < NW; ++i) slots[(slot + i) * stride] = at_v.w[i];
+        }
+    }
+    // the last step is the root (children before parents): its lineage set must be exactly the gene-tree root
+    bool hit = true;
+    for (int i = 0; i < NW; ++i) {
+        const uint64_t want = ((root_bit >> 6) == i) ? (uint64_t{1} << (root_bit & 63)) : 0;
+        hit = hit && (at_v.w[i] == want);
+    }
+    if (!hit) return -INFINITY;
+    return (lp <= LOG_FLOOR + 1.0) ? -INFINITY : lp;
+}
 
 // The DP of one gene tree.  Frontier storage, private to the job: fr_mask holds 2*cap + 1 entries of
 // W*NW words (two ping-pong frontiers and one work entry), fr_lp 2*cap doubles; element k of either

@@ -12,7 +12,7 @@ extern "C" int msnc_host_eval(int n_nodes, int n_edges, const int32_t* edge_src,
                               const double* edge_gamma, const double* height, const int32_t* node_species,
                               int n_species, int64_t n_trees, const int64_t* tree_off, const int32_t* parent,
                               const double* blen, const int32_t* gene_species, double theta, int cap, int force_nw,
-                              int stride_in, const double* edge_theta, double root_theta,
+                              int stride_in, const double* edge_theta, double root_theta, int tree_path,
                               double* out, int32_t* info /* W, n_steps, max status, NW used */, char* err, int err_cap) {
     NetProgram prog;
     std::string e = compile_network(n_nodes, n_edges, edge_src, edge_dst, edge_gamma, height, node_species, n_species, prog);
@@ -51,6 +51,14 @@ extern "C" int msnc_host_eval(int n_nodes, int n_edges, const int32_t* edge_src,
             return 1;
         }
         int status = 0;
+        if (tree_path && prog.retic_step.empty()) {   // the single-entry fast path the kernel takes for species trees
+            out[j] = NW == 1
+                ? msnc_dp_tree<1>(prog.steps.data(), static_cast<int>(prog.steps.size()), prog.down_slot.data(), ev_t.data(), ev_n.data(),
+                                  n_ev, sp_mask.data(), root_bit, step_theta.data(), fr_mask.data(), stride)
+                : msnc_dp_tree<2>(prog.steps.data(), static_cast<int>(prog.steps.size()), prog.down_slot.data(), ev_t.data(), ev_n.data(),
+                                  n_ev, sp_mask.data(), root_bit, step_theta.data(), fr_mask.data(), stride);
+            continue;
+        }
         if (NW == 1)
             out[j] = msnc_dp<1>(prog.steps.data(), static_cast<int>(prog.steps.size()), prog.down_slot.data(), prog.W, cap,
                                 ev_t.data(), ev_n.data(), n_ev, sp_mask.data(), root_bit, step_theta.data(), fr_mask.data(),

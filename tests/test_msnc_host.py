@@ -105,7 +105,7 @@ def _pack(case, net=None):
             np.concatenate(sp).astype(np.int32))
 
 
-def _run_harness(lib, net, off, par, bl, sp, theta, cap=4096, force_nw=0, stride=1, branch_thetas=None):
+def _run_harness(lib, net, off, par, bl, sp, theta, cap=4096, force_nw=0, stride=1, branch_thetas=None, tree_path=1):
     n = len(off) - 1
     edge_theta, root_theta = net.branch_theta_arrays(branch_thetas)
     out = np.zeros(n)
@@ -114,7 +114,7 @@ def _run_harness(lib, net, off, par, bl, sp, theta, cap=4096, force_nw=0, stride
     rc = lib.msnc_host_eval(net.n_nodes, int(net.edge_src.shape[0]), _p(net.edge_src), _p(net.edge_dst), _p(net.edge_gamma),
                             _p(net.height), _p(net.node_species), len(net.species), C.c_int64(n), _p(off), _p(par), _p(bl),
                             _p(sp), C.c_double(theta), cap, force_nw, stride, _p(edge_theta) if edge_theta is not None else None,
-                            C.c_double(root_theta), _p(out), _p(info), err, 256)
+                            C.c_double(root_theta), tree_path, _p(out), _p(info), err, 256)
     return rc, out, info, err.value.decode()
 
 
@@ -146,6 +146,24 @@ def test_tree_shaped_networks_are_bit_identical(harness):
                 assert got == -math.inf
             else:
                 assert abs(got - e) <= 4 * np.spacing(abs(e)) * len(case["network"]["height"])
+
+
+def test_tree_fast_path_equals_general_dp_bit_for_bit(harness):
+    # species trees take msnc_dp_tree (one entry, updated in place); the general frontier DP must agree exactly
+    n = 0
+    for case in CASES:
+        if any(case["network"]["is_retic"]):
+            continue
+        net, off, par, bl, sp = _pack(case)
+        for nw, stride in ((0, 1), (2, 1), (0, 32)):
+            a = _run_harness(harness, net, off, par, bl, sp, case["theta"], force_nw=nw, stride=stride, cap=64,
+                             branch_thetas=_thetas(case), tree_path=1)
+            b = _run_harness(harness, net, off, par, bl, sp, case["theta"], force_nw=nw, stride=stride, cap=64,
+                             branch_thetas=_thetas(case), tree_path=0)
+            assert a[0] == 0 and b[0] == 0
+            assert np.array_equal(a[1], b[1])
+            n += len(a[1])
+    assert n > 300
 
 
 def test_entry_width_stays_small(harness):
