@@ -207,24 +207,44 @@ PNB_HD double msnc_dp_tree(const Step* steps, int n_steps, const int32_t* down_s
     return (lp <= LOG_FLOOR + 1.0) ? -INFINITY : lp;
 }
 
-// The DP of one gene tree.  Frontier storage, private to the job: fr_mask holds 2*cap + 1 entries of
-// W*NW words (two ping-pong frontiers and one work entry), fr_lp 2*cap doubles; element k of either
-// array lives at [k * stride], so the same code runs on a contiguous global block (stride 1) and on
-// shared memory interleaved over the threads of a block (stride = blockDim.x: conflict-free).
-// Returns log P(g | Psi), -inf if the gene tree does not embed.
+// Words of frontier storage one job needs: two ping-pong frontiers of cap entries (W*NW words each) and
+// one 64-bit hash per entry; plus 2*cap doubles for the log-weights (msnc_lp_words).
+PNB_HD size_t msnc_mask_words(int W, int NW, int cap) { return 2 * static_cast<size_t>(cap) * (static_cast<size_t>(W) * NW + 1); }
+PNB_HD size_t msnc_lp_words(int cap) { return 2 * static_cast<size_t>(cap); }
+
+// Position-keyed word hash; 0 for an empty lineage set, so closed slots contribute nothing and the hash of
+// an entry can be updated incrementally (XOR) when slots are closed and opened.
+PNB_HD uint64_t slot_hash(uint32_t word_index, uint64_t w) {
+    uint64_t m = w * ((0x9E3779B97F4A7C15ull * (2ull * word_index + 1ull)) | 1ull);
+    return m ^ (m >> 29);
+}
+
+// The DP of one gene tree (general case: reticulations).  Frontier storage, private to the job: fr_mask
+// holds msnc_mask_words() words -- [2][cap] entries of W*NW words, then [2][cap] hashes -- and fr_lp
+// 2*cap doubles; element k of either array lives at [k * stride], so the same code runs on a contiguous
+// global block (stride 1) and on shared memory interleaved over the threads of a block (stride =
+// blockDim.x: conflict-free).  Returns log P(g | Psi), -inf if the gene tree does not embed.
+//
+// Per (step, entry) the work is: OR the closed slots, run the branch factor(s), write ONE new entry (copy
+// of the old one with the closed slots cleared and the opened slot(s) set) and look for an equal entry among
+// those already written -- by hash first, word by word only on a hash match.  Equal entries merge by
+// log-sum-exp in first-insertion order (the order of the reference's dict).
 template <int NW>
 PNB_HD double msnc_dp(const Step* steps, int n_steps, const int32_t* down_slot, int W, int cap,
                       const double* ev_t, const uint32_t* ev_n, int n_ev,
                       const uint64_t* species_mask /* [n_species][NW] */, int root_bit,
                       const double* step_theta /* [n_steps][4]: 1/theta and log(2/theta) of the up branch(es) */,
-                      uint64_t* fr_mask, double* fr_lp, size_t stride, int* status) {
-    const size_t entry = static_cast<size_t>(W) * NW;
-    size_t cur_m = 0, new_m = static_cast<size_t>(cap) * entry;      // word offsets of the two frontiers
-    const size_t base = 2 * static_cast<size_t>(cap) * entry;        // ... and of the work entry
-    size_t cur_lp = 0, new_lp = static_cast<size_t>(cap);
+                      uint64_t* fr_mask, double* fr_lp, size_t stride_in, int* status) {
+    const uint32_t stride = static_cast<uint32_t>(stride_in);
+    const uint32_t entry = static_cast<uint32_t>(W) * NW;
+    const uint32_t ucap = static_cast<uint32_t>(cap);
+    uint32_t cur_m = 0, new_m = ucap * entry;                    // word offsets of the two frontiers
+    uint32_t cur_h = 2 * ucap * entry, new_h = cur_h + ucap;     // ... and of their hashes
+    uint32_t cur_lp = 0, new_lp = ucap;
 #define PNB_M(off) fr_mask[(off) * stride]
 #define PNB_LP(off) fr_lp[(off) * stride]
-    for (size_t i = 0; i < entry; ++i) PNB_M(cur_m + i) = 0;
+    for (uint32_t i = 0; i < entry; ++i) PNB_M(cur_m + i) = 0;
+    PNB_M(cur_h) = 0;
     PNB_LP(cur_lp) = 0.0;
     int n_cur = 1;
     int root_slot = 0;
@@ -233,39 +253,49 @@ PNB_HD double msnc_dp(const Step* steps, int n_steps, const int32_t* down_slot, 
     for (int s = 0; s < n_steps; ++s) {
         const Step st = steps[s];
         int n_new = 0;
-        // the events inside this node's parent branch(es): a property of the step, shared by all entries
-        const int j_lo = first_event_at_or_after(ev_t, n_ev, st.tau_low);
         const bool is_root = (st.kind & KIND_ROOT) != 0;
-        const int j_hi0 = is_root ? n_ev : first_event_at_or_after(ev_t, n_ev, st.tau_high[0]);
-        const int j_hi1 = (st.kind & KIND_RETIC) ? first_event_at_or_after(ev_t, n_ev, st.tau_high[1]) : j_lo;
+        const bool is_retic = (st.kind & KIND_RETIC) != 0;
+        // the events inside this node's parent branch(es): a property of the step, shared by all entries;
+        // found on first use (a branch entered by fewer than two lineages never looks at events)
+        int j_lo = -1, j_hi0 = 0, j_hi1 = 0;
+        auto ranges = [&]() {
+            if (j_lo >= 0) return;
+            j_lo = first_event_at_or_after(ev_t, n_ev, st.tau_low);
+            j_hi0 = is_root ? n_ev : first_event_at_or_after(ev_t, n_ev, st.tau_high[0]);
+            j_hi1 = is_retic ? first_event_at_or_after(ev_t, n_ev, st.tau_high[1]) : j_lo;
+        };
         const double inv_theta0 = step_theta[4 * s], l2t0 = step_theta[4 * s + 1];
         const double inv_theta1 = step_theta[4 * s + 2], l2t1 = step_theta[4 * s + 3];
-        // Adds the entry (work entry with up slot a = ma [, up slot b = mb]) with log-weight lp to the new
-        // frontier; an equal entry already there absorbs it (first-insertion order, as a dict would).
-        auto emit = [&](int a, const Mask<NW>& ma, int b, const Mask<NW>& mb, double lp) -> bool {
+        // Writes (old entry at src, closed slots cleared, slot a = ma [, slot b = mb]) with hash h and
+        // log-weight lp into the new frontier, or merges it into the equal entry already there.
+        auto emit = [&](uint32_t src, uint64_t h, int a, const Mask<NW>& ma, int b, const Mask<NW>& mb, double lp) -> bool {
             if (n_new >= cap) return false;
-            const size_t mine = new_m + static_cast<size_t>(n_new) * entry;
-            for (size_t i = 0; i < entry; ++i) PNB_M(mine + i) = PNB_M(base + i);
-            for (int i = 0; i < NW; ++i) PNB_M(mine + static_cast<size_t>(a) * NW + i) = ma.w[i];
+            const uint32_t mine = new_m + static_cast<uint32_t>(n_new) * entry;
+            for (uint32_t i = 0; i < entry; ++i) PNB_M(mine + i) = PNB_M(src + i);
+            for (int d = 0; d < st.n_down; ++d)
+                for (int i = 0; i < NW; ++i) PNB_M(mine + static_cast<uint32_t>(down_slot[st.down_off + d]) * NW + i) = 0;
+            for (int i = 0; i < NW; ++i) PNB_M(mine + static_cast<uint32_t>(a) * NW + i) = ma.w[i];
             if (b >= 0)
-                for (int i = 0; i < NW; ++i) PNB_M(mine + static_cast<size_t>(b) * NW + i) = mb.w[i];
+                for (int i = 0; i < NW; ++i) PNB_M(mine + static_cast<uint32_t>(b) * NW + i) = mb.w[i];
             for (int j = 0; j < n_new; ++j) {
-                const size_t other = new_m + static_cast<size_t>(j) * entry;
+                if (PNB_M(new_h + j) != h) continue;
+                const uint32_t other = new_m + static_cast<uint32_t>(j) * entry;
                 bool same = true;
-                for (size_t i = 0; i < entry; ++i) same = same && (PNB_M(other + i) == PNB_M(mine + i));
+                for (uint32_t i = 0; i < entry; ++i) same = same && (PNB_M(other + i) == PNB_M(mine + i));
                 if (same) {
                     PNB_LP(new_lp + j) = log_add(PNB_LP(new_lp + j), lp);
                     return true;
                 }
             }
+            PNB_M(new_h + n_new) = h;
             PNB_LP(new_lp + n_new) = lp;
             ++n_new;
             return true;
         };
         for (int k = 0; k < n_cur; ++k) {
-            const size_t src = cur_m + static_cast<size_t>(k) * entry;
-            for (size_t i = 0; i < entry; ++i) PNB_M(base + i) = PNB_M(src + i);
+            const uint32_t src = cur_m + static_cast<uint32_t>(k) * entry;
             const double lp = PNB_LP(cur_lp + k);
+            uint64_t h = PNB_M(cur_h + k);
             Mask<NW> at_v;
             at_v.clear();
             if (st.kind & KIND_LEAF) {
@@ -273,16 +303,18 @@ PNB_HD double msnc_dp(const Step* steps, int n_steps, const int32_t* down_slot, 
                     for (int i = 0; i < NW; ++i) at_v.w[i] = species_mask[static_cast<size_t>(st.species) * NW + i];
             } else {
                 for (int d = 0; d < st.n_down; ++d) {
-                    const size_t slot = base + static_cast<size_t>(down_slot[st.down_off + d]) * NW;
+                    const uint32_t slot = static_cast<uint32_t>(down_slot[st.down_off + d]) * NW;
                     for (int i = 0; i < NW; ++i) {
-                        at_v.w[i] |= PNB_M(slot + i);
-                        PNB_M(slot + i) = 0;   // the edge is closed
+                        const uint64_t w = PNB_M(src + slot + i);
+                        at_v.w[i] |= w;
+                        h ^= slot_hash(slot + i, w);    // the edge is closed: its words leave the hash
                     }
                 }
             }
             bool ok = true;
-            if (st.kind & KIND_RETIC) {
+            if (is_retic) {
                 const int n_total = at_v.count();
+                const uint32_t sa = static_cast<uint32_t>(st.up_slot[0]) * NW, sb = static_cast<uint32_t>(st.up_slot[1]) * NW;
                 Mask<NW> sub = at_v;
                 while (true) {
                     const int ks = sub.count();
@@ -290,37 +322,47 @@ PNB_HD double msnc_dp(const Step* steps, int n_steps, const int32_t* down_slot, 
                                                  mul_rn(static_cast<double>(n_total - ks), st.log_g[1]));
                     Mask<NW> top1 = sub, top2;
                     for (int i = 0; i < NW; ++i) top2.w[i] = at_v.w[i] ^ sub.w[i];
-                    double lp1, lp2;
-                    branch_timed<NW>(top1, lp1, st.tau_low, st.tau_high[0], true, inv_theta0, l2t0, ev_t, ev_n, j_lo, j_hi0);
-                    branch_timed<NW>(top2, lp2, st.tau_low, st.tau_high[1], true, inv_theta1, l2t1, ev_t, ev_n, j_lo, j_hi1);
+                    double lp1 = 0.0, lp2 = 0.0;
+                    if (ks > 1) {
+                        ranges();
+                        branch_timed<NW>(top1, lp1, st.tau_low, st.tau_high[0], true, inv_theta0, l2t0, ev_t, ev_n, j_lo, j_hi0);
+                    }
+                    if (n_total - ks > 1) {
+                        ranges();
+                        branch_timed<NW>(top2, lp2, st.tau_low, st.tau_high[1], true, inv_theta1, l2t1, ev_t, ev_n, j_lo, j_hi1);
+                    }
+                    uint64_t hh = h;
+                    for (int i = 0; i < NW; ++i) hh ^= slot_hash(sa + i, top1.w[i]) ^ slot_hash(sb + i, top2.w[i]);
                     // lp + factor + lp1 + lp2, left to right (src/_msnc_density.py:353)
-                    ok = emit(st.up_slot[0], top1, st.up_slot[1], top2, add_rn(add_rn(add_rn(lp, factor), lp1), lp2));
+                    ok = emit(src, hh, st.up_slot[0], top1, st.up_slot[1], top2, add_rn(add_rn(add_rn(lp, factor), lp1), lp2));
                     if (!ok || sub.zero()) break;
                     sub.prev_subset(at_v);
                 }
             } else {
-                double blp;
-                branch_timed<NW>(at_v, blp, st.tau_low, st.tau_high[0], !is_root, inv_theta0, l2t0, ev_t, ev_n, j_lo, j_hi0);
+                double blp = 0.0;
+                if (at_v.count() > 1) {
+                    ranges();
+                    branch_timed<NW>(at_v, blp, st.tau_low, st.tau_high[0], !is_root, inv_theta0, l2t0, ev_t, ev_n, j_lo, j_hi0);
+                }
                 if (is_root) root_slot = st.up_slot[0];
-                ok = emit(st.up_slot[0], at_v, -1, at_v, add_rn(lp, blp));
+                const uint32_t sa = static_cast<uint32_t>(st.up_slot[0]) * NW;
+                for (int i = 0; i < NW; ++i) h ^= slot_hash(sa + i, at_v.w[i]);
+                ok = emit(src, h, st.up_slot[0], at_v, -1, at_v, add_rn(lp, blp));
             }
             if (!ok) {
                 *status = JOB_OVERFLOW;
                 return nan("");
             }
         }
-        const size_t tm = cur_m;
-        cur_m = new_m;
-        new_m = tm;
-        const size_t tl = cur_lp;
-        cur_lp = new_lp;
-        new_lp = tl;
+        uint32_t t = cur_m; cur_m = new_m; new_m = t;
+        t = cur_h; cur_h = new_h; new_h = t;
+        t = cur_lp; cur_lp = new_lp; new_lp = t;
         n_cur = n_new;
     }
 
     // the one entry whose root slot holds exactly the gene-tree root (src/_msnc_density.py:374-389)
     for (int k = 0; k < n_cur; ++k) {
-        const size_t e = cur_m + static_cast<size_t>(k) * entry + static_cast<size_t>(root_slot) * NW;
+        const uint32_t e = cur_m + static_cast<uint32_t>(k) * entry + static_cast<uint32_t>(root_slot) * NW;
         bool hit = true;
         for (int i = 0; i < NW; ++i) {
             const uint64_t want = ((root_bit >> 6) == i) ? (uint64_t{1} << (root_bit & 63)) : 0;

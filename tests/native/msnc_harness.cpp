@@ -35,8 +35,8 @@ extern "C" int msnc_host_eval(int n_nodes, int n_edges, const int32_t* edge_src,
     std::vector<uint64_t> sp_mask(static_cast<size_t>(std::max(n_species, 1)) * NW);
     // stride > 1 emulates the interleaved shared-memory layout of the kernel (element k at [k * stride])
     const size_t stride = stride_in > 0 ? static_cast<size_t>(stride_in) : 1;
-    std::vector<uint64_t> fr_mask((2 * static_cast<size_t>(cap) + 1) * prog.W * NW * stride);
-    std::vector<double> fr_lp(2 * static_cast<size_t>(cap) * stride);
+    std::vector<uint64_t> fr_mask(msnc_mask_words(prog.W, NW, cap) * stride);
+    std::vector<double> fr_lp(msnc_lp_words(cap) * stride);
     for (int64_t j = 0; j < n_trees; ++j) {
         const int n = static_cast<int>(tree_off[j + 1] - tree_off[j]);
         if (n == 0) {
