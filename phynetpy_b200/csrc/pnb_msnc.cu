@@ -77,7 +77,6 @@ __global__ void __launch_bounds__(128) pnb_msnc_kernel(MsncLaunch L) {
         return;
     }
     const int64_t e0 = L.ev_off[j];
-    const size_t entry = static_cast<size_t>(L.W) * NW;
     const size_t mask_words = msnc_mask_words(L.W, NW, L.cap);
     // Frontier storage.  A thread re-reads what it has just written (copy entry, merge slots, compare
     // for duplicates): in global memory every such read is an L2 round trip, in shared memory ~30 cycles.
@@ -339,7 +338,6 @@ extern "C" int pnb_msnc_eval(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_tr
     // ---- frontier capacity and scratch ---------------------------------------------------------
     const double bound = frontier_bound(prog, alleles_max.data());
     const int cap = static_cast<int>(std::min<double>(bound, static_cast<double>(net->max_frontier))) + 1;
-    const size_t entry = static_cast<size_t>(prog.W) * NW;
     const size_t job_mask_words = msnc_mask_words(prog.W, NW, cap);
     const size_t per_job = job_mask_words * sizeof(uint64_t) + 2 * static_cast<size_t>(cap) * sizeof(double);
     // Block size: small batches use small blocks so that they spread over the SMs; the frontier goes to

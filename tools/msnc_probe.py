@@ -29,6 +29,10 @@ off = np.zeros(sizes.shape[0] + 1, dtype=np.int64)
 np.cumsum(sizes, out=off[1:])
 args = (off, np.ascontiguousarray(np.concatenate(par), dtype=np.int32), np.ascontiguousarray(np.concatenate(bl)),
         np.ascontiguousarray(np.concatenate(ids), dtype=np.int32))
+if os.environ.get("PROBE_MODE") == "one":      # a single gene tree: the latency of one thread's DP
+    t = trees[0]
+    args = (np.array([0, t.n_nodes], dtype=np.int64), t.parent, t.blen, net.species_ids_of(t, species_of))
+    off = args[0]
 ctx = P.default_context()
 for _ in range(5):
     t0 = time.perf_counter()
