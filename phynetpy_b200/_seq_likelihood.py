@@ -331,6 +331,13 @@ class FelsensteinCalculator:
         self._first_col = first
 
     @classmethod
+    def from_file(cls, path, format: Optional[str] = None, **kwargs) -> "FelsensteinCalculator":
+        """Build from a FASTA / NEXUS / PHYLIP file (``ingest.read_alignment``; the extension decides,
+        NEXUS by default as in the reference's ``_read_alignment``, ``src/data/_sequence.py:258-300``)."""
+        from .ingest import read_alignment
+        return cls(read_alignment(path, format), **kwargs)
+
+    @classmethod
     def from_matrix(cls, taxa: Sequence[str], mat: np.ndarray, *, context: Optional[DeviceContext] = None,
                     device_compress: Optional[bool] = None) -> "FelsensteinCalculator":
         """Build from an (n_taxa, L) uint8 matrix of upper-case ASCII characters (no

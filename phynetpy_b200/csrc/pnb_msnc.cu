@@ -356,7 +356,11 @@ extern "C" int pnb_msnc_eval(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_tr
         while (per_job * threads > smem_limit) threads /= 2;
     const size_t dyn_smem = program_bytes + (in_smem ? per_job * threads : 0);
     // jobs per launch: bounded scratch (the frontiers of a batch may not fit at once)
-    const size_t scratch_budget = size_t{2} << 30;
+    size_t scratch_budget = size_t{2} << 30;
+    if (const char* mb = getenv("PNB_MSNC_SCRATCH_MB")) {   // test knob: small budgets exercise the multi-launch path
+        const long v = atol(mb);
+        if (v > 0) scratch_budget = static_cast<size_t>(v) << 20;
+    }
     const int64_t jobs_per_launch =
         in_smem ? n_trees : std::max<int64_t>(1, std::min<int64_t>(n_trees, static_cast<int64_t>(scratch_budget / per_job)));
     const size_t off_lp = align_up(static_cast<size_t>(jobs_per_launch) * job_mask_words * sizeof(uint64_t), 256);

@@ -69,6 +69,26 @@ def test_both_frontier_placements_agree(monkeypatch):
     monkeypatch.delenv("PNB_MSNC_NO_SMEM", raising=False)
 
 
+def test_global_scratch_is_used_in_several_launches_when_it_is_small(monkeypatch):
+    """Frontiers that do not fit in shared memory go to a bounded global scratch buffer; a batch larger than the
+    buffer is evaluated in several launches (PNB_MSNC_SCRATCH_MB shrinks the 2 GB default for this test)."""
+    P = _pkg()
+    ctx = P.default_context()
+    case = next(c for c in CASES if c["name"] == "rand_n5_r2_a2")
+    net = P.SpeciesNetwork.from_dict(case["network"])
+    trees = _trees(P, case) * 60
+    monkeypatch.delenv("PNB_MSNC_NO_SMEM", raising=False)
+    monkeypatch.delenv("PNB_MSNC_SCRATCH_MB", raising=False)
+    ref = P.msnc_log_density_batch(trees, net, case["species_of"], case["theta"])
+    monkeypatch.setenv("PNB_MSNC_NO_SMEM", "1")
+    monkeypatch.setenv("PNB_MSNC_SCRATCH_MB", "1")
+    got = P.msnc_log_density_batch(trees, net, case["species_of"], case["theta"])
+    assert ctx.last_stats()["launches"] > 1
+    assert np.array_equal(ref, got)
+    for g, e in zip(got[:len(case["expected"])], case["expected"]):
+        assert _close(float(g), e)
+
+
 def test_single_tree_entry_point_and_newick_network():
     P = _pkg()
     by = {c["name"]: c for c in CASES}
