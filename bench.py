@@ -578,14 +578,17 @@ def joint_chain(P, ctx, model, n_loci, n_species, L, n_steps, seed=45):
     cur = list(trees)
     total = eng.log_likelihood(cur, net, theta)
     eng._commit_pending()
-    nodes = cur[0].n_nodes
-    n_tips = (nodes + 1) // 2
-    lat_locus, lat_theta, accepted, impossible = [], [], 0, 0
+    from phynetpy_b200 import moves as MV
+    from phynetpy_b200.candidates import node_heights
+    heights = [node_heights(t) for t in cur]
+    lat_locus, lat_theta, accepted, impossible, void = [], [], 0, 0, 0
     t0 = time.perf_counter()
     for step in range(n_steps):
         snap = eng.clone_caches()
+        prop_h, loghr = None, 0.0
         if step % 10 == 9:
             new_theta = theta * math.exp(float(rng.uniform(-0.2, 0.2)))
+            loghr = math.log(new_theta / theta)            # scaler move (op_change_theta, src/_mcmc_seq.py:888-915)
             eng.invalidate_network()
             prop = cur
             s0 = time.perf_counter()
@@ -594,22 +597,29 @@ def joint_chain(P, ctx, model, n_loci, n_species, L, n_steps, seed=45):
         else:
             new_theta = theta
             i = int(rng.integers(0, n_loci))
-            ft = cur[i]
-            v = int(rng.integers(n_tips, nodes - 1))
-            kids = np.nonzero(ft.parent == v)[0]
-            delta = float(rng.uniform(-0.5 * float(ft.blen[kids].min()), 0.5 * float(ft.blen[v])))
-            b2 = ft.blen.copy()
-            b2[kids] += delta
-            b2[v] -= delta
+            # the reference's gene-tree operators on flat arrays (phynetpy_b200/moves.py): node-height slide
+            # (op_gene_node_height) or height-preserving NNI (op_gene_tree_nni)
+            if step % 3 == 2:
+                out = MV.nni_move(cur[i], heights[i], rng)
+                move = None if out is None else (out[0], out[1], 0.0)
+            else:
+                move = MV.slide_height_move(cur[i], heights[i], rng)
+            if move is None:
+                void += 1
+                continue
             prop = list(cur)
-            prop[i] = ft.with_lengths(b2)
+            prop[i] = move[0]
+            prop_h = (i, move[1])
+            loghr = move[2]
             eng.invalidate_locus(i)
             s0 = time.perf_counter()
             new_total = eng.log_likelihood(prop, net, theta)
             lat_locus.append(time.perf_counter() - s0)
         impossible += new_total == -math.inf
-        if math.log(rng.random()) < (new_total - total):
+        if math.log(rng.random()) < (new_total - total) + loghr:
             cur, total, theta = prop, new_total, new_theta
+            if prop_h is not None:
+                heights[prop_h[0]] = prop_h[1]
             accepted += 1
         else:
             eng.restore_caches(snap)
@@ -626,7 +636,8 @@ def joint_chain(P, ctx, model, n_loci, n_species, L, n_steps, seed=45):
                 "gene_trees, species_net, theta); Python host loop included",
         "loci": n_loci, "species": n_species, "reticulations": 1, "sites": L,
         "steps": n_steps, "logL_evaluations_per_s": n_steps / wall, "accept_rate": accepted / n_steps,
-        "proposals_without_embedding": int(impossible),
+        "proposals_without_embedding": int(impossible), "void_proposals": int(void),
+        "moves": "node-height slide / height-preserving NNI of one locus (moves.py), theta scaling every 10th step",
         "median_latency_us_locus_move": float(np.median(lat_locus) * 1e6),
         "median_latency_us_theta_move_all_loci_msnc": float(np.median(lat_theta) * 1e6),
         "final_total": full,

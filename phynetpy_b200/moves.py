@@ -1,0 +1,145 @@
+"""Gene-tree proposals on flat arrays ("flat-array gene-tree mirror updated by
+the moves").
+
+The reference's gene-tree operators clone the ``Network`` of the chosen locus, recompute every node
+height, mutate the clone and re-derive every edge length (``op_gene_node_height`` /
+``op_gene_tree_nni``, ``src/_mcmc_seq.py:1020-1113``; ``_clone_net`` alone is ~0.6 ms, about 30% of the
+chain's time).  Here a gene tree is a :class:`~phynetpy_b200.tree.FlatTree` plus its
+node-height vector, and a proposal is a handful of NumPy operations that produce the next
+``(FlatTree, heights)`` pair -- the old pair stays untouched, which is the copy-and-swap convention the
+likelihood engine relies on ("a fresh object means a genuine change", ``src/_mcmc_seq.py:682-694``).
+
+Same proposal distributions as the reference:
+
+* :func:`slide_height_move` (``_slide_height_move``, ``:956-990``): candidates are the non-root internal
+  nodes plus the root; a non-root node slides uniformly inside (max child height, parent height), log
+  Hastings ratio 0; the root is scaled by ``f = exp(w (u - 1/2))``, log Hastings ratio ``log f``;
+* :func:`nni_move` (``op_gene_tree_nni``, ``:1053-1113``): for every non-root internal node ``v`` one of its
+  children ``c`` is drawn, then one ``(p, v, s, c)`` uniformly; ``c`` and ``v``'s sibling ``s`` trade places
+  when ``h[v] > h[s]``; heights are kept, so the move is symmetric;
+* edge lengths always follow ``max(h[parent] - h[child], 0)`` (``_sync_lengths``, ``:418-434``).
+
+Random numbers are drawn in the reference's order (node choice, then the uniform), from the caller's
+``numpy.random.Generator``.  Which NODE a given integer selects differs: the reference enumerates
+``net.V()``, a hash-ordered set whose order changes from clone to clone, here nodes are enumerated by
+index -- the distributions are identical, the streams are not comparable.  The deterministic halves
+(:func:`slide_node`, :func:`nni_swap`) are what the golden vectors pin.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from .tree import FlatTree
+
+
+def lengths_from_heights(parent: np.ndarray, h: np.ndarray) -> np.ndarray:
+    """``_sync_lengths``: every edge gets ``max(h[parent] - h[child], 0)``; the root's entry is NaN."""
+    out = np.full(parent.shape[0], np.nan, dtype=np.float64)
+    nz = parent >= 0
+    out[nz] = np.maximum(h[parent[nz]] - h[nz], 0.0)
+    return out
+
+
+def _rebuilt(ft: FlatTree, parent: np.ndarray, h: np.ndarray, same_topology: bool) -> FlatTree:
+    t = FlatTree.__new__(FlatTree)
+    t.parent = parent
+    t.blen = lengths_from_heights(parent, h)
+    t.label = ft.label
+    t._n_children = ft._n_children if same_topology else None
+    t._tip_rows = ft._tip_rows          # leaves stay leaves under both moves
+    return t
+
+
+def slide_candidates(ft: FlatTree) -> np.ndarray:
+    """Non-root internal nodes in index order, then the root (``_internal_nodes(net) + [root]``)."""
+    nk = ft.n_children()
+    internal = np.nonzero((nk > 0) & (ft.parent >= 0))[0]
+    root = np.nonzero(ft.parent < 0)[0][:1]
+    return np.concatenate([internal, root]).astype(np.int64)
+
+
+def slide_node(ft: FlatTree, h: np.ndarray, node: int, u: float,
+               root_scale_window: float = 0.3) -> Optional[Tuple[np.ndarray, float]]:
+    """The deterministic half of the slide: new height vector and log Hastings ratio for ``node`` given
+    the uniform ``u``; ``None`` when the move is impossible (``:971-990``)."""
+    kids = np.nonzero(ft.parent == node)[0]
+    lower = float(h[kids].max()) if kids.shape[0] else 0.0
+    p = int(ft.parent[node])
+    h2 = h.copy()
+    if p < 0:
+        f = math.exp(root_scale_window * (u - 0.5))
+        new_h = float(h[node]) * f
+        if new_h <= lower:
+            return None
+        h2[node] = new_h
+        return h2, math.log(f)
+    upper = float(h[p])
+    if upper <= lower:
+        return None
+    h2[node] = lower + (upper - lower) * u
+    return h2, 0.0
+
+
+def slide_height_move(ft: FlatTree, h: np.ndarray, rng: np.random.Generator,
+                      root_scale_window: float = 0.3) -> Optional[Tuple[FlatTree, np.ndarray, float]]:
+    """``op_gene_node_height`` without the graph: returns the proposed ``(tree, heights, log HR)``."""
+    cands = slide_candidates(ft)
+    if cands.shape[0] == 0:
+        return None
+    node = int(cands[int(rng.integers(cands.shape[0]))])
+    out = slide_node(ft, h, node, float(rng.random()), root_scale_window)
+    if out is None:
+        return None
+    h2, loghr = out
+    return _rebuilt(ft, ft.parent, h2, True), h2, loghr
+
+
+def nni_eligible(ft: FlatTree) -> List[Tuple[int, int, int]]:
+    """``(p, v, s)`` for every non-root node ``v`` with at least two children whose parent ``p`` has
+    another child; ``s`` is the first such sibling (``:1071-1088``)."""
+    nk = ft.n_children()
+    out = []
+    for v in np.nonzero((nk >= 2) & (ft.parent >= 0))[0].tolist():
+        p = int(ft.parent[v])
+        sibs = np.nonzero(ft.parent == p)[0]
+        sibs = sibs[sibs != v]
+        if sibs.shape[0]:
+            out.append((p, v, int(sibs[0])))
+    return out
+
+
+def nni_swap(ft: FlatTree, h: np.ndarray, v: int, c: int) -> Optional[FlatTree]:
+    """The deterministic half of the NNI: child ``c`` of ``v`` and the sibling ``s`` of ``v`` trade places
+    (``s`` goes under ``v``, ``c`` under ``v``'s parent); ``None`` unless ``h[v] > h[s]`` (``:1094-1104``)."""
+    p = int(ft.parent[v])
+    if p < 0 or int(ft.parent[c]) != v:
+        raise ValueError("nni_swap: v must be a non-root node and c one of its children")
+    sibs = np.nonzero(ft.parent == p)[0]
+    sibs = sibs[sibs != v]
+    if sibs.shape[0] == 0:
+        raise ValueError("nni_swap: v has no sibling")
+    s = int(sibs[0])
+    if h[v] <= h[s]:
+        return None
+    parent = ft.parent.copy()
+    parent[s], parent[c] = v, p
+    return _rebuilt(ft, parent, h, False)
+
+
+def nni_move(ft: FlatTree, h: np.ndarray, rng: np.random.Generator) -> Optional[Tuple[FlatTree, np.ndarray]]:
+    """``op_gene_tree_nni`` without the graph: one child is drawn for EVERY eligible node (as the reference
+    does while it builds its list), then one eligible tuple; returns the proposed ``(tree, heights)``."""
+    picks = []
+    for p, v, s in nni_eligible(ft):
+        kids = np.nonzero(ft.parent == v)[0]
+        picks.append((v, int(kids[int(rng.integers(kids.shape[0]))])))
+    if not picks:
+        return None
+    v, c = picks[int(rng.integers(len(picks)))]
+    t = nni_swap(ft, h, v, c)
+    if t is None:
+        return None
+    return t, h
