@@ -95,8 +95,12 @@ def signature(ft: FlatTree, heights: np.ndarray = None) -> FrozenSet:
 
 def nni_neighbors(ft: FlatTree) -> List[Tuple[FlatTree, np.ndarray]]:
     """Height-preserving single-NNI rearrangements (reference ``_gene_tree_nni_neighbors``)."""
+    return nni_neighbors_at(ft, node_heights(ft))
+
+
+def nni_neighbors_at(ft: FlatTree, h: np.ndarray) -> List[Tuple[FlatTree, np.ndarray]]:
+    """:func:`nni_neighbors` for a caller that already holds the node heights."""
     kids = _children(ft.parent)
-    h = node_heights(ft)
     out, seen = [], set()
     for v in range(ft.n_nodes):
         if len(kids[v]) < 2 or ft.parent[v] < 0:
@@ -149,6 +153,36 @@ def candidate_arrays(ft: FlatTree, scales: Sequence[float] = HEIGHT_SCALE_GRID) 
             parents.append(base.parent)
             lengths.append(ft.blen if (k == 0 and s == 1.0) else _lengths_from_heights(base.parent, hs))
     return np.ascontiguousarray(np.stack(parents), dtype=np.int32), np.ascontiguousarray(np.stack(lengths), dtype=np.float64)
+
+
+def candidate_table(ft: FlatTree, heights: np.ndarray = None,
+                    scales: Sequence[float] = HEIGHT_SCALE_GRID) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """:func:`candidate_arrays` plus the node heights of every member: ``(parent[K, n], blen[K, n], height[K, n])``
+    -- what a caller needs to materialise the member it picks (``rebuild(k)`` of the reference,
+    ``src/_mcmc_seq.py:1975-1986``).  ``heights`` are the tree's own node heights when the caller tracks them
+    (the reference's ``gt_heights``); member (tree, scale 1) keeps the tree's lengths untouched (``:1828-1832``)."""
+    h0 = node_heights(ft) if heights is None else np.ascontiguousarray(heights, dtype=np.float64)
+    bases = [(ft, h0)] + nni_neighbors_at(ft, h0)
+    base_sigs = set()
+    parents, lengths, hts = [], [], []
+    internal = ft.n_children() > 0
+    for k, (base, h) in enumerate(bases):
+        bsig = signature(base, h)
+        if k > 0 and bsig in base_sigs:
+            continue
+        base_sigs.add(bsig)
+        seen_h = set()
+        for s in scales:
+            hs = h * s if s != 1.0 else h
+            key = tuple(np.round(hs[internal], 12).tolist())
+            if key in seen_h:
+                continue
+            seen_h.add(key)
+            parents.append(base.parent)
+            lengths.append(ft.blen if (k == 0 and s == 1.0) else _lengths_from_heights(base.parent, hs))
+            hts.append(hs)
+    return (np.ascontiguousarray(np.stack(parents), dtype=np.int32), np.ascontiguousarray(np.stack(lengths), dtype=np.float64),
+            np.ascontiguousarray(np.stack(hts), dtype=np.float64))
 
 
 def candidate_set(ft: FlatTree, scales: Sequence[float] = HEIGHT_SCALE_GRID) -> List[FlatTree]:

@@ -1,0 +1,123 @@
+"""Guided joint re-proposal of every locus' gene tree -- the inner machinery of the reference's coupled
+add / delete / relocate-reticulation moves (``_coupled_gene_tree_reproposal``, ``src/_mcmc_seq.py:1995-2070``;
+``_enumerate_scored_candidates`` ``:1900-1992``) -- with ALL the scoring on the device.
+
+The reference walks the loci one by one; for each it scores ``({g} + NNI(g)) x (0.25, 0.5, 1, 2, 4)`` with a
+Felsenstein pruning and an MSNC density per member under the proposed network, samples one member, then
+scores the candidate set around the chosen tree under the current network to obtain the reverse density:
+``2 * M * K`` prunings and densities on the host per move.  Here one move is FOUR device calls:
+
+1. forward Felsenstein scores of all loci x all members (``score_candidate_sets``, ``PNB_EVAL_NOSTORE``),
+2. forward MSNC densities of the same trees under the target network (``msnc_candidate_sets``),
+3. / 4. the same two calls for the candidate sets around the chosen trees, under the reverse network.
+
+Sampling follows the reference exactly -- per locus, in locus order, one ``rng.choice(K, p=probs)`` with
+``probs = exp(logw - logsumexp(logw))`` renormalised -- and consumes the generator identically, so with the same
+seed the same members are chosen whenever the weights agree to rounding.
+"""
+from __future__ import annotations
+
+import math
+from typing import Any, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from ._engine import SeqLikelihoodEngine
+from ._msnc_density import LOG_FLOOR
+from .candidates import candidate_table, signature
+from .tree import FlatTree
+
+
+def _logsumexp(values: np.ndarray) -> float:
+    # reference _logsumexp (src/_msnc_density.py:950-967): floor for an empty / all -inf set, sum in list order
+    if values.shape[0] == 0:
+        return LOG_FLOOR
+    m = float(values.max())
+    if m == -math.inf:
+        return LOG_FLOOR
+    acc = 0.0
+    for v in values.tolist():
+        acc += math.exp(v - m)
+    return m + math.log(acc)
+
+
+def _member(ft: FlatTree, parent: np.ndarray, blen: np.ndarray) -> FlatTree:
+    t = FlatTree.__new__(FlatTree)
+    t.parent = np.ascontiguousarray(parent, dtype=np.int32)
+    t.blen = np.ascontiguousarray(blen, dtype=np.float64)
+    t.label = ft.label
+    t._n_children = None
+    t._tip_rows = ft._tip_rows       # leaves stay leaves under NNI and scaling
+    return t
+
+
+def _logweights(engine: SeqLikelihoodEngine, sets, net: Any, theta: float) -> List[np.ndarray]:
+    """``logw[j] = log P(S_i | g_j) + log P(g_j | net, theta)``, ``-inf`` where either factor is not finite
+    (``_candidate_logweights`` ``:1864-1897``) -- two device calls for all loci."""
+    fels = engine.score_candidate_sets(sets)
+    msnc = engine.msnc_candidate_sets(sets, net, theta)
+    out = []
+    for f, m in zip(fels, msnc):
+        w = f + m
+        w[~(np.isfinite(f) & np.isfinite(m))] = -np.inf
+        out.append(w)
+    return out
+
+
+def coupled_gene_tree_reproposal(engine: SeqLikelihoodEngine, gene_trees: Sequence[FlatTree], heights: Sequence[np.ndarray],
+                                 target_net: Any, reverse_net: Any, theta: float, rng: np.random.Generator,
+                                 choose: Any = None) -> Optional[Tuple[List[FlatTree], List[np.ndarray], float, float]]:
+    """Returns ``(new_gene_trees, new_heights, log_qf, log_qr)`` or ``None`` where the reference declines the move
+    (a candidate set without a finite-weight member, or an original tree that cannot be matched in the reverse
+    set).  ``gene_trees[i]`` / ``heights[i]`` are the current tree of locus ``i`` and its node heights.
+    ``choose(i, table, probs) -> j`` replaces the random draw (tests: the member order of a candidate set follows
+    node order, which in the reference is the hash order of a set of objects and cannot be replayed)."""
+    M = engine.n_loci
+    if len(gene_trees) != M or len(heights) != M:
+        raise ValueError("coupled_gene_tree_reproposal: one gene tree and one height vector per locus")
+    # ---- forward: candidate sets of the current trees, scored under the target network
+    fwd = [candidate_table(gene_trees[i], heights[i]) for i in range(M)]
+    fwd_lw = _logweights(engine, [(i, (gene_trees[i], fwd[i][0], fwd[i][1])) for i in range(M)], target_net, theta)
+    new_trees: List[FlatTree] = []
+    new_heights: List[np.ndarray] = []
+    log_qf = 0.0
+    for i in range(M):
+        lw = fwd_lw[i]
+        lse = _logsumexp(lw)
+        if not math.isfinite(lse):
+            return None
+        probs = np.exp(lw - lse)
+        total = float(probs.sum())
+        if not math.isfinite(total) or total <= 0.0:
+            return None
+        probs = probs / total
+        j = int(rng.choice(lw.shape[0], p=probs)) if choose is None else int(choose(i, fwd[i], probs))
+        log_qf += float(lw[j]) - lse
+        par, bl, ht = fwd[i]
+        new_trees.append(_member(gene_trees[i], par[j], bl[j]))
+        new_heights.append(ht[j].copy())
+    # ---- reverse: candidate sets of the chosen trees, scored under the reverse network
+    rev = [candidate_table(new_trees[i], new_heights[i]) for i in range(M)]
+    rev_lw = _logweights(engine, [(i, (new_trees[i], rev[i][0], rev[i][1])) for i in range(M)], reverse_net, theta)
+    log_qr = 0.0
+    for i in range(M):
+        lw = rev_lw[i]
+        lse = _logsumexp(lw)
+        if not math.isfinite(lse):
+            return None
+        target_sig = signature(gene_trees[i], heights[i])
+        par, bl, ht = rev[i]
+        # the original is the member with the same internal heights AND the same clades; the height test is a
+        # cheap filter in front of the signature
+        want = np.sort(np.round(heights[i][gene_trees[i].n_children() > 0], 12))
+        match = -1
+        for jj in range(par.shape[0]):
+            cand = _member(new_trees[i], par[jj], bl[jj])
+            got = np.sort(np.round(ht[jj][cand.n_children() > 0], 12))
+            if got.shape == want.shape and np.array_equal(got, want) and signature(cand, ht[jj]) == target_sig:
+                match = jj
+                break
+        if match < 0 or not math.isfinite(float(lw[match])):
+            return None
+        log_qr += float(lw[match]) - lse
+    return new_trees, new_heights, log_qf, log_qr

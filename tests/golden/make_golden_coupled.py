@@ -1,0 +1,137 @@
+"""Golden vectors for the guided joint gene-tree re-proposal of the coupled moves, from the UNMODIFIED reference
+(``_coupled_gene_tree_reproposal`` ``src/_mcmc_seq.py:1995-2070``).  Build-container only (see _ref_loader.py).
+
+    python tests/golden/make_golden_coupled.py   ->  tests/golden/coupled_cases.json
+
+Each case: a species tree (the reverse network) and the same tree with one reticulation added (the target
+network), per-locus alignments and current gene trees, theta, a seed -- and what the reference returned:
+the chosen gene tree of every locus (as [leaf set, height] pairs of its internal nodes), log q_f and log q_r.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from _ref_loader import load_reference  # noqa: E402
+
+load_reference()
+from phynetpy import _mcmc_seq as M  # noqa: E402
+from phynetpy._seq_likelihood import GTR  # noqa: E402
+from phynetpy._sim_seq import simulate_gene_tree, simulate_sequences  # noqa: E402
+from phynetpy.GraphUtils import _node_heights  # noqa: E402
+from phynetpy.Network import Network  # noqa: E402
+from phynetpy.models import BranchLengthUnit  # noqa: E402
+
+from make_golden_msnc import enewick, export_gene_tree, export_network, random_network  # noqa: E402
+
+UNIT = BranchLengthUnit.SUBSTITUTIONS_PER_SITE
+PI, RATES = [0.1, 0.2, 0.3, 0.4], [1.0, 2.5, 0.7, 1.3, 3.1, 0.9]
+
+
+class _State:
+    pass
+
+
+def clade(net, node):
+    out, stack = [], [node]
+    while stack:
+        v = stack.pop()
+        kids = net.get_children(v)
+        if kids:
+            stack.extend(kids)
+        else:
+            out.append(v.label)
+    return sorted(out)
+
+
+def describe(gt, heights):
+    return sorted([clade(gt, v), float(heights[v])] for v in gt.V() if gt.get_children(v))
+
+
+def main():
+    cases = []
+    model = GTR(PI, RATES)
+    for n_species, n_loci, L, seed in [(4, 3, 80, 1), (5, 4, 60, 2), (6, 3, 100, 3), (5, 5, 40, 4)]:
+        rng = np.random.default_rng(500 + seed)
+        nodes, edges = random_network(n_species, 0, rng, height=0.06)
+        tree_nw = enewick(nodes, edges)
+        # the same tree with one reticulation: re-run the generator's insertion on a copy
+        rng_net = np.random.default_rng(900 + seed)
+        nodes2 = [list(x) for x in nodes]
+        edges2 = [list(x) for x in edges]
+
+        def add_retic(nodes, edges, rng, k=0):
+            def split(e, m, gamma_into_m):
+                p, c, g = edges[e]
+                edges[e] = [p, m, gamma_into_m]
+                edges.append([m, c, g])
+            for _ in range(500):
+                r = int(rng.integers(len(edges)))
+                d = int(rng.integers(len(edges)))
+                if r == d:
+                    continue
+                pr, cr, _ = edges[r]
+                pd, cd, _ = edges[d]
+                lo_r, hi_r = nodes[cr][1], nodes[pr][1]
+                if hi_r - lo_r < 1e-6:
+                    continue
+                th = float(rng.uniform(lo_r + 0.1 * (hi_r - lo_r), hi_r - 0.1 * (hi_r - lo_r)))
+                lo_d, hi_d = max(nodes[cd][1], th), nodes[pd][1]
+                if hi_d - lo_d < 1e-6:
+                    continue
+                tx = float(rng.uniform(lo_d + 0.05 * (hi_d - lo_d), hi_d - 0.05 * (hi_d - lo_d)))
+                g = float(rng.uniform(0.2, 0.8))
+                nodes.append(["#H%d" % k, th, True])
+                h = len(nodes) - 1
+                nodes.append(["x%d" % k, tx, False])
+                x = len(nodes) - 1
+                split(r, h, 1.0 - g)
+                split(d, x, None)
+                edges.append([x, h, g])
+                return
+            raise RuntimeError("could not place reticulation")
+        add_retic(nodes2, edges2, rng_net)
+        net_nw = enewick(nodes2, edges2)
+        sp_tree = Network.from_newick(tree_nw, branch_length_unit=UNIT)
+        sp_net = Network.from_newick(net_nw, branch_length_unit=UNIT)
+        alleles = {"s%d" % i: ["s%d" % i] for i in range(n_species)}
+        species_of = {"s%d" % i: "s%d" % i for i in range(n_species)}
+        theta = 0.03
+        gts, loci = [], []
+        for _ in range(n_loci):
+            gt = simulate_gene_tree(sp_tree, alleles, theta, rng)
+            gts.append(gt)
+            loci.append(simulate_sequences(gt, model, L, rng))
+        for direction, (target, reverse) in (("add", (sp_net, sp_tree)), ("delete", (sp_tree, sp_net))):
+            st = _State()
+            st._engine = M._SeqLikelihoodEngine(loci, species_of, model, None)
+            st.gene_trees = list(gts)
+            st.gt_heights = [_node_heights(g) for g in gts]
+            st.theta = theta
+            st.model = model
+            st.branch_thetas = None
+            res = M._coupled_gene_tree_reproposal(st, target, reverse, np.random.default_rng(7000 + seed))
+            rec = {"name": "n%d_m%d_%s" % (n_species, n_loci, direction), "seed": 7000 + seed, "theta": theta,
+                   "target": export_network(target), "reverse": export_network(reverse),
+                   "loci": loci, "species_of": species_of, "trees": [export_gene_tree(g) for g in gts]}
+            if res is None:
+                rec["result"] = None
+            else:
+                new_gts, new_hs, log_qf, log_qr = res
+                rec["result"] = {"chosen": [describe(g, h) for g, h in zip(new_gts, new_hs)],
+                                 "log_qf": float(log_qf), "log_qr": float(log_qr)}
+            cases.append(rec)
+    out = os.path.join(HERE, "coupled_cases.json")
+    with open(out, "w") as f:
+        json.dump({"source": "PhyNetPy v0.6.0 _coupled_gene_tree_reproposal", "cases": cases}, f)
+    print("wrote %s: %d cases (%d declined)" % (out, len(cases), sum(c["result"] is None for c in cases)))
+    for c in cases:
+        print(c["name"], None if c["result"] is None else (round(c["result"]["log_qf"], 4), round(c["result"]["log_qr"], 4)))
+
+
+if __name__ == "__main__":
+    main()
