@@ -24,7 +24,7 @@ import numpy as np
 
 from ._engine import SeqLikelihoodEngine
 from ._msnc_density import LOG_FLOOR
-from .candidates import candidate_table, signature
+from .candidates import _lengths_from_heights, candidate_table, signature
 from .tree import FlatTree
 
 
@@ -94,7 +94,10 @@ def coupled_gene_tree_reproposal(engine: SeqLikelihoodEngine, gene_trees: Sequen
         j = int(rng.choice(lw.shape[0], p=probs)) if choose is None else int(choose(i, fwd[i], probs))
         log_qf += float(lw[j]) - lse
         par, bl, ht = fwd[i]
-        new_trees.append(_member(gene_trees[i], par[j], bl[j]))
+        # materialised as the reference's rebuild(k) does (:1975-1986): lengths re-derived from the heights for
+        # EVERY member -- also for the unchanged tree, whose stored lengths may disagree with its heights in the
+        # last digits (it was SCORED with its stored lengths, :1828-1832)
+        new_trees.append(_member(gene_trees[i], par[j], _lengths_from_heights(par[j], ht[j])))
         new_heights.append(ht[j].copy())
     # ---- reverse: candidate sets of the chosen trees, scored under the reverse network
     rev = [candidate_table(new_trees[i], new_heights[i]) for i in range(M)]
