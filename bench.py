@@ -369,6 +369,7 @@ def main():
         chain = chain_steps(P, ctx, calcs, trees, model, n_steps=min(max(200, 20 * args.steps), 2000))
         chain["coupled_move_candidates"] = candidate_batch(P, ctx, calcs, trees, model, n_loci=min(200, len(calcs)))
         chain["msnc_density"] = msnc_leg(P, ctx, n_loci=len(calcs), n_species=spec["n"], cpu=not args.no_cpu_baseline)
+        chain["coupled_move"] = coupled_move_leg(P, ctx, model, n_loci=min(200, len(calcs)), n_species=spec["n"], L=spec["L"])
         chain["joint_likelihood_chain"] = joint_chain(P, ctx, model, n_loci=len(calcs), n_species=spec["n"], L=spec["L"],
                                                       n_steps=1000)
 
@@ -643,6 +644,43 @@ def joint_chain(P, ctx, model, n_loci, n_species, L, n_steps, seed=45):
         "final_total": full,
         "incremental_equals_full_recompute_bitwise": bool(inc_f == list(eng._felsen) and inc_m == list(eng._msnc)
                                                           and full == total),
+    }
+
+
+def coupled_move_leg(P, ctx, model, n_loci, n_species, L, seed=46):
+    """One guided joint gene-tree re-proposal of a coupled add-reticulation move (reference
+    _coupled_gene_tree_reproposal, src/_mcmc_seq.py:1995-2070): every locus' candidate set scored under the target
+    network (Felsenstein + MSNC), one member sampled, the candidate sets of the chosen trees scored under the
+    reverse network -- four device calls in phynetpy_b200/coupled.py; host enumeration included."""
+    from phynetpy_b200 import simulate as S
+    from phynetpy_b200.candidates import candidate_table, node_heights
+    from phynetpy_b200.coupled import coupled_gene_tree_reproposal
+    rng = np.random.default_rng(seed)
+    theta = 0.02
+    sp_tree = S.random_species_network(n_species, 0, rng, height=0.005 * (n_species - 1))
+    # the same tree with one reticulation = the network the move proposes
+    rng2 = np.random.default_rng(seed)
+    sp_net = S.random_species_network(n_species, 1, rng2, height=0.005 * (n_species - 1))
+    trees, species_of = S.simulate_gene_trees_msnc(sp_tree, 1, theta, rng, n_loci)
+    aln = S.simulate_alignments(np.stack([t.parent for t in trees]), np.stack([t.blen for t in trees]), L,
+                                S.DEFAULT_PI, S.DEFAULT_RATES, rng)
+    eng = P.SeqLikelihoodEngine([S.to_alignment_dict(aln[i]) for i in range(n_loci)], species_of, model, context=ctx)
+    eng.log_likelihood(trees, sp_tree, theta)
+    eng._commit_pending()
+    heights = [node_heights(t) for t in trees]
+    res, times = None, []
+    for rep in range(4):
+        t0 = time.perf_counter()
+        res = coupled_gene_tree_reproposal(eng, trees, heights, sp_net, sp_tree, theta, np.random.default_rng(rep))
+        times.append(time.perf_counter() - t0)
+    n_members = sum(candidate_table(t, h)[0].shape[0] for t, h in zip(trees, heights))
+    return {
+        "what": "coupled_gene_tree_reproposal: forward + reverse candidate sets of all loci, 4 device calls",
+        "loci": n_loci, "forward_candidate_trees": int(n_members),
+        "prunings_and_densities_the_reference_would_run": int(4 * n_members),
+        "seconds_per_move": float(np.median(times[1:])), "first_call_seconds": float(times[0]),
+        "declined": res is None,
+        "log_qf": None if res is None else res[2], "log_qr": None if res is None else res[3],
     }
 
 

@@ -125,14 +125,8 @@ def nni_neighbors_at(ft: FlatTree, h: np.ndarray) -> List[Tuple[FlatTree, np.nda
     return out
 
 
-def candidate_arrays(ft: FlatTree, scales: Sequence[float] = HEIGHT_SCALE_GRID) -> Tuple[np.ndarray, np.ndarray]:
-    """The candidate set as stacked arrays ``(parent[K, n], blen[K, n])`` -- the form
-    ``SeqLikelihoodEngine.score_candidate_sets`` packs without creating K tree objects.
-
-    Same members and order as :func:`candidate_set`.  De-duplication: bases are distinct by
-    signature (checked in :func:`nni_neighbors`); two scales of one base coincide only if their
-    rounded internal heights coincide, which is what is compared here (same leaf sets by construction).
-    """
+def _candidate_arrays_plain(ft: FlatTree, scales: Sequence[float] = HEIGHT_SCALE_GRID) -> Tuple[np.ndarray, np.ndarray]:
+    """Straightforward enumeration (one signature per member); kept as the cross-check of :func:`candidate_table`."""
     h0 = node_heights(ft)
     bases = [(ft, h0)] + nni_neighbors(ft)
     base_sigs = set()
@@ -155,34 +149,98 @@ def candidate_arrays(ft: FlatTree, scales: Sequence[float] = HEIGHT_SCALE_GRID) 
     return np.ascontiguousarray(np.stack(parents), dtype=np.int32), np.ascontiguousarray(np.stack(lengths), dtype=np.float64)
 
 
+def candidate_arrays(ft: FlatTree, scales: Sequence[float] = HEIGHT_SCALE_GRID) -> Tuple[np.ndarray, np.ndarray]:
+    """The candidate set as stacked arrays ``(parent[K, n], blen[K, n])`` -- the form
+    ``SeqLikelihoodEngine.score_candidate_sets`` packs without creating K tree objects.
+    Same members and order as :func:`candidate_set`."""
+    return candidate_table(ft, None, scales)[:2]
+
+
 def candidate_table(ft: FlatTree, heights: np.ndarray = None,
                     scales: Sequence[float] = HEIGHT_SCALE_GRID) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
-    """:func:`candidate_arrays` plus the node heights of every member: ``(parent[K, n], blen[K, n], height[K, n])``
-    -- what a caller needs to materialise the member it picks (``rebuild(k)`` of the reference,
+    """The candidate set with the node heights of every member: ``(parent[K, n], blen[K, n], height[K, n])`` --
+    what a caller needs to score the members and to materialise the one it picks (``rebuild(k)`` of the reference,
     ``src/_mcmc_seq.py:1975-1986``).  ``heights`` are the tree's own node heights when the caller tracks them
-    (the reference's ``gt_heights``); member (tree, scale 1) keeps the tree's lengths untouched (``:1828-1832``)."""
-    h0 = node_heights(ft) if heights is None else np.ascontiguousarray(heights, dtype=np.float64)
-    bases = [(ft, h0)] + nni_neighbors_at(ft, h0)
-    base_sigs = set()
-    parents, lengths, hts = [], [], []
-    internal = ft.n_children() > 0
-    for k, (base, h) in enumerate(bases):
-        bsig = signature(base, h)
-        if k > 0 and bsig in base_sigs:
+    (the reference's ``gt_heights``); member (tree, scale 1) keeps the tree's lengths untouched (``:1828-1832``).
+
+    Enumeration without per-member tree objects or signatures (the reference clones a graph per neighbour and
+    hashes a set of leaf sets per member; on the host that -- not the scoring -- is what a coupled move costs once
+    the scoring runs on the device):
+
+    * an NNI around ``v`` changes exactly one clade (``v``'s) and no height, so neighbours are told apart by
+      (v, new clade of v) with clades as integer bit sets;
+    * scales are exact powers of two, so the lengths / heights of a scaled member are the base's times the scale,
+      bit for bit what re-deriving them from the scaled heights gives (``_sync_lengths`` on ``h * s``);
+    * two scales of one base can only collide after rounding to 12 decimals if every internal height is ~0;
+      only then are the rounded heights compared.
+    """
+    h = node_heights(ft) if heights is None else np.ascontiguousarray(heights, dtype=np.float64)
+    parent = ft.parent
+    plist = parent.tolist()
+    n = len(plist)
+    kids: List[List[int]] = [[] for _ in range(n)]
+    for i, p in enumerate(plist):
+        if p >= 0:
+            kids[p].append(i)
+    # clades as bit sets over leaf ordinals, children before parents
+    clade = [0] * n
+    n_leaf = 0
+    for v in _postorder(parent, kids):
+        if kids[v]:
+            m = 0
+            for c in kids[v]:
+                m |= clade[c]
+            clade[v] = m
+        else:
+            clade[v] = 1 << n_leaf
+            n_leaf += 1
+    hl = h.tolist()
+    base_parents = [parent]
+    seen = set()
+    for v in range(n):
+        if len(kids[v]) < 2 or plist[v] < 0:
             continue
-        base_sigs.add(bsig)
-        seen_h = set()
-        for s in scales:
-            hs = h * s if s != 1.0 else h
-            key = tuple(np.round(hs[internal], 12).tolist())
-            if key in seen_h:
+        p = plist[v]
+        sibs = [c for c in kids[p] if c != v]
+        if len(sibs) != 1:
+            continue
+        s = sibs[0]
+        if hl[v] <= hl[s]:
+            continue
+        for c in kids[v]:
+            key = (v, (clade[v] & ~clade[c]) | clade[s])
+            if key in seen:
                 continue
-            seen_h.add(key)
-            parents.append(base.parent)
-            lengths.append(ft.blen if (k == 0 and s == 1.0) else _lengths_from_heights(base.parent, hs))
-            hts.append(hs)
-    return (np.ascontiguousarray(np.stack(parents), dtype=np.int32), np.ascontiguousarray(np.stack(lengths), dtype=np.float64),
-            np.ascontiguousarray(np.stack(hts), dtype=np.float64))
+            seen.add(key)
+            q = parent.copy()
+            q[s], q[c] = v, p                      # s goes under v, c goes under p
+            base_parents.append(q)
+    sc = np.asarray(scales, dtype=np.float64)
+    internal = np.fromiter((len(k) > 0 for k in kids), dtype=bool, count=n)
+    hi = h[internal]
+    # can two scales give the same rounded internal heights?  only if every internal height is tiny
+    degenerate = hi.shape[0] == 0 or float(np.abs(hi).max()) * float(np.min(np.abs(np.diff(np.sort(sc))), initial=np.inf)) < 1e-9
+    if degenerate:
+        keep = []
+        seen_h = set()
+        for k, s_ in enumerate(sc.tolist()):
+            key_h = tuple(np.round(hi * s_ if s_ != 1.0 else hi, 12).tolist())
+            if key_h not in seen_h:
+                seen_h.add(key_h)
+                keep.append(k)
+        sc = sc[keep]
+    S = sc.shape[0]
+    B = len(base_parents)
+    P = np.repeat(np.stack(base_parents), S, axis=0)
+    H = np.tile(h[None, :] * sc[:, None], (B, 1))
+    H[np.tile(sc == 1.0, B)] = h                   # scale 1 is the height vector itself (no multiplication)
+    L = np.empty((B * S, n), dtype=np.float64)
+    for b, q in enumerate(base_parents):
+        L[b * S:(b + 1) * S] = _lengths_from_heights(q, h)[None, :] * sc[:, None]
+    ident = np.nonzero(sc == 1.0)[0]
+    if ident.shape[0]:
+        L[int(ident[0])] = ft.blen                 # the tree itself at scale 1: lengths untouched
+    return np.ascontiguousarray(P, dtype=np.int32), L, H
 
 
 def candidate_set(ft: FlatTree, scales: Sequence[float] = HEIGHT_SCALE_GRID) -> List[FlatTree]:

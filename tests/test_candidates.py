@@ -3,8 +3,8 @@ the reference's ``_candidate_set``) and their scores in one device call (GPU, 1e
 import numpy as np
 import pytest
 
-from phynetpy_b200.candidates import (HEIGHT_SCALE_GRID, candidate_arrays, candidate_set, nni_neighbors,
-                                      node_heights, signature)
+from phynetpy_b200.candidates import (HEIGHT_SCALE_GRID, _candidate_arrays_plain, candidate_arrays, candidate_set,
+                                      candidate_table, nni_neighbors, node_heights, signature)
 from phynetpy_b200.tree import FlatTree
 from conftest import load_golden
 
@@ -67,3 +67,27 @@ def test_candidate_scores_match_reference(case):
     par, bl = candidate_arrays(ft)
     (vals2,) = eng.score_candidate_sets([(0, (ft, par, bl))])
     assert np.array_equal(vals2, vals)
+
+
+def test_fast_enumeration_equals_the_plain_one():
+    """candidate_table tells NNI neighbours apart by (node, new clade) and scales lengths by exact powers of two
+    instead of building a tree and hashing a signature per member; members, order and every bit must agree."""
+    from phynetpy_b200 import simulate as S
+    rng = np.random.default_rng(8)
+    for n in (2, 3, 4, 6, 9, 16, 25):
+        par, bl = S.random_trees(12, n, rng)
+        for ft in S.flat_trees(par, bl):
+            a = _candidate_arrays_plain(ft)
+            p, l, h = candidate_table(ft)
+            assert np.array_equal(a[0], p)
+            assert np.array_equal(np.nan_to_num(a[1], nan=-1.0), np.nan_to_num(l, nan=-1.0))
+            for k in range(0, p.shape[0], 7):
+                assert np.allclose(node_heights(FlatTree(p[k], l[k], ft.label)), h[k], rtol=0, atol=1e-12)
+    # node order that is not children-first, a polytomy, all-zero heights (scales collide after rounding)
+    for ft in (FlatTree([4, 4, 3, -1, 3], [0.1, 0.1, 0.3, None, 0.2], ["a", "b", "c", None, None]),
+               FlatTree([3, 3, 3, 5, 5, -1], [0.1, 0.1, 0.1, 0.2, 0.3, None], ["a", "b", "c", None, "d", None]),
+               FlatTree([2, 2, 4, 4, -1], [0.0, 0.0, 0.0, 0.0, None], ["a", "b", None, "c", None])):
+        a = _candidate_arrays_plain(ft)
+        p, l, h = candidate_table(ft)
+        assert np.array_equal(a[0], p) and np.array_equal(np.nan_to_num(a[1], nan=-1.0), np.nan_to_num(l, nan=-1.0))
+    assert np.array_equal(candidate_arrays(ft)[0], p)
