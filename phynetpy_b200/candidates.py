@@ -156,8 +156,24 @@ def candidate_arrays(ft: FlatTree, scales: Sequence[float] = HEIGHT_SCALE_GRID) 
     return candidate_table(ft, None, scales)[:2]
 
 
-def candidate_table(ft: FlatTree, heights: np.ndarray = None,
-                    scales: Sequence[float] = HEIGHT_SCALE_GRID) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+def clade_masks(parent: np.ndarray) -> List[int]:
+    """Per node, the set of leaves below it as an integer bit set (bit = the leaf's node index); node indices are
+    stable across NNI rearrangements of a flat tree, so masks of different members are comparable."""
+    kids = _children(parent)
+    clade = [0] * len(kids)
+    for v in _postorder(parent, kids):
+        if kids[v]:
+            m = 0
+            for c in kids[v]:
+                m |= clade[c]
+            clade[v] = m
+        else:
+            clade[v] = 1 << v
+    return clade
+
+
+def candidate_table(ft: FlatTree, heights: np.ndarray = None, scales: Sequence[float] = HEIGHT_SCALE_GRID,
+                    info: dict = None) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     """The candidate set with the node heights of every member: ``(parent[K, n], blen[K, n], height[K, n])`` --
     what a caller needs to score the members and to materialise the one it picks (``rebuild(k)`` of the reference,
     ``src/_mcmc_seq.py:1975-1986``).  ``heights`` are the tree's own node heights when the caller tracks them
@@ -182,9 +198,8 @@ def candidate_table(ft: FlatTree, heights: np.ndarray = None,
     for i, p in enumerate(plist):
         if p >= 0:
             kids[p].append(i)
-    # clades as bit sets over leaf ordinals, children before parents
+    # clades as bit sets, children before parents
     clade = [0] * n
-    n_leaf = 0
     for v in _postorder(parent, kids):
         if kids[v]:
             m = 0
@@ -192,10 +207,10 @@ def candidate_table(ft: FlatTree, heights: np.ndarray = None,
                 m |= clade[c]
             clade[v] = m
         else:
-            clade[v] = 1 << n_leaf
-            n_leaf += 1
+            clade[v] = 1 << v                      # bit = node index of the leaf (stable under NNI)
     hl = h.tolist()
     base_parents = [parent]
+    base_change = [(-1, 0)]                        # per base: (node whose clade changed, its new clade)
     seen = set()
     for v in range(n):
         if len(kids[v]) < 2 or plist[v] < 0:
@@ -215,6 +230,7 @@ def candidate_table(ft: FlatTree, heights: np.ndarray = None,
             q = parent.copy()
             q[s], q[c] = v, p                      # s goes under v, c goes under p
             base_parents.append(q)
+            base_change.append(key)
     sc = np.asarray(scales, dtype=np.float64)
     internal = np.fromiter((len(k) > 0 for k in kids), dtype=bool, count=n)
     hi = h[internal]
@@ -240,7 +256,33 @@ def candidate_table(ft: FlatTree, heights: np.ndarray = None,
     ident = np.nonzero(sc == 1.0)[0]
     if ident.shape[0]:
         L[int(ident[0])] = ft.blen                 # the tree itself at scale 1: lengths untouched
+    if info is not None:     # what find_member needs: member b * S + k = base b at scale sc[k]
+        info.update(clade=clade, internal=[v for v in range(n) if kids[v]], base_change=base_change, scales=sc.tolist(), heights=hl)
     return np.ascontiguousarray(P, dtype=np.int32), L, H
+
+
+def find_member(info: dict, target_parent: np.ndarray, target_heights: np.ndarray) -> int:
+    """Index of the member of a candidate table (built with ``info=``) that has the clades and the 12-decimal
+    heights of the given tree -- the reference's ``_gt_signature`` match (``src/_mcmc_seq.py:2052-2058``) -- or -1.
+    No member tree is built: base b differs from the table's tree in ONE clade, scale k multiplies the heights."""
+    tm = clade_masks(target_parent)
+    th = target_heights.tolist()
+    t_kids = np.bincount(target_parent[target_parent >= 0], minlength=len(tm))
+    target = {tm[u]: round(th[u], 12) for u in range(len(tm)) if t_kids[u] > 0}
+    clade, internal, hl = info["clade"], info["internal"], info["heights"]
+    S = len(info["scales"])
+    for b, (v, new_mask) in enumerate(info["base_change"]):
+        ok = True
+        for u in internal:
+            if (new_mask if u == v else clade[u]) not in target:
+                ok = False
+                break
+        if not ok or len(internal) != len(target):
+            continue
+        for k, s_ in enumerate(info["scales"]):
+            if all(round(hl[u] * s_ if s_ != 1.0 else hl[u], 12) == target[new_mask if u == v else clade[u]] for u in internal):
+                return b * S + k
+    return -1
 
 
 def candidate_set(ft: FlatTree, scales: Sequence[float] = HEIGHT_SCALE_GRID) -> List[FlatTree]:

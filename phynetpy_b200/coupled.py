@@ -24,7 +24,7 @@ import numpy as np
 
 from ._engine import SeqLikelihoodEngine
 from ._msnc_density import LOG_FLOOR
-from .candidates import _lengths_from_heights, candidate_table, signature
+from .candidates import _lengths_from_heights, candidate_table, find_member
 from .tree import FlatTree
 
 
@@ -100,7 +100,8 @@ def coupled_gene_tree_reproposal(engine: SeqLikelihoodEngine, gene_trees: Sequen
         new_trees.append(_member(gene_trees[i], par[j], _lengths_from_heights(par[j], ht[j])))
         new_heights.append(ht[j].copy())
     # ---- reverse: candidate sets of the chosen trees, scored under the reverse network
-    rev = [candidate_table(new_trees[i], new_heights[i]) for i in range(M)]
+    rev_info: List[dict] = [{} for _ in range(M)]
+    rev = [candidate_table(new_trees[i], new_heights[i], info=rev_info[i]) for i in range(M)]
     rev_lw = _logweights(engine, [(i, (new_trees[i], rev[i][0], rev[i][1])) for i in range(M)], reverse_net, theta)
     log_qr = 0.0
     for i in range(M):
@@ -108,18 +109,8 @@ def coupled_gene_tree_reproposal(engine: SeqLikelihoodEngine, gene_trees: Sequen
         lse = _logsumexp(lw)
         if not math.isfinite(lse):
             return None
-        target_sig = signature(gene_trees[i], heights[i])
-        par, bl, ht = rev[i]
-        # the original is the member with the same internal heights AND the same clades; the height test is a
-        # cheap filter in front of the signature
-        want = np.sort(np.round(heights[i][gene_trees[i].n_children() > 0], 12))
-        match = -1
-        for jj in range(par.shape[0]):
-            cand = _member(new_trees[i], par[jj], bl[jj])
-            got = np.sort(np.round(ht[jj][cand.n_children() > 0], 12))
-            if got.shape == want.shape and np.array_equal(got, want) and signature(cand, ht[jj]) == target_sig:
-                match = jj
-                break
+        # the member with the original's clades and (12-decimal) heights: the reference's signature match
+        match = find_member(rev_info[i], gene_trees[i].parent, heights[i])
         if match < 0 or not math.isfinite(float(lw[match])):
             return None
         log_qr += float(lw[match]) - lse
