@@ -212,6 +212,25 @@ PNB_API int pnb_msnc_eval(pnb_ctx *ctx, const pnb_msnc_net *net, int64_t n_trees
                           const int32_t *parent, const double *blen, const int32_t *node_species,
                           double theta, double *logp_out);
 
+/* ---- candidate sets of the coupled moves (host) -------------------------------- */
+/* Replaces _candidate_set / _gene_tree_nni_neighbors / _scaled_gene_tree (src/_mcmc_seq.py:1724-1861) for MANY gene
+ * trees at once, writing straight into the CSR arrays pnb_eval / pnb_msnc_eval take.  The candidate set of a tree
+ * is: the tree, then its height-preserving NNI neighbours (node v ascending, then v's children ascending: child c
+ * and v's only sibling s trade places when height[v] > height[s]), each at every height scale, in that order;
+ * member (tree, scale 1) keeps the tree's branch lengths, every other member gets max(h[parent] - h[child], 0) on
+ * the scaled heights (_sync_lengths, :418-434).  Trees are CSR-packed (tree_off, parent) with node heights.
+ * Two calls: _count gives the members per tree; the caller sizes the outputs (member_off = prefix sum; rows are
+ * members x nodes of their tree, concatenated) and _fill writes them.  changed_node_out / scale_out (may be NULL):
+ * per member the node whose clade the NNI changed (-1 for the tree itself) and the scale.  ctx may be NULL or
+ * host-only (its worker pool, if any, is used).  Up to 128 nodes per tree, up to 16 scales.                    */
+PNB_API int pnb_candidates_count(pnb_ctx *ctx, int64_t n_trees, const int64_t *tree_off, const int32_t *parent,
+                                 const double *height, int32_t n_scales, const double *scales,
+                                 int64_t *n_members_out);
+PNB_API int pnb_candidates_fill(pnb_ctx *ctx, int64_t n_trees, const int64_t *tree_off, const int32_t *parent,
+                                const double *blen, const double *height, int32_t n_scales, const double *scales,
+                                const int64_t *member_off, int32_t *parent_out, double *blen_out,
+                                double *height_out, int32_t *changed_node_out, double *scale_out);
+
 /* ---- host-only planning (tests of the host runtime; no device involved) -- */
 /* A planning context owns no GPU: loci created on it hold no device memory and
  * pnb_eval on it fails.  pnb_plan runs exactly the host half of pnb_eval -- cache

@@ -348,6 +348,29 @@ class SeqLikelihoodEngine:
             k += K
         return res
 
+    # -- natively enumerated candidate batches (candidates.CandidateBatch) ---------------------------------
+    def score_batch(self, batch: Any, loci: Sequence[int], *, site_rate: float = 1.0) -> np.ndarray:
+        """Felsenstein log-likelihood of every member of a :class:`~phynetpy_b200.candidates.CandidateBatch`
+        (tree ``j`` of the batch belongs to locus ``loci[j]``) in ONE ``PNB_EVAL_NOSTORE`` call; the arrays the
+        native enumerator wrote are handed to ``pnb_eval`` as they are."""
+        self._commit_pending()
+        ctx = self._context()
+        counts = np.diff(batch.member_off)
+        handles = np.repeat(self._handles(loci), counts)
+        tip_row = batch.expand([batch.trees[j].tip_rows(self._calcs[i]._row_of) for j, i in enumerate(loci)], np.int32)
+        P_edge = _explicit_P_edges(self._model, batch.blen, site_rate) if _device_kind(self._model) == "explicit" else None
+        out = ctx.eval(_model_handle(self._model, ctx), handles, batch.node_off, batch.parent, batch.blen, tip_row,
+                       site_rate, _lib.EVAL_NOSTORE | self._mode, P_edge)
+        self.last_stats = ctx.last_stats()
+        return out
+
+    def msnc_batch(self, batch: Any, loci: Sequence[int], species_net: Any, theta: float) -> np.ndarray:
+        """log P(g | Psi) of every member of a candidate batch in one ``pnb_msnc_eval`` call."""
+        theta = _check_theta(theta)
+        net = self._network(species_net)
+        ids = batch.expand([self._species_ids(i, batch.trees[j], net) for j, i in enumerate(loci)], np.int32)
+        return msnc_eval_packed(net, batch.node_off, batch.parent, batch.blen, ids, theta, self._context(), self._branch_thetas)
+
     def score_candidate_sets(self, sets: Sequence[Tuple[int, Sequence[Any]]], *, site_rate: float = 1.0) -> List[np.ndarray]:
         """Candidate trees for MANY loci in ONE launch: ``sets = [(locus, [tree, ...]), ...]``.
 

@@ -41,6 +41,7 @@ ABI_SYMBOLS = (
     "pnb_ctx_create_host", "pnb_plan",
     "pnb_msnc_net_create", "pnb_msnc_net_destroy", "pnb_msnc_net_info", "pnb_msnc_net_set_max_frontier", "pnb_msnc_net_set_branch_thetas",
     "pnb_msnc_eval",
+    "pnb_candidates_count", "pnb_candidates_fill",
 )
 
 
@@ -105,6 +106,8 @@ def load() -> C.CDLL:
             "pnb_msnc_net_set_max_frontier": [_vp, _i64],
             "pnb_msnc_net_set_branch_thetas": [_vp, _vp, C.c_double],
             "pnb_msnc_eval": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, C.c_double, _vp],
+            "pnb_candidates_count": [_vp, _i64, _vp, _vp, _vp, _i32, _vp, _vp],
+            "pnb_candidates_fill": [_vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
         }
         for name, argtypes in sigs.items():
             fn = getattr(lib, name)

@@ -307,3 +307,117 @@ def candidate_set(ft: FlatTree, scales: Sequence[float] = HEIGHT_SCALE_GRID) -> 
             seen.add(sig)
             out.append(cand)
     return out
+
+
+class CandidateBatch:
+    """The candidate sets of MANY gene trees, enumerated natively (``pnb_candidates_count`` / ``_fill``) straight
+    into the CSR arrays the device calls take.  Tree ``j`` owns members ``member_off[j] .. member_off[j+1]-1``;
+    member ``m`` owns nodes ``node_off[m] .. node_off[m+1]-1`` of ``parent`` / ``blen`` / ``height``.
+    Same members, order and bits as :func:`candidate_table` per tree."""
+
+    __slots__ = ("trees", "member_off", "node_off", "parent", "blen", "height", "changed_node", "scale", "tree_of_member")
+
+    def __init__(self, trees: Sequence[FlatTree], heights: Sequence[np.ndarray], scales: Sequence[float] = HEIGHT_SCALE_GRID,
+                 context=None):
+        import ctypes as C
+        from . import _lib
+        lib = _lib.load()
+        self.trees = list(trees)
+        T = len(self.trees)
+        sizes = np.fromiter((t.n_nodes for t in self.trees), dtype=np.int64, count=T)
+        tree_off = np.zeros(T + 1, dtype=np.int64)
+        np.cumsum(sizes, out=tree_off[1:])
+        parent = np.ascontiguousarray(np.concatenate([t.parent for t in self.trees]) if T else np.zeros(0), dtype=np.int32)
+        blen = np.ascontiguousarray(np.concatenate([t.blen for t in self.trees]) if T else np.zeros(0), dtype=np.float64)
+        h = np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=np.float64) for x in heights]) if T else np.zeros(0),
+                                 dtype=np.float64)
+        if h.shape[0] != parent.shape[0]:
+            raise ValueError("CandidateBatch: one height per node of every tree")
+        sc = np.ascontiguousarray(scales, dtype=np.float64)
+        ctx_h = context.handle if context is not None else None
+        counts = np.zeros(T, dtype=np.int64)
+        _lib.check(lib.pnb_candidates_count(ctx_h, T, _lib.ptr(tree_off), _lib.ptr(parent), _lib.ptr(h), int(sc.shape[0]),
+                                            _lib.ptr(sc), _lib.ptr(counts)))
+        self.member_off = np.zeros(T + 1, dtype=np.int64)
+        np.cumsum(counts, out=self.member_off[1:])
+        n_members = int(self.member_off[-1])
+        member_sizes = np.repeat(sizes, counts)
+        self.node_off = np.zeros(n_members + 1, dtype=np.int64)
+        np.cumsum(member_sizes, out=self.node_off[1:])
+        rows = int(self.node_off[-1])
+        self.parent = np.empty(rows, dtype=np.int32)
+        self.blen = np.empty(rows, dtype=np.float64)
+        self.height = np.empty(rows, dtype=np.float64)
+        self.changed_node = np.empty(n_members, dtype=np.int32)
+        self.scale = np.empty(n_members, dtype=np.float64)
+        self.tree_of_member = np.repeat(np.arange(T, dtype=np.int64), counts)
+        _lib.check(lib.pnb_candidates_fill(ctx_h, T, _lib.ptr(tree_off), _lib.ptr(parent), _lib.ptr(blen), _lib.ptr(h),
+                                           int(sc.shape[0]), _lib.ptr(sc), _lib.ptr(self.member_off), _lib.ptr(self.parent),
+                                           _lib.ptr(self.blen), _lib.ptr(self.height), _lib.ptr(self.changed_node),
+                                           _lib.ptr(self.scale)))
+
+    @property
+    def n_members(self) -> int:
+        return int(self.member_off[-1])
+
+    def expand(self, per_tree: Sequence[np.ndarray], dtype) -> np.ndarray:
+        """One per-node array per TREE (tip rows, species ids) repeated for every member of that tree."""
+        counts = np.diff(self.member_off)
+        sizes = {a.shape[0] for a in per_tree}
+        if len(sizes) == 1 and len(per_tree):       # equal tree sizes: one repeat over a 2-D array
+            return np.ascontiguousarray(np.repeat(np.stack(per_tree), counts, axis=0).reshape(-1), dtype=dtype)
+        return np.ascontiguousarray(np.concatenate([np.tile(a, int(k)) for a, k in zip(per_tree, counts)]), dtype=dtype)
+
+    def member(self, m: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        a, b = int(self.node_off[m]), int(self.node_off[m + 1])
+        return self.parent[a:b], self.blen[a:b], self.height[a:b]
+
+    def table(self, j: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """Members of tree ``j`` as ``(parent[K, n], blen[K, n], height[K, n])`` views (the form of candidate_table)."""
+        m0, m1 = int(self.member_off[j]), int(self.member_off[j + 1])
+        a, b = int(self.node_off[m0]), int(self.node_off[m1])
+        n = self.trees[j].n_nodes
+        return self.parent[a:b].reshape(m1 - m0, n), self.blen[a:b].reshape(m1 - m0, n), self.height[a:b].reshape(m1 - m0, n)
+
+
+def find_member_in_batch(batch: CandidateBatch, j: int, target_parent: np.ndarray, target_heights: np.ndarray) -> int:
+    """:func:`find_member` for tree ``j`` of a natively enumerated batch: index (within that tree's members) of the
+    member with the clades and 12-decimal heights of the given tree, or -1.  Uses what the enumerator recorded per
+    member -- the node whose clade the NNI changed and the scale -- so no member tree is rebuilt."""
+    ft = batch.trees[j]
+    m0, m1 = int(batch.member_off[j]), int(batch.member_off[j + 1])
+    # common case first: node identities are shared by a tree and everything enumerated from it, so the original
+    # usually IS a member parent array for parent array (an NNI undone) with node-wise equal rounded heights
+    if target_parent.shape[0] == ft.n_nodes:
+        P, _L, H = batch.table(j)
+        inner = ft.n_children() > 0
+        hit = np.nonzero((P == target_parent[None, :]).all(axis=1)
+                         & (np.round(H[:, inner], 12) == np.round(target_heights[inner], 12)[None, :]).all(axis=1))[0]
+        if hit.shape[0]:
+            return int(hit[0])
+    clade = clade_masks(ft.parent)
+    tm = clade_masks(target_parent)
+    th = target_heights.tolist()
+    t_kids = np.bincount(target_parent[target_parent >= 0], minlength=len(tm))
+    target = {tm[u]: round(th[u], 12) for u in range(len(tm)) if t_kids[u] > 0}
+    internal = np.nonzero(ft.n_children() > 0)[0].tolist()
+    if len(internal) != len(target):
+        return -1
+    topo_ok = {}                      # (changed node, its new clade) -> the member's clades are the target's
+    for m in range(m0, m1):
+        v = int(batch.changed_node[m])
+        par, _bl, ht = batch.member(m)
+        new_mask = 0
+        if v >= 0:                    # the member's clades are the tree's, except node v's
+            for c in np.nonzero(par == v)[0].tolist():
+                new_mask |= clade[c]
+        ok = topo_ok.get((v, new_mask))
+        if ok is None:
+            ok = all((new_mask if u == v else clade[u]) in target for u in internal)
+            topo_ok[(v, new_mask)] = ok
+        if not ok:
+            continue
+        hl = ht.tolist()
+        if all(round(hl[u], 12) == target[new_mask if u == v else clade[u]] for u in internal):
+            return m - m0
+    return -1

@@ -7,9 +7,12 @@ Felsenstein pruning and an MSNC density per member under the proposed network, s
 scores the candidate set around the chosen tree under the current network to obtain the reverse density:
 ``2 * M * K`` prunings and densities on the host per move.  Here one move is FOUR device calls:
 
-1. forward Felsenstein scores of all loci x all members (``score_candidate_sets``, ``PNB_EVAL_NOSTORE``),
-2. forward MSNC densities of the same trees under the target network (``msnc_candidate_sets``),
+1. forward Felsenstein scores of all loci x all members (``score_batch``, ``PNB_EVAL_NOSTORE``),
+2. forward MSNC densities of the same trees under the target network (``msnc_batch``),
 3. / 4. the same two calls for the candidate sets around the chosen trees, under the reverse network.
+
+The candidate sets themselves are enumerated natively for all loci at once (``candidates.CandidateBatch`` over
+``pnb_candidates_count`` / ``pnb_candidates_fill``), directly in the packed form the two calls take.
 
 Sampling follows the reference exactly -- per locus, in locus order, one ``rng.choice(K, p=probs)`` with
 ``probs = exp(logw - logsumexp(logw))`` renormalised -- and consumes the generator identically, so with the same
@@ -22,9 +25,8 @@ from typing import Any, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from ._engine import SeqLikelihoodEngine
 from ._msnc_density import LOG_FLOOR
-from .candidates import _lengths_from_heights, candidate_table, find_member
+from .candidates import CandidateBatch, _lengths_from_heights, find_member_in_batch
 from .tree import FlatTree
 
 
@@ -51,20 +53,17 @@ def _member(ft: FlatTree, parent: np.ndarray, blen: np.ndarray) -> FlatTree:
     return t
 
 
-def _logweights(engine: SeqLikelihoodEngine, sets, net: Any, theta: float) -> List[np.ndarray]:
-    """``logw[j] = log P(S_i | g_j) + log P(g_j | net, theta)``, ``-inf`` where either factor is not finite
-    (``_candidate_logweights`` ``:1864-1897``) -- two device calls for all loci."""
-    fels = engine.score_candidate_sets(sets)
-    msnc = engine.msnc_candidate_sets(sets, net, theta)
-    out = []
-    for f, m in zip(fels, msnc):
-        w = f + m
-        w[~(np.isfinite(f) & np.isfinite(m))] = -np.inf
-        out.append(w)
-    return out
+def _logweights(engine: Any, batch: CandidateBatch, loci: Sequence[int], net: Any, theta: float) -> np.ndarray:
+    """``logw[m] = log P(S_i | g_m) + log P(g_m | net, theta)`` for every member of the batch, ``-inf`` where either
+    factor is not finite (``_candidate_logweights`` ``:1864-1897``) -- two device calls for all loci."""
+    f = engine.score_batch(batch, loci)
+    m = engine.msnc_batch(batch, loci, net, theta)
+    w = f + m
+    w[~(np.isfinite(f) & np.isfinite(m))] = -np.inf
+    return w
 
 
-def coupled_gene_tree_reproposal(engine: SeqLikelihoodEngine, gene_trees: Sequence[FlatTree], heights: Sequence[np.ndarray],
+def coupled_gene_tree_reproposal(engine: Any, gene_trees: Sequence[FlatTree], heights: Sequence[np.ndarray],
                                  target_net: Any, reverse_net: Any, theta: float, rng: np.random.Generator,
                                  choose: Any = None) -> Optional[Tuple[List[FlatTree], List[np.ndarray], float, float]]:
     """Returns ``(new_gene_trees, new_heights, log_qf, log_qr)`` or ``None`` where the reference declines the move
@@ -75,14 +74,16 @@ def coupled_gene_tree_reproposal(engine: SeqLikelihoodEngine, gene_trees: Sequen
     M = engine.n_loci
     if len(gene_trees) != M or len(heights) != M:
         raise ValueError("coupled_gene_tree_reproposal: one gene tree and one height vector per locus")
-    # ---- forward: candidate sets of the current trees, scored under the target network
-    fwd = [candidate_table(gene_trees[i], heights[i]) for i in range(M)]
-    fwd_lw = _logweights(engine, [(i, (gene_trees[i], fwd[i][0], fwd[i][1])) for i in range(M)], target_net, theta)
+    loci = list(range(M))
+    ctx = getattr(engine, "_ctx", None)
+    # ---- forward: candidate sets of the current trees (one native enumeration), scored under the target network
+    fwd = CandidateBatch(gene_trees, heights, context=ctx)
+    fwd_lw = _logweights(engine, fwd, loci, target_net, theta)
     new_trees: List[FlatTree] = []
     new_heights: List[np.ndarray] = []
     log_qf = 0.0
     for i in range(M):
-        lw = fwd_lw[i]
+        lw = fwd_lw[int(fwd.member_off[i]):int(fwd.member_off[i + 1])]
         lse = _logsumexp(lw)
         if not math.isfinite(lse):
             return None
@@ -91,26 +92,25 @@ def coupled_gene_tree_reproposal(engine: SeqLikelihoodEngine, gene_trees: Sequen
         if not math.isfinite(total) or total <= 0.0:
             return None
         probs = probs / total
-        j = int(rng.choice(lw.shape[0], p=probs)) if choose is None else int(choose(i, fwd[i], probs))
+        j = int(rng.choice(lw.shape[0], p=probs)) if choose is None else int(choose(i, fwd.table(i), probs))
         log_qf += float(lw[j]) - lse
-        par, bl, ht = fwd[i]
+        par, _bl, ht = fwd.member(int(fwd.member_off[i]) + j)
         # materialised as the reference's rebuild(k) does (:1975-1986): lengths re-derived from the heights for
         # EVERY member -- also for the unchanged tree, whose stored lengths may disagree with its heights in the
         # last digits (it was SCORED with its stored lengths, :1828-1832)
-        new_trees.append(_member(gene_trees[i], par[j], _lengths_from_heights(par[j], ht[j])))
-        new_heights.append(ht[j].copy())
+        new_trees.append(_member(gene_trees[i], par, _lengths_from_heights(par, ht)))
+        new_heights.append(ht.copy())
     # ---- reverse: candidate sets of the chosen trees, scored under the reverse network
-    rev_info: List[dict] = [{} for _ in range(M)]
-    rev = [candidate_table(new_trees[i], new_heights[i], info=rev_info[i]) for i in range(M)]
-    rev_lw = _logweights(engine, [(i, (new_trees[i], rev[i][0], rev[i][1])) for i in range(M)], reverse_net, theta)
+    rev = CandidateBatch(new_trees, new_heights, context=ctx)
+    rev_lw = _logweights(engine, rev, loci, reverse_net, theta)
     log_qr = 0.0
     for i in range(M):
-        lw = rev_lw[i]
+        lw = rev_lw[int(rev.member_off[i]):int(rev.member_off[i + 1])]
         lse = _logsumexp(lw)
         if not math.isfinite(lse):
             return None
         # the member with the original's clades and (12-decimal) heights: the reference's signature match
-        match = find_member(rev_info[i], gene_trees[i].parent, heights[i])
+        match = find_member_in_batch(rev, i, gene_trees[i].parent, heights[i])
         if match < 0 or not math.isfinite(float(lw[match])):
             return None
         log_qr += float(lw[match]) - lse

@@ -27,16 +27,24 @@ class OracleEngine:
         self.model = O.gtr([0.1, 0.2, 0.3, 0.4], [1.0, 2.5, 0.7, 1.3, 3.1, 0.9])
         self.calls = 0
 
-    def score_candidate_sets(self, sets):
+    def score_batch(self, batch, loci):
         self.calls += 1
-        return [np.array([O.log_likelihood(self.loc[i], O.OracleTree(par[k].tolist(), [None if b != b else b for b in bl[k].tolist()],
-                                                                        base.label), self.model) for k in range(par.shape[0])])
-                for i, (base, par, bl) in sets]
+        out = np.empty(batch.n_members)
+        for m in range(batch.n_members):
+            j = int(batch.tree_of_member[m])
+            par, bl, _ = batch.member(m)
+            out[m] = O.log_likelihood(self.loc[loci[j]], O.OracleTree(par.tolist(), [None if b != b else b for b in bl.tolist()],
+                                                                      batch.trees[j].label), self.model)
+        return out
 
-    def msnc_candidate_sets(self, sets, net, theta):
+    def msnc_batch(self, batch, loci, net, theta):
         self.calls += 1
-        return [np.array([MO.msnc_log_density(net, par[k].tolist(), bl[k].tolist(), base.label, self.case["species_of"], theta)
-                          for k in range(par.shape[0])]) for i, (base, par, bl) in sets]
+        out = np.empty(batch.n_members)
+        for m in range(batch.n_members):
+            j = int(batch.tree_of_member[m])
+            par, bl, _ = batch.member(m)
+            out[m] = MO.msnc_log_density(net, par.tolist(), bl.tolist(), batch.trees[j].label, self.case["species_of"], theta)
+        return out
 
 
 def _describe(ft, h):
@@ -98,7 +106,7 @@ def test_candidate_table_extends_candidate_arrays():
 def test_declines_like_the_reference_when_nothing_has_weight():
     case = CASES[0]
     eng = OracleEngine(case)
-    eng.msnc_candidate_sets = lambda sets, net, theta: [np.full(par.shape[0], -np.inf) for _, (_, par, _) in sets]
+    eng.msnc_batch = lambda batch, loci, net, theta: np.full(batch.n_members, -np.inf)
     trees = [FlatTree(t["parent"], t["blen"], t["label"]) for t in case["trees"]]
     heights = [node_heights(t) for t in trees]
     assert CP.coupled_gene_tree_reproposal(eng, trees, heights, case["target"], case["reverse"], case["theta"],
