@@ -185,8 +185,8 @@ def candidate_table(ft: FlatTree, heights: np.ndarray = None, scales: Sequence[f
 
     * an NNI around ``v`` changes exactly one clade (``v``'s) and no height, so neighbours are told apart by
       (v, new clade of v) with clades as integer bit sets;
-    * scales are exact powers of two, so the lengths / heights of a scaled member are the base's times the scale,
-      bit for bit what re-deriving them from the scaled heights gives (``_sync_lengths`` on ``h * s``);
+    * the heights of a scaled member are the base's times the scale and its lengths are re-derived from them
+      (``_sync_lengths`` on ``h * s``), vectorised over the scales;
     * two scales of one base can only collide after rounding to 12 decimals if every internal height is ~0;
       only then are the rounded heights compared.
     """
@@ -250,9 +250,11 @@ def candidate_table(ft: FlatTree, heights: np.ndarray = None, scales: Sequence[f
     P = np.repeat(np.stack(base_parents), S, axis=0)
     H = np.tile(h[None, :] * sc[:, None], (B, 1))
     H[np.tile(sc == 1.0, B)] = h                   # scale 1 is the height vector itself (no multiplication)
-    L = np.empty((B * S, n), dtype=np.float64)
-    for b, q in enumerate(base_parents):
-        L[b * S:(b + 1) * S] = _lengths_from_heights(q, h)[None, :] * sc[:, None]
+    L = np.full((B * S, n), np.nan, dtype=np.float64)
+    Hs = H[:S]                                     # the S scaled height vectors (the same for every base)
+    for b, q in enumerate(base_parents):           # _sync_lengths on the scaled heights, for any scale
+        nz = q >= 0
+        L[b * S:(b + 1) * S, nz] = np.maximum(Hs[:, q[nz]] - Hs[:, nz], 0.0)
     ident = np.nonzero(sc == 1.0)[0]
     if ident.shape[0]:
         L[int(ident[0])] = ft.blen                 # the tree itself at scale 1: lengths untouched
