@@ -187,28 +187,99 @@ class SeqLikelihoodEngine:
             vec = self._shard.allreduce_sum(vec)
             self._felsen = [float(v) for v in vec]
         try:
-            if self._msnc_fn is None and species_net is None:
-                total = sum(self._felsen)  # C loop, locus order
-            elif self._msnc_fn is None:
-                self._fill_msnc(gene_trees, species_net, theta)
-                # two C-level sums instead of the reference's Python loop over loci (src/_mcmc_seq.py:745-761):
-                # at 10^3 loci that loop costs more than the device work of a single-locus move
-                total = sum(self._felsen) + sum(self._msnc)
-            else:
-                total = 0.0
-                for i in range(self.n_loci):  # reference loop, src/_mcmc_seq.py:745-761
-                    if self._msnc[i] is None:
-                        self._msnc[i] = float(self._msnc_fn(i, gene_trees[i], species_net, theta))
-                    total += self._felsen[i] + self._msnc[i]
+            return self._total(gene_trees, species_net, theta)
         except TypeError:
             # an entry is still None: it was invalidated without invalidate_locus() (a caller that shares
             # the list); recount the dirty set once and evaluate again
             if rescan:
                 raise
             return self.log_likelihood(gene_trees, species_net, theta, rescan=True)
+
+    def _total(self, gene_trees: Sequence[Any], species_net: Any, theta: float) -> float:
+        """The sum over loci once every ``_felsen`` entry is filled; fills the ``None`` entries of ``_msnc``."""
+        if self._msnc_fn is None and species_net is None:
+            total = sum(self._felsen)  # C loop, locus order
+        elif self._msnc_fn is None:
+            self._fill_msnc(gene_trees, species_net, theta)
+            # two C-level sums instead of the reference's Python loop over loci (src/_mcmc_seq.py:745-761):
+            # at 10^3 loci that loop costs more than the device work of a single-locus move
+            total = sum(self._felsen) + sum(self._msnc)
+        else:
+            total = 0.0
+            for i in range(self.n_loci):  # reference loop, src/_mcmc_seq.py:745-761
+                if self._msnc[i] is None:
+                    self._msnc[i] = float(self._msnc_fn(i, gene_trees[i], species_net, theta))
+                total += self._felsen[i] + self._msnc[i]
         if not math.isfinite(total):
             return float("-inf")
         return total
+
+    # -- several chains at once (MC3; SURVEY section 8f, rank 4) ----------------------------------------
+    @staticmethod
+    def log_likelihood_many(engines: Sequence["SeqLikelihoodEngine"], gene_trees: Sequence[Sequence[Any]],
+                            species_nets: Optional[Sequence[Any]] = None, thetas: Optional[Sequence[float]] = None
+                            ) -> List[float]:
+        """``log_likelihood`` of several engines -- the chains of a Metropolis-coupled run
+        (``src/_mcmc_seq.py:3584-3723``), or independent chains sharing one device -- with the dirty loci of ALL
+        of them in ONE ``pnb_eval``: per chain a gene-tree move dirties one locus, so T chains cost one launch and
+        one synchronisation instead of T.  Each engine keeps its own partials cache, pending / commit / rollback
+        state and scalar caches, exactly as if it had been evaluated alone (results are bit-identical).  The
+        engines must share context, model and numerical mode and be unsharded."""
+        T = len(engines)
+        if len(gene_trees) != T:
+            raise ValueError("log_likelihood_many: one gene-tree list per engine")
+        species_nets = [None] * T if species_nets is None else list(species_nets)
+        thetas = [0.0] * T if thetas is None else list(thetas)
+        if T == 0:
+            return []
+        e0 = engines[0]
+        ctx = e0._context()
+        for e in engines:
+            if e._shard.world_size != 1:
+                raise ValueError("log_likelihood_many: sharded engines are evaluated one by one")
+            if e._context() is not ctx or e._model is not e0._model or e._mode != e0._mode:
+                raise ValueError("log_likelihood_many: engines must share context, model and numerical mode")
+        owners: List[Tuple["SeqLikelihoodEngine", List[int]]] = []
+        flats: List[FlatTree] = []
+        rows: List[dict] = []
+        handles: List[np.ndarray] = []
+        full = False
+        for e, trees in zip(engines, gene_trees):
+            e._commit_pending()
+            dirty = sorted(i for i in e._dirty if e._felsen[i] is None)
+            e._dirty.clear()
+            full = full or e._full_next
+            e._full_next = False
+            owners.append((e, dirty))
+            for i in dirty:
+                flats.append(flatten(trees[i]))
+                rows.append(e._calcs[i]._row_of)
+            if dirty:
+                handles.append(e._handles(dirty))
+        if flats:
+            node_off, parent, blen, tip_row = pack_trees(flats, rows)
+            P_edge = _explicit_P_edges(e0._model, blen, 1.0) if _device_kind(e0._model) == "explicit" else None
+            flags = _lib.EVAL_PENDING | e0._mode | (_lib.EVAL_FULL if full else 0)
+            vals = ctx.eval(_model_handle(e0._model, ctx), np.concatenate(handles), node_off, parent, blen, tip_row,
+                            1.0, flags, P_edge)
+            stats = ctx.last_stats()
+            k = 0
+            for e, dirty in owners:
+                for i in dirty:
+                    e._felsen[i] = float(vals[k])
+                    k += 1
+                e._pending = list(dirty)
+                e.last_stats = stats
+        # every _felsen entry is filled and PENDING on the device; each engine adds its own MSNC factor and sums
+        # (not through log_likelihood(): that would commit what has just been evaluated)
+        out = []
+        for e, trees, net, th in zip(engines, gene_trees, species_nets, thetas):
+            try:
+                out.append(e._total(trees, net, th))
+            except TypeError as exc:
+                raise RuntimeError("log_likelihood_many: a cache entry was set to None without invalidate_locus(); "
+                                   "evaluate that engine with log_likelihood() once") from exc
+        return out
 
     # -- MSNC density on the device ----------------------------------------------------------------
     def _network(self, species_net: Any) -> SpeciesNetwork:

@@ -321,7 +321,6 @@ class CandidateBatch:
 
     def __init__(self, trees: Sequence[FlatTree], heights: Sequence[np.ndarray], scales: Sequence[float] = HEIGHT_SCALE_GRID,
                  context=None):
-        import ctypes as C
         from . import _lib
         lib = _lib.load()
         self.trees = list(trees)

@@ -165,7 +165,6 @@ def test_random_inputs_against_the_oracle():
 
 
 def test_frontier_ceiling_is_reported_not_silently_wrong():
-    import ctypes as C
     from phynetpy_b200 import _lib
     P = _pkg()
     case = next(c for c in CASES if c["name"] == "rand_n5_r2_a2")

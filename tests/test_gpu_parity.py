@@ -686,3 +686,66 @@ def test_cfg5_shape_batch_split_invariance():
     for i in (3, 150):
         exp = O.log_likelihood(O.OracleLocus(S.to_alignment_dict(aln[i])), _otree(trees[i]), om)
         assert rel_err(whole[i], exp) <= REL
+
+
+def test_several_engines_in_one_device_call():
+    """MC3 / several chains on one device: the dirty loci of all engines go out in ONE pnb_eval; values, pending
+    state, commit and rollback behave exactly as for engines evaluated one by one (reference MC3 loop
+    src/_mcmc_seq.py:3584-3723 evaluates its chains one after the other)."""
+    from phynetpy_b200 import simulate as S
+    P = _pkg()
+    rng = np.random.default_rng(31)
+    M, n, L, T = 12, 9, 150, 3
+    par, bl = S.random_trees(M, n, rng)
+    aln = S.simulate_alignments(par, bl, L, S.DEFAULT_PI, S.DEFAULT_RATES, rng)
+    loci = [S.to_alignment_dict(aln[i]) for i in range(M)]
+    model = P.GTR(S.DEFAULT_PI, S.DEFAULT_RATES)
+    chains = [P.SeqLikelihoodEngine(loci, None, model) for _ in range(T)]
+    solo = [P.SeqLikelihoodEngine(loci, None, model) for _ in range(T)]
+    # every chain has its own gene trees
+    trees = []
+    for c in range(T):
+        p2, b2 = S.random_trees(M, n, rng)
+        trees.append(S.flat_trees(p2, b2))
+    many = P.SeqLikelihoodEngine.log_likelihood_many(chains, trees)
+    assert chains[0].last_stats["launches"] <= 2                     # one evaluation for 3 x 12 loci
+    one = [solo[c].log_likelihood(trees[c], None, 0.0) for c in range(T)]
+    assert many == one
+    assert [e._felsen for e in chains] == [e._felsen for e in solo]
+    # one gene-tree move per chain, different loci: accept in chain 0 and 2, reject in chain 1
+    new = [list(t) for t in trees]
+    moved = [2, 7, 11]
+    for c in range(T):
+        b = trees[c][moved[c]].blen.copy()
+        b[0] *= 1.5
+        new[c][moved[c]] = trees[c][moved[c]].with_lengths(b)
+    snaps = [e.clone_caches() for e in chains]
+    ssnaps = [e.clone_caches() for e in solo]
+    for c in range(T):
+        chains[c].invalidate_locus(moved[c])
+        solo[c].invalidate_locus(moved[c])
+    many2 = P.SeqLikelihoodEngine.log_likelihood_many(chains, new)
+    one2 = [solo[c].log_likelihood(new[c], None, 0.0) for c in range(T)]
+    assert many2 == one2 and many2 != many
+    assert chains[0].last_stats["nodes_recomputed"] <= 3 * (n - 1)      # dirty paths only, all chains together
+    chains[1].restore_caches(snaps[1])
+    solo[1].restore_caches(ssnaps[1])
+    cur = [new[0], trees[1], new[2]]
+    many3 = P.SeqLikelihoodEngine.log_likelihood_many(chains, cur)
+    one3 = [solo[c].log_likelihood(cur[c], None, 0.0) for c in range(T)]
+    assert many3 == one3 and many3[1] == many[1] and many3[0] == many2[0]
+    # the rejected proposal left no trace on the device: re-proposing it recomputes the same value
+    chains[1].invalidate_locus(moved[1])
+    again = P.SeqLikelihoodEngine.log_likelihood_many(chains, new)
+    assert again == many2
+    # a full recomputation of every chain agrees bit for bit
+    for c in range(T):
+        for i in range(M):
+            chains[c].invalidate_locus(i)
+        chains[c].invalidate_device_cache()
+    assert P.SeqLikelihoodEngine.log_likelihood_many(chains, new) == many2
+    with pytest.raises(ValueError, match="one gene-tree list per engine"):
+        P.SeqLikelihoodEngine.log_likelihood_many(chains, new[:2])
+    other = P.SeqLikelihoodEngine(loci, None, P.JC69())
+    with pytest.raises(ValueError, match="share context, model"):
+        P.SeqLikelihoodEngine.log_likelihood_many([chains[0], other], [new[0], new[0]])
