@@ -26,7 +26,7 @@ from phynetpy.GraphUtils import _node_heights  # noqa: E402
 from phynetpy.Network import Network  # noqa: E402
 from phynetpy.models import BranchLengthUnit  # noqa: E402
 
-from make_golden_msnc import enewick, export_gene_tree, export_network, random_network  # noqa: E402
+from make_golden_msnc import add_reticulation, enewick, export_gene_tree, export_network, random_network  # noqa: E402
 
 UNIT = BranchLengthUnit.SUBSTITUTIONS_PER_SITE
 PI, RATES = [0.1, 0.2, 0.3, 0.4], [1.0, 2.5, 0.7, 1.3, 3.1, 0.9]
@@ -64,37 +64,7 @@ def main():
         nodes2 = [list(x) for x in nodes]
         edges2 = [list(x) for x in edges]
 
-        def add_retic(nodes, edges, rng, k=0):
-            def split(e, m, gamma_into_m):
-                p, c, g = edges[e]
-                edges[e] = [p, m, gamma_into_m]
-                edges.append([m, c, g])
-            for _ in range(500):
-                r = int(rng.integers(len(edges)))
-                d = int(rng.integers(len(edges)))
-                if r == d:
-                    continue
-                pr, cr, _ = edges[r]
-                pd, cd, _ = edges[d]
-                lo_r, hi_r = nodes[cr][1], nodes[pr][1]
-                if hi_r - lo_r < 1e-6:
-                    continue
-                th = float(rng.uniform(lo_r + 0.1 * (hi_r - lo_r), hi_r - 0.1 * (hi_r - lo_r)))
-                lo_d, hi_d = max(nodes[cd][1], th), nodes[pd][1]
-                if hi_d - lo_d < 1e-6:
-                    continue
-                tx = float(rng.uniform(lo_d + 0.05 * (hi_d - lo_d), hi_d - 0.05 * (hi_d - lo_d)))
-                g = float(rng.uniform(0.2, 0.8))
-                nodes.append(["#H%d" % k, th, True])
-                h = len(nodes) - 1
-                nodes.append(["x%d" % k, tx, False])
-                x = len(nodes) - 1
-                split(r, h, 1.0 - g)
-                split(d, x, None)
-                edges.append([x, h, g])
-                return
-            raise RuntimeError("could not place reticulation")
-        add_retic(nodes2, edges2, rng_net)
+        add_reticulation(nodes2, edges2, rng_net, 0, gamma_range=(0.2, 0.8))
         net_nw = enewick(nodes2, edges2)
         sp_tree = Network.from_newick(tree_nw, branch_length_unit=UNIT)
         sp_net = Network.from_newick(net_nw, branch_length_unit=UNIT)

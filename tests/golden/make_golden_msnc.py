@@ -5,6 +5,9 @@
 
     python tests/golden/make_golden_msnc.py   ->  tests/golden/msnc_cases.json
 
+(Node and edge numbering follow the reference's ``V()`` / ``E()``, sets of objects whose iteration order changes
+from run to run: a regenerated file holds the same cases in a different numbering.)
+
 Each case holds a species network as flat arrays read back from the reference's own
 ``_NetworkIndex`` (edge order, reticulation flags, gammas, node heights), a batch of gene trees
 as flat parent / length / label arrays (reference ``V()`` order), the allele -> species map,
@@ -51,40 +54,44 @@ def random_network(n_leaves, n_retic, rng, height=0.05):
         v = len(nodes) - 1
         edges += [[v, a, None], [v, b, None]]
         live.append(v)
+    for k in range(n_retic):
+        add_reticulation(nodes, edges, rng, k)
+    return nodes, edges
+
+
+def add_reticulation(nodes, edges, rng, k=0, gamma_range=(0.1, 0.9)):
+    """Insert hybrid node #Hk on a random recipient edge and its second parent xk on a donor edge at or above it."""
     def split(e, m, gamma_into_m):
         # p -> c becomes p -> m -> c; a gamma on p -> c (c is a reticulation) stays on the half into c
         p, c, g = edges[e]
         edges[e] = [p, m, gamma_into_m]
         edges.append([m, c, g])
 
-    for k in range(n_retic):
-        for _ in range(500):
-            r = int(rng.integers(len(edges)))
-            d = int(rng.integers(len(edges)))
-            if r == d:
-                continue
-            pr, cr, _ = edges[r]
-            pd, cd, _ = edges[d]
-            lo_r, hi_r = nodes[cr][1], nodes[pr][1]
-            if hi_r - lo_r < 1e-6:
-                continue
-            th = float(rng.uniform(lo_r + 0.1 * (hi_r - lo_r), hi_r - 0.1 * (hi_r - lo_r)))
-            lo_d, hi_d = max(nodes[cd][1], th), nodes[pd][1]
-            if hi_d - lo_d < 1e-6:
-                continue
-            tx = float(rng.uniform(lo_d + 0.05 * (hi_d - lo_d), hi_d - 0.05 * (hi_d - lo_d)))
-            g = float(rng.uniform(0.1, 0.9))
-            nodes.append(["#H%d" % k, th, True])
-            h = len(nodes) - 1
-            nodes.append(["x%d" % k, tx, False])
-            x = len(nodes) - 1
-            split(r, h, 1.0 - g)        # recipient edge: pr -> H -> cr
-            split(d, x, None)           # donor edge:     pd -> X -> cd
-            edges.append([x, h, g])     # hybrid edge X -> H
-            break
-        else:
-            raise RuntimeError("could not place reticulation")
-    return nodes, edges
+    for _ in range(500):
+        r = int(rng.integers(len(edges)))
+        d = int(rng.integers(len(edges)))
+        if r == d:
+            continue
+        pr, cr, _ = edges[r]
+        pd, cd, _ = edges[d]
+        lo_r, hi_r = nodes[cr][1], nodes[pr][1]
+        if hi_r - lo_r < 1e-6:
+            continue
+        th = float(rng.uniform(lo_r + 0.1 * (hi_r - lo_r), hi_r - 0.1 * (hi_r - lo_r)))
+        lo_d, hi_d = max(nodes[cd][1], th), nodes[pd][1]
+        if hi_d - lo_d < 1e-6:
+            continue
+        tx = float(rng.uniform(lo_d + 0.05 * (hi_d - lo_d), hi_d - 0.05 * (hi_d - lo_d)))
+        g = float(rng.uniform(*gamma_range))
+        nodes.append(["#H%d" % k, th, True])
+        h = len(nodes) - 1
+        nodes.append(["x%d" % k, tx, False])
+        x = len(nodes) - 1
+        split(r, h, 1.0 - g)        # recipient edge: pr -> H -> cr
+        split(d, x, None)           # donor edge:     pd -> X -> cd
+        edges.append([x, h, g])     # hybrid edge X -> H
+        return
+    raise RuntimeError("could not place reticulation")
 
 
 def enewick(nodes, edges):
