@@ -363,3 +363,55 @@ def test_abi_compiles_networks_on_a_host_context_and_refuses_to_evaluate():
         assert rc == _lib.PNB_ERR_INVALID and b"no root" in lib.pnb_last_error()
     finally:
         lib.pnb_ctx_destroy(ctx)
+
+
+def test_stress_own_generators_against_oracle(harness):
+    """Networks and gene trees from the package's own generators (several alleles per species, up to four
+    reticulations, frontiers of hundreds of entries with many merges): the kernel's DP source vs the oracle."""
+    from phynetpy_b200 import simulate as S
+    rng = np.random.default_rng(123)
+    n_checked, max_frontier_seen = 0, 0
+    for n_species, n_retic, alleles, n_trees in [(4, 1, 3, 6), (5, 2, 2, 6), (6, 3, 1, 8), (7, 4, 1, 6), (3, 2, 3, 6), (9, 0, 3, 4),
+                                                 (6, 2, 2, 5)]:
+        net = S.random_species_network(n_species, n_retic, rng)
+        trees, species_of = S.simulate_gene_trees_msnc(net, alleles, 0.03, rng, n_trees)
+        # half of the trees get perturbed heights: some stop embedding
+        flats = []
+        for k, t in enumerate(trees):
+            flats.append(t if k % 2 == 0 else t.with_lengths(t.blen * float(rng.uniform(0.6, 1.4))))
+        off = np.zeros(len(flats) + 1, np.int64)
+        np.cumsum([t.n_nodes for t in flats], out=off[1:])
+        par = np.concatenate([t.parent for t in flats]).astype(np.int32)
+        bl = np.concatenate([t.blen for t in flats])
+        sp = np.concatenate([net.species_ids_of(t, species_of) for t in flats]).astype(np.int32)
+        rc, out, info, err = _run_harness(harness, net, off, par, bl, sp, 0.03, cap=1 << 14)
+        assert rc == 0 and info[2] == 0, err
+        d = net.to_dict()
+        for t, got in zip(flats, out):
+            want = MO.msnc_log_density(d, t.parent.tolist(), t.blen.tolist(), t.label, species_of, 0.03)
+            assert _close(got, want), (n_species, n_retic, alleles, got, want)
+            n_checked += 1
+    assert n_checked >= 40
+
+
+def test_tied_event_times_keep_node_order(harness):
+    """Equal coalescence times (a zero-length internal branch): events are sorted stably, i.e. ties stay in node
+    order -- the reference's ``events.sort(key=time)`` over its node order (src/_msnc_density.py:150-169)."""
+    net = SpeciesNetwork.from_newick("((A:0.01,B:0.01)ab:0.02,C:0.03)r;")
+    so = {"A": "A", "B": "B", "C": "C"}
+    # node 3 = (A,B) at height 0.05, node 4 = root also at 0.05 (zero-length branch above node 3): child listed first
+    child_first = FlatTree([3, 3, 4, 4, -1], [0.05, 0.05, 0.05, 0.0, None], ["A", "B", "C", None, None])
+    # the same tree with the root listed BEFORE its child: the tie now puts the parent's event first
+    parent_first = FlatTree([4, 4, 3, -1, 3], [0.05, 0.05, 0.05, None, 0.0], ["A", "B", "C", None, None])
+    for ft in (child_first, parent_first):
+        off = np.array([0, ft.n_nodes], np.int64)
+        sp = net.species_ids_of(ft, so)
+        rc, out, info, err = _run_harness(harness, net, off, ft.parent, ft.blen, sp, 0.02)
+        assert rc == 0, err
+        want = MO.msnc_log_density(net.to_dict(), ft.parent.tolist(), ft.blen.tolist(), ft.label, so, 0.02)
+        assert _close(out[0], want)
+    # with the parent's event first the two root children are not both present yet: no embedding
+    off = np.array([0, 5], np.int64)
+    a = _run_harness(harness, net, off, child_first.parent, child_first.blen, net.species_ids_of(child_first, so), 0.02)[1][0]
+    b = _run_harness(harness, net, off, parent_first.parent, parent_first.blen, net.species_ids_of(parent_first, so), 0.02)[1][0]
+    assert math.isfinite(a) and b == -math.inf
