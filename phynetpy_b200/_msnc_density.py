@@ -75,6 +75,18 @@ class SpeciesNetwork:
         """From the layout of ``tests/golden/msnc_cases.json`` (``network`` entries)."""
         return cls(d["edge_src"], d["edge_dst"], d["edge_gamma"], d["height"], d["leaf_label"], d.get("node_label"))
 
+    def replaced(self, height: Optional[np.ndarray] = None, edge_gamma: Optional[np.ndarray] = None) -> "SpeciesNetwork":
+        """A new network with other node heights and / or inheritance probabilities, same topology and labels
+        (what a height or gamma move of the sampler produces; the old object stays untouched)."""
+        n = SpeciesNetwork.__new__(SpeciesNetwork)
+        n.__dict__.update(self.__dict__)
+        n.height = self.height if height is None else np.ascontiguousarray(height, dtype=np.float64)
+        n.edge_gamma = self.edge_gamma if edge_gamma is None else np.ascontiguousarray(edge_gamma, dtype=np.float64)
+        n._handles = {}
+        if n.height.shape != self.height.shape or n.edge_gamma.shape != self.edge_gamma.shape:
+            raise ValueError("SpeciesNetwork.replaced: array shapes must not change")
+        return n
+
     def to_dict(self) -> dict:
         """The layout :meth:`from_dict` reads (plain lists; ``None`` for an absent gamma)."""
         return {"n_nodes": self.n_nodes, "edge_src": self.edge_src.tolist(), "edge_dst": self.edge_dst.tolist(),

@@ -24,11 +24,18 @@ Random numbers are drawn in the reference's order (node choice, then the uniform
 ``net.V()``, a hash-ordered set whose order changes from clone to clone, here nodes are enumerated by
 index -- the distributions are identical, the streams are not comparable.  The deterministic halves
 (:func:`slide_node`, :func:`nni_swap`) are what the golden vectors pin.
+
+The parameter moves of the species network have flat twins too -- :func:`net_slide_height_move`
+(``op_net_node_height``, ``:993-1017``; the same ``_slide_height_move`` on the network, a reticulation being bounded
+by BOTH parents), :func:`gamma_move` (``op_change_gamma``, ``:909-953``) and :func:`theta_move`
+(``op_change_theta``, ``:886-906``) -- each returning a fresh :class:`~phynetpy_b200._msnc_density.SpeciesNetwork`
+(or theta) so that the engine's identity-keyed network cache sees a genuine change.  The dimension-changing
+moves (add / delete / relocate reticulation) stay with the sampler; their gene-tree half is ``coupled.py``.
 """
 from __future__ import annotations
 
 import math
-from typing import List, Optional, Tuple
+from typing import Any, List, Optional, Tuple
 
 import numpy as np
 
@@ -143,3 +150,88 @@ def nni_move(ft: FlatTree, h: np.ndarray, rng: np.random.Generator) -> Optional[
     if t is None:
         return None
     return t, h
+
+
+# ---------------------------------------------------------------------------------------------------
+# species-network parameter moves
+# ---------------------------------------------------------------------------------------------------
+def theta_move(theta: float, rng: np.random.Generator, window: float = 0.4) -> Tuple[float, float]:
+    """``op_change_theta``: ``theta * f`` with ``f = exp(window (u - 1/2))``; returns ``(theta', log f)``."""
+    f = math.exp(window * (float(rng.random()) - 0.5))
+    return theta * f, math.log(f)
+
+
+def net_slide_candidates(net: Any) -> np.ndarray:
+    """Non-root internal network nodes in index order, then the root."""
+    n = net.n_nodes
+    out_deg = np.bincount(net.edge_src, minlength=n)
+    in_deg = np.bincount(net.edge_dst, minlength=n)
+    internal = np.nonzero((out_deg > 0) & (in_deg > 0))[0]
+    root = np.nonzero(in_deg == 0)[0][:1]
+    return np.concatenate([internal, root]).astype(np.int64)
+
+
+def net_slide_node(net: Any, node: int, u: float, root_scale_window: float = 0.3) -> Optional[Tuple[Any, float]]:
+    """The deterministic half of ``op_net_node_height``: ``node`` slides uniformly between its tallest child and its
+    LOWEST parent (a reticulation has two), the root is scaled; ``None`` when the move is impossible."""
+    h = net.height
+    kids = net.edge_dst[net.edge_src == node]
+    parents = net.edge_src[net.edge_dst == node]
+    lower = float(h[kids].max()) if kids.shape[0] else 0.0
+    h2 = h.copy()
+    if parents.shape[0] == 0:
+        f = math.exp(root_scale_window * (u - 0.5))
+        new_h = float(h[node]) * f
+        if new_h <= lower:
+            return None
+        h2[node] = new_h
+        return net.replaced(height=h2), math.log(f)
+    upper = float(h[parents].min())
+    if upper <= lower:
+        return None
+    h2[node] = lower + (upper - lower) * u
+    return net.replaced(height=h2), 0.0
+
+
+def net_slide_height_move(net: Any, rng: np.random.Generator, root_scale_window: float = 0.3) -> Optional[Tuple[Any, float]]:
+    """``op_net_node_height`` without the graph: returns the proposed ``(network, log HR)``."""
+    cands = net_slide_candidates(net)
+    if cands.shape[0] == 0:
+        return None
+    node = int(cands[int(rng.integers(cands.shape[0]))])
+    return net_slide_node(net, node, float(rng.random()), root_scale_window)
+
+
+def reticulations(net: Any) -> np.ndarray:
+    return np.nonzero(np.bincount(net.edge_dst, minlength=net.n_nodes) >= 2)[0].astype(np.int64)
+
+
+def gamma_move_at(net: Any, retic: int, u: float, window: float = 0.2, first_edge: Optional[int] = None) -> Any:
+    """The deterministic half of ``op_change_gamma``: the inheritance probability of one parent edge of ``retic``
+    (``first_edge``, by default the first in edge order) takes a step ``window (u - 1/2)``, reflected into (0, 1);
+    the other parent edge gets the complement."""
+    edges = np.nonzero(net.edge_dst == retic)[0]
+    if edges.shape[0] < 2:
+        raise ValueError("gamma_move_at: node %d is not a reticulation" % retic)
+    e0 = int(edges[0]) if first_edge is None else int(first_edge)
+    e1 = int(edges[1]) if e0 == int(edges[0]) else int(edges[0])
+    g = float(net.edge_gamma[e0])
+    g_new = g + window * (u - 0.5)
+    while g_new <= 0.0 or g_new >= 1.0:
+        if g_new <= 0.0:
+            g_new = -g_new
+        if g_new >= 1.0:
+            g_new = 2.0 - g_new
+    gam = net.edge_gamma.copy()
+    gam[e0] = float(g_new)
+    gam[e1] = float(1.0 - g_new)
+    return net.replaced(edge_gamma=gam)
+
+
+def gamma_move(net: Any, rng: np.random.Generator, window: float = 0.2) -> Optional[Tuple[Any, float]]:
+    """``op_change_gamma`` without the graph (symmetric: log HR 0); ``None`` for a tree."""
+    rets = reticulations(net)
+    if rets.shape[0] == 0:
+        return None
+    r = int(rets[int(rng.integers(rets.shape[0]))])
+    return gamma_move_at(net, r, float(rng.random()), window), 0.0

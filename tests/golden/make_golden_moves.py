@@ -28,6 +28,7 @@ from phynetpy.models import BranchLengthUnit  # noqa: E402
 
 from phynetpy_b200 import simulate as S  # noqa: E402  (input generator only)
 from make_golden_candidates import newick  # noqa: E402
+from make_golden_msnc import enewick, export_network, random_network  # noqa: E402
 
 UNIT = BranchLengthUnit.SUBSTITUTIONS_PER_SITE
 
@@ -74,6 +75,65 @@ class _State:
         self.gt_heights = [_node_heights(gt)]
 
 
+class _NetEngine(_Engine):
+    def invalidate_network(self):
+        pass
+
+
+class _NetState:
+    def __init__(self, net):
+        self._engine = _NetEngine()
+        self.species_net = net
+        self.net_heights = _node_heights(net)
+
+
+def network_cases(rng0):
+    """Species-network parameter moves: _slide_height_move on networks (op_net_node_height) and op_change_gamma."""
+    out = []
+    for n_leaves, n_retic in ((4, 1), (6, 2), (8, 3), (5, 0)):
+        nodes, edges = random_network(n_leaves, n_retic, rng0, height=0.08)
+        nw = enewick(nodes, edges)
+        net = Network.from_newick(nw, branch_length_unit=UNIT)
+        slides = []
+        for seed in range(50):
+            work = _clone_net(net)
+            heights = _node_heights(work)
+            cands = M._internal_nodes(work) + [work.root()]
+            replay = np.random.default_rng(seed)
+            k = int(replay.integers(len(cands)))
+            u = float(replay.random())
+            loghr = M._slide_height_move(work, heights, np.random.default_rng(seed), 0.3)
+            rec = {"seed": seed, "n_candidates": len(cands), "node": cands[k].label, "u": u}
+            rec["result"] = None if loghr is None else {"height": float(heights[cands[k]]), "loghr": float(loghr)}
+            slides.append(rec)
+        gammas = []
+        for seed in range(30 if n_retic else 2):
+            st = _NetState(net)
+            rets = [v for v in net.V() if v.is_reticulation()]
+            res = M.op_change_gamma(st, np.random.default_rng(seed), window=0.6)
+            if not rets:
+                gammas.append({"seed": seed, "result": None})
+                assert res is None
+                continue
+            replay = np.random.default_rng(seed)
+            replay.integers(len(rets))
+            u = float(replay.random())
+            new = st.species_net
+            changed = None
+            for v in new.V():
+                if not v.is_reticulation():
+                    continue
+                old_v = [x for x in net.V() if x.label == v.label][0]
+                g_new = {e.src.label: float(e.get_gamma()) for e in new.in_edges(v)}
+                g_old = {e.src.label: float(e.get_gamma()) for e in net.in_edges(old_v)}
+                if g_new != g_old:
+                    changed = {"retic": v.label, "old": g_old, "new": g_new}
+            gammas.append({"seed": seed, "u": u, "window": 0.6, "n_reticulations": len(rets), "result": changed})
+        out.append({"name": "net_n%d_r%d" % (n_leaves, n_retic), "newick": nw, "network": export_network(net),
+                    "slides": slides, "gammas": gammas})
+    return out
+
+
 def main():
     rng0 = np.random.default_rng(77)
     cases = []
@@ -116,9 +176,11 @@ def main():
         cases.append({"name": "n%d" % n, "parent": par[0].tolist(), "blen": [None if b != b else b for b in bl[0].tolist()],
                       "label": label, "slides": slides, "nni_outcomes": list(outcomes.values()),
                       "nni_rejected": rejected, "nni_runs": n_runs})
+    nets = network_cases(rng0)
     out = os.path.join(HERE, "moves_cases.json")
     with open(out, "w") as f:
-        json.dump({"source": "PhyNetPy v0.6.0 _slide_height_move / op_gene_tree_nni", "cases": cases}, f)
+        json.dump({"source": "PhyNetPy v0.6.0 _slide_height_move / op_gene_tree_nni / op_change_gamma", "cases": cases,
+                   "network_cases": nets}, f)
     print("wrote %s: %d trees, %d slide records, %d distinct NNI outcomes" % (
         out, len(cases), sum(len(c["slides"]) for c in cases), sum(len(c["nni_outcomes"]) for c in cases)))
 

@@ -138,3 +138,87 @@ def test_draw_order_follows_the_reference():
         r2.integers(int((ft.parent == v).sum()))
     r2.integers(len(el))
     assert r1.random() == r2.random()
+
+
+# ---------------------------------------------------------------------------------------------------
+# species-network parameter moves
+# ---------------------------------------------------------------------------------------------------
+NET_CASES = json.load(open(os.path.join(HERE, "golden", "moves_cases.json")))["network_cases"]
+
+
+@pytest.mark.parametrize("case", NET_CASES, ids=[c["name"] for c in NET_CASES])
+def test_network_height_slide_reproduces_the_reference(case):
+    from phynetpy_b200._msnc_density import SpeciesNetwork
+    net = SpeciesNetwork.from_dict(case["network"])
+    label = net.node_label
+    cands = MV.net_slide_candidates(net)
+    for rec in case["slides"]:
+        assert rec["n_candidates"] == cands.shape[0]
+        node = label.index(rec["node"])
+        assert node in cands.tolist()
+        out = MV.net_slide_node(net, node, rec["u"])
+        if rec["result"] is None:
+            assert out is None
+            continue
+        new, loghr = out
+        assert new is not net and float(new.height[node]) == rec["result"]["height"] and loghr == rec["result"]["loghr"]
+        assert np.array_equal(np.delete(new.height, node), np.delete(net.height, node))
+        assert np.array_equal(new.edge_gamma, net.edge_gamma, equal_nan=True) and new.species == net.species
+        # a reticulation never rises above its LOWER parent
+        parents = net.edge_src[net.edge_dst == node]
+        if parents.shape[0] == 2:
+            assert new.height[node] < net.height[parents].min()
+
+
+@pytest.mark.parametrize("case", NET_CASES, ids=[c["name"] for c in NET_CASES])
+def test_gamma_move_reproduces_the_reference(case):
+    from phynetpy_b200._msnc_density import SpeciesNetwork
+    net = SpeciesNetwork.from_dict(case["network"])
+    label = net.node_label
+    rets = MV.reticulations(net)
+    for rec in case["gammas"]:
+        if rec["result"] is None:
+            assert rets.shape[0] == 0 and MV.gamma_move(net, np.random.default_rng(rec["seed"])) is None
+            continue
+        assert rec["n_reticulations"] == rets.shape[0]
+        r = label.index(rec["result"]["retic"])
+        edges = np.nonzero(net.edge_dst == r)[0]
+        by_parent = {label[int(net.edge_src[e])]: int(e) for e in edges}
+        assert {p: float(net.edge_gamma[e]) for p, e in by_parent.items()} == rec["result"]["old"]
+        # the reference steps the gamma of whichever in-edge its (unordered) edge set lists first: try both
+        outcomes = []
+        for first in edges.tolist():
+            new = MV.gamma_move_at(net, r, rec["u"], rec["window"], first_edge=first)
+            outcomes.append({p: float(new.edge_gamma[e]) for p, e in by_parent.items()})
+            others = np.ones(net.edge_gamma.shape[0], bool)
+            others[edges] = False
+            assert np.array_equal(new.edge_gamma[others], net.edge_gamma[others], equal_nan=True)
+            assert sum(outcomes[-1].values()) == pytest.approx(1.0, abs=1e-15) and all(0 < g < 1 for g in outcomes[-1].values())
+        assert rec["result"]["new"] in outcomes
+
+
+def test_network_moves_feed_the_oracle_density_consistently():
+    """A moved network is a valid network: the density of a gene tree changes continuously with a small slide and
+    the old object is untouched."""
+    from oracle import msnc_oracle as MO
+    from phynetpy_b200 import simulate as S
+    rng = np.random.default_rng(9)
+    net = S.random_species_network(6, 2, rng)
+    trees, species_of = S.simulate_gene_trees_msnc(net, 1, 0.02, rng, 3)
+    h0, g0 = net.height.copy(), net.edge_gamma.copy()
+    base = [MO.msnc_log_density(net.to_dict(), t.parent.tolist(), t.blen.tolist(), t.label, species_of, 0.02) for t in trees]
+    n_moved = 0
+    for step in range(40):
+        out = MV.net_slide_height_move(net, rng) if step % 2 else MV.gamma_move(net, rng)
+        if out is None:
+            continue
+        new, loghr = out
+        assert math.isfinite(loghr) and new is not net
+        assert (new.height[new.edge_src] >= new.height[new.edge_dst]).all()           # still time-consistent
+        d = [MO.msnc_log_density(new.to_dict(), t.parent.tolist(), t.blen.tolist(), t.label, species_of, 0.02) for t in trees]
+        assert all(math.isfinite(x) or x == -math.inf for x in d)
+        n_moved += 1
+    assert n_moved > 20
+    assert np.array_equal(net.height, h0) and np.array_equal(net.edge_gamma, g0, equal_nan=True)
+    th, lh = MV.theta_move(0.02, np.random.default_rng(1))
+    assert th == 0.02 * math.exp(lh) and abs(lh) <= 0.2
