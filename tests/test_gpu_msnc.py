@@ -244,3 +244,29 @@ def test_engine_adds_the_coalescent_factor():
                                 case["theta"])
         assert _close(float(res[0][k]), w)
     assert _close(float(res[1][0]), want_msnc[2]) and res[1][0] == res[1][1]
+
+
+def test_moved_networks_are_scored_like_fresh_ones():
+    """Parameter moves of the species network (moves.net_slide_height_move / gamma_move) return a new flat
+    network; its device handle is built on first use and the density follows the oracle."""
+    from phynetpy_b200 import moves as MV, simulate as S
+    P = _pkg()
+    rng = np.random.default_rng(12)
+    net = S.random_species_network(7, 2, rng)
+    trees, species_of = S.simulate_gene_trees_msnc(net, 1, 0.02, rng, 12)
+    cur, n_moved = net, 0
+    for step in range(12):
+        out = MV.net_slide_height_move(cur, rng) if step % 2 else MV.gamma_move(cur, rng)
+        if out is None:
+            continue
+        cur = out[0]
+        n_moved += 1
+        got = P.msnc_log_density_batch(trees, cur, species_of, 0.02)
+        d = cur.to_dict()
+        for t, g in zip(trees, got):
+            assert _close(float(g), MO.msnc_log_density(d, t.parent.tolist(), t.blen.tolist(), t.label, species_of, 0.02))
+    assert n_moved >= 8
+    base = P.msnc_log_density_batch(trees, net, species_of, 0.02)       # the original network is untouched
+    d0 = net.to_dict()
+    for t, g in zip(trees, base):
+        assert _close(float(g), MO.msnc_log_density(d0, t.parent.tolist(), t.blen.tolist(), t.label, species_of, 0.02))
