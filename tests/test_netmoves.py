@@ -1,0 +1,130 @@
+"""Reticulation surgery and the placement scan of the informed add / delete moves on flat networks
+(phynetpy_b200/netmoves.py) against the reference (tests/golden/netmoves_cases.json, prior patched to 0).  Host
+logic; the densities come from the oracle here and from one ``pnb_msnc_eval`` per candidate network in production."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle import msnc_oracle as MO
+from phynetpy_b200 import netmoves as NM
+from phynetpy_b200._msnc_density import SpeciesNetwork
+from phynetpy_b200.candidates import HEIGHT_SCALE_GRID
+from phynetpy_b200.tree import FlatTree
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CASES = json.load(open(os.path.join(HERE, "golden", "netmoves_cases.json")))["cases"]
+
+
+def _labels(net, e):
+    return [net.node_label[int(net.edge_src[e])], net.node_label[int(net.edge_dst[e])]]
+
+
+def _canonical(net):
+    return {"nodes": sorted([net.node_label[v], float(net.height[v])] for v in range(net.n_nodes)),
+            "edges": sorted([net.node_label[int(s)], net.node_label[int(d)], None if g != g else float(g)]
+                            for s, d, g in zip(net.edge_src, net.edge_dst, net.edge_gamma.tolist()))}
+
+
+def _density_fn(case, scaled):
+    def fn(cand):
+        d = cand.to_dict()
+        return np.array([MO.msnc_log_density(d, t.parent.tolist(), t.blen.tolist(), t.label, case["species_of"], case["theta"])
+                         for t in scaled])
+    return fn
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_geometric_placements_equal_the_reference(case):
+    net = SpeciesNetwork.from_dict(case["network"])
+    mine = sorted([_labels(net, d), _labels(net, r)] for d, r in NM.geometric_placements(net))
+    assert mine == sorted(case["geometric"])
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_scored_placements_equal_the_reference(case):
+    net = SpeciesNetwork.from_dict(case["network"])
+    trees = [FlatTree(t["parent"], t["blen"], t["label"]) for t in case["trees"]]
+    scaled = NM.scaled_gene_trees(trees)
+    assert len(scaled) == len(trees) * len(HEIGHT_SCALE_GRID)
+    fn = _density_fn(case, scaled)
+    # the score of the network itself (reference _network_only_log_score with the prior at 0)
+    assert NM.network_only_msnc_score(fn(net), len(HEIGHT_SCALE_GRID)) == pytest.approx(case["base_score"], rel=1e-12)
+    got = NM.add_reticulation_placements(net, fn, len(HEIGHT_SCALE_GRID))
+    mine = {(tuple(_labels(net, p["donor_edge"])), tuple(_labels(net, p["retic_edge"]))): p for p in got}
+    ref = {(tuple(p["donor"]), tuple(p["retic"])): p for p in case["placements"]}
+    assert set(mine) == set(ref)
+    for k, p in ref.items():
+        assert mine[k]["l2"] == pytest.approx(p["l2"], rel=1e-13)
+        assert mine[k]["s_rep"] == pytest.approx(p["s_rep"], rel=1e-11)
+    # the selection the add move makes from these scores
+    s = np.array([p["s_rep"] for p in got])
+    lse = s.max() + math.log(np.exp(s - s.max()).sum())
+    assert abs(np.exp(s - lse).sum() - 1.0) < 1e-12
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c["deletes"]], ids=[c["name"] for c in CASES if c["deletes"]])
+def test_delete_surgery_equals_the_reference(case):
+    net = SpeciesNetwork.from_dict(case["network"])
+    lab = net.node_label
+    for d in case["deletes"]:
+        out = NM.remove_reticulation(net, lab.index(d["retic"]), lab.index(d["donor_parent"]))
+        if d["result"] is None:
+            assert out is None
+            continue
+        assert out is not None
+        got = _canonical(out)
+        assert got["nodes"] == [[a, pytest.approx(b, abs=1e-15)] for a, b in d["result"]["nodes"]]
+        assert got["edges"] == d["result"]["edges"]
+        assert out.n_reticulations() == net.n_reticulations() - 1 and NM.is_acyclic(out) and not NM.has_parallel_edges(out)
+
+
+def test_insert_then_remove_is_the_identity():
+    rng = np.random.default_rng(3)
+    for case in CASES:
+        net = SpeciesNetwork.from_dict(case["network"])
+        base = _canonical(net)
+        done = 0
+        for d, r in NM.geometric_placements(net):
+            rep = NM.representative_placement(net, d, r)
+            if rep is None:
+                continue
+            cand, l2 = rep
+            assert cand.n_nodes == net.n_nodes + 2 and cand.n_reticulations() == net.n_reticulations() + 1
+            assert (cand.height[cand.edge_src] >= cand.height[cand.edge_dst]).all()
+            v1, v2 = net.n_nodes, net.n_nodes + 1
+            back = NM.remove_reticulation(cand, v2, v1)
+            if back is None:
+                continue
+            got = _canonical(back)
+            # gammas: a split drops the inheritance probability of the edge it splits (as the reference does), so
+            # compare topology and heights, and the gammas wherever the original edge was not split
+            assert got["nodes"] == base["nodes"]
+            assert sorted(e[:2] for e in got["edges"]) == sorted(e[:2] for e in base["edges"])
+            done += 1
+        assert done >= 4
+    assert NM.insert_reticulation(net, 0, 0, 0.1, 0.05, 0.5) is None
+
+
+def test_device_density_fn_plumbing(monkeypatch):
+    """device_density_fn hands the scaled trees and the candidate network to msnc_log_density_batch (one call per
+    candidate); with the oracle behind that call the scan reproduces the reference."""
+    case = CASES[1]
+    calls = []
+
+    def fake_batch(trees, net, species_of, theta, *, branch_thetas=None, context=None):
+        calls.append(len(trees))
+        d = net.to_dict()
+        return np.array([MO.msnc_log_density(d, t.parent.tolist(), t.blen.tolist(), t.label, species_of, theta) for t in trees])
+    monkeypatch.setattr(NM, "msnc_log_density_batch", fake_batch)
+    net = SpeciesNetwork.from_dict(case["network"])
+    trees = [FlatTree(t["parent"], t["blen"], t["label"]) for t in case["trees"]]
+    fn = NM.device_density_fn(trees, case["species_of"], case["theta"])
+    got = NM.add_reticulation_placements(net, fn, len(HEIGHT_SCALE_GRID), prior_fn=lambda n: -1.5)
+    assert len(got) == len(case["placements"]) and set(calls) == {len(trees) * len(HEIGHT_SCALE_GRID)}
+    ref = {(tuple(p["donor"]), tuple(p["retic"])): p["s_rep"] for p in case["placements"]}
+    for p in got:
+        k = (tuple(_labels(net, p["donor_edge"])), tuple(_labels(net, p["retic_edge"])))
+        assert p["s_rep"] == pytest.approx(ref[k] - 1.5, rel=1e-11)          # the caller's prior is added to every score
