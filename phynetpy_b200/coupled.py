@@ -115,3 +115,58 @@ def coupled_gene_tree_reproposal(engine: Any, gene_trees: Sequence[FlatTree], he
             return None
         log_qr += float(lw[match]) - lse
     return new_trees, new_heights, log_qf, log_qr
+
+
+# ---------------------------------------------------------------------------------------------------
+# the coupled reticulation moves (network surgery + joint gene-tree re-proposal)
+# ---------------------------------------------------------------------------------------------------
+def coupled_add_reticulation(engine: Any, net: Any, gene_trees: Sequence[FlatTree], heights: Sequence[np.ndarray],
+                             theta: float, rng: np.random.Generator, placements_for: Any, *, placement: Any = None,
+                             choose: Any = None) -> Optional[Tuple[Any, List[FlatTree], List[np.ndarray], float]]:
+    """``op_add_reticulation_coupled`` (``src/_mcmc_seq.py:2072-2192``) on flat objects: the informed add move of
+    ``netmoves`` followed by the joint gene-tree re-proposal under the NEW network (reverse density under the old
+    one).  ``placements_for(network, gene_trees)`` returns the scored placements
+    (``netmoves.add_reticulation_placements`` with the caller's prior).  Returns
+    ``(new_network, new_gene_trees, new_heights, log HR)`` with
+
+        log HR = [informed-add ratio] + (log q_r - log q_f)                                   (``:2168-2175``)
+
+    ``placement=(k, u_t2, u_t1, gamma)`` / ``choose`` replace the random draws (tests)."""
+    from . import netmoves as NM
+    placements = placements_for(net, gene_trees)
+    if not placements:
+        return None
+    mv = NM.add_reticulation_move(net, placements, rng) if placement is None else NM.add_reticulation_at(net, placements, *placement)
+    if mv is None:
+        return None
+    new_net, loghr_net = mv
+    repro = coupled_gene_tree_reproposal(engine, gene_trees, heights, new_net, net, theta, rng, choose)
+    if repro is None:
+        return None
+    new_trees, new_heights, log_qf, log_qr = repro
+    return new_net, new_trees, new_heights, loghr_net + (log_qr - log_qf)
+
+
+def coupled_delete_reticulation(engine: Any, net: Any, gene_trees: Sequence[FlatTree], heights: Sequence[np.ndarray],
+                                theta: float, rng: np.random.Generator, placements_for: Any, *, pick: Any = None,
+                                choose: Any = None) -> Optional[Tuple[Any, List[FlatTree], List[np.ndarray], float]]:
+    """``op_delete_reticulation_coupled`` (``:2195-2330``): remove a reticulation (``pick=(retic, donor_parent)`` or
+    drawn as the reference draws), re-propose every gene tree under the post-delete network, then score the reverse
+    add's placements on the post-delete network with the NEW gene trees (``:2293-2299``)."""
+    from . import netmoves as NM
+    if pick is None:
+        pick = NM.draw_reticulation_to_delete(net, rng)
+        if pick is None:
+            return None
+    geom = NM.delete_reticulation_geometry(net, int(pick[0]), int(pick[1]))
+    if geom is None:
+        return None
+    new_net = geom["network"]
+    repro = coupled_gene_tree_reproposal(engine, gene_trees, heights, new_net, net, theta, rng, choose)
+    if repro is None:
+        return None
+    new_trees, new_heights, log_qf, log_qr = repro
+    loghr_net = NM.delete_reticulation_loghr(geom, placements_for(new_net, new_trees))
+    if loghr_net is None:
+        return None
+    return new_net, new_trees, new_heights, loghr_net + (log_qr - log_qf)

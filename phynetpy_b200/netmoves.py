@@ -247,3 +247,166 @@ def device_density_fn(trees: Sequence[FlatTree], species_of: Dict[str, str], the
     def fn(cand: SpeciesNetwork) -> np.ndarray:
         return msnc_log_density_batch(scaled, cand, species_of, theta, branch_thetas=branch_thetas, context=context)
     return fn
+
+
+# ---------------------------------------------------------------------------------------------------
+# the informed add / delete moves themselves (network part; src/_mcmc_seq.py:1365-1625)
+# ---------------------------------------------------------------------------------------------------
+def _logsumexp(values: Sequence[float]) -> float:
+    m = -math.inf
+    for v in values:
+        if v > m:
+            m = v
+    if m == -math.inf:
+        return -math.inf
+    acc = 0.0
+    for v in values:
+        acc += math.exp(v - m)
+    return m + math.log(acc)
+
+
+def placement_probabilities(placements: Sequence[Dict[str, Any]]) -> Tuple[np.ndarray, float]:
+    """Selection probabilities ``exp(s_rep - logsumexp)`` (renormalised) and the log-sum-exp (``:1411-1415``)."""
+    s = [p["s_rep"] for p in placements]
+    lse = _logsumexp(s)
+    probs = np.asarray([math.exp(x - lse) for x in s], dtype=np.float64)
+    probs /= probs.sum()
+    return probs, lse
+
+
+def add_reticulation_at(net: SpeciesNetwork, placements: Sequence[Dict[str, Any]], k: int, u_t2: float, u_t1: float,
+                        gamma: float) -> Optional[Tuple[SpeciesNetwork, float]]:
+    """The deterministic half of ``op_add_reticulation``: placement ``k`` with the uniforms for the hybrid height,
+    the donor height and gamma.  Returns ``(network, log HR)`` with
+
+        log HR = logsumexp_k s_rep_k - s_rep* - log(2 (R + 1)) + log l2 + log win        (``:1454-1461``)
+
+    or ``None`` where the reference declines (empty window, bubble, cycle)."""
+    _, lse = placement_probabilities(placements)
+    chosen = placements[k]
+    d, r = int(chosen["donor_edge"]), int(chosen["retic_edge"])
+    h = net.height
+    v3, v4 = int(net.edge_src[d]), int(net.edge_dst[d])
+    v5, v6 = int(net.edge_src[r]), int(net.edge_dst[r])
+    l2 = float(h[v5] - h[v6])
+    if l2 <= 0.0:
+        return None
+    t2 = float(h[v6]) + l2 * u_t2
+    lo, hi = max(float(h[v4]), t2), float(h[v3])
+    win = hi - lo
+    if win <= 0.0:
+        return None
+    t1 = lo + win * u_t1
+    new = insert_reticulation(net, d, r, t1, t2, float(gamma))
+    if new is None:
+        return None
+    R = net.n_reticulations()
+    loghr = lse - chosen["s_rep"] - math.log(2.0 * (R + 1)) + math.log(l2) + math.log(win)
+    return new, loghr
+
+
+def add_reticulation_move(net: SpeciesNetwork, placements: Sequence[Dict[str, Any]], rng: np.random.Generator
+                          ) -> Optional[Tuple[SpeciesNetwork, float]]:
+    """``op_add_reticulation`` without the graph; draws in the reference's order (placement, t2, t1, gamma)."""
+    if not placements:
+        return None
+    probs, _ = placement_probabilities(placements)
+    k = int(rng.choice(len(placements), p=probs))
+    u2 = float(rng.random())
+    # the reference stops before drawing t1 / gamma when the window is empty (``:1426-1431``)
+    chosen = placements[k]
+    d, r = int(chosen["donor_edge"]), int(chosen["retic_edge"])
+    h = net.height
+    l2 = float(h[net.edge_src[r]] - h[net.edge_dst[r]])
+    if l2 <= 0.0:
+        return None
+    t2 = float(h[net.edge_dst[r]]) + l2 * u2
+    if float(h[net.edge_src[d]]) - max(float(h[net.edge_dst[d]]), t2) <= 0.0:
+        return None
+    u1 = float(rng.random())
+    g = float(rng.random())
+    return add_reticulation_at(net, placements, k, u2, u1, g)
+
+
+def delete_reticulation_geometry(net: SpeciesNetwork, retic: int, donor_parent: int) -> Optional[Dict[str, Any]]:
+    """The network half of a delete: the post-delete network plus what the reverse add needs -- the labels of the
+    merged donor and reticulation edges, ``l2`` and the donor window (``:1538-1551``).  ``None`` where the reference
+    declines."""
+    src, dst = net.edge_src.tolist(), net.edge_dst.tolist()
+    parents = [src[e] for e in range(len(src)) if dst[e] == retic]
+    if len(parents) != 2 or donor_parent not in parents:
+        return None
+    v1, v2 = donor_parent, retic
+    v5 = parents[1] if parents[0] == v1 else parents[0]
+    up1 = [src[e] for e in range(len(src)) if dst[e] == v1]
+    if len(up1) != 1:
+        return None
+    v3 = up1[0]
+    others = [dst[e] for e in range(len(src)) if src[e] == v1 and dst[e] != v2]
+    down2 = [dst[e] for e in range(len(src)) if src[e] == v2]
+    if len(others) != 1 or len(down2) != 1:
+        return None
+    v4, v6 = others[0], down2[0]
+    h = net.height
+    l2 = float(h[v5] - h[v6])
+    if l2 <= 0.0:
+        return None
+    lo, hi = max(float(h[v4]), float(h[v2])), float(h[v3])
+    win = hi - lo
+    if win <= 0.0:
+        return None
+    new = remove_reticulation(net, v2, v1)
+    if new is None:
+        return None
+    lab = net.node_label
+    return {"network": new, "donor_labels": (lab[v3], lab[v4]), "retic_labels": (lab[v5], lab[v6]), "l2": l2, "win": win,
+            "R": net.n_reticulations()}
+
+
+def delete_reticulation_loghr(geom: Dict[str, Any], placements: Sequence[Dict[str, Any]]) -> Optional[float]:
+    """``s_rep(reverse placement) - logsumexp_k s_rep_k + log(2 R) - log l2 - log win`` (``:1597-1603``) from the
+    placements of the post-delete network; ``None`` if the reverse add cannot recreate the removed reticulation."""
+    if not placements:
+        return None
+    new = geom["network"]
+    lab = new.node_label
+    _, lse = placement_probabilities(placements)
+    for p in placements:
+        d, r = int(p["donor_edge"]), int(p["retic_edge"])
+        if (lab[int(new.edge_src[d])], lab[int(new.edge_dst[d])]) == geom["donor_labels"] and \
+           (lab[int(new.edge_src[r])], lab[int(new.edge_dst[r])]) == geom["retic_labels"]:
+            return p["s_rep"] - lse + math.log(2.0 * geom["R"]) - math.log(geom["l2"]) - math.log(geom["win"])
+    return None
+
+
+def delete_reticulation_at(net: SpeciesNetwork, retic: int, donor_parent: int,
+                           placements_fn: Callable[[SpeciesNetwork], List[Dict[str, Any]]]
+                           ) -> Optional[Tuple[SpeciesNetwork, float]]:
+    """The deterministic half of ``op_delete_reticulation``: remove the hybrid edge ``donor_parent -> retic``, score
+    the placements of the resulting network with the add move's own rule (``placements_fn``) and return
+    ``(network, log HR)``; ``None`` where the reference declines."""
+    geom = delete_reticulation_geometry(net, retic, donor_parent)
+    if geom is None:
+        return None
+    loghr = delete_reticulation_loghr(geom, placements_fn(geom["network"]))
+    return None if loghr is None else (geom["network"], loghr)
+
+
+def draw_reticulation_to_delete(net: SpeciesNetwork, rng: np.random.Generator) -> Optional[Tuple[int, int]]:
+    """A reticulation uniformly, then one of its two parents uniformly (``:1500-1506``)."""
+    rets = np.nonzero(np.bincount(net.edge_dst, minlength=net.n_nodes) >= 2)[0]
+    if rets.shape[0] == 0:
+        return None
+    v2 = int(rets[int(rng.integers(rets.shape[0]))])
+    parents = net.edge_src[net.edge_dst == v2]
+    if parents.shape[0] != 2:
+        return None
+    return v2, int(parents[int(rng.integers(2))])
+
+
+def delete_reticulation_move(net: SpeciesNetwork, rng: np.random.Generator,
+                             placements_fn: Callable[[SpeciesNetwork], List[Dict[str, Any]]]
+                             ) -> Optional[Tuple[SpeciesNetwork, float]]:
+    """``op_delete_reticulation`` without the graph."""
+    pick = draw_reticulation_to_delete(net, rng)
+    return None if pick is None else delete_reticulation_at(net, pick[0], pick[1], placements_fn)

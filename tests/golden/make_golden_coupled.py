@@ -52,6 +52,68 @@ def describe(gt, heights):
     return sorted([clade(gt, v), float(heights[v])] for v in gt.V() if gt.get_children(v))
 
 
+def coupled_move_cases(model):
+    """op_add_reticulation_coupled / op_delete_reticulation_coupled with the sampler's prior patched to 0 and a
+    recording generator: the placement (labels), the three uniforms, the chosen gene tree of every locus, the
+    resulting network (new nodes named by height) and the log Hastings ratio."""
+    import types
+    from make_golden_netmoves import RecordingRng, canonical, keyed
+    M.log_prior_seq = lambda *a, **k: 0.0
+    out = []
+    for n_species, n_retic, n_loci, L, seed in [(4, 0, 3, 60, 11), (5, 0, 2, 50, 12), (4, 1, 2, 60, 13), (5, 1, 3, 40, 14)]:
+        rng = np.random.default_rng(1500 + seed)
+        nodes, edges = random_network(n_species, n_retic, rng, height=0.06)
+        nw = enewick(nodes, edges)
+        net = Network.from_newick(nw, branch_length_unit=UNIT)
+        alleles = {"s%d" % i: ["s%d" % i] for i in range(n_species)}
+        species_of = {"s%d" % i: "s%d" % i for i in range(n_species)}
+        theta = 0.03
+        gts = [simulate_gene_tree(net, alleles, theta, rng) for _ in range(n_loci)]
+        loci = [simulate_sequences(g, model, L, rng) for g in gts]
+
+        def state():
+            st = _State()
+            st._engine = M._SeqLikelihoodEngine(loci, species_of, model, None)
+            st.gene_trees = list(gts)
+            st.gt_heights = [_node_heights(g) for g in gts]
+            st.theta = theta
+            st.model = model
+            st.branch_thetas = None
+            st.priors = types.SimpleNamespace(max_reticulations=10, max_level=None)
+            st.species_net = net
+            st.net_heights = _node_heights(net)
+            st.num_reticulations = lambda: sum(1 for v in st.species_net.V() if v.is_reticulation())
+            return st
+        old_labels = {v.label for v in net.V()}
+        recs = []
+        for s_ in range(4):
+            st = state()
+            pl = M._add_reticulation_placements(st, net, _node_heights(net))
+            rr = RecordingRng(2000 + 10 * seed + s_)
+            res = M.op_add_reticulation_coupled(st, rr)
+            if res is None:
+                continue
+            k = rr.log[0][1]
+            recs.append({"kind": "add", "donor": list(pl[k]["donor_labels"]), "retic": list(pl[k]["retic_labels"]),
+                         "uniforms": [x[1] for x in rr.log[1:4]], "loghr": float(res[0]),
+                         "network": keyed(st.species_net, old_labels),
+                         "chosen": [describe(g, h) for g, h in zip(st.gene_trees, st.gt_heights)]})
+        for s_ in range(4 if n_retic else 0):
+            st = state()
+            res = M.op_delete_reticulation_coupled(st, RecordingRng(3000 + 10 * seed + s_))
+            if res is None:
+                continue
+            gone = sorted(old_labels - {v.label for v in st.species_net.V()})
+            retic = [x for x in gone if [v for v in net.V() if v.label == x][0].is_reticulation()][0]
+            recs.append({"kind": "delete", "retic": retic, "donor_parent": [x for x in gone if x != retic][0],
+                         "loghr": float(res[0]), "network": canonical(st.species_net),
+                         "chosen": [describe(g, h) for g, h in zip(st.gene_trees, st.gt_heights)]})
+        out.append({"name": "n%d_r%d_m%d" % (n_species, n_retic, n_loci), "network": export_network(net), "theta": theta,
+                    "loci": loci, "species_of": species_of, "trees": [export_gene_tree(g) for g in gts], "moves": recs})
+        print(out[-1]["name"], [(r["kind"], round(r["loghr"], 3)) for r in recs])
+    return out
+
+
 def main():
     cases = []
     model = GTR(PI, RATES)
@@ -95,9 +157,11 @@ def main():
                 rec["result"] = {"chosen": [describe(g, h) for g, h in zip(new_gts, new_hs)],
                                  "log_qf": float(log_qf), "log_qr": float(log_qr)}
             cases.append(rec)
+    moves = coupled_move_cases(model)
     out = os.path.join(HERE, "coupled_cases.json")
     with open(out, "w") as f:
-        json.dump({"source": "PhyNetPy v0.6.0 _coupled_gene_tree_reproposal", "cases": cases}, f)
+        json.dump({"source": "PhyNetPy v0.6.0 _coupled_gene_tree_reproposal, op_add/delete_reticulation_coupled (prior at 0)",
+                   "cases": cases, "move_cases": moves}, f)
     print("wrote %s: %d cases (%d declined)" % (out, len(cases), sum(c["result"] is None for c in cases)))
     for c in cases:
         print(c["name"], None if c["result"] is None else (round(c["result"]["log_qf"], 4), round(c["result"]["log_qr"], 4)))

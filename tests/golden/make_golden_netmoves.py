@@ -37,6 +37,54 @@ class _State:
     pass
 
 
+class RecordingRng:
+    """A numpy Generator that remembers what it returned, so the deterministic half of an operator can be replayed."""
+
+    def __init__(self, seed):
+        self.r = np.random.default_rng(seed)
+        self.log = []
+
+    def choice(self, n, p=None):
+        k = int(self.r.choice(n, p=p))
+        self.log.append(["choice", k])
+        return k
+
+    def random(self):
+        u = float(self.r.random())
+        self.log.append(["random", u])
+        return u
+
+    def integers(self, n):
+        k = int(self.r.integers(n))
+        self.log.append(["integers", k])
+        return k
+
+
+def keyed(net, old_labels):
+    """Canonical form in which nodes the move created are named by their height (their labels are arbitrary)."""
+    h = _node_heights(net)
+
+    def key(v):
+        return v.label if v.label in old_labels else "new@%r" % float(h[v])
+    return {"nodes": sorted([key(v), float(h[v])] for v in net.V()),
+            "edges": sorted([key(e.src), key(e.dest), None if e.get_gamma() is None else float(e.get_gamma())] for e in net.E())}
+
+
+def make_state(net, gts, loci, species_of, model, theta):
+    import types
+    st = _State()
+    st._engine = M._SeqLikelihoodEngine(loci, species_of, model, None)
+    st.gene_trees = gts
+    st.gt_heights = [_node_heights(g) for g in gts]
+    st.theta = theta
+    st.branch_thetas = None
+    st.priors = types.SimpleNamespace(max_reticulations=10, max_level=None)
+    st.species_net = net
+    st.net_heights = _node_heights(net)
+    st.num_reticulations = lambda: sum(1 for v in st.species_net.V() if v.is_reticulation())
+    return st
+
+
 def canonical(net):
     h = _node_heights(net)
     return {"nodes": sorted([v.label, float(h[v])] for v in net.V()),
@@ -112,9 +160,33 @@ def main():
             if v.is_reticulation():
                 for p in net.get_parents(v):
                     deletes.append({"retic": v.label, "donor_parent": p.label, "result": delete_surgery(net, v.label, p.label)})
+        # the informed moves themselves, with a recording generator (network part only: the prior is 0)
+        old_labels = {v.label for v in net.V()}
+        adds = []
+        for s_ in range(6):
+            st2 = make_state(net, gts, loci, species_of, model, theta)
+            pl = M._add_reticulation_placements(st2, net, _node_heights(net))
+            rr = RecordingRng(40 + s_)
+            res = M.op_add_reticulation(st2, rr)
+            k = rr.log[0][1]
+            rec = {"donor": list(pl[k]["donor_labels"]), "retic": list(pl[k]["retic_labels"]),
+                   "uniforms": [x[1] for x in rr.log[1:]]}
+            rec["result"] = None if res is None else {"loghr": float(res[0]), "network": keyed(st2.species_net, old_labels)}
+            adds.append(rec)
+        dels = []
+        for s_ in range(6 if n_retic else 0):
+            st2 = make_state(net, gts, loci, species_of, model, theta)
+            res = M.op_delete_reticulation(st2, RecordingRng(60 + s_))
+            if res is None:
+                continue            # which pair was drawn cannot be read back from a declined move
+            gone = sorted(old_labels - {v.label for v in st2.species_net.V()})
+            retic = [x for x in gone if [v for v in net.V() if v.label == x][0].is_reticulation()][0]
+            donor_parent = [x for x in gone if x != retic][0]
+            dels.append({"retic": retic, "donor_parent": donor_parent, "loghr": float(res[0]),
+                         "network": canonical(st2.species_net)})
         cases.append({"name": "n%d_r%d" % (n_species, n_retic), "newick": nw, "network": export_network(net), "theta": theta,
                       "species_of": species_of, "trees": [export_gene_tree(g) for g in gts], "base_score": base_score,
-                      "geometric": geo, "placements": placed, "deletes": deletes})
+                      "geometric": geo, "placements": placed, "deletes": deletes, "add_moves": adds, "delete_moves": dels})
         print(cases[-1]["name"], "edges", len(list(net.E())), "geometric", len(geo), "scored", len(placed), "deletes",
               [d["result"] is not None for d in deletes], "base", round(base_score, 4) if math.isfinite(base_score) else base_score)
     out = os.path.join(HERE, "netmoves_cases.json")

@@ -39,6 +39,7 @@ class OracleEngine:
 
     def msnc_batch(self, batch, loci, net, theta):
         self.calls += 1
+        net = net if isinstance(net, dict) else net.to_dict()
         out = np.empty(batch.n_members)
         for m in range(batch.n_members):
             j = int(batch.tree_of_member[m])
@@ -114,3 +115,113 @@ def test_declines_like_the_reference_when_nothing_has_weight():
     with pytest.raises(ValueError, match="one gene tree"):
         CP.coupled_gene_tree_reproposal(eng, trees[:1], heights, case["target"], case["reverse"], case["theta"],
                                         np.random.default_rng(0))
+
+
+# ---------------------------------------------------------------------------------------------------
+# the coupled reticulation moves: network surgery + joint gene-tree re-proposal
+# ---------------------------------------------------------------------------------------------------
+MOVE_CASES = json.load(open(os.path.join(HERE, "golden", "coupled_cases.json")))["move_cases"]
+
+
+def _setup_move_case(case):
+    from phynetpy_b200 import netmoves as NM
+    from phynetpy_b200._msnc_density import SpeciesNetwork
+    from phynetpy_b200.candidates import HEIGHT_SCALE_GRID
+    eng = OracleEngine(case)
+    net = SpeciesNetwork.from_dict(case["network"])
+    trees = [FlatTree(t["parent"], t["blen"], t["label"]) for t in case["trees"]]
+    heights = [node_heights(t) for t in trees]
+
+    def placements_for(network, gene_trees):
+        scaled = NM.scaled_gene_trees(gene_trees)
+
+        def dens(cand):
+            d = cand.to_dict()
+            return np.array([MO.msnc_log_density(d, t.parent.tolist(), t.blen.tolist(), t.label, case["species_of"], case["theta"])
+                             for t in scaled])
+        return NM.add_reticulation_placements(network, dens, len(HEIGHT_SCALE_GRID))
+    return eng, net, trees, heights, placements_for
+
+
+def _chooser(trees, want):
+    def choose(i, table, probs):
+        par, bl, ht = table
+        hits = [j for j in range(par.shape[0]) if _same(_describe(CP._member(trees[i], par[j], bl[j]), ht[j]), want[i])]
+        assert len(hits) == 1
+        return hits[0]
+    return choose
+
+
+def _keyed(net, old_labels):
+    def key(v):
+        lab = net.node_label[v]
+        return lab if lab in old_labels else "new@%r" % float(net.height[v])
+    return sorted([key(int(s)), key(int(d)), None if g != g else float(g)]
+                  for s, d, g in zip(net.edge_src, net.edge_dst, net.edge_gamma.tolist()))
+
+
+@pytest.mark.parametrize("case", MOVE_CASES, ids=[c["name"] for c in MOVE_CASES])
+def test_coupled_reticulation_moves_equal_the_reference(case):
+    """op_add_reticulation_coupled / op_delete_reticulation_coupled (prior at 0): with the reference's placement,
+    uniforms and chosen gene trees forced, the same network and the same log Hastings ratio."""
+    eng, net, trees, heights, placements_for = _setup_move_case(case)
+    lab = net.node_label
+    old = set(lab)
+    placements = placements_for(net, trees)
+    index = {((lab[int(net.edge_src[p["donor_edge"]])], lab[int(net.edge_dst[p["donor_edge"]])]),
+              (lab[int(net.edge_src[p["retic_edge"]])], lab[int(net.edge_dst[p["retic_edge"]])])): k
+             for k, p in enumerate(placements)}
+    n_add = n_del = 0
+    for rec in case["moves"]:
+        choose = _chooser(trees, rec["chosen"])
+        if rec["kind"] == "add":
+            k = index[(tuple(rec["donor"]), tuple(rec["retic"]))]
+            out = CP.coupled_add_reticulation(eng, net, trees, heights, case["theta"], np.random.default_rng(0), placements_for,
+                                              placement=(k,) + tuple(rec["uniforms"]), choose=choose)
+            assert out is not None
+            new_net, new_trees, new_h, loghr = out
+            assert _keyed(new_net, old) == rec["network"]["edges"]
+            n_add += 1
+        else:
+            out = CP.coupled_delete_reticulation(eng, net, trees, heights, case["theta"], np.random.default_rng(0), placements_for,
+                                                 pick=(lab.index(rec["retic"]), lab.index(rec["donor_parent"])), choose=choose)
+            assert out is not None
+            new_net, new_trees, new_h, loghr = out
+            assert _keyed(new_net, old) == rec["network"]["edges"]
+            n_del += 1
+        assert loghr == pytest.approx(rec["loghr"], abs=1e-8)
+        for t, h, w in zip(new_trees, new_h, rec["chosen"]):
+            assert _same(_describe(t, h), w)
+    assert n_add >= 4
+
+
+def test_coupled_add_and_delete_are_exact_reverses():
+    """log H(add: x -> x') + log H(delete: x' -> x) == 0 when the delete picks the reticulation the add created and
+    every locus re-selects its original gene tree -- the identity of tests/test_mcmc_seq_coupled.py in the reference,
+    up to the re-derivation of branch lengths of the materialised trees (the simulator prints 10 decimals)."""
+    from phynetpy_b200.candidates import signature
+    case = MOVE_CASES[0]
+    eng, net, trees, heights, placements_for = _setup_move_case(case)
+    # start from trees whose lengths agree with their heights, so that materialising changes nothing
+    trees = [CP._member(t, t.parent, CP._lengths_from_heights(t.parent, h)) for t, h in zip(trees, heights)]
+    rng = np.random.default_rng(8)
+    done = 0
+    for attempt in range(6):
+        fwd = CP.coupled_add_reticulation(eng, net, trees, heights, case["theta"], rng, placements_for)
+        if fwd is None:
+            continue
+        new_net, new_trees, new_h, h_add = fwd
+        sigs = [signature(t, h) for t, h in zip(trees, heights)]
+
+        def back_choose(i, table, probs):
+            par, bl, ht = table
+            return next(j for j in range(par.shape[0]) if signature(CP._member(new_trees[i], par[j], bl[j]), ht[j]) == sigs[i])
+        back = CP.coupled_delete_reticulation(eng, new_net, new_trees, new_h, case["theta"], rng, placements_for,
+                                              pick=(net.n_nodes + 1, net.n_nodes), choose=back_choose)
+        if back is None:
+            continue
+        old_net, old_trees, old_h, h_del = back
+        assert h_add + h_del == pytest.approx(0.0, abs=1e-8)
+        assert old_net.n_reticulations() == net.n_reticulations()
+        done += 1
+    assert done >= 2

@@ -128,3 +128,93 @@ def test_device_density_fn_plumbing(monkeypatch):
     for p in got:
         k = (tuple(_labels(net, p["donor_edge"])), tuple(_labels(net, p["retic_edge"])))
         assert p["s_rep"] == pytest.approx(ref[k] - 1.5, rel=1e-11)          # the caller's prior is added to every score
+
+
+def _keyed(net, old_labels):
+    def key(v):
+        lab = net.node_label[v]
+        return lab if lab in old_labels else "new@%r" % float(net.height[v])
+    return {"nodes": sorted([key(v), float(net.height[v])] for v in range(net.n_nodes)),
+            "edges": sorted([key(int(s)), key(int(d)), None if g != g else float(g)]
+                            for s, d, g in zip(net.edge_src, net.edge_dst, net.edge_gamma.tolist()))}
+
+
+def _placements_fn(case):
+    trees = [FlatTree(t["parent"], t["blen"], t["label"]) for t in case["trees"]]
+    scaled = NM.scaled_gene_trees(trees)
+
+    def fn(net):
+        return NM.add_reticulation_placements(net, _density_fn(case, scaled), len(HEIGHT_SCALE_GRID))
+    return fn
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_informed_add_move_equals_the_reference(case):
+    """op_add_reticulation (prior at 0): for the placement and the three uniforms the reference drew, the same
+    network (new nodes named by height) and the same log Hastings ratio."""
+    net = SpeciesNetwork.from_dict(case["network"])
+    old = set(net.node_label)
+    placements = _placements_fn(case)(net)
+    index = {(tuple(_labels(net, p["donor_edge"])), tuple(_labels(net, p["retic_edge"]))): k for k, p in enumerate(placements)}
+    for rec in case["add_moves"]:
+        k = index[(tuple(rec["donor"]), tuple(rec["retic"]))]
+        u2, u1, g = rec["uniforms"]
+        out = NM.add_reticulation_at(net, placements, k, u2, u1, g)
+        assert (out is None) == (rec["result"] is None)
+        if out is None:
+            continue
+        new, loghr = out
+        assert loghr == pytest.approx(rec["result"]["loghr"], abs=1e-9)
+        got, want = _keyed(new, old), rec["result"]["network"]
+        assert [n[0] for n in got["nodes"]] == [n[0] for n in want["nodes"]]
+        assert [n[1] for n in got["nodes"]] == pytest.approx([n[1] for n in want["nodes"]], abs=1e-15)
+        assert got["edges"] == want["edges"]
+        assert new.n_reticulations() == net.n_reticulations() + 1
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c["delete_moves"]], ids=[c["name"] for c in CASES if c["delete_moves"]])
+def test_informed_delete_move_equals_the_reference(case):
+    net = SpeciesNetwork.from_dict(case["network"])
+    lab = net.node_label
+    fn = _placements_fn(case)
+    for rec in case["delete_moves"]:
+        out = NM.delete_reticulation_at(net, lab.index(rec["retic"]), lab.index(rec["donor_parent"]), fn)
+        assert out is not None
+        new, loghr = out
+        assert loghr == pytest.approx(rec["loghr"], abs=1e-9)
+        got = _canonical(new)
+        assert got["edges"] == rec["network"]["edges"]
+        assert [n[0] for n in got["nodes"]] == [n[0] for n in rec["network"]["nodes"]]
+
+
+def test_add_and_delete_are_exact_reverses():
+    """log H(add: x -> x') == -log H(delete: x' -> x) when both use the same scoring rule -- the identity the
+    reference's own tests check for its operators (tests/test_mcmc_seq_coupled.py)."""
+    case = CASES[1]
+    net = SpeciesNetwork.from_dict(case["network"])
+    fn = _placements_fn(case)
+    placements = fn(net)
+    rng = np.random.default_rng(4)
+    n_checked = 0
+    for _ in range(8):
+        k = int(rng.integers(len(placements)))
+        out = NM.add_reticulation_at(net, placements, k, float(rng.random()), float(rng.random()), float(rng.uniform(0.1, 0.9)))
+        if out is None:
+            continue
+        new, h_add = out
+        v1, v2 = net.n_nodes, net.n_nodes + 1
+        back = NM.delete_reticulation_at(new, v2, v1, fn)
+        if back is None:
+            continue
+        old, h_del = back
+        assert h_add == pytest.approx(-h_del, abs=1e-9)
+        assert _canonical(old)["nodes"] == _canonical(net)["nodes"]
+        n_checked += 1
+    assert n_checked >= 4
+    # the random-draw wrappers
+    mv = NM.add_reticulation_move(net, placements, np.random.default_rng(1))
+    assert mv is None or (mv[0].n_reticulations() == 1 and math.isfinite(mv[1]))
+    assert NM.delete_reticulation_move(net, np.random.default_rng(1), fn) is None          # a tree has nothing to delete
+    if mv is not None:
+        dm = NM.delete_reticulation_move(mv[0], np.random.default_rng(2), fn)
+        assert dm is None or dm[0].n_reticulations() == 0
