@@ -131,7 +131,8 @@ def delete_surgery(net, v2_label, v1_label):
 
 
 def main():
-    M.log_prior_seq = lambda *a, **k: 0.0          # the sampler's prior is not part of this path
+    orig_prior = M.log_prior_seq
+    M.log_prior_seq = lambda *a, **k: 0.0          # scores without the prior (the MSNC part alone)
     model = GTR([0.25] * 4, [1.0] * 6)
     cases = []
     for n_species, n_retic, n_loci, seed in [(3, 0, 2, 1), (4, 0, 3, 2), (5, 0, 2, 3), (4, 1, 2, 4), (5, 1, 2, 5), (5, 2, 2, 6)]:
@@ -155,6 +156,14 @@ def main():
         placed = [{"donor": list(p["donor_labels"]), "retic": list(p["retic_labels"]), "l2": float(p["l2"]), "s_rep": float(p["s_rep"])}
                   for p in M._add_reticulation_placements(st, net, heights)]
         base_score = float(M._network_only_log_score(st, net))
+        # ... and once with the reference's real prior at its default hyper-parameters (its identifiability guards
+        # drop the placements that would create cycles of fewer than 4 nodes)
+        M.log_prior_seq = orig_prior
+        st.priors = M.MCMCSeqPriors()
+        placed_prior = [{"donor": list(p["donor_labels"]), "retic": list(p["retic_labels"]), "s_rep": float(p["s_rep"])}
+                        for p in M._add_reticulation_placements(st, net, heights)]
+        M.log_prior_seq = lambda *a, **k: 0.0
+        st.priors = None
         deletes = []
         for v in net.V():
             if v.is_reticulation():
@@ -186,7 +195,8 @@ def main():
                          "network": canonical(st2.species_net)})
         cases.append({"name": "n%d_r%d" % (n_species, n_retic), "newick": nw, "network": export_network(net), "theta": theta,
                       "species_of": species_of, "trees": [export_gene_tree(g) for g in gts], "base_score": base_score,
-                      "geometric": geo, "placements": placed, "deletes": deletes, "add_moves": adds, "delete_moves": dels})
+                      "geometric": geo, "placements": placed, "placements_with_prior": placed_prior, "deletes": deletes,
+                      "add_moves": adds, "delete_moves": dels})
         print(cases[-1]["name"], "edges", len(list(net.E())), "geometric", len(geo), "scored", len(placed), "deletes",
               [d["result"] is not None for d in deletes], "base", round(base_score, 4) if math.isfinite(base_score) else base_score)
     out = os.path.join(HERE, "netmoves_cases.json")

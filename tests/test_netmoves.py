@@ -158,6 +158,10 @@ def test_informed_add_move_equals_the_reference(case):
     index = {(tuple(_labels(net, p["donor_edge"])), tuple(_labels(net, p["retic_edge"]))): k for k, p in enumerate(placements)}
     for rec in case["add_moves"]:
         k = index[(tuple(rec["donor"]), tuple(rec["retic"]))]
+        if len(rec["uniforms"]) < 3:       # the reference stopped after drawing the hybrid height: empty donor window
+            assert rec["result"] is None
+            assert NM.add_reticulation_at(net, placements, k, rec["uniforms"][0], 0.5, 0.5) is None
+            continue
         u2, u1, g = rec["uniforms"]
         out = NM.add_reticulation_at(net, placements, k, u2, u1, g)
         assert (out is None) == (rec["result"] is None)
@@ -218,3 +222,21 @@ def test_add_and_delete_are_exact_reverses():
     if mv is not None:
         dm = NM.delete_reticulation_move(mv[0], np.random.default_rng(2), fn)
         assert dm is None or dm[0].n_reticulations() == 0
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_scored_placements_with_the_real_prior(case):
+    """The scan with the reference's own prior at its defaults (phynetpy_b200/priors.py as ``prior_fn``): the
+    identifiability guards drop the same placements, every surviving score agrees."""
+    from phynetpy_b200.priors import SeqPriors, log_prior_seq
+    net = SpeciesNetwork.from_dict(case["network"])
+    trees = [FlatTree(t["parent"], t["blen"], t["label"]) for t in case["trees"]]
+    fn = _density_fn(case, NM.scaled_gene_trees(trees))
+    pri = SeqPriors()
+    got = NM.add_reticulation_placements(net, fn, len(HEIGHT_SCALE_GRID), prior_fn=lambda n: log_prior_seq(n, case["theta"], pri))
+    mine = {(tuple(_labels(net, p["donor_edge"])), tuple(_labels(net, p["retic_edge"]))): p["s_rep"] for p in got}
+    ref = {(tuple(p["donor"]), tuple(p["retic"])): p["s_rep"] for p in case["placements_with_prior"]}
+    assert set(mine) == set(ref)
+    assert len(ref) <= len(case["placements"])
+    for k, v in ref.items():
+        assert mine[k] == pytest.approx(v, rel=1e-11)
