@@ -170,3 +170,59 @@ def coupled_delete_reticulation(engine: Any, net: Any, gene_trees: Sequence[Flat
     if loghr_net is None:
         return None
     return new_net, new_trees, new_heights, loghr_net + (log_qr - log_qf)
+
+
+def coupled_relocate_reticulation(engine: Any, net: Any, gene_trees: Sequence[FlatTree], heights: Sequence[np.ndarray],
+                                  theta: float, rng: np.random.Generator, *, pick: Any = None, placement: Any = None,
+                                  choose: Any = None) -> Optional[Tuple[Any, List[FlatTree], List[np.ndarray], float]]:
+    """``op_relocate_reticulation_coupled`` (``src/_mcmc_seq.py:2604-2790``): detach a reticulation A (as the delete
+    move does), re-attach it at a placement B drawn UNIFORMLY from the geometric placements of the base network,
+    re-propose every gene tree under the new network.  The ``1 / K`` selection cancels between the two directions,
+    so (``_relocation_loghr`` ``:2578-2601``)
+
+        log HR = log l2_B + log win_B - log l2_A - log win_A + (log q_r - log q_f).
+
+    ``pick=(retic, donor_parent)``, ``placement=(donor_edge, retic_edge, u_t2, u_t1, gamma)`` (edges of the base
+    network) and ``choose`` replace the random draws (tests).  The level cap (``max_level``) is the caller's."""
+    from . import netmoves as NM
+    if pick is None:
+        pick = NM.draw_reticulation_to_delete(net, rng)
+        if pick is None:
+            return None
+    geom = NM.delete_reticulation_geometry(net, int(pick[0]), int(pick[1]))
+    if geom is None:
+        return None
+    n0 = geom["network"]
+    if placement is None:
+        places = NM.geometric_placements(n0)
+        if not places:
+            return None
+        d, r = places[int(rng.integers(len(places)))]
+        u2 = u1 = g = None
+    else:
+        d, r, u2, u1, g = placement
+    h = n0.height
+    b3, b4 = int(n0.edge_src[d]), int(n0.edge_dst[d])
+    b5, b6 = int(n0.edge_src[r]), int(n0.edge_dst[r])
+    l2_b = float(h[b5] - h[b6])
+    if l2_b <= 0.0:
+        return None
+    if u2 is None:
+        u2 = float(rng.random())
+    t2 = float(h[b6]) + l2_b * u2
+    lo = max(float(h[b4]), t2)
+    win_b = float(h[b3]) - lo
+    if win_b <= 0.0:
+        return None
+    if u1 is None:
+        u1 = float(rng.random())
+        g = float(rng.random())
+    new_net = NM.insert_reticulation(n0, int(d), int(r), lo + win_b * u1, t2, float(g))
+    if new_net is None:
+        return None
+    repro = coupled_gene_tree_reproposal(engine, gene_trees, heights, new_net, net, theta, rng, choose)
+    if repro is None:
+        return None
+    new_trees, new_heights, log_qf, log_qr = repro
+    loghr = (math.log(l2_b) + math.log(win_b) - math.log(geom["l2"]) - math.log(geom["win"]) + (log_qr - log_qf))
+    return new_net, new_trees, new_heights, loghr

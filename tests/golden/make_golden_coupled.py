@@ -108,6 +108,27 @@ def coupled_move_cases(model):
             recs.append({"kind": "delete", "retic": retic, "donor_parent": [x for x in gone if x != retic][0],
                          "loghr": float(res[0]), "network": canonical(st.species_net),
                          "chosen": [describe(g, h) for g, h in zip(st.gene_trees, st.gt_heights)]})
+        for s_ in range(8 if n_retic else 0):
+            st = state()
+            rr = RecordingRng(4000 + 10 * seed + s_)
+            res = M.op_relocate_reticulation_coupled(st, rr)
+            if res is None:
+                continue
+            new = st.species_net
+            gone = sorted(old_labels - {v.label for v in new.V()})
+            retic = [x for x in gone if [v for v in net.V() if v.label == x][0].is_reticulation()][0]
+            fresh = [v for v in new.V() if v.label not in old_labels]
+            nv2 = [v for v in fresh if v.is_reticulation()][0]
+            nv1 = [v for v in fresh if v is not nv2][0]
+            b3 = new.get_parents(nv1)[0]
+            b4 = [c for c in new.get_children(nv1) if c is not nv2][0]
+            b5 = [p for p in new.get_parents(nv2) if p is not nv1][0]
+            b6 = new.get_children(nv2)[0]
+            rand = [x[1] for x in rr.log if x[0] == "random"][:3]
+            recs.append({"kind": "relocate", "retic": retic, "donor_parent": [x for x in gone if x != retic][0],
+                         "donor": [b3.label, b4.label], "retic_edge": [b5.label, b6.label], "uniforms": rand,
+                         "loghr": float(res[0]), "network": keyed(new, old_labels),
+                         "chosen": [describe(g, h) for g, h in zip(st.gene_trees, st.gt_heights)]})
         out.append({"name": "n%d_r%d_m%d" % (n_species, n_retic, n_loci), "network": export_network(net), "theta": theta,
                     "loci": loci, "species_of": species_of, "trees": [export_gene_tree(g) for g in gts], "moves": recs})
         print(out[-1]["name"], [(r["kind"], round(r["loghr"], 3)) for r in recs])

@@ -182,17 +182,77 @@ def test_coupled_reticulation_moves_equal_the_reference(case):
             new_net, new_trees, new_h, loghr = out
             assert _keyed(new_net, old) == rec["network"]["edges"]
             n_add += 1
-        else:
+        elif rec["kind"] == "delete":
             out = CP.coupled_delete_reticulation(eng, net, trees, heights, case["theta"], np.random.default_rng(0), placements_for,
                                                  pick=(lab.index(rec["retic"]), lab.index(rec["donor_parent"])), choose=choose)
             assert out is not None
             new_net, new_trees, new_h, loghr = out
             assert _keyed(new_net, old) == rec["network"]["edges"]
             n_del += 1
+        else:       # relocate: detach A, re-attach at the placement B the reference drew on the base network
+            from phynetpy_b200 import netmoves as NM
+            pick = (lab.index(rec["retic"]), lab.index(rec["donor_parent"]))
+            n0 = NM.delete_reticulation_geometry(net, *pick)["network"]
+            l0 = n0.node_label
+            edge = {(l0[int(s)], l0[int(d)]): e for e, (s, d) in enumerate(zip(n0.edge_src, n0.edge_dst))}
+            d_e, r_e = edge[tuple(rec["donor"])], edge[tuple(rec["retic_edge"])]
+            assert (d_e, r_e) in NM.geometric_placements(n0)
+            out = CP.coupled_relocate_reticulation(eng, net, trees, heights, case["theta"], np.random.default_rng(0), pick=pick,
+                                                   placement=(d_e, r_e) + tuple(rec["uniforms"]), choose=choose)
+            assert out is not None
+            new_net, new_trees, new_h, loghr = out
+            assert _keyed(new_net, old) == rec["network"]["edges"]
+            assert new_net.n_reticulations() == net.n_reticulations()
         assert loghr == pytest.approx(rec["loghr"], abs=1e-8)
         for t, h, w in zip(new_trees, new_h, rec["chosen"]):
             assert _same(_describe(t, h), w)
     assert n_add >= 4
+
+
+def test_relocation_is_its_own_reverse():
+    """log H(relocate A -> B) == -log H(relocate B -> A) when the way back re-attaches at A's place with A's heights
+    and gamma and every locus re-selects its original tree (``_relocation_loghr`` is antisymmetric, ``:2578-2601``)."""
+    from phynetpy_b200 import netmoves as NM
+    from phynetpy_b200.candidates import signature
+    case = next(c for c in MOVE_CASES if any(m["kind"] == "relocate" for m in c["moves"]))
+    eng, net, trees, heights, placements_for = _setup_move_case(case)
+    trees = [CP._member(t, t.parent, CP._lengths_from_heights(t.parent, h)) for t, h in zip(trees, heights)]
+    sigs = [signature(t, h) for t, h in zip(trees, heights)]
+    lab = net.node_label
+    rng = np.random.default_rng(3)
+    done = 0
+    for attempt in range(10):
+        pick = NM.draw_reticulation_to_delete(net, rng)
+        fwd = CP.coupled_relocate_reticulation(eng, net, trees, heights, case["theta"], rng, pick=pick)
+        if fwd is None:
+            continue
+        new_net, new_trees, new_h, h_fwd = fwd
+        # the way back: detach B (the two nodes the forward move appended), re-attach on A's merged edges
+        geom_a = NM.delete_reticulation_geometry(net, *pick)
+        n0 = geom_a["network"]
+        b_pick = (new_net.n_nodes - 1, new_net.n_nodes - 2)
+        n0_back = NM.delete_reticulation_geometry(new_net, *b_pick)["network"]
+        l0 = n0_back.node_label
+        edge = {(l0[int(s)], l0[int(d)]): e for e, (s, d) in enumerate(zip(n0_back.edge_src, n0_back.edge_dst))}
+        d_e, r_e = edge[geom_a["donor_labels"]], edge[geom_a["retic_labels"]]
+        v2, v1 = pick
+        h = net.height
+        (b3, b4), (b5, b6) = [(lab.index(a), lab.index(b)) for a, b in (geom_a["donor_labels"], geom_a["retic_labels"])]
+        u2 = (h[v2] - h[b6]) / (h[b5] - h[b6])
+        lo = max(h[b4], h[v2])
+        u1 = (h[v1] - lo) / (h[b3] - lo)
+        e_hyb = int(np.nonzero((net.edge_src == v1) & (net.edge_dst == v2))[0][0])
+        back = CP.coupled_relocate_reticulation(
+            eng, new_net, new_trees, new_h, case["theta"], rng, pick=b_pick,
+            placement=(d_e, r_e, float(u2), float(u1), float(net.edge_gamma[e_hyb])),
+            choose=lambda i, table, probs: next(j for j in range(table[0].shape[0])
+                                                if signature(CP._member(new_trees[i], table[0][j], table[1][j]), table[2][j]) == sigs[i]))
+        if back is None:
+            continue
+        assert h_fwd + back[3] == pytest.approx(0.0, abs=1e-8)
+        assert np.sort(back[0].height) == pytest.approx(np.sort(net.height), abs=1e-12)
+        done += 1
+    assert done >= 2
 
 
 def test_coupled_add_and_delete_are_exact_reverses():
