@@ -122,7 +122,8 @@ def coupled_gene_tree_reproposal(engine: Any, gene_trees: Sequence[FlatTree], he
 # ---------------------------------------------------------------------------------------------------
 def coupled_add_reticulation(engine: Any, net: Any, gene_trees: Sequence[FlatTree], heights: Sequence[np.ndarray],
                              theta: float, rng: np.random.Generator, placements_for: Any, *, placement: Any = None,
-                             choose: Any = None) -> Optional[Tuple[Any, List[FlatTree], List[np.ndarray], float]]:
+                             choose: Any = None, max_level: Optional[int] = None
+                             ) -> Optional[Tuple[Any, List[FlatTree], List[np.ndarray], float]]:
     """``op_add_reticulation_coupled`` (``src/_mcmc_seq.py:2072-2192``) on flat objects: the informed add move of
     ``netmoves`` followed by the joint gene-tree re-proposal under the NEW network (reverse density under the old
     one).  ``placements_for(network, gene_trees)`` returns the scored placements
@@ -140,6 +141,8 @@ def coupled_add_reticulation(engine: Any, net: Any, gene_trees: Sequence[FlatTre
     if mv is None:
         return None
     new_net, loghr_net = mv
+    if max_level is not None and NM.network_level(new_net) > max_level:      # before the expensive part (:2150-2155)
+        return None
     repro = coupled_gene_tree_reproposal(engine, gene_trees, heights, new_net, net, theta, rng, choose)
     if repro is None:
         return None
@@ -174,7 +177,8 @@ def coupled_delete_reticulation(engine: Any, net: Any, gene_trees: Sequence[Flat
 
 def coupled_relocate_reticulation(engine: Any, net: Any, gene_trees: Sequence[FlatTree], heights: Sequence[np.ndarray],
                                   theta: float, rng: np.random.Generator, *, pick: Any = None, placement: Any = None,
-                                  choose: Any = None) -> Optional[Tuple[Any, List[FlatTree], List[np.ndarray], float]]:
+                                  choose: Any = None, max_level: Optional[int] = None
+                                  ) -> Optional[Tuple[Any, List[FlatTree], List[np.ndarray], float]]:
     """``op_relocate_reticulation_coupled`` (``src/_mcmc_seq.py:2604-2790``): detach a reticulation A (as the delete
     move does), re-attach it at a placement B drawn UNIFORMLY from the geometric placements of the base network,
     re-propose every gene tree under the new network.  The ``1 / K`` selection cancels between the two directions,
@@ -183,7 +187,7 @@ def coupled_relocate_reticulation(engine: Any, net: Any, gene_trees: Sequence[Fl
         log HR = log l2_B + log win_B - log l2_A - log win_A + (log q_r - log q_f).
 
     ``pick=(retic, donor_parent)``, ``placement=(donor_edge, retic_edge, u_t2, u_t1, gamma)`` (edges of the base
-    network) and ``choose`` replace the random draws (tests).  The level cap (``max_level``) is the caller's."""
+    network) and ``choose`` replace the random draws (tests); ``max_level`` is the level cap of ``MCMCSeqPriors``."""
     from . import netmoves as NM
     if pick is None:
         pick = NM.draw_reticulation_to_delete(net, rng)
@@ -219,6 +223,8 @@ def coupled_relocate_reticulation(engine: Any, net: Any, gene_trees: Sequence[Fl
         g = float(rng.random())
     new_net = NM.insert_reticulation(n0, int(d), int(r), lo + win_b * u1, t2, float(g))
     if new_net is None:
+        return None
+    if max_level is not None and NM.network_level(new_net) > max_level:
         return None
     repro = coupled_gene_tree_reproposal(engine, gene_trees, heights, new_net, net, theta, rng, choose)
     if repro is None:

@@ -410,3 +410,66 @@ def delete_reticulation_move(net: SpeciesNetwork, rng: np.random.Generator,
     """``op_delete_reticulation`` without the graph."""
     pick = draw_reticulation_to_delete(net, rng)
     return None if pick is None else delete_reticulation_at(net, pick[0], pick[1], placements_fn)
+
+
+def network_level(net: SpeciesNetwork) -> int:
+    """The level of a network: the largest number of reticulation nodes in one biconnected component of its
+    undirected graph, 0 for a tree (``level`` / ``blobs``, ``src/GraphUtils.py:603-732``; Tarjan's algorithm, here
+    without recursion).  The reticulation moves reject proposals above ``priors.max_level`` before paying for the
+    gene-tree re-proposal (``src/_mcmc_seq.py:2150-2155``)."""
+    n = net.n_nodes
+    if n == 0:
+        return 0
+    adj: List[List[int]] = [[] for _ in range(n)]
+    for s, d in zip(net.edge_src.tolist(), net.edge_dst.tolist()):
+        adj[s].append(d)
+        adj[d].append(s)
+    is_ret = (np.bincount(net.edge_dst, minlength=n) >= 2).tolist()
+    disc = [-1] * n
+    low = [0] * n
+    parent = [-1] * n
+    edge_stack: List[Tuple[int, int]] = []
+    best = 0
+    time = 0
+
+    def close(until: Tuple[int, int]) -> None:
+        nonlocal best
+        nodes = set()
+        while edge_stack:
+            a, b = edge_stack.pop()
+            nodes.add(a)
+            nodes.add(b)
+            if (a, b) == until or (b, a) == until:
+                break
+        best = max(best, sum(1 for v in nodes if is_ret[v]))
+
+    for root in range(n):
+        if disc[root] != -1:
+            continue
+        disc[root] = low[root] = time
+        time += 1
+        stack = [(root, 0)]
+        while stack:
+            u, k = stack[-1]
+            if k < len(adj[u]):
+                stack[-1] = (u, k + 1)
+                v = adj[u][k]
+                if disc[v] == -1:
+                    parent[v] = u
+                    edge_stack.append((u, v))
+                    disc[v] = low[v] = time
+                    time += 1
+                    stack.append((v, 0))
+                elif v != parent[u] and disc[v] < disc[u]:
+                    edge_stack.append((u, v))
+                    low[u] = min(low[u], disc[v])
+            else:
+                stack.pop()
+                if stack:
+                    p = stack[-1][0]
+                    low[p] = min(low[p], low[u])
+                    if low[u] >= disc[p]:
+                        close((p, u))
+        if edge_stack:
+            close(edge_stack[-1])
+    return best

@@ -17,6 +17,7 @@ from _ref_loader import load_reference  # noqa: E402
 
 load_reference()
 from phynetpy._mcmc_seq import MCMCSeqPriors, log_prior_seq  # noqa: E402
+from phynetpy.GraphUtils import level  # noqa: E402
 from phynetpy.Network import Network  # noqa: E402
 from phynetpy.models import BranchLengthUnit  # noqa: E402
 
@@ -37,7 +38,7 @@ SETTINGS = [
 def main():
     rng = np.random.default_rng(99)
     cases = []
-    nets = [(3, 0), (5, 0), (4, 1), (5, 1), (6, 2), (7, 3), (6, 1), (8, 4), (5, 2), (4, 2)]
+    nets = [(3, 0), (5, 0), (4, 1), (5, 1), (6, 2), (7, 3), (6, 1), (8, 4), (5, 2), (4, 2), (12, 3), (16, 4), (10, 5)]
     for n_leaves, n_retic in nets:
         nodes, edges = random_network(n_leaves, n_retic, rng, height=0.06)
         nw = enewick(nodes, edges)
@@ -48,7 +49,8 @@ def main():
             for theta in (0.02, 0.003):
                 v = log_prior_seq(net, theta, pri)
                 vals.append({"priors": kw, "theta": theta, "value": None if math.isinf(v) else float(v)})
-        cases.append({"name": "n%d_r%d" % (n_leaves, n_retic), "newick": nw, "network": export_network(net), "values": vals})
+        cases.append({"name": "n%d_r%d" % (n_leaves, n_retic), "newick": nw, "network": export_network(net), "values": vals,
+                      "level": int(level(net))})
         print(cases[-1]["name"], [None if v["value"] is None else round(v["value"], 3) for v in vals[:6]])
     # the reference's own bubble / tiny-cycle guard: a reticulation whose parents are parent and child (3-cycle)
     nw = "((A:0.02,(B:0.01)#H1:0.01[&gamma=0.4])x:0.01,#H1:0.02[&gamma=0.6])r;"
@@ -57,7 +59,7 @@ def main():
     for kw in SETTINGS:
         v = log_prior_seq(net, 0.02, MCMCSeqPriors(**kw))
         vals.append({"priors": kw, "theta": 0.02, "value": None if math.isinf(v) else float(v)})
-    cases.append({"name": "three_cycle", "newick": nw, "network": export_network(net), "values": vals})
+    cases.append({"name": "three_cycle", "newick": nw, "network": export_network(net), "values": vals, "level": int(level(net))})
     print(cases[-1]["name"], [v["value"] for v in vals])
     out = os.path.join(HERE, "prior_cases.json")
     with open(out, "w") as f:

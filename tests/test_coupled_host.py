@@ -285,3 +285,17 @@ def test_coupled_add_and_delete_are_exact_reverses():
         assert old_net.n_reticulations() == net.n_reticulations()
         done += 1
     assert done >= 2
+
+
+def test_level_cap_rejects_before_the_reproposal():
+    case = next(c for c in MOVE_CASES if sum(c["network"]["is_retic"]) >= 1)
+    eng, net, trees, heights, placements_for = _setup_move_case(case)
+    calls0 = eng.calls
+    rng = np.random.default_rng(2)
+    # every added reticulation lands in or next to the existing blob or makes its own: with a cap of 0 nothing passes
+    out = CP.coupled_add_reticulation(eng, net, trees, heights, case["theta"], rng, placements_for, max_level=0)
+    assert out is None and eng.calls == calls0            # declined without a single scoring call
+    out = CP.coupled_relocate_reticulation(eng, net, trees, heights, case["theta"], rng, max_level=0)
+    assert out is None and eng.calls == calls0
+    out = CP.coupled_add_reticulation(eng, net, trees, heights, case["theta"], rng, placements_for, max_level=5)
+    assert out is None or out[0].n_reticulations() == net.n_reticulations() + 1

@@ -39,3 +39,15 @@ def test_cycle_sizes():
     assert reticulation_cycle_size([[], [0, 0]], 1) == 2
     assert reticulation_cycle_size([[], [0]], 1) == 0
     assert log_prior_seq(SpeciesNetwork.from_newick("((A:1,B:1)x:1,C:2)r;"), 0.0, SeqPriors()) == -math.inf     # theta <= 0
+
+
+def test_network_level_equals_the_reference():
+    from phynetpy_b200.netmoves import network_level
+    levels = set()
+    for case in CASES:
+        for net in (SpeciesNetwork.from_dict(case["network"]), SpeciesNetwork.from_newick(case["newick"])):
+            assert network_level(net) == case["level"]
+        levels.add(case["level"])
+    assert {0, 1, 2, 3, 4} <= levels
+    # several reticulations, yet level 1 (galled): the cap distinguishes blobs, not counts
+    assert any(c["level"] == 1 and sum(c["network"]["is_retic"]) >= 2 for c in CASES)
