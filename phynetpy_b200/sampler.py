@@ -89,8 +89,8 @@ def species_tree_from_concatenation(loci: Sequence[Dict[str, str]], mapping: Dic
 
 
 class FlatMCMCSeq:
-    """``MCMC_SEQ(loci, mapping, priors=..., model=...)`` with a flat state; ``engine`` may be supplied (tests use
-    one backed by the CPU oracles), otherwise a :class:`SeqLikelihoodEngine` on the default device is built."""
+    """``MCMC_SEQ(loci, mapping, priors=..., model=...)`` with a flat state; ``engine`` may be supplied (the CPU tests pass
+    one over a fake device), otherwise a :class:`SeqLikelihoodEngine` on the default device is built."""
 
     def __init__(self, loci: Sequence[Dict[str, str]], mapping: Dict[str, List[str]], *, priors: Optional[SeqPriors] = None,
                  model: Any = None, theta: Optional[float] = None, gene_trees: Optional[Sequence[FlatTree]] = None,
