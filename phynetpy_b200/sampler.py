@@ -17,7 +17,9 @@ unless ``coupled_dimension_moves``), the same accept rule (``log u < (post' - po
 cannot be built, or whose posterior is not finite, is a rejection) and the same copy-and-swap discipline: a
 rejected proposal is undone by ``restore_caches``, which also rolls the pending device partials back.
 
-Deliberately small: no MC3 ladder, no warm start from MCMC_GT, no trace files -- those stay the reference's.  Random
+Deliberately small: a single chain (:meth:`FlatMCMCSeq.search`) and the MC3 ladder in lockstep
+(:meth:`FlatMCMCSeq.search_mc3`, all chains' dirty loci in one device call); no warm start from MCMC_GT, no control
+hooks, no trace files -- those stay the reference's.  Random
 streams are not comparable with the reference's (its node enumeration follows the hash order of Python sets).
 """
 from __future__ import annotations
@@ -184,6 +186,32 @@ class FlatMCMCSeq:
         raise ValueError("unknown operator %r" % name)
 
     # -- the chain --------------------------------------------------------------------------------------
+    def _apply(self, prop) -> None:
+        """Tell the engine what a proposal changed (its evaluation then recomputes exactly that)."""
+        _loghr, _net, trees, _heights, _theta, dirty, net_dirty = prop
+        eng = self.engine
+        if dirty == "all":
+            for i in range(len(trees)):
+                eng.invalidate_locus(i)
+        elif dirty:
+            for i in dirty:
+                eng.invalidate_locus(i)
+        if net_dirty:
+            eng.invalidate_network()
+
+    def _adopt(self, prop, new: float) -> None:
+        _loghr, net, trees, heights, theta, _dirty, _net_dirty = prop
+        self.net, self.trees, self.heights, self.theta = net, list(trees), list(heights), theta
+
+    def _sample(self, it: int, cur: float) -> FlatSample:
+        rets = MV.reticulations(self.net).tolist()
+        gmaj = None
+        if rets:
+            g = self.net.edge_gamma[np.isin(self.net.edge_dst, rets)]
+            g = g[g == g]
+            gmaj = float(g.max()) if g.shape[0] else None
+        return FlatSample(it, cur, cur - self.log_prior(), self.theta, len(rets), gmaj, self.net)
+
     def search(self, *, num_iter: int = 20000, burn_in: int = 5000, sample_freq: int = 100, seed: Any = None) -> FlatResult:
         rng = np.random.default_rng(seed)
         names = [n for n, _ in OPERATORS]
@@ -208,18 +236,11 @@ class FlatMCMCSeq:
                 prop = None                          # an operator that fails is a rejection (:2878-2881)
                 eng.restore_caches(snap)
             if prop is not None:
-                loghr, net, trees, heights, theta, dirty, net_dirty = prop
-                if dirty == "all":
-                    for i in range(len(trees)):
-                        eng.invalidate_locus(i)
-                elif dirty:
-                    for i in dirty:
-                        eng.invalidate_locus(i)
-                if net_dirty:
-                    eng.invalidate_network()
-                new = eng.log_likelihood(trees, net, theta) + log_prior_seq(net, theta, self.priors)
-                if math.isfinite(new) and math.log(rng.random()) < (new - cur) + loghr:
-                    self.net, self.trees, self.heights, self.theta, cur = net, list(trees), list(heights), theta, new
+                self._apply(prop)
+                new = eng.log_likelihood(prop[2], prop[1], prop[4]) + log_prior_seq(prop[1], prop[4], self.priors)
+                if math.isfinite(new) and math.log(rng.random()) < (new - cur) + prop[0]:
+                    self._adopt(prop, new)
+                    cur = new
                     accepted += 1
                     counts[name][1] += 1
                     if cur > best[0]:
@@ -227,12 +248,105 @@ class FlatMCMCSeq:
                 else:
                     eng.restore_caches(snap)
             if it > burn_in and sample_freq > 0 and (it - burn_in) % sample_freq == 0:
-                rets = MV.reticulations(self.net).tolist()
-                gmaj = None
-                if rets:
-                    g = self.net.edge_gamma[np.isin(self.net.edge_dst, rets)]
-                    g = g[g == g]
-                    gmaj = float(g.max()) if g.shape[0] else None
-                samples.append(FlatSample(it, cur, cur - self.log_prior(), self.theta, len(rets), gmaj, self.net))
+                samples.append(self._sample(it, cur))
         return FlatResult(best[1], best[0], best[2], best[3], samples, accepted / max(num_iter, 1), num_iter,
                           time.perf_counter() - t0, counts)
+
+    # -- Metropolis-coupled chains (MC3) ---------------------------------------------------------------------
+    def fork(self, engine: Any) -> "FlatMCMCSeq":
+        """A second chain on the same data and starting state, with its own engine (its own partials cache)."""
+        other = FlatMCMCSeq.__new__(FlatMCMCSeq)
+        other.__dict__.update(self.__dict__)
+        other.trees, other.heights = list(self.trees), list(self.heights)
+        other.engine = engine
+        return other
+
+    def search_mc3(self, temperatures: Sequence[float], *, engines: Optional[Sequence[Any]] = None, num_iter: int = 20000,
+                   burn_in: int = 5000, sample_freq: int = 100, swap_interval: int = 1, seed: Any = None) -> FlatResult:
+        """The reference's MC3 ladder (``_mc3``, ``src/_mcmc_seq.py:3584-3723``) in lockstep: chain c targets
+        ``posterior ** (1 / T_c)`` (accept if ``log u < (post' - post) / T_c + log HR``), adjacent chains swap states
+        with log ratio ``(1/T_i - 1/T_j) (post_j - post_i)`` every ``swap_interval`` iterations, the coldest chain is
+        sampled.  What differs is the evaluation: all chains propose first, then the dirty loci of ALL chains are
+        scored in one device call (``SeqLikelihoodEngine.log_likelihood_many``) -- T chains, one launch.
+        ``engines``: one engine per additional chain (built on the default device when omitted)."""
+        m = len(temperatures)
+        if m < 2:
+            return self.search(num_iter=num_iter, burn_in=burn_in, sample_freq=sample_freq, seed=seed)
+        betas = [1.0 / float(t) for t in temperatures]
+        cold = int(min(range(m), key=lambda i: temperatures[i]))
+        if engines is None:
+            engines = [SeqLikelihoodEngine(self.loci, self.species_of, self.model) for _ in range(m - 1)]
+        if len(engines) != m - 1:
+            raise ValueError("search_mc3: one engine per additional chain")
+        chains = [self] + [self.fork(e) for e in engines]
+        ss = seed if isinstance(seed, np.random.SeedSequence) else np.random.SeedSequence(seed)
+        rngs = [np.random.default_rng(s) for s in ss.spawn(m)]
+        swap_rng = np.random.default_rng(ss.spawn(1)[0])
+        names = [n for n, _ in OPERATORS]
+        weights = np.asarray([w for _, w in OPERATORS], dtype=np.float64)
+        weights /= weights.sum()
+        many = type(self.engine).log_likelihood_many
+        t0 = time.perf_counter()
+        liks = many([c.engine for c in chains], [c.trees for c in chains], [c.net for c in chains], [c.theta for c in chains])
+        curs = [lk + c.log_prior() for lk, c in zip(liks, chains)]
+        if not all(math.isfinite(x) for x in curs):
+            raise RuntimeError("the starting state has zero posterior")
+        best = (curs[cold], chains[cold].net, chains[cold].theta, list(chains[cold].trees))
+        samples: List[FlatSample] = []
+        counts = {n: [0, 0] for n in names}
+        accepted = swaps = swaps_ok = 0
+        for it in range(1, num_iter + 1):
+            props: List[Any] = []
+            snaps = []
+            for c, ch in enumerate(chains):
+                name = names[int(rngs[c].choice(len(names), p=weights))]
+                if c == cold:
+                    counts[name][0] += 1
+                snaps.append(ch.engine.clone_caches())
+                try:
+                    prop = ch._propose(name, rngs[c])
+                except Exception:
+                    prop = None
+                    ch.engine.restore_caches(snaps[-1])
+                if prop is not None:
+                    ch._apply(prop)
+                props.append((name, prop))
+            # one device call for the dirty loci of every chain (a chain without a proposal has nothing dirty)
+            liks = many([ch.engine for ch in chains],
+                        [p[1][2] if p[1] is not None else ch.trees for p, ch in zip(props, chains)],
+                        [p[1][1] if p[1] is not None else ch.net for p, ch in zip(props, chains)],
+                        [p[1][4] if p[1] is not None else ch.theta for p, ch in zip(props, chains)])
+            for c, ch in enumerate(chains):
+                name, prop = props[c]
+                if prop is None:
+                    continue
+                new = liks[c] + log_prior_seq(prop[1], prop[4], ch.priors)
+                if math.isfinite(new) and math.log(rngs[c].random()) < betas[c] * (new - curs[c]) + prop[0]:
+                    ch._adopt(prop, new)
+                    curs[c] = new
+                    if c == cold:
+                        accepted += 1
+                        counts[name][1] += 1
+                else:
+                    ch.engine.restore_caches(snaps[c])
+            if curs[cold] > best[0]:
+                best = (curs[cold], chains[cold].net, chains[cold].theta, list(chains[cold].trees))
+            if it % swap_interval == 0:
+                i = int(swap_rng.integers(0, m - 1))
+                j = i + 1
+                swaps += 1
+                if math.log(swap_rng.random()) < (betas[i] - betas[j]) * (curs[j] - curs[i]):
+                    # the states migrate, each temperature slot keeps its generator; a state travels WITH its engine,
+                    # whose device caches describe exactly that state
+                    chains[i], chains[j] = chains[j], chains[i]
+                    curs[i], curs[j] = curs[j], curs[i]
+                    swaps_ok += 1
+            if it > burn_in and sample_freq > 0 and (it - burn_in) % sample_freq == 0:
+                samples.append(chains[cold]._sample(it, curs[cold]))
+        # leave this object in the cold chain's final state
+        final = chains[cold]
+        self.net, self.trees, self.heights, self.theta, self.engine = final.net, final.trees, final.heights, final.theta, final.engine
+        res = FlatResult(best[1], best[0], best[2], best[3], samples, accepted / max(num_iter, 1), num_iter,
+                         time.perf_counter() - t0, counts)
+        res.operator_counts["__swaps__"] = [swaps, swaps_ok]
+        return res

@@ -102,3 +102,32 @@ def test_species_tree_start_and_bad_inputs(chain):
     assert frozenset({"A", "B"}) in _clusters(st)
     with pytest.raises(ValueError, match="finite and positive"):
         FlatMCMCSeq(inf.loci, inf.mapping, theta=-1.0, engine=inf.engine)
+
+
+def test_mc3_ladder_in_lockstep_shares_device_calls(chain, monkeypatch):
+    """Two tempered chains: every iteration scores the dirty loci of BOTH chains in one pending evaluation
+    (log_likelihood_many), swaps migrate states together with their engines, the cold chain is the one reported."""
+    inf, dev = chain
+    second = E.SeqLikelihoodEngine([_stub_calc(100 + i, d) for i, d in enumerate(inf.loci)], inf.species_of, inf.model, context=dev)
+    dev.loci = dev.loci + [None] * (100 - len(dev.loci)) + [O.OracleLocus(d) for d in inf.loci]
+    start = inf.score()
+    n_iter = 400
+    res = inf.search_mc3([1.0, 2.5], engines=[second], num_iter=n_iter, burn_in=100, sample_freq=50, swap_interval=2, seed=11)
+    assert math.isfinite(res.map_log_posterior) and res.map_log_posterior >= start
+    assert 0.0 < res.acceptance_rate <= 1.0 and len(res.samples) == 6
+    swaps, swaps_ok = res.operator_counts.pop("__swaps__")
+    assert swaps == n_iter // 2 and 0 < swaps_ok <= swaps
+    assert sum(c[0] for c in res.operator_counts.values()) == n_iter          # cold-chain proposals
+    assert frozenset({"A", "B"}) in _clusters(res.map_network)
+    # pending evaluations: at most ONE per iteration although two chains stepped (plus the initial one); the other
+    # evaluations are the score-only (NOSTORE) batches of the coupled moves
+    pend = [c for c in dev.calls if c[0] == "eval" and c[2] & 0x2]
+    assert len(pend) <= n_iter + 1
+    assert any(c[1] >= 2 for c in pend)                                        # both chains' loci in one call
+    # the cold chain's cached state is its true state
+    final = inf.score()
+    for i in range(len(inf.trees)):
+        inf.engine.invalidate_locus(i)
+    inf.engine.invalidate_network()
+    assert inf.score() == pytest.approx(final, rel=1e-12)
+    assert inf.search_mc3([1.0], num_iter=5, burn_in=0, sample_freq=1, seed=1).num_iterations == 5      # one temperature = plain chain
