@@ -68,6 +68,10 @@ typedef struct pnb_locus pnb_locus;
 PNB_API int         pnb_abi_version(void);
 PNB_API const char *pnb_last_error(void);
 
+/* Number of CUDA devices visible to this process (0 and PNB_OK when there is none).  Used by the
+ * device policy of run_parallel_chains (src/_mcmc_seq.py:4144-4175): chain c -> device c % count. */
+PNB_API int         pnb_device_count(int *count_out);
+
 /* ---- context: one per process per device ------------------------------ */
 /* device < 0 selects the current CUDA device.                             */
 PNB_API int pnb_ctx_create(int device, pnb_ctx **out);

@@ -14,7 +14,8 @@ from typing import Optional
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libphynet_b200.so")
+# PNB_LIB selects a tuning variant of the same library (tools/variants.py); the product path is the in-tree build
+LIB_PATH = os.environ.get("PNB_LIB") or os.path.join(HERE, "libphynet_b200.so")
 
 PNB_OK = 0
 PNB_ERR_INVALID = 1
@@ -31,7 +32,7 @@ EVAL_RESCALE = 0x10
 
 # every symbol include/phynet_b200.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = (
-    "pnb_abi_version", "pnb_last_error",
+    "pnb_abi_version", "pnb_last_error", "pnb_device_count",
     "pnb_ctx_create", "pnb_ctx_destroy", "pnb_ctx_set_stream", "pnb_ctx_synchronize", "pnb_ctx_last_stats",
     "pnb_ctx_set_profiling", "pnb_ctx_last_timings",
     "pnb_model_create_eigen", "pnb_model_create_jc69", "pnb_model_create_explicit", "pnb_model_destroy",
@@ -78,6 +79,7 @@ def load() -> C.CDLL:
         lib.pnb_abi_version.restype = C.c_int
         lib.pnb_last_error.restype = C.c_char_p
         sigs = {
+            "pnb_device_count": [C.POINTER(C.c_int)],
             "pnb_ctx_create": [C.c_int, C.POINTER(_vp)],
             "pnb_ctx_destroy": [_vp],
             "pnb_ctx_set_stream": [_vp, _vp],

@@ -40,19 +40,22 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, out: str = LIB, defs=None) -> str:
+    """Compile every source into one shared library.  ``out`` / ``defs`` build a tuning variant next to the
+    product library (``tools/variants.py``; loaded through ``PNB_LIB=<path>``)."""
+    if out == LIB and not force and not needs_build():
         return LIB
-    defs = os.environ.get("PNB_NVCC_DEFS", "").split()  # tuning knobs, e.g. "-DPNB_PPT=1 -DPNB_MIN_BLOCKS=8"
-    cmd = [_nvcc()] + NVCC_FLAGS + defs + (["-Xptxas", "-v"] if verbose else []) + \
-        [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB + ".tmp"]
+    if defs is None:
+        defs = os.environ.get("PNB_NVCC_DEFS", "").split()  # tuning knobs, e.g. "-DPNB_PPT=1 -DPNB_MIN_BLOCKS=8"
+    cmd = [_nvcc()] + NVCC_FLAGS + list(defs) + (["-Xptxas", "-v"] if verbose else []) + \
+        [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out + ".tmp"]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
-    os.replace(LIB + ".tmp", LIB)
+    os.replace(out + ".tmp", out)
     if verbose:
         sys.stderr.write(proc.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

@@ -115,6 +115,17 @@ using namespace pnb;
 extern "C" int pnb_abi_version(void) { return PNB_ABI_VERSION; }
 extern "C" const char* pnb_last_error(void) { return g_err; }
 
+extern "C" int pnb_device_count(int* count_out) {
+    PNB_REQUIRE(count_out != nullptr, PNB_ERR_INVALID, "pnb_device_count: count_out is NULL");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        (void)cudaGetLastError();
+        n = 0;
+    }
+    *count_out = n;
+    return PNB_OK;
+}
+
 extern "C" int pnb_ctx_create(int device, pnb_ctx** out) {
     PNB_REQUIRE(out != nullptr, PNB_ERR_INVALID, "pnb_ctx_create: out is NULL");
     *out = nullptr;

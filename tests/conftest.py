@@ -19,6 +19,8 @@ os.environ.setdefault("PNB_CHUNK_MIN_JOBS", "128")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+if os.path.join(ROOT, "tests") not in sys.path:
+    sys.path.insert(0, os.path.join(ROOT, "tests"))   # shared helpers (dropin_common)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
