@@ -64,10 +64,19 @@ int pnb::compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int3
                memcmp(T.parent.data(), parent, static_cast<size_t>(n) * sizeof(int32_t)) == 0 &&
                (!tip_row || memcmp(T.tip_row.data(), tip_row, static_cast<size_t>(n) * sizeof(int32_t)) == 0);
     };
-    auto refresh_program = [&](const pnb_locus::Template& T) {
+    const Op* res_ops = nullptr;
+    auto refresh_program = [&](pnb_locus::Template& T) {
         const int n_ops_t = T.jo.n_ops;
-        // with a valid device-resident copy of the program only the branch lengths travel
-        if (n_ops_t > 0 && !T.d_ops_valid) memcpy(ops, T.ops.data(), static_cast<size_t>(n_ops_t) * sizeof(Op));
+        // with a valid device-resident copy of the program only the branch lengths travel.  The decision is
+        // taken HERE (caller holds the template read lock, or owns the locus in store mode) and travels with
+        // the job: a later job of the same batch may rebuild the template, but never rewrites a buffer that
+        // carries this batch's mark (pnb_eval gives the rebuilt program a fresh buffer instead).
+        if (n_ops_t > 0 && T.d_ops_valid && T.d_ops) {
+            res_ops = T.d_ops;
+            T.d_ops_used_mark.store(loc->ctx->batch_counter, std::memory_order_relaxed);
+        } else if (n_ops_t > 0) {
+            memcpy(ops, T.ops.data(), static_cast<size_t>(n_ops_t) * sizeof(Op));
+        }
         for (int k = 0; k < n_ops_t; ++k) {
             const int c = T.op_child[k];
             t_out[k] = eff_len(c);
@@ -79,7 +88,7 @@ int pnb::compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int3
     const bool rescale = (flags & PNB_EVAL_RESCALE) != 0;
     if (!nostore && full && !(flags & PNB_EVAL_PENDING) && loc->committed_from_tmpl && C.valid &&
         C.rescale == rescale && loc->tmpl[0].n_slots == loc->n_slots && same_topology(loc->tmpl[0])) {
-        const pnb_locus::Template& T0 = loc->tmpl[0];
+        pnb_locus::Template& T0 = loc->tmpl[0];
         refresh_program(T0);
         const size_t ne = T0.kid_child.size();
         for (size_t e = 0; e < ne; ++e) C.kid_len[e] = dbits(eff_len(T0.kid_child[e]));
@@ -91,6 +100,7 @@ int pnb::compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int3
         jo->in_place = true;
         jo->tmpl_hit = 0;
         jo->tmpl_new = -1;
+        jo->res_ops = res_ops;
         return PNB_OK;
     }
     if (!nostore) {
@@ -136,6 +146,7 @@ int pnb::compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int3
         jo->in_place = false;
         jo->tmpl_hit = nostore ? 1 : 0;
         jo->tmpl_new = -1;
+        jo->res_ops = res_ops;
         return PNB_OK;
     }
     read_guard.release();
@@ -445,6 +456,7 @@ int pnb::compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int3
     jo->tmpl_hit = -1;
     jo->tmpl_new = -1;
     jo->in_place = false;
+    jo->res_ops = nullptr;
     int expect0 = 0;
     const bool write_locked = all_dirty_canonical &&
                               loc->tmpl_lock.compare_exchange_strong(expect0, -1, std::memory_order_acquire);
@@ -464,6 +476,7 @@ int pnb::compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int3
         jo->tmpl_new = nostore ? 1 : 0;
         T.jo = *jo;
         T.jo.tmpl_new = -1;
+        T.jo.res_ops = nullptr;
         if (!nostore) {
             T.cache = loc->pending;
             T.kid_child = S.kid_child;
@@ -554,7 +567,7 @@ extern "C" int pnb_plan(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
             return jo.rc >= 100 ? PNB_ERR_STATE : jo.rc;
         }
         // a template hit with a valid resident copy does not rewrite the program: hand it out anyway
-        if (jo.tmpl_hit >= 0 && loc->tmpl[jo.tmpl_hit].d_ops_valid && jo.n_ops > 0)
+        if (jo.tmpl_hit >= 0 && jo.res_ops && jo.n_ops > 0)
             memcpy(reinterpret_cast<Op*>(ops_out) + o, loc->tmpl[jo.tmpl_hit].ops.data(), static_cast<size_t>(jo.n_ops) * sizeof(Op));
         const bool cached = jo.root_clean_cached;
         if (auto_commit && !jo.in_place) locus_commit(loc);

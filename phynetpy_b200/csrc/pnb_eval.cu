@@ -80,6 +80,8 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
     // ---- pass 0: validate, size the staging regions, make sure partial slots exist ---------
     // (parallel over jobs for large batches: at 10^4 loci even this bookkeeping is milliseconds)
     const uint32_t mark = ++ctx->batch_counter;
+    for (auto& pr : ctx->deferred_release) ctx->arena.release(pr.first, pr.second);  // stream order protects reuse
+    ctx->deferred_release.clear();
     const int n_workers = ctx->pool ? ctx->pool->size() : 0;
     auto parallel_for = [&](int64_t n, int64_t min_parallel, const std::function<void(int, int64_t, int64_t)>& fn) {
         if (n >= min_parallel && n_workers > 1) {
@@ -248,9 +250,8 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
         jd.out_index = static_cast<int32_t>(j);
         jd.scale = loc->d_scale;
         jd.pad0 = 0;
-        const pnb_locus::Template* Th = jo.tmpl_hit >= 0 ? &loc->tmpl[jo.tmpl_hit] : nullptr;
-        const bool resident = Th && Th->d_ops_valid && jo.n_ops > 0;
-        jd.ops = resident ? Th->d_ops : reinterpret_cast<const Op*>(desc_prog_base + off_ops) + o;
+        const bool resident = jo.res_ops != nullptr && jo.n_ops > 0;   // decided under the template lock (compile_job)
+        jd.ops = resident ? jo.res_ops : reinterpret_cast<const Op*>(desc_prog_base + off_ops) + o;
         if (!resident && jo.n_ops > 0) {
             if (A.prog_lo < 0 || o < A.prog_lo) A.prog_lo = o;
             A.prog_hi = std::max(A.prog_hi, o + jo.n_ops);
@@ -445,8 +446,14 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
             // program IS the template's final program may publish the device copy
             if (!Tn.valid || Tn.jo.n_ops != nops ||
                 memcmp(Tn.ops.data(), h_ops + o_chk, static_cast<size_t>(nops) * sizeof(Op)) != 0) continue;
-            if (Tn.d_ops_cap < nops) {
-                if (Tn.d_ops) ctx->arena.release(Tn.d_ops, static_cast<size_t>(Tn.d_ops_cap) * sizeof(Op));
+            // never rewrite a buffer that a job of THIS batch reads in place (an earlier job of the same locus hit the
+            // previous template): the rebuilt program gets a fresh buffer, the old one is recycled at the next call
+            const bool in_use = Tn.d_ops && Tn.d_ops_used_mark.load(std::memory_order_relaxed) == mark;
+            if (Tn.d_ops_cap < nops || in_use) {
+                if (Tn.d_ops) {
+                    if (in_use) ctx->deferred_release.emplace_back(Tn.d_ops, static_cast<size_t>(Tn.d_ops_cap) * sizeof(Op));
+                    else ctx->arena.release(Tn.d_ops, static_cast<size_t>(Tn.d_ops_cap) * sizeof(Op));
+                }
                 void* pp = nullptr;
                 const int cap = std::max(nops, 64);
                 if (ctx->arena.alloc(static_cast<size_t>(cap) * sizeof(Op), &pp) != PNB_OK) { Tn.d_ops = nullptr; Tn.d_ops_cap = 0; continue; }

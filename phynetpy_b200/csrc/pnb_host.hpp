@@ -86,6 +86,8 @@ struct JobOut {
     bool in_place = false;      // the committed cache was refreshed in place: nothing to commit
     int8_t tmpl_hit = -1;       // >= 0: program taken from tmpl[tmpl_hit]; its resident device copy can be used
     int8_t tmpl_new = -1;       // >= 0: tmpl[tmpl_new] was (re)built by this job and needs its device copy
+    const Op* res_ops = nullptr; // template hit served from the locus' device-resident program (captured under the
+                                 // template read lock; the buffer is not rewritten while this batch references it)
 };
 
 // Per-thread scratch of the tree compiler (no allocation in steady state).
@@ -233,6 +235,8 @@ struct pnb_ctx {
     std::vector<int64_t> job_of_batch;
     std::vector<int64_t> save_list;
     std::vector<int64_t> tile_first;   // per job of the batch: its first tile (prefix sum, M + 1 entries)
+    // device program buffers replaced while a batch still referenced them: back to the arena at the next call
+    std::vector<std::pair<void*, size_t>> deferred_release;
 };
 
 struct pnb_locus {
@@ -287,6 +291,10 @@ struct pnb_locus {
         pnb::Op* d_ops = nullptr;   // device-resident copy of `ops` (arena): template hits send no program
         int32_t d_ops_cap = 0;      // capacity of d_ops in ops
         bool d_ops_valid = false;   // d_ops holds (or a stream-ordered copy will hold) exactly `ops`
+        std::atomic<uint32_t> d_ops_used_mark{0};  // batch (ctx->batch_counter) whose jobs read d_ops in place
+        Template() = default;
+        Template(const Template&) = delete;
+        Template& operator=(const Template&) = delete;
     };
     Template tmpl[2];
     // readers/writer spin state for tmpl[] (a NOSTORE batch may hold the same locus many times and is

@@ -749,3 +749,35 @@ def test_several_engines_in_one_device_call():
     other = P.SeqLikelihoodEngine(loci, None, P.JC69())
     with pytest.raises(ValueError, match="share context, model"):
         P.SeqLikelihoodEngine.log_likelihood_many([chains[0], other], [new[0], new[0]])
+
+
+def test_resident_program_is_not_rewritten_under_a_batch_that_reads_it():
+    """Score-only batches on a locus WITHOUT a committed cache: batch [Z] makes Z's program device-resident;
+    batch [Z, A, Z, B, Z] lets a later job of the same locus rebuild the template (other topology, same op count)
+    while an earlier job of that batch reads the resident copy in place.  Every value must still be its own
+    tree's (round-1 advisory: the rebuilt program used to be copied over the buffer the earlier job read)."""
+    P = _pkg()
+    from phynetpy_b200 import simulate as S
+    rng = np.random.default_rng(2024)
+    n = 12
+    par, bl = S.random_trees(3, n, rng, height=0.3)
+    aln = S.simulate_alignments(par[:1], bl[:1], 400, S.DEFAULT_PI, S.DEFAULT_RATES, rng)[0]
+    d = S.to_alignment_dict(aln)
+    Z, A, B = S.flat_trees(par, bl)
+    model = P.GTR(S.DEFAULT_PI, S.DEFAULT_RATES)
+    om = O.gtr(S.DEFAULT_PI, S.DEFAULT_RATES)
+    locus = O.OracleLocus(d)
+    want = {id(t): O.log_likelihood(locus, _otree(t), om) for t in (Z, A, B)}
+    for rep in range(3):
+        eng = P.SeqLikelihoodEngine([d], None, model)        # fresh, uncommitted locus each time
+        v1 = eng.score_candidates(0, [Z])
+        assert rel_err(v1[0], want[id(Z)]) <= REL
+        batch = [Z, A, Z, B, Z, A]
+        v2 = eng.score_candidates(0, batch)
+        for t, v in zip(batch, v2):
+            assert rel_err(v, want[id(t)]) <= REL, (rep, v, want[id(t)])
+        assert v2[0] == v2[2] == v2[4] == v1[0] and v2[1] == v2[5]
+        # many repetitions in one batch: several workers, several rebuilds
+        big = [Z, A, B] * 200
+        v3 = eng.score_candidates(0, big)
+        assert all(v3[k] == v2[(0, 1, 3)[k % 3]] for k in range(len(big)))
