@@ -178,6 +178,37 @@ PNB_API int pnb_eval(pnb_ctx *ctx, const pnb_model *m, int64_t M, pnb_locus *con
 PNB_API int pnb_commit(pnb_ctx *ctx, int64_t M, pnb_locus *const *loci);
 PNB_API int pnb_rollback(pnb_ctx *ctx, int64_t M, pnb_locus *const *loci);
 
+/* ---- resident batches: fixed (locus, topology) jobs, lengths-only evaluations ------------------- */
+/* The steady state of a sharded full evaluation (BASELINE cfg5; the loop body of
+ * _SeqLikelihoodEngine.log_likelihood, src/_mcmc_seq.py:746-750, over ALL loci with unchanged topologies):
+ * pnb_batch_create compiles the M jobs once (same arrays as pnb_eval, no lengths) and keeps op programs,
+ * job descriptors and the tile map in HBM; pnb_batch_eval then takes ONLY the branch lengths, in the node
+ * order of the creation arrays (total_nodes doubles; NaN = None -> 0, src/_seq_likelihood.py:419-420):
+ *   - host pointer (pinned memory is uploaded asynchronously in chunks that overlap the pruning of the
+ *     previous chunk; pageable memory is staged through the batch's pinned buffer, pnb_batch_blen_host), or
+ *   - with PNB_BATCH_BLEN_DEVICE a device pointer that is read in place,
+ * computes P(t) per edge on the device and launches the pruning kernel.  No tree is compiled and no per-locus
+ * host state is touched per evaluation.  Results are bit-identical to pnb_eval(PNB_EVAL_FULL) on the same
+ * trees.  Creation flags: PNB_EVAL_NOSTORE (score only) or 0 (every evaluation is committed: the loci's
+ * cached partials describe the last evaluated lengths, so a later dirty-path pnb_eval on any of them starts
+ * from there), optionally PNB_EVAL_RESCALE.  Evaluation flags: PNB_EVAL_OUT_DEVICE (logL_out[M] is a
+ * device pointer, e.g. this rank's slice of the NCCL buffer; no host synchronisation) and
+ * PNB_BATCH_BLEN_DEVICE.  A batch whose locus is destroyed or re-allocated answers PNB_ERR_STATE: create
+ * it again.  Explicit (host P) models are not supported here.                                        */
+#define PNB_BATCH_BLEN_DEVICE 0x20u
+typedef struct pnb_batch pnb_batch;
+PNB_API int pnb_batch_create(pnb_ctx *ctx, const pnb_model *m, int64_t M, pnb_locus *const *loci,
+                             const int64_t *node_off, const int32_t *parent, const int32_t *tip_row,
+                             uint32_t flags, pnb_batch **out);
+PNB_API int pnb_batch_destroy(pnb_batch *b);
+/* info: [0] jobs, [1] nodes, [2] ops, [3] tiles, [4] site-node updates per evaluation, [5] internal nodes,
+ * [6] dynamic shared memory per block, [7] upload chunks                                              */
+PNB_API int pnb_batch_info(const pnb_batch *b, int64_t info[8]);
+/* The batch's pinned staging buffer (total_nodes doubles): lengths written here are uploaded without a copy. */
+PNB_API int pnb_batch_blen_host(pnb_batch *b, double **pinned_out);
+PNB_API int pnb_batch_eval(pnb_batch *b, const pnb_model *m, const double *blen, double site_rate,
+                           uint32_t flags, double *logL_out);
+
 /* ---- K-m: timed MSNC density log P(g | Psi) ---------------------- */
 /* The other factor of the MCMC_SEQ likelihood, sum_i [log P(S_i|g_i) + log P(g_i|Psi)]
  * (src/_mcmc_seq.py:745-761).  A species network handle replaces _NetworkIndex +

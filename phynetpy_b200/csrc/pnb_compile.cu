@@ -86,7 +86,8 @@ int pnb::compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int3
     // ---- fastest path: a full, immediately committed re-evaluation of the topology the committed
     // cache already describes (same slots): refresh branch lengths in place, no pending image.
     const bool rescale = (flags & PNB_EVAL_RESCALE) != 0;
-    if (!nostore && full && !(flags & PNB_EVAL_PENDING) && loc->committed_from_tmpl && C.valid &&
+    const bool no_tmpl = (flags & PNB_COMPILE_NO_TEMPLATE) != 0;  // resident batches own their programs
+    if (!no_tmpl && !nostore && full && !(flags & PNB_EVAL_PENDING) && loc->committed_from_tmpl && C.valid &&
         C.rescale == rescale && loc->tmpl[0].n_slots == loc->n_slots && same_topology(loc->tmpl[0])) {
         pnb_locus::Template& T0 = loc->tmpl[0];
         refresh_program(T0);
@@ -114,7 +115,7 @@ int pnb::compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int3
     // ---- fast path: same topology as the last all-dirty compilation of this locus --------------
     pnb_locus::Template& T = loc->tmpl[nostore ? 1 : 0];
     bool read_locked = false;
-    if (all_dirty_canonical) {
+    if (all_dirty_canonical && !no_tmpl) {
         int v = loc->tmpl_lock.load(std::memory_order_acquire);
         while (v >= 0 && !loc->tmpl_lock.compare_exchange_weak(v, v + 1, std::memory_order_acquire)) {}
         read_locked = v >= 0;
@@ -458,7 +459,7 @@ int pnb::compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int3
     jo->in_place = false;
     jo->res_ops = nullptr;
     int expect0 = 0;
-    const bool write_locked = all_dirty_canonical &&
+    const bool write_locked = all_dirty_canonical && !no_tmpl &&
                               loc->tmpl_lock.compare_exchange_strong(expect0, -1, std::memory_order_acquire);
     if (write_locked && templ_ok && n_dirty == n_internal) {
         T.valid = true;

@@ -192,6 +192,29 @@ pnb_pmatrix_kernel(const __grid_constant__ ModelParams mp, const double* __restr
     for (int i = 0; i < 4; ++i) stg256(o + i * 4, Pm[i * 4 + 0], Pm[i * 4 + 1], Pm[i * 4 + 2], Pm[i * 4 + 3]);
 }
 
+// K-a for resident batches: op k takes the length of tree node node_of_op[k] from a node-ordered array
+// that lives in HBM (the caller's, or the batch's upload buffer); same arithmetic as the host's
+// eff_len (None/NaN -> 0, * site_rate, clamp) followed by pmatrix_of_t, so P is bit-identical to the
+// pnb_eval path.  keep != NULL: remember the raw length per node (what a later locus_sync reads).
+__global__ void __launch_bounds__(128)
+pnb_pmatrix_gather_kernel(const __grid_constant__ ModelParams mp, const double* __restrict__ blen,
+                          const int32_t* __restrict__ node_of_op, double site_rate, int64_t n_ops,
+                          double* __restrict__ P_out, double* __restrict__ keep) {
+    const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (g >= n_ops) return;
+    const int32_t node = node_of_op[g];
+    const double raw = blen[node];
+    if (keep) keep[node] = raw;
+    double t = raw;
+    if (t != t) t = 0.0;
+    t *= site_rate;
+    double Pm[16];
+    pmatrix_of_t(mp, t, Pm);
+    double* o = P_out + g * 16;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) stg256(o + i * 4, Pm[i * 4 + 0], Pm[i * 4 + 1], Pm[i * 4 + 2], Pm[i * 4 + 3]);
+}
+
 // ------------------------------------------------------------------------
 // K-b / K-c: pruning.  grid = tiles, block = TPB threads, PPT patterns per thread.
 //

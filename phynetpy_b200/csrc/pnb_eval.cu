@@ -27,6 +27,24 @@ int pnb::configure_kernels(pnb_ctx* ctx) {
     return static_cast<int>(se);
 }
 
+int pnb::launch_pmatrix_gather(const ModelParams& mp, const double* d_blen, const int32_t* d_node_of_op, double site_rate,
+                               int64_t n_ops, double* d_P, double* d_keep, cudaStream_t st) {
+    if (n_ops <= 0) return PNB_OK;
+    const int64_t blocks = (n_ops + 127) / 128;
+    pnb_pmatrix_gather_kernel<<<static_cast<unsigned>(blocks), 128, 0, st>>>(mp, d_blen, d_node_of_op, site_rate, n_ops, d_P, d_keep);
+    PNB_CUDA_TRY(cudaGetLastError());
+    return PNB_OK;
+}
+
+int pnb::launch_prune(const PruneLaunch& L, const ModelParams& mp, unsigned grid, size_t dyn_smem, bool rescale,
+                      cudaStream_t st) {
+    if (grid == 0) return PNB_OK;
+    if (rescale) pnb_prune_kernel_t<false, true><<<grid, TPB, dyn_smem, st>>>(L, mp);
+    else pnb_prune_kernel_t<false, false><<<grid, TPB, dyn_smem, st>>>(L, mp);
+    PNB_CUDA_TRY(cudaGetLastError());
+    return PNB_OK;
+}
+
 extern "C" int pnb_pmatrix_batch(pnb_ctx* ctx, const pnb_model* m, const double* t, int64_t nb,
                                  double* P_out) {
     PNB_REQUIRE(ctx && m, PNB_ERR_INVALID, "pnb_pmatrix_batch: NULL handle");
@@ -79,6 +97,9 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
 
     // ---- pass 0: validate, size the staging regions, make sure partial slots exist ---------
     // (parallel over jobs for large batches: at 10^4 loci even this bookkeeping is milliseconds)
+    // loci owned by a resident batch learn lazily what that batch last computed: settle them before the (parallel) passes
+    for (int64_t j = 0; j < M; ++j)
+        if (loci[j] && loci[j]->lazy_batch) locus_sync_slow(loci[j]);
     const uint32_t mark = ++ctx->batch_counter;
     for (auto& pr : ctx->deferred_release) ctx->arena.release(pr.first, pr.second);  // stream order protects reuse
     ctx->deferred_release.clear();

@@ -303,9 +303,25 @@ struct pnb_locus {
     std::atomic<int> tmpl_lock{0};
     std::vector<int32_t> free_slots;
     std::atomic<uint32_t> batch_mark{0};  // duplicate detection inside one pnb_eval batch
+    // resident batches (pnb_batch_*) that hold this locus; lazy_batch != NULL: the committed tree is what that
+    // batch's last evaluation computed, not yet written into `committed` (locus_sync does it on demand)
+    std::vector<struct pnb_batch*> batches;
+    struct pnb_batch* lazy_batch = nullptr;
+    int64_t lazy_job = -1;
 };
 
 namespace pnb {
+constexpr uint32_t PNB_COMPILE_NO_TEMPLATE = 0x80000000u;  // internal compile_job flag: no program templates
+// pnb_batch.cu: bring a locus' committed-tree description up to date with the last evaluation of the resident
+// batch that owns it (lazy: a batch evaluation touches no per-locus host state)
+void locus_sync_slow(pnb_locus* loc);
+inline void locus_sync(pnb_locus* loc) { if (loc->lazy_batch) locus_sync_slow(loc); }
+void locus_detach_batches(pnb_locus* loc);
+// pnb_eval.cu: kernel launchers for the other translation units (the kernels are compiled there only)
+int launch_pmatrix_gather(const ModelParams& mp, const double* d_blen, const int32_t* d_node_of_op, double site_rate,
+                          int64_t n_ops, double* d_P, double* d_keep, cudaStream_t st);
+int launch_prune(const PruneLaunch& L, const ModelParams& mp, unsigned grid, size_t dyn_smem, bool rescale,
+                 cudaStream_t st);
 // pnb_runtime.cu
 void locus_free_partials(pnb_locus* loc);
 void locus_reset_cache(pnb_locus* loc);

@@ -366,6 +366,7 @@ extern "C" int pnb_compress(pnb_ctx* ctx, int use_device, const uint8_t* cols, i
 // locus
 // =====================================================================
 void pnb::locus_free_partials(pnb_locus* loc) {
+    locus_detach_batches(loc);  // resident batches hold the old buffers' addresses
     loc->committed_from_tmpl = loc->pending_from_tmpl = false;
     if (loc->d_scale) loc->ctx->arena.release(loc->d_scale, loc->scale_bytes);
     loc->d_scale = nullptr;
@@ -381,6 +382,8 @@ void pnb::locus_free_partials(pnb_locus* loc) {
 }
 
 void pnb::locus_reset_cache(pnb_locus* loc) {
+    loc->lazy_batch = nullptr;
+    loc->lazy_job = -1;
     loc->committed.clear();
     loc->pending.clear();
     loc->has_pending = false;
@@ -480,8 +483,10 @@ extern "C" int pnb_locus_destroy(pnb_locus* loc) {
         delete loc;
         return PNB_OK;
     }
+    // (resident batches exist on device contexts only)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    locus_detach_batches(loc);
     locus_free_partials(loc);
     for (auto& T : loc->tmpl)
         if (T.d_ops) ctx->arena.release(T.d_ops, static_cast<size_t>(T.d_ops_cap) * sizeof(Op));
@@ -500,6 +505,7 @@ extern "C" int pnb_locus_invalidate(pnb_locus* loc) {
 
 extern "C" int pnb_locus_read_partial(pnb_locus* loc, int32_t node, double* out) {
     PNB_REQUIRE(loc && out, PNB_ERR_INVALID, "pnb_locus_read_partial: NULL argument");
+    locus_sync(loc);
     const auto& c = loc->committed;
     PNB_REQUIRE(c.valid, PNB_ERR_STATE, "pnb_locus_read_partial: no committed tree");
     PNB_REQUIRE(node >= 0 && node < static_cast<int32_t>(c.node_ref.size()), PNB_ERR_INVALID,

@@ -109,6 +109,72 @@ class DeviceContext:
         _lib.check(self._lib.pnb_rollback(self.handle, int(loci.shape[0]), _lib.ptr(loci)))
 
 
+class ResidentBatch:
+    """A fixed set of (locus, topology) jobs resident in HBM (``pnb_batch_*``): evaluations send branch
+    lengths only.  ``flags``: 0 (every evaluation is committed to the loci's partial caches) or
+    ``_lib.EVAL_NOSTORE``, optionally ``| _lib.EVAL_RESCALE``."""
+
+    def __init__(self, ctx: DeviceContext, model_handle: C.c_void_p, loci: np.ndarray, node_off: np.ndarray,
+                 parent: np.ndarray, tip_row: Optional[np.ndarray], flags: int = 0):
+        assert loci.dtype == np.uint64 and node_off.dtype == np.int64 and parent.dtype == np.int32
+        assert tip_row is None or tip_row.dtype == np.int32
+        self._ctx = ctx
+        self._lib = ctx._lib
+        h = C.c_void_p()
+        _lib.check(self._lib.pnb_batch_create(ctx.handle, model_handle, int(loci.shape[0]), _lib.ptr(loci), _lib.ptr(node_off),
+                                              _lib.ptr(parent), _lib.ptr(tip_row), flags, C.byref(h)))
+        self._h = h
+        self._pid = os.getpid()
+        self.n_jobs = int(loci.shape[0])
+        arr = (C.c_int64 * 8)()
+        _lib.check(self._lib.pnb_batch_info(h, arr))
+        self.info = dict(zip(("jobs", "nodes", "ops", "tiles", "updates", "internal_nodes", "smem_bytes", "chunks"),
+                             (int(x) for x in arr)))
+        self.n_nodes = self.info["nodes"]
+        self._pinned: Optional[np.ndarray] = None
+
+    @property
+    def blen_host(self) -> np.ndarray:
+        """The batch's pinned staging buffer as a float64 array (``n_nodes``): lengths written here upload without a copy."""
+        if self._pinned is None:
+            p = C.c_void_p()
+            _lib.check(self._lib.pnb_batch_blen_host(self._h, C.byref(p)))
+            buf = (C.c_double * self.n_nodes).from_address(p.value)
+            self._pinned = np.frombuffer(buf, dtype=np.float64)
+        return self._pinned
+
+    def eval(self, model_handle: C.c_void_p, blen, site_rate: float = 1.0, out_device_ptr: Optional[int] = None
+             ) -> Optional[np.ndarray]:
+        """``blen``: float64 host array in the node order of the creation arrays, or an ``int`` device address."""
+        flags = 0
+        if isinstance(blen, (int, np.integer)):
+            flags |= _lib.BATCH_BLEN_DEVICE
+            blen_ptr = C.c_void_p(int(blen))
+        else:
+            assert blen.dtype == np.float64 and blen.shape[0] == self.n_nodes and blen.flags["C_CONTIGUOUS"]
+            blen_ptr = _lib.ptr(blen)
+        if out_device_ptr is not None:
+            flags |= _lib.EVAL_OUT_DEVICE
+            out, out_ptr = None, C.c_void_p(out_device_ptr)
+        else:
+            out = np.empty(self.n_jobs, dtype=np.float64)
+            out_ptr = _lib.ptr(out)
+        _lib.check(self._lib.pnb_batch_eval(self._h, model_handle, blen_ptr, float(site_rate), flags, out_ptr))
+        return out
+
+    def close(self) -> None:
+        if self._h is not None and self._pid == os.getpid() and self._ctx._h is not None:
+            self._pinned = None
+            self._lib.pnb_batch_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def default_context(device: Optional[int] = None) -> DeviceContext:
     dev = default_device() if device is None else int(device)
     key = (os.getpid(), dev)
