@@ -1,13 +1,16 @@
 #!/usr/bin/env python
-"""bench.py -- site-node partial updates/s of the sequence-likelihood hot path.
+"""bench.py -- site-node partial updates/s of the sequence-likelihood hot path, at 1/2/4/8 B200.
 
-    python bench.py --gpus 1 --steps K --warmup W              # cfg2: 50 taxa x 1e6 patterns, one GPU
-    torchrun --nproc-per-node N bench.py --gpus N ...          # cfg5: 10,000 loci sharded over N GPUs
-    python bench.py --impl reference ...                       # the reference algorithm on the host cores
+    python bench.py --gpus 1 --steps K --warmup W            # cfg5 on one GPU (+ the cfg2 roofline run and the chain block)
+    torchrun --nproc-per-node N bench.py --gpus N ...        # cfg5: 10,000 loci sharded over N GPUs
+    python bench.py --impl reference ...                     # the reference's own CPU path on the host cores
+    python bench.py --workload cfg2|cfg3|cfg4 ...            # one other BASELINE configuration as the headline
 
-One "step" = one full log-likelihood evaluation (every internal node recomputed,
-P(t) of every branch, root reduction) of the workload.  Prints ONE JSON line.
-See DESIGN.md "Measurement" for every field.
+The headline workload is the SAME configuration at every N (BASELINE.json configs[4], "10,000 loci x 32 taxa x
+2,000 sites sharded over 1/2/4/8 B200"), so the driver's 1 -> N efficiency is one curve on one workload.  One
+"step" = one full log-likelihood evaluation of the workload with NEW branch lengths: P(t) of every branch,
+every internal node recomputed, root reduction, and for N > 1 the collective that gives every rank all per-locus
+values.  Prints ONE JSON line; DESIGN.md section 5 explains every field.
 """
 from __future__ import annotations
 
@@ -28,13 +31,13 @@ sys.path.insert(0, ROOT)
 ALGO_BYTES_PER_UPDATE = 96  # 2 child reads x 32 B + 1 write x 32 B
 PI = (0.1, 0.2, 0.3, 0.4)
 RATES = (1.0, 2.5, 0.7, 1.3, 3.1, 0.9)
+SEEDS = {"cfg3": 3, "cfg4": 4, "cfg5": 5}
 
 WORKLOADS = {
-    # name: (loci, taxa, sites or patterns, description)
     "cfg2": dict(M=1, n=50, P=1_000_000, desc="single 50-taxon gene tree, GTR, 1e6 unique site patterns"),
     "cfg3": dict(M=200, n=24, L=1000, desc="200 loci x 24 taxa x 1,000 sites, full logL eval"),
     "cfg4": dict(M=1000, n=16, L=500, desc="1,000 loci x 16 taxa x 500 sites"),
-    "cfg5": dict(M=10_000, n=32, L=2000, desc="10,000 loci x 32 taxa x 2,000 sites sharded over N GPUs, NCCL logL allreduce"),
+    "cfg5": dict(M=10_000, n=32, L=2000, desc="10,000 loci x 32 taxa x 2,000 sites sharded over N GPUs, one collective of the per-locus logL per evaluation"),
 }
 
 
@@ -103,24 +106,28 @@ class ClockSampler:
 
 
 def make_locus_data(M, n, L, seed, lo=0, hi=None, chunk=250):
-    """Seeded synthetic loci [lo, hi): trees + (n, L) ASCII alignments (per-locus seeds so any
-    shard of the same workload sees identical data regardless of the number of ranks)."""
+    """Seeded synthetic loci [lo, hi): trees + (n, L) ASCII alignments (per-chunk seeds so any shard of the
+    same workload sees identical data regardless of the number of ranks)."""
     from phynetpy_b200 import simulate as S
     hi = M if hi is None else hi
     trees, alns = [], []
-    for c0 in range(lo, hi, chunk):
-        c1 = min(hi, c0 + chunk)
+    c_lo = (lo // chunk) * chunk
+    for c0 in range(c_lo, hi, chunk):
+        c1 = min(M, c0 + chunk)
         rng = np.random.default_rng([seed, c0])
         par, bl = S.random_trees(c1 - c0, n, rng)
         aln = S.simulate_alignments(par, bl, L, PI, RATES, rng)
-        trees.extend(S.flat_trees(par, bl))
-        alns.extend(aln[i] for i in range(c1 - c0))
+        ft = S.flat_trees(par, bl)
+        for i in range(c1 - c0):
+            if lo <= c0 + i < hi:
+                trees.append(ft[i])
+                alns.append(aln[i])
     return trees, alns
 
 
 def build_cfg2(P_target, n, seed, P):
-    """50 taxa, exactly P_target unique patterns: simulate, compress on the GPU, keep the first
-    P_target patterns with their weights (cfg 2)."""
+    """50 taxa, exactly P_target unique patterns: simulate, compress on the GPU, keep the first P_target
+    patterns with their weights (cfg 2)."""
     from phynetpy_b200 import simulate as S
     from phynetpy_b200._seq_likelihood import compress_alignment, _CODE_OF_BYTE
     rng = np.random.default_rng(seed)
@@ -143,71 +150,377 @@ def build_cfg2(P_target, n, seed, P):
 
 
 # --------------------------------------------------------------------------- CPU legs
-def oracle_time_single(codes, weights, ft, n_patterns, repeats):
-    """The reference algorithm (oracle port, NumPy) on the first n_patterns patterns."""
-    from oracle import felsenstein_oracle as O
-    om = O.gtr(PI, RATES)
-    tree = O.OracleTree(ft.parent.tolist(), [None if math.isnan(b) else float(b) for b in ft.blen], ft.label)
-    tip_row = ft.tip_rows({"t%d" % i: i for i in range(codes.shape[0])})
-    locus = O.OracleCodesLocus(np.ascontiguousarray(codes[:, :n_patterns]), weights[:n_patterns])  # construction untimed
-    best = float("inf")
-    val = None
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        val = locus.log_likelihood(tip_row, tree, om)
-        best = min(best, time.perf_counter() - t0)
-    n_int = int((ft.n_children() > 0).sum())
-    return best, n_int * n_patterns, val
+# The reference's own implementation of the path (baseline/_ref: the UNMODIFIED package, installed by
+# baseline/install_reference.sh) when it is present, else the oracle port -- always on a bounded sample, with the
+# per-locus objects built ONCE outside the clock, loci split over worker processes that live across steps.
+def reference_available() -> bool:
+    from baseline import ref_loader
+    return ref_loader.available()
 
 
-def _oracle_worker(args):
-    from oracle import felsenstein_oracle as O
-    alns, trees, reps = args
-    om = O.gtr(PI, RATES)
-    loci = [O.OracleLocus({"t%d" % i: a[i].tobytes().decode() for i in range(a.shape[0])}) for a in alns]
-    otrees = [O.OracleTree(t.parent.tolist(), [None if math.isnan(b) else float(b) for b in t.blen], t.label) for t in trees]
+def _cpu_worker_main(conn, kind, payload):
+    """One worker: build calculators + trees for its share once, then answer evaluation requests."""
+    try:
+        os.environ.setdefault("OMP_NUM_THREADS", "1")
+        os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+        from phynetpy_b200.tree import FlatTree, GeneTree
+        items = []  # (evaluate(tree_index) -> float)
+        if kind == "reference":
+            from baseline import ref_loader
+            ref_loader.load_reference()
+            import phynetpy._seq_likelihood as RSL
+            model = RSL.GTR(list(PI), list(RATES))
+            for entry in payload:
+                if entry[0] == "aln":      # (tag, taxa, matrix, [flat trees as (parent, blen, label)])
+                    _, taxa, mat, trees = entry
+                    calc = RSL.FelsensteinCalculator({t: mat[i].tobytes().decode() for i, t in enumerate(taxa)})
+                    items.append((calc, [GeneTree(p.tolist(), [None if b != b else float(b) for b in bl.tolist()], lab)
+                                         for p, bl, lab in trees], model, calc.n_patterns))
+        else:
+            from oracle import felsenstein_oracle as O
+            model = O.gtr(PI, RATES)
+            for entry in payload:
+                if entry[0] == "aln":
+                    _, taxa, mat, trees = entry
+                    locus = O.OracleLocus({t: mat[i].tobytes().decode() for i, t in enumerate(taxa)})
+                    items.append((locus, [O.OracleTree(p.tolist(), [None if b != b else float(b) for b in bl.tolist()], lab)
+                                          for p, bl, lab in trees], model, locus.n_patterns))
+                else:                      # ("codes", codes, weights, tip_row, tree): already compressed (cfg2)
+                    _, codes, weights, tip_row, (p, bl, lab) = entry
+                    locus = O.OracleCodesLocus(codes, weights)
+                    tree = O.OracleTree(p.tolist(), [None if b != b else float(b) for b in bl.tolist()], lab)
+                    items.append((("codes", locus, tip_row), [tree], model, codes.shape[1]))
+
+        def evaluate(obj, tree, model):
+            if kind == "reference":
+                return obj.log_likelihood(tree, model)
+            from oracle import felsenstein_oracle as O
+            if isinstance(obj, tuple):
+                return obj[1].log_likelihood(obj[2], tree, model)
+            return O.log_likelihood(obj, tree, model)
+        conn.send(("ready", len(items)))
+        while True:
+            msg = conn.recv()
+            if msg is None:
+                break
+            reps, which = msg           # which tree of every item (the trees differ by branch lengths)
+            t0 = time.perf_counter()
+            vals = None
+            for _ in range(reps):
+                vals = [evaluate(obj, trees[which % len(trees)], model) for obj, trees, model, _ in items]
+            dt = (time.perf_counter() - t0) / reps
+            ups = sum(npat * sum(1 for c in _n_children(trees[0]) if c > 0) for _, trees, _, npat in items)
+            conn.send((dt, ups, vals))
+    except Exception:
+        import traceback
+        conn.send(("error", traceback.format_exc()))
+
+
+def _n_children(tree):
+    parent = getattr(tree, "parent", None)
+    if parent is None:
+        parent = tree._parent
+    n = len(parent)
+    cnt = [0] * n
+    for p in parent:
+        if p >= 0:
+            cnt[p] += 1
+    return cnt
+
+
+class CpuPath:
+    """Worker processes holding the CPU implementation of the path for a bounded sample of a workload."""
+
+    def __init__(self, entries, procs):
+        import multiprocessing as mp
+        self.kind = "reference" if reference_available() and all(e[0] == "aln" for e in entries) else "port"
+        self.procs = max(1, min(procs, len(entries)))
+        ctx = mp.get_context("spawn")
+        self.workers = []
+        for r in range(self.procs):
+            a, b = ctx.Pipe()
+            p = ctx.Process(target=_cpu_worker_main, args=(b, self.kind, entries[r::self.procs]), daemon=True)
+            p.start()
+            self.workers.append((p, a))
+        for _, a in self.workers:
+            msg = a.recv()
+            if msg[0] == "error":
+                raise RuntimeError("CPU worker failed:\n" + msg[1])
+
+    def step(self, reps=1, which=0):
+        """One timed pass over the sample: max over workers of the mean evaluation time."""
+        for _, a in self.workers:
+            a.send((reps, which))
+        res = [a.recv() for _, a in self.workers]
+        for r in res:
+            if r[0] == "error":
+                raise RuntimeError("CPU worker failed:\n" + r[1])
+        vals = [None] * sum(len(r[2]) for r in res)
+        for k, r in enumerate(res):
+            vals[k::self.procs] = r[2]
+        return max(r[0] for r in res), sum(r[1] for r in res), vals
+
+    def close(self):
+        for p, a in self.workers:
+            try:
+                a.send(None)
+            except Exception:
+                pass
+        for p, _ in self.workers:
+            p.join(timeout=5)
+
+
+def _tree_tuple(ft, scale=1.0):
+    return (ft.parent, ft.blen * scale, ft.label)
+
+
+def cpu_entries_loci(trees, alns, taxa, scales=(1.0,)):
+    return [("aln", taxa, a, [_tree_tuple(t, s) for s in scales]) for t, a in zip(trees, alns)]
+
+
+def describe_cpu(kind, procs, what):
+    impl = ("the UNMODIFIED reference (baseline/_ref: phynetpy._seq_likelihood.FelsensteinCalculator.log_likelihood, "
+            "NumPy/OpenBLAS)" if kind == "reference" else
+            "oracle port (NumPy restatement of the reference's _postorder_partials; the reference package is not installed here)")
+    return "%s on %s, calculators built once outside the clock, loci split over %d worker process(es)" % (impl, what, procs)
+
+
+# --------------------------------------------------------------------------- device workload
+class Workload:
+    """A resident workload on this rank: loci in HBM, a resident batch, branch-length sets on host and device."""
+
+    def __init__(self, P, ctx, model, calcs, trees, n_sets):
+        import torch
+        from phynetpy_b200._seq_likelihood import _model_handle
+        from phynetpy_b200.device import ResidentBatch, pack_trees
+        self.P, self.ctx, self.model, self.calcs, self.trees = P, ctx, model, calcs, trees
+        for c in calcs:
+            c._locus_handle()
+        self.handles = np.array([c._locus.value for c in calcs], dtype=np.uint64)
+        self.node_off, self.parent, self.blen, self.tip_row = pack_trees(trees, [c._row_of for c in calcs])
+        self.mh = _model_handle(model, ctx)
+        self.batch = ResidentBatch(ctx, self.mh, self.handles, self.node_off, self.parent, self.tip_row)
+        self.score_batch = None
+        # every step scores the same topologies with NEW branch lengths (a height-rescaling proposal)
+        self.h_blens = [torch.from_numpy(np.ascontiguousarray(self.blen * (1.0 + 0.002 * k))).pin_memory() for k in range(n_sets)]
+        self.d_blens = [t.cuda() for t in self.h_blens]
+        self.n_local = len(calcs)
+        self.patterns_local = int(sum(c.n_patterns for c in calcs))
+        self.updates_local = self.batch.info["updates"]
+
+    def make_score_batch(self):
+        from phynetpy_b200 import _lib
+        from phynetpy_b200.device import ResidentBatch
+        if self.score_batch is None:
+            self.score_batch = ResidentBatch(self.ctx, self.mh, self.handles, self.node_off, self.parent, self.tip_row, _lib.EVAL_NOSTORE)
+        return self.score_batch
+
+    def close(self):
+        for b in (self.batch, self.score_batch):
+            if b is not None:
+                b.close()
+        for c in self.calcs:
+            c.close()
+
+
+def measure(args, wl_name, W, plan, stream, rank, world, clock_sampler=None):
+    """value / e2e / per-kernel numbers of one resident workload (this rank's shard), timed as the contract says."""
+    import torch
+    import torch.distributed as dist
+    ctx = W.ctx
+    M = plan["M"]
+    lo, per = plan["lo"], plan["per"]
+    vec_len = per * world
+    out_vec = torch.zeros(vec_len, dtype=torch.float64, device="cuda")       # every rank ends with all per-locus values
+    out_host = torch.zeros(vec_len, dtype=torch.float64).pin_memory()
+    out_local_ptr = out_vec.data_ptr() + 8 * lo
+    steps = args.steps
+    warm = max(args.warmup, 3)
+    step_no = [0]
+    n_sets = len(W.d_blens)
+    inplace_ok = [True]
+
+    def collective():
+        if world > 1 and not args.skip_collective:
+            if inplace_ok[0]:
+                # in place: this rank's slice of the M-vector IS the send buffer (equal slices by construction)
+                dist.all_gather_into_tensor(out_vec, out_vec[lo:lo + per])
+            else:
+                dist.all_gather_into_tensor(out_vec, out_vec[lo:lo + per].clone())
+
+    def step_device():
+        """inputs resident in HBM (lengths included); logL stays on the device; collective when sharded"""
+        k = step_no[0] % n_sets
+        step_no[0] += 1
+        with torch.cuda.stream(stream):
+            W.batch.eval(W.mh, W.d_blens[k].data_ptr(), out_device_ptr=out_local_ptr)
+            collective()
+
+    def step_e2e():
+        """the call a user makes: host branch lengths (pinned) in, host log-likelihoods of ALL loci out"""
+        k = step_no[0] % n_sets
+        step_no[0] += 1
+        with torch.cuda.stream(stream):
+            W.batch.eval(W.mh, W.h_blens[k].numpy(), out_device_ptr=out_local_ptr)
+            collective()
+            out_host.copy_(out_vec, non_blocking=True)
+        stream.synchronize()
+        return out_host.numpy()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also: does the in-place all-gather give what the out-of-place one gives?) ----------
+    for _ in range(warm):
+        step_device()
+    barrier()
+    if world > 1 and not args.skip_collective:
+        a = out_vec.clone()
+        inplace_ok[0] = False
+        step_no[0] -= 1
+        step_device()
+        barrier()
+        inplace_ok[0] = bool(torch.equal(a, out_vec))
+        t = torch.tensor([1.0 if inplace_ok[0] else 0.0], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        inplace_ok[0] = bool(t.item() > 0.5)
+    st = ctx.last_stats()
+    launches_per_step = st["launches"]
+
+    # ---- timed: device-resident -----------------------------------------------------------------------
+    if clock_sampler is not None:
+        clock_sampler.start()
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    ctx.set_profiling(False)
+    barrier()
+    step_no[0] = 0
+    ev0.record(stream)
+    for _ in range(steps):
+        step_device()
+    ev1.record(stream)
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    logL_device = out_vec.cpu().numpy().copy()
+
+    # ---- per-kernel durations: the same steps with CUDA events around each launch (library-side, same stream) ----
+    ctx.set_profiling(True)
+    prune_ms, pm_ms, call_ms = [], [], []
+    step_no[0] = 0
+    for _ in range(steps):
+        step_device()
+        tm = ctx.last_timings()
+        prune_ms.append(tm["prune_ms"]); pm_ms.append(tm["pmatrix_ms"]); call_ms.append(tm["call_ms"])
+    barrier()
+    ctx.set_profiling(False)
+
+    # ---- timed: end to end with host buffers ----------------------------------------------------------------
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    step_no[0] = 0
     t0 = time.perf_counter()
-    for _ in range(reps):
-        vals = [O.log_likelihood(l, t, om) for l, t in zip(loci, otrees)]
-    dt = (time.perf_counter() - t0) / reps
-    ups = sum(l.n_patterns * (len(t.parent) - sum(1 for c in t.children if not c)) for l, t in zip(loci, otrees))
-    return dt, ups, vals
+    for _ in range(steps):
+        vals_e2e = step_e2e()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    st_e2e = ctx.last_stats()
+    logL_e2e = vals_e2e.copy()
+    barrier()
+    clocks = clock_sampler.stop() if clock_sampler is not None else None
+
+    # ---- reduce over ranks ------------------------------------------------------------------------------
+    t = torch.tensor([elapsed_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    u = torch.tensor([float(W.updates_local), float(W.patterns_local)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(u, op=dist.ReduceOp.SUM)
+    return {
+        "elapsed_ms": float(t[0]), "e2e_ms": float(t[1]), "updates_total": float(u[0]), "patterns_total": int(u[1]),
+        "kernel_ms": float(np.mean(prune_ms)), "pmatrix_ms": float(np.mean(pm_ms)), "call_ms": float(np.mean(call_ms)),
+        "launches_per_step": int(launches_per_step), "h2d": int(st_e2e["h2d_bytes"]),
+        "d2h": int(vec_len * 8), "logL_device": logL_device[:M], "logL_e2e": logL_e2e[:M], "clocks": clocks,
+        "inplace_allgather": bool(inplace_ok[0]) if world > 1 else None,
+    }
 
 
-def oracle_time_loci(trees, alns, procs, reps=10):
-    """Reference loop over loci (src/_mcmc_seq.py:746-750), loci split over host processes."""
-    import multiprocessing as mp
-    procs = max(1, min(procs, len(trees)))
-    parts = [(alns[i::procs], trees[i::procs], reps) for i in range(procs)]
-    if procs == 1:
-        res = [_oracle_worker(parts[0])]
-    else:
-        with mp.get_context("spawn").Pool(procs) as pool:
-            res = pool.map(_oracle_worker, parts)
-    wall = max(r[0] for r in res)  # evaluation only; construction is excluded as in BASELINE.md
-    ups = sum(r[1] for r in res)
-    return wall, ups
+def score_only_leg(args, W, stream):
+    """PNB_EVAL_NOSTORE: the same evaluation with no partial written (candidate scoring)."""
+    import torch
+    sb = W.make_score_batch()
+    out = torch.zeros(W.n_local, dtype=torch.float64, device="cuda")
+    W.ctx.set_profiling(True)
+    ks = []
+    for k in range(3 + args.steps):
+        with torch.cuda.stream(stream):
+            sb.eval(W.mh, W.d_blens[k % len(W.d_blens)].data_ptr(), out_device_ptr=out.data_ptr())
+        tm = W.ctx.last_timings()
+        if k >= 3:
+            ks.append(tm["prune_ms"])
+    # same lengths as the last timed store-mode step for the equality check
+    with torch.cuda.stream(stream):
+        sb.eval(W.mh, W.d_blens[(args.steps - 1) % len(W.d_blens)].data_ptr(), out_device_ptr=out.data_ptr())
+    stream.synchronize()
+    W.ctx.set_profiling(False)
+    return float(np.mean(ks)), out.cpu().numpy()
+
+
+def roofline_block(W, kernel_ms, pm_ms, call_ms, traffic_ncu_file=None):
+    peak, peak_src = peak_hbm()
+    tr = W.batch.traffic
+    compulsory = tr["partials_written"] + tr["tip_codes"] + 8 * sum(c.n_patterns for c in W.calcs)
+    achieved_real = compulsory / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else None
+    achieved_model = W.updates_local * ALGO_BYTES_PER_UPDATE / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else None
+    out = {
+        "bound": "hbm", "kernel": "pnb_prune_kernel",
+        "achieved": achieved_real, "peak": peak, "unit": "GB/s",
+        "frac": (achieved_real / peak) if achieved_real else None,
+        "traffic": compulsory,
+        "traffic_source": "counted live from the compiled op programs of this run (pnb_batch_traffic): node partials the kernel "
+                          "writes (stored nodes x padded patterns x 32 B) + tip-code rows + weights; re-reads of siblings "
+                          "written in the same launch (%d B) and per-tile program / P staging (%d B) are L2 traffic and not counted"
+                          % (tr["partials_reread"], tr["weights_programs_pmatrices"]),
+        "bytes_definition": "achieved / frac use the bytes THIS kernel has to move (a thread carries its patterns through the whole "
+                            "tree: tips are 1-byte codes, a just-computed child stays in registers, tip-only subtrees are never "
+                            "stored); model_96B is SURVEY section 8d's streaming model (2 x 32 B read + 32 B written per update)",
+        "model_96B": {"achieved": achieved_model, "frac": (achieved_model / peak) if achieved_model else None,
+                      "algorithmic_bytes_per_update": ALGO_BYTES_PER_UPDATE},
+        "peak_source": peak_src,
+        "kernel_ms": kernel_ms, "pmatrix_kernel_ms": pm_ms, "host_call_ms": call_ms,
+    }
+    if traffic_ncu_file and os.path.exists(os.path.join(ROOT, traffic_ncu_file)):
+        try:
+            d = json.load(open(os.path.join(ROOT, traffic_ncu_file)))
+            out["traffic_ncu"] = {"dram_bytes_per_launch": d.get("dram_bytes_per_launch"), "file": traffic_ncu_file,
+                                  "note": "ncu --set full capture of this kernel at the recorded commit (a committed file, not this run)"}
+        except Exception:
+            pass
+    return out
 
 
 # --------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="auto", choices=["auto"] + sorted(WORKLOADS))
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (smoke runs only; reported)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--skip-allreduce", action="store_true", help="diagnostic only: time the sharded step without the collective")
+    ap.add_argument("--no-extras", action="store_true", help="N=1: skip the cfg2 roofline block and the chain block")
+    ap.add_argument("--skip-collective", action="store_true", help="diagnostic only: time the sharded step without the collective")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     wl = args.workload
+    extras = False
     if wl == "auto":
-        wl = "cfg2" if max(args.gpus, world) == 1 else "cfg5"
+        wl = "cfg5"
+        extras = world == 1 and not args.no_extras and args.scale == 1.0
     spec = dict(WORKLOADS[wl])
     if args.scale != 1.0:
         for k in ("P", "M"):
@@ -220,10 +533,6 @@ def main():
     import torch
     import torch.distributed as dist
     from phynetpy_b200 import infer as P
-    from phynetpy_b200 import _lib
-    from phynetpy_b200._seq_likelihood import _model_handle
-    from phynetpy_b200.device import pack_trees
-    from phynetpy_b200.distributed import ShardPlan, balanced_ranges
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -232,203 +541,60 @@ def main():
     ctx = P.default_context(local_rank)
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
-    ctx.set_profiling(True)
     model = P.GTR(PI, RATES)
-    mh = _model_handle(model, ctx)
-    setup = {}
+    n_sets = max(min(args.steps, 8), 1)
 
-    # ---- build the resident workload -------------------------------------------------
+    cfg2_block = chain = None
+    if extras:
+        cfg2_block = run_cfg2_block(args, P, ctx, model, stream, n_sets)
+        chain = run_chain_block(args, P, ctx, model)
+
+    # ---- build the resident headline workload ---------------------------------------------------------
     t_setup0 = time.perf_counter()
+    setup = {}
+    cpu_entries = None
     if wl == "cfg2":
         if world > 1:
             raise SystemExit("cfg2 is a single-locus, single-GPU workload (replicas only); use cfg5 for N>1")
         fc, ft, setup = build_cfg2(spec["P"], spec["n"], 2, P)
         calcs, trees = [fc], [ft]
-        M = 1
-        lo, hi = 0, 1
-        plan = ShardPlan.single(1)
-        cpu_sample = (fc._codes, fc._int_weights, ft)
+        M, lo, per = 1, 0, 1
+        n_pat = min(200_000, fc.n_patterns)
+        cpu_entries = [("codes", np.ascontiguousarray(fc._codes[:, :n_pat]), fc._int_weights[:n_pat].copy(),
+                        ft.tip_rows(fc._row_of).tolist(), _tree_tuple(ft))]
+        cpu_what = "the first %d of the %d patterns" % (n_pat, fc.n_patterns)
     else:
         M = spec["M"]
-        ranges = balanced_ranges(np.ones(M), world)
-        plan = ShardPlan(M, rank, world, ranges)
-        lo, hi = plan.local_range()
-        trees, alns = make_locus_data(M, spec["n"], spec["L"], {"cfg3": 3, "cfg4": 4, "cfg5": 5}[wl], lo, hi)
+        per = (M + world - 1) // world              # equal contiguous slices (the loci of one workload do equal work)
+        lo, hi = rank * per, min(M, (rank + 1) * per)
+        trees, alns = make_locus_data(M, spec["n"], spec["L"], SEEDS[wl], lo, hi)
         taxa = ["t%d" % i for i in range(spec["n"])]
         calcs = [P.FelsensteinCalculator.from_matrix(taxa, a, device_compress=False) for a in alns]
-        cpu_sample = (trees[:256], alns[:256])
+        n_cpu = min(len(trees), 512)
+        cpu_entries = cpu_entries_loci(trees[:n_cpu], alns[:n_cpu], taxa)
+        cpu_what = "the first %d of the %d loci" % (n_cpu, M)
         del alns
-    for c in calcs:
-        c._locus_handle()
-    handles = np.array([c._locus.value for c in calcs], dtype=np.uint64)
-    node_off, parent, blen, tip_row = pack_trees(trees, [c._row_of for c in calcs])
-    n_local = len(calcs)
-    patterns_local = int(sum(c.n_patterns for c in calcs))
+    W = Workload(P, ctx, model, calcs, trees, n_sets)
     setup["setup_s"] = round(time.perf_counter() - t_setup0, 2)
 
-    out_vec = torch.zeros(M, dtype=torch.float64, device="cuda")      # all-reduced per-locus logL
-    local_vec = torch.zeros(M, dtype=torch.float64, device="cuda") if world > 1 else out_vec
-    out_local_ptr = local_vec.data_ptr() + 8 * lo                      # the kernel writes this rank's slice
-    flags = _lib.EVAL_FULL
-
-    # every step scores the same topologies with NEW branch lengths (a height-rescaling proposal):
-    # nothing of a previous step's result can be reused, and the host recompiles lengths each time
-    blens = [np.ascontiguousarray(blen * (1.0 + 0.002 * k)) for k in range(max(min(args.steps, 8), 1))]
-    step_no = [0]
-
-    def next_blen():
-        b = blens[step_no[0] % len(blens)]
-        step_no[0] += 1
-        return b
-
-    def step_device():
-        """inputs resident in HBM; logL stays on the device; all-reduce when sharded"""
-        with torch.cuda.stream(stream):
-            ctx.eval(mh, handles, node_off, parent, next_blen(), tip_row, 1.0, flags, None, out_device_ptr=out_local_ptr)
-            if world > 1 and not args.skip_allreduce:
-                out_vec.copy_(local_vec)   # zeros outside this rank's range: the sum is exact
-                dist.all_reduce(out_vec)
-
-    def step_e2e():
-        """the call a user makes: host trees in, host log-likelihoods out"""
-        vals = ctx.eval(mh, handles, node_off, parent, next_blen(), tip_row, 1.0, flags, None)
-        if world > 1:
-            v = torch.zeros(M, dtype=torch.float64)
-            v[lo:hi] = torch.from_numpy(vals)
-            v = v.cuda()
-            dist.all_reduce(v)
-            return v.cpu().numpy()
-        return vals
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- warm-up ----------------------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        step_device()
-    barrier()
-    stats = ctx.last_stats()
-    updates_local = stats["updates"]
-    launches_per_step = stats["launches"]
-
-    # ---- timed: device-resident ---------------------------------------------------------
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ev0 = torch.cuda.Event(enable_timing=True)
-    ev1 = torch.cuda.Event(enable_timing=True)
-    ctx.set_profiling(False)
-    barrier()
-    step_no[0] = 0
-    ev0.record(stream)
-    for _ in range(args.steps):
-        step_device()
-    ev1.record(stream)
-    barrier()
-    elapsed_ms = ev0.elapsed_time(ev1)
-    logL_device = out_vec.cpu().numpy().copy()
-
-    # ---- per-kernel durations: same steps again with CUDA events around each kernel launch ----
-    ctx.set_profiling(True)
-    prune_ms, pm_ms, comp_ms, call_ms = [], [], [], []
-    for _ in range(args.steps):
-        step_device()
-        tm = ctx.last_timings()  # waits for this step's events
-        prune_ms.append(tm["prune_ms"]); pm_ms.append(tm["pmatrix_ms"]); comp_ms.append(tm["compile_ms"])
-        call_ms.append(tm["call_ms"])
-    barrier()
-
-    # ---- score-only mode (PNB_EVAL_NOSTORE): same evaluation, partials never leave the SM ----
-    score_ms = None
-    if wl == "cfg2" or world == 1:
-        for c in calcs:
-            c.invalidate()
-        sflags = _lib.EVAL_NOSTORE
-        def step_score():
-            with torch.cuda.stream(stream):
-                ctx.eval(mh, handles, node_off, parent, next_blen(), tip_row, 1.0, sflags, None, out_device_ptr=out_local_ptr)
-        for _ in range(3):
-            step_score()
-        barrier()
-        sk = []
-        step_no[0] = 0
-        for _ in range(args.steps):
-            step_score()
-            sk.append(ctx.last_timings()["prune_ms"])
-        barrier()
-        score_ms = float(np.mean(sk))
-        score_updates = ctx.last_stats()["updates"]
-        score_logL = out_vec.cpu().numpy().copy()
-    ctx.set_profiling(False)
-
-    # ---- cfg4: MCMC chain steps with dirty-path recompute (one locus per proposal) -------------
-    chain = None
-    if wl == "cfg4" and world == 1:
-        chain = chain_steps(P, ctx, calcs, trees, model, n_steps=min(max(200, 20 * args.steps), 2000))
-        chain["coupled_move_candidates"] = candidate_batch(P, ctx, calcs, trees, model, n_loci=min(200, len(calcs)))
-        chain["msnc_density"] = msnc_leg(P, ctx, n_loci=len(calcs), n_species=spec["n"], cpu=not args.no_cpu_baseline)
-        chain["coupled_move"] = coupled_move_leg(P, ctx, model, n_loci=min(200, len(calcs)), n_species=spec["n"], L=spec["L"])
-        chain["joint_likelihood_chain"] = joint_chain(P, ctx, model, n_loci=len(calcs), n_species=spec["n"], L=spec["L"],
-                                                      n_steps=1000)
-
-    # ---- timed: end to end through the C ABI with host buffers ---------------------------
-    for _ in range(2):
-        step_e2e()
-    barrier()
-    step_no[0] = 0
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        vals_e2e = step_e2e()
-    torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) * 1e3
-    st_e2e = ctx.last_stats()
-    # the same call one level up: the reference-shaped Python facade with a Network-like tree OBJECT
-    # (root()/get_children()/get_edge().get_length()), marshalled per call as the reference's callers do
-    facade_ms = None
-    if wl == "cfg2":
-        gt = P.GeneTree.from_flat(trees[0])
-        calcs[0].log_likelihood(gt, model, full=True)
-        t0 = time.perf_counter()
-        nrep = min(args.steps, 10)
-        for _ in range(nrep):
-            facade_val = calcs[0].log_likelihood(gt, model, full=True)
-        facade_ms = (time.perf_counter() - t0) * 1e3 / nrep
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-
-    # ---- reduce over ranks ----------------------------------------------------------------
-    t = torch.tensor([elapsed_ms, e2e_ms], dtype=torch.float64, device="cuda")
-    u = torch.tensor([float(updates_local), float(patterns_local)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(u, op=dist.ReduceOp.SUM)
-    elapsed_ms, e2e_ms = float(t[0]), float(t[1])
-    updates_total = float(u[0])
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    m = measure(args, wl, W, {"M": M, "lo": lo, "per": per}, stream, rank, world, sampler)
+    score_ms = score_vals = None
+    if world == 1:
+        score_ms, score_vals = score_only_leg(args, W, stream)
 
     if rank == 0:
-        ms_per_step = elapsed_ms / args.steps
-        value = updates_total * args.steps / (elapsed_ms * 1e-3)
-        e2e_value = updates_total * args.steps / (e2e_ms * 1e-3)
-        peak, peak_src = peak_hbm()
-        k_ms = float(np.mean(prune_ms))
-        achieved = updates_local * ALGO_BYTES_PER_UPDATE / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic_%s.json" % wl)
-        if os.path.exists(tpath):
-            try:
-                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
-        total_logL = float(np.sum(logL_device)) if world > 1 or wl != "cfg2" else float(logL_device[0])
-        e2e_total = float(np.sum(vals_e2e))
+        steps = args.steps
+        ms_per_step = m["elapsed_ms"] / steps
+        value = m["updates_total"] * steps / (m["elapsed_ms"] * 1e-3)
+        e2e_value = m["updates_total"] * steps / (m["e2e_ms"] * 1e-3)
+        total_logL = float(np.sum(m["logL_device"]))
         result = {
             "metric": "site-node partial updates/sec",
             "value": value,
             "unit": "updates/s",
             "n_gpus": world,
-            "steps": args.steps,
+            "steps": steps,
             "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step,
             "higher_is_better": True,
@@ -438,184 +604,319 @@ def main():
             "data": "synthetic",
             "config": {
                 "workload": "%s: %s" % (wl, spec["desc"]),
-                "loci": M, "taxa": spec["n"], "site_patterns_total": int(u[1]),
-                "updates_per_step": int(updates_total),
+                "loci": M, "taxa": spec["n"], "site_patterns_total": m["patterns_total"],
+                "updates_per_step": int(m["updates_total"]),
                 "model": "GTR pi=(.1,.2,.3,.4) rates=(1,2.5,.7,1.3,3.1,.9)",
-                "step": "full logL evaluation of a fresh proposal (same topologies, new branch lengths every step): "
-                        "P(t) of every branch + every internal node recomputed + root reduction"
-                        + (" + NCCL all-reduce of the per-locus vector" if world > 1 else ""),
-                "parallelism": "loci sharded over %d GPU(s), one process per GPU" % world,
-                "l2": "working set per step (%.2f GB of partials written) exceeds the 126 MB L2; no flush needed"
-                      % (updates_local * 32 / 1e9),
-                "scale": args.scale, "diagnostic_skip_allreduce": bool(args.skip_allreduce),
+                "step": "full logL evaluation of a fresh proposal (same topologies, new branch lengths every step): P(t) of every "
+                        "branch + every internal node recomputed + root reduction"
+                        + (" + in-place NCCL all-gather of the per-locus vector (every rank ends with all %d values)" % M if world > 1 else "")
+                        + "; op programs resident in HBM (pnb_batch_*), compiled once per topology",
+                "parallelism": "loci sharded over %d GPU(s) in equal contiguous slices, one process per GPU" % world,
+                "collective": None if world == 1 else ("ncclAllGather in place on the kernel's stream" if m["inplace_allgather"]
+                                                       else "ncclAllGather (out of place)"),
+                "l2": "working set per step (%.2f GB of partials written per GPU) exceeds the 126 MB L2; no flush needed"
+                      % (W.batch.traffic["partials_written"] / 1e9),
+                "scale": args.scale, "diagnostic_skip_collective": bool(args.skip_collective),
                 **setup,
             },
             "e2e": {
-                "value": e2e_value, "unit": "updates/s", "ms_per_step": e2e_ms / args.steps,
-                "h2d_bytes_per_step": int(st_e2e["h2d_bytes"]), "d2h_bytes_per_step": int(st_e2e["d2h_bytes"]),
-                "what": "pnb_eval through the C ABI: host tree arrays in (compiled to the op program on the host, "
-                        "copied H2D), kernels, per-locus logL copied D2H; alignment resident since construction",
-                "python_facade_ms_per_step": facade_ms,
-                "python_facade_what": None if facade_ms is None else
-                    "FelsensteinCalculator.log_likelihood(tree object, model, full=True): per-call marshalling of a "
-                    "Network-like object included",
+                "value": e2e_value, "unit": "updates/s", "ms_per_step": m["e2e_ms"] / steps,
+                "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"],
+                "what": "pnb_batch_eval through the C ABI with HOST buffers: branch lengths of every tree in pinned host memory -> "
+                        "chunked H2D overlapped with pruning -> P(t) + pruning kernels -> "
+                        + ("all-gather -> " if world > 1 else "") + "per-locus logL of ALL loci copied D2H into pinned host memory "
+                        "(per-rank bytes); alignments resident since construction",
             },
-            "gpu_launches": int(launches_per_step * args.steps),
-            "kernels_per_step": {"pnb_pmatrix_kernel": 1, "pnb_prune_kernel": 1},
-            "roofline": {
-                "bound": "hbm", "kernel": "pnb_prune_kernel",
-                "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None,
-                "traffic": traffic,
-                "peak_source": peak_src,
-                "algorithmic_bytes_per_update": ALGO_BYTES_PER_UPDATE,
-                "kernel_ms": k_ms, "pmatrix_kernel_ms": float(np.mean(pm_ms)),
-                "host_compile_ms": float(np.mean(comp_ms)), "host_call_ms": float(np.mean(call_ms)),
-                "note": "achieved uses the 96 B/update streaming model; the kernel keeps a node's freshly computed "
-                        "child in registers, so its real DRAM traffic (`traffic`) is lower than algorithmic",
-            },
+            "gpu_launches": int(m["launches_per_step"] * steps),
+            "kernels_per_step": {"pnb_pmatrix_gather_kernel": 1, "pnb_prune_kernel": 1},
+            "roofline": roofline_block(W, m["kernel_ms"], m["pmatrix_ms"], m["call_ms"],
+                                       "profiles/traffic_%s_r2.json" % wl),
             "score_only": None if score_ms is None else {
                 "what": "PNB_EVAL_NOSTORE: every node recomputed, no partial written to HBM (candidate scoring)",
-                "kernel_ms": score_ms, "updates_per_s_kernel": score_updates / (score_ms * 1e-3),
-                "logL_equal_to_store_mode": bool(np.array_equal(score_logL, logL_device)),
+                "kernel_ms": score_ms, "updates_per_s_kernel": W.updates_local / (score_ms * 1e-3),
+                "logL_equal_to_store_mode": bool(np.array_equal(score_vals, m["logL_device"][:len(score_vals)])),
             },
+            "cfg2": cfg2_block,
             "chain": chain,
-            "clocks": clocks,
+            "clocks": m["clocks"],
             "logL": total_logL,
-            "logL_e2e": e2e_total,
+            "logL_e2e": float(np.sum(m["logL_e2e"])),
+            "logL_e2e_equals_device_bitwise": bool(np.array_equal(m["logL_e2e"], m["logL_device"])),
         }
-        if not args.no_cpu_baseline:
-            result["cpu_baseline"] = cpu_baseline(wl, spec, cpu_sample)
-            chk = result["cpu_baseline"].pop("_check", None)
-            if chk is not None:
-                result["parity"] = chk(calcs, trees, model, P)
+        if not args.no_cpu_baseline and world == 1:
+            result["cpu_baseline"], result["parity"] = cpu_baseline(cpu_entries, cpu_what, W, m)
         print(json.dumps(result))
+    W.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def chain_steps(P, ctx, calcs, trees, model, n_steps, seed=4):
-    """BASELINE cfg4: a stream of single-locus proposals through the engine seam the sampler uses
-    (invalidate_locus -> log_likelihood -> accept | restore_caches).  Each proposal moves one
-    internal node's height (its two child branches and its parent branch change, as
-    op_gene_node_height does, reference src/_mcmc_seq.py:1020-1039), so the device recomputes
-    that node and its ancestors only.  Ends with a full recomputation of every locus, which must
-    reproduce the incrementally maintained total bit for bit."""
-    rng = np.random.default_rng(seed)
-    eng = P.SeqLikelihoodEngine(calcs, None, model, context=ctx)
-    cur = list(trees)
-    total = eng.log_likelihood(cur, None, 0.0)
-    eng._commit_pending()
-    M = len(cur)
-    nodes = cur[0].n_nodes
-    n_tips = (nodes + 1) // 2
-    upd, recomputed, accepted = 0, 0, 0
-    lat, c_ms = [], []
+def cpu_baseline(entries, what, W, m):
+    """The reference (or its port) on a bounded sample of the SAME inputs on this box's host cores, and the
+    in-run parity check of the GPU values against it."""
+    cores = os.cpu_count() or 1
+    procs = min(cores, 32)
+    cp = CpuPath(entries, procs)
+    try:
+        cp.step(1)                                   # warm-up
+        reps = 3 if entries[0][0] == "codes" else 5
+        best, ups, vals = None, 0, None
+        for _ in range(3):
+            dt, ups, vals = cp.step(reps)
+            best = dt if best is None else min(best, dt)
+    finally:
+        cp.close()
+    base = {"value": ups / best, "unit": "updates/s", "cores": cp.procs, "kind": cp.kind,
+            "sample": describe_cpu(cp.kind, cp.procs, what) + "; best of 3 timings of %d evaluations each" % reps,
+            "seconds_per_eval_sample": best}
+    # parity: the GPU's values for the same loci at the same (unscaled) branch lengths
+    if entries[0][0] == "codes":
+        n_pat = entries[0][1].shape[1]
+        sub = W.P.FelsensteinCalculator.from_codes(W.calcs[0].taxa, entries[0][1], entries[0][2])
+        got = [sub.log_likelihood(W.trees[0], W.model)]
+        sub.close()
+        label = "first %d patterns" % n_pat
+    else:
+        n = len(entries)
+        got = W.batch.eval(W.mh, np.ascontiguousarray(W.blen))[:n].tolist()
+        label = "first %d loci" % n
+    err = max(abs(g - v) / max(1.0, abs(v)) for g, v in zip(got, vals))
+    parity = {"max_rel_err_vs_cpu": err, "cpu_kind": cp.kind, "sample": label,
+              "cpu_logL_sample_sum": float(sum(vals)), "gpu_logL_sample_sum": float(sum(got))}
+    return base, parity
+
+
+# --------------------------------------------------------------------------- N=1 extras
+def run_cfg2_block(args, P, ctx, model, stream, n_sets):
+    """BASELINE configs[1], the single-GPU roofline run: one 50-taxon gene tree, 1e6 unique site patterns."""
+    spec = WORKLOADS["cfg2"]
+    fc, ft, setup = build_cfg2(spec["P"], spec["n"], 2, P)
+    W = Workload(P, ctx, model, [fc], [ft], n_sets)
+    m = measure(args, "cfg2", W, {"M": 1, "lo": 0, "per": 1}, stream, 0, 1, None)
+    score_ms, score_vals = score_only_leg(args, W, stream)
+    steps = args.steps
+    # the same call one level up: the reference-shaped Python facade with a Network-like tree OBJECT
+    gt = P.GeneTree.from_flat(ft)
+    fc.log_likelihood(gt, model, full=True)
     t0 = time.perf_counter()
-    for _ in range(n_steps):
-        i = int(rng.integers(0, M))
-        ft = cur[i]
-        v = int(rng.integers(n_tips, nodes - 1))           # internal, non-root
-        kids = np.nonzero(ft.parent == v)[0]
-        room_dn = float(ft.blen[kids].min())
-        room_up = float(ft.blen[v])
-        delta = float(rng.uniform(-0.5 * room_dn, 0.5 * room_up))
-        bl = ft.blen.copy()
-        bl[kids] += delta
-        bl[v] -= delta
-        prop = list(cur)
-        prop[i] = ft.with_lengths(bl)
+    nrep = min(steps, 10)
+    for _ in range(nrep):
+        fc.log_likelihood(gt, model, full=True)
+    facade_ms = (time.perf_counter() - t0) * 1e3 / nrep
+    out = {
+        "workload": "cfg2: " + spec["desc"],
+        "value": m["updates_total"] * steps / (m["elapsed_ms"] * 1e-3), "unit": "updates/s",
+        "ms_per_step": m["elapsed_ms"] / steps,
+        "e2e": {"value": m["updates_total"] * steps / (m["e2e_ms"] * 1e-3), "ms_per_step": m["e2e_ms"] / steps,
+                "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"],
+                "python_facade_ms_per_step": facade_ms,
+                "python_facade_what": "FelsensteinCalculator.log_likelihood(tree object, model, full=True): per-call marshalling "
+                                      "of a Network-like object and tree compilation included"},
+        "roofline": roofline_block(W, m["kernel_ms"], m["pmatrix_ms"], m["call_ms"], "profiles/traffic_cfg2_r2.json"),
+        "score_only": {"kernel_ms": score_ms, "updates_per_s_kernel": W.updates_local / (score_ms * 1e-3),
+                       "logL_equal_to_store_mode": bool(np.array_equal(score_vals, m["logL_device"][:1]))},
+        "logL": float(m["logL_device"][0]),
+        **setup,
+    }
+    if not args.no_cpu_baseline:
+        n_pat = min(200_000, fc.n_patterns)
+        entries = [("codes", np.ascontiguousarray(fc._codes[:, :n_pat]), fc._int_weights[:n_pat].copy(),
+                    ft.tip_rows(fc._row_of).tolist(), _tree_tuple(ft))]
+        out["cpu_baseline"], out["parity"] = cpu_baseline(entries, "the first %d of the %d patterns" % (n_pat, fc.n_patterns), W, m)
+    W.close()
+    return out
+
+
+def run_chain_block(args, P, ctx, model):
+    """The second half of the metric -- MCMC_SEQ logL evaluations / s -- on BASELINE configs[2] (cfg3: full logL of
+    every locus per proposal) and configs[3] (cfg4: chain steps with dirty-path recompute), each with the CPU path
+    timed on the same inputs and a bitwise cached == recomputed flag.  Bounded to a few seconds each."""
+    out = {}
+    out["cfg3_full_eval"] = chain_cfg3(args, P, ctx, model)
+    out["cfg4_dirty_chain"], out["cfg4_joint_chain"] = chain_cfg4(args, P, ctx, model)
+    return out
+
+
+def chain_cfg3(args, P, ctx, model):
+    """cfg3: 200 loci x 24 taxa x 1,000 sites; every proposal re-scores EVERY locus (reference loop
+    src/_mcmc_seq.py:746-750 with every _felsen entry None), through the engine seam and through the resident batch."""
+    spec = WORKLOADS["cfg3"]
+    trees, alns = make_locus_data(spec["M"], spec["n"], spec["L"], SEEDS["cfg3"])
+    taxa = ["t%d" % i for i in range(spec["n"])]
+    calcs = [P.FelsensteinCalculator.from_matrix(taxa, a, device_compress=False) for a in alns]
+    eng = P.SeqLikelihoodEngine(calcs, None, model, context=ctx)
+    scales = [1.0 + 0.002 * k for k in range(8)]
+    props = [[t.with_lengths(t.blen * s) for t in trees] for s in scales]
+    M = len(trees)
+
+    def one(k):
+        for i in range(M):
+            eng.invalidate_locus(i)
+        return eng.log_likelihood(props[k % 8], None, 0.0)
+    for k in range(3):
+        one(k)
+    n = 100
+    t0 = time.perf_counter()
+    for k in range(n):
+        total = one(k)
+    seam_s = (time.perf_counter() - t0) / n
+    eng._commit_pending()
+    cached = list(eng._felsen)
+    for i in range(M):
+        eng.invalidate_locus(i)
+    eng.invalidate_device_cache()
+    fresh_total = eng.log_likelihood(props[(n - 1) % 8], None, 0.0)
+    eng._commit_pending()
+    # the same evaluation through the resident batch (lengths only)
+    import torch
+    W = Workload(P, ctx, model, calcs, trees, 8)
+    for k in range(3):
+        W.batch.eval(W.mh, W.h_blens[k].numpy())
+    t0 = time.perf_counter()
+    for k in range(n):
+        vals = W.batch.eval(W.mh, W.h_blens[k % 8].numpy())
+    batch_s = (time.perf_counter() - t0) / n
+    res = {
+        "what": "full logL of all 200 loci per proposal, host trees / lengths in -> host values out, Python loop included",
+        "evals_per_s_engine_seam": 1.0 / seam_s, "evals_per_s_resident_batch": 1.0 / batch_s,
+        "updates_per_eval": int(W.updates_local),
+        "cached_equals_recomputed_bitwise": bool(cached == list(eng._felsen) and fresh_total == total),
+        "batch_equals_engine_bitwise": bool(np.array_equal(vals, np.array(cached))),
+    }
+    if not args.no_cpu_baseline:
+        cp = CpuPath(cpu_entries_loci(trees, alns, taxa, scales=(scales[(n - 1) % 8],)), min(os.cpu_count() or 1, 32))
+        try:
+            cp.step(1)
+            dt, _, cvals = cp.step(3)
+        finally:
+            cp.close()
+        res["cpu"] = {"evals_per_s": 1.0 / dt, "kind": cp.kind, "cores": cp.procs,
+                      "sample": describe_cpu(cp.kind, cp.procs, "all 200 loci (the whole evaluation)"),
+                      "max_rel_err_gpu_vs_cpu": max(abs(g - v) / abs(v) for g, v in zip(cached, cvals))}
+    W.batch.close()
+    for c in calcs:
+        c.close()
+    return res
+
+
+def chain_cfg4(args, P, ctx, model):
+    """cfg4: 1,000 loci x 16 taxa x 500 sites as MCMC chains.  (a) Felsenstein only: single-locus node-height
+    proposals through the engine seam (dirty-path recompute, commit on accept / rollback on reject).  (b) Both
+    factors of the MCMC_SEQ likelihood (reference src/_mcmc_seq.py:745-761): the reference's gene-tree operators on
+    flat arrays + a theta move every 10th step, on a 1-reticulation network."""
+    from phynetpy_b200 import simulate as S, moves as MV
+    from phynetpy_b200.candidates import node_heights
+    spec = WORKLOADS["cfg4"]
+    n_loci, n_species, L = spec["M"], spec["n"], spec["L"]
+    rng = np.random.default_rng(45)
+    theta = 0.02
+    net = S.random_species_network(n_species, 1, rng, height=0.005 * (n_species - 1))
+    trees, species_of = S.simulate_gene_trees_msnc(net, 1, theta, rng, n_loci)
+    aln = S.simulate_alignments(np.stack([t.parent for t in trees]), np.stack([t.blen for t in trees]), L,
+                                S.DEFAULT_PI, S.DEFAULT_RATES, rng)
+    loci = [S.to_alignment_dict(aln[i]) for i in range(n_loci)]
+    taxa = list(loci[0].keys())
+
+    # ---- (a) dirty-path chain, Felsenstein factor only -------------------------------------------------
+    eng = P.SeqLikelihoodEngine(loci, species_of, model, context=ctx)
+    cur = list(trees)
+    heights = [node_heights(t) for t in cur]
+    total = eng.log_likelihood(cur, None, 0.0)
+    n_steps = 1500
+    accepted = recomputed = 0
+    lat = []
+    touched = []
+    t0 = time.perf_counter()
+    for step in range(n_steps):
+        i = int(rng.integers(0, n_loci))
+        mv = MV.slide_height_move(cur[i], heights[i], rng)
+        if mv is None:
+            continue
         snap = eng.clone_caches()
+        prop = list(cur)
+        prop[i] = mv[0]
         eng.invalidate_locus(i)
         s0 = time.perf_counter()
         new_total = eng.log_likelihood(prop, None, 0.0)
         lat.append(time.perf_counter() - s0)
-        c_ms.append(ctx.last_timings()["call_ms"])
-        upd += eng.last_stats["updates"]
         recomputed += eng.last_stats["nodes_recomputed"]
-        if math.log(rng.random()) < (new_total - total):    # Metropolis on the likelihood alone
+        touched.append(i)
+        if math.log(rng.random()) < (new_total - total) + mv[2]:
             cur, total = prop, new_total
+            heights[i] = mv[1]
             accepted += 1
         else:
             eng.restore_caches(snap)
     wall = time.perf_counter() - t0
     eng._commit_pending()
-    incremental = list(eng._felsen)
-    # full recomputation of the final state
-    for i in range(M):
+    inc = list(eng._felsen)
+    for i in range(n_loci):
         eng.invalidate_locus(i)
     eng.invalidate_device_cache()
     full = eng.log_likelihood(cur, None, 0.0)
     eng._commit_pending()
-    return {
-        "what": "single-locus node-height proposals through SeqLikelihoodEngine (dirty-path recompute, "
-                "commit on accept / rollback on reject), Python host loop included",
-        "steps": n_steps, "steps_per_s": n_steps / wall, "accept_rate": accepted / n_steps,
-        "mean_nodes_recomputed": recomputed / n_steps, "mean_updates_per_step": upd / n_steps,
+    dirty = {
+        "what": "single-locus node-height proposals (the reference's op_gene_node_height on flat arrays) through "
+                "SeqLikelihoodEngine: dirty-path recompute, commit on accept / rollback on reject, Python loop included",
+        "steps": n_steps, "steps_per_s": len(lat) / wall, "accept_rate": accepted / max(len(lat), 1),
+        "mean_nodes_recomputed": recomputed / max(len(lat), 1),
         "median_eval_latency_us": float(np.median(lat) * 1e6),
-        "median_c_abi_call_us": float(np.median(c_ms) * 1e3),
-        "full_recompute_total": full,
-        "per_locus_incremental_equals_full_recompute_bitwise": bool(incremental == list(eng._felsen)),
+        "cached_equals_recomputed_bitwise": bool(inc == list(eng._felsen) and full == total),
     }
+    if not args.no_cpu_baseline:
+        # what the reference does for such a step: re-prune the dirty locus from the tips (src/_mcmc_seq.py:746-750)
+        sel = sorted(set(touched))[:128]
+        cp = CpuPath(cpu_entries_loci([cur[i] for i in sel], [aln[i] for i in sel], taxa), 1)
+        try:
+            cp.step(1)
+            dt, _, cvals = cp.step(3)
+        finally:
+            cp.close()
+        dirty["cpu"] = {"steps_per_s": len(sel) / dt, "kind": cp.kind, "cores": 1,
+                        "sample": describe_cpu(cp.kind, 1, "%d of the loci the chain touched (one full re-pruning per step, "
+                                               "which is what the reference's scalar cache does)" % len(sel)),
+                        "max_rel_err_gpu_vs_cpu": max(abs(eng._felsen[i] - v) / abs(v) for i, v in zip(sel, cvals))}
 
-
-def joint_chain(P, ctx, model, n_loci, n_species, L, n_steps, seed=45):
-    """MCMC_SEQ's whole likelihood, sum_i [log P(S_i|g_i) + log P(g_i|Psi)] (reference src/_mcmc_seq.py:745-761),
-    through the engine seam with BOTH factors on the device: single-locus node-height proposals (dirty-path
-    pruning + one MSNC density) and, every 10th step, a theta proposal (invalidate_network: the MSNC density of
-    every locus in one call).  Data: a 1-reticulation species network, gene trees from the network coalescent on
-    it, GTR alignments on those trees.  Ends with a full recomputation that must reproduce both cached factors."""
-    from phynetpy_b200 import simulate as S
-    rng = np.random.default_rng(seed)
-    theta = 0.02
-    net = S.random_species_network(n_species, 1, rng, height=0.005 * (n_species - 1))
-    trees, species_of = S.simulate_gene_trees_msnc(net, 1, theta, rng, n_loci)
-    par = np.stack([t.parent for t in trees])
-    bl = np.stack([t.blen for t in trees])
-    aln = S.simulate_alignments(par, bl, L, S.DEFAULT_PI, S.DEFAULT_RATES, rng)
-    loci = [S.to_alignment_dict(aln[i]) for i in range(n_loci)]
-    eng = P.SeqLikelihoodEngine(loci, species_of, model, context=ctx)
+    # ---- (b) joint chain: both factors on the device ----------------------------------------------------
+    eng2 = P.SeqLikelihoodEngine(eng._calcs, species_of, model, context=ctx)
     cur = list(trees)
-    total = eng.log_likelihood(cur, net, theta)
-    eng._commit_pending()
-    from phynetpy_b200 import moves as MV
-    from phynetpy_b200.candidates import node_heights
     heights = [node_heights(t) for t in cur]
-    lat_locus, lat_theta, accepted, impossible, void = [], [], 0, 0, 0
+    total = eng2.log_likelihood(cur, net, theta)
+    n2 = 1000
+    lat_locus, lat_theta, accepted, impossible = [], [], 0, 0
     t0 = time.perf_counter()
-    for step in range(n_steps):
-        snap = eng.clone_caches()
+    done = 0
+    for step in range(n2):
+        snap = eng2.clone_caches()
         prop_h, loghr = None, 0.0
         if step % 10 == 9:
             new_theta = theta * math.exp(float(rng.uniform(-0.2, 0.2)))
-            loghr = math.log(new_theta / theta)            # scaler move (op_change_theta, src/_mcmc_seq.py:888-915)
-            eng.invalidate_network()
+            loghr = math.log(new_theta / theta)
+            eng2.invalidate_network()
             prop = cur
             s0 = time.perf_counter()
-            new_total = eng.log_likelihood(prop, net, new_theta)
+            new_total = eng2.log_likelihood(prop, net, new_theta)
             lat_theta.append(time.perf_counter() - s0)
         else:
             new_theta = theta
             i = int(rng.integers(0, n_loci))
-            # the reference's gene-tree operators on flat arrays (phynetpy_b200/moves.py): node-height slide
-            # (op_gene_node_height) or height-preserving NNI (op_gene_tree_nni)
             if step % 3 == 2:
-                out = MV.nni_move(cur[i], heights[i], rng)
-                move = None if out is None else (out[0], out[1], 0.0)
+                o = MV.nni_move(cur[i], heights[i], rng)
+                move = None if o is None else (o[0], o[1], 0.0)
             else:
                 move = MV.slide_height_move(cur[i], heights[i], rng)
             if move is None:
-                void += 1
                 continue
             prop = list(cur)
             prop[i] = move[0]
             prop_h = (i, move[1])
             loghr = move[2]
-            eng.invalidate_locus(i)
+            eng2.invalidate_locus(i)
             s0 = time.perf_counter()
-            new_total = eng.log_likelihood(prop, net, theta)
+            new_total = eng2.log_likelihood(prop, net, theta)
             lat_locus.append(time.perf_counter() - s0)
+        done += 1
         impossible += new_total == -math.inf
         if math.log(rng.random()) < (new_total - total) + loghr:
             cur, total, theta = prop, new_total, new_theta
@@ -623,246 +924,92 @@ def joint_chain(P, ctx, model, n_loci, n_species, L, n_steps, seed=45):
                 heights[prop_h[0]] = prop_h[1]
             accepted += 1
         else:
-            eng.restore_caches(snap)
+            eng2.restore_caches(snap)
     wall = time.perf_counter() - t0
-    eng._commit_pending()
-    inc_f, inc_m = list(eng._felsen), list(eng._msnc)
+    eng2._commit_pending()
+    inc_f, inc_m = list(eng2._felsen), list(eng2._msnc)
     for i in range(n_loci):
-        eng.invalidate_locus(i)
-    eng.invalidate_device_cache()
-    full = eng.log_likelihood(cur, net, theta)
-    eng._commit_pending()
-    return {
-        "what": "both factors of the MCMC_SEQ likelihood on the device through SeqLikelihoodEngine.log_likelihood("
-                "gene_trees, species_net, theta); Python host loop included",
-        "loci": n_loci, "species": n_species, "reticulations": 1, "sites": L,
-        "steps": n_steps, "logL_evaluations_per_s": n_steps / wall, "accept_rate": accepted / n_steps,
-        "proposals_without_embedding": int(impossible), "void_proposals": int(void),
-        "moves": "node-height slide / height-preserving NNI of one locus (moves.py), theta scaling every 10th step",
+        eng2.invalidate_locus(i)
+    eng2.invalidate_device_cache()
+    full = eng2.log_likelihood(cur, net, theta)
+    eng2._commit_pending()
+    joint = {
+        "what": "both factors of the MCMC_SEQ likelihood on the device through SeqLikelihoodEngine.log_likelihood(gene_trees, "
+                "species_net, theta): node-height slide / NNI of one locus, theta scaling every 10th step; Python loop included",
+        "loci": n_loci, "species": n_species, "reticulations": 1,
+        "logL_evaluations_per_s": done / wall, "accept_rate": accepted / max(done, 1),
+        "proposals_without_embedding": int(impossible),
         "median_latency_us_locus_move": float(np.median(lat_locus) * 1e6),
         "median_latency_us_theta_move_all_loci_msnc": float(np.median(lat_theta) * 1e6),
-        "final_total": full,
-        "incremental_equals_full_recompute_bitwise": bool(inc_f == list(eng._felsen) and inc_m == list(eng._msnc)
-                                                          and full == total),
+        "cached_equals_recomputed_bitwise": bool(inc_f == list(eng2._felsen) and inc_m == list(eng2._msnc) and full == total),
     }
-
-
-def coupled_move_leg(P, ctx, model, n_loci, n_species, L, seed=46):
-    """One guided joint gene-tree re-proposal of a coupled add-reticulation move (reference
-    _coupled_gene_tree_reproposal, src/_mcmc_seq.py:1995-2070): every locus' candidate set scored under the target
-    network (Felsenstein + MSNC), one member sampled, the candidate sets of the chosen trees scored under the
-    reverse network -- four device calls in phynetpy_b200/coupled.py; host enumeration included."""
-    from phynetpy_b200 import simulate as S
-    from phynetpy_b200.candidates import candidate_table, node_heights
-    from phynetpy_b200.coupled import coupled_gene_tree_reproposal
-    rng = np.random.default_rng(seed)
-    theta = 0.02
-    sp_tree = S.random_species_network(n_species, 0, rng, height=0.005 * (n_species - 1))
-    # the same tree with one reticulation = the network the move proposes
-    rng2 = np.random.default_rng(seed)
-    sp_net = S.random_species_network(n_species, 1, rng2, height=0.005 * (n_species - 1))
-    trees, species_of = S.simulate_gene_trees_msnc(sp_tree, 1, theta, rng, n_loci)
-    aln = S.simulate_alignments(np.stack([t.parent for t in trees]), np.stack([t.blen for t in trees]), L,
-                                S.DEFAULT_PI, S.DEFAULT_RATES, rng)
-    eng = P.SeqLikelihoodEngine([S.to_alignment_dict(aln[i]) for i in range(n_loci)], species_of, model, context=ctx)
-    eng.log_likelihood(trees, sp_tree, theta)
-    eng._commit_pending()
-    heights = [node_heights(t) for t in trees]
-    res, times = None, []
-    for rep in range(4):
+    if not args.no_cpu_baseline:
+        from oracle import msnc_oracle as MO   # checker and CPU baseline only
+        netd = net.to_dict()
+        k = 40
         t0 = time.perf_counter()
-        res = coupled_gene_tree_reproposal(eng, trees, heights, sp_net, sp_tree, theta, np.random.default_rng(rep))
-        times.append(time.perf_counter() - t0)
-    n_members = sum(candidate_table(t, h)[0].shape[0] for t, h in zip(trees, heights))
-    return {
-        "what": "coupled_gene_tree_reproposal: forward + reverse candidate sets of all loci, 4 device calls",
-        "loci": n_loci, "forward_candidate_trees": int(n_members),
-        "prunings_and_densities_the_reference_would_run": int(4 * n_members),
-        "seconds_per_move": float(np.median(times[1:])), "first_call_seconds": float(times[0]),
-        "declined": res is None,
-        "log_qf": None if res is None else res[2], "log_qr": None if res is None else res[3],
-    }
+        want = [MO.msnc_log_density(netd, t.parent.tolist(), t.blen.tolist(), t.label, species_of, theta) for t in cur[:k]]
+        dt = time.perf_counter() - t0
+        joint["cpu_msnc"] = {"gene_trees_per_s": k / dt, "kind": "port", "cores": 1,
+                             "sample": "oracle/msnc_oracle.py (Python restatement of the reference DP) on %d gene trees" % k,
+                             "max_rel_err_gpu_vs_cpu": max(abs(g - w) / max(1.0, abs(w)) for g, w in zip(eng2._msnc[:k], want))}
+    for c in eng._calcs:
+        c.close()
+    return dirty, joint
 
 
-def candidate_batch(P, ctx, calcs, trees, model, n_loci):
-    """The coupled moves' inner double loop (reference src/_mcmc_seq.py:2028 x :1935-1957): for every locus
-    the candidate set (tree + height-preserving NNI neighbours) x (0.25, 0.5, 1, 2, 4), every member scored
-    by a full pruning -- here all loci x all candidates in ONE PNB_EVAL_NOSTORE call."""
-    from phynetpy_b200.candidates import candidate_arrays
-    eng = P.SeqLikelihoodEngine(calcs[:n_loci], None, model, context=ctx)
-    base = eng.log_likelihood(trees[:n_loci], None, 0.0)
-    eng._commit_pending()
-    t0 = time.perf_counter()
-    sets = [(i, (trees[i],) + candidate_arrays(trees[i])) for i in range(n_loci)]
-    t_enum = time.perf_counter() - t0
-    n_trees = sum(c[1].shape[0] for _, c in sets)
-    for _ in range(2):                                 # warm-up: templates, both pinned staging buffers
-        eng.score_candidate_sets(sets)
-    t0 = time.perf_counter()
-    res = eng.score_candidate_sets(sets)
-    wall = time.perf_counter() - t0
-    st = dict(eng.last_stats)
-    tm = ctx.last_timings()
-    ctx.set_profiling(True)
-    eng.score_candidate_sets(sets)
-    tm_prof = ctx.last_timings()
-    ctx.set_profiling(False)
-    # the identity candidate of every locus must reproduce the committed tree's value
-    ident_ok = all(any(v == eng._felsen[i] for v in vals) for (i, _), vals in zip(sets, res))
-    return {
-        "what": "all candidates of %d loci scored in one device call (NOSTORE), Python packing included" % n_loci,
-        "candidate_trees": n_trees, "trees_per_locus": n_trees / n_loci,
-        "seconds": wall, "trees_per_s": n_trees / wall, "updates_per_s": st["updates"] / wall,
-        "c_abi_call_ms": tm["call_ms"], "host_compile_ms": tm["compile_ms"],
-        "kernel_span_ms": tm_prof["prune_ms"], "tiles": st["tiles"], "launches": st["launches"],
-        "enumeration_seconds_python": t_enum,
-        "identity_candidate_reproduces_committed_value": bool(ident_ok), "base_total": base,
-    }
-
-
-def msnc_leg(P, ctx, n_loci, n_species, cpu=True, seed=44):
-    """The other factor of the MCMC_SEQ likelihood, log P(g_i | Psi) (kernel K-m):
-    all loci of a full evaluation in one pnb_msnc_eval call, and the candidate sets of the coupled moves in
-    one call, on a species tree and on a network with two reticulations.  Host arrays in, host values out."""
-    from phynetpy_b200 import simulate as S
-    from phynetpy_b200._msnc_density import msnc_eval_packed
-    from phynetpy_b200.candidates import candidate_arrays
-    from oracle import msnc_oracle as MO   # checker and CPU baseline only
-    rng = np.random.default_rng(seed)
-    theta = 0.02
-    out = {}
-    for name, n_retic in (("species_tree", 0), ("network_2_reticulations", 2)):
-        net = S.random_species_network(n_species, n_retic, rng, height=0.005 * (n_species - 1))
-        trees, species_of = S.simulate_gene_trees_msnc(net, 1, theta, rng, n_loci)
-
-        def pack(sets):
-            par = np.ascontiguousarray(np.concatenate([p.reshape(-1) for p, _, _ in sets]), dtype=np.int32)
-            bl = np.ascontiguousarray(np.concatenate([b.reshape(-1) for _, b, _ in sets]), dtype=np.float64)
-            ids = np.ascontiguousarray(np.concatenate([np.tile(i, p.shape[0]) for p, _, i in sets]), dtype=np.int32)
-            sizes = np.concatenate([np.full(p.shape[0], p.shape[1], dtype=np.int64) for p, _, _ in sets])
-            off = np.zeros(sizes.shape[0] + 1, dtype=np.int64)
-            np.cumsum(sizes, out=off[1:])
-            return off, par, bl, ids
-
-        ids_of = [net.species_ids_of(t, species_of) for t in trees]
-        full = pack([(t.parent[None, :], t.blen[None, :], i) for t, i in zip(trees, ids_of)])
-        n_cand_loci = min(200, n_loci)
-        cand = pack([candidate_arrays(trees[k]) + (ids_of[k],) for k in range(n_cand_loci)])
-        res = {"reticulations": n_retic, "program": net.info(ctx)}
-        one = pack([(trees[0].parent[None, :], trees[0].blen[None, :], ids_of[0])])
-        for tag, arrs in (("one_locus", one), ("all_loci", full), ("candidate_sets", cand)):
-            n_trees = arrs[0].shape[0] - 1
-            for _ in range(3):
-                vals = msnc_eval_packed(net, *arrs, theta, ctx)
-            reps = 200 if tag == "one_locus" else 20
-            t0 = time.perf_counter()
-            for _ in range(reps):
-                vals = msnc_eval_packed(net, *arrs, theta, ctx)
-            wall = (time.perf_counter() - t0) / reps
-            ctx.set_profiling(True)
-            msnc_eval_packed(net, *arrs, theta, ctx)
-            tm = ctx.last_timings()
-            ctx.set_profiling(False)
-            res[tag] = {"gene_trees": int(n_trees), "ms_per_call": wall * 1e3, "trees_per_s": n_trees / wall,
-                        "kernel_ms": tm["prune_ms"], "host_prepare_ms": tm["compile_ms"],
-                        "finite": int(np.isfinite(vals).sum())}
-            if tag == "all_loci":
-                netd = net.to_dict()
-                k = min(100, n_loci)
-                t0 = time.perf_counter()
-                want = [MO.msnc_log_density(netd, t.parent.tolist(), t.blen.tolist(), t.label, species_of, theta)
-                        for t in trees[:k]] if cpu else []
-                dt = time.perf_counter() - t0
-                if cpu:
-                    err = max(abs(g - w) / max(1.0, abs(w)) for g, w in zip(vals[:k], want))
-                    res["parity_max_rel_err_vs_oracle"] = err
-                    res["cpu_baseline"] = {"value": k / dt, "unit": "gene trees/s", "cores": 1, "kind": "port",
-                                           "sample": "oracle/msnc_oracle.py (Python restatement of the reference DP) on %d of the "
-                                                     "gene trees" % k}
-        out[name] = res
-    out["what"] = ("pnb_msnc_eval through the C ABI: packed host tree arrays in -> host preparation (heights, sorted "
-                   "coalescence events, lineage sets) -> one kernel, one thread per gene tree -> values out")
-    return out
-
-
-def cpu_baseline(wl, spec, sample):
-    cores = os.cpu_count() or 1
-    if wl == "cfg2":
-        codes, weights, ft = sample
-        n_pat = min(200_000, codes.shape[1])
-        dt, ups, val = oracle_time_single(codes, weights, ft, n_pat, repeats=3)
-
-        def check(calcs, trees, model, P):
-            sub = P.FelsensteinCalculator.from_codes(calcs[0].taxa, codes[:, :n_pat], weights[:n_pat])
-            got = sub.log_likelihood(trees[0], model)
-            sub.close()
-            return {"oracle_logL_sample": val, "gpu_logL_sample": got, "rel_err": abs(got - val) / abs(val),
-                    "sample": "first %d patterns" % n_pat}
-        return {"value": ups / dt, "unit": "updates/s", "cores": cores, "kind": "port",
-                "sample": "oracle (NumPy restatement of the reference's _postorder_partials) on the first %d of the "
-                          "patterns, best of 3 evaluations; NumPy/OpenBLAS default threading" % n_pat,
-                "seconds_per_eval_sample": dt, "_check": check}
-    trees, alns = sample
-    procs = min(cores, 32)
-    dt, ups = oracle_time_loci(trees, alns, procs)
-    return {"value": ups / dt, "unit": "updates/s", "cores": procs, "kind": "port",
-            "sample": "oracle (NumPy restatement of the reference loop src/_mcmc_seq.py:746-750) on the first %d loci, "
-                      "loci split over %d processes, mean of 10 evaluations each (construction excluded)" % (len(trees), procs),
-            "seconds_sample": dt}
-
-
+# --------------------------------------------------------------------------- reference arm
 def run_reference(args, wl, spec, rank):
-    """The reference's CPU algorithm for the path (oracle port: the reference is pure NumPy/Python
-    and cannot travel to the GPU box) on this box's host cores, bounded sample per step."""
+    """The reference's own CPU implementation of the path on this box's host cores (rank 0 only): the UNMODIFIED
+    package from baseline/_ref when present (kind "reference"), else the oracle port.  Each step = one evaluation of
+    a bounded sample of the workload; the per-locus objects are built once, outside the clock."""
     if rank != 0:
         return
     from phynetpy_b200 import simulate as S
-    from oracle import felsenstein_oracle as O
     cores = os.cpu_count() or 1
-    steps, warm = args.steps, max(args.warmup, 1)
+    procs = min(cores, 32)
+    steps, warm = max(1, min(args.steps, 10)), max(args.warmup, 1)
     if wl == "cfg2":
-        n, n_pat = spec["n"], 100_000
+        from oracle import felsenstein_oracle as O
+        n, n_pat = spec["n"], 200_000
         rng = np.random.default_rng(2)
         par, bl = S.random_trees(1, n, rng)
         ft = S.flat_trees(par, bl)[0]
         mat = S.simulate_alignments(par, bl, int(n_pat * 1.05), PI, RATES, rng)[0]
         first, w, _ = O.compress_fast(mat)
         lut = np.array([O.tip_code_for_char(chr(b)) for b in range(256)], dtype=np.uint8)
-        codes = lut[mat[:, first[:n_pat]]]
-        w = w[:n_pat]
+        codes = np.ascontiguousarray(lut[mat[:, first[:n_pat]]])
         n_pat = codes.shape[1]
-        steps = min(steps, 10)
-        for _ in range(warm):
-            oracle_time_single(codes, w, ft, n_pat, 1)
-        t0 = time.perf_counter()
-        ups = 0
-        for _ in range(steps):
-            _, u, _ = oracle_time_single(codes, w, ft, n_pat, 1)
-            ups += u
-        dt = time.perf_counter() - t0
-        sample = "each step = one evaluation of the first %d patterns of the cfg2 workload (1/%d of it)" % (n_pat, spec["P"] // n_pat)
-        used = cores
+        tip_row = ft.tip_rows({"t%d" % i: i for i in range(n)}).tolist()
+        entries = [("codes", codes, w[:n_pat].copy(), tip_row, _tree_tuple(ft))]
+        what = "the first %d patterns of the cfg2 workload (1/%d of it)" % (n_pat, max(1, spec["P"] // n_pat))
     else:
-        n_loci = min(spec["M"], 128)
-        trees, alns = make_locus_data(spec["M"], spec["n"], spec["L"], {"cfg3": 3, "cfg4": 4, "cfg5": 5}[wl], 0, n_loci)
-        used = min(cores, 32)
-        steps = min(steps, 10)
-        for _ in range(warm):
-            oracle_time_loci(trees, alns, used)
-        dt, ups = 0.0, 0
-        for _ in range(steps):
-            d, u = oracle_time_loci(trees, alns, used)
+        n_loci = min(spec["M"], 512)
+        trees, alns = make_locus_data(spec["M"], spec["n"], spec["L"], SEEDS[wl], 0, n_loci)
+        taxa = ["t%d" % i for i in range(spec["n"])]
+        entries = cpu_entries_loci(trees, alns, taxa, scales=tuple(1.0 + 0.002 * k for k in range(8)))
+        what = "the first %d of the %d loci" % (n_loci, spec["M"])
+    cp = CpuPath(entries, procs)
+    try:
+        for k in range(warm):
+            cp.step(1, k)
+        dt = 0.0
+        ups = 0
+        for k in range(steps):
+            d, u, _ = cp.step(1, k)
             dt += d
             ups += u
-        sample = "each step = the first %d of %d loci, split over %d host processes" % (n_loci, spec["M"], used)
+    finally:
+        cp.close()
     value = ups / dt
+    sample = "each step = one evaluation of " + describe_cpu(cp.kind, cp.procs, what)
     print(json.dumps({
         "impl": "reference", "metric": "site-node partial updates/sec", "value": value, "unit": "updates/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3,
         "higher_is_better": True, "scaling": "strong" if wl != "cfg2" else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "%s: %s" % (wl, spec["desc"]), "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "updates/s", "cores": used, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "updates/s", "cores": cp.procs, "kind": cp.kind, "sample": sample},
         "e2e": {"value": value, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 

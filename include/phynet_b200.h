@@ -204,6 +204,11 @@ PNB_API int pnb_batch_destroy(pnb_batch *b);
 /* info: [0] jobs, [1] nodes, [2] ops, [3] tiles, [4] site-node updates per evaluation, [5] internal nodes,
  * [6] dynamic shared memory per block, [7] upload chunks                                              */
 PNB_API int pnb_batch_info(const pnb_batch *b, int64_t info[8]);
+/* Bytes one evaluation moves, counted from the compiled programs: [0] node partials written to HBM (stored
+ * nodes x padded patterns x 32 B), [1] node partials read back (siblings written earlier in the same launch:
+ * normally L2 hits), [2] tip-code bytes, [3] weights + per-tile staging of programs and P matrices (L2).
+ * bench.py reports [0]+[2] (+ weights) as the kernel's compulsory DRAM traffic next to ncu's measured figure. */
+PNB_API int pnb_batch_traffic(const pnb_batch *b, int64_t bytes[4]);
 /* The batch's pinned staging buffer (total_nodes doubles): lengths written here are uploaded without a copy. */
 PNB_API int pnb_batch_blen_host(pnb_batch *b, double **pinned_out);
 PNB_API int pnb_batch_eval(pnb_batch *b, const pnb_model *m, const double *blen, double site_rate,

@@ -33,6 +33,7 @@ struct pnb_batch {
     Buffer h_blen, h_out;            // pinned staging
     int ops_cap = 1, rows_cap = 1, stk_cap = 0;
     size_t dyn_smem = 0;
+    int64_t traffic[4] = {0, 0, 0, 0};  // bytes per evaluation, counted from the programs (pnb_batch_traffic)
     // chunks of jobs for the pipelined host-lengths path: [c] = first job / node / op / tile of chunk c
     std::vector<int64_t> ck_job, ck_node, ck_op, ck_tile;
     // state of the last evaluation (what locus_sync materialises)
@@ -261,6 +262,23 @@ extern "C" int pnb_batch_create(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb
         jd.ops = nullptr;  // patched below once the device array exists
         if (loc->P > 0)
             for (int64_t t = tile_first[j]; t < tile_first[j + 1]; ++t) h_tile_job[t] = static_cast<int32_t>(j);
+        {
+            // what the kernel moves for this job, per evaluation: every F_STORE writes one 32-byte partial per (padded)
+            // pattern, every K_MEM op reads one (a sibling written earlier in the same launch: normally an L2 hit),
+            // every tip op stages one code byte per pattern; each tile also stages the program and its P matrices
+            int64_t n_store = 0, n_mem = 0, n_tip = 0;
+            for (int k = 0; k < jo.n_ops; ++k) {
+                const Op& o = h_ops[op_cursor + k];
+                if (o.flags & F_STORE) n_store++;
+                if ((o.flags & F_KIND_MASK) == K_MEM) n_mem++;
+                if ((o.flags & F_KIND_MASK) == K_TIP && o.src >= 0) n_tip++;
+            }
+            const int64_t tiles = tile_first[j + 1] - tile_first[j];
+            b->traffic[0] += n_store * loc->P_pad * 32;
+            b->traffic[1] += n_mem * loc->P_pad * 32;
+            b->traffic[2] += n_tip * loc->P_pad;
+            b->traffic[3] += loc->P_pad * 8 + tiles * static_cast<int64_t>(jo.n_ops) * (sizeof(Op) + 128);
+        }
         b->updates += static_cast<int64_t>(jo.n_dirty) * loc->P;
         b->n_dirty += jo.n_dirty;
         b->ops_cap = std::max(b->ops_cap, std::min(jo.n_ops, SEG_MAX_OPS));
@@ -352,6 +370,12 @@ extern "C" int pnb_batch_info(const pnb_batch* b, int64_t info[8]) {
     info[0] = b->M; info[1] = b->total_nodes; info[2] = b->total_ops; info[3] = b->total_tiles;
     info[4] = b->updates; info[5] = b->n_dirty; info[6] = static_cast<int64_t>(b->dyn_smem);
     info[7] = static_cast<int64_t>(b->ck_job.size()) - 1;
+    return PNB_OK;
+}
+
+extern "C" int pnb_batch_traffic(const pnb_batch* b, int64_t bytes[4]) {
+    PNB_REQUIRE(b && bytes, PNB_ERR_INVALID, "pnb_batch_traffic: NULL argument");
+    memcpy(bytes, b->traffic, sizeof(b->traffic));
     return PNB_OK;
 }
 

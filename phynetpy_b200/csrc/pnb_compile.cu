@@ -22,6 +22,12 @@ constexpr int64_t REF_ABSENT = -1;   // leaf whose taxon is not in the alignment
 constexpr int64_t REF_COMPUTED = -3; // NOSTORE: recomputed node that has no slot
 
 
+// explicit (host-supplied) P matrices arrive row-major; the pruning kernel reads P column by column (pnb_device.cuh)
+inline void copy_transposed(double* dst, const double* src) {
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) dst[j * 4 + i] = src[i * 4 + j];
+}
+
 #define CJ_REQUIRE(cond, code, ...)                           \
     do {                                                      \
         if (!(cond)) {                                        \
@@ -80,7 +86,7 @@ int pnb::compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int3
         for (int k = 0; k < n_ops_t; ++k) {
             const int c = T.op_child[k];
             t_out[k] = eff_len(c);
-            if (Pexp_out) memcpy(Pexp_out + static_cast<size_t>(k) * 16, P_edge + static_cast<size_t>(c) * 16, 128);
+            if (Pexp_out) copy_transposed(Pexp_out + static_cast<size_t>(k) * 16, P_edge + static_cast<size_t>(c) * 16);
         }
     };
     // ---- fastest path: a full, immediately committed re-evaluation of the topology the committed
@@ -217,11 +223,25 @@ int pnb::compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int3
     // being computed, and never read back: whoever needs them recomputes them.
     auto& virt = S.virt;
     virt.assign(n, 0);
-    for (int v = 0; v < n; ++v) {
-        if (cnt[v] == 0) continue;
-        bool all_tips = true;
-        for (int j = 0; j < cnt[v] && all_tips; ++j) all_tips = cnt[kids[off[v] + j]] == 0;
-        virt[v] = all_tips;
+    {
+        // Small subtrees are VIRTUAL: a node with at most `virt_tips` tips below it (and every node whose children are all
+        // tips, whatever its arity) is a short product of P columns selected by 1-byte tip codes -- cheaper to recompute
+        // from the codes than to move 32 B/pattern through HBM each way.  post-order: children before parents.
+        const int vmax = loc->ctx->virt_tips;
+        auto& tips = S.order;   // scratch (re-used below)
+        tips.assign(n, 0);
+        for (int v : post) {
+            if (cnt[v] == 0) { tips[v] = 1; continue; }
+            int t = 0;
+            bool all_tips = true;
+            for (int j = 0; j < cnt[v]; ++j) {
+                const int c = kids[off[v] + j];
+                t += tips[c];
+                all_tips &= cnt[c] == 0;
+            }
+            tips[v] = t;
+            virt[v] = all_tips || t <= vmax;
+        }
     }
     auto& P_ = loc->pending;
     if (!nostore) {
@@ -306,7 +326,7 @@ int pnb::compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int3
         }
         // stash need: recomputed internal kids are visited in order of decreasing need; the last one is
         // forwarded in registers, every earlier one is stashed while its later siblings are computed
-        if (dirty[v]) {
+        if (dirty[v] || virt[v]) {   // (a clean virtual subtree is recomputed too whenever its parent is)
             auto& tmp = S.order;
             tmp.clear();
             for (int j = 0; j < k; ++j) {
@@ -343,16 +363,19 @@ int pnb::compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int3
         // frame.push_idx: >= 0 stash index (NOSTORE); -1 nothing; -2 must be written to its slot
         auto open = [&](int v, int sp, int push_idx) {
             const int base = static_cast<int>(dk.size());
+            // stored nodes that are recomputed first, virtual (small) subtrees after them, then everything by
+            // decreasing stash need (stable): a virtual subtree with internal structure needs stash room too, and
+            // need[v] above is computed for exactly this order
             for (int j = 0; j < cnt[v]; ++j) {
                 const int c = kids[off[v] + j];
                 if (cnt[c] > 0 && dirty[c] && !virt[c]) dk.push_back(c);
             }
-            if (dk.size() - base > 1)
-                std::stable_sort(dk.begin() + base, dk.end(), [&](int a, int b) { return need[a] > need[b]; });
             for (int j = 0; j < cnt[v]; ++j) {
                 const int c = kids[off[v] + j];
                 if (cnt[c] > 0 && virt[c]) dk.push_back(c);
             }
+            if (dk.size() - base > 1)
+                std::stable_sort(dk.begin() + base, dk.end(), [&](int a, int b) { return need[a] > need[b]; });
             fs.push_back({v, 0, sp, push_idx, static_cast<int>(dk.size()) - base});
             dk_base.push_back(base);
         };
@@ -384,7 +407,7 @@ int pnb::compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int3
                 double tt;
                 memcpy(&tt, &len[c], 8);
                 t_out[n_ops] = tt;
-                if (Pexp_out) memcpy(Pexp_out + static_cast<size_t>(n_ops) * 16, P_edge + static_cast<size_t>(c) * 16, 128);
+                if (Pexp_out) copy_transposed(Pexp_out + static_cast<size_t>(n_ops) * 16, P_edge + static_cast<size_t>(c) * 16);
                 S.op_child.push_back(c);
                 n_ops++;
             };

@@ -21,10 +21,10 @@ namespace pnb {
 #define PNB_TPB 128
 #endif
 #ifndef PNB_PPT
-#define PNB_PPT 2
+#define PNB_PPT 4
 #endif
 #ifndef PNB_MIN_BLOCKS
-#define PNB_MIN_BLOCKS 6
+#define PNB_MIN_BLOCKS 4
 #endif
 constexpr int TPB = PNB_TPB;        // threads per block
 constexpr int PPT = PNB_PPT;        // site patterns per thread (independent dependency chains)
@@ -180,6 +180,20 @@ __device__ __forceinline__ void pmatrix_of_t(const ModelParams& mp, double t, do
     }
 }
 
+// The pruning kernel reads P COLUMN by column (a tip child selects one column of P by its state; an internal
+// child's contribution is accumulated column by column, P[:,j] * l_j): K-a writes P transposed for it, so a
+// column is 32 contiguous bytes (two LDS.128).  TRANSPOSED = false is the public row-major layout
+// (pnb_pmatrix_batch: P[i*4+j] = prob(i -> j)).
+template <bool TRANSPOSED>
+__device__ __forceinline__ void store_pmatrix(double* o, const double (&Pm)[16]) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        if (TRANSPOSED) stg256(o + a * 4, Pm[0 * 4 + a], Pm[1 * 4 + a], Pm[2 * 4 + a], Pm[3 * 4 + a]);
+        else stg256(o + a * 4, Pm[a * 4 + 0], Pm[a * 4 + 1], Pm[a * 4 + 2], Pm[a * 4 + 3]);
+    }
+}
+
+template <bool TRANSPOSED>
 __global__ void __launch_bounds__(128)
 pnb_pmatrix_kernel(const __grid_constant__ ModelParams mp, const double* __restrict__ t,
                    int64_t nb, double* __restrict__ P_out) {
@@ -187,9 +201,7 @@ pnb_pmatrix_kernel(const __grid_constant__ ModelParams mp, const double* __restr
     if (g >= nb) return;
     double Pm[16];
     pmatrix_of_t(mp, t[g], Pm);
-    double* o = P_out + g * 16;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) stg256(o + i * 4, Pm[i * 4 + 0], Pm[i * 4 + 1], Pm[i * 4 + 2], Pm[i * 4 + 3]);
+    store_pmatrix<TRANSPOSED>(P_out + g * 16, Pm);
 }
 
 // K-a for resident batches: op k takes the length of tree node node_of_op[k] from a node-ordered array
@@ -210,9 +222,7 @@ pnb_pmatrix_gather_kernel(const __grid_constant__ ModelParams mp, const double* 
     t *= site_rate;
     double Pm[16];
     pmatrix_of_t(mp, t, Pm);
-    double* o = P_out + g * 16;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) stg256(o + i * 4, Pm[i * 4 + 0], Pm[i * 4 + 1], Pm[i * 4 + 2], Pm[i * 4 + 3]);
+    store_pmatrix<true>(P_out + g * 16, Pm);
 }
 
 // ------------------------------------------------------------------------
@@ -277,39 +287,31 @@ __device__ __forceinline__ void lds_op(uint32_t a, uint32_t& f, int32_t& src, in
     asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(f), "=r"(src), "=r"(dst), "=r"(aux) : "r"(a));
 }
 
-// v = P . l   (child_partials @ P.T, reference :425); P row-major at shared address pk (broadcast reads).
-// OUT may alias nothing in `l`; ACCUM = multiply the result into `out` instead of overwriting it.
+// v = P . l   (child_partials @ P.T, reference :425).  P is staged TRANSPOSED: column j of P (the 4 values
+// P[0..3][j]) is 32 contiguous bytes at pk + 32 j, read by every lane at the same address (broadcast).  The
+// accumulation runs over columns, r_i = ((P_i0 l_0 + P_i1 l_1) + P_i2 l_2) + P_i3 l_3 -- the same expression
+// and rounding as a row-wise dot product.  ACCUM = multiply the result into `out` instead of overwriting it;
+// `out` may alias `l` only when !ACCUM (the register-forwarded child).
 template <bool ACCUM>
 __device__ __forceinline__ void matvec(uint32_t pk, const Vec4 (&l)[PPT], Vec4 (&out)[PPT]) {
-#ifdef PNB_MATVEC_P_IN_REGS
-    // the whole 4x4 P in registers, then one pattern at a time: `out` may alias `l`
-    double p[16];
-    lds_v2f64<0>(pk, p[0], p[1]);    lds_v2f64<16>(pk, p[2], p[3]);
-    lds_v2f64<32>(pk, p[4], p[5]);   lds_v2f64<48>(pk, p[6], p[7]);
-    lds_v2f64<64>(pk, p[8], p[9]);   lds_v2f64<80>(pk, p[10], p[11]);
-    lds_v2f64<96>(pk, p[12], p[13]); lds_v2f64<112>(pk, p[14], p[15]);
-#pragma unroll
-    for (int u = 0; u < PPT; ++u) {
-        const double a0 = l[u].x0, a1 = l[u].x1, a2 = l[u].x2, a3 = l[u].x3;
-        const double r0 = fma(p[3], a3, fma(p[2], a2, fma(p[1], a1, p[0] * a0)));
-        const double r1 = fma(p[7], a3, fma(p[6], a2, fma(p[5], a1, p[4] * a0)));
-        const double r2 = fma(p[11], a3, fma(p[10], a2, fma(p[9], a1, p[8] * a0)));
-        const double r3 = fma(p[15], a3, fma(p[14], a2, fma(p[13], a1, p[12] * a0)));
-        if (ACCUM) { out[u].x0 *= r0; out[u].x1 *= r1; out[u].x2 *= r2; out[u].x3 *= r3; }
-        else { out[u].x0 = r0; out[u].x1 = r1; out[u].x2 = r2; out[u].x3 = r3; }
-    }
-#else
     double r[PPT][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        double p0, p1, p2, p3;
-        if (i == 0) { lds_v2f64<0>(pk, p0, p1); lds_v2f64<16>(pk, p2, p3); }
-        else if (i == 1) { lds_v2f64<32>(pk, p0, p1); lds_v2f64<48>(pk, p2, p3); }
-        else if (i == 2) { lds_v2f64<64>(pk, p0, p1); lds_v2f64<80>(pk, p2, p3); }
-        else { lds_v2f64<96>(pk, p0, p1); lds_v2f64<112>(pk, p2, p3); }
+    for (int j = 0; j < 4; ++j) {
+        double c0, c1, c2, c3;
+        if (j == 0) { lds_v2f64<0>(pk, c0, c1); lds_v2f64<16>(pk, c2, c3); }
+        else if (j == 1) { lds_v2f64<32>(pk, c0, c1); lds_v2f64<48>(pk, c2, c3); }
+        else if (j == 2) { lds_v2f64<64>(pk, c0, c1); lds_v2f64<80>(pk, c2, c3); }
+        else { lds_v2f64<96>(pk, c0, c1); lds_v2f64<112>(pk, c2, c3); }
 #pragma unroll
-        for (int u = 0; u < PPT; ++u)
-            r[u][i] = fma(p3, l[u].x3, fma(p2, l[u].x2, fma(p1, l[u].x1, p0 * l[u].x0)));
+        for (int u = 0; u < PPT; ++u) {
+            const double lj = (j == 0) ? l[u].x0 : (j == 1) ? l[u].x1 : (j == 2) ? l[u].x2 : l[u].x3;
+            if (j == 0) {
+                r[u][0] = c0 * lj; r[u][1] = c1 * lj; r[u][2] = c2 * lj; r[u][3] = c3 * lj;
+            } else {
+                r[u][0] = fma(c0, lj, r[u][0]); r[u][1] = fma(c1, lj, r[u][1]);
+                r[u][2] = fma(c2, lj, r[u][2]); r[u][3] = fma(c3, lj, r[u][3]);
+            }
+        }
     }
 #pragma unroll
     for (int u = 0; u < PPT; ++u) {
@@ -319,7 +321,6 @@ __device__ __forceinline__ void matvec(uint32_t pk, const Vec4 (&l)[PPT], Vec4 (
             out[u].x0 = r[u][0]; out[u].x1 = r[u][1]; out[u].x2 = r[u][2]; out[u].x3 = r[u][3];
         }
     }
-#endif
 }
 
 // contribution of a tip child: column(s) of P selected by the device tip code
@@ -333,8 +334,10 @@ __device__ __forceinline__ void tip_contrib(uint32_t pk, const uint32_t (&code)[
     if (!__any_sync(0xffffffffu, amb)) {
 #pragma unroll
         for (int u = 0; u < PPT; ++u) {
-            const uint32_t col = pk + code[u] * 8u;
-            const double v0 = lds_f64<0>(col), v1 = lds_f64<32>(col), v2 = lds_f64<64>(col), v3 = lds_f64<96>(col);
+            const uint32_t col = pk + code[u] * 32u;   // column `state` of P: 32 contiguous bytes
+            double v0, v1, v2, v3;
+            lds_v2f64<0>(col, v0, v1);
+            lds_v2f64<16>(col, v2, v3);
             if (ACCUM) { out[u].x0 *= v0; out[u].x1 *= v1; out[u].x2 *= v2; out[u].x3 *= v3; }
             else { out[u].x0 = v0; out[u].x1 = v1; out[u].x2 = v2; out[u].x3 = v3; }
         }
@@ -346,8 +349,8 @@ __device__ __forceinline__ void tip_contrib(uint32_t pk, const uint32_t (&code)[
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 if (m & (1u << j)) {
-                    const uint32_t col = pk + j * 8;
-                    s0 += lds_f64<0>(col); s1 += lds_f64<32>(col); s2 += lds_f64<64>(col); s3 += lds_f64<96>(col);
+                    const uint32_t col = pk + j * 32;
+                    s0 += lds_f64<0>(col); s1 += lds_f64<8>(col); s2 += lds_f64<16>(col); s3 += lds_f64<24>(col);
                 }
             }
             if (ACCUM) { out[u].x0 *= s0; out[u].x1 *= s1; out[u].x2 *= s2; out[u].x3 *= s3; }
@@ -434,7 +437,9 @@ pnb_prune_kernel_t(const __grid_constant__ PruneLaunch L, const __grid_constant_
                 double Pm[16];
                 pmatrix_of_t(mp, L.t[op_off + seg + k], Pm);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) s_P[k * 16 + i] = Pm[i];
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) s_P[k * 16 + j * 4 + i] = Pm[i * 4 + j];   // transposed, as K-a writes it
                 if ((op.flags & F_KIND_MASK) == K_TIP && op.src >= 0) {
                     tma_bulk_g2s(s_codes + static_cast<size_t>(op.aux) * TILE_PATTERNS,
                                  g_codes + static_cast<int64_t>(op.src) * ld_codes + p0, TILE_PATTERNS, &bar_stage);
@@ -473,10 +478,29 @@ pnb_prune_kernel_t(const __grid_constant__ PruneLaunch L, const __grid_constant_
 
         uint32_t op_addr = ops_base;
         uint32_t pk = p_base;
+        uint32_t nflags;
+        int32_t nsrc, ndst, naux;
+#ifdef PNB_UNIFORM_LD
+        { const int4 o4 = __ldg(reinterpret_cast<const int4*>(g_ops + seg)); nflags = o4.x; nsrc = o4.y; ndst = o4.z; naux = o4.w; }
+#else
+        lds_op(op_addr, nflags, nsrc, ndst, naux);
+#endif
         for (int k = 0; k < nseg; ++k, op_addr += 16, pk += 128) {
-            uint32_t flags;
-            int32_t src, dst, aux;
-            lds_op(op_addr, flags, src, dst, aux);
+            // the op one ahead is fetched now: its ~30-cycle shared-memory latency overlaps this op's arithmetic
+            // (past the last op this reads the first bytes of the P area, still inside the block's shared memory)
+#ifdef PNB_UNIFORM_SHFL
+            const uint32_t flags = __shfl_sync(0xffffffffu, nflags, 0);
+            const int32_t src = __shfl_sync(0xffffffffu, nsrc, 0), dst = __shfl_sync(0xffffffffu, ndst, 0),
+                          aux = __shfl_sync(0xffffffffu, naux, 0);
+#else
+            const uint32_t flags = nflags;
+            const int32_t src = nsrc, dst = ndst, aux = naux;
+#endif
+#ifdef PNB_UNIFORM_LD
+            { const int4 o4 = __ldg(reinterpret_cast<const int4*>(g_ops + seg + k + 1)); nflags = o4.x; nsrc = o4.y; ndst = o4.z; naux = o4.w; }
+#else
+            lds_op(op_addr + 16, nflags, nsrc, ndst, naux);
+#endif
             const uint32_t kind = flags & F_KIND_MASK;
             const bool first = (flags & F_FIRST) != 0;
             if (kind == K_TIP) {
@@ -493,14 +517,7 @@ pnb_prune_kernel_t(const __grid_constant__ PruneLaunch L, const __grid_constant_
             } else if (kind == K_REG) {
                 // the child is the node completed just before: its partial is still in `acc`
                 // (the host always emits the forwarded child as the FIRST op of its parent)
-#ifdef PNB_MATVEC_P_IN_REGS
-                matvec<false>(pk, acc, acc);
-#else
-                Vec4 v[PPT];
-                matvec<false>(pk, acc, v);
-#pragma unroll
-                for (int u = 0; u < PPT; ++u) acc[u] = v[u];
-#endif
+                matvec<false>(pk, acc, acc);   // reads acc completely before it writes it
             } else {
                 Vec4 l[PPT];
                 int le[PPT];
@@ -608,7 +625,8 @@ pnb_prune_kernel_t(const __grid_constant__ PruneLaunch L, const __grid_constant_
         }
     }
 
-    // fused per-locus reduction: tile sum -> last-arriving tile sums tiles in index order
+    // fused per-locus reduction: tile sum -> last-arriving tile sums tiles in index order.  (One fence + one ticket per
+    // BLOCK: a per-warp version without the block barriers measured 7% slower -- __threadfence invalidates L1.)
     const double tsum = block_sum(lsum, red);
     const int n_tiles = jd.n_tiles;
     if (tid == 0) {

@@ -62,7 +62,7 @@ extern "C" int pnb_pmatrix_batch(pnb_ctx* ctx, const pnb_model* m, const double*
     PNB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     PNB_CUDA_TRY(cudaMemcpyAsync(ctx->d_stage.p, t, nb * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     const int64_t blocks = (nb + 127) / 128;
-    pnb_pmatrix_kernel<<<static_cast<unsigned>(blocks), 128, 0, ctx->stream>>>(
+    pnb_pmatrix_kernel<false><<<static_cast<unsigned>(blocks), 128, 0, ctx->stream>>>(
         m->mp, static_cast<const double*>(ctx->d_stage.p), nb, static_cast<double*>(ctx->d_P.p));
     PNB_CUDA_TRY(cudaGetLastError());
     PNB_CUDA_TRY(cudaMemcpyAsync(P_out, ctx->d_P.p, nb * 16 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -491,7 +491,7 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
         if (n_op_range > 0 && !explicit_P && !fused) {
             const int64_t blocks = (n_op_range + 127) / 128;
             if (prof) PNB_CUDA_TRY(cudaEventRecord(ctx->ev[0], up));
-            pnb_pmatrix_kernel<<<static_cast<unsigned>(blocks), 128, 0, up>>>(
+            pnb_pmatrix_kernel<true><<<static_cast<unsigned>(blocks), 128, 0, up>>>(
                 m->mp, reinterpret_cast<const double*>(ds + off_t) + ops_lo, n_op_range,
                 static_cast<double*>(ctx->d_P.p) + ops_lo * 16);
             PNB_CUDA_TRY(cudaGetLastError());

@@ -210,6 +210,8 @@ struct pnb_ctx {
     int chunk_min_jobs = 1024;     // batches of at least this many jobs are launched in chunks
     int store_stash_levels = 0;    // storing evaluations: siblings waiting at stash index < this use shared memory
                                    // instead of an L2 round trip through their slot (PNB_STORE_STASH)
+    int virt_tips = 4;             // subtrees of at most this many tips are recomputed from the tip codes, never stored
+                                   // (PNB_VIRT_TIPS; 2 = only tip-only nodes)
     bool allow_fused = true;       // small batches: single-kernel latency path (PNB_NO_FUSED=1 disables)
     bool msnc_configured = false;  // K-m kernels have their dynamic shared-memory limit raised
     pnb::Arena arena;

@@ -190,6 +190,7 @@ extern "C" int pnb_ctx_create(int device, pnb_ctx** out) {
     if (const char* e = getenv("PNB_CHUNK_MIN_JOBS")) ctx->chunk_min_jobs = std::max(2, atoi(e));
     if (const char* e = getenv("PNB_NO_FUSED")) ctx->allow_fused = atoi(e) == 0;
     if (const char* e = getenv("PNB_STORE_STASH")) ctx->store_stash_levels = std::max(0, std::min(atoi(e), 8));
+    if (const char* e = getenv("PNB_VIRT_TIPS")) ctx->virt_tips = std::max(1, std::min(atoi(e), 64));
     ctx->scratch.resize(workers);
     if (workers > 1) ctx->pool = new (std::nothrow) WorkerPool(workers);
     *out = ctx;
@@ -203,6 +204,7 @@ extern "C" int pnb_ctx_create_host(pnb_ctx** out) {
     ctx->device = -1;  // planning only: no stream, no arena, no kernels
     ctx->scratch.resize(1);
     if (const char* e = getenv("PNB_STORE_STASH")) ctx->store_stash_levels = std::max(0, std::min(atoi(e), 8));
+    if (const char* e = getenv("PNB_VIRT_TIPS")) ctx->virt_tips = std::max(1, std::min(atoi(e), 64));
     *out = ctx;
     return PNB_OK;
 }
@@ -517,8 +519,8 @@ extern "C" int pnb_locus_read_partial(pnb_locus* loc, int32_t node, double* out)
     if (ref >= loc->n_rows) {
         const int64_t slot = ref - loc->n_rows;
         PNB_REQUIRE(c.stored[slot], PNB_ERR_STATE,
-                    "pnb_locus_read_partial: node %d is a tip-only node; those are recomputed from the tip codes, "
-                    "not kept in HBM", node);
+                    "pnb_locus_read_partial: node %d is the root of a small subtree (tip-only, or at most %d tips); those are "
+                    "recomputed from the tip codes, not kept in HBM", node, loc->ctx->virt_tips);
         PNB_CUDA_TRY(cudaMemcpy(out, loc->d_partials + slot * loc->P_pad * 4,
                                 static_cast<size_t>(loc->P) * 4 * sizeof(double), cudaMemcpyDeviceToHost));
     } else if (ref >= 0) {

@@ -131,6 +131,9 @@ class ResidentBatch:
         self.info = dict(zip(("jobs", "nodes", "ops", "tiles", "updates", "internal_nodes", "smem_bytes", "chunks"),
                              (int(x) for x in arr)))
         self.n_nodes = self.info["nodes"]
+        _lib.check(self._lib.pnb_batch_traffic(h, arr))
+        self.traffic = {"partials_written": int(arr[0]), "partials_reread": int(arr[1]), "tip_codes": int(arr[2]),
+                        "weights_programs_pmatrices": int(arr[3])}
         self._pinned: Optional[np.ndarray] = None
 
     @property

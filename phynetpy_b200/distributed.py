@@ -88,10 +88,33 @@ class ShardPlan:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return t.cpu().numpy()
 
-    def allreduce_sum_device_(self, tensor) -> None:
-        """In-place all-reduce of a CUDA tensor the pruning kernel has just written
-        (same stream as the kernel: no host round trip between the two)."""
+    # -- the per-locus vector as equal slices: rank r owns [r * per, (r + 1) * per) -------------------------
+    @property
+    def slice_len(self) -> int:
+        """Length of one rank's slice of the gathered vector (the longest shard; shorter shards are padded)."""
+        return max(hi - lo for lo, hi in self.ranges)
+
+    def gathered_index(self) -> np.ndarray:
+        """For every locus its position in the gathered vector (``world_size * slice_len`` long)."""
+        per = self.slice_len
+        idx = np.empty(self.n_loci, dtype=np.int64)
+        for r, (lo, hi) in enumerate(self.ranges):
+            idx[lo:hi] = r * per + np.arange(hi - lo)
+        return idx
+
+    def allgather_slices_(self, vec) -> None:
+        """In-place all-gather of equal slices: every rank has written its own slice of ``vec``
+        (``world_size * slice_len`` doubles; a CUDA tensor the pruning kernel has just filled, on the
+        stream the kernel ran on); afterwards every rank holds all slices.  NCCL: one ``ncclAllGather``
+        whose send buffer IS this rank's slice of the receive buffer -- no staging copy, no zero-fill, no
+        host round trip.  Adding nothing to anything, the result is bit-identical for any number of ranks."""
         if self.world_size == 1:
             return
         import torch.distributed as dist
-        dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=self.group)
+        per = self.slice_len
+        mine = vec[self.rank * per:(self.rank + 1) * per]
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_gather_into_tensor(vec, mine, group=self.group)
+        else:   # gloo (CPU tests): gather into views of the same vector
+            parts = list(vec.view(self.world_size, per).unbind(0))
+            dist.all_gather(parts, mine.clone(), group=self.group)

@@ -1,6 +1,7 @@
 """The driver's contract for bench.py, checked on the CPU through the reference arm (`--impl reference` times the
-oracle port on host cores and needs no GPU): ONE JSON line with the agreed keys; the GPU arm refuses to run without
-a device instead of falling back."""
+reference's own CPU path -- the unmodified package from baseline/_ref when it is installed, else the oracle port --
+on host cores and needs no GPU): ONE JSON line with the agreed keys; the GPU arm refuses to run without a device
+instead of falling back."""
 import json
 import os
 import subprocess
@@ -29,7 +30,10 @@ def test_reference_arm_prints_one_contract_line():
     assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["dtype"] == "f64" and d["data"] == "synthetic"
     assert d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1
     assert "workload" in d["config"] and "model" not in d["config"]
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    have_ref = os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "phynetpy"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert "cfg5" in d["config"]["workload"]          # the same configuration at every N
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
 
 

@@ -137,18 +137,23 @@ def test_baseline_shapes_vs_oracle(n, L, seed):
     # every internal node's partial, as stored in HBM, against the oracle's
     # tip-only nodes ("cherries") are recomputed from the 1-byte codes instead of being kept in HBM
     nc = ft.n_children()
+    tips = (nc == 0).astype(int)
+    for v in range(ft.n_nodes):          # random_trees numbers children before parents
+        if ft.parent[v] >= 0:
+            tips[ft.parent[v]] += tips[v]
     checked = 0
     for node in np.nonzero(nc > 0)[0]:
         kids = np.nonzero(ft.parent == node)[0]
         try:
             got_partial = fc.node_partial(int(node))
         except P.PhyNetB200Error as e:
-            # only tip-only nodes may be absent (one that had to be held for a sibling IS materialised)
-            assert "tip-only" in str(e) and (nc[kids] == 0).all()
+            # only roots of small subtrees (tip-only, or <= PNB_VIRT_TIPS = 4 tips) may be absent (one that had to be
+            # held for a sibling IS materialised)
+            assert "small subtree" in str(e) and ((nc[kids] == 0).all() or tips[node] <= 4)
             continue
         np.testing.assert_allclose(got_partial, sink[int(node)], rtol=1e-12, atol=0)
         checked += 1
-    assert checked >= (n - 1) // 3 or n <= 5
+    assert checked >= (n - 1) // 4 or n <= 8
 
 
 def test_dirty_path_equals_full_recompute():

@@ -149,6 +149,7 @@ class Planner:
                 if flags & F_STORE:
                     slots[dst] = acc.copy()
                 if flags & F_PUSH:
+                    assert ((flags >> 8) & 0xFF) < stk_need, "stash index beyond the capacity the job announced"
                     stack[(flags >> 8) & 0xFF] = acc.copy()
         if root_kind == K_REG:
             assert n_ops > 0 and complete
@@ -162,11 +163,35 @@ class Planner:
         return float(np.dot(np.log(site), ol.weights))
 
 
-@pytest.fixture()
-def planner():
+VIRT_TIPS = [2, 4, 7]      # PNB_VIRT_TIPS: subtrees of at most this many tips are recomputed, never stored
+
+
+@pytest.fixture(params=VIRT_TIPS, ids=["virt%d" % v for v in VIRT_TIPS])
+def planner(request, monkeypatch):
+    monkeypatch.setenv("PNB_VIRT_TIPS", str(request.param))   # read when the planning context is created
     p = Planner()
+    p.virt_tips = request.param
     yield p
     p.close()
+
+
+def _tips_below(ft):
+    nc = ft.n_children()
+    tips = (nc == 0).astype(np.int64)
+    order = []
+    stack = [int(np.nonzero(ft.parent < 0)[0][0])]
+    kids = [[] for _ in range(ft.n_nodes)]
+    for i, p in enumerate(ft.parent.tolist()):
+        if p >= 0:
+            kids[p].append(i)
+    while stack:
+        v = stack.pop()
+        order.append(v)
+        stack.extend(kids[v])
+    for v in reversed(order):
+        for c in kids[v]:
+            tips[v] += tips[c]
+    return tips
 
 
 def _omodel(spec):
@@ -203,8 +228,9 @@ def test_compiled_program_reproduces_reference_logL(planner, case):
     nc = ft.n_children()
     root = int(np.nonzero(ft.parent < 0)[0][0])
     root_is_tip_only = nc[root] > 0 and all(nc[c] == 0 for c in np.nonzero(ft.parent == root)[0])
-    if root_is_tip_only:
-        assert p2[0][2] == K_REG and p2[0][0] == nc[root]   # a tip-only root is recomputed from the codes
+    root_is_virtual = nc[root] > 0 and (root_is_tip_only or _tips_below(ft)[root] <= planner.virt_tips)
+    if root_is_virtual:
+        assert p2[0][2] == K_REG and p2[0][0] == ft.n_nodes - 1   # a small-subtree root is recomputed from the codes
     elif n_internal:
         assert p2[0][2] == K_MEM and p2[0][0] == 0          # read back from its slot, no ops
     assert planner.run(i, p2, "m") == got
