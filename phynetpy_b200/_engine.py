@@ -14,10 +14,14 @@ the same way when a species network is passed: every locus whose ``_msnc`` entry
 ``None`` goes to kernel K-m in ONE ``pnb_msnc_eval`` call (``_msnc_density.py`` here).
 A host callable can still be plugged in as ``msnc_fn`` instead.
 
-Multi-GPU (one process per GPU): loci are sharded in contiguous ranges; every rank
-evaluates its shard into an M-long device vector (zeros elsewhere) and ONE NCCL
-all-reduce gives every rank all per-locus values, summed on the host in locus
-order, so the total does not depend on the number of GPUs.
+Multi-GPU (one process per GPU): loci are sharded in contiguous ranges; the pruning
+kernel writes a rank's per-locus values straight into its slice of a device vector
+(``PNB_EVAL_OUT_DEVICE``) and ONE in-place ``ncclAllGather`` on the same stream gives
+every rank all values (``ShardPlan.allgather_slices_``); one pinned D2H copy brings the
+vector to the host, which sums it in locus order, so the total does not depend on the
+number of GPUs.  When every local locus is dirty and the topologies are the ones of the
+previous such evaluation, the loci go through a resident batch (``pnb_batch_*``): only
+branch lengths travel.
 """
 from __future__ import annotations
 
@@ -29,7 +33,7 @@ import numpy as np
 from . import _lib
 from ._msnc_density import SpeciesNetwork, as_species_network, msnc_eval_packed, _check_theta
 from ._seq_likelihood import FelsensteinCalculator, _device_kind, _explicit_P_edges, _model_handle
-from .device import DeviceContext, default_context, pack_trees
+from .device import DeviceContext, ResidentBatch, default_context, pack_trees
 from .distributed import ShardPlan
 from .tree import FlatTree, flatten
 
@@ -66,6 +70,7 @@ class SeqLikelihoodEngine:
         self._msnc: List[Optional[float]] = [None] * self.n_loci
         self._pending: List[int] = []   # loci with an uncommitted device evaluation
         self._dirty: set = set(range(lo, hi))  # local loci whose _felsen entry is None
+        self._dirty_any: set = set(range(self.n_loci))   # loci whose entry is None on ANY rank (sharded engines)
         self._snap_dirty: dict = {}            # id(snapshot list) -> dirty sets at clone time
         self._msnc_dirty: set = set()          # loci whose _msnc entry is None (when not all of them are)
         self._msnc_all = True                  # every _msnc entry is None
@@ -78,6 +83,9 @@ class SeqLikelihoodEngine:
         self._net: Optional[SpeciesNetwork] = None
         self._sp_ids: List[Optional[Tuple[Any, np.ndarray]]] = [None] * self.n_loci
         self._store: Optional[dict] = None     # packed gene trees of all loci (see _packed_all)
+        self._batch: Optional[ResidentBatch] = None   # resident programs of the last all-local-loci evaluation
+        self._batch_key: Optional[tuple] = None
+        self._sh: Optional[dict] = None        # sharded mode: device vector, pinned host copy, stream (see _shard_state)
 
     # -- reference seam (src/_mcmc_seq.py:696-703, :766-772) ------------------
     def invalidate_locus(self, i: int) -> None:
@@ -86,6 +94,7 @@ class SeqLikelihoodEngine:
         lo, hi = self._shard.local_range()
         if lo <= i < hi:
             self._dirty.add(i)
+        self._dirty_any.add(i)
         self._msnc_dirty.add(i)
 
     def invalidate_network(self) -> None:
@@ -97,7 +106,8 @@ class SeqLikelihoodEngine:
         snap = (list(self._felsen), list(self._msnc))
         if len(self._snap_dirty) > 8:
             self._snap_dirty.clear()
-        self._snap_dirty[id(snap[0])] = (snap[0], frozenset(self._dirty), frozenset(self._msnc_dirty), self._msnc_all)
+        self._snap_dirty[id(snap[0])] = (snap[0], frozenset(self._dirty), frozenset(self._msnc_dirty), self._msnc_all,
+                                         frozenset(self._dirty_any))
         return snap
 
     def restore_caches(self, snapshot: Tuple[list, list]) -> None:
@@ -108,9 +118,11 @@ class SeqLikelihoodEngine:
         if known is not None and known[0] is snapshot[0]:
             self._dirty = set(known[1])
             self._msnc_dirty, self._msnc_all = set(known[2]), known[3]
+            self._dirty_any = set(known[4])
         else:  # a snapshot we did not hand out: recount
             lo, hi = self._shard.local_range()
             self._dirty = {i for i in range(lo, hi) if self._felsen[i] is None}
+            self._dirty_any = {i for i, v in enumerate(self._felsen) if v is None}
             self._recount_msnc()
         self._rollback_pending()
 
@@ -163,6 +175,7 @@ class SeqLikelihoodEngine:
         lo, hi = self._shard.local_range()
         if rescan:  # entries were set to None behind our back (a caller sharing the list): recount
             self._dirty = {i for i in range(lo, hi) if self._felsen[i] is None}
+            self._dirty_any = {i for i, v in enumerate(self._felsen) if v is None}
             self._recount_msnc()
         dirty = sorted(i for i in self._dirty if self._felsen[i] is None)
         self._dirty.clear()
@@ -170,22 +183,19 @@ class SeqLikelihoodEngine:
         self._full_next = False
         if self._shard.world_size == 1:
             if dirty:
-                vals = self.felsenstein_batch(dirty, gene_trees, flags=flags)
-                for i, v in zip(dirty, vals):
-                    self._felsen[i] = float(v)
-                self._pending = list(dirty)
+                if len(dirty) == hi - lo and len(dirty) >= self.BATCH_MIN_LOCI and _device_kind(self._model) != "explicit" \
+                        and not (flags & _lib.EVAL_FULL):
+                    vals = self._eval_all_local(dirty, gene_trees)        # resident batch: committed at once
+                else:
+                    vals = self.felsenstein_batch(dirty, gene_trees, flags=flags)
+                    self._pending = list(dirty)
+                if len(dirty) == dirty[-1] - dirty[0] + 1:
+                    self._felsen[dirty[0]:dirty[-1] + 1] = vals.tolist()     # a contiguous run: one slice assignment
+                else:
+                    for i, v in zip(dirty, vals.tolist()):
+                        self._felsen[i] = v
         else:
-            # every rank fills its dirty local loci, then one all-reduce of the M-vector
-            vec = np.zeros(self.n_loci, dtype=np.float64)
-            for i in range(self.n_loci):
-                if self._felsen[i] is not None and lo <= i < hi:
-                    vec[i] = self._felsen[i]
-            if dirty:
-                vals = self.felsenstein_batch(dirty, gene_trees, flags=flags)
-                vec[dirty] = vals
-                self._pending = list(dirty)
-            vec = self._shard.allreduce_sum(vec)
-            self._felsen = [float(v) for v in vec]
+            self._log_likelihood_sharded(dirty, gene_trees, flags)
         try:
             return self._total(gene_trees, species_net, theta)
         except TypeError:
@@ -194,6 +204,97 @@ class SeqLikelihoodEngine:
             if rescan:
                 raise
             return self.log_likelihood(gene_trees, species_net, theta, rescan=True)
+
+    BATCH_MIN_LOCI = 32   # all-local-loci evaluations of at least this many loci go through a resident batch
+
+    def _eval_all_local(self, idx: Sequence[int], gene_trees: Sequence[Any], out_device_ptr: Optional[int] = None
+                        ) -> Optional[np.ndarray]:
+        """Every local locus at once through a resident batch: the op programs of the previous such evaluation
+        are reused when the topologies are the same (one memcmp of the packed parent arrays), so only branch
+        lengths travel.  The evaluation is committed at once: the loci's partial caches are content-addressed,
+        so a proposal that is rejected afterwards costs the next evaluation of a locus a full recomputation of
+        that locus, never a wrong value."""
+        ctx = self._context()
+        flats = [flatten(gene_trees[i]) for i in idx]
+        node_off, parent, blen, tip_row = pack_trees(flats, [self._calcs[i]._row_of for i in idx])
+        mh = _model_handle(self._model, ctx)
+        key = self._batch_key
+        if self._batch is None or key is None or key[0] != self._mode or key[1].shape != parent.shape or \
+                not np.array_equal(key[1], parent) or not np.array_equal(key[2], tip_row) or not np.array_equal(key[3], node_off):
+            if self._batch is not None:
+                self._batch.close()
+            self._batch = ResidentBatch(ctx, mh, self._handles(idx), node_off, parent, tip_row, self._mode)
+            self._batch_key = (self._mode, parent, tip_row, node_off)
+        try:
+            out = self._batch.eval(mh, blen, 1.0, out_device_ptr)
+        except _lib.PhyNetB200Error:
+            # a locus was re-allocated or destroyed underneath the batch: build it again, once
+            self._batch.close()
+            self._batch = ResidentBatch(ctx, mh, self._handles(idx), node_off, parent, tip_row, self._mode)
+            out = self._batch.eval(mh, blen, 1.0, out_device_ptr)
+        self.last_stats = ctx.last_stats()
+        return out
+
+    # -- sharded evaluation: device vector + in-place all-gather ------------------------------------------
+    def _shard_state(self) -> dict:
+        if self._sh is None:
+            import torch
+            plan = self._shard
+            per = plan.slice_len
+            on_gpu = torch.cuda.is_available() and getattr(self._context(), "device", None) is not None \
+                and isinstance(self._context(), DeviceContext)
+            sh = {"per": per, "index": plan.gathered_index(), "gpu": on_gpu}
+            if on_gpu:
+                dev = torch.device("cuda", self._context().device)
+                sh["stream"] = torch.cuda.Stream(device=dev)
+                self._context().set_stream(sh["stream"].cuda_stream)   # kernels and the collective share one stream
+                sh["vec"] = torch.zeros(per * plan.world_size, dtype=torch.float64, device=dev)
+                sh["host"] = torch.zeros(per * plan.world_size, dtype=torch.float64).pin_memory()
+            else:   # CPU collectives (gloo): the host-side logic of the same protocol
+                sh["vec"] = torch.zeros(per * plan.world_size, dtype=torch.float64)
+                sh["host"] = sh["vec"]
+            self._sh = sh
+        return self._sh
+
+    def _log_likelihood_sharded(self, dirty: List[int], gene_trees: Sequence[Any], flags: int) -> None:
+        """This rank's dirty loci -> its slice of the device vector -> one in-place all-gather -> one D2H copy.
+        Every rank runs the same chain, so every rank knows which loci are dirty anywhere (``_dirty_any``)."""
+        import torch
+        plan = self._shard
+        lo, hi = plan.local_range()
+        if not self._dirty_any and not dirty:
+            return
+        sh = self._shard_state()
+        per = sh["per"]
+        base = plan.rank * per
+        if sh["gpu"]:
+            with torch.cuda.stream(sh["stream"]):
+                if dirty:
+                    if len(dirty) == hi - lo and _device_kind(self._model) != "explicit" and not (flags & _lib.EVAL_FULL):
+                        self._eval_all_local(dirty, gene_trees, out_device_ptr=sh["vec"].data_ptr() + 8 * base)
+                    else:
+                        vals = self.felsenstein_batch(dirty, gene_trees, flags=flags)
+                        self._pending = list(dirty)
+                        pos = torch.from_numpy(base + np.asarray(dirty, dtype=np.int64) - lo).to(sh["vec"].device)
+                        sh["vec"].index_copy_(0, pos, torch.from_numpy(np.ascontiguousarray(vals)).to(sh["vec"].device))
+                plan.allgather_slices_(sh["vec"])
+                sh["host"].copy_(sh["vec"], non_blocking=True)
+            sh["stream"].synchronize()
+        else:
+            if dirty:
+                vals = self.felsenstein_batch(dirty, gene_trees, flags=flags)
+                self._pending = list(dirty)
+                sh["vec"].numpy()[base + np.asarray(dirty, dtype=np.int64) - lo] = vals
+            plan.allgather_slices_(sh["vec"])
+        # only the entries that were dirty somewhere are taken from the gathered vector (a slot of the device vector
+        # may still hold the value of a proposal that was rejected since)
+        if len(self._dirty_any) == self.n_loci:
+            self._felsen[:] = sh["host"].numpy()[sh["index"]].tolist()     # one C-level conversion, locus order
+        else:
+            hv, ix = sh["host"].numpy(), sh["index"]
+            for i in self._dirty_any:
+                self._felsen[i] = float(hv[ix[i]])
+        self._dirty_any.clear()
 
     def _total(self, gene_trees: Sequence[Any], species_net: Any, theta: float) -> float:
         """The sum over loci once every ``_felsen`` entry is filled; fills the ``None`` entries of ``_msnc``."""

@@ -323,16 +323,21 @@ extern "C" int pnb_batch_create(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb
     }
     memset(b->h_out.p, 0, static_cast<size_t>(M) * sizeof(double));
 
-    // ---- chunks for the pipelined host-lengths path: ~equal node counts, at most 8 -----------------
-    // (thresholds follow the context's chunking knob, PNB_CHUNK_MIN_JOBS: 1024 -> >= 256 jobs and >= 16384 nodes per chunk)
-    const int64_t cj = std::max(ctx->chunk_min_jobs / 4, 1), cn = static_cast<int64_t>(ctx->chunk_min_jobs) * 16;
-    const int64_t n_chunks = std::max<int64_t>(1, std::min<int64_t>(8, std::min<int64_t>(M / cj, b->total_nodes / cn)));
+    // ---- chunks for the pipelined host-lengths path ------------------------------------------------------
+    // The upload of chunk c+1 hides behind the pruning of chunk c, so only chunk 0's upload is exposed: chunks grow
+    // geometrically (1/16, 3/16, 12/16 of the nodes; 1/4, 3/4 for medium batches) -- few launches (every launch has
+    // a partially filled last wave), a small exposed first copy.  Thresholds follow PNB_CHUNK_MIN_JOBS (1024 ->
+    // two chunks from 512 jobs / 32768 nodes, three from 4096 jobs / 262144 nodes).
+    const int64_t cj = std::max(ctx->chunk_min_jobs / 2, 1), cn = static_cast<int64_t>(ctx->chunk_min_jobs) * 32;
+    std::vector<double> cuts;
+    if (M >= 8 * cj && b->total_nodes >= 8 * cn) cuts = {1.0 / 16, 4.0 / 16};
+    else if (M >= cj && b->total_nodes >= cn) cuts = {1.0 / 4};
     b->ck_job.assign(1, 0);
-    for (int64_t c = 1; c < n_chunks; ++c) {
-        const int64_t target = b->total_nodes * c / n_chunks;
+    for (double f : cuts) {
+        const int64_t target = static_cast<int64_t>(b->total_nodes * f);
         int64_t j = std::lower_bound(b->node_off.begin(), b->node_off.end(), target) - b->node_off.begin();
-        j = std::min<int64_t>(std::max<int64_t>(j, b->ck_job.back() + 1), M - (n_chunks - c));
-        b->ck_job.push_back(j);
+        j = std::min<int64_t>(std::max<int64_t>(j, b->ck_job.back() + 1), M - 1);
+        if (j > b->ck_job.back()) b->ck_job.push_back(j);
     }
     b->ck_job.push_back(M);
     for (int64_t j : b->ck_job) {
