@@ -331,18 +331,52 @@ def measure(args, wl_name, W, plan, stream, rank, world, clock_sampler=None):
     M = plan["M"]
     lo, per = plan["lo"], plan["per"]
     vec_len = per * world
-    out_vec = torch.zeros(vec_len, dtype=torch.float64, device="cuda")       # every rank ends with all per-locus values
+    # Every rank ends with all per-locus values.  Preferred: the vector lives in symmetric memory (every peer's copy is
+    # mapped here) and the pruning kernel itself stores each finished locus into every peer's vector -- the collective is
+    # fused into the kernel's epilogue, followed by one device-side barrier.  Otherwise: in-place ncclAllGather.
+    sym = None
+    if world > 1 and not args.skip_collective and args.collective == "p2p":
+        from phynetpy_b200.distributed import ShardPlan
+        sp = ShardPlan(M, rank, world, [(r * per, min(M, (r + 1) * per)) for r in range(world)])
+        sym = sp.symmetric_vector()
+    if sym is not None:
+        # two copies used alternately by consecutive steps: a fast rank's next kernel never stores into a vector that a slower
+        # rank is still copying to its host (it cannot get two steps ahead: it waits in the barrier in between)
+        sym_t, sym_hdl = sym
+        vecs = [sym_t[:vec_len], sym_t[vec_len:]]
+        peer_sets = [[sym_hdl.buffer_ptrs[r] + 8 * (c * vec_len + lo) for r in range(world) if r != rank] for c in range(2)]
+    else:
+        vecs, sym_hdl, peer_sets = [torch.zeros(vec_len, dtype=torch.float64, device="cuda")] * 2, None, [[], []]
     out_host = torch.zeros(vec_len, dtype=torch.float64).pin_memory()
-    out_local_ptr = out_vec.data_ptr() + 8 * lo
+    cur = {"vec": vecs[0]}
     steps = args.steps
     warm = max(args.warmup, 3)
     step_no = [0]
     n_sets = len(W.d_blens)
+    mode = ["p2p" if sym is not None else "nccl"]
     inplace_ok = [True]
 
+    def set_mode(m):
+        mode[0] = m
+        if m != "p2p":
+            W.batch.set_peer_outputs([])
+
+    def begin_step():
+        """-> (index of the branch-length set, this rank's slice of the output vector of this step)"""
+        k = step_no[0]
+        step_no[0] += 1
+        c = k % 2 if mode[0] == "p2p" else 0
+        cur["vec"] = vecs[c]
+        if mode[0] == "p2p":
+            W.batch.set_peer_outputs(peer_sets[c])
+        return k % n_sets, vecs[c].data_ptr() + 8 * lo
+
     def collective():
+        out_vec = cur["vec"]
         if world > 1 and not args.skip_collective:
-            if inplace_ok[0]:
+            if mode[0] == "p2p":
+                sym_hdl.barrier()       # every peer's stores (issued by its kernel, which has completed) have landed
+            elif inplace_ok[0]:
                 # in place: this rank's slice of the M-vector IS the send buffer (equal slices by construction)
                 dist.all_gather_into_tensor(out_vec, out_vec[lo:lo + per])
             else:
@@ -350,20 +384,18 @@ def measure(args, wl_name, W, plan, stream, rank, world, clock_sampler=None):
 
     def step_device():
         """inputs resident in HBM (lengths included); logL stays on the device; collective when sharded"""
-        k = step_no[0] % n_sets
-        step_no[0] += 1
+        k, out_local_ptr = begin_step()
         with torch.cuda.stream(stream):
             W.batch.eval(W.mh, W.d_blens[k].data_ptr(), out_device_ptr=out_local_ptr)
             collective()
 
     def step_e2e():
         """the call a user makes: host branch lengths (pinned) in, host log-likelihoods of ALL loci out"""
-        k = step_no[0] % n_sets
-        step_no[0] += 1
+        k, out_local_ptr = begin_step()
         with torch.cuda.stream(stream):
             W.batch.eval(W.mh, W.h_blens[k].numpy(), out_device_ptr=out_local_ptr)
             collective()
-            out_host.copy_(out_vec, non_blocking=True)
+            out_host.copy_(cur["vec"], non_blocking=True)
         stream.synchronize()
         return out_host.numpy()
 
@@ -372,38 +404,72 @@ def measure(args, wl_name, W, plan, stream, rank, world, clock_sampler=None):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up (also: does the in-place all-gather give what the out-of-place one gives?) ----------
+    def timed_device_loop():
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev1 = torch.cuda.Event(enable_timing=True)
+        barrier()
+        step_no[0] = 0
+        ev0.record(stream)
+        for _ in range(steps):
+            step_device()
+        ev1.record(stream)
+        barrier()
+        return ev0.elapsed_time(ev1)
+
+    # ---- warm-up; the three ways of combining the ranks' values must agree bit for bit ----------------------
+    set_mode("nccl")
+    inplace_ok[0] = False
     for _ in range(warm):
         step_device()
     barrier()
+    nccl_ms = p2p_ms = None
     if world > 1 and not args.skip_collective:
-        a = out_vec.clone()
-        inplace_ok[0] = False
+        ref_vec = cur["vec"].clone()
+        inplace_ok[0] = True
         step_no[0] -= 1
         step_device()
         barrier()
-        inplace_ok[0] = bool(torch.equal(a, out_vec))
-        t = torch.tensor([1.0 if inplace_ok[0] else 0.0], device="cuda")
+        flags_ok = [bool(torch.equal(ref_vec, cur["vec"])), True]
+        if sym is not None:
+            set_mode("p2p")
+            vecs[0].zero_(); vecs[1].zero_()
+            barrier()
+            step_no[0] -= 1
+            step_device()
+            barrier()
+            flags_ok[1] = bool(torch.equal(ref_vec, cur["vec"]))
+        t = torch.tensor([1.0 if f else 0.0 for f in flags_ok], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
-        inplace_ok[0] = bool(t.item() > 0.5)
+        inplace_ok[0] = bool(t[0].item() > 0.5)
+        if sym is not None and t[1].item() < 0.5:
+            raise RuntimeError("fused peer stores disagree with the NCCL all-gather")
+        if sym is not None:
+            # both variants of the same step timed the same way; the faster one (agreed over ranks) runs the timed region
+            set_mode("nccl")
+            for _ in range(warm):
+                step_device()
+            nccl_ms = timed_device_loop() / steps
+            set_mode("p2p")
+            for _ in range(warm):
+                step_device()
+            p2p_ms = timed_device_loop() / steps
+            tt = torch.tensor([nccl_ms, p2p_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            nccl_ms, p2p_ms = float(tt[0]), float(tt[1])
+            if args.collective_auto and nccl_ms < p2p_ms:
+                set_mode("nccl")
+            for _ in range(warm):
+                step_device()
+            barrier()
     st = ctx.last_stats()
     launches_per_step = st["launches"]
 
     # ---- timed: device-resident -----------------------------------------------------------------------
     if clock_sampler is not None:
         clock_sampler.start()
-    ev0 = torch.cuda.Event(enable_timing=True)
-    ev1 = torch.cuda.Event(enable_timing=True)
     ctx.set_profiling(False)
-    barrier()
-    step_no[0] = 0
-    ev0.record(stream)
-    for _ in range(steps):
-        step_device()
-    ev1.record(stream)
-    barrier()
-    elapsed_ms = ev0.elapsed_time(ev1)
-    logL_device = out_vec.cpu().numpy().copy()
+    elapsed_ms = timed_device_loop()
+    logL_device = cur["vec"].cpu().numpy().copy()
 
     # ---- per-kernel durations: the same steps with CUDA events around each launch (library-side, same stream) ----
     ctx.set_profiling(True)
@@ -442,6 +508,7 @@ def measure(args, wl_name, W, plan, stream, rank, world, clock_sampler=None):
         "launches_per_step": int(launches_per_step), "h2d": int(st_e2e["h2d_bytes"]),
         "d2h": int(vec_len * 8), "logL_device": logL_device[:M], "logL_e2e": logL_e2e[:M], "clocks": clocks,
         "inplace_allgather": bool(inplace_ok[0]) if world > 1 else None,
+        "collective_mode": None if world == 1 else mode[0], "nccl_ms_per_step": nccl_ms, "p2p_ms_per_step": p2p_ms,
     }
 
 
@@ -511,6 +578,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="N=1: skip the cfg2 roofline block and the chain block")
     ap.add_argument("--skip-collective", action="store_true", help="diagnostic only: time the sharded step without the collective")
+    ap.add_argument("--no-collective-auto", dest="collective_auto", action="store_false",
+                    help="keep the fused peer stores even when the NCCL all-gather timed faster in the trial")
+    ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: fused peer stores from the kernel (falls back to NCCL when symmetric memory is unavailable) or ncclAllGather")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -609,11 +680,16 @@ def main():
                 "model": "GTR pi=(.1,.2,.3,.4) rates=(1,2.5,.7,1.3,3.1,.9)",
                 "step": "full logL evaluation of a fresh proposal (same topologies, new branch lengths every step): P(t) of every "
                         "branch + every internal node recomputed + root reduction"
-                        + (" + in-place NCCL all-gather of the per-locus vector (every rank ends with all %d values)" % M if world > 1 else "")
+                        + (" + every rank ends with all %d per-locus values (see collective)" % M if world > 1 else "")
                         + "; op programs resident in HBM (pnb_batch_*), compiled once per topology",
                 "parallelism": "loci sharded over %d GPU(s) in equal contiguous slices, one process per GPU" % world,
-                "collective": None if world == 1 else ("ncclAllGather in place on the kernel's stream" if m["inplace_allgather"]
-                                                       else "ncclAllGather (out of place)"),
+                "collective": None if world == 1 else (
+                    "fused into the pruning kernel: the block that completes a locus stores its logL into every peer's vector "
+                    "(symmetric memory, NVLink peer stores), then one device-side barrier; checked bit-equal to the NCCL all-gather "
+                    "in this run" if m["collective_mode"] == "p2p" else
+                    ("ncclAllGather in place on the kernel's stream" if m["inplace_allgather"] else "ncclAllGather (out of place)")),
+                "collective_trials_ms_per_step": {"nccl_all_gather_in_place": m["nccl_ms_per_step"],
+                                                  "fused_peer_stores": m["p2p_ms_per_step"]},
                 "l2": "working set per step (%.2f GB of partials written per GPU) exceeds the 126 MB L2; no flush needed"
                       % (W.batch.traffic["partials_written"] / 1e9),
                 "scale": args.scale, "diagnostic_skip_collective": bool(args.skip_collective),
@@ -624,7 +700,7 @@ def main():
                 "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"],
                 "what": "pnb_batch_eval through the C ABI with HOST buffers: branch lengths of every tree in pinned host memory -> "
                         "chunked H2D overlapped with pruning -> P(t) + pruning kernels -> "
-                        + ("all-gather -> " if world > 1 else "") + "per-locus logL of ALL loci copied D2H into pinned host memory "
+                        + ("peer stores / all-gather -> " if world > 1 else "") + "per-locus logL of ALL loci copied D2H into pinned host memory "
                         "(per-rank bytes); alignments resident since construction",
             },
             "gpu_launches": int(m["launches_per_step"] * steps),

@@ -213,6 +213,13 @@ PNB_API int pnb_batch_traffic(const pnb_batch *b, int64_t bytes[4]);
 PNB_API int pnb_batch_blen_host(pnb_batch *b, double **pinned_out);
 PNB_API int pnb_batch_eval(pnb_batch *b, const pnb_model *m, const double *blen, double site_rate,
                            uint32_t flags, double *logL_out);
+/* Fused collective for loci sharded over the GPUs of one NVSwitch domain (replaces the all-reduce / all-gather
+ * that would follow the kernel): with PNB_EVAL_OUT_DEVICE the block that completes a job stores its logL into
+ * logL_out[j] AND into peer_out[r][j] of every peer -- peer_out[r] is a device pointer, valid in THIS process, to
+ * the same slot of peer r's vector (CUDA IPC / symmetric memory; the caller maps it).  8 bytes per job and peer
+ * over NVLink, no collective kernel; the caller orders consumers with one cross-GPU barrier.  n_peers = 0 turns
+ * it off.  At most 7 peers.                                                                              */
+PNB_API int pnb_batch_set_peer_outputs(pnb_batch *b, int32_t n_peers, double *const *peer_out);
 
 /* ---- K-m: timed MSNC density log P(g | Psi) ---------------------- */
 /* The other factor of the MCMC_SEQ likelihood, sum_i [log P(S_i|g_i) + log P(g_i|Psi)]

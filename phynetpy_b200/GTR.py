@@ -44,10 +44,9 @@ class SubstitutionModelError(Exception):
 
 
 def _as_float_list(values: Any) -> List[float]:
-    try:
-        return [float(v) for v in values]
-    except (TypeError, ValueError) as exc:
-        raise SubstitutionModelError("Expected a sequence of numbers, got %r" % (values,)) from exc
+    """Any array-like of numbers as a FLAT list of floats: a column vector such as ``np.ones((6, 1))`` is
+    flattened, as in the reference (``src/GTR.py:154-168``), instead of iterating as length-1 arrays."""
+    return np.asarray(values, dtype=np.double).reshape(-1).tolist()
 
 
 def _positive(name: str, value: Any) -> float:

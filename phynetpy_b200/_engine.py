@@ -207,8 +207,8 @@ class SeqLikelihoodEngine:
 
     BATCH_MIN_LOCI = 32   # all-local-loci evaluations of at least this many loci go through a resident batch
 
-    def _eval_all_local(self, idx: Sequence[int], gene_trees: Sequence[Any], out_device_ptr: Optional[int] = None
-                        ) -> Optional[np.ndarray]:
+    def _eval_all_local(self, idx: Sequence[int], gene_trees: Sequence[Any], out_device_ptr: Optional[int] = None,
+                        peer_ptrs: Sequence[int] = ()) -> Optional[np.ndarray]:
         """Every local locus at once through a resident batch: the op programs of the previous such evaluation
         are reused when the topologies are the same (one memcmp of the packed parent arrays), so only branch
         lengths travel.  The evaluation is committed at once: the loci's partial caches are content-addressed,
@@ -226,11 +226,13 @@ class SeqLikelihoodEngine:
             self._batch = ResidentBatch(ctx, mh, self._handles(idx), node_off, parent, tip_row, self._mode)
             self._batch_key = (self._mode, parent, tip_row, node_off)
         try:
+            self._batch.set_peer_outputs(list(peer_ptrs))
             out = self._batch.eval(mh, blen, 1.0, out_device_ptr)
         except _lib.PhyNetB200Error:
             # a locus was re-allocated or destroyed underneath the batch: build it again, once
             self._batch.close()
             self._batch = ResidentBatch(ctx, mh, self._handles(idx), node_off, parent, tip_row, self._mode)
+            self._batch.set_peer_outputs(list(peer_ptrs))
             out = self._batch.eval(mh, blen, 1.0, out_device_ptr)
         self.last_stats = ctx.last_stats()
         return out
@@ -248,11 +250,24 @@ class SeqLikelihoodEngine:
                 dev = torch.device("cuda", self._context().device)
                 sh["stream"] = torch.cuda.Stream(device=dev)
                 self._context().set_stream(sh["stream"].cuda_stream)   # kernels and the collective share one stream
-                sh["vec"] = torch.zeros(per * plan.world_size, dtype=torch.float64, device=dev)
+                # preferred: the vector in symmetric memory, so that the kernel of a full evaluation stores every locus'
+                # value straight into all peers' copies (fused collective); plain memory + NCCL all-gather otherwise
+                with torch.cuda.device(dev):
+                    sym = plan.symmetric_vector()
+                n = per * plan.world_size
+                if sym is not None:
+                    # two copies of the vector, used alternately by consecutive evaluations (ShardPlan.symmetric_vector)
+                    sh["vecs"], sh["sym"] = [sym[0][:n], sym[0][n:]], sym[1]
+                    sh["peers"] = [[sym[1].buffer_ptrs[r] + 8 * (c * n + plan.rank * per) for r in range(plan.world_size)
+                                    if r != plan.rank] for c in range(2)]
+                else:
+                    sh["vecs"], sh["sym"], sh["peers"] = [torch.zeros(n, dtype=torch.float64, device=dev)] * 2, None, [[], []]
+                sh["turn"] = 0
                 sh["host"] = torch.zeros(per * plan.world_size, dtype=torch.float64).pin_memory()
             else:   # CPU collectives (gloo): the host-side logic of the same protocol
-                sh["vec"] = torch.zeros(per * plan.world_size, dtype=torch.float64)
-                sh["host"] = sh["vec"]
+                sh["vecs"] = [torch.zeros(per * plan.world_size, dtype=torch.float64)] * 2
+                sh["host"] = sh["vecs"][0]
+                sh["turn"] = 0
             self._sh = sh
         return self._sh
 
@@ -267,25 +282,35 @@ class SeqLikelihoodEngine:
         sh = self._shard_state()
         per = sh["per"]
         base = plan.rank * per
+        turn = sh["turn"] = sh["turn"] ^ 1
+        vec = sh["vecs"][turn]
         if sh["gpu"]:
             with torch.cuda.stream(sh["stream"]):
+                fused = False
                 if dirty:
                     if len(dirty) == hi - lo and _device_kind(self._model) != "explicit" and not (flags & _lib.EVAL_FULL):
-                        self._eval_all_local(dirty, gene_trees, out_device_ptr=sh["vec"].data_ptr() + 8 * base)
+                        # every rank takes this branch together (every rank's shard is dirty as a whole): with symmetric
+                        # memory the kernel's peer stores + one device-side barrier replace the all-gather
+                        fused = sh["sym"] is not None and len(self._dirty_any) == self.n_loci
+                        self._eval_all_local(dirty, gene_trees, out_device_ptr=vec.data_ptr() + 8 * base,
+                                             peer_ptrs=sh["peers"][turn] if fused else [])
                     else:
                         vals = self.felsenstein_batch(dirty, gene_trees, flags=flags)
                         self._pending = list(dirty)
-                        pos = torch.from_numpy(base + np.asarray(dirty, dtype=np.int64) - lo).to(sh["vec"].device)
-                        sh["vec"].index_copy_(0, pos, torch.from_numpy(np.ascontiguousarray(vals)).to(sh["vec"].device))
-                plan.allgather_slices_(sh["vec"])
-                sh["host"].copy_(sh["vec"], non_blocking=True)
+                        pos = torch.from_numpy(base + np.asarray(dirty, dtype=np.int64) - lo).to(vec.device)
+                        vec.index_copy_(0, pos, torch.from_numpy(np.ascontiguousarray(vals)).to(vec.device))
+                if fused:
+                    sh["sym"].barrier()
+                else:
+                    plan.allgather_slices_(vec)
+                sh["host"].copy_(vec, non_blocking=True)
             sh["stream"].synchronize()
         else:
             if dirty:
                 vals = self.felsenstein_batch(dirty, gene_trees, flags=flags)
                 self._pending = list(dirty)
-                sh["vec"].numpy()[base + np.asarray(dirty, dtype=np.int64) - lo] = vals
-            plan.allgather_slices_(sh["vec"])
+                vec.numpy()[base + np.asarray(dirty, dtype=np.int64) - lo] = vals
+            plan.allgather_slices_(vec)
         # only the entries that were dirty somewhere are taken from the gathered vector (a slot of the device vector
         # may still hold the value of a proposal that was rejected since)
         if len(self._dirty_any) == self.n_loci:
@@ -385,10 +410,16 @@ class SeqLikelihoodEngine:
     # -- MSNC density on the device ----------------------------------------------------------------
     def _network(self, species_net: Any) -> SpeciesNetwork:
         if species_net is not self._net_obj or self._net is None:
-            self._net = as_species_network(species_net)
+            new = as_species_network(species_net)
+            # species ids are the ranks of the leaf labels: a height, gamma or topology move that keeps the species
+            # (every move of the sampler does) keeps the per-locus id arrays and the packed gene-tree store
+            if self._net is None or new.species != self._net.species:
+                self._sp_ids = [None] * self.n_loci
+                self._store = None
+            elif self._store is not None:
+                self._store["net"] = new
+            self._net = new
             self._net_obj = species_net
-            self._sp_ids = [None] * self.n_loci
-            self._store = None
         return self._net
 
     def _species_ids(self, i: int, ft: FlatTree, net: SpeciesNetwork) -> np.ndarray:

@@ -196,6 +196,36 @@ class _ModelHandle:
             pass
 
 
+# handles of model objects that cannot carry an attribute (``__slots__`` classes): id(model) -> (weakref | model, cache)
+_slot_model_handles: Dict[int, Any] = {}
+
+
+def _handle_cache(model: Any) -> Dict[Any, "_ModelHandle"]:
+    """Where the device handles of a model object live: on the object when it has a ``__dict__`` (they go away
+    with it and are dropped by ``__getstate__``), else in a module-level table keyed by identity that holds the
+    object weakly when it can (the entry is dropped when the model dies) and strongly when it cannot."""
+    d = getattr(model, "__dict__", None)
+    if d is not None:
+        cache = d.get("_pnb_handles")
+        if cache is None:
+            cache = d["_pnb_handles"] = {}
+        return cache
+    import weakref
+    key = id(model)
+    hit = _slot_model_handles.get(key)
+    if hit is not None:
+        owner = hit[0]() if isinstance(hit[0], weakref.ref) else hit[0]
+        if owner is model:
+            return hit[1]
+    cache: Dict[Any, "_ModelHandle"] = {}
+    try:
+        ref: Any = weakref.ref(model, lambda _r, k=key: _slot_model_handles.pop(k, None))
+    except TypeError:
+        ref = model
+    _slot_model_handles[key] = (ref, cache)
+    return cache
+
+
 def _model_handle(model: Any, ctx: DeviceContext) -> C.c_void_p:
     """``pnb_model*`` for (model, context); rebuilt when the parameters change."""
     kind = _device_kind(model)
@@ -205,15 +235,14 @@ def _model_handle(model: Any, ctx: DeviceContext) -> C.c_void_p:
         U = np.ascontiguousarray(model._U, dtype=np.float64)
         Ui = np.ascontiguousarray(model._Uinv, dtype=np.float64)
         fp = (kind, pi.tobytes(), ev.tobytes(), U.tobytes(), Ui.tobytes())
+    elif kind == "explicit":
+        # user code computes P(t): the only way to notice that its parameters changed is to ask it.  Two probe
+        # matrices are part of the identity, so cached partials of the old parameters are never reused.
+        probe = b"".join(np.ascontiguousarray(model.p_matrix(t), dtype=np.float64).tobytes() for t in (0.0625, 1.0))
+        fp = (kind, pi.tobytes(), probe)
     else:
         fp = (kind, pi.tobytes())
-    cache = model.__dict__.get("_pnb_handles") if hasattr(model, "__dict__") else None
-    if cache is None:
-        cache = {}
-        try:
-            model.__dict__["_pnb_handles"] = cache
-        except Exception:
-            pass
+    cache = _handle_cache(model)
     key = (os.getpid(), id(ctx))
     mh = cache.get(key)
     if mh is not None and mh.fingerprint == fp:

@@ -34,6 +34,8 @@ struct pnb_batch {
     int ops_cap = 1, rows_cap = 1, stk_cap = 0;
     size_t dyn_smem = 0;
     int64_t traffic[4] = {0, 0, 0, 0};  // bytes per evaluation, counted from the programs (pnb_batch_traffic)
+    int n_peers = 0;                    // fused collective: peers' output vectors (pnb_batch_set_peer_outputs)
+    double* peer_out[MAX_PEERS] = {nullptr};
     // chunks of jobs for the pipelined host-lengths path: [c] = first job / node / op / tile of chunk c
     std::vector<int64_t> ck_job, ck_node, ck_op, ck_tile;
     // state of the last evaluation (what locus_sync materialises)
@@ -384,6 +386,18 @@ extern "C" int pnb_batch_traffic(const pnb_batch* b, int64_t bytes[4]) {
     return PNB_OK;
 }
 
+extern "C" int pnb_batch_set_peer_outputs(pnb_batch* b, int32_t n_peers, double* const* peer_out) {
+    PNB_REQUIRE(b != nullptr, PNB_ERR_INVALID, "pnb_batch_set_peer_outputs: NULL batch");
+    PNB_REQUIRE(n_peers >= 0 && n_peers <= MAX_PEERS, PNB_ERR_INVALID, "pnb_batch_set_peer_outputs: %d peers (at most %d)",
+                n_peers, MAX_PEERS);
+    PNB_REQUIRE(n_peers == 0 || peer_out, PNB_ERR_INVALID, "pnb_batch_set_peer_outputs: NULL array");
+    for (int r = 0; r < n_peers; ++r)
+        PNB_REQUIRE(peer_out[r] != nullptr, PNB_ERR_INVALID, "pnb_batch_set_peer_outputs: peer %d is NULL", r);
+    for (int r = 0; r < MAX_PEERS; ++r) b->peer_out[r] = r < n_peers ? peer_out[r] : nullptr;
+    b->n_peers = n_peers;
+    return PNB_OK;
+}
+
 extern "C" int pnb_batch_blen_host(pnb_batch* b, double** pinned_out) {
     PNB_REQUIRE(b && pinned_out, PNB_ERR_INVALID, "pnb_batch_blen_host: NULL argument");
     *pinned_out = static_cast<double*>(b->h_blen.p);
@@ -438,6 +452,8 @@ extern "C" int pnb_batch_eval(pnb_batch* b, const pnb_model* m, const double* bl
     L.rows_cap = b->rows_cap;
     L.stk_cap = b->stk_cap;
     L.tile_base = 0;
+    L.n_peers = out_dev ? b->n_peers : 0;
+    for (int r = 0; r < MAX_PEERS; ++r) L.peer_out[r] = b->peer_out[r];
     int64_t h2d = 0, d2h = 0, launches = 0;
     const double* d_blen = static_cast<const double*>(b->d_blen.p);
     int rc;

@@ -28,6 +28,7 @@ namespace pnb {
 #endif
 constexpr int TPB = PNB_TPB;        // threads per block
 constexpr int PPT = PNB_PPT;        // site patterns per thread (independent dependency chains)
+constexpr int MAX_PEERS = 7;         // other GPUs of one NVSwitch domain
 constexpr int SEG_MAX_OPS = 192;     // a tree program longer than this is streamed through shared memory in segments
 constexpr int TILE_PATTERNS = TPB * PPT;  // patterns per tile; FIXED so the summation order of a locus
                                           // never depends on batch composition or GPU count
@@ -95,6 +96,10 @@ struct PruneLaunch {
     int32_t rows_cap;          // smem capacity in staged code rows
     int32_t stk_cap;           // smem stash entries
     int32_t tile_base;         // first tile of this launch (a batch may be launched in chunks)
+    // fused collective (multi-GPU resident batches): the block that completes a job also stores its logL into the
+    // same slot of every peer's vector -- peer-mapped device pointers (NVLink / NVSwitch), 8 bytes per peer and job
+    int32_t n_peers;
+    double* peer_out[MAX_PEERS];
 };
 
 #ifdef PNB_DEVICE_KERNELS  // kernel bodies: compiled into exactly one translation unit (pnb_eval.cu)
@@ -643,6 +648,7 @@ pnb_prune_kernel_t(const __grid_constant__ PruneLaunch L, const __grid_constant_
         const double total = block_sum(s, red);
         if (tid == 0) {
             L.out[jd.out_index] = total;
+            for (int r = 0; r < L.n_peers; ++r) L.peer_out[r][jd.out_index] = total;   // stores over NVLink into the peers' vectors
             L.job_done[job] = 0u;
         }
     }

@@ -503,6 +503,7 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
             PNB_CUDA_TRY(cudaStreamWaitEvent(st, ctx->chunk_ready[c], 0));
         }
         PruneLaunch L;
+        L.n_peers = 0;
         L.jobs = reinterpret_cast<const JobDesc*>(prog_base + off_jobs);
         L.tile_job = reinterpret_cast<const int32_t*>(prog_base + off_tiles);
         L.Pm = static_cast<const double*>(ctx->d_P.p);

@@ -165,6 +165,12 @@ class ResidentBatch:
         _lib.check(self._lib.pnb_batch_eval(self._h, model_handle, blen_ptr, float(site_rate), flags, out_ptr))
         return out
 
+    def set_peer_outputs(self, peer_ptrs: Sequence[int]) -> None:
+        """Fused collective: device addresses (valid in this process) of the same output slot in every PEER's
+        vector; evaluations with ``out_device_ptr`` then store each job's logL there too.  ``[]`` turns it off."""
+        arr = (C.c_void_p * max(len(peer_ptrs), 1))(*[C.c_void_p(int(p)) for p in peer_ptrs])
+        _lib.check(self._lib.pnb_batch_set_peer_outputs(self._h, len(peer_ptrs), arr))
+
     def close(self) -> None:
         if self._h is not None and self._pid == os.getpid() and self._ctx._h is not None:
             self._pinned = None

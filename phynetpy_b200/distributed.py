@@ -102,6 +102,42 @@ class ShardPlan:
             idx[lo:hi] = r * per + np.arange(hi - lo)
         return idx
 
+    # -- peer-mapped vector: the pruning kernel stores results into every peer's copy (fused collective) -------
+    def symmetric_vector(self, copies: int = 2):
+        """``copies`` x (``world_size * slice_len``) float64 CUDA values allocated in symmetric memory, with every peer's copy
+        mapped into this process (``torch.distributed._symmetric_memory``: CUDA VMM handles exchanged through the
+        process group's store).  Returns ``(tensor, handle)`` or ``None`` when the platform cannot do it (then the
+        NCCL all-gather is used).  ``handle.buffer_ptrs[r]`` is rank r's vector, ``handle.barrier()`` a device-side
+        barrier over NVLink signal pads on the current stream.  Two copies, used alternately by consecutive
+        evaluations, keep a fast rank's next kernel from storing into a vector a slower rank is still reading
+        (a rank cannot run two evaluations ahead: it waits in the barrier of the one in between)."""
+        if self.world_size == 1 or self.world_size > 8:
+            return None
+        try:
+            import torch
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm_mem
+            if dist.get_backend(self.group) != "nccl":
+                return None
+            t = symm_mem.empty(copies * self.slice_len * self.world_size, dtype=torch.float64,
+                               device=torch.device("cuda", torch.cuda.current_device()))
+            t.zero_()
+            hdl = symm_mem.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
+            ok = torch.tensor([1.0 if len(hdl.buffer_ptrs) == self.world_size else 0.0], device=t.device)
+        except Exception:
+            try:
+                import torch
+                import torch.distributed as dist
+                ok = torch.tensor([0.0], device=torch.device("cuda", torch.cuda.current_device()))
+                t = hdl = None
+            except Exception:
+                return None
+        import torch.distributed as dist
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)     # all ranks or none
+        if ok.item() < 0.5:
+            return None
+        return t, hdl
+
     def allgather_slices_(self, vec) -> None:
         """In-place all-gather of equal slices: every rank has written its own slice of ``vec``
         (``world_size * slice_len`` doubles; a CUDA tensor the pruning kernel has just filled, on the

@@ -226,7 +226,7 @@ class FlatMCMCSeq:
         counts = {n: [0, 0] for n in names}
         samples: List[FlatSample] = []
         accepted = 0
-        for it in range(1, num_iter + 1):
+        for it in range(num_iter):   # 0-based, as the reference (src/_mcmc_seq.py:3478, :3637)
             name = names[int(rng.choice(len(names), p=weights))]
             counts[name][0] += 1
             snap = eng.clone_caches()
@@ -247,7 +247,7 @@ class FlatMCMCSeq:
                         best = (cur, self.net, self.theta, list(self.trees))
                 else:
                     eng.restore_caches(snap)
-            if it > burn_in and sample_freq > 0 and (it - burn_in) % sample_freq == 0:
+            if it >= burn_in and sample_freq > 0 and (it - burn_in) % sample_freq == 0:   # (:3501, :3668)
                 samples.append(self._sample(it, cur))
         return FlatResult(best[1], best[0], best[2], best[3], samples, accepted / max(num_iter, 1), num_iter,
                           time.perf_counter() - t0, counts)
@@ -295,7 +295,7 @@ class FlatMCMCSeq:
         samples: List[FlatSample] = []
         counts = {n: [0, 0] for n in names}
         accepted = swaps = swaps_ok = 0
-        for it in range(1, num_iter + 1):
+        for it in range(num_iter):   # 0-based, as the reference (src/_mcmc_seq.py:3478, :3637)
             props: List[Any] = []
             snaps = []
             for c, ch in enumerate(chains):
@@ -341,7 +341,7 @@ class FlatMCMCSeq:
                     chains[i], chains[j] = chains[j], chains[i]
                     curs[i], curs[j] = curs[j], curs[i]
                     swaps_ok += 1
-            if it > burn_in and sample_freq > 0 and (it - burn_in) % sample_freq == 0:
+            if it >= burn_in and sample_freq > 0 and (it - burn_in) % sample_freq == 0:   # (:3501, :3668)
                 samples.append(chains[cold]._sample(it, curs[cold]))
         # leave this object in the cold chain's final state
         final = chains[cold]
