@@ -105,23 +105,31 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def make_locus_data(M, n, L, seed, lo=0, hi=None, chunk=250):
-    """Seeded synthetic loci [lo, hi): trees + (n, L) ASCII alignments (per-chunk seeds so any shard of the
-    same workload sees identical data regardless of the number of ranks)."""
+def make_locus_trees(M, n, seed, lo=0, hi=None, chunk=250):
+    """Seeded random gene trees of loci [lo, hi) (per-chunk seeds: a shard sees the trees of the whole workload)."""
     from phynetpy_b200 import simulate as S
     hi = M if hi is None else hi
-    trees, alns = [], []
-    c_lo = (lo // chunk) * chunk
-    for c0 in range(c_lo, hi, chunk):
+    trees = []
+    for c0 in range((lo // chunk) * chunk, hi, chunk):
         c1 = min(M, c0 + chunk)
-        rng = np.random.default_rng([seed, c0])
-        par, bl = S.random_trees(c1 - c0, n, rng)
-        aln = S.simulate_alignments(par, bl, L, PI, RATES, rng)
+        par, bl = S.random_trees(c1 - c0, n, np.random.default_rng([seed, c0]))
         ft = S.flat_trees(par, bl)
-        for i in range(c1 - c0):
-            if lo <= c0 + i < hi:
-                trees.append(ft[i])
-                alns.append(aln[i])
+        trees.extend(ft[i] for i in range(c1 - c0) if lo <= c0 + i < hi)
+    return trees
+
+
+def make_locus_data(M, n, L, seed, lo=0, hi=None, device=True):
+    """Seeded synthetic loci [lo, hi): trees + (n, L) ASCII alignments evolved down them under the GTR model.  The
+    sequences come from the counter-based simulator keyed by (seed, global locus index, site, node): on the device
+    (K-s, pnb_simulate_alignments) for the GPU arm, from its NumPy twin (identical bytes, tests/test_gpu_chain.py) for
+    the CPU arm -- any shard, on any number of ranks, on either side, sees the same data."""
+    from phynetpy_b200 import simulate as S
+    hi = M if hi is None else hi
+    trees = make_locus_trees(M, n, seed, lo, hi)
+    sim = S.simulate_alignments_device if device else S.simulate_alignments_counter
+    alns = []
+    for c0 in range(0, len(trees), 2500):      # bounded host / device memory per call
+        alns.extend(sim(trees[c0:c0 + 2500], L, PI, RATES, seed, list(range(lo + c0, lo + min(c0 + 2500, len(trees))))))
     return trees, alns
 
 
@@ -134,10 +142,7 @@ def build_cfg2(P_target, n, seed, P):
     par, bl = S.random_trees(1, n, rng)
     ft = S.flat_trees(par, bl)[0]
     L = int(P_target * 1.06) + 64
-    blocks = []
-    for c0 in range(0, L, 131072):  # bounded host memory while simulating
-        blocks.append(S.simulate_alignments(par, bl, min(131072, L - c0), PI, RATES, rng)[0])
-    mat = np.concatenate(blocks, axis=1)
+    mat = S.simulate_alignments_device([ft], L, PI, RATES, seed, [0])[0]     # K-s: one thread per site
     t0 = time.perf_counter()
     codes, w, first, _ = compress_alignment(mat, _CODE_OF_BYTE, use_device=True)
     t_comp = time.perf_counter() - t0
@@ -1051,7 +1056,7 @@ def run_reference(args, wl, spec, rank):
         rng = np.random.default_rng(2)
         par, bl = S.random_trees(1, n, rng)
         ft = S.flat_trees(par, bl)[0]
-        mat = S.simulate_alignments(par, bl, int(n_pat * 1.05), PI, RATES, rng)[0]
+        mat = S.simulate_alignments_counter([ft], int(n_pat * 1.05), PI, RATES, 2, [0])[0]   # the first columns of the GPU arm's data
         first, w, _ = O.compress_fast(mat)
         lut = np.array([O.tip_code_for_char(chr(b)) for b in range(256)], dtype=np.uint8)
         codes = np.ascontiguousarray(lut[mat[:, first[:n_pat]]])
@@ -1061,7 +1066,7 @@ def run_reference(args, wl, spec, rank):
         what = "the first %d patterns of the cfg2 workload (1/%d of it)" % (n_pat, max(1, spec["P"] // n_pat))
     else:
         n_loci = min(spec["M"], 512)
-        trees, alns = make_locus_data(spec["M"], spec["n"], spec["L"], SEEDS[wl], 0, n_loci)
+        trees, alns = make_locus_data(spec["M"], spec["n"], spec["L"], SEEDS[wl], 0, n_loci, device=False)
         taxa = ["t%d" % i for i in range(spec["n"])]
         entries = cpu_entries_loci(trees, alns, taxa, scales=tuple(1.0 + 0.002 * k for k in range(8)))
         what = "the first %d of the %d loci" % (n_loci, spec["M"])

@@ -278,6 +278,19 @@ PNB_API int pnb_candidates_fill(pnb_ctx *ctx, int64_t n_trees, const int64_t *tr
                                 const int64_t *member_off, int32_t *parent_out, double *blen_out,
                                 double *height_out, int32_t *changed_node_out, double *scale_out);
 
+/* ---- K-s: synthetic alignments on the device (input generator) -------------------- */
+/* Replaces simulate_sequences / _evolve (src/_sim_seq.py:431-504) for M gene trees at once: a root state from pi,
+ * every child state from the row P[parent state] of its branch, L sites per tree, one thread per (tree, site).
+ * Trees are CSR-packed like pnb_eval's; P_edge: total_nodes x 16 host doubles, row-major P of the edge above each
+ * node (the root's is ignored) -- supplied by the caller so that host and device compare against identical
+ * thresholds.  Draws come from a counter-based generator keyed by (seed, stream_id[j], site, node): a tree's
+ * alignment depends on nothing else (not on the batch, the GPU count or the device; phynetpy_b200/simulate.py
+ * reproduces the same bytes in NumPy).  out: host bytes, tree j at out_off[j] (written, M + 1 entries): one row of
+ * L ASCII characters A/C/G/T per leaf, leaves in node order.  Up to 512 nodes per tree.                      */
+PNB_API int pnb_simulate_alignments(pnb_ctx *ctx, int64_t M, const int64_t *node_off, const int32_t *parent,
+                                    const double *P_edge, const double pi[4], int64_t L, uint64_t seed,
+                                    const int64_t *stream_id, uint8_t *out, int64_t *out_off);
+
 /* ---- host-only planning (tests of the host runtime; no device involved) -- */
 /* A planning context owns no GPU: loci created on it hold no device memory and
  * pnb_eval on it fails.  pnb_plan runs exactly the host half of pnb_eval -- cache

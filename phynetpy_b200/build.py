@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libphynet_b200.so")
-SOURCES = ["pnb_runtime.cu", "pnb_compile.cu", "pnb_eval.cu", "pnb_batch.cu", "pnb_compress.cu", "pnb_msnc.cu", "pnb_candidates.cu"]
+SOURCES = ["pnb_runtime.cu", "pnb_compile.cu", "pnb_eval.cu", "pnb_batch.cu", "pnb_compress.cu", "pnb_msnc.cu", "pnb_candidates.cu", "pnb_simulate.cu"]
 HEADERS = ["pnb_device.cuh", "pnb_host.hpp", "pnb_msnc_core.hpp", os.path.join("..", "..", "include", "phynet_b200.h")]
 
 NVCC_FLAGS = [

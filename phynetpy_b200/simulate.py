@@ -236,3 +236,109 @@ def simulate_gene_trees_msnc(net, alleles_per_species: int, theta: float, rng: n
         blen = [float("nan") if parent[i] < 0 else node_h[parent[i]] - node_h[i] for i in range(2 * n_leaves - 1)]
         trees.append(FlatTree(parent, blen, labels))
     return trees, species_of
+
+
+# ---------------------------------------------------------------------------------------------
+# Counter-based sequence simulation: on the device (K-s, pnb_simulate_alignments) and its NumPy twin
+# ---------------------------------------------------------------------------------------------
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _mix64(x: np.ndarray) -> np.ndarray:
+    """splitmix64 finaliser on uint64 arrays (wrapping arithmetic), as ``sim_mix`` in csrc/pnb_simulate.cu."""
+    with np.errstate(over="ignore"):
+        x = x ^ (x >> np.uint64(30))
+        x = x * np.uint64(0xBF58476D1CE4E5B9)
+        x = x ^ (x >> np.uint64(27))
+        x = x * np.uint64(0x94D049BB133111EB)
+        x = x ^ (x >> np.uint64(31))
+    return x
+
+
+def counter_uniform(seed: int, stream: int, sites: np.ndarray, node: int) -> np.ndarray:
+    """U[0, 1) draws keyed by (seed, stream, site, node): the generator of K-s, bit for bit."""
+    with np.errstate(over="ignore"):
+        s0 = _mix64(np.array([seed], dtype=np.uint64) + np.uint64(0x9E3779B97F4A7C15) * np.uint64(stream + 1))
+        k = sites.astype(np.uint64) * np.uint64(0xD1B54A32D192ED03) + np.uint64(node) * np.uint64(0x8CB92BA72F3D8DD7) \
+            + np.uint64(0x2545F4914F6CDD1D)
+        x = _mix64(s0 ^ k)
+    return (x >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+def edge_p_matrices(blen: np.ndarray, pi: Sequence[float], rates: Sequence[float]) -> np.ndarray:
+    """Row-major P(t) of the edge above every node, ``(..., 16)`` float64, on the host (NaN length -> 0): the
+    thresholds both simulators compare against."""
+    ev, U, Ui = gtr_eigen(pi, rates)
+    t = np.nan_to_num(np.asarray(blen, dtype=np.float64), nan=0.0)
+    Pm = np.einsum("ik,...k,kj->...ij", U, np.exp(ev * t[..., None]), Ui)
+    return np.ascontiguousarray(Pm.reshape(t.shape + (16,)))
+
+
+def _cum_rows(P16: np.ndarray) -> np.ndarray:
+    """Sequential cumulative sums of the clipped rows (the order ``cum_rows`` uses on the device side)."""
+    P = np.clip(P16.reshape(-1, 4, 4), 0.0, None)
+    c = np.empty_like(P)
+    s = np.zeros(P.shape[:2])
+    for j in range(4):
+        s = s + P[:, :, j]
+        c[:, :, j] = s
+    return c
+
+
+def simulate_alignments_counter(trees: Sequence[FlatTree], L: int, pi: Sequence[float], rates: Sequence[float], seed: int,
+                                stream_ids: Sequence[int]) -> List[np.ndarray]:
+    """NumPy twin of K-s: the alignment of every tree as an ``(n_tips, L)`` ASCII matrix (leaves in node order)."""
+    pi = np.asarray(pi, dtype=np.float64)
+    c = np.cumsum(pi)          # sequential: c0, c1, c2 as on the device
+    sites = np.arange(L)
+    out = []
+    for t, sid in zip(trees, stream_ids):
+        nn = t.n_nodes
+        cum = _cum_rows(edge_p_matrices(t.blen, pi, rates))
+        kids = [[] for _ in range(nn)]
+        root = -1
+        for v, p in enumerate(t.parent.tolist()):
+            if p < 0:
+                root = v
+            else:
+                kids[p].append(v)
+        st = np.zeros((nn, L), dtype=np.uint8)
+        stack = [root]
+        while stack:
+            v = stack.pop()
+            u = counter_uniform(seed, int(sid), sites, v)
+            if v == root:
+                st[v] = (u > c[0]).astype(np.uint8) + (u > c[1]) + (u > c[2])
+            else:
+                row = cum[v][st[t.parent[v]]]          # (L, 4)
+                st[v] = (u > row[:, 0]).astype(np.uint8) + (u > row[:, 1]) + (u > row[:, 2])
+            stack.extend(kids[v])
+        tips = [v for v in range(nn) if not kids[v]]
+        out.append(ASCII_ACGT[st[tips]])
+    return out
+
+
+def simulate_alignments_device(trees: Sequence[FlatTree], L: int, pi: Sequence[float], rates: Sequence[float], seed: int,
+                               stream_ids: Sequence[int], context=None) -> List[np.ndarray]:
+    """K-s through the C ABI: every tree's alignment in one launch (one thread per tree and site)."""
+    import ctypes as C
+    from . import _lib
+    from .device import default_context
+    ctx = context or default_context()
+    M = len(trees)
+    if M == 0:
+        return []
+    sizes = np.fromiter((t.n_nodes for t in trees), dtype=np.int64, count=M)
+    node_off = np.zeros(M + 1, dtype=np.int64)
+    np.cumsum(sizes, out=node_off[1:])
+    parent = np.ascontiguousarray(np.concatenate([t.parent for t in trees]), dtype=np.int32)
+    blen = np.concatenate([t.blen for t in trees])
+    P_edge = edge_p_matrices(blen, pi, rates)
+    n_tips = np.fromiter((int((t.n_children() == 0).sum()) for t in trees), dtype=np.int64, count=M)
+    out = np.empty(int((n_tips * L).sum()), dtype=np.uint8)
+    out_off = np.zeros(M + 1, dtype=np.int64)
+    sid = np.ascontiguousarray(stream_ids, dtype=np.int64)
+    pi_a = np.ascontiguousarray(pi, dtype=np.float64)
+    _lib.check(ctx._lib.pnb_simulate_alignments(ctx.handle, M, _lib.ptr(node_off), _lib.ptr(parent), _lib.ptr(P_edge), _lib.ptr(pi_a),
+                                                int(L), C.c_uint64(int(seed)), _lib.ptr(sid), _lib.ptr(out), _lib.ptr(out_off)))
+    return [out[out_off[j]:out_off[j + 1]].reshape(int(n_tips[j]), L) for j in range(M)]
