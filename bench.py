@@ -826,7 +826,7 @@ def chain_cfg3(args, P, ctx, model):
     trees, alns = make_locus_data(spec["M"], spec["n"], spec["L"], SEEDS["cfg3"])
     taxa = ["t%d" % i for i in range(spec["n"])]
     calcs = [P.FelsensteinCalculator.from_matrix(taxa, a, device_compress=False) for a in alns]
-    eng = P.SeqLikelihoodEngine(calcs, None, model, context=ctx)
+    eng = P.SeqLikelihoodEngine(calcs, None, model, context=ctx, resident_batches=True)
     scales = [1.0 + 0.002 * k for k in range(8)]
     props = [[t.with_lengths(t.blen * s) for t in trees] for s in scales]
     M = len(trees)
@@ -966,6 +966,7 @@ def chain_cfg4(args, P, ctx, model):
     total = eng2.log_likelihood(cur, net, theta)
     n2 = 1000
     lat_locus, lat_theta, accepted, impossible = [], [], 0, 0
+    abi_locus = []
     t0 = time.perf_counter()
     done = 0
     for step in range(n2):
@@ -997,6 +998,7 @@ def chain_cfg4(args, P, ctx, model):
             s0 = time.perf_counter()
             new_total = eng2.log_likelihood(prop, net, theta)
             lat_locus.append(time.perf_counter() - s0)
+            abi_locus.append(ctx.last_timings()["call_ms"])
         done += 1
         impossible += new_total == -math.inf
         if math.log(rng.random()) < (new_total - total) + loghr:
@@ -1021,6 +1023,8 @@ def chain_cfg4(args, P, ctx, model):
         "logL_evaluations_per_s": done / wall, "accept_rate": accepted / max(done, 1),
         "proposals_without_embedding": int(impossible),
         "median_latency_us_locus_move": float(np.median(lat_locus) * 1e6),
+        "median_c_abi_us_locus_move": float(np.median(abi_locus) * 1e3),
+        "locus_move_what": "pnb_eval_move: dirty-path pruning and the MSNC density of the moved gene tree queued on two streams, one host synchronisation",
         "median_latency_us_theta_move_all_loci_msnc": float(np.median(lat_theta) * 1e6),
         "cached_equals_recomputed_bitwise": bool(inc_f == list(eng2._felsen) and inc_m == list(eng2._msnc) and full == total),
     }

@@ -259,6 +259,15 @@ PNB_API int pnb_msnc_eval(pnb_ctx *ctx, const pnb_msnc_net *net, int64_t n_trees
                           const int32_t *parent, const double *blen, const int32_t *node_species,
                           double theta, double *logp_out);
 
+/* One gene-tree move of the chain (op_gene_node_height / op_gene_tree_nni, src/_mcmc_seq.py:1020-1113) dirties ONE locus:
+ * _SeqLikelihoodEngine.log_likelihood then re-scores both of its factors (:746-760).  pnb_eval_move does both with one
+ * host synchronisation: pnb_eval of the single (locus, tree) job (flags: PNB_EVAL_PENDING / PNB_EVAL_FULL /
+ * PNB_EVAL_RESCALE) and pnb_msnc_eval of the same tree are queued back to back; out[0] = log P(S | g),
+ * out[1] = log P(g | Psi).  node_species as for pnb_msnc_eval.                                                   */
+PNB_API int pnb_eval_move(pnb_ctx *ctx, const pnb_model *m, pnb_locus *locus, int32_t n_nodes, const int32_t *parent,
+                          const double *blen, const int32_t *tip_row, double site_rate, uint32_t flags,
+                          const pnb_msnc_net *net, const int32_t *node_species, double theta, double out[2]);
+
 /* ---- candidate sets of the coupled moves (host) -------------------------------- */
 /* Replaces _candidate_set / _gene_tree_nni_neighbors / _scaled_gene_tree (src/_mcmc_seq.py:1724-1861) for MANY gene
  * trees at once, writing straight into the CSR arrays pnb_eval / pnb_msnc_eval take.  The candidate set of a tree

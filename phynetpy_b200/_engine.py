@@ -50,10 +50,16 @@ class SeqLikelihoodEngine:
     def __init__(self, loci: Sequence[Any], species_of: Optional[dict] = None, model: Any = None,
                  branch_thetas: Optional[dict] = None, *, msnc_fn: Optional[MsncFn] = None,
                  context: Optional[DeviceContext] = None, shard: Optional[ShardPlan] = None,
-                 rescale: bool = False) -> None:
+                 rescale: bool = False, resident_batches: bool = False) -> None:
         """``loci``: per-locus alignments (``dict`` label -> sequence) or ready
         :class:`FelsensteinCalculator` objects.  With ``shard`` only this rank's loci
-        are made resident (entries outside the shard may be ``None``)."""
+        are made resident (entries outside the shard may be ``None``).
+
+        ``resident_batches``: evaluations in which EVERY local locus is dirty go through a resident batch
+        (``pnb_batch_*``: op programs stay in HBM, only branch lengths travel, every node is recomputed and the
+        result is committed at once).  The right choice when such evaluations change all branch lengths (height
+        rescalings, model changes, throughput runs); leave it off when they change a branch or two per locus --
+        the default path recomputes only the changed paths and keeps the evaluation pending for a rollback."""
         self.n_loci = len(loci)
         self._species_of = species_of
         self._model = model
@@ -76,6 +82,7 @@ class SeqLikelihoodEngine:
         self._msnc_all = True                  # every _msnc entry is None
         self._full_next = False
         self._mode = _lib.EVAL_RESCALE if rescale else 0  # numerical mode (beyond the reference when set)
+        self.resident_batches = bool(resident_batches)
         self.last_stats: dict = {}
         # MSNC side: the network view is rebuilt when a different network OBJECT arrives (the reference
         # keys on identity too, src/_mcmc_seq.py:705-713); per-locus species ids are keyed by the label list
@@ -154,7 +161,7 @@ class SeqLikelihoodEngine:
 
     # -- evaluation -----------------------------------------------------------
     def felsenstein_batch(self, idx: Sequence[int], gene_trees: Sequence[Any], *, flags: int = 0,
-                          site_rate: float = 1.0) -> np.ndarray:
+                          site_rate: float = 1.0, out_device_ptr: Optional[int] = None) -> Optional[np.ndarray]:
         """log P(S_i | g_i) for the given local loci in one device call."""
         ctx = self._context()
         flats = [flatten(gene_trees[i]) for i in idx]
@@ -162,8 +169,9 @@ class SeqLikelihoodEngine:
         P_edge = None
         if _device_kind(self._model) == "explicit":
             P_edge = _explicit_P_edges(self._model, blen, site_rate)
+        extra = {} if out_device_ptr is None else {"out_device_ptr": out_device_ptr}
         out = ctx.eval(_model_handle(self._model, ctx), self._handles(idx), node_off, parent, blen, tip_row,
-                       site_rate, flags, P_edge)
+                       site_rate, flags, P_edge, **extra)
         self.last_stats = ctx.last_stats()
         return out
 
@@ -181,10 +189,14 @@ class SeqLikelihoodEngine:
         self._dirty.clear()
         flags = _lib.EVAL_PENDING | self._mode | (_lib.EVAL_FULL if self._full_next else 0)
         self._full_next = False
-        if self._shard.world_size == 1:
+        if (self._shard.world_size == 1 and len(dirty) == 1 and species_net is not None and self._msnc_fn is None
+                and not self._msnc_all and self._msnc_dirty == {dirty[0]} and self._msnc[dirty[0]] is None
+                and _device_kind(self._model) != "explicit" and hasattr(self._context(), "eval_move")):
+            self._eval_move(dirty[0], gene_trees[dirty[0]], species_net, theta, flags)   # a gene-tree move: one device call
+        elif self._shard.world_size == 1:
             if dirty:
-                if len(dirty) == hi - lo and len(dirty) >= self.BATCH_MIN_LOCI and _device_kind(self._model) != "explicit" \
-                        and not (flags & _lib.EVAL_FULL):
+                if self.resident_batches and len(dirty) == hi - lo and len(dirty) >= self.BATCH_MIN_LOCI \
+                        and _device_kind(self._model) != "explicit" and not (flags & _lib.EVAL_FULL):
                     vals = self._eval_all_local(dirty, gene_trees)        # resident batch: committed at once
                 else:
                     vals = self.felsenstein_batch(dirty, gene_trees, flags=flags)
@@ -204,6 +216,23 @@ class SeqLikelihoodEngine:
             if rescan:
                 raise
             return self.log_likelihood(gene_trees, species_net, theta, rescan=True)
+
+    def _eval_move(self, i: int, gene_tree: Any, species_net: Any, theta: float, flags: int) -> None:
+        """A gene-tree move dirtied locus ``i`` alone: its Felsenstein factor (dirty-path pruning) and its MSNC
+        density in ONE device call with one host synchronisation (``pnb_eval_move``); the reference computes them
+        one after the other in its loop over loci (``src/_mcmc_seq.py:746-760``)."""
+        theta = _check_theta(theta)
+        ctx = self._context()
+        net = self._network(species_net)
+        ft = flatten(gene_tree)
+        calc = self._calcs[i]
+        f, m = ctx.eval_move(_model_handle(self._model, ctx), calc._locus_handle(), ft.parent, ft.blen, ft.tip_rows(calc._row_of),
+                             1.0, flags, net.handle(ctx, self._branch_thetas), self._species_ids(i, ft, net), theta)
+        self._felsen[i] = f
+        self._msnc[i] = m
+        self._pending = [i]
+        self._msnc_dirty.clear()
+        self.last_stats = ctx.last_stats()
 
     BATCH_MIN_LOCI = 32   # all-local-loci evaluations of at least this many loci go through a resident batch
 
@@ -288,12 +317,17 @@ class SeqLikelihoodEngine:
             with torch.cuda.stream(sh["stream"]):
                 fused = False
                 if dirty:
-                    if len(dirty) == hi - lo and _device_kind(self._model) != "explicit" and not (flags & _lib.EVAL_FULL):
+                    if self.resident_batches and len(dirty) == hi - lo and _device_kind(self._model) != "explicit" \
+                            and not (flags & _lib.EVAL_FULL):
                         # every rank takes this branch together (every rank's shard is dirty as a whole): with symmetric
                         # memory the kernel's peer stores + one device-side barrier replace the all-gather
                         fused = sh["sym"] is not None and len(self._dirty_any) == self.n_loci
                         self._eval_all_local(dirty, gene_trees, out_device_ptr=vec.data_ptr() + 8 * base,
                                              peer_ptrs=sh["peers"][turn] if fused else [])
+                    elif len(dirty) == hi - lo:
+                        # the whole shard through pnb_eval (dirty-path aware, pending): the kernel writes this rank's slice
+                        self.felsenstein_batch(dirty, gene_trees, flags=flags, out_device_ptr=vec.data_ptr() + 8 * base)
+                        self._pending = list(dirty)
                     else:
                         vals = self.felsenstein_batch(dirty, gene_trees, flags=flags)
                         self._pending = list(dirty)

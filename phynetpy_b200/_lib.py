@@ -43,7 +43,7 @@ ABI_SYMBOLS = (
     "pnb_batch_create", "pnb_batch_destroy", "pnb_batch_info", "pnb_batch_traffic", "pnb_batch_blen_host", "pnb_batch_eval", "pnb_batch_set_peer_outputs",
     "pnb_ctx_create_host", "pnb_plan",
     "pnb_msnc_net_create", "pnb_msnc_net_destroy", "pnb_msnc_net_info", "pnb_msnc_net_set_max_frontier", "pnb_msnc_net_set_branch_thetas",
-    "pnb_msnc_eval",
+    "pnb_msnc_eval", "pnb_eval_move",
     "pnb_candidates_count", "pnb_candidates_fill",
     "pnb_simulate_alignments",
 )
@@ -118,6 +118,7 @@ def load() -> C.CDLL:
             "pnb_msnc_net_set_max_frontier": [_vp, _i64],
             "pnb_msnc_net_set_branch_thetas": [_vp, _vp, C.c_double],
             "pnb_msnc_eval": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, C.c_double, _vp],
+            "pnb_eval_move": [_vp, _vp, _vp, _i32, _vp, _vp, _vp, C.c_double, C.c_uint32, _vp, _vp, C.c_double, _vp],
             "pnb_simulate_alignments": [_vp, _i64, _vp, _vp, _vp, _vp, _i64, C.c_uint64, _vp, _vp, _vp],
             "pnb_candidates_count": [_vp, _i64, _vp, _vp, _vp, _i32, _vp, _vp],
             "pnb_candidates_fill": [_vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],

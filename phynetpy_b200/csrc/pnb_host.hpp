@@ -222,6 +222,12 @@ struct pnb_ctx {
     int stage_idx = 0;
     pnb::Buffer d_P;               // [ops][16] P matrices (K-a output)
     pnb::Buffer d_tile_sum, d_job_done, d_out, h_out;
+    // K-m (pnb_msnc.cu) owns its buffers: a gene-tree move runs it next to the pruning path (pnb_eval_move)
+    pnb::Buffer m_hstage, m_dstage, m_scratch, m_dout, m_hout;
+    int64_t msnc_pending_trees = 0;      // launched, not yet handed out (msnc_finish)
+    size_t msnc_pending_status_off = 0;
+    int msnc_pending_cap = 0;
+    int64_t msnc_stats[8] = {0};
     size_t job_done_zeroed = 0;    // counters [0, job_done_zeroed) are known to be zero
     int64_t stats[8] = {0};
     bool profiling = false;

@@ -204,16 +204,21 @@ extern "C" int pnb_msnc_net_set_max_frontier(pnb_msnc_net* net, int64_t entries)
     return PNB_OK;
 }
 
-extern "C" int pnb_msnc_eval(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_trees, const int64_t* tree_off,
-                             const int32_t* parent, const double* blen, const int32_t* node_species, double theta,
-                             double* logp_out) {
+// The evaluation in two halves, so that a gene-tree move can put both likelihood factors behind ONE host
+// synchronisation (pnb_eval_move): msnc_launch prepares the trees on the host, uploads and launches (everything is
+// queued on the context's stream, results travel to the K-m-owned pinned buffer); msnc_finish waits and hands out.
+static int msnc_finish(pnb_ctx* ctx, double* logp_out, cudaStream_t st);
+
+static int msnc_launch(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_trees, const int64_t* tree_off,
+                       const int32_t* parent, const double* blen, const int32_t* node_species, double theta, cudaStream_t st) {
     PNB_REQUIRE(ctx && net, PNB_ERR_INVALID, "pnb_msnc_eval: NULL handle");
     PNB_REQUIRE(ctx->device >= 0, PNB_ERR_STATE, "pnb_msnc_eval: host-only planning context has no device");
     PNB_REQUIRE(net->ctx == ctx, PNB_ERR_INVALID, "pnb_msnc_eval: network belongs to another context");
     PNB_REQUIRE(n_trees >= 0, PNB_ERR_INVALID, "pnb_msnc_eval: n_trees < 0");
     PNB_REQUIRE(theta > 0.0 && std::isfinite(theta), PNB_ERR_INVALID, "pnb_msnc_eval: theta must be positive and finite");
+    ctx->msnc_pending_trees = 0;
     if (n_trees == 0) return PNB_OK;
-    PNB_REQUIRE(tree_off && parent && blen && node_species && logp_out, PNB_ERR_INVALID, "pnb_msnc_eval: NULL array");
+    PNB_REQUIRE(tree_off && parent && blen && node_species, PNB_ERR_INVALID, "pnb_msnc_eval: NULL array");
     PNB_CUDA_TRY(cudaSetDevice(ctx->device));
     const auto t_call0 = std::chrono::steady_clock::now();
     ctx->ev_ka = ctx->ev_prune = false;
@@ -243,13 +248,12 @@ extern "C" int pnb_msnc_eval(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_tr
     const size_t off_theta = align_up(off_sp + static_cast<size_t>(n_trees) * n_species * NW * sizeof(uint64_t), 256);
     const size_t stage_bytes = off_theta + prog.steps.size() * 4 * sizeof(double);
 
-    // the felsenstein path's staging buffers are reused: wait for whatever still reads them
-    PNB_CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
-    PNB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    // K-m owns its staging, scratch and result buffers (the pruning path may be in flight next to it); every
+    // evaluation ends in msnc_finish, which waits for the stream, so they are free here
     int rc;
-    if ((rc = ensure_pinned(ctx->h_stage2[0], stage_bytes))) return rc;
-    if ((rc = ensure_device(ctx->d_stage, stage_bytes))) return rc;
-    char* hs = static_cast<char*>(ctx->h_stage2[0].p);
+    if ((rc = ensure_pinned(ctx->m_hstage, stage_bytes))) return rc;
+    if ((rc = ensure_device(ctx->m_dstage, stage_bytes))) return rc;
+    char* hs = static_cast<char*>(ctx->m_hstage.p);
     int64_t* ev_off = reinterpret_cast<int64_t*>(hs + off_evoff);
     int32_t* root_bit = reinterpret_cast<int32_t*>(hs + off_root);
     double* ev_t = reinterpret_cast<double*>(hs + off_evt);
@@ -364,7 +368,7 @@ extern "C" int pnb_msnc_eval(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_tr
     const int64_t jobs_per_launch =
         in_smem ? n_trees : std::max<int64_t>(1, std::min<int64_t>(n_trees, static_cast<int64_t>(scratch_budget / per_job)));
     const size_t off_lp = align_up(static_cast<size_t>(jobs_per_launch) * job_mask_words * sizeof(uint64_t), 256);
-    if (!in_smem && (rc = ensure_device(ctx->d_P, off_lp + static_cast<size_t>(jobs_per_launch) * 2 * cap * sizeof(double)))) return rc;
+    if (!in_smem && (rc = ensure_device(ctx->m_scratch, off_lp + static_cast<size_t>(jobs_per_launch) * 2 * cap * sizeof(double)))) return rc;
     if (!ctx->msnc_configured) {   // once per context: opt in to large dynamic shared memory
         const int lim = std::max(ctx->max_smem_optin - 2048, 0);
         PNB_CUDA_TRY(cudaFuncSetAttribute(pnb_msnc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
@@ -372,14 +376,13 @@ extern "C" int pnb_msnc_eval(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_tr
         ctx->msnc_configured = true;
     }
     const size_t off_status = align_up(static_cast<size_t>(n_trees) * sizeof(double), 256);
-    if ((rc = ensure_device(ctx->d_out, off_status + static_cast<size_t>(n_trees) * sizeof(int32_t)))) return rc;
-    if ((rc = ensure_pinned(ctx->h_out, off_status + static_cast<size_t>(n_trees) * sizeof(int32_t)))) return rc;
+    if ((rc = ensure_device(ctx->m_dout, off_status + static_cast<size_t>(n_trees) * sizeof(int32_t)))) return rc;
+    if ((rc = ensure_pinned(ctx->m_hout, off_status + static_cast<size_t>(n_trees) * sizeof(int32_t)))) return rc;
 
     ctx->t_compile_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call0).count();
-    cudaStream_t st = ctx->stream;
-    PNB_CUDA_TRY(cudaMemcpyAsync(ctx->d_stage.p, hs, stage_bytes, cudaMemcpyHostToDevice, st));
+    PNB_CUDA_TRY(cudaMemcpyAsync(ctx->m_dstage.p, hs, stage_bytes, cudaMemcpyHostToDevice, st));
     if (ctx->profiling) PNB_CUDA_TRY(cudaEventRecord(ctx->ev[2], st));   // reported as the "prune" slot of last_timings
-    char* ds = static_cast<char*>(ctx->d_stage.p);
+    char* ds = static_cast<char*>(ctx->m_dstage.p);
     MsncLaunch L;
     L.steps = net->d_steps;
     L.down_slot = net->d_down;
@@ -392,8 +395,8 @@ extern "C" int pnb_msnc_eval(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_tr
     L.tree_shaped = prog.retic_step.empty() ? 1 : 0;
     L.n_down = static_cast<int32_t>(prog.down_slot.size());
     L.program_words = static_cast<int32_t>(program_bytes / 8);
-    L.fr_mask = in_smem ? nullptr : static_cast<uint64_t*>(ctx->d_P.p);
-    L.fr_lp = in_smem ? nullptr : reinterpret_cast<double*>(static_cast<char*>(ctx->d_P.p) + off_lp);
+    L.fr_mask = in_smem ? nullptr : static_cast<uint64_t*>(ctx->m_scratch.p);
+    L.fr_lp = in_smem ? nullptr : reinterpret_cast<double*>(static_cast<char*>(ctx->m_scratch.p) + off_lp);
     int64_t launches = 0;
     for (int64_t j0 = 0; j0 < n_trees; j0 += jobs_per_launch) {
         const int64_t nj = std::min(jobs_per_launch, n_trees - j0);
@@ -403,8 +406,8 @@ extern "C" int pnb_msnc_eval(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_tr
         L.ev_n = reinterpret_cast<const uint32_t*>(ds + off_evn);
         L.species_mask = reinterpret_cast<const uint64_t*>(ds + off_sp) + static_cast<size_t>(j0) * n_species * NW;
         L.root_bit = reinterpret_cast<const int32_t*>(ds + off_root) + j0;
-        L.out = static_cast<double*>(ctx->d_out.p) + j0;
-        L.status = reinterpret_cast<int32_t*>(static_cast<char*>(ctx->d_out.p) + off_status) + j0;
+        L.out = static_cast<double*>(ctx->m_dout.p) + j0;
+        L.status = reinterpret_cast<int32_t*>(static_cast<char*>(ctx->m_dout.p) + off_status) + j0;
         const unsigned blocks = static_cast<unsigned>((nj + threads - 1) / threads);
         if (NW == 1) pnb_msnc_kernel<1><<<blocks, threads, dyn_smem, st>>>(L);
         else pnb_msnc_kernel<2><<<blocks, threads, dyn_smem, st>>>(L);
@@ -412,26 +415,75 @@ extern "C" int pnb_msnc_eval(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_tr
         ++launches;
     }
     if (ctx->profiling) { PNB_CUDA_TRY(cudaEventRecord(ctx->ev[3], st)); ctx->ev_prune = true; }
-    PNB_CUDA_TRY(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, off_status + static_cast<size_t>(n_trees) * sizeof(int32_t),
+    PNB_CUDA_TRY(cudaMemcpyAsync(ctx->m_hout.p, ctx->m_dout.p, off_status + static_cast<size_t>(n_trees) * sizeof(int32_t),
                                  cudaMemcpyDeviceToHost, st));
+    ctx->msnc_pending_trees = n_trees;
+    ctx->msnc_pending_status_off = off_status;
+    ctx->msnc_pending_cap = cap;
+    ctx->msnc_stats[0] = n_trees;
+    ctx->msnc_stats[1] = ev_off[n_trees];
+    ctx->msnc_stats[2] = cap - 1;
+    ctx->msnc_stats[3] = launches;
+    ctx->msnc_stats[4] = static_cast<int64_t>(stage_bytes);
+    ctx->msnc_stats[5] = static_cast<int64_t>(off_status + static_cast<size_t>(n_trees) * sizeof(int32_t));
+    ctx->msnc_stats[6] = in_smem ? static_cast<int64_t>(dyn_smem - program_bytes) : 0;   // bytes of shared memory per block holding frontiers
+    ctx->msnc_stats[7] = threads;
+    return PNB_OK;
+}
+
+static int msnc_finish(pnb_ctx* ctx, double* logp_out, cudaStream_t st) {
+    const int64_t n_trees = ctx->msnc_pending_trees;
+    if (n_trees == 0) return PNB_OK;
+    ctx->msnc_pending_trees = 0;
     PNB_CUDA_TRY(cudaStreamSynchronize(st));
-    const double* ho = static_cast<const double*>(ctx->h_out.p);
-    const int32_t* hstat = reinterpret_cast<const int32_t*>(static_cast<const char*>(ctx->h_out.p) + off_status);
+    const double* ho = static_cast<const double*>(ctx->m_hout.p);
+    const int32_t* hstat = reinterpret_cast<const int32_t*>(static_cast<const char*>(ctx->m_hout.p) + ctx->msnc_pending_status_off);
     for (int64_t j = 0; j < n_trees; ++j) {
         PNB_REQUIRE(hstat[j] == JOB_OK, PNB_ERR_UNSUPPORTED,
                     "pnb_msnc_eval: gene tree %lld needs more than %d frontier entries (raise pnb_msnc_net_set_max_frontier)",
-                    static_cast<long long>(j), cap - 1);
+                    static_cast<long long>(j), ctx->msnc_pending_cap - 1);
         logp_out[j] = ho[j];
     }
-    memset(ctx->stats, 0, sizeof(ctx->stats));
-    ctx->stats[3] = launches;
-    ctx->stats[4] = static_cast<int64_t>(stage_bytes);
-    ctx->stats[5] = static_cast<int64_t>(off_status + static_cast<size_t>(n_trees) * sizeof(int32_t));
-    ctx->stats[1] = ev_off[n_trees];
-    ctx->stats[0] = n_trees;
-    ctx->stats[2] = cap - 1;
-    ctx->stats[6] = in_smem ? static_cast<int64_t>(dyn_smem - program_bytes) : 0;   // bytes of shared memory per block holding frontiers
-    ctx->stats[7] = threads;
+    return PNB_OK;
+}
+
+extern "C" int pnb_msnc_eval(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_trees, const int64_t* tree_off,
+                             const int32_t* parent, const double* blen, const int32_t* node_species, double theta,
+                             double* logp_out) {
+    PNB_REQUIRE(n_trees <= 0 || logp_out, PNB_ERR_INVALID, "pnb_msnc_eval: NULL array");
+    const auto t_call0 = std::chrono::steady_clock::now();
+    PNB_REQUIRE(ctx != nullptr, PNB_ERR_INVALID, "pnb_msnc_eval: NULL handle");
+    int rc = msnc_launch(ctx, net, n_trees, tree_off, parent, blen, node_species, theta, ctx->stream);
+    if (rc) return rc;
+    if ((rc = msnc_finish(ctx, logp_out, ctx->stream))) return rc;
+    memcpy(ctx->stats, ctx->msnc_stats, sizeof(ctx->stats));
+    ctx->t_call_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call0).count();
+    return PNB_OK;
+}
+
+// One gene-tree move of MCMC_SEQ re-scores both factors of ONE locus (src/_mcmc_seq.py:746-760 with a single dirty
+// locus): the pruning of its alignment along the changed path and the MSNC density of its gene tree.  Both kernels are
+// queued on the context's stream and the host waits once.
+extern "C" int pnb_eval_move(pnb_ctx* ctx, const pnb_model* m, pnb_locus* locus, int32_t n_nodes, const int32_t* parent,
+                             const double* blen, const int32_t* tip_row, double site_rate, uint32_t flags,
+                             const pnb_msnc_net* net, const int32_t* node_species, double theta, double out[2]) {
+    PNB_REQUIRE(ctx && m && locus && net && out, PNB_ERR_INVALID, "pnb_eval_move: NULL argument");
+    PNB_REQUIRE(!(flags & (PNB_EVAL_OUT_DEVICE | PNB_EVAL_NOSTORE)), PNB_ERR_INVALID,
+                "pnb_eval_move: results go to the host and the evaluation is stored (PENDING or committed)");
+    PNB_REQUIRE(n_nodes >= 1, PNB_ERR_INVALID, "pnb_eval_move: empty tree");
+    const auto t_call0 = std::chrono::steady_clock::now();
+    const int64_t off[2] = {0, n_nodes};
+    // the two factors are independent: K-m runs on the context's second stream NEXT TO the pruning kernel
+    int rc = msnc_launch(ctx, net, 1, off, parent, blen, node_species, theta, ctx->copy_stream);
+    if (rc) return rc;
+    pnb_locus* loci[1] = {locus};
+    const int rc_f = pnb_eval(ctx, m, 1, loci, off, parent, blen, tip_row, nullptr, site_rate, flags, &out[0]);
+    const int rc_m = msnc_finish(ctx, &out[1], ctx->copy_stream);     // always drains, also after a failed pruning call
+    if (rc_f) return rc_f;
+    if (rc_m) {
+        if (flags & PNB_EVAL_PENDING) pnb_rollback(ctx, 1, loci);
+        return rc_m;
+    }
     ctx->t_call_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call0).count();
     return PNB_OK;
 }

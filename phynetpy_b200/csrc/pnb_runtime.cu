@@ -225,8 +225,11 @@ extern "C" int pnb_ctx_destroy(pnb_ctx* ctx) {
     for (auto& e : ctx->stage_ev) if (e) cudaEventDestroy(e);
     if (ctx->h_out.p) cudaFreeHost(ctx->h_out.p);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
-    for (Buffer* b : {&ctx->d_stage, &ctx->d_P, &ctx->d_tile_sum, &ctx->d_job_done, &ctx->d_out})
+    for (Buffer* b : {&ctx->d_stage, &ctx->d_P, &ctx->d_tile_sum, &ctx->d_job_done, &ctx->d_out, &ctx->m_dstage, &ctx->m_scratch,
+                      &ctx->m_dout})
         if (b->p) cudaFree(b->p);
+    for (Buffer* b : {&ctx->m_hstage, &ctx->m_hout})
+        if (b->p) cudaFreeHost(b->p);
     ctx->arena.destroy();
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;

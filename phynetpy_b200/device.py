@@ -102,6 +102,17 @@ class DeviceContext:
                                       float(site_rate), flags, out_ptr))
         return out
 
+    def eval_move(self, model_handle: C.c_void_p, locus_handle: C.c_void_p, parent: np.ndarray, blen: np.ndarray,
+                  tip_row: np.ndarray, site_rate: float, flags: int, net_handle: C.c_void_p, node_species: np.ndarray,
+                  theta: float) -> Tuple[float, float]:
+        """Both likelihood factors of ONE locus' gene tree behind one host synchronisation (``pnb_eval_move``)."""
+        assert parent.dtype == np.int32 and blen.dtype == np.float64 and tip_row.dtype == np.int32 and node_species.dtype == np.int32
+        out = (C.c_double * 2)()
+        _lib.check(self._lib.pnb_eval_move(self.handle, model_handle, locus_handle, int(parent.shape[0]), _lib.ptr(parent),
+                                           _lib.ptr(blen), _lib.ptr(tip_row), float(site_rate), flags, net_handle,
+                                           _lib.ptr(node_species), float(theta), out))
+        return out[0], out[1]
+
     def commit(self, loci: np.ndarray) -> None:
         _lib.check(self._lib.pnb_commit(self.handle, int(loci.shape[0]), _lib.ptr(loci)))
 

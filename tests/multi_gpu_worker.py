@@ -72,14 +72,19 @@ def main():
 
     plan = ShardPlan.from_env(M)
     lo, hi = plan.local_range()
-    sharded = P.SeqLikelihoodEngine([d if lo <= i < hi else None for i, d in enumerate(data)], None, model, shard=plan)
-    got = run(sharded)
+    results = []
+    for resident in (True, False):          # all-loci proposals through a resident batch + fused peer stores / through pnb_eval
+        sharded = P.SeqLikelihoodEngine([d if lo <= i < hi else None for i, d in enumerate(data)], None, model, shard=plan,
+                                        resident_batches=resident)
+        results.append(run(sharded))
+    got = results[0]
+    both_paths_agree = results[0] == results[1]
     # every rank holds the same values
     t = torch.tensor(got[0] + got[1] + [got[2]], dtype=torch.float64, device="cuda")
     gathered = [torch.empty_like(t) for _ in range(world)]
     dist.all_gather(gathered, t)
     same = all(torch.equal(g, gathered[0]) for g in gathered)
-    ok = same
+    ok = same and both_paths_agree
     if rank == 0:
         single = P.SeqLikelihoodEngine(data, None, model)
         want = run(single)
