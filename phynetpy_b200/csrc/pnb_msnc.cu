@@ -49,6 +49,9 @@ struct MsncLaunch {
     int32_t n_down;                 // entries of down_slot
     int32_t program_words;          // 8-byte words of shared memory holding the staged program (frontiers follow)
     int32_t tree_shaped;            // 1: no reticulation -> msnc_dp_tree
+    int32_t stage_words;            // > 0: every thread copies its gene tree's events and species masks into this many
+                                    // 8-byte words of shared memory (after the frontiers) before the DP
+    int32_t stage_ev_cap;           // events per tree the staging area holds
 };
 
 template <int NW>
@@ -94,16 +97,30 @@ __global__ void __launch_bounds__(128) pnb_msnc_kernel(MsncLaunch L) {
         fr_lp = L.fr_lp + static_cast<size_t>(j) * 2 * L.cap;
         stride = 1;
     }
+    // The DP looks its events up again and again (two binary searches per step, a scan per entry and branch): from global
+    // memory every probe is an L2 round trip, which is most of a single gene tree's latency.  When the block's shared
+    // memory has room, each thread first copies its tree's events and species masks next to the frontiers.
+    const int n_ev = static_cast<int>(L.ev_off[j + 1] - e0);
+    const double* ev_t = L.ev_t + e0;
+    const uint32_t* ev_n = L.ev_n + e0;
+    const uint64_t* sp_mask = L.species_mask + static_cast<size_t>(j) * L.n_species * NW;
+    if (L.stage_words > 0 && n_ev <= L.stage_ev_cap) {
+        uint64_t* reg = pnb_msnc_smem + L.program_words + (L.frontier_in_smem ? (mask_words + 2 * static_cast<size_t>(L.cap)) * blockDim.x : 0) +
+                        static_cast<size_t>(threadIdx.x) * L.stage_words;
+        double* st = reinterpret_cast<double*>(reg);
+        uint32_t* sn = reinterpret_cast<uint32_t*>(reg + L.stage_ev_cap);
+        uint64_t* ss = reg + L.stage_ev_cap + (L.stage_ev_cap + 1) / 2;
+        for (int i = 0; i < n_ev; ++i) { st[i] = ev_t[i]; sn[i] = ev_n[i]; }
+        for (int i = 0; i < L.n_species * NW; ++i) ss[i] = sp_mask[i];
+        ev_t = st; ev_n = sn; sp_mask = ss;
+    }
     if (L.tree_shaped) {   // no reticulation: single-entry frontier, updated in place
-        L.out[j] = msnc_dp_tree<NW>(s_steps, L.n_steps, s_down, L.ev_t + e0, L.ev_n + e0, static_cast<int>(L.ev_off[j + 1] - e0),
-                                    L.species_mask + static_cast<size_t>(j) * L.n_species * NW, root_bit, s_theta, fr_mask, stride);
+        L.out[j] = msnc_dp_tree<NW>(s_steps, L.n_steps, s_down, ev_t, ev_n, n_ev, sp_mask, root_bit, s_theta, fr_mask, stride);
         L.status[j] = JOB_OK;
         return;
     }
     int status;
-    const double v = msnc_dp<NW>(s_steps, L.n_steps, s_down, L.W, L.cap, L.ev_t + e0, L.ev_n + e0,
-                                 static_cast<int>(L.ev_off[j + 1] - e0),
-                                 L.species_mask + static_cast<size_t>(j) * L.n_species * NW, root_bit, s_theta,
+    const double v = msnc_dp<NW>(s_steps, L.n_steps, s_down, L.W, L.cap, ev_t, ev_n, n_ev, sp_mask, root_bit, s_theta,
                                  fr_mask, fr_lp, stride, &status);
     L.out[j] = v;
     L.status[j] = status;
@@ -358,7 +375,17 @@ static int msnc_launch(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_trees, c
     const bool in_smem = per_job * 32 <= smem_limit && !(no_smem && no_smem[0] == '1');
     if (in_smem)
         while (per_job * threads > smem_limit) threads /= 2;
-    const size_t dyn_smem = program_bytes + (in_smem ? per_job * threads : 0);
+    // per-thread staging of events + species masks: taken when it fits next to the frontiers without shrinking the block
+    int max_ev = 0;
+    for (int64_t j = 0; j < n_trees; ++j) max_ev = std::max<int>(max_ev, static_cast<int>(ev_off[j + 1] - ev_off[j]));
+    int stage_ev_cap = max_ev | 1;                                     // odd: neighbouring threads start on different banks
+    size_t stage_words = static_cast<size_t>(stage_ev_cap) + (stage_ev_cap + 1) / 2 + static_cast<size_t>(n_species) * NW;
+    stage_words |= 1;
+    const size_t fr_bytes = in_smem ? per_job * threads : 0;
+    const bool stage = max_ev > 0 && !(getenv("PNB_MSNC_NO_STAGE") && getenv("PNB_MSNC_NO_STAGE")[0] == '1') &&
+                       fr_bytes + stage_words * 8 * threads <= smem_limit;
+    if (!stage) stage_words = 0;
+    const size_t dyn_smem = program_bytes + fr_bytes + stage_words * 8 * threads;
     // jobs per launch: bounded scratch (the frontiers of a batch may not fit at once)
     size_t scratch_budget = size_t{2} << 30;
     if (const char* mb = getenv("PNB_MSNC_SCRATCH_MB")) {   // test knob: small budgets exercise the multi-launch path
@@ -395,6 +422,8 @@ static int msnc_launch(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_trees, c
     L.tree_shaped = prog.retic_step.empty() ? 1 : 0;
     L.n_down = static_cast<int32_t>(prog.down_slot.size());
     L.program_words = static_cast<int32_t>(program_bytes / 8);
+    L.stage_words = static_cast<int32_t>(stage_words);
+    L.stage_ev_cap = stage_ev_cap;
     L.fr_mask = in_smem ? nullptr : static_cast<uint64_t*>(ctx->m_scratch.p);
     L.fr_lp = in_smem ? nullptr : reinterpret_cast<double*>(static_cast<char*>(ctx->m_scratch.p) + off_lp);
     int64_t launches = 0;
@@ -426,7 +455,7 @@ static int msnc_launch(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_trees, c
     ctx->msnc_stats[3] = launches;
     ctx->msnc_stats[4] = static_cast<int64_t>(stage_bytes);
     ctx->msnc_stats[5] = static_cast<int64_t>(off_status + static_cast<size_t>(n_trees) * sizeof(int32_t));
-    ctx->msnc_stats[6] = in_smem ? static_cast<int64_t>(dyn_smem - program_bytes) : 0;   // bytes of shared memory per block holding frontiers
+    ctx->msnc_stats[6] = static_cast<int64_t>(fr_bytes);   // bytes of shared memory per block holding frontiers
     ctx->msnc_stats[7] = threads;
     return PNB_OK;
 }
