@@ -303,7 +303,7 @@ extern "C" int pnb_batch_create(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb
     if ((rc = ensure_device(b->d_ops, n_ops_alloc * sizeof(Op))) || (rc = ensure_device(b->d_node_of_op, n_ops_alloc * sizeof(int32_t))) ||
         (rc = ensure_device(b->d_P, n_ops_alloc * 128)) || (rc = ensure_device(b->d_jobs, static_cast<size_t>(M) * sizeof(JobDesc))) ||
         (rc = ensure_device(b->d_tile_job, h_tile_job.size() * sizeof(int32_t))) ||
-        (rc = ensure_device(b->d_tile_sum, h_tile_job.size() * sizeof(double))) ||
+        (rc = ensure_device(b->d_tile_sum, 2 * h_tile_job.size() * sizeof(double))) ||
         (rc = ensure_device(b->d_job_done, static_cast<size_t>(M) * sizeof(unsigned))) ||
         (rc = ensure_device(b->d_out, static_cast<size_t>(M) * sizeof(double))) ||
         (rc = ensure_device(b->d_blen, static_cast<size_t>(b->total_nodes) * sizeof(double))) ||

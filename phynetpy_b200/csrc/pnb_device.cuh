@@ -89,13 +89,16 @@ struct PruneLaunch {
     const int32_t* tile_job;   // tile -> job (batch index), -1 for tiles of jobs served from the cache
     const double* Pm;          // batch P matrices [total_ops][16]
     const double* t;           // FUSED launches: effective branch length per op (P(t) is computed in-kernel)
-    double* tile_sum;          // [n_tiles]
+    double* tile_sum;          // [n_tiles][2]: one sum per HALF tile (patterns u < PPT/2, u >= PPT/2 of every thread)
     unsigned int* job_done;    // [batch jobs] arrival counters (self-resetting)
     double* out;               // per-job logL
     int32_t ops_cap;           // smem capacity in ops
     int32_t rows_cap;          // smem capacity in staged code rows
     int32_t stk_cap;           // smem stash entries
     int32_t tile_base;         // first tile of this launch (a batch may be launched in chunks)
+    int32_t n_full;            // blocks [0, n_full) take one whole tile each; every later PAIR of blocks shares one tile,
+                               // half of its patterns each (the last, partial wave of a launch runs as twice as many
+                               // blocks of half the duration; launch_prune decides)
     // fused collective (multi-GPU resident batches): the block that completes a job also stores its logL into the
     // same slot of every peer's vector -- peer-mapped device pointers (NVLink / NVSwitch), 8 bytes per peer and job
     int32_t n_peers;
@@ -297,9 +300,9 @@ __device__ __forceinline__ void lds_op(uint32_t a, uint32_t& f, int32_t& src, in
 // accumulation runs over columns, r_i = ((P_i0 l_0 + P_i1 l_1) + P_i2 l_2) + P_i3 l_3 -- the same expression
 // and rounding as a row-wise dot product.  ACCUM = multiply the result into `out` instead of overwriting it;
 // `out` may alias `l` only when !ACCUM (the register-forwarded child).
-template <bool ACCUM>
-__device__ __forceinline__ void matvec(uint32_t pk, const Vec4 (&l)[PPT], Vec4 (&out)[PPT]) {
-    double r[PPT][4];
+template <bool ACCUM, int NP>
+__device__ __forceinline__ void matvec(uint32_t pk, const Vec4 (&l)[NP], Vec4 (&out)[NP]) {
+    double r[NP][4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         double c0, c1, c2, c3;
@@ -308,7 +311,7 @@ __device__ __forceinline__ void matvec(uint32_t pk, const Vec4 (&l)[PPT], Vec4 (
         else if (j == 2) { lds_v2f64<64>(pk, c0, c1); lds_v2f64<80>(pk, c2, c3); }
         else { lds_v2f64<96>(pk, c0, c1); lds_v2f64<112>(pk, c2, c3); }
 #pragma unroll
-        for (int u = 0; u < PPT; ++u) {
+        for (int u = 0; u < NP; ++u) {
             const double lj = (j == 0) ? l[u].x0 : (j == 1) ? l[u].x1 : (j == 2) ? l[u].x2 : l[u].x3;
             if (j == 0) {
                 r[u][0] = c0 * lj; r[u][1] = c1 * lj; r[u][2] = c2 * lj; r[u][3] = c3 * lj;
@@ -319,7 +322,7 @@ __device__ __forceinline__ void matvec(uint32_t pk, const Vec4 (&l)[PPT], Vec4 (
         }
     }
 #pragma unroll
-    for (int u = 0; u < PPT; ++u) {
+    for (int u = 0; u < NP; ++u) {
         if (ACCUM) {
             out[u].x0 *= r[u][0]; out[u].x1 *= r[u][1]; out[u].x2 *= r[u][2]; out[u].x3 *= r[u][3];
         } else {
@@ -331,14 +334,14 @@ __device__ __forceinline__ void matvec(uint32_t pk, const Vec4 (&l)[PPT], Vec4 (
 // contribution of a tip child: column(s) of P selected by the device tip code
 //   code < 4        : the single state j = code           -> column j of P
 //   code & 0x80     : ambiguity / gap, low 4 bits = mask   -> sum of the allowed columns, in state order
-template <bool ACCUM>
-__device__ __forceinline__ void tip_contrib(uint32_t pk, const uint32_t (&code)[PPT], Vec4 (&out)[PPT]) {
+template <bool ACCUM, int NP>
+__device__ __forceinline__ void tip_contrib(uint32_t pk, const uint32_t (&code)[NP], Vec4 (&out)[NP]) {
     bool amb = false;
 #pragma unroll
-    for (int u = 0; u < PPT; ++u) amb |= (code[u] & 0x80u) != 0;
+    for (int u = 0; u < NP; ++u) amb |= (code[u] & 0x80u) != 0;
     if (!__any_sync(0xffffffffu, amb)) {
 #pragma unroll
-        for (int u = 0; u < PPT; ++u) {
+        for (int u = 0; u < NP; ++u) {
             const uint32_t col = pk + code[u] * 32u;   // column `state` of P: 32 contiguous bytes
             double v0, v1, v2, v3;
             lds_v2f64<0>(col, v0, v1);
@@ -348,7 +351,7 @@ __device__ __forceinline__ void tip_contrib(uint32_t pk, const uint32_t (&code)[
         }
     } else {
 #pragma unroll
-        for (int u = 0; u < PPT; ++u) {
+        for (int u = 0; u < NP; ++u) {
             const uint32_t m = (code[u] & 0x80u) ? (code[u] & 0xFu) : (1u << code[u]);
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
@@ -370,9 +373,12 @@ __device__ __forceinline__ void tip_contrib(uint32_t pk, const uint32_t (&code)[
 // RESCALE = optional numerical mode beyond the reference: every completed node is renormalised by an
 // exact power of two and carries the binary exponent of its subtree, so trees of thousands of taxa do
 // not underflow (the reference, and the default mode here, floor such sites at 1e-300).
-template <bool FUSED, bool RESCALE>
-__global__ void __launch_bounds__(TPB, PRUNE_MIN_BLOCKS)
-pnb_prune_kernel_t(const __grid_constant__ PruneLaunch L, const __grid_constant__ ModelParams mp) {
+// One block = NP patterns per thread of one tile: NP = PPT (u0 = 0) is a whole tile, NP = PPT / 2 one half of it
+// (u0 = 0 or PPT / 2: the thread's patterns tid + (u0 + u) TPB).  Either way a thread's weighted log-likelihoods are
+// summed per HALF (u < PPT / 2, u >= PPT / 2) and every half is reduced over the block on its own, so a tile gives the
+// same two sums whether one block or two computed it -- results never depend on how a launch was cut into blocks.
+template <bool FUSED, bool RESCALE, int NP>
+__device__ __forceinline__ void prune_tile(const PruneLaunch& L, const ModelParams& mp, const int tile, const int u0) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar_stage;
     __shared__ double red[TPB / 32];
@@ -380,7 +386,6 @@ pnb_prune_kernel_t(const __grid_constant__ PruneLaunch L, const __grid_constant_
     __shared__ int s_rows;
 
     const int tid = threadIdx.x;
-    const int tile = blockIdx.x + L.tile_base;
     const int job = L.tile_job[tile];
     if (job < 0) return;  // tile of a job that needed no device work (served from the cache)
     const JobDesc& jd = L.jobs[job];
@@ -409,21 +414,22 @@ pnb_prune_kernel_t(const __grid_constant__ PruneLaunch L, const __grid_constant_
     // partial slots zero-filled), so lanes past the last pattern run the same instruction stream on
     // padding and only the final weighted sum looks at the pattern index.
     const int64_t slot_stride = jd.slot_stride;
-    double* part0 = jd.partials + static_cast<int64_t>(p0 + tid) * 4;
-    const bool warp_active = __any_sync(0xffffffffu, (p0 + tid) < P);
+    const int pu0 = p0 + u0 * TPB;   // the block's first pattern
+    double* part0 = jd.partials + static_cast<int64_t>(pu0 + tid) * 4;
+    const bool warp_active = __any_sync(0xffffffffu, (pu0 + tid) < P);
     const uint32_t ops_base = smem_u32(s_ops);
     const uint32_t p_base = smem_u32(s_P);
-    const uint32_t codes_addr = smem_u32(s_codes) + tid;
-    const uint32_t stk_addr = smem_u32(s_stk) + tid * 16;
+    const uint32_t codes_addr = smem_u32(s_codes) + u0 * TPB + tid;
+    const uint32_t stk_addr = smem_u32(s_stk) + (u0 * TPB + tid) * 16;
 
-    Vec4 acc[PPT];  // node under construction; once complete it is also the register-forwarded child
-    int acc_e[PPT]; // RESCALE: binary exponent carried by `acc` (true partial = acc * 2^acc_e)
+    Vec4 acc[NP];  // node under construction; once complete it is also the register-forwarded child
+    int acc_e[NP]; // RESCALE: binary exponent carried by `acc` (true partial = acc * 2^acc_e)
 #pragma unroll
-    for (int u = 0; u < PPT; ++u) { acc[u] = {1.0, 1.0, 1.0, 1.0}; acc_e[u] = 0; }
-    int32_t* scale0 = RESCALE ? jd.scale + (p0 + tid) : nullptr;
+    for (int u = 0; u < NP; ++u) { acc[u] = {1.0, 1.0, 1.0, 1.0}; acc_e[u] = 0; }
+    int32_t* scale0 = RESCALE ? jd.scale + (pu0 + tid) : nullptr;
     const int64_t scale_stride = slot_stride / 4;  // ints per slot (= P_pad)
     // stash exponents live behind the stash partials: [stk_cap][TILE_PATTERNS] int32
-    const uint32_t stk_e_addr = smem_u32(s_stk) + static_cast<uint32_t>(L.stk_cap) * (TILE_PATTERNS * 32) + tid * 4;
+    const uint32_t stk_e_addr = smem_u32(s_stk) + static_cast<uint32_t>(L.stk_cap) * (TILE_PATTERNS * 32) + (u0 * TPB + tid) * 4;
 
     // The program is walked in segments of at most SEG_MAX_OPS ops (one segment for trees of up to
     // ~97 taxa): warp 0 is the TMA producer of a segment -- its ops, its P matrices and the code rows
@@ -446,14 +452,14 @@ pnb_prune_kernel_t(const __grid_constant__ PruneLaunch L, const __grid_constant_
 #pragma unroll
                     for (int j = 0; j < 4; ++j) s_P[k * 16 + j * 4 + i] = Pm[i * 4 + j];   // transposed, as K-a writes it
                 if ((op.flags & F_KIND_MASK) == K_TIP && op.src >= 0) {
-                    tma_bulk_g2s(s_codes + static_cast<size_t>(op.aux) * TILE_PATTERNS,
-                                 g_codes + static_cast<int64_t>(op.src) * ld_codes + p0, TILE_PATTERNS, &bar_stage);
+                    tma_bulk_g2s(s_codes + static_cast<size_t>(op.aux) * TILE_PATTERNS + u0 * TPB,
+                                 g_codes + static_cast<int64_t>(op.src) * ld_codes + pu0, NP * TPB, &bar_stage);
                     ++my_rows;
                 }
             }
             if (my_rows) atomicAdd(&s_rows, my_rows);
             __syncthreads();
-            if (tid == 0) mbar_arrive_expect_tx(&bar_stage, static_cast<uint32_t>(s_rows) * TILE_PATTERNS);
+            if (tid == 0) mbar_arrive_expect_tx(&bar_stage, static_cast<uint32_t>(s_rows) * (NP * TPB));
         } else {
         if (seg > 0) __syncthreads();  // every warp is done with the previous segment's shared memory
         if (tid < 32) {
@@ -466,8 +472,8 @@ pnb_prune_kernel_t(const __grid_constant__ PruneLaunch L, const __grid_constant_
             for (int k = tid; k < nseg; k += 32) {
                 const Op op = g_ops[seg + k];
                 if ((op.flags & F_KIND_MASK) == K_TIP && op.src >= 0) {
-                    tma_bulk_g2s(s_codes + static_cast<size_t>(op.aux) * TILE_PATTERNS,
-                                 g_codes + static_cast<int64_t>(op.src) * ld_codes + p0, TILE_PATTERNS, &bar_stage);
+                    tma_bulk_g2s(s_codes + static_cast<size_t>(op.aux) * TILE_PATTERNS + u0 * TPB,
+                                 g_codes + static_cast<int64_t>(op.src) * ld_codes + pu0, NP * TPB, &bar_stage);
                     ++my_rows;
                 }
             }
@@ -475,7 +481,7 @@ pnb_prune_kernel_t(const __grid_constant__ PruneLaunch L, const __grid_constant_
             // the pending arrival keeps the phase open until the byte count has been announced
             if (tid == 0)
                 mbar_arrive_expect_tx(&bar_stage, static_cast<uint32_t>(nseg) * (sizeof(Op) + 128u) +
-                                                      static_cast<uint32_t>(rows) * TILE_PATTERNS);
+                                                      static_cast<uint32_t>(rows) * (NP * TPB));
         }
         }
         mbar_wait(&bar_stage, phase);
@@ -509,57 +515,57 @@ pnb_prune_kernel_t(const __grid_constant__ PruneLaunch L, const __grid_constant_
             const uint32_t kind = flags & F_KIND_MASK;
             const bool first = (flags & F_FIRST) != 0;
             if (kind == K_TIP) {
-                uint32_t code[PPT];
+                uint32_t code[NP];
 #pragma unroll
-                for (int u = 0; u < PPT; ++u)
+                for (int u = 0; u < NP; ++u)
                     code[u] = (src >= 0) ? lds_u8(codes_addr + aux * TILE_PATTERNS + u * TPB) : 0x8Fu;
-                if (first) tip_contrib<false>(pk, code, acc);
-                else tip_contrib<true>(pk, code, acc);
+                if (first) tip_contrib<false, NP>(pk, code, acc);
+                else tip_contrib<true, NP>(pk, code, acc);
                 if (RESCALE && first) {
 #pragma unroll
-                    for (int u = 0; u < PPT; ++u) acc_e[u] = 0;
+                    for (int u = 0; u < NP; ++u) acc_e[u] = 0;
                 }
             } else if (kind == K_REG) {
                 // the child is the node completed just before: its partial is still in `acc`
                 // (the host always emits the forwarded child as the FIRST op of its parent)
-                matvec<false>(pk, acc, acc);   // reads acc completely before it writes it
+                matvec<false, NP>(pk, acc, acc);   // reads acc completely before it writes it
             } else {
-                Vec4 l[PPT];
-                int le[PPT];
+                Vec4 l[NP];
+                int le[NP];
                 if (kind == K_MEM) {
                     const double* g = part0 + static_cast<int64_t>(src) * slot_stride;
 #pragma unroll
-                    for (int u = 0; u < PPT; ++u) ldg256(g + u * TPB * 4, l[u].x0, l[u].x1, l[u].x2, l[u].x3);
+                    for (int u = 0; u < NP; ++u) ldg256(g + u * TPB * 4, l[u].x0, l[u].x1, l[u].x2, l[u].x3);
                     if (RESCALE) {
                         const int32_t* ge = scale0 + static_cast<int64_t>(src) * scale_stride;
 #pragma unroll
-                        for (int u = 0; u < PPT; ++u) le[u] = ge[u * TPB];
+                        for (int u = 0; u < NP; ++u) le[u] = ge[u * TPB];
                     }
                 } else {
                     const uint32_t a = stk_addr + static_cast<uint32_t>(src) * (TILE_PATTERNS * 32);
 #pragma unroll
-                    for (int u = 0; u < PPT; ++u) {
+                    for (int u = 0; u < NP; ++u) {
                         lds_v2f64<0>(a + u * TPB * 16, l[u].x0, l[u].x1);
                         lds_v2f64<TILE_PATTERNS * 16>(a + u * TPB * 16, l[u].x2, l[u].x3);
                     }
                     if (RESCALE) {
                         const uint32_t ae = stk_e_addr + static_cast<uint32_t>(src) * (TILE_PATTERNS * 4);
 #pragma unroll
-                        for (int u = 0; u < PPT; ++u)
+                        for (int u = 0; u < NP; ++u)
                             asm volatile("ld.shared.s32 %0, [%1];" : "=r"(le[u]) : "r"(ae + u * TPB * 4));
                     }
                 }
-                if (first) matvec<false>(pk, l, acc);
-                else matvec<true>(pk, l, acc);
+                if (first) matvec<false, NP>(pk, l, acc);
+                else matvec<true, NP>(pk, l, acc);
                 if (RESCALE) {
 #pragma unroll
-                    for (int u = 0; u < PPT; ++u) acc_e[u] = first ? le[u] : acc_e[u] + le[u];
+                    for (int u = 0; u < NP; ++u) acc_e[u] = first ? le[u] : acc_e[u] + le[u];
                 }
             }
             if (flags & F_LAST) {
                 if (RESCALE) {
 #pragma unroll
-                    for (int u = 0; u < PPT; ++u) {
+                    for (int u = 0; u < NP; ++u) {
                         const double mx = fmax(fmax(acc[u].x0, acc[u].x1), fmax(acc[u].x2, acc[u].x3));
                         if (mx > 0.0) {  // exact renormalisation by 2^-e, e = binary exponent of the largest state
                             const int e = ((__double2hiint(mx) >> 20) & 0x7ff) - 1023;
@@ -572,25 +578,25 @@ pnb_prune_kernel_t(const __grid_constant__ PruneLaunch L, const __grid_constant_
                 if (flags & F_STORE) {
                     double* g = part0 + static_cast<int64_t>(dst) * slot_stride;
 #pragma unroll
-                    for (int u = 0; u < PPT; ++u)
+                    for (int u = 0; u < NP; ++u)
                         stg256(g + u * TPB * 4, acc[u].x0, acc[u].x1, acc[u].x2, acc[u].x3);
                     if (RESCALE) {
                         int32_t* ge = scale0 + static_cast<int64_t>(dst) * scale_stride;
 #pragma unroll
-                        for (int u = 0; u < PPT; ++u) ge[u * TPB] = acc_e[u];
+                        for (int u = 0; u < NP; ++u) ge[u * TPB] = acc_e[u];
                     }
                 }
                 if (flags & F_PUSH) {
                     const uint32_t a = stk_addr + ((flags >> 8) & 0xffu) * (TILE_PATTERNS * 32);
 #pragma unroll
-                    for (int u = 0; u < PPT; ++u) {
+                    for (int u = 0; u < NP; ++u) {
                         sts_v2f64(a + u * TPB * 16, acc[u].x0, acc[u].x1);
                         sts_v2f64(a + u * TPB * 16 + TILE_PATTERNS * 16, acc[u].x2, acc[u].x3);
                     }
                     if (RESCALE) {
                         const uint32_t ae = stk_e_addr + ((flags >> 8) & 0xffu) * (TILE_PATTERNS * 4);
 #pragma unroll
-                        for (int u = 0; u < PPT; ++u)
+                        for (int u = 0; u < NP; ++u)
                             asm volatile("st.shared.s32 [%0], %1;" :: "r"(ae + u * TPB * 4), "r"(acc_e[u]) : "memory");
                     }
                 }
@@ -599,13 +605,17 @@ pnb_prune_kernel_t(const __grid_constant__ PruneLaunch L, const __grid_constant_
     }
 
     // root: site likelihood, clamp, log, weight  (reference :394-397)
-    double lsum = 0.0;
+    constexpr int HALF = (PPT % 2 == 0) ? PPT / 2 : PPT;   // patterns per thread and half tile
+    constexpr int NH = NP / HALF;                          // halves this block computes (2: a whole tile, 1: one half)
+    double lsum[NH];
+#pragma unroll
+    for (int h = 0; h < NH; ++h) lsum[h] = 0.0;
     const int root_kind = jd.root_kind;
     const int root_src = jd.root_src;
     const double* weights = jd.weights;
 #pragma unroll
-    for (int u = 0; u < PPT; ++u) {
-        const int pat = p0 + tid + u * TPB;
+    for (int u = 0; u < NP; ++u) {
+        const int pat = pu0 + tid + u * TPB;
         if (pat >= P) continue;
         Vec4 r = acc[u];
         int re = RESCALE ? acc_e[u] : 0;
@@ -623,34 +633,53 @@ pnb_prune_kernel_t(const __grid_constant__ PruneLaunch L, const __grid_constant_
             // log(site * 2^re); a site that is exactly impossible keeps the reference's floor
             const double ls = (site > 0.0) ? fma(static_cast<double>(re), 0.6931471805599453094, log(site))
                                            : ((site == 0.0) ? -690.77552789821370 : site);
-            lsum = fma(ls, weights[pat], lsum);
+            lsum[u / HALF] = fma(ls, weights[pat], lsum[u / HALF]);
         } else {
             site = (site < 1e-300) ? 1e-300 : site;  // np.maximum(site_like, 1e-300): NaN propagates
-            lsum = fma(log(site), weights[pat], lsum);
+            lsum[u / HALF] = fma(log(site), weights[pat], lsum[u / HALF]);
         }
     }
 
     // fused per-locus reduction: tile sum -> last-arriving tile sums tiles in index order.  (One fence + one ticket per
     // BLOCK: a per-warp version without the block barriers measured 7% slower -- __threadfence invalidates L1.)
-    const double tsum = block_sum(lsum, red);
+    double tsum[NH];
+#pragma unroll
+    for (int h = 0; h < NH; ++h) tsum[h] = block_sum(lsum[h], red);
     const int n_tiles = jd.n_tiles;
+    constexpr int HALVES_PER_TILE = PPT / HALF;   // 2 (1 when PPT is odd: tiles are never split)
     if (tid == 0) {
-        __stcg(&L.tile_sum[tile], tsum);
+#pragma unroll
+        for (int h = 0; h < NH; ++h) __stcg(&L.tile_sum[2 * static_cast<int64_t>(tile) + u0 / HALF + h], tsum[h]);
+        if (HALVES_PER_TILE == 1) __stcg(&L.tile_sum[2 * static_cast<int64_t>(tile) + 1], 0.0);
         __threadfence();
-        const unsigned int prev = atomicAdd(&L.job_done[job], 1u);
-        s_is_last = (prev == static_cast<unsigned int>(n_tiles) - 1u);
+        const unsigned int prev = atomicAdd(&L.job_done[job], static_cast<unsigned int>(NH));
+        s_is_last = (prev + NH == static_cast<unsigned int>(n_tiles) * HALVES_PER_TILE);
     }
     __syncthreads();
     if (s_is_last) {
         __threadfence();
         double s = 0.0;
-        for (int t = tid; t < n_tiles; t += TPB) s += __ldcg(&L.tile_sum[tile0 + t]);
+        for (int t = tid; t < n_tiles; t += TPB)   // a tile's two halves first, tiles in index order
+            s += __ldcg(&L.tile_sum[2 * static_cast<int64_t>(tile0 + t)]) + __ldcg(&L.tile_sum[2 * static_cast<int64_t>(tile0 + t) + 1]);
         const double total = block_sum(s, red);
         if (tid == 0) {
             L.out[jd.out_index] = total;
             for (int r = 0; r < L.n_peers; ++r) L.peer_out[r][jd.out_index] = total;   // stores over NVLink into the peers' vectors
             L.job_done[job] = 0u;
         }
+    }
+}
+
+template <bool FUSED, bool RESCALE>
+__global__ void __launch_bounds__(TPB, PRUNE_MIN_BLOCKS)
+pnb_prune_kernel_t(const __grid_constant__ PruneLaunch L, const __grid_constant__ ModelParams mp) {
+    const int b = blockIdx.x;
+    if (PPT % 2 != 0 || b < L.n_full) {
+        prune_tile<FUSED, RESCALE, PPT>(L, mp, L.tile_base + b, 0);
+    } else {
+        constexpr int HALF = (PPT % 2 == 0) ? PPT / 2 : PPT;
+        const int h = b - L.n_full;
+        prune_tile<FUSED, RESCALE, HALF>(L, mp, L.tile_base + L.n_full + (h >> 1), (h & 1) * HALF);
     }
 }
 

@@ -36,9 +36,59 @@ int pnb::launch_pmatrix_gather(const ModelParams& mp, const double* d_blen, cons
     return PNB_OK;
 }
 
-int pnb::launch_prune(const PruneLaunch& L, const ModelParams& mp, unsigned grid, size_t dyn_smem, bool rescale,
+// How a launch of n_tiles tiles is cut into blocks.  Blocks are dispatched in index order onto `slots` = SMs x resident
+// blocks per SM; all tiles of a launch cost about the same, so the last, partial wave of whole-tile blocks leaves
+// (slots - rem) block slots idle for a full tile time -- 6 % of an 8.45-wave launch (cfg5 on 8 GPUs).  When that wave
+// is at most half full its tiles are computed by two blocks each (half the patterns per thread, half the duration):
+// twice the blocks still fit in one wave, which then ends in half the time.  A launch smaller than half a wave (a
+// single-locus MCMC step: one or two tiles) is all half tiles -- two SMs share the latency of every tile.
+// PNB_SPLIT_TAIL=0 switches the split off (every block a whole tile); the results are the same bits either way.
+static void split_tail(unsigned n_tiles, size_t dyn_smem, bool fused, bool rescale, int32_t* n_full, unsigned* grid) {
+    static int slots_cache[4] = {0, 0, 0, 0};
+    static size_t smem_cache[4] = {~size_t{0}, ~size_t{0}, ~size_t{0}, ~size_t{0}};
+    static int sm_count = 0;
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char* e = getenv("PNB_SPLIT_TAIL");
+        enabled = (PPT % 2 == 0 && !(e && e[0] == '0')) ? 1 : 0;
+    }
+    *n_full = static_cast<int32_t>(n_tiles);
+    *grid = n_tiles;
+    if (!enabled || n_tiles == 0) return;
+    const int v = (fused ? 2 : 0) + (rescale ? 1 : 0);
+    if (smem_cache[v] != dyn_smem) {
+        int per_sm = 0;
+        cudaError_t e;
+        if (v == 0) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pnb_prune_kernel_t<false, false>, TPB, dyn_smem);
+        else if (v == 1) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pnb_prune_kernel_t<false, true>, TPB, dyn_smem);
+        else if (v == 2) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pnb_prune_kernel_t<true, false>, TPB, dyn_smem);
+        else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pnb_prune_kernel_t<true, true>, TPB, dyn_smem);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); return; }
+        if (sm_count == 0) {
+            int dev = 0;
+            if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+                (void)cudaGetLastError();
+                sm_count = 0;
+                return;
+            }
+        }
+        slots_cache[v] = per_sm * sm_count;
+        smem_cache[v] = dyn_smem;
+    }
+    const unsigned slots = static_cast<unsigned>(slots_cache[v]);
+    if (slots < 2) return;
+    const unsigned rem = n_tiles % slots;
+    if (rem == 0 || 2 * rem > slots) return;
+    *n_full = static_cast<int32_t>(n_tiles - rem);
+    *grid = n_tiles + rem;
+}
+
+int pnb::launch_prune(const PruneLaunch& L_in, const ModelParams& mp, unsigned n_tiles, size_t dyn_smem, bool rescale,
                       cudaStream_t st) {
-    if (grid == 0) return PNB_OK;
+    if (n_tiles == 0) return PNB_OK;
+    PruneLaunch L = L_in;
+    unsigned grid;
+    split_tail(n_tiles, dyn_smem, false, rescale, &L.n_full, &grid);
     if (rescale) pnb_prune_kernel_t<false, true><<<grid, TPB, dyn_smem, st>>>(L, mp);
     else pnb_prune_kernel_t<false, false><<<grid, TPB, dyn_smem, st>>>(L, mp);
     PNB_CUDA_TRY(cudaGetLastError());
@@ -322,7 +372,7 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
     // ~1,000 jobs per chunk: below that the extra launches / events cost more than the overlap gains
     const int64_t n_chunks = std::max<int64_t>(1, std::min<int64_t>(8, M / ctx->chunk_min_jobs));
     if ((rc = ensure_device(ctx->d_P, static_cast<size_t>(std::max<int64_t>(ops_bound, 1)) * 128))) return rc;
-    if ((rc = ensure_device(ctx->d_tile_sum, static_cast<size_t>(std::max<int64_t>(total_tiles, 1)) * sizeof(double)))) return rc;
+    if ((rc = ensure_device(ctx->d_tile_sum, 2 * static_cast<size_t>(std::max<int64_t>(total_tiles, 1)) * sizeof(double)))) return rc;
     if ((rc = ensure_device(ctx->d_out, static_cast<size_t>(M) * sizeof(double)))) return rc;
     if (ctx->d_job_done.cap < static_cast<size_t>(M) * sizeof(unsigned)) {
         PNB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -522,7 +572,8 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
             memset_done = true;
         }
         if (ctx->profiling && c == 0) PNB_CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
-        const unsigned grid = static_cast<unsigned>(ct);
+        unsigned grid;
+        split_tail(static_cast<unsigned>(ct), dyn_smem, fused, rescale, &L.n_full, &grid);
         if (fused) {
             if (rescale) pnb_prune_kernel_t<true, true><<<grid, TPB, dyn_smem, st>>>(L, m->mp);
             else pnb_prune_kernel_t<true, false><<<grid, TPB, dyn_smem, st>>>(L, m->mp);

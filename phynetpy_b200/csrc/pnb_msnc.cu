@@ -52,9 +52,353 @@ struct MsncLaunch {
     int32_t stage_words;            // > 0: every thread copies its gene tree's events and species masks into this many
                                     // 8-byte words of shared memory (after the frontiers) before the DP
     int32_t stage_ev_cap;           // events per tree the staging area holds
+    int32_t warp_tsize;             // warp kernel: slots of the duplicate-detection table (power of two >= 2 cap)
+    int64_t warp_job_words;         // warp kernel: 8-byte words of frontier storage per job (msnc_warp_words)
 };
 
-template <int NW>
+// ------------------------------------------------------------------------------------------------------------
+// One WARP per gene tree (reticulate networks).  The DP of pnb_msnc_core.hpp::msnc_dp is a loop over network
+// nodes; at each node every frontier entry -- and, at a reticulation, every subset of the lineages that reach it
+// -- produces one candidate entry, independently of the others.  Here the candidates of a step are spread over
+// the 32 lanes, then merged exactly as the serial DP merges them:
+//   A  (reticulation) lanes count the subsets of each entry, a warp scan turns the counts into candidate offsets;
+//   B  lane t builds candidate t = (entry k, r-th subset in decreasing order): branch factor(s), new lineage
+//      sets, incremental hash, log-weight -- written as entry t of the other frontier buffer;
+//   C  equal candidates are found through an open-addressing table keyed by the entry hash (atomicCAS claims a
+//      slot for a class of equal entries, atomicMin leaves the FIRST candidate of the class in it);
+//   D  the log-weights of later duplicates are folded into the first one in candidate order (one leader lane per
+//      class, log-sum-exp in the order the serial DP would have met them), then the first occurrences are
+//      compacted in place, in order.
+// Entry order, merge order and every floating-point operation are those of msnc_dp, so the two kernels return the
+// same bits (tests/test_gpu_msnc.py::test_warp_and_thread_kernels_agree); what changes is that a frontier of T
+// candidates costs T / 32 rounds instead of T, and that a batch fills the SMs with 32x more threads.
+// Frontier layout (per job, word-major so that consecutive lanes touch consecutive words):
+//   mask[2][W NW][cap] | hash[2][cap] | lp[2][cap] | idx int32[cap + 1] | dup int32[cap] | table int32[tsize]
+// ------------------------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t msnc_warp_words(int W, int NW, int cap, int tsize) {
+    const size_t c = static_cast<size_t>(cap);
+    return 2 * c * (static_cast<size_t>(W) * NW + 2) + ((c + 2) & ~size_t{1}) / 2 + ((c + 1) & ~size_t{1}) / 2 +
+           static_cast<size_t>(tsize) / 2;
+}
+
+template <int NW, bool SMEM>
+__device__ double msnc_dp_warp(const Step* steps, int n_steps, const int32_t* down_slot, int W, int cap, const double* ev_t,
+                               const uint32_t* ev_n, int n_ev, const uint64_t* species_mask, int root_bit,
+                               const double* step_theta, uint64_t* buf, int* status) {
+    constexpr unsigned FULL = 0xffffffffu;
+    __builtin_assume(__isShared(steps));
+    __builtin_assume(__isShared(down_slot));
+    __builtin_assume(__isShared(step_theta));
+    if (SMEM) {   // everything the DP touches is in shared memory: 32-bit addresses, LDS / STS / ATOMS instead of generic accesses
+        __builtin_assume(__isShared(buf));
+        __builtin_assume(__isShared(ev_t));
+        __builtin_assume(__isShared(ev_n));
+        __builtin_assume(__isShared(species_mask));
+    }
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const uint32_t entry = static_cast<uint32_t>(W) * NW, ucap = static_cast<uint32_t>(cap);
+    // the two frontiers are word offsets into `buf`, swapped after every step (offsets, not pointers: every access stays
+    // visibly relative to the one base pointer, which is what lets the SMEM variant use shared-memory instructions)
+    double* const bufd = reinterpret_cast<double*>(buf);
+    uint32_t m_cur = 0, m_new = entry * ucap;
+    uint32_t h_cur = 2 * entry * ucap, h_new = h_cur + ucap;
+    uint32_t l_cur = h_new + ucap, l_new = l_cur + ucap;
+    int32_t* idx = reinterpret_cast<int32_t*>(buf + (l_new + ucap));
+    int32_t* dup = idx + ((ucap + 2) & ~1u);
+    int32_t* table = dup + ((ucap + 1) & ~1u);
+
+    if (lane == 0) {
+        for (uint32_t i = 0; i < entry; ++i) buf[m_cur + (i) * ucap] = 0;
+        buf[h_cur + 0] = 0;
+        bufd[l_cur + 0] = 0.0;
+    }
+    __syncwarp();
+    uint32_t n_cur = 1;
+    int root_slot = 0;
+    *status = JOB_OK;
+
+    for (int s = 0; s < n_steps; ++s) {
+        const Step& st = steps[s];
+        const int kind = st.kind, species = st.species, n_down = st.n_down, down_off = st.down_off;
+        const int up0 = st.up_slot[0], up1 = st.up_slot[1];
+        const bool is_root = (kind & KIND_ROOT) != 0, is_retic = (kind & KIND_RETIC) != 0, is_leaf = (kind & KIND_LEAF) != 0;
+        const double tau_low = st.tau_low, tau_h0 = st.tau_high[0], tau_h1 = st.tau_high[1];
+        const double inv_theta0 = step_theta[4 * s], l2t0 = step_theta[4 * s + 1];
+        const double inv_theta1 = step_theta[4 * s + 2], l2t1 = step_theta[4 * s + 3];
+        // events inside this node's parent branch(es): events are sorted by time, so "first index with t >= tau" is the
+        // number of events with t < tau -- one ballot per 32 events instead of a binary search per lane
+        int j_lo = 0, j_hi0 = 0, j_hi1 = 0;
+        for (int base = 0; base < n_ev; base += 32) {
+            const int e = base + lane;
+            const double t = (e < n_ev) ? ev_t[e] : INFINITY;
+            j_lo += __popc(__ballot_sync(FULL, t < tau_low));
+            j_hi0 += __popc(__ballot_sync(FULL, t < tau_h0));
+            j_hi1 += __popc(__ballot_sync(FULL, t < tau_h1));
+        }
+        if (is_root) j_hi0 = n_ev;
+        if (!is_retic) j_hi1 = j_lo;
+
+        // lineage set reaching the node in entry k; the closed slots leave the hash
+        auto arriving = [&](uint32_t k, uint64_t& h) {
+            Mask<NW> a;
+            a.clear();
+            if (is_leaf) {
+                if (species >= 0)
+                    for (int i = 0; i < NW; ++i) a.w[i] = species_mask[static_cast<size_t>(species) * NW + i];
+            } else {
+                for (int d = 0; d < n_down; ++d) {
+                    const uint32_t slot = static_cast<uint32_t>(down_slot[down_off + d]) * NW;
+                    for (int i = 0; i < NW; ++i) {
+                        const uint64_t w = buf[m_cur + (slot + i) * ucap + k];
+                        a.w[i] |= w;
+                        h ^= slot_hash(slot + i, w);
+                    }
+                }
+            }
+            return a;
+        };
+
+        // ---- A: candidate offsets -------------------------------------------------------------------------
+        uint32_t T = n_cur;
+        if (is_retic) {
+            uint32_t running = 0;
+            for (uint32_t base = 0; base < n_cur; base += 32) {
+                const uint32_t k = base + lane;
+                uint32_t n = 0;
+                if (k < n_cur) {
+                    uint64_t unused = 0;
+                    const int c = arriving(k, unused).count();
+                    n = (c >= 20) ? ucap + 1 : min(1u << c, ucap + 1);
+                }
+                uint32_t incl = n;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t v = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                if (k < n_cur) idx[k] = static_cast<int32_t>(min(running + incl - n, ucap + 1));
+                running = min(running + __shfl_sync(FULL, incl, 31), ucap + 1);
+            }
+            if (lane == 0) idx[n_cur] = static_cast<int32_t>(running);
+            T = running;
+        }
+        if (T > ucap) {
+            *status = JOB_OVERFLOW;
+            return nan("");
+        }
+        __syncwarp();
+
+        // ---- B: one candidate per lane ----------------------------------------------------------------------
+        for (uint32_t t = lane; t < T; t += 32) {
+            uint32_t k = t, r = 0;
+            if (is_retic) {   // the entry whose subsets include candidate t: largest k with idx[k] <= t
+                uint32_t lo = 0, hi = n_cur - 1;
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi + 1) >> 1;
+                    if (static_cast<uint32_t>(idx[mid]) <= t) lo = mid;
+                    else hi = mid - 1;
+                }
+                k = lo;
+                r = t - static_cast<uint32_t>(idx[k]);
+            }
+            const double lp = bufd[l_cur + k];
+            uint64_t h = buf[h_cur + k];
+            Mask<NW> ma = arriving(k, h), mb;
+            mb.clear();
+            double lpn;
+            if (is_retic) {
+                const int n_total = ma.count();
+                uint32_t v = ((1u << n_total) - 1u) - r;   // subsets in decreasing order: the r-th one has rank 2^n - 1 - r
+                Mask<NW> sub;
+                sub.clear();
+                for (int w = 0; w < NW; ++w) {
+                    uint64_t m = ma.w[w];
+                    while (m) {
+                        const uint64_t low = m & (~m + 1);
+                        if (v & 1u) sub.w[w] |= low;
+                        v >>= 1;
+                        m ^= low;
+                    }
+                }
+                const int ks = sub.count();
+                const double factor = add_rn(mul_rn(static_cast<double>(ks), st.log_g[0]),
+                                             mul_rn(static_cast<double>(n_total - ks), st.log_g[1]));
+                for (int i = 0; i < NW; ++i) mb.w[i] = ma.w[i] ^ sub.w[i];
+                ma = sub;
+                double lp1 = 0.0, lp2 = 0.0;
+                if (ks > 1) branch_timed<NW>(ma, lp1, tau_low, tau_h0, true, inv_theta0, l2t0, ev_t, ev_n, j_lo, j_hi0);
+                if (n_total - ks > 1) branch_timed<NW>(mb, lp2, tau_low, tau_h1, true, inv_theta1, l2t1, ev_t, ev_n, j_lo, j_hi1);
+                const uint32_t sa = static_cast<uint32_t>(up0) * NW, sb = static_cast<uint32_t>(up1) * NW;
+                for (int i = 0; i < NW; ++i) h ^= slot_hash(sa + i, ma.w[i]) ^ slot_hash(sb + i, mb.w[i]);
+                lpn = add_rn(add_rn(add_rn(lp, factor), lp1), lp2);   // left to right (src/_msnc_density.py:353)
+            } else {
+                double blp = 0.0;
+                if (ma.count() > 1) branch_timed<NW>(ma, blp, tau_low, tau_h0, !is_root, inv_theta0, l2t0, ev_t, ev_n, j_lo, j_hi0);
+                const uint32_t sa = static_cast<uint32_t>(up0) * NW;
+                for (int i = 0; i < NW; ++i) h ^= slot_hash(sa + i, ma.w[i]);
+                lpn = add_rn(lp, blp);
+            }
+            for (uint32_t i = 0; i < entry; ++i) buf[m_new + (i) * ucap + t] = buf[m_cur + (i) * ucap + k];
+            for (int d = 0; d < n_down; ++d)
+                for (int i = 0; i < NW; ++i) buf[m_new + (down_slot[down_off + d] * NW + i) * ucap + t] = 0;
+            for (int i = 0; i < NW; ++i) buf[m_new + (up0 * NW + i) * ucap + t] = ma.w[i];
+            if (is_retic)
+                for (int i = 0; i < NW; ++i) buf[m_new + (up1 * NW + i) * ucap + t] = mb.w[i];
+            buf[h_new + t] = h;
+            bufd[l_new + t] = lpn;
+        }
+        if (is_root) root_slot = up0;
+        __syncwarp();
+
+        uint32_t n_new = T;
+        if (T > 1) {
+            // ---- C: first occurrence of every candidate ---------------------------------------------------
+            uint32_t ts = 64;
+            while (ts < 2 * T) ts <<= 1;
+            for (uint32_t i = lane; i < ts; i += 32) table[i] = -1;
+            __syncwarp();
+            for (uint32_t t = lane; t < T; t += 32) {
+                const uint64_t h = buf[h_new + t];
+                uint32_t slot = static_cast<uint32_t>(h ^ (h >> 32)) & (ts - 1);
+                for (;;) {
+                    const int old = atomicCAS(&table[slot], -1, static_cast<int>(t));
+                    if (old == -1) break;   // first of its class to arrive: the slot now belongs to the class
+                    bool same = buf[h_new + old] == h;
+                    for (uint32_t i = 0; same && i < entry; ++i)
+                        same = buf[m_new + (i) * ucap + old] == buf[m_new + (i) * ucap + t];
+                    if (same) {
+                        atomicMin(&table[slot], static_cast<int>(t));
+                        break;
+                    }
+                    slot = (slot + 1) & (ts - 1);
+                }
+                idx[t] = static_cast<int32_t>(slot);
+            }
+            __syncwarp();
+            for (uint32_t t = lane; t < T; t += 32) idx[t] = table[idx[t]];
+            __syncwarp();
+            // ---- D: merge duplicates in candidate order, compact the first occurrences -----------------------
+            uint32_t nd = 0;
+            for (uint32_t base = 0; base < T; base += 32) {
+                const uint32_t t = base + lane;
+                const bool isd = t < T && idx[t] != static_cast<int32_t>(t);
+                const unsigned b = __ballot_sync(FULL, isd);
+                if (isd) dup[nd + __popc(b & lt)] = static_cast<int32_t>(t);
+                nd += __popc(b);
+            }
+            if (nd > 0) {
+                __syncwarp();
+                for (uint32_t base = 0; base < nd; base += 32) {
+                    const int d = (base + lane < nd) ? dup[base + lane] : -1;
+                    const int u = (d >= 0) ? idx[d] : -1 - lane;
+                    const unsigned grp = __match_any_sync(FULL, u);
+                    if (d >= 0 && lane == __ffs(grp) - 1) {
+                        double acc = bufd[l_new + u];
+                        for (unsigned m = grp; m; m &= m - 1) acc = log_add(acc, bufd[l_new + dup[base + __ffs(m) - 1]]);
+                        bufd[l_new + u] = acc;
+                    }
+                    __syncwarp();
+                }
+                uint32_t running = 0;
+                for (uint32_t base = 0; base < T; base += 32) {
+                    const uint32_t t = base + lane;
+                    const bool isu = t < T && idx[t] == static_cast<int32_t>(t);
+                    const unsigned b = __ballot_sync(FULL, isu);
+                    const uint32_t pos = running + __popc(b & lt);
+                    {
+                        const uint64_t v = isu ? buf[h_new + t] : 0;
+                        const double l = isu ? bufd[l_new + t] : 0.0;
+                        __syncwarp();
+                        if (isu) { buf[h_new + pos] = v; bufd[l_new + pos] = l; }
+                    }
+                    for (uint32_t i = 0; i < entry; ++i) {
+                        uint64_t* row = buf + (m_new + i * ucap);
+                        const uint64_t v = isu ? row[t] : 0;
+                        __syncwarp();
+                        if (isu) row[pos] = v;
+                    }
+                    __syncwarp();
+                    running += __popc(b);
+                }
+                n_new = running;
+            }
+        }
+        uint32_t tm = m_cur; m_cur = m_new; m_new = tm;
+        tm = h_cur; h_cur = h_new; h_new = tm;
+        tm = l_cur; l_cur = l_new; l_new = tm;
+        n_cur = n_new;
+        __syncwarp();
+    }
+
+    // the one entry whose root slot holds exactly the gene-tree root (src/_msnc_density.py:374-389)
+    for (uint32_t base = 0; base < n_cur; base += 32) {
+        const uint32_t k = base + lane;
+        bool hit = k < n_cur;
+        if (hit)
+            for (int i = 0; i < NW; ++i) {
+                const uint64_t want = ((root_bit >> 6) == i) ? (uint64_t{1} << (root_bit & 63)) : 0;
+                hit = hit && (buf[m_cur + (root_slot * NW + i) * ucap + k] == want);
+            }
+        const unsigned b = __ballot_sync(FULL, hit);
+        if (b) {
+            const double score = bufd[l_cur + base + __ffs(b) - 1];
+            return (score <= LOG_FLOOR + 1.0) ? -INFINITY : score;   // msnc_log_density_prebuilt :488-490
+        }
+    }
+    return -INFINITY;
+}
+
+template <int NW, bool SMEM>
+__global__ void __launch_bounds__(128) pnb_msnc_warp_kernel(MsncLaunch L) {
+    // Dynamic shared memory: [step program | step thetas | down slots] [per warp: frontier storage, if it fits]
+    // [per warp: the gene tree's events and species lineage sets, if they fit]
+    extern __shared__ uint64_t pnb_msnc_smem[];
+    Step* s_steps = reinterpret_cast<Step*>(pnb_msnc_smem);
+    double* s_theta = reinterpret_cast<double*>(s_steps + L.n_steps);
+    int32_t* s_down = reinterpret_cast<int32_t*>(s_theta + 4 * static_cast<size_t>(L.n_steps));
+    {
+        const uint64_t* src = reinterpret_cast<const uint64_t*>(L.steps);
+        const int words = L.n_steps * static_cast<int>(sizeof(Step) / 8);
+        for (int i = threadIdx.x; i < words; i += blockDim.x) pnb_msnc_smem[i] = src[i];
+        for (int i = threadIdx.x; i < 4 * L.n_steps; i += blockDim.x) s_theta[i] = L.step_theta[i];
+        for (int i = threadIdx.x; i < L.n_down; i += blockDim.x) s_down[i] = L.down_slot[i];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int64_t j = static_cast<int64_t>(blockIdx.x) * wpb + wib;
+    if (j >= L.n_jobs) return;
+    const int root_bit = L.root_bit[j];
+    if (root_bit < 0) {   // empty gene tree: density 1 (src/_msnc_density.py:222-223)
+        if (lane == 0) { L.out[j] = 0.0; L.status[j] = JOB_OK; }
+        return;
+    }
+    const size_t job_words = static_cast<size_t>(L.warp_job_words);
+    uint64_t* buf = L.frontier_in_smem ? pnb_msnc_smem + L.program_words + wib * job_words
+                                       : L.fr_mask + static_cast<size_t>(j) * job_words;
+    const int64_t e0 = L.ev_off[j];
+    const int n_ev = static_cast<int>(L.ev_off[j + 1] - e0);
+    const double* ev_t = L.ev_t + e0;
+    const uint32_t* ev_n = L.ev_n + e0;
+    const uint64_t* sp_mask = L.species_mask + static_cast<size_t>(j) * L.n_species * NW;
+    if (L.stage_words > 0 && n_ev <= L.stage_ev_cap) {
+        uint64_t* reg = pnb_msnc_smem + L.program_words + (L.frontier_in_smem ? job_words * wpb : 0) +
+                        static_cast<size_t>(wib) * L.stage_words;
+        double* stt = reinterpret_cast<double*>(reg);
+        uint32_t* sn = reinterpret_cast<uint32_t*>(reg + L.stage_ev_cap);
+        uint64_t* ss = reg + L.stage_ev_cap + (L.stage_ev_cap + 1) / 2;
+        for (int i = lane; i < n_ev; i += 32) { stt[i] = ev_t[i]; sn[i] = ev_n[i]; }
+        for (int i = lane; i < L.n_species * NW; i += 32) ss[i] = sp_mask[i];
+        __syncwarp();
+        ev_t = stt; ev_n = sn; sp_mask = ss;
+    }
+    int status;
+    const double v = msnc_dp_warp<NW, SMEM>(s_steps, L.n_steps, s_down, L.W, L.cap, ev_t, ev_n, n_ev, sp_mask, root_bit, s_theta,
+                                            buf, &status);
+    if (lane == 0) { L.out[j] = v; L.status[j] = status; }
+}
+
+template <int NW, bool SMEM>
 __global__ void __launch_bounds__(128) pnb_msnc_kernel(MsncLaunch L) {
     // Dynamic shared memory: [step program | step thetas | down slots] [frontiers, if they fit].
     // Every thread walks the same program; staging it once per block turns ~3 dependent global loads per
@@ -113,6 +457,16 @@ __global__ void __launch_bounds__(128) pnb_msnc_kernel(MsncLaunch L) {
         for (int i = 0; i < n_ev; ++i) { st[i] = ev_t[i]; sn[i] = ev_n[i]; }
         for (int i = 0; i < L.n_species * NW; ++i) ss[i] = sp_mask[i];
         ev_t = st; ev_n = sn; sp_mask = ss;
+    }
+    __builtin_assume(__isShared(s_steps));
+    __builtin_assume(__isShared(s_down));
+    __builtin_assume(__isShared(s_theta));
+    if (SMEM) {   // the host picks this variant when the frontier AND the staged events are in shared memory
+        __builtin_assume(__isShared(fr_mask));
+        __builtin_assume(__isShared(fr_lp));
+        __builtin_assume(__isShared(ev_t));
+        __builtin_assume(__isShared(ev_n));
+        __builtin_assume(__isShared(sp_mask));
     }
     if (L.tree_shaped) {   // no reticulation: single-entry frontier, updated in place
         L.out[j] = msnc_dp_tree<NW>(s_steps, L.n_steps, s_down, ev_t, ev_n, n_ev, sp_mask, root_bit, s_theta, fr_mask, stride);
@@ -359,12 +713,21 @@ static int msnc_launch(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_trees, c
     // ---- frontier capacity and scratch ---------------------------------------------------------
     const double bound = frontier_bound(prog, alleles_max.data());
     const int cap = static_cast<int>(std::min<double>(bound, static_cast<double>(net->max_frontier))) + 1;
-    const size_t job_mask_words = msnc_mask_words(prog.W, NW, cap);
-    const size_t per_job = job_mask_words * sizeof(uint64_t) + 2 * static_cast<size_t>(cap) * sizeof(double);
+    // Reticulate networks: one warp per gene tree (msnc_dp_warp); species trees -- a single-entry frontier, nothing to
+    // spread over lanes -- and PNB_MSNC_SERIAL=1 (test knob): one thread per gene tree.
+    const char* serial_env = getenv("PNB_MSNC_SERIAL");
+    const bool warp_mode = !prog.retic_step.empty() && !(serial_env && serial_env[0] == '1');
+    int tsize = 64;
+    while (tsize < 2 * cap) tsize <<= 1;
+    const size_t job_mask_words = warp_mode ? msnc_warp_words(prog.W, NW, cap, tsize) : msnc_mask_words(prog.W, NW, cap);
+    const size_t per_job = warp_mode ? job_mask_words * sizeof(uint64_t)
+                                     : job_mask_words * sizeof(uint64_t) + 2 * static_cast<size_t>(cap) * sizeof(double);
     // Block size: small batches use small blocks so that they spread over the SMs; the frontier goes to
     // shared memory when a block's worth of it fits (it does for every tree-shaped network and for
     // networks whose reticulations sit above few gene lineages), else to a global scratch buffer.
     int threads = n_trees >= int64_t(ctx->sm_count) * 256 ? 128 : (n_trees >= int64_t(ctx->sm_count) * 128 ? 64 : 32);
+    if (warp_mode) threads = n_trees >= int64_t(ctx->sm_count) * 8 ? 128 : (n_trees >= int64_t(ctx->sm_count) * 4 ? 64 : 32);
+    const int lanes_per_job = warp_mode ? 32 : 1;
     // the step program is staged in shared memory by every block (steps, thetas, down slots)
     const size_t program_bytes = align_up(prog.steps.size() * (sizeof(Step) + 4 * sizeof(double)) +
                                           prog.down_slot.size() * sizeof(int32_t), 16);
@@ -372,20 +735,22 @@ static int msnc_launch(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_trees, c
                 "pnb_msnc_eval: the species network has too many nodes (%zu) for the staged step program", prog.steps.size());
     const size_t smem_limit = static_cast<size_t>(std::max(ctx->max_smem_optin - 2048, 0)) - program_bytes;
     const char* no_smem = getenv("PNB_MSNC_NO_SMEM");   // test knob: force the global-scratch path
-    const bool in_smem = per_job * 32 <= smem_limit && !(no_smem && no_smem[0] == '1');
+    const bool in_smem = per_job * (warp_mode ? 1 : 32) <= smem_limit && !(no_smem && no_smem[0] == '1');
     if (in_smem)
-        while (per_job * threads > smem_limit) threads /= 2;
-    // per-thread staging of events + species masks: taken when it fits next to the frontiers without shrinking the block
+        while (per_job * (threads / lanes_per_job) > smem_limit) threads /= 2;
+    const int jobs_per_block = threads / lanes_per_job;
+    // staging of events + species masks (per thread, or per warp): taken when it fits next to the frontiers without
+    // shrinking the block
     int max_ev = 0;
     for (int64_t j = 0; j < n_trees; ++j) max_ev = std::max<int>(max_ev, static_cast<int>(ev_off[j + 1] - ev_off[j]));
     int stage_ev_cap = max_ev | 1;                                     // odd: neighbouring threads start on different banks
     size_t stage_words = static_cast<size_t>(stage_ev_cap) + (stage_ev_cap + 1) / 2 + static_cast<size_t>(n_species) * NW;
     stage_words |= 1;
-    const size_t fr_bytes = in_smem ? per_job * threads : 0;
+    const size_t fr_bytes = in_smem ? per_job * jobs_per_block : 0;
     const bool stage = max_ev > 0 && !(getenv("PNB_MSNC_NO_STAGE") && getenv("PNB_MSNC_NO_STAGE")[0] == '1') &&
-                       fr_bytes + stage_words * 8 * threads <= smem_limit;
+                       fr_bytes + stage_words * 8 * jobs_per_block <= smem_limit;
     if (!stage) stage_words = 0;
-    const size_t dyn_smem = program_bytes + fr_bytes + stage_words * 8 * threads;
+    const size_t dyn_smem = program_bytes + fr_bytes + stage_words * 8 * jobs_per_block;
     // jobs per launch: bounded scratch (the frontiers of a batch may not fit at once)
     size_t scratch_budget = size_t{2} << 30;
     if (const char* mb = getenv("PNB_MSNC_SCRATCH_MB")) {   // test knob: small budgets exercise the multi-launch path
@@ -395,11 +760,17 @@ static int msnc_launch(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_trees, c
     const int64_t jobs_per_launch =
         in_smem ? n_trees : std::max<int64_t>(1, std::min<int64_t>(n_trees, static_cast<int64_t>(scratch_budget / per_job)));
     const size_t off_lp = align_up(static_cast<size_t>(jobs_per_launch) * job_mask_words * sizeof(uint64_t), 256);
-    if (!in_smem && (rc = ensure_device(ctx->m_scratch, off_lp + static_cast<size_t>(jobs_per_launch) * 2 * cap * sizeof(double)))) return rc;
+    if (!in_smem && (rc = ensure_device(ctx->m_scratch, off_lp + (warp_mode ? 0 : static_cast<size_t>(jobs_per_launch) * 2 * cap * sizeof(double))))) return rc;
     if (!ctx->msnc_configured) {   // once per context: opt in to large dynamic shared memory
         const int lim = std::max(ctx->max_smem_optin - 2048, 0);
-        PNB_CUDA_TRY(cudaFuncSetAttribute(pnb_msnc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-        PNB_CUDA_TRY(cudaFuncSetAttribute(pnb_msnc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        PNB_CUDA_TRY(cudaFuncSetAttribute(pnb_msnc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        PNB_CUDA_TRY(cudaFuncSetAttribute(pnb_msnc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        PNB_CUDA_TRY(cudaFuncSetAttribute(pnb_msnc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        PNB_CUDA_TRY(cudaFuncSetAttribute(pnb_msnc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        PNB_CUDA_TRY(cudaFuncSetAttribute(pnb_msnc_warp_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        PNB_CUDA_TRY(cudaFuncSetAttribute(pnb_msnc_warp_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        PNB_CUDA_TRY(cudaFuncSetAttribute(pnb_msnc_warp_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        PNB_CUDA_TRY(cudaFuncSetAttribute(pnb_msnc_warp_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
         ctx->msnc_configured = true;
     }
     const size_t off_status = align_up(static_cast<size_t>(n_trees) * sizeof(double), 256);
@@ -424,6 +795,8 @@ static int msnc_launch(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_trees, c
     L.program_words = static_cast<int32_t>(program_bytes / 8);
     L.stage_words = static_cast<int32_t>(stage_words);
     L.stage_ev_cap = stage_ev_cap;
+    L.warp_tsize = tsize;
+    L.warp_job_words = static_cast<int64_t>(job_mask_words);
     L.fr_mask = in_smem ? nullptr : static_cast<uint64_t*>(ctx->m_scratch.p);
     L.fr_lp = in_smem ? nullptr : reinterpret_cast<double*>(static_cast<char*>(ctx->m_scratch.p) + off_lp);
     int64_t launches = 0;
@@ -437,9 +810,17 @@ static int msnc_launch(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_trees, c
         L.root_bit = reinterpret_cast<const int32_t*>(ds + off_root) + j0;
         L.out = static_cast<double*>(ctx->m_dout.p) + j0;
         L.status = reinterpret_cast<int32_t*>(static_cast<char*>(ctx->m_dout.p) + off_status) + j0;
-        const unsigned blocks = static_cast<unsigned>((nj + threads - 1) / threads);
-        if (NW == 1) pnb_msnc_kernel<1><<<blocks, threads, dyn_smem, st>>>(L);
-        else pnb_msnc_kernel<2><<<blocks, threads, dyn_smem, st>>>(L);
+        const unsigned blocks = static_cast<unsigned>((nj + jobs_per_block - 1) / jobs_per_block);
+        // all_smem: frontiers AND staged events / lineage sets of every job are in shared memory (every tree has at most
+        // stage_ev_cap events by construction) -> the variant compiled with shared-memory addressing throughout
+        const bool all_smem = in_smem && stage;
+        if (warp_mode) {
+            if (NW == 1) { if (all_smem) pnb_msnc_warp_kernel<1, true><<<blocks, threads, dyn_smem, st>>>(L); else pnb_msnc_warp_kernel<1, false><<<blocks, threads, dyn_smem, st>>>(L); }
+            else { if (all_smem) pnb_msnc_warp_kernel<2, true><<<blocks, threads, dyn_smem, st>>>(L); else pnb_msnc_warp_kernel<2, false><<<blocks, threads, dyn_smem, st>>>(L); }
+        } else {
+            if (NW == 1) { if (all_smem) pnb_msnc_kernel<1, true><<<blocks, threads, dyn_smem, st>>>(L); else pnb_msnc_kernel<1, false><<<blocks, threads, dyn_smem, st>>>(L); }
+            else { if (all_smem) pnb_msnc_kernel<2, true><<<blocks, threads, dyn_smem, st>>>(L); else pnb_msnc_kernel<2, false><<<blocks, threads, dyn_smem, st>>>(L); }
+        }
         PNB_CUDA_TRY(cudaGetLastError());
         ++launches;
     }

@@ -69,6 +69,54 @@ def test_both_frontier_placements_agree(monkeypatch):
     monkeypatch.delenv("PNB_MSNC_NO_SMEM", raising=False)
 
 
+def test_warp_and_thread_kernels_agree(monkeypatch):
+    """Reticulate networks run one WARP per gene tree (candidates of a step spread over the lanes, duplicates merged in
+    candidate order); PNB_MSNC_SERIAL=1 runs the one-thread-per-tree DP instead.  Same entry order, same merge order,
+    same floating-point operations: the two return the same bits, in shared memory and in the global scratch buffer."""
+    P = _pkg()
+    n_retic_cases = 0
+    for case in CASES:
+        net = P.SpeciesNetwork.from_dict(case["network"])
+        if net.info(P.default_context())["reticulations"] == 0:
+            continue
+        n_retic_cases += 1
+        trees = _trees(P, case)
+        bt = _thetas(case)
+        out = {}
+        for serial in ("0", "1"):
+            for no_smem in ("0", "1"):
+                monkeypatch.setenv("PNB_MSNC_SERIAL", serial)
+                monkeypatch.setenv("PNB_MSNC_NO_SMEM", no_smem)
+                out[serial, no_smem] = P.msnc_log_density_batch(trees, net, case["species_of"], case["theta"], branch_thetas=bt)
+        base = out["1", "0"]
+        for key, v in out.items():
+            assert np.array_equal(base, v, equal_nan=True), (case["name"], key)
+    monkeypatch.delenv("PNB_MSNC_SERIAL", raising=False)
+    monkeypatch.delenv("PNB_MSNC_NO_SMEM", raising=False)
+    assert n_retic_cases >= 10
+
+
+def test_warp_kernel_large_batch_with_duplicates(monkeypatch):
+    """Many gene trees with several alleles per species under two / three reticulations: frontiers of hundreds of
+    candidates per step with duplicate entries; blocks of four warps."""
+    from phynetpy_b200 import simulate as S
+    P = _pkg()
+    rng = np.random.default_rng(77)
+    for n_species, n_retic, alleles, n_trees in ((6, 2, 2, 1500), (8, 3, 1, 1500)):
+        net = S.random_species_network(n_species, n_retic, rng)
+        trees, species_of = S.simulate_gene_trees_msnc(net, alleles, 0.02, rng, 40)
+        trees = (trees * (n_trees // len(trees) + 1))[:n_trees]
+        monkeypatch.setenv("PNB_MSNC_SERIAL", "1")
+        a = P.msnc_log_density_batch(trees, net, species_of, 0.02)
+        monkeypatch.setenv("PNB_MSNC_SERIAL", "0")
+        b = P.msnc_log_density_batch(trees, net, species_of, 0.02)
+        assert np.array_equal(a, b)
+        d = net.to_dict()
+        for t, g in list(zip(trees, b))[:6]:
+            assert _close(float(g), MO.msnc_log_density(d, t.parent.tolist(), t.blen.tolist(), t.label, species_of, 0.02))
+    monkeypatch.delenv("PNB_MSNC_SERIAL", raising=False)
+
+
 def test_global_scratch_is_used_in_several_launches_when_it_is_small(monkeypatch):
     """Frontiers that do not fit in shared memory go to a bounded global scratch buffer; a batch larger than the
     buffer is evaluated in several launches (PNB_MSNC_SCRATCH_MB shrinks the 2 GB default for this test)."""

@@ -34,8 +34,13 @@ if os.environ.get("PROBE_MODE") == "one":      # a single gene tree: the latency
     args = (np.array([0, t.n_nodes], dtype=np.int64), t.parent, t.blen, net.species_ids_of(t, species_of))
     off = args[0]
 ctx = P.default_context()
-for _ in range(5):
+for it in range(8):
+    if it == 5:
+        ctx.set_profiling(True)     # CUDA events around the kernel (slot "prune_ms" of last_timings)
     t0 = time.perf_counter()
     v = msnc_eval_packed(net, *args, 0.02, ctx)
     dt = time.perf_counter() - t0
+    if it >= 5:
+        print("kernel (events) %.1f us, call %.3f ms" % (ctx.last_timings()["prune_ms"] * 1e3, dt * 1e3))
+ctx.set_profiling(False)
 print("gene trees %d  finite %d  last call %.3f ms  stats %s" % (off.shape[0] - 1, int(np.isfinite(v).sum()), dt * 1e3, ctx.last_stats()))
