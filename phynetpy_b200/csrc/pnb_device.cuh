@@ -105,6 +105,19 @@ struct PruneLaunch {
     double* peer_out[MAX_PEERS];
 };
 
+// FUSED launches of one or two loci (the single-locus MCMC step): the tile map, the job descriptors, the op program and
+// the branch lengths travel IN THE KERNEL PARAMETERS instead of being read from pinned host memory -- four dependent
+// PCIe round trips (~1.5 us each) less on the critical path of the step.
+constexpr int SMALL_MAX_TILES = 8, SMALL_MAX_JOBS = 2, SMALL_MAX_OPS = 64;
+struct SmallBatch {
+    int32_t n_jobs;   // 0: not used (everything is read through PruneLaunch)
+    int32_t pad;
+    int32_t tile_job[SMALL_MAX_TILES];
+    JobDesc jobs[SMALL_MAX_JOBS];
+    Op ops[SMALL_MAX_OPS];        // JobDesc.ops == NULL: the job's program is ops[op_off ...]
+    double t[SMALL_MAX_OPS];
+};
+
 #ifdef PNB_DEVICE_KERNELS  // kernel bodies: compiled into exactly one translation unit (pnb_eval.cu)
 
 // ------------------------------------------------------------------------
@@ -378,7 +391,8 @@ __device__ __forceinline__ void tip_contrib(uint32_t pk, const uint32_t (&code)[
 // summed per HALF (u < PPT / 2, u >= PPT / 2) and every half is reduced over the block on its own, so a tile gives the
 // same two sums whether one block or two computed it -- results never depend on how a launch was cut into blocks.
 template <bool FUSED, bool RESCALE, int NP>
-__device__ __forceinline__ void prune_tile(const PruneLaunch& L, const ModelParams& mp, const int tile, const int u0) {
+__device__ __forceinline__ void prune_tile(const PruneLaunch& L, const ModelParams& mp, const SmallBatch& S, const int tile,
+                                           const int u0) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar_stage;
     __shared__ double red[TPB / 32];
@@ -386,9 +400,10 @@ __device__ __forceinline__ void prune_tile(const PruneLaunch& L, const ModelPara
     __shared__ int s_rows;
 
     const int tid = threadIdx.x;
-    const int job = L.tile_job[tile];
+    const bool small = FUSED && S.n_jobs > 0;
+    const int job = small ? S.tile_job[tile] : L.tile_job[tile];
     if (job < 0) return;  // tile of a job that needed no device work (served from the cache)
-    const JobDesc& jd = L.jobs[job];
+    const JobDesc& jd = small ? S.jobs[job] : L.jobs[job];
     const int n_ops = jd.n_ops;
     const int op_off = jd.op_off;
     const int tile0 = jd.tile0;
@@ -442,11 +457,12 @@ __device__ __forceinline__ void prune_tile(const PruneLaunch& L, const ModelPara
             if (tid == 0) s_rows = 0;
             __syncthreads();  // also: every warp is done with the previous segment's shared memory
             int my_rows = 0;
+            const bool param_ops = small && g_ops == nullptr;
             for (int k = tid; k < nseg; k += TPB) {
-                const Op op = g_ops[seg + k];
+                const Op op = param_ops ? S.ops[op_off + seg + k] : g_ops[seg + k];
                 s_ops[k] = op;
                 double Pm[16];
-                pmatrix_of_t(mp, L.t[op_off + seg + k], Pm);
+                pmatrix_of_t(mp, small ? S.t[op_off + seg + k] : L.t[op_off + seg + k], Pm);
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -672,14 +688,15 @@ __device__ __forceinline__ void prune_tile(const PruneLaunch& L, const ModelPara
 
 template <bool FUSED, bool RESCALE>
 __global__ void __launch_bounds__(TPB, PRUNE_MIN_BLOCKS)
-pnb_prune_kernel_t(const __grid_constant__ PruneLaunch L, const __grid_constant__ ModelParams mp) {
+pnb_prune_kernel_t(const __grid_constant__ PruneLaunch L, const __grid_constant__ ModelParams mp,
+                   const __grid_constant__ SmallBatch S) {
     const int b = blockIdx.x;
     if (PPT % 2 != 0 || b < L.n_full) {
-        prune_tile<FUSED, RESCALE, PPT>(L, mp, L.tile_base + b, 0);
+        prune_tile<FUSED, RESCALE, PPT>(L, mp, S, L.tile_base + b, 0);
     } else {
         constexpr int HALF = (PPT % 2 == 0) ? PPT / 2 : PPT;
         const int h = b - L.n_full;
-        prune_tile<FUSED, RESCALE, HALF>(L, mp, L.tile_base + L.n_full + (h >> 1), (h & 1) * HALF);
+        prune_tile<FUSED, RESCALE, HALF>(L, mp, S, L.tile_base + L.n_full + (h >> 1), (h & 1) * HALF);
     }
 }
 

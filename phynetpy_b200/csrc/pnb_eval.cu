@@ -36,22 +36,19 @@ int pnb::launch_pmatrix_gather(const ModelParams& mp, const double* d_blen, cons
     return PNB_OK;
 }
 
-// How a launch of n_tiles tiles is cut into blocks.  Blocks are dispatched in index order onto `slots` = SMs x resident
-// blocks per SM; all tiles of a launch cost about the same, so the last, partial wave of whole-tile blocks leaves
-// (slots - rem) block slots idle for a full tile time -- 6 % of an 8.45-wave launch (cfg5 on 8 GPUs).  When that wave
-// is at most half full its tiles are computed by two blocks each (half the patterns per thread, half the duration):
-// twice the blocks still fit in one wave, which then ends in half the time.  A launch smaller than half a wave (a
-// single-locus MCMC step: one or two tiles) is all half tiles -- two SMs share the latency of every tile.
-// PNB_SPLIT_TAIL=0 switches the split off (every block a whole tile); the results are the same bits either way.
+// How a launch of n_tiles tiles is cut into blocks: one block per tile, or -- PNB_SPLIT_TAIL=1 -- the tiles of the last,
+// partial wave as two half-tile blocks each when that wave is at most half full (blocks are dispatched in index order
+// onto `slots` = SMs x resident blocks per SM).  Written against the idea that an 8.45-wave launch (cfg5 on 8 GPUs)
+// loses half a wave to quantisation; measured (gpurun_out/wave_*.json, s3_n8*.json), kernel time is LINEAR in the
+// number of tiles with a fixed ~26 us per launch (ramp-up + drain of the resident blocks), a half-tile block lives
+// almost as long as a whole one (its latency is the op walk, not the patterns), and the split changes nothing: it
+// stays off by default.  The results are the same bits either way (tests/test_gpu_parity.py::test_split_tail_same_bits).
 static void split_tail(unsigned n_tiles, size_t dyn_smem, bool fused, bool rescale, int32_t* n_full, unsigned* grid) {
     static int slots_cache[4] = {0, 0, 0, 0};
     static size_t smem_cache[4] = {~size_t{0}, ~size_t{0}, ~size_t{0}, ~size_t{0}};
     static int sm_count = 0;
-    static int enabled = -1;
-    if (enabled < 0) {
-        const char* e = getenv("PNB_SPLIT_TAIL");
-        enabled = (PPT % 2 == 0 && !(e && e[0] == '0')) ? 1 : 0;
-    }
+    const char* env = getenv("PNB_SPLIT_TAIL");
+    const bool enabled = PPT % 2 == 0 && env && env[0] == '1';
     *n_full = static_cast<int32_t>(n_tiles);
     *grid = n_tiles;
     if (!enabled || n_tiles == 0) return;
@@ -89,8 +86,9 @@ int pnb::launch_prune(const PruneLaunch& L_in, const ModelParams& mp, unsigned n
     PruneLaunch L = L_in;
     unsigned grid;
     split_tail(n_tiles, dyn_smem, false, rescale, &L.n_full, &grid);
-    if (rescale) pnb_prune_kernel_t<false, true><<<grid, TPB, dyn_smem, st>>>(L, mp);
-    else pnb_prune_kernel_t<false, false><<<grid, TPB, dyn_smem, st>>>(L, mp);
+    static const SmallBatch no_small = {};   // n_jobs == 0: unused outside the fused latency path
+    if (rescale) pnb_prune_kernel_t<false, true><<<grid, TPB, dyn_smem, st>>>(L, mp, no_small);
+    else pnb_prune_kernel_t<false, false><<<grid, TPB, dyn_smem, st>>>(L, mp, no_small);
     PNB_CUDA_TRY(cudaGetLastError());
     return PNB_OK;
 }
@@ -574,13 +572,30 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
         if (ctx->profiling && c == 0) PNB_CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
         unsigned grid;
         split_tail(static_cast<unsigned>(ct), dyn_smem, fused, rescale, &L.n_full, &grid);
+        static const SmallBatch no_small = {};
         if (fused) {
-            if (rescale) pnb_prune_kernel_t<true, true><<<grid, TPB, dyn_smem, st>>>(L, m->mp);
-            else pnb_prune_kernel_t<true, false><<<grid, TPB, dyn_smem, st>>>(L, m->mp);
+            // one or two loci: descriptors, program and lengths go into the kernel parameters (no PCIe reads for them)
+            SmallBatch sm = {};
+            const int64_t n_ops_all = total_nodes - M;
+            if (M <= SMALL_MAX_JOBS && total_tiles <= SMALL_MAX_TILES && n_ops_all <= SMALL_MAX_OPS) {
+                sm.n_jobs = static_cast<int32_t>(M);
+                const int32_t* tj = reinterpret_cast<const int32_t*>(hs + off_tiles);
+                for (int64_t t = 0; t < total_tiles; ++t) sm.tile_job[t] = tj[t];
+                const JobDesc* hj = reinterpret_cast<const JobDesc*>(hs + off_jobs);
+                const Op* staged = reinterpret_cast<const Op*>(hs + off_ops);
+                for (int64_t j = 0; j < M; ++j) {
+                    sm.jobs[j] = hj[j];
+                    if (sm.jobs[j].ops >= staged && sm.jobs[j].ops < staged + n_ops_all) sm.jobs[j].ops = nullptr;   // staged program -> parameters
+                }
+                memcpy(sm.ops, staged, static_cast<size_t>(n_ops_all) * sizeof(Op));
+                memcpy(sm.t, hs + off_t, static_cast<size_t>(n_ops_all) * sizeof(double));
+            }
+            if (rescale) pnb_prune_kernel_t<true, true><<<grid, TPB, dyn_smem, st>>>(L, m->mp, sm);
+            else pnb_prune_kernel_t<true, false><<<grid, TPB, dyn_smem, st>>>(L, m->mp, sm);
             stage_read_by_kernel = true;
         } else {
-            if (rescale) pnb_prune_kernel_t<false, true><<<grid, TPB, dyn_smem, st>>>(L, m->mp);
-            else pnb_prune_kernel_t<false, false><<<grid, TPB, dyn_smem, st>>>(L, m->mp);
+            if (rescale) pnb_prune_kernel_t<false, true><<<grid, TPB, dyn_smem, st>>>(L, m->mp, no_small);
+            else pnb_prune_kernel_t<false, false><<<grid, TPB, dyn_smem, st>>>(L, m->mp, no_small);
         }
         PNB_CUDA_TRY(cudaGetLastError());
         if (ctx->profiling && c == n_chunks - 1) { PNB_CUDA_TRY(cudaEventRecord(ctx->ev[3], st)); ctx->ev_prune = true; }

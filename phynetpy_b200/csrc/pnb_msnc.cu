@@ -21,7 +21,8 @@ struct pnb_msnc_net {
     pnb_ctx* ctx = nullptr;
     NetProgram prog;
     Step* d_steps = nullptr;
-    int32_t* d_down = nullptr;
+    int32_t* d_down = nullptr;        // [down_slot (n_down) | down_step (n_down) | level (n_steps)]
+    size_t down_bytes = 0;
     int64_t max_frontier = 1 << 16;   // entries per job the scratch may be sized for
     int32_t n_edges = 0;
     std::vector<double> edge_theta;   // per-branch theta overrides (NaN = the call's theta); empty = none
@@ -398,6 +399,104 @@ __global__ void __launch_bounds__(128) pnb_msnc_warp_kernel(MsncLaunch L) {
     if (lane == 0) { L.out[j] = v; L.status[j] = status; }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// One warp per gene tree on a species TREE (the MSC case), for small batches -- a gene-tree move scores one tree, and
+// one thread walking the 2 n - 1 network nodes one after the other is 20+ us of dependent instructions.  The frontier
+// of a tree-shaped network is a single entry, so the nodes of different subtrees do not interact: lane s takes node
+// (step) s, the warp advances LEVEL by level (leaves = 0, a node one above its highest child), every lane of a level
+// ORs the lineage sets its children left, runs the same branch factor as msnc_dp_tree and leaves its own set and
+// factor in shared memory.  The factors are then added in step order, exactly the additions msnc_dp_tree makes, so the
+// result has the same bits.  Depth ~2 log2(n) rounds instead of 2 n - 1.
+// Shared memory per warp: out[n_steps][NW] lineage sets | blp[n_steps] factors | counted[n_steps] ("branch entered by < 2
+// lineages" factors are flagged and skipped in the sum as msnc_dp_tree skips them) | staged events and species sets.
+// ------------------------------------------------------------------------------------------------------------
+template <int NW>
+__global__ void __launch_bounds__(128) pnb_msnc_tree_warp_kernel(MsncLaunch L) {
+    extern __shared__ uint64_t pnb_msnc_smem[];
+    Step* s_steps = reinterpret_cast<Step*>(pnb_msnc_smem);
+    double* s_theta = reinterpret_cast<double*>(s_steps + L.n_steps);
+    int32_t* s_down = reinterpret_cast<int32_t*>(s_theta + 4 * static_cast<size_t>(L.n_steps));   // down_slot | down_step | level
+    {
+        const uint64_t* src = reinterpret_cast<const uint64_t*>(L.steps);
+        const int words = L.n_steps * static_cast<int>(sizeof(Step) / 8);
+        for (int i = threadIdx.x; i < words; i += blockDim.x) pnb_msnc_smem[i] = src[i];
+        for (int i = threadIdx.x; i < 4 * L.n_steps; i += blockDim.x) s_theta[i] = L.step_theta[i];
+        for (int i = threadIdx.x; i < 2 * L.n_down + L.n_steps; i += blockDim.x) s_down[i] = L.down_slot[i];
+    }
+    __syncthreads();
+    const int32_t* s_down_step = s_down + L.n_down;
+    const int32_t* s_level = s_down + 2 * L.n_down;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int64_t j = static_cast<int64_t>(blockIdx.x) * wpb + wib;
+    if (j >= L.n_jobs) return;
+    const int root_bit = L.root_bit[j];
+    if (root_bit < 0) {   // empty gene tree: density 1 (src/_msnc_density.py:222-223)
+        if (lane == 0) { L.out[j] = 0.0; L.status[j] = JOB_OK; }
+        return;
+    }
+    const int n_steps = L.n_steps;
+    uint64_t* reg = pnb_msnc_smem + L.program_words + static_cast<size_t>(wib) * L.warp_job_words;
+    uint64_t* out = reg;                                                          // [n_steps][NW]
+    double* blp = reinterpret_cast<double*>(reg + static_cast<size_t>(n_steps) * NW);   // [n_steps]
+    int32_t* counted = reinterpret_cast<int32_t*>(reg + static_cast<size_t>(n_steps) * (NW + 1));   // [n_steps]: factor enters the sum
+    uint64_t* stage = reg + static_cast<size_t>(n_steps) * (NW + 1) + (n_steps + 1) / 2;
+    const int64_t e0 = L.ev_off[j];
+    const int n_ev = static_cast<int>(L.ev_off[j + 1] - e0);
+    double* ev_t = reinterpret_cast<double*>(stage);
+    uint32_t* ev_n = reinterpret_cast<uint32_t*>(stage + L.stage_ev_cap);
+    uint64_t* sp_mask = stage + L.stage_ev_cap + (L.stage_ev_cap + 1) / 2;
+    for (int i = lane; i < n_ev; i += 32) { ev_t[i] = L.ev_t[e0 + i]; ev_n[i] = L.ev_n[e0 + i]; }
+    for (int i = lane; i < L.n_species * NW; i += 32) sp_mask[i] = L.species_mask[static_cast<size_t>(j) * L.n_species * NW + i];
+    int max_level = 0;
+    for (int s = lane; s < n_steps; s += 32) max_level = max(max_level, s_level[s]);
+    max_level = __reduce_max_sync(0xffffffffu, max_level);
+    __syncwarp();
+    for (int lvl = 0; lvl <= max_level; ++lvl) {
+        for (int s = lane; s < n_steps; s += 32) {
+            if (s_level[s] != lvl) continue;
+            const Step& st = s_steps[s];
+            Mask<NW> at_v;
+            at_v.clear();
+            if (st.kind & KIND_LEAF) {
+                if (st.species >= 0)
+                    for (int i = 0; i < NW; ++i) at_v.w[i] = sp_mask[static_cast<size_t>(st.species) * NW + i];
+            } else {
+                for (int d = 0; d < st.n_down; ++d) {
+                    const int c = s_down_step[st.down_off + d];
+                    for (int i = 0; i < NW; ++i) at_v.w[i] |= out[static_cast<size_t>(c) * NW + i];
+                }
+            }
+            const bool is_root = (st.kind & KIND_ROOT) != 0;
+            double b = 0.0;
+            const bool two = at_v.count() > 1;
+            if (two) {
+                const int j_lo = first_event_at_or_after(ev_t, n_ev, st.tau_low);
+                const int j_hi = is_root ? n_ev : first_event_at_or_after(ev_t, n_ev, st.tau_high[0]);
+                branch_timed<NW>(at_v, b, st.tau_low, st.tau_high[0], !is_root, s_theta[4 * s], s_theta[4 * s + 1], ev_t, ev_n,
+                                 j_lo, j_hi);
+            }
+            for (int i = 0; i < NW; ++i) out[static_cast<size_t>(s) * NW + i] = at_v.w[i];
+            blp[s] = b;
+            counted[s] = two ? 1 : 0;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        double lp = 0.0;
+        for (int s = 0; s < n_steps; ++s) {
+            if (counted[s]) lp = add_rn(lp, blp[s]);
+        }
+        // the last step is the root (children before parents): its lineage set must be exactly the gene-tree root
+        bool hit = true;
+        for (int i = 0; i < NW; ++i) {
+            const uint64_t want = ((root_bit >> 6) == i) ? (uint64_t{1} << (root_bit & 63)) : 0;
+            hit = hit && (out[static_cast<size_t>(n_steps - 1) * NW + i] == want);
+        }
+        L.out[j] = !hit ? -INFINITY : ((lp <= LOG_FLOOR + 1.0) ? -INFINITY : lp);
+        L.status[j] = JOB_OK;
+    }
+}
+
 template <int NW, bool SMEM>
 __global__ void __launch_bounds__(128) pnb_msnc_kernel(MsncLaunch L) {
     // Dynamic shared memory: [step program | step thetas | down slots] [frontiers, if they fit].
@@ -508,7 +607,11 @@ extern "C" int pnb_msnc_net_create(pnb_ctx* ctx, int32_t n_nodes, int32_t n_edge
         }
         void* p = nullptr;
         const size_t sb = net->prog.steps.size() * sizeof(Step);
-        const size_t db = std::max<size_t>(net->prog.down_slot.size(), 1) * sizeof(int32_t);
+        std::vector<int32_t> packed(net->prog.down_slot);
+        packed.insert(packed.end(), net->prog.down_step.begin(), net->prog.down_step.end());
+        packed.insert(packed.end(), net->prog.level.begin(), net->prog.level.end());
+        const size_t db = std::max<size_t>(packed.size(), 1) * sizeof(int32_t);
+        net->down_bytes = db;
         int rc = ctx->arena.alloc(sb, &p);
         if (rc) { delete net; return rc; }
         net->d_steps = static_cast<Step*>(p);
@@ -516,9 +619,8 @@ extern "C" int pnb_msnc_net_create(pnb_ctx* ctx, int32_t n_nodes, int32_t n_edge
         if (rc) { ctx->arena.release(net->d_steps, sb); delete net; return rc; }
         net->d_down = static_cast<int32_t*>(p);
         cudaError_t ce = cudaMemcpyAsync(net->d_steps, net->prog.steps.data(), sb, cudaMemcpyHostToDevice, ctx->stream);
-        if (ce == cudaSuccess && !net->prog.down_slot.empty())
-            ce = cudaMemcpyAsync(net->d_down, net->prog.down_slot.data(), net->prog.down_slot.size() * sizeof(int32_t),
-                                 cudaMemcpyHostToDevice, ctx->stream);
+        if (ce == cudaSuccess && !packed.empty())
+            ce = cudaMemcpyAsync(net->d_down, packed.data(), packed.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);   // the vectors are pageable
         if (ce != cudaSuccess) {
             ctx->arena.release(net->d_steps, sb);
@@ -538,7 +640,7 @@ extern "C" int pnb_msnc_net_destroy(pnb_msnc_net* net) {
         cudaSetDevice(net->ctx->device);
         cudaStreamSynchronize(net->ctx->stream);
         net->ctx->arena.release(net->d_steps, net->prog.steps.size() * sizeof(Step));
-        net->ctx->arena.release(net->d_down, std::max<size_t>(net->prog.down_slot.size(), 1) * sizeof(int32_t));
+        net->ctx->arena.release(net->d_down, net->down_bytes);
     }
     delete net;
     return PNB_OK;
@@ -716,7 +818,8 @@ static int msnc_launch(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_trees, c
     // Reticulate networks: one warp per gene tree (msnc_dp_warp); species trees -- a single-entry frontier, nothing to
     // spread over lanes -- and PNB_MSNC_SERIAL=1 (test knob): one thread per gene tree.
     const char* serial_env = getenv("PNB_MSNC_SERIAL");
-    const bool warp_mode = !prog.retic_step.empty() && !(serial_env && serial_env[0] == '1');
+    const bool serial_forced = serial_env && serial_env[0] == '1';
+    const bool warp_mode = !prog.retic_step.empty() && !serial_forced;
     int tsize = 64;
     while (tsize < 2 * cap) tsize <<= 1;
     const size_t job_mask_words = warp_mode ? msnc_warp_words(prog.W, NW, cap, tsize) : msnc_mask_words(prog.W, NW, cap);
@@ -746,11 +849,27 @@ static int msnc_launch(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_trees, c
     int stage_ev_cap = max_ev | 1;                                     // odd: neighbouring threads start on different banks
     size_t stage_words = static_cast<size_t>(stage_ev_cap) + (stage_ev_cap + 1) / 2 + static_cast<size_t>(n_species) * NW;
     stage_words |= 1;
+    const size_t stage_words_raw = stage_words;
     const size_t fr_bytes = in_smem ? per_job * jobs_per_block : 0;
     const bool stage = max_ev > 0 && !(getenv("PNB_MSNC_NO_STAGE") && getenv("PNB_MSNC_NO_STAGE")[0] == '1') &&
                        fr_bytes + stage_words * 8 * jobs_per_block <= smem_limit;
     if (!stage) stage_words = 0;
-    const size_t dyn_smem = program_bytes + fr_bytes + stage_words * 8 * jobs_per_block;
+    size_t dyn_smem = program_bytes + fr_bytes + stage_words * 8 * jobs_per_block;
+    // Species tree, small batch: one warp per gene tree, network nodes of one level side by side (pnb_msnc_tree_warp_kernel).
+    // Everything a warp needs (lineage set and factor per node, staged events) lives in shared memory.
+    const size_t tree_warp_words = prog.steps.size() * (NW + 1) + (prog.steps.size() + 1) / 2 + stage_words_raw;
+    const size_t tree_program_bytes = align_up(prog.steps.size() * (sizeof(Step) + 4 * sizeof(double)) +
+                                               (2 * prog.down_slot.size() + prog.steps.size()) * sizeof(int32_t), 16);
+    const bool tree_warp = prog.retic_step.empty() && !serial_forced && in_smem && n_trees <= int64_t(ctx->sm_count) * 64 &&
+                           tree_program_bytes + tree_warp_words * 8 + 4096 < static_cast<size_t>(ctx->max_smem_optin);
+    int tree_warps_per_block = 1;
+    if (tree_warp) {
+        tree_warps_per_block = n_trees >= int64_t(ctx->sm_count) * 4 ? 4 : (n_trees >= int64_t(ctx->sm_count) * 2 ? 2 : 1);
+        while (tree_warps_per_block > 1 &&
+               tree_program_bytes + tree_warp_words * 8 * tree_warps_per_block + 4096 >= static_cast<size_t>(ctx->max_smem_optin))
+            tree_warps_per_block /= 2;
+        dyn_smem = tree_program_bytes + tree_warp_words * 8 * tree_warps_per_block;
+    }
     // jobs per launch: bounded scratch (the frontiers of a batch may not fit at once)
     size_t scratch_budget = size_t{2} << 30;
     if (const char* mb = getenv("PNB_MSNC_SCRATCH_MB")) {   // test knob: small budgets exercise the multi-launch path
@@ -771,6 +890,8 @@ static int msnc_launch(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_trees, c
         PNB_CUDA_TRY(cudaFuncSetAttribute(pnb_msnc_warp_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
         PNB_CUDA_TRY(cudaFuncSetAttribute(pnb_msnc_warp_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
         PNB_CUDA_TRY(cudaFuncSetAttribute(pnb_msnc_warp_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        PNB_CUDA_TRY(cudaFuncSetAttribute(pnb_msnc_tree_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+        PNB_CUDA_TRY(cudaFuncSetAttribute(pnb_msnc_tree_warp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
         ctx->msnc_configured = true;
     }
     const size_t off_status = align_up(static_cast<size_t>(n_trees) * sizeof(double), 256);
@@ -778,9 +899,20 @@ static int msnc_launch(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_trees, c
     if ((rc = ensure_pinned(ctx->m_hout, off_status + static_cast<size_t>(n_trees) * sizeof(int32_t)))) return rc;
 
     ctx->t_compile_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call0).count();
-    PNB_CUDA_TRY(cudaMemcpyAsync(ctx->m_dstage.p, hs, stage_bytes, cudaMemcpyHostToDevice, st));
+    // Small batches (a gene-tree move scores ONE tree): the kernel reads the packed input straight from the pinned staging
+    // buffer and writes its results into the pinned result buffer (both mapped into the device's address space) -- no
+    // H2D copy before the kernel and no D2H copy after it, i.e. two DMA start-ups less on the critical path of a move.
+    bool zero_copy = false;
+    if (ctx->allow_fused && n_trees <= 64 && stage_bytes <= (64u << 10)) {
+        void *da = nullptr, *db = nullptr;
+        zero_copy = cudaHostGetDevicePointer(&da, hs, 0) == cudaSuccess && da == static_cast<void*>(hs) &&
+                    cudaHostGetDevicePointer(&db, ctx->m_hout.p, 0) == cudaSuccess && db == ctx->m_hout.p;
+        if (!zero_copy) (void)cudaGetLastError();
+    }
+    if (!zero_copy) PNB_CUDA_TRY(cudaMemcpyAsync(ctx->m_dstage.p, hs, stage_bytes, cudaMemcpyHostToDevice, st));
     if (ctx->profiling) PNB_CUDA_TRY(cudaEventRecord(ctx->ev[2], st));   // reported as the "prune" slot of last_timings
-    char* ds = static_cast<char*>(ctx->m_dstage.p);
+    char* ds = zero_copy ? hs : static_cast<char*>(ctx->m_dstage.p);
+    char* dout = static_cast<char*>(zero_copy ? ctx->m_hout.p : ctx->m_dout.p);
     MsncLaunch L;
     L.steps = net->d_steps;
     L.down_slot = net->d_down;
@@ -796,7 +928,8 @@ static int msnc_launch(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_trees, c
     L.stage_words = static_cast<int32_t>(stage_words);
     L.stage_ev_cap = stage_ev_cap;
     L.warp_tsize = tsize;
-    L.warp_job_words = static_cast<int64_t>(job_mask_words);
+    L.warp_job_words = static_cast<int64_t>(tree_warp ? tree_warp_words : job_mask_words);
+    if (tree_warp) L.program_words = static_cast<int32_t>(tree_program_bytes / 8);
     L.fr_mask = in_smem ? nullptr : static_cast<uint64_t*>(ctx->m_scratch.p);
     L.fr_lp = in_smem ? nullptr : reinterpret_cast<double*>(static_cast<char*>(ctx->m_scratch.p) + off_lp);
     int64_t launches = 0;
@@ -808,9 +941,17 @@ static int msnc_launch(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_trees, c
         L.ev_n = reinterpret_cast<const uint32_t*>(ds + off_evn);
         L.species_mask = reinterpret_cast<const uint64_t*>(ds + off_sp) + static_cast<size_t>(j0) * n_species * NW;
         L.root_bit = reinterpret_cast<const int32_t*>(ds + off_root) + j0;
-        L.out = static_cast<double*>(ctx->m_dout.p) + j0;
-        L.status = reinterpret_cast<int32_t*>(static_cast<char*>(ctx->m_dout.p) + off_status) + j0;
-        const unsigned blocks = static_cast<unsigned>((nj + jobs_per_block - 1) / jobs_per_block);
+        L.out = reinterpret_cast<double*>(dout) + j0;
+        L.status = reinterpret_cast<int32_t*>(dout + off_status) + j0;
+        unsigned blocks = static_cast<unsigned>((nj + jobs_per_block - 1) / jobs_per_block);
+        if (tree_warp) {
+            blocks = static_cast<unsigned>((nj + tree_warps_per_block - 1) / tree_warps_per_block);
+            if (NW == 1) pnb_msnc_tree_warp_kernel<1><<<blocks, 32 * tree_warps_per_block, dyn_smem, st>>>(L);
+            else pnb_msnc_tree_warp_kernel<2><<<blocks, 32 * tree_warps_per_block, dyn_smem, st>>>(L);
+            PNB_CUDA_TRY(cudaGetLastError());
+            ++launches;
+            continue;
+        }
         // all_smem: frontiers AND staged events / lineage sets of every job are in shared memory (every tree has at most
         // stage_ev_cap events by construction) -> the variant compiled with shared-memory addressing throughout
         const bool all_smem = in_smem && stage;
@@ -825,8 +966,9 @@ static int msnc_launch(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_trees, c
         ++launches;
     }
     if (ctx->profiling) { PNB_CUDA_TRY(cudaEventRecord(ctx->ev[3], st)); ctx->ev_prune = true; }
-    PNB_CUDA_TRY(cudaMemcpyAsync(ctx->m_hout.p, ctx->m_dout.p, off_status + static_cast<size_t>(n_trees) * sizeof(int32_t),
-                                 cudaMemcpyDeviceToHost, st));
+    if (!zero_copy)
+        PNB_CUDA_TRY(cudaMemcpyAsync(ctx->m_hout.p, ctx->m_dout.p, off_status + static_cast<size_t>(n_trees) * sizeof(int32_t),
+                                     cudaMemcpyDeviceToHost, st));
     ctx->msnc_pending_trees = n_trees;
     ctx->msnc_pending_status_off = off_status;
     ctx->msnc_pending_cap = cap;

@@ -388,6 +388,8 @@ struct NetProgram {
     int n_species = 0;
     std::vector<int32_t> step_edge;           // [n_steps][2] up edge ids of each step (-1: none / root branch)
     std::vector<int32_t> retic_step;          // steps that are reticulations
+    std::vector<int32_t> down_step;           // parallel to down_slot: the step whose node sits below that edge
+    std::vector<int32_t> level;               // per step: 0 for a leaf, else 1 + the largest level among its children
     std::vector<std::vector<int32_t>> species_below;   // per reticulation step: species ids below it
 };
 
@@ -472,7 +474,7 @@ inline std::string compile_network(int n_nodes, int n_edges, const int32_t* edge
     // slots by liveness
     out = NetProgram();
     out.n_species = n_species;
-    std::vector<int> slot_of_edge(n_edges, -1), free_slots;
+    std::vector<int> slot_of_edge(n_edges, -1), free_slots, step_of_node(n_nodes, -1);
     int n_slots = 0;
     auto take = [&]() {
         if (!free_slots.empty()) {
@@ -499,6 +501,7 @@ inline std::string compile_network(int n_nodes, int n_edges, const int32_t* edge
                 if (slot_of_edge[e] < 0) return "internal error: edge closed before it was opened";
                 out.down_slot.push_back(slot_of_edge[e]);
                 const int c = edge_dst[e];
+                out.down_step.push_back(step_of_node[c]);
                 below[v].insert(below[v].end(), below[c].begin(), below[c].end());
             }
             std::sort(below[v].begin(), below[v].end());
@@ -535,6 +538,10 @@ inline std::string compile_network(int n_nodes, int n_edges, const int32_t* edge
         for (int e : down[v]) free_slots.push_back(slot_of_edge[e]);
         out.step_edge.push_back(up[v].empty() ? -1 : up[v][0]);
         out.step_edge.push_back(up[v].size() == 2 ? up[v][1] : -1);
+        step_of_node[v] = static_cast<int>(out.steps.size());
+        int lvl = 0;
+        for (int e : down[v]) lvl = std::max(lvl, out.level[step_of_node[edge_dst[e]]] + 1);
+        out.level.push_back(lvl);
         out.steps.push_back(st);
     }
     out.W = std::max(1, n_slots);

@@ -96,6 +96,38 @@ def test_warp_and_thread_kernels_agree(monkeypatch):
     assert n_retic_cases >= 10
 
 
+def test_species_tree_warp_kernel_agrees_with_thread_kernel(monkeypatch):
+    """Species trees, small batches: one warp per gene tree, network nodes of one level side by side, factors added in
+    step order afterwards (pnb_msnc_tree_warp_kernel).  PNB_MSNC_SERIAL=1 runs the one-thread-per-tree walk: same bits.
+    Also on a 40-species tree (more network nodes than lanes) with several alleles per species."""
+    from phynetpy_b200 import simulate as S
+    P = _pkg()
+    n_tree_cases = 0
+    sets = []
+    for case in CASES:
+        net = P.SpeciesNetwork.from_dict(case["network"])
+        if net.info(P.default_context())["reticulations"] == 0:
+            sets.append((case["name"], net, _trees(P, case), case["species_of"], case["theta"], _thetas(case)))
+    rng = np.random.default_rng(202)
+    for n_species, alleles in ((40, 1), (12, 3), (3, 2)):
+        net = S.random_species_network(n_species, 0, rng)
+        trees, species_of = S.simulate_gene_trees_msnc(net, alleles, 0.02, rng, 25)
+        sets.append(("sim_%d_%d" % (n_species, alleles), net, trees, species_of, 0.02, None))
+    for name, net, trees, species_of, theta, bt in sets:
+        n_tree_cases += 1
+        monkeypatch.setenv("PNB_MSNC_SERIAL", "1")
+        a = P.msnc_log_density_batch(trees, net, species_of, theta, branch_thetas=bt)
+        monkeypatch.setenv("PNB_MSNC_SERIAL", "0")
+        b = P.msnc_log_density_batch(trees, net, species_of, theta, branch_thetas=bt)
+        assert np.array_equal(a, b, equal_nan=True), name
+        if name.startswith("sim_"):
+            d = net.to_dict()
+            for t, g in list(zip(trees, b))[:5]:
+                assert _close(float(g), MO.msnc_log_density(d, t.parent.tolist(), t.blen.tolist(), t.label, species_of, theta))
+    monkeypatch.delenv("PNB_MSNC_SERIAL", raising=False)
+    assert n_tree_cases >= 8
+
+
 def test_warp_kernel_large_batch_with_duplicates(monkeypatch):
     """Many gene trees with several alleles per species under two / three reticulations: frontiers of hundreds of
     candidates per step with duplicate entries; blocks of four warps."""

@@ -786,3 +786,44 @@ def test_resident_program_is_not_rewritten_under_a_batch_that_reads_it():
         big = [Z, A, B] * 200
         v3 = eng.score_candidates(0, big)
         assert all(v3[k] == v2[(0, 1, 3)[k % 3]] for k in range(len(big)))
+
+
+def test_split_tail_same_bits(monkeypatch):
+    """PNB_SPLIT_TAIL=1 runs the tiles of a launch's last, partial wave as two half-tile blocks each (every launch of at
+    most half a wave is all half tiles).  A tile's two half sums are formed the same way by one block or by two, so the
+    log-likelihoods are the same bits: single loci of 1 .. 5 tiles (full and dirty-path evaluations, stored, score-only
+    and rescaled) and a batch of 700 small loci (more than one wave of blocks, the tail split)."""
+    P = _pkg()
+    from phynetpy_b200 import simulate as S
+    rng = np.random.default_rng(314)
+    model = P.GTR(S.DEFAULT_PI, S.DEFAULT_RATES)
+
+    def run():
+        out = []
+        r = np.random.default_rng(99)
+        for n, L in ((7, 300), (12, 1400), (20, 2600)):
+            par, bl = S.random_trees(1, n, r)
+            aln = S.simulate_alignments(par, bl, L, S.DEFAULT_PI, S.DEFAULT_RATES, r)[0]
+            ft = S.flat_trees(par, bl)[0]
+            for rescale in (False, True):
+                fc = P.FelsensteinCalculator(S.to_alignment_dict(aln))
+                out.append(fc.log_likelihood(ft, model, rescale=rescale))
+                bl2 = ft.blen.copy()
+                bl2[1] *= 1.3
+                out.append(fc.log_likelihood(ft.with_lengths(bl2), model, rescale=rescale))          # dirty path
+                fc.close()
+        M = 700
+        par, bl = S.random_trees(M, 8, r)
+        aln = S.simulate_alignments(par, bl, 200, S.DEFAULT_PI, S.DEFAULT_RATES, r)
+        eng = P.SeqLikelihoodEngine([S.to_alignment_dict(aln[i]) for i in range(M)], None, model)
+        trees = S.flat_trees(par, bl)
+        out.append(eng.log_likelihood(trees, None, 0.0))
+        out.extend(eng._felsen)
+        return out
+
+    monkeypatch.setenv("PNB_SPLIT_TAIL", "0")
+    a = run()
+    monkeypatch.setenv("PNB_SPLIT_TAIL", "1")
+    b = run()
+    monkeypatch.delenv("PNB_SPLIT_TAIL", raising=False)
+    assert a == b
