@@ -181,6 +181,17 @@ def _cpu_worker_main(conn, kind, payload):
                     calc = RSL.FelsensteinCalculator({t: mat[i].tobytes().decode() for i, t in enumerate(taxa)})
                     items.append((calc, [GeneTree(p.tolist(), [None if b != b else float(b) for b in bl.tolist()], lab)
                                          for p, bl, lab in trees], model, calc.n_patterns))
+                else:                      # ("codes", codes, weights, tip_row, tree): compressed patterns (cfg2) -> the alignment
+                    _, codes, weights, tip_row, (p, bl, lab) = entry      # they came from, column j repeated weights[j] times
+                    assert int(codes.max()) < 4, "unambiguous states only"
+                    cols = np.repeat(np.arange(codes.shape[1]), np.asarray(weights, dtype=np.int64))
+                    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+                    aln = {lab[i]: lut[codes[int(r)][cols]].tobytes().decode() for i, r in enumerate(np.asarray(tip_row).tolist())
+                           if r >= 0 and lab[i] is not None}
+                    calc = RSL.FelsensteinCalculator(aln)
+                    assert calc.n_patterns == codes.shape[1], (calc.n_patterns, codes.shape)
+                    items.append((calc, [GeneTree(p.tolist(), [None if b != b else float(b) for b in bl.tolist()], lab)], model,
+                                  calc.n_patterns))
         else:
             from oracle import felsenstein_oracle as O
             model = O.gtr(PI, RATES)
@@ -238,7 +249,7 @@ class CpuPath:
 
     def __init__(self, entries, procs):
         import multiprocessing as mp
-        self.kind = "reference" if reference_available() and all(e[0] == "aln" for e in entries) else "port"
+        self.kind = "reference" if reference_available() else "port"
         self.procs = max(1, min(procs, len(entries)))
         ctx = mp.get_context("spawn")
         self.workers = []
@@ -286,7 +297,7 @@ def cpu_entries_loci(trees, alns, taxa, scales=(1.0,)):
 def describe_cpu(kind, procs, what):
     impl = ("the UNMODIFIED reference (baseline/_ref: phynetpy._seq_likelihood.FelsensteinCalculator.log_likelihood, "
             "NumPy/OpenBLAS)" if kind == "reference" else
-            "oracle port (NumPy restatement of the reference's _postorder_partials; the reference package is not installed here)")
+            "oracle port (NumPy restatement of the reference's _postorder_partials; baseline/_ref is absent)")
     return "%s on %s, calculators built once outside the clock, loci split over %d worker process(es)" % (impl, what, procs)
 
 

@@ -57,6 +57,18 @@ struct MsncLaunch {
     int64_t warp_job_words;         // warp kernel: 8-byte words of frontier storage per job (msnc_warp_words)
 };
 
+// ONE gene tree (a gene-tree move of the chain): its packed input travels in the kernel parameters -- the root bit, the
+// event list, the species lineage sets and the per-step theta terms would otherwise be three dependent reads of
+// freshly copied (or host-mapped) memory before the DP can start.
+constexpr int MS_MAX_EV = 64, MS_MAX_SP = 32, MS_MAX_THETA = 252;
+struct MsncSmall {
+    int32_t used, n_ev, root_bit, pad;
+    double ev_t[MS_MAX_EV];
+    uint64_t sp[MS_MAX_SP];
+    double theta[MS_MAX_THETA];
+    uint32_t ev_n[MS_MAX_EV];
+};
+
 // ------------------------------------------------------------------------------------------------------------
 // One WARP per gene tree (reticulate networks).  The DP of pnb_msnc_core.hpp::msnc_dp is a loop over network
 // nodes; at each node every frontier entry -- and, at a reticulation, every subset of the lineages that reach it
@@ -351,7 +363,7 @@ __device__ double msnc_dp_warp(const Step* steps, int n_steps, const int32_t* do
 }
 
 template <int NW, bool SMEM>
-__global__ void __launch_bounds__(128) pnb_msnc_warp_kernel(MsncLaunch L) {
+__global__ void __launch_bounds__(128) pnb_msnc_warp_kernel(const __grid_constant__ MsncLaunch L, const __grid_constant__ MsncSmall S) {
     // Dynamic shared memory: [step program | step thetas | down slots] [per warp: frontier storage, if it fits]
     // [per warp: the gene tree's events and species lineage sets, if they fit]
     extern __shared__ uint64_t pnb_msnc_smem[];
@@ -362,14 +374,14 @@ __global__ void __launch_bounds__(128) pnb_msnc_warp_kernel(MsncLaunch L) {
         const uint64_t* src = reinterpret_cast<const uint64_t*>(L.steps);
         const int words = L.n_steps * static_cast<int>(sizeof(Step) / 8);
         for (int i = threadIdx.x; i < words; i += blockDim.x) pnb_msnc_smem[i] = src[i];
-        for (int i = threadIdx.x; i < 4 * L.n_steps; i += blockDim.x) s_theta[i] = L.step_theta[i];
+        for (int i = threadIdx.x; i < 4 * L.n_steps; i += blockDim.x) s_theta[i] = S.used ? S.theta[i] : L.step_theta[i];
         for (int i = threadIdx.x; i < L.n_down; i += blockDim.x) s_down[i] = L.down_slot[i];
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int64_t j = static_cast<int64_t>(blockIdx.x) * wpb + wib;
     if (j >= L.n_jobs) return;
-    const int root_bit = L.root_bit[j];
+    const int root_bit = S.used ? S.root_bit : L.root_bit[j];
     if (root_bit < 0) {   // empty gene tree: density 1 (src/_msnc_density.py:222-223)
         if (lane == 0) { L.out[j] = 0.0; L.status[j] = JOB_OK; }
         return;
@@ -377,11 +389,11 @@ __global__ void __launch_bounds__(128) pnb_msnc_warp_kernel(MsncLaunch L) {
     const size_t job_words = static_cast<size_t>(L.warp_job_words);
     uint64_t* buf = L.frontier_in_smem ? pnb_msnc_smem + L.program_words + wib * job_words
                                        : L.fr_mask + static_cast<size_t>(j) * job_words;
-    const int64_t e0 = L.ev_off[j];
-    const int n_ev = static_cast<int>(L.ev_off[j + 1] - e0);
-    const double* ev_t = L.ev_t + e0;
-    const uint32_t* ev_n = L.ev_n + e0;
-    const uint64_t* sp_mask = L.species_mask + static_cast<size_t>(j) * L.n_species * NW;
+    const int64_t e0 = S.used ? 0 : L.ev_off[j];
+    const int n_ev = S.used ? S.n_ev : static_cast<int>(L.ev_off[j + 1] - e0);
+    const double* ev_t = S.used ? S.ev_t : L.ev_t + e0;
+    const uint32_t* ev_n = S.used ? S.ev_n : L.ev_n + e0;
+    const uint64_t* sp_mask = S.used ? S.sp : L.species_mask + static_cast<size_t>(j) * L.n_species * NW;
     if (L.stage_words > 0 && n_ev <= L.stage_ev_cap) {
         uint64_t* reg = pnb_msnc_smem + L.program_words + (L.frontier_in_smem ? job_words * wpb : 0) +
                         static_cast<size_t>(wib) * L.stage_words;
@@ -411,7 +423,7 @@ __global__ void __launch_bounds__(128) pnb_msnc_warp_kernel(MsncLaunch L) {
 // lineages" factors are flagged and skipped in the sum as msnc_dp_tree skips them) | staged events and species sets.
 // ------------------------------------------------------------------------------------------------------------
 template <int NW>
-__global__ void __launch_bounds__(128) pnb_msnc_tree_warp_kernel(MsncLaunch L) {
+__global__ void __launch_bounds__(128) pnb_msnc_tree_warp_kernel(const __grid_constant__ MsncLaunch L, const __grid_constant__ MsncSmall S) {
     extern __shared__ uint64_t pnb_msnc_smem[];
     Step* s_steps = reinterpret_cast<Step*>(pnb_msnc_smem);
     double* s_theta = reinterpret_cast<double*>(s_steps + L.n_steps);
@@ -420,7 +432,7 @@ __global__ void __launch_bounds__(128) pnb_msnc_tree_warp_kernel(MsncLaunch L) {
         const uint64_t* src = reinterpret_cast<const uint64_t*>(L.steps);
         const int words = L.n_steps * static_cast<int>(sizeof(Step) / 8);
         for (int i = threadIdx.x; i < words; i += blockDim.x) pnb_msnc_smem[i] = src[i];
-        for (int i = threadIdx.x; i < 4 * L.n_steps; i += blockDim.x) s_theta[i] = L.step_theta[i];
+        for (int i = threadIdx.x; i < 4 * L.n_steps; i += blockDim.x) s_theta[i] = S.used ? S.theta[i] : L.step_theta[i];
         for (int i = threadIdx.x; i < 2 * L.n_down + L.n_steps; i += blockDim.x) s_down[i] = L.down_slot[i];
     }
     __syncthreads();
@@ -429,7 +441,7 @@ __global__ void __launch_bounds__(128) pnb_msnc_tree_warp_kernel(MsncLaunch L) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int64_t j = static_cast<int64_t>(blockIdx.x) * wpb + wib;
     if (j >= L.n_jobs) return;
-    const int root_bit = L.root_bit[j];
+    const int root_bit = S.used ? S.root_bit : L.root_bit[j];
     if (root_bit < 0) {   // empty gene tree: density 1 (src/_msnc_density.py:222-223)
         if (lane == 0) { L.out[j] = 0.0; L.status[j] = JOB_OK; }
         return;
@@ -440,13 +452,17 @@ __global__ void __launch_bounds__(128) pnb_msnc_tree_warp_kernel(MsncLaunch L) {
     double* blp = reinterpret_cast<double*>(reg + static_cast<size_t>(n_steps) * NW);   // [n_steps]
     int32_t* counted = reinterpret_cast<int32_t*>(reg + static_cast<size_t>(n_steps) * (NW + 1));   // [n_steps]: factor enters the sum
     uint64_t* stage = reg + static_cast<size_t>(n_steps) * (NW + 1) + (n_steps + 1) / 2;
-    const int64_t e0 = L.ev_off[j];
-    const int n_ev = static_cast<int>(L.ev_off[j + 1] - e0);
+    const int64_t e0 = S.used ? 0 : L.ev_off[j];
+    const int n_ev = S.used ? S.n_ev : static_cast<int>(L.ev_off[j + 1] - e0);
     double* ev_t = reinterpret_cast<double*>(stage);
     uint32_t* ev_n = reinterpret_cast<uint32_t*>(stage + L.stage_ev_cap);
     uint64_t* sp_mask = stage + L.stage_ev_cap + (L.stage_ev_cap + 1) / 2;
-    for (int i = lane; i < n_ev; i += 32) { ev_t[i] = L.ev_t[e0 + i]; ev_n[i] = L.ev_n[e0 + i]; }
-    for (int i = lane; i < L.n_species * NW; i += 32) sp_mask[i] = L.species_mask[static_cast<size_t>(j) * L.n_species * NW + i];
+    for (int i = lane; i < n_ev; i += 32) {
+        ev_t[i] = S.used ? S.ev_t[i] : L.ev_t[e0 + i];
+        ev_n[i] = S.used ? S.ev_n[i] : L.ev_n[e0 + i];
+    }
+    for (int i = lane; i < L.n_species * NW; i += 32)
+        sp_mask[i] = S.used ? S.sp[i] : L.species_mask[static_cast<size_t>(j) * L.n_species * NW + i];
     int max_level = 0;
     for (int s = lane; s < n_steps; s += 32) max_level = max(max_level, s_level[s]);
     max_level = __reduce_max_sync(0xffffffffu, max_level);
@@ -498,7 +514,7 @@ __global__ void __launch_bounds__(128) pnb_msnc_tree_warp_kernel(MsncLaunch L) {
 }
 
 template <int NW, bool SMEM>
-__global__ void __launch_bounds__(128) pnb_msnc_kernel(MsncLaunch L) {
+__global__ void __launch_bounds__(128) pnb_msnc_kernel(const __grid_constant__ MsncLaunch L, const __grid_constant__ MsncSmall S) {
     // Dynamic shared memory: [step program | step thetas | down slots] [frontiers, if they fit].
     // Every thread walks the same program; staging it once per block turns ~3 dependent global loads per
     // step (L2 / DRAM latency each when the batch is a single gene tree) into shared-memory broadcasts.
@@ -510,19 +526,19 @@ __global__ void __launch_bounds__(128) pnb_msnc_kernel(MsncLaunch L) {
         const uint64_t* src = reinterpret_cast<const uint64_t*>(L.steps);
         const int words = L.n_steps * static_cast<int>(sizeof(Step) / 8);
         for (int i = threadIdx.x; i < words; i += blockDim.x) pnb_msnc_smem[i] = src[i];
-        for (int i = threadIdx.x; i < 4 * L.n_steps; i += blockDim.x) s_theta[i] = L.step_theta[i];
+        for (int i = threadIdx.x; i < 4 * L.n_steps; i += blockDim.x) s_theta[i] = S.used ? S.theta[i] : L.step_theta[i];
         for (int i = threadIdx.x; i < L.n_down; i += blockDim.x) s_down[i] = L.down_slot[i];
     }
     __syncthreads();
     const int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (j >= L.n_jobs) return;
-    const int root_bit = L.root_bit[j];
+    const int root_bit = S.used ? S.root_bit : L.root_bit[j];
     if (root_bit < 0) {   // empty gene tree: density 1 (src/_msnc_density.py:222-223)
         L.out[j] = 0.0;
         L.status[j] = JOB_OK;
         return;
     }
-    const int64_t e0 = L.ev_off[j];
+    const int64_t e0 = S.used ? 0 : L.ev_off[j];
     const size_t mask_words = msnc_mask_words(L.W, NW, L.cap);
     // Frontier storage.  A thread re-reads what it has just written (copy entry, merge slots, compare
     // for duplicates): in global memory every such read is an L2 round trip, in shared memory ~30 cycles.
@@ -543,10 +559,10 @@ __global__ void __launch_bounds__(128) pnb_msnc_kernel(MsncLaunch L) {
     // The DP looks its events up again and again (two binary searches per step, a scan per entry and branch): from global
     // memory every probe is an L2 round trip, which is most of a single gene tree's latency.  When the block's shared
     // memory has room, each thread first copies its tree's events and species masks next to the frontiers.
-    const int n_ev = static_cast<int>(L.ev_off[j + 1] - e0);
-    const double* ev_t = L.ev_t + e0;
-    const uint32_t* ev_n = L.ev_n + e0;
-    const uint64_t* sp_mask = L.species_mask + static_cast<size_t>(j) * L.n_species * NW;
+    const int n_ev = S.used ? S.n_ev : static_cast<int>(L.ev_off[j + 1] - e0);
+    const double* ev_t = S.used ? S.ev_t : L.ev_t + e0;
+    const uint32_t* ev_n = S.used ? S.ev_n : L.ev_n + e0;
+    const uint64_t* sp_mask = S.used ? S.sp : L.species_mask + static_cast<size_t>(j) * L.n_species * NW;
     if (L.stage_words > 0 && n_ev <= L.stage_ev_cap) {
         uint64_t* reg = pnb_msnc_smem + L.program_words + (L.frontier_in_smem ? (mask_words + 2 * static_cast<size_t>(L.cap)) * blockDim.x : 0) +
                         static_cast<size_t>(threadIdx.x) * L.stage_words;
@@ -909,7 +925,19 @@ static int msnc_launch(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_trees, c
                     cudaHostGetDevicePointer(&db, ctx->m_hout.p, 0) == cudaSuccess && db == ctx->m_hout.p;
         if (!zero_copy) (void)cudaGetLastError();
     }
-    if (!zero_copy) PNB_CUDA_TRY(cudaMemcpyAsync(ctx->m_dstage.p, hs, stage_bytes, cudaMemcpyHostToDevice, st));
+    MsncSmall small;
+    small.used = 0;
+    if (n_trees == 1 && ev_off[1] <= MS_MAX_EV && static_cast<size_t>(n_species) * NW <= MS_MAX_SP &&
+        prog.steps.size() * 4 <= MS_MAX_THETA && root_bit[0] >= 0) {
+        small.used = 1;
+        small.n_ev = static_cast<int32_t>(ev_off[1]);
+        small.root_bit = root_bit[0];
+        memcpy(small.ev_t, ev_t, static_cast<size_t>(ev_off[1]) * sizeof(double));
+        memcpy(small.ev_n, ev_n, static_cast<size_t>(ev_off[1]) * sizeof(uint32_t));
+        memcpy(small.sp, sp_mask, static_cast<size_t>(n_species) * NW * sizeof(uint64_t));
+        memcpy(small.theta, hs + off_theta, prog.steps.size() * 4 * sizeof(double));
+    }
+    if (!zero_copy && !small.used) PNB_CUDA_TRY(cudaMemcpyAsync(ctx->m_dstage.p, hs, stage_bytes, cudaMemcpyHostToDevice, st));
     if (ctx->profiling) PNB_CUDA_TRY(cudaEventRecord(ctx->ev[2], st));   // reported as the "prune" slot of last_timings
     char* ds = zero_copy ? hs : static_cast<char*>(ctx->m_dstage.p);
     char* dout = static_cast<char*>(zero_copy ? ctx->m_hout.p : ctx->m_dout.p);
@@ -946,8 +974,8 @@ static int msnc_launch(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_trees, c
         unsigned blocks = static_cast<unsigned>((nj + jobs_per_block - 1) / jobs_per_block);
         if (tree_warp) {
             blocks = static_cast<unsigned>((nj + tree_warps_per_block - 1) / tree_warps_per_block);
-            if (NW == 1) pnb_msnc_tree_warp_kernel<1><<<blocks, 32 * tree_warps_per_block, dyn_smem, st>>>(L);
-            else pnb_msnc_tree_warp_kernel<2><<<blocks, 32 * tree_warps_per_block, dyn_smem, st>>>(L);
+            if (NW == 1) pnb_msnc_tree_warp_kernel<1><<<blocks, 32 * tree_warps_per_block, dyn_smem, st>>>(L, small);
+            else pnb_msnc_tree_warp_kernel<2><<<blocks, 32 * tree_warps_per_block, dyn_smem, st>>>(L, small);
             PNB_CUDA_TRY(cudaGetLastError());
             ++launches;
             continue;
@@ -956,11 +984,11 @@ static int msnc_launch(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_trees, c
         // stage_ev_cap events by construction) -> the variant compiled with shared-memory addressing throughout
         const bool all_smem = in_smem && stage;
         if (warp_mode) {
-            if (NW == 1) { if (all_smem) pnb_msnc_warp_kernel<1, true><<<blocks, threads, dyn_smem, st>>>(L); else pnb_msnc_warp_kernel<1, false><<<blocks, threads, dyn_smem, st>>>(L); }
-            else { if (all_smem) pnb_msnc_warp_kernel<2, true><<<blocks, threads, dyn_smem, st>>>(L); else pnb_msnc_warp_kernel<2, false><<<blocks, threads, dyn_smem, st>>>(L); }
+            if (NW == 1) { if (all_smem) pnb_msnc_warp_kernel<1, true><<<blocks, threads, dyn_smem, st>>>(L, small); else pnb_msnc_warp_kernel<1, false><<<blocks, threads, dyn_smem, st>>>(L, small); }
+            else { if (all_smem) pnb_msnc_warp_kernel<2, true><<<blocks, threads, dyn_smem, st>>>(L, small); else pnb_msnc_warp_kernel<2, false><<<blocks, threads, dyn_smem, st>>>(L, small); }
         } else {
-            if (NW == 1) { if (all_smem) pnb_msnc_kernel<1, true><<<blocks, threads, dyn_smem, st>>>(L); else pnb_msnc_kernel<1, false><<<blocks, threads, dyn_smem, st>>>(L); }
-            else { if (all_smem) pnb_msnc_kernel<2, true><<<blocks, threads, dyn_smem, st>>>(L); else pnb_msnc_kernel<2, false><<<blocks, threads, dyn_smem, st>>>(L); }
+            if (NW == 1) { if (all_smem) pnb_msnc_kernel<1, true><<<blocks, threads, dyn_smem, st>>>(L, small); else pnb_msnc_kernel<1, false><<<blocks, threads, dyn_smem, st>>>(L, small); }
+            else { if (all_smem) pnb_msnc_kernel<2, true><<<blocks, threads, dyn_smem, st>>>(L, small); else pnb_msnc_kernel<2, false><<<blocks, threads, dyn_smem, st>>>(L, small); }
         }
         PNB_CUDA_TRY(cudaGetLastError());
         ++launches;
