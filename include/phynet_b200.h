@@ -220,6 +220,17 @@ PNB_API int pnb_batch_eval(pnb_batch *b, const pnb_model *m, const double *blen,
  * over NVLink, no collective kernel; the caller orders consumers with one cross-GPU barrier.  n_peers = 0 turns
  * it off.  At most 7 peers.                                                                              */
 PNB_API int pnb_batch_set_peer_outputs(pnb_batch *b, int32_t n_peers, double *const *peer_out);
+/* The cross-GPU barrier of that fused collective, issued by the kernel itself: the block that finishes the LAST job of
+ * the next evaluation publishes `epoch` in peer_flag[r] -- the slot [this rank] of peer r's flag array, peer-mapped
+ * like peer_out -- and waits until my_flags[peer_rank[r]] >= epoch for every peer, so when the kernel has completed on
+ * this rank every peer's stores into this rank's vector have landed.  Flag arrays are uint64[world] in the same
+ * symmetric allocation as the vectors, zero at start; the caller owns the epoch counter (1, 2, 3, ... in the order all
+ * ranks run their sharded evaluations) and arms the barrier before EACH evaluation (it is used once).  A peer that
+ * does not arrive within ~2 s sets a flag (pnb_batch_barrier_timed_out) instead of hanging the kernel.
+ * Replaces: the NCCL collective after the kernel (src/_mcmc_seq.py:746-761 is a plain sum over loci).      */
+PNB_API int pnb_batch_set_peer_barrier(pnb_batch *b, int32_t n_peers, uint64_t *const *peer_flag,
+                                       const uint64_t *my_flags, const int32_t *peer_rank, uint64_t epoch);
+PNB_API int pnb_batch_barrier_timed_out(const pnb_batch *b, int32_t *timed_out);
 
 /* ---- K-m: timed MSNC density log P(g | Psi) ---------------------- */
 /* The other factor of the MCMC_SEQ likelihood, sum_i [log P(S_i|g_i) + log P(g_i|Psi)]

@@ -237,7 +237,7 @@ class SeqLikelihoodEngine:
     BATCH_MIN_LOCI = 32   # all-local-loci evaluations of at least this many loci go through a resident batch
 
     def _eval_all_local(self, idx: Sequence[int], gene_trees: Sequence[Any], out_device_ptr: Optional[int] = None,
-                        peer_ptrs: Sequence[int] = ()) -> Optional[np.ndarray]:
+                        peer_ptrs: Sequence[int] = (), barrier: Optional[tuple] = None) -> Optional[np.ndarray]:
         """Every local locus at once through a resident batch: the op programs of the previous such evaluation
         are reused when the topologies are the same (one memcmp of the packed parent arrays), so only branch
         lengths travel.  The evaluation is committed at once: the loci's partial caches are content-addressed,
@@ -256,12 +256,16 @@ class SeqLikelihoodEngine:
             self._batch_key = (self._mode, parent, tip_row, node_off)
         try:
             self._batch.set_peer_outputs(list(peer_ptrs))
+            if barrier is not None:
+                self._batch.set_peer_barrier(*barrier)
             out = self._batch.eval(mh, blen, 1.0, out_device_ptr)
         except _lib.PhyNetB200Error:
             # a locus was re-allocated or destroyed underneath the batch: build it again, once
             self._batch.close()
             self._batch = ResidentBatch(ctx, mh, self._handles(idx), node_off, parent, tip_row, self._mode)
             self._batch.set_peer_outputs(list(peer_ptrs))
+            if barrier is not None:
+                self._batch.set_peer_barrier(*barrier)
             out = self._batch.eval(mh, blen, 1.0, out_device_ptr)
         self.last_stats = ctx.last_stats()
         return out
@@ -286,9 +290,11 @@ class SeqLikelihoodEngine:
                 n = per * plan.world_size
                 if sym is not None:
                     # two copies of the vector, used alternately by consecutive evaluations (ShardPlan.symmetric_vector)
-                    sh["vecs"], sh["sym"] = [sym[0][:n], sym[0][n:]], sym[1]
+                    sh["vecs"], sh["sym"] = [sym[0][:n], sym[0][n:2 * n]], sym[1]
                     sh["peers"] = [[sym[1].buffer_ptrs[r] + 8 * (c * n + plan.rank * per) for r in range(plan.world_size)
                                     if r != plan.rank] for c in range(2)]
+                    sh["barrier"] = plan.peer_barrier_args(sym[1])     # kernel-issued barrier: flag addresses, peers' ranks
+                    sh["epoch"] = 0
                 else:
                     sh["vecs"], sh["sym"], sh["peers"] = [torch.zeros(n, dtype=torch.float64, device=dev)] * 2, None, [[], []]
                 sh["turn"] = 0
@@ -322,8 +328,11 @@ class SeqLikelihoodEngine:
                         # every rank takes this branch together (every rank's shard is dirty as a whole): with symmetric
                         # memory the kernel's peer stores + one device-side barrier replace the all-gather
                         fused = sh["sym"] is not None and len(self._dirty_any) == self.n_loci
+                        if fused:
+                            sh["epoch"] += 1      # every rank counts the same fused evaluations
                         self._eval_all_local(dirty, gene_trees, out_device_ptr=vec.data_ptr() + 8 * base,
-                                             peer_ptrs=sh["peers"][turn] if fused else [])
+                                             peer_ptrs=sh["peers"][turn] if fused else [],
+                                             barrier=(sh["barrier"] + (sh["epoch"],)) if fused else None)
                     elif len(dirty) == hi - lo:
                         # the whole shard through pnb_eval (dirty-path aware, pending): the kernel writes this rank's slice
                         self.felsenstein_batch(dirty, gene_trees, flags=flags, out_device_ptr=vec.data_ptr() + 8 * base)
@@ -333,12 +342,12 @@ class SeqLikelihoodEngine:
                         self._pending = list(dirty)
                         pos = torch.from_numpy(base + np.asarray(dirty, dtype=np.int64) - lo).to(vec.device)
                         vec.index_copy_(0, pos, torch.from_numpy(np.ascontiguousarray(vals)).to(vec.device))
-                if fused:
-                    sh["sym"].barrier()
-                else:
+                if not fused:    # (fused: the kernel's last block has exchanged epochs with every peer before it completed)
                     plan.allgather_slices_(vec)
                 sh["host"].copy_(vec, non_blocking=True)
             sh["stream"].synchronize()
+            if fused and self._batch is not None and self._batch.barrier_timed_out():
+                raise RuntimeError("sharded evaluation: a peer GPU did not reach the barrier of the fused collective within 2 s")
         else:
             if dirty:
                 vals = self.felsenstein_batch(dirty, gene_trees, flags=flags)

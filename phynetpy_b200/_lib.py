@@ -40,7 +40,7 @@ ABI_SYMBOLS = (
     "pnb_pmatrix_batch", "pnb_compress",
     "pnb_locus_create", "pnb_locus_destroy", "pnb_locus_invalidate", "pnb_locus_read_partial",
     "pnb_eval", "pnb_commit", "pnb_rollback",
-    "pnb_batch_create", "pnb_batch_destroy", "pnb_batch_info", "pnb_batch_traffic", "pnb_batch_blen_host", "pnb_batch_eval", "pnb_batch_set_peer_outputs",
+    "pnb_batch_create", "pnb_batch_destroy", "pnb_batch_info", "pnb_batch_traffic", "pnb_batch_blen_host", "pnb_batch_eval", "pnb_batch_set_peer_outputs", "pnb_batch_set_peer_barrier", "pnb_batch_barrier_timed_out",
     "pnb_ctx_create_host", "pnb_plan",
     "pnb_msnc_net_create", "pnb_msnc_net_destroy", "pnb_msnc_net_info", "pnb_msnc_net_set_max_frontier", "pnb_msnc_net_set_branch_thetas",
     "pnb_msnc_eval", "pnb_eval_move",
@@ -108,6 +108,8 @@ def load() -> C.CDLL:
             "pnb_batch_blen_host": [_vp, C.POINTER(_vp)],
             "pnb_batch_eval": [_vp, _vp, _vp, C.c_double, C.c_uint32, _vp],
             "pnb_batch_set_peer_outputs": [_vp, _i32, _vp],
+            "pnb_batch_set_peer_barrier": [_vp, _i32, C.POINTER(_vp), _vp, C.POINTER(_i32), C.c_uint64],
+            "pnb_batch_barrier_timed_out": [_vp, C.POINTER(_i32)],
             "pnb_commit": [_vp, _i64, _vp],
             "pnb_rollback": [_vp, _i64, _vp],
             "pnb_ctx_create_host": [C.POINTER(_vp)],

@@ -36,6 +36,14 @@ struct pnb_batch {
     int64_t traffic[4] = {0, 0, 0, 0};  // bytes per evaluation, counted from the programs (pnb_batch_traffic)
     int n_peers = 0;                    // fused collective: peers' output vectors (pnb_batch_set_peer_outputs)
     double* peer_out[MAX_PEERS] = {nullptr};
+    // in-kernel barrier of the fused collective (pnb_batch_set_peer_barrier): armed for ONE evaluation at a time
+    unsigned long long bar_epoch = 0;
+    unsigned long long* bar_peer[MAX_PEERS] = {nullptr};
+    const unsigned long long* bar_mine = nullptr;
+    int32_t bar_rank[MAX_PEERS] = {0};
+    int64_t jobs_with_tiles = 0;     // jobs the kernel finishes (a locus without patterns has no tile)
+    Buffer d_launch_done;            // one counter
+    int32_t* h_bar_timeout = nullptr;   // pinned + mapped
     // chunks of jobs for the pipelined host-lengths path: [c] = first job / node / op / tile of chunk c
     std::vector<int64_t> ck_job, ck_node, ck_op, ck_tile;
     // state of the last evaluation (what locus_sync materialises)
@@ -51,10 +59,12 @@ namespace {
 
 void batch_free(pnb_batch* b) {
     for (Buffer* q : {&b->d_jobs, &b->d_tile_job, &b->d_ops, &b->d_node_of_op, &b->d_blen, &b->d_P, &b->d_tile_sum,
-                      &b->d_job_done, &b->d_out})
+                      &b->d_job_done, &b->d_out, &b->d_launch_done})
         if (q->p) cudaFree(q->p);
     if (b->h_blen.p) cudaFreeHost(b->h_blen.p);
     if (b->h_out.p) cudaFreeHost(b->h_out.p);
+    if (b->h_bar_timeout) cudaFreeHost(b->h_bar_timeout);
+
     delete b;
 }
 
@@ -262,8 +272,10 @@ extern "C" int pnb_batch_create(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb
         jd.out_index = static_cast<int32_t>(j);
         jd.scale = loc->d_scale;
         jd.ops = nullptr;  // patched below once the device array exists
-        if (loc->P > 0)
+        if (loc->P > 0) {
             for (int64_t t = tile_first[j]; t < tile_first[j + 1]; ++t) h_tile_job[t] = static_cast<int32_t>(j);
+            b->jobs_with_tiles++;
+        }
         {
             // what the kernel moves for this job, per evaluation: every F_STORE writes one 32-byte partial per (padded)
             // pattern, every K_MEM op reads one (a sibling written earlier in the same launch: normally an L2 hit),
@@ -398,6 +410,50 @@ extern "C" int pnb_batch_set_peer_outputs(pnb_batch* b, int32_t n_peers, double*
     return PNB_OK;
 }
 
+extern "C" int pnb_batch_set_peer_barrier(pnb_batch* b, int32_t n_peers, uint64_t* const* peer_flag, const uint64_t* my_flags,
+                                          const int32_t* peer_rank, uint64_t epoch) {
+    PNB_REQUIRE(b != nullptr, PNB_ERR_INVALID, "pnb_batch_set_peer_barrier: NULL batch");
+    if (n_peers == 0 || epoch == 0) {
+        b->bar_epoch = 0;
+        return PNB_OK;
+    }
+    PNB_REQUIRE(n_peers > 0 && n_peers <= MAX_PEERS, PNB_ERR_INVALID, "pnb_batch_set_peer_barrier: %d peers (at most %d)", n_peers,
+                MAX_PEERS);
+    PNB_REQUIRE(peer_flag && my_flags && peer_rank, PNB_ERR_INVALID, "pnb_batch_set_peer_barrier: NULL array");
+    PNB_REQUIRE(n_peers == b->n_peers, PNB_ERR_STATE,
+                "pnb_batch_set_peer_barrier: %d peers, but pnb_batch_set_peer_outputs named %d (the barrier orders THOSE stores)",
+                n_peers, b->n_peers);
+    for (int r = 0; r < n_peers; ++r)
+        PNB_REQUIRE(peer_flag[r] != nullptr && peer_rank[r] >= 0 && peer_rank[r] < 64, PNB_ERR_INVALID,
+                    "pnb_batch_set_peer_barrier: peer %d: NULL flag slot or bad rank", r);
+    pnb_ctx* ctx = b->ctx;
+    PNB_CUDA_TRY(cudaSetDevice(ctx->device));
+    if (!b->d_launch_done.p) {
+        int rc = ensure_device(b->d_launch_done, 256);
+        if (rc) return rc;
+        PNB_CUDA_TRY(cudaMemsetAsync(b->d_launch_done.p, 0, 256, ctx->stream));
+    }
+    if (!b->h_bar_timeout) {
+        void* p = nullptr;
+        PNB_CUDA_TRY(cudaHostAlloc(&p, 64, cudaHostAllocMapped));
+        memset(p, 0, 64);
+        b->h_bar_timeout = static_cast<int32_t*>(p);
+    }
+    for (int r = 0; r < MAX_PEERS; ++r) {
+        b->bar_peer[r] = r < n_peers ? reinterpret_cast<unsigned long long*>(peer_flag[r]) : nullptr;
+        b->bar_rank[r] = r < n_peers ? peer_rank[r] : 0;
+    }
+    b->bar_mine = reinterpret_cast<const unsigned long long*>(my_flags);
+    b->bar_epoch = epoch;
+    return PNB_OK;
+}
+
+extern "C" int pnb_batch_barrier_timed_out(const pnb_batch* b, int32_t* timed_out) {
+    PNB_REQUIRE(b && timed_out, PNB_ERR_INVALID, "pnb_batch_barrier_timed_out: NULL argument");
+    *timed_out = b->h_bar_timeout ? *static_cast<volatile int32_t*>(b->h_bar_timeout) : 0;
+    return PNB_OK;
+}
+
 extern "C" int pnb_batch_blen_host(pnb_batch* b, double** pinned_out) {
     PNB_REQUIRE(b && pinned_out, PNB_ERR_INVALID, "pnb_batch_blen_host: NULL argument");
     *pinned_out = static_cast<double*>(b->h_blen.p);
@@ -454,6 +510,21 @@ extern "C" int pnb_batch_eval(pnb_batch* b, const pnb_model* m, const double* bl
     L.tile_base = 0;
     L.n_peers = out_dev ? b->n_peers : 0;
     for (int r = 0; r < MAX_PEERS; ++r) L.peer_out[r] = b->peer_out[r];
+    // the barrier is armed for this evaluation only (the caller owns the epoch counter that lives with the flags)
+    L.bar_epoch = (L.n_peers > 0) ? b->bar_epoch : 0;
+    b->bar_epoch = 0;
+    L.launch_jobs = static_cast<int32_t>(b->jobs_with_tiles);
+    L.out_len = static_cast<int32_t>(M);
+    if (b->jobs_with_tiles == 0) L.bar_epoch = 0;   // nothing runs, nothing can signal
+    L.launch_done = static_cast<unsigned int*>(b->d_launch_done.p);
+    L.bar_mine = b->bar_mine;
+    L.bar_timeout = nullptr;
+    for (int r = 0; r < MAX_PEERS; ++r) { L.bar_peer[r] = b->bar_peer[r]; L.bar_rank[r] = b->bar_rank[r]; }
+    if (L.bar_epoch) {
+        void* dp = nullptr;
+        PNB_CUDA_TRY(cudaHostGetDevicePointer(&dp, b->h_bar_timeout, 0));
+        L.bar_timeout = static_cast<int32_t*>(dp);
+    }
     int64_t h2d = 0, d2h = 0, launches = 0;
     const double* d_blen = static_cast<const double*>(b->d_blen.p);
     int rc;

@@ -353,6 +353,7 @@ int pnb::compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int3
     int n_ops = 0, n_tip_ops = 0;
     const bool compute_root = cnt[root] > 0 && (dirty[root] || virt[root]);
     const int stash_levels = nostore ? (1 << 30) : loc->ctx->store_stash_levels;
+    const bool hold_reg = loc->ctx->hold_reg;
     if (compute_root) {
         auto& fs = S.frames;
         auto& dk = S.dk;
@@ -390,7 +391,12 @@ int pnb::compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int3
                     const int sp = f.sp;
                     const bool is_last = i == f.kd - 1;
                     int disp = -1;
-                    if (!is_last) disp = (nostore || sp + i < stash_levels) ? sp + i : -2;
+                    if (!is_last) {
+                        // the innermost waiting sibling -- nothing else is held while the last sibling is computed -- stays in
+                        // the kernel's HOLD registers: no stash slot, no L2 round trip, and no write at all if it is virtual
+                        const bool reg_hold = hold_reg && i == f.kd - 2 && need[dk[base + f.kd - 1]] == 0;
+                        disp = reg_hold ? -3 : ((nostore || sp + i < stash_levels) ? sp + i : -2);
+                    }
                     open(d, sp + i, disp);
                     continue;
                 }
@@ -414,7 +420,8 @@ int pnb::compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int3
             if (f.kd > 0) add(K_REG, 0, 0, dk[base + f.kd - 1]);
             for (int i = 0; i + 1 < f.kd; ++i) {
                 const int d = dk[base + i];
-                if (nostore || f.sp + i < stash_levels) add(K_STK, f.sp + i, 0, d);
+                if (hold_reg && i == f.kd - 2 && need[dk[base + f.kd - 1]] == 0) add(K_STK, -1, 0, d);   // from the HOLD registers
+                else if (nostore || f.sp + i < stash_levels) add(K_STK, f.sp + i, 0, d);
                 else add(K_MEM, static_cast<int>(ref[d] - n_rows), 0, d);
             }
             for (int j = 0; j < cnt[v]; ++j) {
@@ -435,6 +442,7 @@ int pnb::compile_job(CompileScratch& S, pnb_locus* loc, const pnb_model* m, int3
                 last.dst = static_cast<int>(ref[v] - n_rows);
                 loc->pending.stored[last.dst] = 1;
             }
+            if (f.push_idx == -3) last.flags |= F_HOLD;
             if (f.push_idx >= 0) {
                 CJ_REQUIRE(f.push_idx < 256, PNB_ERR_UNSUPPORTED, "pnb_eval: stash depth %d exceeds 255", f.push_idx);
                 last.flags |= F_PUSH | (static_cast<uint32_t>(f.push_idx) << 8);

@@ -42,6 +42,12 @@ constexpr uint32_t F_FIRST = 0x4u;   // first child of its node: acc  = v
 constexpr uint32_t F_LAST  = 0x8u;   // last child of its node: `acc` is now the complete node partial
 constexpr uint32_t F_STORE = 0x10u;  // on F_LAST: write the node partial to HBM slot `dst`
 constexpr uint32_t F_PUSH  = 0x20u;  // on F_LAST: stash the node partial in smem stack[(flags>>8)&0xff]
+constexpr uint32_t F_HOLD  = 0x40u;  // on F_LAST: keep the node partial in the HOLD registers (read back by K_STK with src < 0)
+#ifdef PNB_HOLD
+constexpr bool HOLD_REGS = true;     // the kernel has a second register set for ONE waiting sibling (host compiler: hold_reg)
+#else
+constexpr bool HOLD_REGS = false;
+#endif
 
 // One op = one (parent <- child) edge: v = P(edge) . L(child); acc (*)= v.
 // Op k of a job uses P matrix k of that job (one-to-one), so the program and
@@ -103,6 +109,17 @@ struct PruneLaunch {
     // same slot of every peer's vector -- peer-mapped device pointers (NVLink / NVSwitch), 8 bytes per peer and job
     int32_t n_peers;
     double* peer_out[MAX_PEERS];
+    // ... and the barrier that orders the peers' consumers after those stores, issued by the block that finishes the
+    // evaluation's LAST job (bar_epoch != 0): it publishes bar_epoch in slot [this rank] of every peer's flag array and
+    // waits until every peer's epoch has arrived in its own -- no separate barrier launch after the kernel
+    int32_t launch_jobs;               // jobs of the whole evaluation that have tiles (it may be launched in chunks)
+    int32_t out_len;                   // values in this rank's slice of the vector (out[0 .. out_len))
+    unsigned int* launch_done;         // finished jobs of the evaluation (self-resetting)
+    unsigned long long bar_epoch;
+    unsigned long long* bar_peer[MAX_PEERS];     // slot [this rank] of peer r's flag array (peer-mapped)
+    const unsigned long long* bar_mine;          // this rank's flag array, indexed by rank
+    int32_t bar_rank[MAX_PEERS];                 // rank of peer r
+    int32_t* bar_timeout;                        // mapped host word: set when a peer did not arrive within ~2 s
 };
 
 // FUSED launches of one or two loci (the single-locus MCMC step): the tile map, the job descriptors, the op program and
@@ -397,6 +414,7 @@ __device__ __forceinline__ void prune_tile(const PruneLaunch& L, const ModelPara
     __shared__ __align__(8) uint64_t bar_stage;
     __shared__ double red[TPB / 32];
     __shared__ int s_is_last;
+    __shared__ int s_final;
     __shared__ int s_rows;
 
     const int tid = threadIdx.x;
@@ -441,6 +459,10 @@ __device__ __forceinline__ void prune_tile(const PruneLaunch& L, const ModelPara
     int acc_e[NP]; // RESCALE: binary exponent carried by `acc` (true partial = acc * 2^acc_e)
 #pragma unroll
     for (int u = 0; u < NP; ++u) { acc[u] = {1.0, 1.0, 1.0, 1.0}; acc_e[u] = 0; }
+    Vec4 hold[NP];   // HOLD_REGS: one waiting sibling (the innermost: nothing is held while its last sibling is computed)
+    int hold_e[NP];
+#pragma unroll
+    for (int u = 0; u < NP; ++u) { hold[u] = {1.0, 1.0, 1.0, 1.0}; hold_e[u] = 0; }
     int32_t* scale0 = RESCALE ? jd.scale + (pu0 + tid) : nullptr;
     const int64_t scale_stride = slot_stride / 4;  // ints per slot (= P_pad)
     // stash exponents live behind the stash partials: [stk_cap][TILE_PATTERNS] int32
@@ -557,6 +579,9 @@ __device__ __forceinline__ void prune_tile(const PruneLaunch& L, const ModelPara
 #pragma unroll
                         for (int u = 0; u < NP; ++u) le[u] = ge[u * TPB];
                     }
+                } else if (HOLD_REGS && src < 0) {
+#pragma unroll
+                    for (int u = 0; u < NP; ++u) { l[u] = hold[u]; le[u] = hold_e[u]; }
                 } else {
                     const uint32_t a = stk_addr + static_cast<uint32_t>(src) * (TILE_PATTERNS * 32);
 #pragma unroll
@@ -601,6 +626,10 @@ __device__ __forceinline__ void prune_tile(const PruneLaunch& L, const ModelPara
 #pragma unroll
                         for (int u = 0; u < NP; ++u) ge[u * TPB] = acc_e[u];
                     }
+                }
+                if (HOLD_REGS && (flags & F_HOLD)) {
+#pragma unroll
+                    for (int u = 0; u < NP; ++u) { hold[u] = acc[u]; hold_e[u] = acc_e[u]; }
                 }
                 if (flags & F_PUSH) {
                     const uint32_t a = stk_addr + ((flags >> 8) & 0xffu) * (TILE_PATTERNS * 32);
@@ -680,8 +709,63 @@ __device__ __forceinline__ void prune_tile(const PruneLaunch& L, const ModelPara
         const double total = block_sum(s, red);
         if (tid == 0) {
             L.out[jd.out_index] = total;
-            for (int r = 0; r < L.n_peers; ++r) L.peer_out[r][jd.out_index] = total;   // stores over NVLink into the peers' vectors
             L.job_done[job] = 0u;
+            s_final = 0;
+            if (L.bar_epoch == 0ull) {
+                // peers ordered by a barrier the caller launches: every finished job goes to the peers' vectors at once
+                for (int r = 0; r < L.n_peers; ++r) L.peer_out[r][jd.out_index] = total;   // stores over NVLink
+            } else {
+                // release pattern at GPU scope: this job's value happens before its arrival
+                __threadfence();
+                if (atomicAdd(L.launch_done, 1u) == static_cast<unsigned int>(L.launch_jobs) - 1u) {
+                    __threadfence();   // acquire side: every other job's value is visible to this block
+                    s_final = 1;
+                }
+            }
+        }
+        __syncthreads();
+        if (s_final) {
+            // The block that sees the evaluation's LAST job arrive is the collective: it pushes this rank's slice of the
+            // vector into every peer's copy with coalesced stores over NVLink (out_len x 8 bytes per peer), fences ONCE at
+            // system scope, raises its epoch flag at every peer and waits for theirs -- when the kernel has completed on this
+            // rank, every peer's slice has landed here.  (Per-job peer stores, as in the branch above, cost the kernel 30 us
+            // at 5,000 jobs; a release store per flag would pay the system fence seven times.)
+            for (int i0 = 0; i0 < L.out_len; i0 += TPB * 8) {   // 8 independent L2 loads in flight per thread, then the stores
+                double v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int i = i0 + q * TPB + tid;
+                    v[q] = (i < L.out_len) ? __ldcg(&L.out[i]) : 0.0;
+                }
+                for (int r = 0; r < L.n_peers; ++r) {
+                    double* dst = L.peer_out[r];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int i = i0 + q * TPB + tid;
+                        if (i < L.out_len) dst[i] = v[q];
+                    }
+                }
+            }
+            __threadfence_system();
+            __syncthreads();
+            if (tid == 0) {
+                *L.launch_done = 0u;
+                for (int r = 0; r < L.n_peers; ++r)
+                    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(L.bar_peer[r]), "l"(L.bar_epoch) : "memory");
+                const long long t0 = clock64();
+                for (int r = 0; r < L.n_peers; ++r) {
+                    const unsigned long long* f = L.bar_mine + L.bar_rank[r];
+                    unsigned long long seen;
+                    do {
+                        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(f) : "memory");
+                        if (seen < L.bar_epoch && clock64() - t0 > 4000000000ll) {   // ~2 s: a peer is gone; say so, do not hang
+                            *L.bar_timeout = 1;
+                            seen = L.bar_epoch;
+                        }
+                    } while (seen < L.bar_epoch);
+                }
+                __threadfence_system();   // acquire side: what the peers pushed before their flags is visible to what follows
+            }
         }
     }
 }

@@ -552,6 +552,8 @@ extern "C" int pnb_eval(pnb_ctx* ctx, const pnb_model* m, int64_t M, pnb_locus* 
         }
         PruneLaunch L;
         L.n_peers = 0;
+        L.bar_epoch = 0;
+        L.out_len = 0;
         L.jobs = reinterpret_cast<const JobDesc*>(prog_base + off_jobs);
         L.tile_job = reinterpret_cast<const int32_t*>(prog_base + off_tiles);
         L.Pm = static_cast<const double*>(ctx->d_P.p);

@@ -210,6 +210,7 @@ struct pnb_ctx {
     int chunk_min_jobs = 1024;     // batches of at least this many jobs are launched in chunks
     int store_stash_levels = 0;    // storing evaluations: siblings waiting at stash index < this use shared memory
                                    // instead of an L2 round trip through their slot (PNB_STORE_STASH)
+    bool hold_reg = pnb::HOLD_REGS;   // the innermost waiting sibling stays in the kernel's HOLD registers (PNB_HOLD builds)
     int virt_tips = 4;             // subtrees of at most this many tips are recomputed from the tip codes, never stored
                                    // (PNB_VIRT_TIPS; 2 = only tip-only nodes)
     bool allow_fused = true;       // small batches: single-kernel latency path (PNB_NO_FUSED=1 disables)

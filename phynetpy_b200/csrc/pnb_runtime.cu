@@ -191,6 +191,7 @@ extern "C" int pnb_ctx_create(int device, pnb_ctx** out) {
     if (const char* e = getenv("PNB_NO_FUSED")) ctx->allow_fused = atoi(e) == 0;
     if (const char* e = getenv("PNB_STORE_STASH")) ctx->store_stash_levels = std::max(0, std::min(atoi(e), 8));
     if (const char* e = getenv("PNB_VIRT_TIPS")) ctx->virt_tips = std::max(1, std::min(atoi(e), 64));
+    if (const char* e = getenv("PNB_HOLD_REG")) ctx->hold_reg = pnb::HOLD_REGS && atoi(e) != 0;
     ctx->scratch.resize(workers);
     if (workers > 1) ctx->pool = new (std::nothrow) WorkerPool(workers);
     *out = ctx;
@@ -205,6 +206,7 @@ extern "C" int pnb_ctx_create_host(pnb_ctx** out) {
     ctx->scratch.resize(1);
     if (const char* e = getenv("PNB_STORE_STASH")) ctx->store_stash_levels = std::max(0, std::min(atoi(e), 8));
     if (const char* e = getenv("PNB_VIRT_TIPS")) ctx->virt_tips = std::max(1, std::min(atoi(e), 64));
+    if (const char* e = getenv("PNB_HOLD_REG")) ctx->hold_reg = pnb::HOLD_REGS && atoi(e) != 0;
     *out = ctx;
     return PNB_OK;
 }

@@ -182,6 +182,21 @@ class ResidentBatch:
         arr = (C.c_void_p * max(len(peer_ptrs), 1))(*[C.c_void_p(int(p)) for p in peer_ptrs])
         _lib.check(self._lib.pnb_batch_set_peer_outputs(self._h, len(peer_ptrs), arr))
 
+    def set_peer_barrier(self, peer_flag_ptrs: Sequence[int], my_flags_ptr: int, peer_ranks: Sequence[int], epoch: int) -> None:
+        """Arm the kernel-issued barrier of the fused collective for the NEXT evaluation (``ShardPlan.peer_barrier_args``
+        gives the three address arguments): the block that finishes the evaluation's last job publishes ``epoch`` to every
+        peer and waits for theirs, so no barrier launch follows the kernel.  ``epoch`` = 1, 2, 3, ... in the order all
+        ranks run their sharded evaluations."""
+        n = len(peer_flag_ptrs)
+        arr = (C.c_void_p * max(n, 1))(*[C.c_void_p(int(p)) for p in peer_flag_ptrs])
+        ranks = (C.c_int32 * max(n, 1))(*[int(r) for r in peer_ranks])
+        _lib.check(self._lib.pnb_batch_set_peer_barrier(self._h, n, arr, C.c_void_p(int(my_flags_ptr)), ranks, C.c_uint64(int(epoch))))
+
+    def barrier_timed_out(self) -> bool:
+        v = C.c_int32(0)
+        _lib.check(self._lib.pnb_batch_barrier_timed_out(self._h, C.byref(v)))
+        return bool(v.value)
+
     def close(self) -> None:
         if self._h is not None and self._pid == os.getpid() and self._ctx._h is not None:
             self._pinned = None

@@ -119,7 +119,8 @@ class ShardPlan:
             import torch.distributed._symmetric_memory as symm_mem
             if dist.get_backend(self.group) != "nccl":
                 return None
-            t = symm_mem.empty(copies * self.slice_len * self.world_size, dtype=torch.float64,
+            # + BARRIER_SLOTS 8-byte words behind the vectors: the flag array of the kernel-issued barrier (peer_barrier_args)
+            t = symm_mem.empty(copies * self.slice_len * self.world_size + self.BARRIER_SLOTS, dtype=torch.float64,
                                device=torch.device("cuda", torch.cuda.current_device()))
             t.zero_()
             hdl = symm_mem.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
@@ -137,6 +138,18 @@ class ShardPlan:
         if ok.item() < 0.5:
             return None
         return t, hdl
+
+    BARRIER_SLOTS = 16   # uint64 flags, one per rank (world_size <= 8), behind the vectors of symmetric_vector()
+
+    def peer_barrier_args(self, handle, copies: int = 2):
+        """What ``ResidentBatch.set_peer_barrier`` needs, from the handle ``symmetric_vector`` returned: the address (valid in
+        this process) of slot [this rank] in every peer's flag array, the address of this rank's own array, and the peers'
+        ranks.  The flags are zero at allocation; the caller counts epochs 1, 2, 3, ... -- one per sharded evaluation, the
+        same on every rank."""
+        off = 8 * copies * self.slice_len * self.world_size
+        peers = [r for r in range(self.world_size) if r != self.rank]
+        return ([int(handle.buffer_ptrs[r]) + off + 8 * self.rank for r in peers],
+                int(handle.buffer_ptrs[self.rank]) + off, peers)
 
     def allgather_slices_(self, vec) -> None:
         """In-place all-gather of equal slices: every rank has written its own slice of ``vec``

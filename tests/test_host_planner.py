@@ -22,7 +22,7 @@ from conftest import load_golden
 
 CASES = load_golden("felsen_cases.json")["cases"]
 K_TIP, K_MEM, K_REG, K_STK = 0, 1, 2, 3
-F_FIRST, F_LAST, F_STORE, F_PUSH = 0x4, 0x8, 0x10, 0x20
+F_FIRST, F_LAST, F_STORE, F_PUSH, F_HOLD = 0x4, 0x8, 0x10, 0x20, 0x40
 SEG_MAX_OPS = 192
 BITS = np.array([[(c >> j) & 1 for j in range(4)] for c in range(16)], dtype=np.float64)
 
@@ -113,6 +113,7 @@ class Planner:
         acc = None
         complete = False          # acc holds a finished node (what a REG op may consume)
         stack = {}
+        hold = None               # PNB_HOLD builds: the ONE register-held sibling (K_STK with src < 0 reads it)
         seen_aux = set()
         for k in range(n_ops):
             flags, src, dst, aux = (int(x) for x in ops[k])
@@ -134,6 +135,9 @@ class Planner:
             elif kind == K_REG:
                 assert flags & F_FIRST and complete, "REG must be the first op after a completed node"
                 child = acc
+            elif src < 0:
+                assert hold is not None, "HOLD registers read while empty"
+                child, hold = hold, None
             else:
                 assert src in stack, "stash %d read before it was pushed" % src
                 assert src < stk_need
@@ -148,6 +152,9 @@ class Planner:
             if flags & F_LAST:
                 if flags & F_STORE:
                     slots[dst] = acc.copy()
+                if flags & F_HOLD:
+                    assert hold is None, "a second node wants the HOLD registers while they are in use"
+                    hold = acc.copy()
                 if flags & F_PUSH:
                     assert ((flags >> 8) & 0xFF) < stk_need, "stash index beyond the capacity the job announced"
                     stack[(flags >> 8) & 0xFF] = acc.copy()
