@@ -183,9 +183,10 @@ def _cpu_worker_main(conn, kind, payload):
                                          for p, bl, lab in trees], model, calc.n_patterns))
                 else:                      # ("codes", codes, weights, tip_row, tree): compressed patterns (cfg2) -> the alignment
                     _, codes, weights, tip_row, (p, bl, lab) = entry      # they came from, column j repeated weights[j] times
-                    assert int(codes.max()) < 4, "unambiguous states only"
                     cols = np.repeat(np.arange(codes.shape[1]), np.asarray(weights, dtype=np.int64))
-                    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+                    # a code is the 4-bit set of allowed states (bit j = "ACGT"[j]); its IUPAC letter
+                    assert int(codes.min()) >= 1 and int(codes.max()) <= 15
+                    lut = np.frombuffer(b"-ACMGRSVTWYHKDBN", dtype=np.uint8)
                     aln = {lab[i]: lut[codes[int(r)][cols]].tobytes().decode() for i, r in enumerate(np.asarray(tip_row).tolist())
                            if r >= 0 and lab[i] is not None}
                     calc = RSL.FelsensteinCalculator(aln)
@@ -848,6 +849,8 @@ def run_chain_block(args, P, ctx, model):
     out = {}
     out["cfg3_full_eval"] = chain_cfg3(args, P, ctx, model)
     out["cfg4_dirty_chain"], out["cfg4_joint_chain"] = chain_cfg4(args, P, ctx, model)
+    if not args.no_cpu_baseline:
+        out["reference_mcmc_seq"] = chain_dropin(args)
     return out
 
 
@@ -911,6 +914,53 @@ def chain_cfg3(args, P, ctx, model):
     for c in calcs:
         c.close()
     return res
+
+
+def chain_dropin(args, n_loci=30, n_taxa=10, n_sites=400, n_iter=120):
+    """The reference's OWN sampler -- ``MCMC_SEQ(...).search()``, unmodified Python from ``baseline/_ref`` -- timed twice on
+    the same data and seed: as it is (every likelihood on the host), and with ``phynetpy_b200.dropin.install()`` (every
+    Felsenstein pruning, every MSNC density and the placement scans of the informed network moves on the device).  What
+    a user of the reference gets by switching; iterations / s include all of the reference's Python (operators on
+    Network objects, priors, bookkeeping).  The chain is not reproducible from its seed (set iteration over objects
+    hashed by address), so the two arms walk different trajectories of the same sampler."""
+    if not reference_available():
+        return {"unavailable": "baseline/_ref is not installed"}
+    from baseline import ref_loader
+    from phynetpy_b200 import simulate as S, dropin
+    ref = ref_loader.load_reference()
+    import phynetpy._mcmc_seq as mcmc
+    rng = np.random.default_rng(5)
+    net = S.random_species_network(n_taxa, 0, rng, height=0.005 * (n_taxa - 1))
+    trees, _ = S.simulate_gene_trees_msnc(net, 1, 0.02, rng, n_loci)
+    aln = S.simulate_alignments(np.stack([t.parent for t in trees]), np.stack([t.blen for t in trees]), n_sites,
+                                S.DEFAULT_PI, S.DEFAULT_RATES, rng)
+    loci = [S.to_alignment_dict(aln[i]) for i in range(n_loci)]
+    mapping = {t: [t] for t in loci[0].keys()}
+
+    def arm():
+        inf = mcmc.MCMC_SEQ(loci, mapping, priors=mcmc.MCMCSeqPriors(max_reticulations=1))
+        s0 = inf.score()
+        t0 = time.perf_counter()
+        res = inf.search(num_iter=n_iter, burn_in=10, sample_freq=10, seed=7)
+        return s0, time.perf_counter() - t0, res
+
+    dropin.install(ref)
+    try:
+        arm()                                  # warm-up: contexts, handles, first launches
+        s_gpu, t_gpu, r_gpu = arm()
+    finally:
+        dropin.uninstall()
+    s_cpu, t_cpu, r_cpu = arm()
+    return {
+        "what": "the reference's own MCMC_SEQ.search(num_iter=%d) on %d loci x %d taxa x %d sites, max 1 reticulation, "
+                "default operator mixture (gene-tree moves, theta / height moves, informed add / delete of reticulations)"
+                % (n_iter, n_loci, n_taxa, n_sites),
+        "iterations_per_s_with_drop_in": n_iter / t_gpu, "iterations_per_s_reference_alone": n_iter / t_cpu,
+        "seconds_with_drop_in": t_gpu, "seconds_reference_alone": t_cpu,
+        "initial_score_rel_diff": abs(s_gpu - s_cpu) / max(1.0, abs(s_cpu)),
+        "acceptance_rates": [r_gpu.acceptance_rate, r_cpu.acceptance_rate],
+        "cores_reference": 1,
+    }
 
 
 def chain_cfg4(args, P, ctx, model):

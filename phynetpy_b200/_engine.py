@@ -93,6 +93,7 @@ class SeqLikelihoodEngine:
         self._batch: Optional[ResidentBatch] = None   # resident programs of the last all-local-loci evaluation
         self._batch_key: Optional[tuple] = None
         self._sh: Optional[dict] = None        # sharded mode: device vector, pinned host copy, stream (see _shard_state)
+        self._scan_pack: Optional[dict] = None   # gene trees of all loci at every height scale, packed (network_only_msnc_score)
 
     # -- reference seam (src/_mcmc_seq.py:696-703, :766-772) ------------------
     def invalidate_locus(self, i: int) -> None:
@@ -593,6 +594,51 @@ class SeqLikelihoodEngine:
             res.append(out[k:k + K])
             k += K
         return res
+
+    def network_only_msnc_score(self, gene_trees: Sequence[Any], species_net: Any, theta: float,
+                                scales: Sequence[float]) -> float:
+        """``sum_i logsumexp_s log P(g_i with heights scaled by s | candidate network)`` -- the likelihood part of the
+        reference's ``_network_only_log_score`` (``src/_mcmc_seq.py:1163-1214``), the score the informed add / delete /
+        relocate moves rank every candidate placement by.  The reference runs ``n_loci x len(scales)`` host densities
+        per candidate (94 % of its chain time on 30 loci); here one candidate is ONE ``pnb_msnc_eval`` over the gene
+        trees of all loci at all scales, packed once per set of gene-tree objects (they do not change inside a network
+        move).  The candidate never touches the engine's own network / cache state."""
+        theta = _check_theta(theta)
+        cand = as_species_network(species_net)
+        scales = tuple(float(x) for x in scales)
+        pk = self._scan_pack
+        if pk is None or pk["scales"] != scales or pk["species"] != cand.species or len(pk["objs"]) != len(gene_trees) \
+                or any(a is not b for a, b in zip(pk["objs"], gene_trees)):
+            species_of = self._species_of
+            parents, blens, idss, sizes = [], [], [], []
+            for g in gene_trees:
+                ft = flatten(g)
+                so = species_of if species_of is not None else {lab: lab for lab in ft.label if lab is not None}
+                ids = cand.species_ids_of(ft, so)
+                for sc in scales:
+                    parents.append(ft.parent)
+                    blens.append(ft.blen if sc == 1.0 else ft.blen * sc)   # powers of two: the scaled times are exact
+                    idss.append(ids)
+                    sizes.append(ft.n_nodes)
+            off = np.zeros(len(sizes) + 1, dtype=np.int64)
+            np.cumsum(np.asarray(sizes, dtype=np.int64), out=off[1:])
+            pk = self._scan_pack = {
+                "scales": scales, "species": cand.species, "objs": list(gene_trees), "off": off,
+                "parent": np.ascontiguousarray(np.concatenate(parents), dtype=np.int32),
+                "blen": np.ascontiguousarray(np.concatenate(blens), dtype=np.float64),
+                "ids": np.ascontiguousarray(np.concatenate(idss), dtype=np.int32)}
+        dens = msnc_eval_packed(cand, pk["off"], pk["parent"], pk["blen"], pk["ids"], theta, self._context(), self._branch_thetas)
+        total = 0.0
+        for row in dens.reshape(-1, len(scales)).tolist():     # _logsumexp over the finite terms (:1149-1160, :1209-1213)
+            terms = [x for x in row if math.isfinite(x)]
+            if not terms:
+                return -math.inf
+            m = max(terms)
+            acc = 0.0
+            for v in terms:
+                acc += math.exp(v - m)
+            total += m + math.log(acc)
+        return total
 
     # -- natively enumerated candidate batches (candidates.CandidateBatch) ---------------------------------
     def score_batch(self, batch: Any, loci: Sequence[int], *, site_rate: float = 1.0) -> np.ndarray:

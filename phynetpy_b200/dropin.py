@@ -6,6 +6,10 @@ changes INTEGRATION.md sections 2 and 3 describe as source edits:
 * ``FelsensteinCalculator`` -- every module of the reference that imported the class
   (``src/_mcmc_seq.py:86-90``, ``src/infer.py:105``, ...) gets the B200 class instead, so
   ``_SeqLikelihoodEngine.__init__`` (``src/_mcmc_seq.py:673``) builds device-resident loci;
+* ``_network_only_log_score`` (``src/_mcmc_seq.py:1163-1214``) -- the placement scan of the informed add / delete /
+  relocate moves scores every candidate network with ``n_loci x 5`` host densities (94 % of the reference's chain time
+  on 30 loci); the replacement asks the engine for the same sum through ONE ``pnb_msnc_eval`` per candidate
+  (``SeqLikelihoodEngine.network_only_msnc_score``) and adds the reference's own prior;
 * ``_SeqLikelihoodEngine`` (``src/_mcmc_seq.py:647-772``) -- replaced by
   :class:`B200SeqLikelihoodEngine`, the same seam (``log_likelihood`` / ``invalidate_locus`` /
   ``invalidate_network`` / ``clone_caches`` / ``restore_caches``, ``_felsen`` / ``_msnc`` lists)
@@ -110,6 +114,26 @@ class B200SeqLikelihoodEngine(SeqLikelihoodEngine):
         return self._gt_index[i]
 
 
+def _network_only_log_score(state: Any, net: Any) -> float:
+    """``_network_only_log_score`` of the reference (``src/_mcmc_seq.py:1163-1214``) with the densities on the device.
+    Anything this path cannot take (an engine that is not ours, a network the flat form rejects) goes to the
+    reference's own function."""
+    import math
+    eng = getattr(state, "_engine", None)
+    ref_fn = _state["ref_network_only_log_score"]
+    if not isinstance(eng, B200SeqLikelihoodEngine) or getattr(state, "branch_thetas", None) != eng._branch_thetas:
+        return ref_fn(state, net)
+    mcmc = _state["mcmc"]
+    try:
+        total = eng.network_only_msnc_score(state.gene_trees, net, state.theta, mcmc._HEIGHT_SCALE_GRID)
+    except (ValueError, KeyError, _lib.PhyNetB200Error):
+        return ref_fn(state, net)
+    if not math.isfinite(total):
+        return float("-inf")
+    total += mcmc.log_prior_seq(net, state.theta, state.priors)
+    return total if math.isfinite(total) else float("-inf")
+
+
 def _reference_modules(ref_pkg: Any):
     prefix = ref_pkg.__name__ + "."
     for name, mod in list(sys.modules.items()):
@@ -141,6 +165,10 @@ def install(ref_pkg: Any = None, *, devices: Optional[Sequence[int]] = None) -> 
                 setattr(mod, attr, FelsensteinCalculator)
     undo.append((mcmc, "_SeqLikelihoodEngine", mcmc._SeqLikelihoodEngine))
     mcmc._SeqLikelihoodEngine = B200SeqLikelihoodEngine
+    undo.append((mcmc, "_network_only_log_score", mcmc._network_only_log_score))
+    _state["ref_network_only_log_score"] = mcmc._network_only_log_score
+    _state["mcmc"] = mcmc
+    mcmc._network_only_log_score = _network_only_log_score
     undo.append((mcmc, "_chain_worker", mcmc._chain_worker))
     mcmc._chain_worker = _chain_worker
     if devices is not None:

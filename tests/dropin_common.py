@@ -130,12 +130,22 @@ def run_lockstep_chain(mcmc_mod, loci, mapping, n_iter, seed, max_reticulations=
     """The loop body of ``MCMC_SEQ.search`` (``src/_mcmc_seq.py:3478-3499``) with both likelihood values."""
     from phynetpy_b200 import dropin
     assert dropin.installed()
-    log = {"evals": [], "candidates": [], "felsen": [], "msnc": [], "errors": [], "decisions": []}
+    log = {"evals": [], "candidates": [], "felsen": [], "msnc": [], "errors": [], "decisions": [], "placements": []}
     undo = dropin._state["undo"]
     ref_engine_cls = [v for (m, a, v) in undo if a == "_SeqLikelihoodEngine"][0]
     ref_calc_cls = [v for (m, a, v) in undo if a == "FelsensteinCalculator" and m is mcmc_mod][0]
     saved = mcmc_mod._SeqLikelihoodEngine
     mcmc_mod._SeqLikelihoodEngine = make_lockstep_engine_class(mcmc_mod, ref_engine_cls, ref_calc_cls, log)
+    # the placement scan of the informed add / delete / relocate moves (_network_only_log_score, :1163-1214): every
+    # candidate network scored by the drop-in (one device call) AND by the reference's own host loop
+    saved_scan = mcmc_mod._network_only_log_score
+    ref_scan = dropin._state["ref_network_only_log_score"]
+
+    def both_scans(state, net):
+        b = saved_scan(state, net)
+        log["placements"].append((b, ref_scan(state, net)))
+        return b
+    mcmc_mod._network_only_log_score = both_scans
     try:
         inf = mcmc_mod.MCMC_SEQ(loci, mapping, priors=mcmc_mod.MCMCSeqPriors(max_reticulations=max_reticulations))
         rng = np.random.default_rng(seed)
@@ -188,6 +198,7 @@ def run_lockstep_chain(mcmc_mod, loci, mapping, n_iter, seed, max_reticulations=
         return log
     finally:
         mcmc_mod._SeqLikelihoodEngine = saved
+        mcmc_mod._network_only_log_score = saved_scan
 
 
 def check_lockstep_log(log, n_iter):
@@ -201,6 +212,9 @@ def check_lockstep_log(log, n_iter):
         assert close(b, r), (b, r)
     for b, r in log["msnc"]:
         assert close(b, r), (b, r)
+    for b, r in log["placements"]:
+        assert close(b, r), (b, r)
+    assert len(log["placements"]) > 20, "the placement scan never ran through the drop-in"
     assert all(a == b for a, b in log["decisions"]), "an accept / reject decision differs"
     assert 0 < log["accepted"] < len(log["decisions"])
     cached, fresh, ref = log["final"]
