@@ -226,7 +226,7 @@ PNB_API int pnb_batch_set_peer_outputs(pnb_batch *b, int32_t n_peers, double *co
  * this rank every peer's stores into this rank's vector have landed.  Flag arrays are uint64[world] in the same
  * symmetric allocation as the vectors, zero at start; the caller owns the epoch counter (1, 2, 3, ... in the order all
  * ranks run their sharded evaluations) and arms the barrier before EACH evaluation (it is used once).  A peer that
- * does not arrive within ~2 s sets a flag (pnb_batch_barrier_timed_out) instead of hanging the kernel.
+ * does not arrive within ~4 s sets a flag (pnb_batch_barrier_timed_out) instead of hanging the kernel.
  * Replaces: the NCCL collective after the kernel (src/_mcmc_seq.py:746-761 is a plain sum over loci).      */
 PNB_API int pnb_batch_set_peer_barrier(pnb_batch *b, int32_t n_peers, uint64_t *const *peer_flag,
                                        const uint64_t *my_flags, const int32_t *peer_rank, uint64_t epoch);

@@ -348,7 +348,7 @@ class SeqLikelihoodEngine:
                 sh["host"].copy_(vec, non_blocking=True)
             sh["stream"].synchronize()
             if fused and self._batch is not None and self._batch.barrier_timed_out():
-                raise RuntimeError("sharded evaluation: a peer GPU did not reach the barrier of the fused collective within 2 s")
+                raise RuntimeError("sharded evaluation: a peer GPU did not reach the barrier of the fused collective within 4 s")
         else:
             if dirty:
                 vals = self.felsenstein_batch(dirty, gene_trees, flags=flags)

@@ -119,7 +119,7 @@ struct PruneLaunch {
     unsigned long long* bar_peer[MAX_PEERS];     // slot [this rank] of peer r's flag array (peer-mapped)
     const unsigned long long* bar_mine;          // this rank's flag array, indexed by rank
     int32_t bar_rank[MAX_PEERS];                 // rank of peer r
-    int32_t* bar_timeout;                        // mapped host word: set when a peer did not arrive within ~2 s
+    int32_t* bar_timeout;                        // mapped host word: set when a peer did not arrive within ~4 s
 };
 
 // FUSED launches of one or two loci (the single-locus MCMC step): the tile map, the job descriptors, the op program and
@@ -758,7 +758,7 @@ __device__ __forceinline__ void prune_tile(const PruneLaunch& L, const ModelPara
                     unsigned long long seen;
                     do {
                         asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(f) : "memory");
-                        if (seen < L.bar_epoch && clock64() - t0 > 4000000000ll) {   // ~2 s: a peer is gone; say so, do not hang
+                        if (seen < L.bar_epoch && clock64() - t0 > 8000000000ll) {   // ~4 s: a peer is gone; say so, do not hang
                             *L.bar_timeout = 1;
                             seen = L.bar_epoch;
                         }
