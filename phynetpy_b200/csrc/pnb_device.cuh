@@ -542,8 +542,9 @@ __device__ __forceinline__ void prune_tile(const PruneLaunch& L, const ModelPara
             const int32_t src = __shfl_sync(0xffffffffu, nsrc, 0), dst = __shfl_sync(0xffffffffu, ndst, 0),
                           aux = __shfl_sync(0xffffffffu, naux, 0);
 #else
-            const uint32_t flags = nflags;
-            const int32_t src = nsrc, dst = ndst, aux = naux;
+            uint32_t flags = nflags;
+            int32_t dst = ndst;
+            const int32_t src = nsrc, aux = naux;
 #endif
 #ifdef PNB_UNIFORM_LD
             { const int4 o4 = __ldg(reinterpret_cast<const int4*>(g_ops + seg + k + 1)); nflags = o4.x; nsrc = o4.y; ndst = o4.z; naux = o4.w; }
@@ -552,21 +553,60 @@ __device__ __forceinline__ void prune_tile(const PruneLaunch& L, const ModelPara
 #endif
             const uint32_t kind = flags & F_KIND_MASK;
             const bool first = (flags & F_FIRST) != 0;
+            // A tip child that FOLLOWS inside the same node (the second tip of a cherry, the tip next to the register-forwarded
+            // child) is taken in the same iteration: its fields are already in the prefetched registers, so it costs its code
+            // bytes, one column of P per pattern and four multiplications -- not another round of op fetch / decode / dispatch /
+            // loop control (~50 of a tip op's ~80 instructions).  Same products in the same order, hence the same bits.
+            // The loads (the tip's code bytes, the op after it) are issued BEFORE this op's arithmetic, the products after it.
+#define PNB_PEEK_TRAILING_TIP()                                                                                      \
+            const bool take2 = k + 1 < nseg && (nflags & (F_KIND_MASK | F_FIRST)) == K_TIP;                          \
+            uint32_t code2[NP];                                                                                      \
+            uint32_t flags2 = 0;                                                                                     \
+            int32_t dst2 = 0;                                                                                        \
+            if (take2) { /* loads first: the tip's code bytes and the op after it are in flight during this op's arithmetic */ \
+                flags2 = nflags;                                                                                     \
+                dst2 = ndst;                                                                                         \
+                const int32_t src2 = nsrc, aux2 = naux;                                                              \
+                lds_op(op_addr + 32, nflags, nsrc, ndst, naux);                                                      \
+                _Pragma("unroll") for (int u = 0; u < NP; ++u)                                                       \
+                    code2[u] = (src2 >= 0) ? lds_u8(codes_addr + aux2 * TILE_PATTERNS + u * TPB) : 0x8Fu;            \
+            }
+#define PNB_APPLY_TRAILING_TIP()                                                                                     \
+            if (take2) {                                                                                             \
+                tip_contrib<true, NP>(pk + 128, code2, acc);                                                         \
+                flags = flags2;                                                                                      \
+                dst = dst2;                                                                                          \
+                ++k;                                                                                                 \
+                op_addr += 16;                                                                                       \
+                pk += 128;                                                                                           \
+            }
             if (kind == K_TIP) {
                 uint32_t code[NP];
 #pragma unroll
                 for (int u = 0; u < NP; ++u)
                     code[u] = (src >= 0) ? lds_u8(codes_addr + aux * TILE_PATTERNS + u * TPB) : 0x8Fu;
+#ifndef PNB_NO_TIP_PAIRS
+                PNB_PEEK_TRAILING_TIP()
+#endif
                 if (first) tip_contrib<false, NP>(pk, code, acc);
                 else tip_contrib<true, NP>(pk, code, acc);
                 if (RESCALE && first) {
 #pragma unroll
                     for (int u = 0; u < NP; ++u) acc_e[u] = 0;
                 }
+#ifndef PNB_NO_TIP_PAIRS
+                PNB_APPLY_TRAILING_TIP()
+#endif
             } else if (kind == K_REG) {
                 // the child is the node completed just before: its partial is still in `acc`
                 // (the host always emits the forwarded child as the FIRST op of its parent)
+#ifndef PNB_NO_TIP_AFTER_REG
+                PNB_PEEK_TRAILING_TIP()
+#endif
                 matvec<false, NP>(pk, acc, acc);   // reads acc completely before it writes it
+#ifndef PNB_NO_TIP_AFTER_REG
+                PNB_APPLY_TRAILING_TIP()
+#endif
             } else {
                 Vec4 l[NP];
                 int le[NP];
@@ -649,6 +689,8 @@ __device__ __forceinline__ void prune_tile(const PruneLaunch& L, const ModelPara
         }
     }
 
+#undef PNB_PEEK_TRAILING_TIP
+#undef PNB_APPLY_TRAILING_TIP
     // root: site likelihood, clamp, log, weight  (reference :394-397)
     constexpr int HALF = (PPT % 2 == 0) ? PPT / 2 : PPT;   // patterns per thread and half tile
     constexpr int NH = NP / HALF;                          // halves this block computes (2: a whole tile, 1: one half)
