@@ -473,16 +473,17 @@ def measure(args, wl_name, W, plan, stream, rank, world, clock_sampler=None):
             # both variants of the same step timed the same way; the faster one (agreed over ranks) runs the timed region
             # (two rounds each, alternating, best of the two: long kernels run under the power cap, and whichever variant is
             # timed later in a run would otherwise be charged for the warmer GPU)
-            # ... and short: the trials only choose the variant, the timed region below is the measurement)
+            # ... and short -- 2 x 6 steps per variant: the trials only choose the variant, the timed region below is the
+            # measurement, and every step run before it costs the timed region clock under the power cap)
             nccl_ms = p2p_ms = float("inf")
-            n_trial = max(5, min(steps, 15))
+            n_trial = max(3, min(steps, 6))
             for _round in range(2):
                 set_mode("nccl")
-                for _ in range(warm):
+                for _ in range(2):
                     step_device()
                 nccl_ms = min(nccl_ms, timed_device_loop(n_trial) / n_trial)
                 set_mode("p2p")
-                for _ in range(warm):
+                for _ in range(2):
                     step_device()
                 p2p_ms = min(p2p_ms, timed_device_loop(n_trial) / n_trial)
             tt = torch.tensor([nccl_ms, p2p_ms], dtype=torch.float64, device="cuda")
