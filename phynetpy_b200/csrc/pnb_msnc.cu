@@ -139,6 +139,27 @@ __device__ double msnc_dp_warp(const Step* steps, int n_steps, const int32_t* do
         const double tau_low = st.tau_low, tau_h0 = st.tau_high[0], tau_h1 = st.tau_high[1];
         const double inv_theta0 = step_theta[4 * s], l2t0 = step_theta[4 * s + 1];
         const double inv_theta1 = step_theta[4 * s + 2], l2t1 = step_theta[4 * s + 3];
+        // Short road 1 -- a leaf of the network entered by at most one gene lineage (half of all steps when every species
+        // has one allele): no branch factor (exactly 1), nothing closed, nothing that could make two entries equal.  Every
+        // entry gets the species' lineage set in the opened slot IN PLACE: no candidate buffer, no duplicate search, no swap.
+        if (is_leaf && !is_retic) {
+            Mask<NW> a;
+            a.clear();
+            if (species >= 0)
+                for (int i = 0; i < NW; ++i) a.w[i] = species_mask[static_cast<size_t>(species) * NW + i];
+            if (a.count() <= 1) {
+                const uint32_t sa = static_cast<uint32_t>(up0) * NW;
+                uint64_t dh = 0;
+                for (int i = 0; i < NW; ++i) dh ^= slot_hash(sa + i, a.w[i]);
+                for (uint32_t t = lane; t < n_cur; t += 32) {
+                    for (int i = 0; i < NW; ++i) buf[m_cur + (sa + i) * ucap + t] = a.w[i];
+                    buf[h_cur + t] ^= dh;
+                }
+                if (is_root) root_slot = up0;
+                __syncwarp();
+                continue;
+            }
+        }
         // events inside this node's parent branch(es): events are sorted by time, so "first index with t >= tau" is the
         // number of events with t < tau -- one ballot per 32 events instead of a binary search per lane
         int j_lo = 0, j_hi0 = 0, j_hi1 = 0;
@@ -172,6 +193,28 @@ __device__ double msnc_dp_warp(const Step* steps, int n_steps, const int32_t* do
             return a;
         };
 
+        // Short road 2 -- ONE entry and no reticulation (the DP before the first reticulation, and wherever the frontier has
+        // collapsed again): the entry is updated in place by lane 0, as msnc_dp_tree does it.
+        if (!is_retic && n_cur == 1) {
+            if (lane == 0) {
+                uint64_t h = buf[h_cur];
+                Mask<NW> ma = arriving(0, h);
+                double blp = 0.0;
+                if (ma.count() > 1) branch_timed<NW>(ma, blp, tau_low, tau_h0, !is_root, inv_theta0, l2t0, ev_t, ev_n, j_lo, j_hi0);
+                for (int d = 0; d < n_down; ++d)
+                    for (int i = 0; i < NW; ++i) buf[m_cur + (down_slot[down_off + d] * NW + i) * ucap] = 0;
+                const uint32_t sa = static_cast<uint32_t>(up0) * NW;
+                for (int i = 0; i < NW; ++i) {
+                    buf[m_cur + (sa + i) * ucap] = ma.w[i];
+                    h ^= slot_hash(sa + i, ma.w[i]);
+                }
+                buf[h_cur] = h;
+                bufd[l_cur] = add_rn(bufd[l_cur], blp);
+            }
+            if (is_root) root_slot = up0;
+            __syncwarp();
+            continue;
+        }
         // ---- A: candidate offsets -------------------------------------------------------------------------
         uint32_t T = n_cur;
         if (is_retic) {
