@@ -83,7 +83,8 @@ class SeqLikelihoodEngine:
         self._full_next = False
         self._mode = _lib.EVAL_RESCALE if rescale else 0  # numerical mode (beyond the reference when set)
         self.resident_batches = bool(resident_batches)
-        self.last_stats: dict = {}
+        self._stats: Optional[dict] = {}
+        self._stats_ctx: Any = None
         # MSNC side: the network view is rebuilt when a different network OBJECT arrives (the reference
         # keys on identity too, src/_mcmc_seq.py:705-713); per-locus species ids are keyed by the label list
         self._net_obj: Any = None
@@ -94,6 +95,18 @@ class SeqLikelihoodEngine:
         self._batch_key: Optional[tuple] = None
         self._sh: Optional[dict] = None        # sharded mode: device vector, pinned host copy, stream (see _shard_state)
         self._scan_pack: Optional[dict] = None   # gene trees of all loci at every height scale, packed (network_only_msnc_score)
+
+    @property
+    def last_stats(self) -> dict:
+        """Counters of the device call behind the engine's last evaluation (``DeviceContext.last_stats``), read from the
+        library when asked for: a chain step does not pay a second ABI call for numbers nobody looks at."""
+        if self._stats is None:
+            self._stats = self._stats_ctx.last_stats() if self._stats_ctx is not None else {}
+        return self._stats
+
+    @last_stats.setter
+    def last_stats(self, value: dict) -> None:
+        self._stats = value
 
     # -- reference seam (src/_mcmc_seq.py:696-703, :766-772) ------------------
     def invalidate_locus(self, i: int) -> None:
@@ -173,7 +186,7 @@ class SeqLikelihoodEngine:
         extra = {} if out_device_ptr is None else {"out_device_ptr": out_device_ptr}
         out = ctx.eval(_model_handle(self._model, ctx), self._handles(idx), node_off, parent, blen, tip_row,
                        site_rate, flags, P_edge, **extra)
-        self.last_stats = ctx.last_stats()
+        self._stats, self._stats_ctx = None, ctx      # fetched when somebody reads last_stats
         return out
 
     def log_likelihood(self, gene_trees: Sequence[Any], species_net: Any = None, theta: float = 0.0,
@@ -233,7 +246,7 @@ class SeqLikelihoodEngine:
         self._msnc[i] = m
         self._pending = [i]
         self._msnc_dirty.clear()
-        self.last_stats = ctx.last_stats()
+        self._stats, self._stats_ctx = None, ctx      # fetched when somebody reads last_stats
 
     BATCH_MIN_LOCI = 32   # all-local-loci evaluations of at least this many loci go through a resident batch
 
@@ -268,7 +281,7 @@ class SeqLikelihoodEngine:
             if barrier is not None:
                 self._batch.set_peer_barrier(*barrier)
             out = self._batch.eval(mh, blen, 1.0, out_device_ptr)
-        self.last_stats = ctx.last_stats()
+        self._stats, self._stats_ctx = None, ctx      # fetched when somebody reads last_stats
         return out
 
     # -- sharded evaluation: device vector + in-place all-gather ------------------------------------------
@@ -653,7 +666,7 @@ class SeqLikelihoodEngine:
         P_edge = _explicit_P_edges(self._model, batch.blen, site_rate) if _device_kind(self._model) == "explicit" else None
         out = ctx.eval(_model_handle(self._model, ctx), handles, batch.node_off, batch.parent, batch.blen, tip_row,
                        site_rate, _lib.EVAL_NOSTORE | self._mode, P_edge)
-        self.last_stats = ctx.last_stats()
+        self._stats, self._stats_ctx = None, ctx      # fetched when somebody reads last_stats
         return out
 
     def msnc_batch(self, batch: Any, loci: Sequence[int], species_net: Any, theta: float) -> np.ndarray:
@@ -686,7 +699,7 @@ class SeqLikelihoodEngine:
         P_edge = _explicit_P_edges(self._model, blen, site_rate) if _device_kind(self._model) == "explicit" else None
         out = ctx.eval(_model_handle(self._model, ctx), self._handles(idx), node_off, parent, blen, tip_row,
                        site_rate, _lib.EVAL_NOSTORE | self._mode, P_edge)
-        self.last_stats = ctx.last_stats()
+        self._stats, self._stats_ctx = None, ctx      # fetched when somebody reads last_stats
         res, k = [], 0
         for _, trees in sets:
             res.append(out[k:k + len(trees)])
@@ -716,7 +729,7 @@ class SeqLikelihoodEngine:
         P_edge = _explicit_P_edges(self._model, blen, site_rate) if _device_kind(self._model) == "explicit" else None
         out = ctx.eval(_model_handle(self._model, ctx), np.concatenate(handles), node_off, parent, blen, tip_row,
                        site_rate, _lib.EVAL_NOSTORE | self._mode, P_edge)
-        self.last_stats = ctx.last_stats()
+        self._stats, self._stats_ctx = None, ctx      # fetched when somebody reads last_stats
         res, k = [], 0
         for _, (_, par, _) in sets:
             res.append(out[k:k + par.shape[0]])
@@ -736,5 +749,5 @@ class SeqLikelihoodEngine:
         P_edge = _explicit_P_edges(self._model, blen, site_rate) if _device_kind(self._model) == "explicit" else None
         out = ctx.eval(_model_handle(self._model, ctx), self._handles(idx), node_off, parent, blen, tip_row,
                        site_rate, _lib.EVAL_NOSTORE | self._mode, P_edge)
-        self.last_stats = ctx.last_stats()
+        self._stats, self._stats_ctx = None, ctx      # fetched when somebody reads last_stats
         return out
