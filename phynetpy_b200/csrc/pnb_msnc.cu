@@ -968,8 +968,7 @@ static int msnc_launch(pnb_ctx* ctx, const pnb_msnc_net* net, int64_t n_trees, c
                     cudaHostGetDevicePointer(&db, ctx->m_hout.p, 0) == cudaSuccess && db == ctx->m_hout.p;
         if (!zero_copy) (void)cudaGetLastError();
     }
-    MsncSmall small;
-    small.used = 0;
+    MsncSmall small = {};
     if (n_trees == 1 && ev_off[1] <= MS_MAX_EV && static_cast<size_t>(n_species) * NW <= MS_MAX_SP &&
         prog.steps.size() * 4 <= MS_MAX_THETA && root_bit[0] >= 0) {
         small.used = 1;
