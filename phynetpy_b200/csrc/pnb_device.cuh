@@ -250,6 +250,9 @@ __global__ void __launch_bounds__(128)
 pnb_pmatrix_gather_kernel(const __grid_constant__ ModelParams mp, const double* __restrict__ blen,
                           const int32_t* __restrict__ node_of_op, double site_rate, int64_t n_ops,
                           double* __restrict__ P_out, double* __restrict__ keep) {
+    // programmatic dependent launch: the pruning kernel queued behind this one may start its prologue (descriptors, program
+    // and tip-code staging -- nothing this kernel writes) now; it waits for P(t) with griddepcontrol.wait
+    asm volatile("griddepcontrol.launch_dependents;");
     const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (g >= n_ops) return;
     const int32_t node = node_of_op[g];
@@ -501,11 +504,7 @@ __device__ __forceinline__ void prune_tile(const PruneLaunch& L, const ModelPara
         } else {
         if (seg > 0) __syncthreads();  // every warp is done with the previous segment's shared memory
         if (tid < 32) {
-            if (tid == 0) {
-                tma_bulk_g2s(s_ops, g_ops + seg, static_cast<uint32_t>(nseg) * sizeof(Op), &bar_stage);
-                tma_bulk_g2s(s_P, L.Pm + (static_cast<int64_t>(op_off) + seg) * 16, static_cast<uint32_t>(nseg) * 128u,
-                             &bar_stage);
-            }
+            if (tid == 0) tma_bulk_g2s(s_ops, g_ops + seg, static_cast<uint32_t>(nseg) * sizeof(Op), &bar_stage);
             int my_rows = 0;
             for (int k = tid; k < nseg; k += 32) {
                 const Op op = g_ops[seg + k];
@@ -516,6 +515,14 @@ __device__ __forceinline__ void prune_tile(const PruneLaunch& L, const ModelPara
                 }
             }
             const int rows = __reduce_add_sync(0xffffffffu, my_rows);
+            if (tid == 0) {
+                // P(t) is what the K-a launch in front of this kernel writes: everything above (descriptors, program, tip
+                // codes) was staged while K-a may still have been running (programmatic dependent launch, launch_prune);
+                // this is where the kernel waits for it.  Without such a launch in front the wait returns at once.
+                if (seg == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
+                tma_bulk_g2s(s_P, L.Pm + (static_cast<int64_t>(op_off) + seg) * 16, static_cast<uint32_t>(nseg) * 128u,
+                             &bar_stage);
+            }
             // the pending arrival keeps the phase open until the byte count has been announced
             if (tid == 0)
                 mbar_arrive_expect_tx(&bar_stage, static_cast<uint32_t>(nseg) * (sizeof(Op) + 128u) +

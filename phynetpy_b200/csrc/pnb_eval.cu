@@ -87,8 +87,22 @@ int pnb::launch_prune(const PruneLaunch& L_in, const ModelParams& mp, unsigned n
     unsigned grid;
     split_tail(n_tiles, dyn_smem, false, rescale, &L.n_full, &grid);
     static const SmallBatch no_small = {};   // n_jobs == 0: unused outside the fused latency path
-    if (rescale) pnb_prune_kernel_t<false, true><<<grid, TPB, dyn_smem, st>>>(L, mp, no_small);
-    else pnb_prune_kernel_t<false, false><<<grid, TPB, dyn_smem, st>>>(L, mp, no_small);
+    // Programmatic dependent launch: this kernel may become resident while the kernel in front of it on the stream (K-a of
+    // the same evaluation) is still running; it stages everything K-a does not write and waits for P(t) with
+    // griddepcontrol.wait.  PNB_NO_PDL=1: plain stream order.
+    static const bool pdl = !(getenv("PNB_NO_PDL") && getenv("PNB_NO_PDL")[0] == '1');
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(TPB);
+    cfg.dynamicSmemBytes = dyn_smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    if (rescale) PNB_CUDA_TRY(cudaLaunchKernelEx(&cfg, pnb_prune_kernel_t<false, true>, L, mp, no_small));
+    else PNB_CUDA_TRY(cudaLaunchKernelEx(&cfg, pnb_prune_kernel_t<false, false>, L, mp, no_small));
     PNB_CUDA_TRY(cudaGetLastError());
     return PNB_OK;
 }
