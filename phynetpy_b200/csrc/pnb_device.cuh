@@ -252,6 +252,10 @@ pnb_pmatrix_gather_kernel(const __grid_constant__ ModelParams mp, const double* 
                           double* __restrict__ P_out, double* __restrict__ keep) {
     // programmatic dependent launch: the pruning kernel queued behind this one may start its prologue (descriptors, program
     // and tip-code staging -- nothing this kernel writes) now; it waits for P(t) with griddepcontrol.wait
+    // (this kernel is itself a dependent launch behind whatever precedes it on the stream -- the previous evaluation's
+    // pruning kernel, which still reads the P array this one rewrites: it waits for that kernel's completion first; what
+    // the early launch saves is the launch latency)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;");
     const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (g >= n_ops) return;

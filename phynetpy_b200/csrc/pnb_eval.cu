@@ -31,7 +31,17 @@ int pnb::launch_pmatrix_gather(const ModelParams& mp, const double* d_blen, cons
                                int64_t n_ops, double* d_P, double* d_keep, cudaStream_t st) {
     if (n_ops <= 0) return PNB_OK;
     const int64_t blocks = (n_ops + 127) / 128;
-    pnb_pmatrix_gather_kernel<<<static_cast<unsigned>(blocks), 128, 0, st>>>(mp, d_blen, d_node_of_op, site_rate, n_ops, d_P, d_keep);
+    static const bool pdl = !(getenv("PNB_NO_PDL") && getenv("PNB_NO_PDL")[0] == '1');
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(blocks));
+    cfg.blockDim = dim3(128);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    PNB_CUDA_TRY(cudaLaunchKernelEx(&cfg, pnb_pmatrix_gather_kernel, mp, d_blen, d_node_of_op, site_rate, n_ops, d_P, d_keep));
     PNB_CUDA_TRY(cudaGetLastError());
     return PNB_OK;
 }
