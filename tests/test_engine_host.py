@@ -225,3 +225,57 @@ def test_several_engines_share_one_call_and_stay_pending(world):
     assert not d1.pending and many3[0] == many[0] and many3[1] == many2[1]
     with pytest.raises(ValueError, match="one gene-tree list per engine"):
         E.SeqLikelihoodEngine.log_likelihood_many([e1, e2], [w.trees])
+
+
+def test_network_only_msnc_score_is_the_placement_scan_sum(world):
+    """``network_only_msnc_score`` (the likelihood part of the reference's ``_network_only_log_score``,
+    ``src/_mcmc_seq.py:1163-1214``): sum over loci of the log-sum-exp over the height-scale grid of the density of the
+    scaled gene tree -- one packed device call per candidate network; the pack is reused while the gene-tree OBJECTS,
+    the species and the grid stay the same, and the candidate never touches the engine's own network / cache state."""
+    from phynetpy_b200 import netmoves as NM
+    w = world
+    eng, dev = w.make_engine()
+    theta = 0.02
+    grid = (0.25, 0.5, 1.0, 2.0, 4.0)
+    total0 = eng.log_likelihood(list(w.trees), w.net, theta)
+    felsen0, msnc0 = list(eng._felsen), list(eng._msnc)
+    n_calls = len(w.msnc_calls)
+
+    def want(trees, net):
+        rows = []
+        d = net.to_dict()
+        for t in trees:
+            for s in grid:
+                rows.append(MO.msnc_log_density(d, t.parent.tolist(), (t.blen * s).tolist(), t.label, w.species_of, theta))
+        return NM.network_only_msnc_score(np.asarray(rows), len(grid))
+
+    got = eng.network_only_msnc_score(w.trees, w.net, theta, grid)
+    assert w.msnc_calls[n_calls:] == [w.M * len(grid)]                   # ONE call over loci x scales
+    exp = want(w.trees, w.net)
+    assert (got == exp == -math.inf) or got == pytest.approx(exp, rel=1e-12)
+    pack = eng._scan_pack
+    # a candidate network (heights moved): same gene-tree objects -> the pack is reused
+    cand = None
+    for _ in range(20):
+        out = MV.net_slide_height_move(w.net, w.rng)
+        if out is not None:
+            cand = out[0]
+            break
+    assert cand is not None
+    got2 = eng.network_only_msnc_score(w.trees, cand, theta, grid)
+    assert eng._scan_pack is pack
+    exp2 = want(w.trees, cand)
+    assert (got2 == exp2 == -math.inf) or got2 == pytest.approx(exp2, rel=1e-12)
+    # one gene-tree object replaced -> repacked; a different grid -> repacked
+    trees2 = list(w.trees)
+    trees2[1] = trees2[1].with_lengths(trees2[1].blen * 1.5)
+    got3 = eng.network_only_msnc_score(trees2, w.net, theta, grid)
+    assert eng._scan_pack is not pack
+    exp3 = want(trees2, w.net)
+    assert (got3 == exp3 == -math.inf) or got3 == pytest.approx(exp3, rel=1e-12)
+    pack3 = eng._scan_pack
+    eng.network_only_msnc_score(trees2, w.net, theta, (0.5, 1.0, 2.0))
+    assert eng._scan_pack is not pack3 and w.msnc_calls[-1] == w.M * 3
+    # the engine's own state was never touched
+    assert eng._felsen == felsen0 and eng._msnc == msnc0
+    assert eng.log_likelihood(list(w.trees), w.net, theta) == total0

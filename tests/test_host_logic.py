@@ -178,3 +178,21 @@ def test_public_gtr_family_Q_matches_reference_golden():
     h.set_hyperparams({"kappa": 4.0})
     assert h._decomp is None and not np.allclose(q0, h.getQ())
     assert G.K80(2.0).alpha == pytest.approx(0.5) and G.K80(2.0).beta == pytest.approx(0.25)
+
+
+def test_peer_barrier_args_address_arithmetic():
+    """ShardPlan.peer_barrier_args: the flag array sits behind the `copies` vectors of the symmetric allocation; a rank
+    raises ITS slot in every peer's array and polls its own array at the peers' ranks."""
+    import types
+    from phynetpy_b200.distributed import ShardPlan
+    world, per = 4, 250
+    bases = [0x10000000 * (r + 1) for r in range(world)]
+    hdl = types.SimpleNamespace(buffer_ptrs=bases)
+    for rank in range(world):
+        plan = ShardPlan(world * per, rank, world, [(r * per, (r + 1) * per) for r in range(world)])
+        peer_flags, mine, peers = plan.peer_barrier_args(hdl, copies=2)
+        off = 8 * 2 * per * world
+        assert peers == [r for r in range(world) if r != rank]
+        assert mine == bases[rank] + off
+        assert peer_flags == [bases[r] + off + 8 * rank for r in peers]
+        assert ShardPlan.BARRIER_SLOTS >= world
