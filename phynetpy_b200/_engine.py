@@ -40,6 +40,84 @@ from .tree import FlatTree, flatten
 MsncFn = Callable[[int, Any, Any, float], float]
 
 
+class _SummedList(list):
+    """A per-locus cache list (``_felsen`` / ``_msnc``) that knows its sum.  The reference returns the total as a loop over all
+    loci on every evaluation (``src/_mcmc_seq.py:745-761``); after a single-locus move that loop -- even as two C-level
+    ``sum`` calls -- costs more than everything else the host does for the step (20 of 92 us at 1,000 loci).  Here the sum is
+    kept per block of 32 entries: an item assignment marks its block, ``total()`` re-adds the marked blocks and then the
+    block sums, always in the same order -- so the total is a function of the CONTENT alone (a cached state and a
+    from-scratch evaluation of the same state give the same bits), and a ``None`` written by anybody, through any
+    reference to the list, still raises ``TypeError`` in ``total()`` exactly as ``sum`` would."""
+
+    B = 32
+
+    def __init__(self, values=()):
+        super().__init__(values)
+        self._blocks = [None] * ((len(self) + self.B - 1) // self.B)
+
+    def _all_dirty(self):
+        self._blocks = [None] * ((len(self) + self.B - 1) // self.B)
+
+    def __setitem__(self, i, v):
+        if type(i) is int:
+            list.__setitem__(self, i, v)
+            self._blocks[(i if i >= 0 else i + len(self)) // self.B] = None
+            return
+        n = len(self)
+        list.__setitem__(self, i, v)
+        if isinstance(i, slice) and len(self) == n:     # a run of entries rewritten in place: only its blocks
+            start, stop, step = i.indices(n)
+            if step == 1 and stop > start:
+                for b in range(start // self.B, (stop - 1) // self.B + 1):
+                    self._blocks[b] = None
+                return
+            if stop <= start and step == 1:
+                return
+        elif not isinstance(i, slice):                  # an integer-like index (numpy integer)
+            k = int(i)
+            self._blocks[(k if k >= 0 else k + n) // self.B] = None
+            return
+        self._all_dirty()
+
+    def _mutator(name):   # every other way of changing a list: correct, not fast
+        def f(self, *a, **k):
+            r = getattr(list, name)(self, *a, **k)
+            self._all_dirty()
+            return r
+        f.__name__ = name
+        return f
+
+    for _n in ("__delitem__", "__iadd__", "__imul__", "append", "extend", "insert", "pop", "remove", "clear", "sort", "reverse"):
+        locals()[_n] = _mutator(_n)
+    del _n, _mutator
+
+    def copy(self):
+        c = _SummedList.__new__(_SummedList)
+        list.extend(c, self)                 # C-level copy; the block sums come along
+        c._blocks = self._blocks.copy()
+        return c
+
+    def __reduce__(self):   # pickled (run_parallel_chains) as its content
+        return (_SummedList, (list(self),))
+
+    def total(self):
+        if len(self) <= 2 * self.B:
+            return sum(self)
+        bl, B = self._blocks, self.B
+        for b, v in enumerate(bl):
+            if v is None:
+                bl[b] = sum(self[b * B:(b + 1) * B])    # TypeError when an entry is None, as sum(list) would
+        return sum(bl)
+
+
+def _list_total(values) -> float:
+    return values.total() if type(values) is _SummedList else sum(values)
+
+
+def _copy_cache(values) -> list:
+    return values.copy() if type(values) is _SummedList else _SummedList(values)
+
+
 class SeqLikelihoodEngine:
     """Incremental ``sum_i log P(S_i | g_i) [+ log P(g_i | Psi)]`` over all loci.
 
@@ -72,8 +150,8 @@ class SeqLikelihoodEngine:
         for i in range(lo, hi):
             a = loci[i]
             self._calcs[i] = a if isinstance(a, FelsensteinCalculator) else FelsensteinCalculator(a, context=context)
-        self._felsen: List[Optional[float]] = [None] * self.n_loci
-        self._msnc: List[Optional[float]] = [None] * self.n_loci
+        self._felsen: List[Optional[float]] = _SummedList([None] * self.n_loci)
+        self._msnc: List[Optional[float]] = _SummedList([None] * self.n_loci)
         self._pending: List[int] = []   # loci with an uncommitted device evaluation
         self._dirty: set = set(range(lo, hi))  # local loci whose _felsen entry is None
         self._dirty_any: set = set(range(self.n_loci))   # loci whose entry is None on ANY rank (sharded engines)
@@ -119,12 +197,13 @@ class SeqLikelihoodEngine:
         self._msnc_dirty.add(i)
 
     def invalidate_network(self) -> None:
-        self._msnc = [None] * self.n_loci
+        self._msnc = _SummedList([None] * self.n_loci)
         self._msnc_all = True
         self._msnc_dirty.clear()
 
     def clone_caches(self) -> Tuple[list, list]:
-        snap = (list(self._felsen), list(self._msnc))
+        # (copies that carry their block sums: a restored snapshot does not pay the full sum again)
+        snap = (_copy_cache(self._felsen), _copy_cache(self._msnc))
         if len(self._snap_dirty) > 8:
             self._snap_dirty.clear()
         self._snap_dirty[id(snap[0])] = (snap[0], frozenset(self._dirty), frozenset(self._msnc_dirty), self._msnc_all,
@@ -134,7 +213,7 @@ class SeqLikelihoodEngine:
     def restore_caches(self, snapshot: Tuple[list, list]) -> None:
         """Reject path: scalar caches come back from the snapshot and the device
         discards the partials written by the rejected proposal."""
-        self._felsen, self._msnc = list(snapshot[0]), list(snapshot[1])
+        self._felsen, self._msnc = _copy_cache(snapshot[0]), _copy_cache(snapshot[1])
         known = self._snap_dirty.get(id(snapshot[0]))
         if known is not None and known[0] is snapshot[0]:
             self._dirty = set(known[1])
@@ -381,12 +460,12 @@ class SeqLikelihoodEngine:
     def _total(self, gene_trees: Sequence[Any], species_net: Any, theta: float) -> float:
         """The sum over loci once every ``_felsen`` entry is filled; fills the ``None`` entries of ``_msnc``."""
         if self._msnc_fn is None and species_net is None:
-            total = sum(self._felsen)  # C loop, locus order
+            total = _list_total(self._felsen)
         elif self._msnc_fn is None:
             self._fill_msnc(gene_trees, species_net, theta)
-            # two C-level sums instead of the reference's Python loop over loci (src/_mcmc_seq.py:745-761):
-            # at 10^3 loci that loop costs more than the device work of a single-locus move
-            total = sum(self._felsen) + sum(self._msnc)
+            # blocked sums instead of the reference's Python loop over loci (src/_mcmc_seq.py:745-761): at 10^3 loci that
+            # loop costs more than the device work of a single-locus move (_SummedList)
+            total = _list_total(self._felsen) + _list_total(self._msnc)
         else:
             total = 0.0
             for i in range(self.n_loci):  # reference loop, src/_mcmc_seq.py:745-761

@@ -279,3 +279,42 @@ def test_network_only_msnc_score_is_the_placement_scan_sum(world):
     # the engine's own state was never touched
     assert eng._felsen == felsen0 and eng._msnc == msnc0
     assert eng.log_likelihood(list(w.trees), w.net, theta) == total0
+
+
+def test_summed_list_total_is_a_function_of_the_content():
+    """The cache lists keep block sums: the total after any sequence of writes equals the total of a fresh list with the
+    same content BIT FOR BIT (cached == from-scratch), a None anywhere raises TypeError as sum() would, copies carry
+    their sums, every other list mutation stays correct, and the list pickles as a list."""
+    import pickle
+    rng = np.random.default_rng(3)
+    n = 1000
+    vals = (-rng.random(n) * 1e4).tolist()
+    a = E._SummedList(vals)
+    t0 = a.total()
+    assert t0 == E._SummedList(list(vals)).total()
+    assert abs(t0 - sum(vals)) <= 1e-9 * abs(t0)
+    for _ in range(200):
+        i = int(rng.integers(-n, n))
+        a[i] = float(-rng.random() * 1e4)
+        if rng.random() < 0.3:
+            assert a.total() == E._SummedList(list(a)).total()
+    b = a.copy()
+    assert type(b) is E._SummedList and b == a and b.total() == a.total()
+    b[5] = 1.0
+    assert a[5] != 1.0 and a.total() == E._SummedList(list(a)).total()
+    a[10:20] = [0.5] * 10                       # slice assignment (the engine's contiguous-run path)
+    assert a.total() == E._SummedList(list(a)).total()
+    a[777] = None                               # anybody, through any reference
+    with pytest.raises(TypeError):
+        a.total()
+    a[777] = -2.0
+    a.append(-1.0)
+    a.pop(0)
+    assert a.total() == E._SummedList(list(a)).total()
+    c = pickle.loads(pickle.dumps(a))
+    assert type(c) is E._SummedList and list(c) == list(a) and c.total() == a.total()
+    small = E._SummedList([1.0, 2.0, None])
+    with pytest.raises(TypeError):
+        small.total()
+    assert E._SummedList([-math.inf, 1.0] * 40).total() == -math.inf
+    assert E._list_total([1.0, 2.0]) == 3.0 and type(E._copy_cache([1.0])) is E._SummedList
