@@ -12,6 +12,7 @@
 
 #define PNB_DEVICE_KERNELS
 #include "pnb_host.hpp"
+#include <mutex>
 
 using namespace pnb;
 
@@ -54,6 +55,7 @@ int pnb::launch_pmatrix_gather(const ModelParams& mp, const double* d_blen, cons
 // almost as long as a whole one (its latency is the op walk, not the patterns), and the split changes nothing: it
 // stays off by default.  The results are the same bits either way (tests/test_gpu_parity.py::test_split_tail_same_bits).
 static void split_tail(unsigned n_tiles, size_t dyn_smem, bool fused, bool rescale, int32_t* n_full, unsigned* grid) {
+    static std::mutex mu;    // contexts of several devices / threads may launch at once
     static int slots_cache[4] = {0, 0, 0, 0};
     static size_t smem_cache[4] = {~size_t{0}, ~size_t{0}, ~size_t{0}, ~size_t{0}};
     static int sm_count = 0;
@@ -62,6 +64,7 @@ static void split_tail(unsigned n_tiles, size_t dyn_smem, bool fused, bool resca
     *n_full = static_cast<int32_t>(n_tiles);
     *grid = n_tiles;
     if (!enabled || n_tiles == 0) return;
+    std::lock_guard<std::mutex> lock(mu);
     const int v = (fused ? 2 : 0) + (rescale ? 1 : 0);
     if (smem_cache[v] != dyn_smem) {
         int per_sm = 0;
