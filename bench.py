@@ -869,7 +869,13 @@ def run_chain_block(args, P, ctx, model):
     out["cfg3_full_eval"] = chain_cfg3(args, P, ctx, model)
     out["cfg4_dirty_chain"], out["cfg4_joint_chain"] = chain_cfg4(args, P, ctx, model)
     if not args.no_cpu_baseline:
-        out["reference_mcmc_seq"] = chain_dropin(args)
+        try:
+            out["reference_mcmc_seq"] = chain_dropin(args)
+        except Exception:      # the reference's own sampler is the one leg here that is not our code: say what happened, keep the line
+            import traceback
+            from phynetpy_b200 import dropin
+            dropin.uninstall()
+            out["reference_mcmc_seq"] = {"error": traceback.format_exc()[-1500:]}
     return out
 
 
